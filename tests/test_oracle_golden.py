@@ -1,0 +1,95 @@
+"""The oracle restatement (oracle/chain.py, oracle/bs1770.py) against the golden vectors that
+tests/golden/make_golden.py produced by running the unmodified reference."""
+import numpy as np
+import pytest
+
+from conftest import load_golden, tpdf_noise
+from oracle import chain as oc
+from mm_b200 import synth
+
+CHAIN_CASES = [
+    ("v1_edm_44k", 0, 0.6, 2, "v1", "edm"),
+    ("v1_standard_96k", 1, 0.6, 2, "v1", "standard"),
+    ("v2_standard_48k", 7, 0.75, 2, "v2", "standard"),
+    ("v2_hiphop_44k_mono", 3, 0.75, 1, "v2", "hiphop"),
+    ("v1_podcast_48k", 5, 0.6, 2, "v1", "podcast"),
+    ("v2_house_44k", 11, 0.6, 2, "v2", "house_basic"),
+]
+
+
+@pytest.mark.parametrize("name,track,dur,ch,which,style", CHAIN_CASES)
+def test_chain_matches_reference_golden(name, track, dur, ch, which, style):
+    g = load_golden(name)
+    sr, target = int(g["sr"]), float(g["target"])
+    x = synth.numpy_track(track, sr, dur)
+    x = x if ch == 2 else np.ascontiguousarray(x[:, 0])
+    assert np.array_equal(x, g["input"]), "synthetic generator drifted from the stored golden input"
+    stages = {}
+    out = (oc.run_v1 if which == "v1" else oc.run_v2)(x.copy(), sr, target, style, stages=stages)
+    # float32 samples: the restatement calls the same scipy routines -> expect (near) bit equality
+    assert np.max(np.abs(out.astype(np.float64) - g["out"])) <= 1e-6
+    for k in g:
+        if k.startswith("stage_"):
+            assert np.max(np.abs(stages[k[6:]].astype(np.float64) - g[k])) <= 1e-6, k
+    assert abs(oc.measure_lufs(out, sr) - float(g["lufs_out"])) < 1e-6
+    assert abs(oc.measure_lufs(x, sr) - float(g["lufs_in"])) < 1e-6
+    assert abs(oc.true_peak_dbfs(out) - float(g["true_peak_out"])) < 1e-6
+    noise = tpdf_noise(g["noise_seed"], g["int16"].shape)
+    q = oc.quantize_int16(g["out"].reshape(g["int16"].shape), noise)
+    assert np.array_equal(q, g["int16"])
+
+
+def test_single_stages_match_reference_golden():
+    g = load_golden("stages_noise_48k")
+    sr = int(g["sr"])
+    x = g["input"]
+    loud = (x * np.float32(6.0)).astype(np.float32)
+    got = {
+        "dc": oc.remove_dc_offset(x + np.float32(0.01)),
+        "peak_guard_loud": oc.remove_intersample_peaks(loud, 0.5),
+        "target_curve": oc.apply_target_curve(x, sr),
+        "target_curve_ms": oc.apply_target_curve(x, sr, eq_ms=True),
+        "deesser_loud": oc.apply_deesser(loud, sr),
+        "dynamics_v1": oc.apply_dynamics(loud, sr),
+        "dynamics_v2": oc.apply_dynamics(loud, sr, crossovers_hz=(214.0, 2230.0, 10000.0)),
+        "dynamics_upward": oc.apply_dynamics(x, sr, band_ratios=(0.8, 2.0, 1.0, 0.6)),
+        "parallel": oc.apply_parallel_compression(loud, sr, mix=0.3),
+        "normalize": oc.normalize_lufs(x, sr, -14.0),
+        "final_balance": oc.apply_final_spectral_balance(x, sr),
+        "style_eq_edm": oc.apply_style_eq(x, sr, "edm"),
+        "style_eq_classical": oc.apply_style_eq(x, sr, "classical"),
+        "exciter": oc.apply_harmonic_exciter(loud, sr, 0.8),
+        "imager": oc.apply_stereo_imager(x, 1.3),
+        "fade": oc.apply_output_edge_fade_in(x, sr, 6.0),
+        "maximizer": oc.apply_maximizer(loud),
+    }
+    for k, v in got.items():
+        err = np.max(np.abs(np.asarray(v, dtype=np.float64) - g[k]))
+        assert err <= 2e-7, (k, err)
+
+
+def test_analyzers_match_reference_golden():
+    g = load_golden("analyzers")
+    for tag in "abc":
+        x, sr = g[f"{tag}_input"], int(g[f"{tag}_sr"])
+        assert abs(oc.measure_lufs(x, sr) - float(g[f"{tag}_lufs"])) < 1e-9
+        assert abs(oc.measure_lufs(np.ascontiguousarray(x[:, 0]), sr) - float(g[f"{tag}_lufs_mono"])) < 1e-9
+        assert abs(oc.true_peak_dbfs(x) - float(g[f"{tag}_true_peak"])) < 1e-9
+        assert abs(oc.true_peak_explicit(x) - float(g[f"{tag}_true_peak"])) < 1e-9
+        assert np.allclose(oc.compute_spectrum_bars(x, sr), g[f"{tag}_bars"], atol=1e-9)
+        assert np.allclose(oc.compute_spectrum_bars((x[:, 0] + x[:, 1]) * 0.5, sr), g[f"{tag}_bars_mid"], atol=1e-9)
+        assert abs(oc.measure_stereo_correlation(x) - float(g[f"{tag}_corr"])) < 1e-12
+        tl, step = oc.compute_lufs_timeline(x, sr)
+        ref_tl = g[f"{tag}_timeline"]
+        assert len(tl) == len(ref_tl) and step == float(g[f"{tag}_timeline_step"])
+        for a, b in zip(tl, ref_tl):
+            assert (a is None and np.isnan(b)) or abs(a - b) < 1e-9
+        assert np.allclose(np.array(oc.compute_vectorscope_points(x)), g[f"{tag}_vscope"])
+
+
+def test_filtfilt_explicit_is_scipy_filtfilt():
+    from scipy import signal as sg
+    rng = np.random.default_rng(5)
+    x = rng.standard_normal(5000)
+    for b, a in (sg.butter(2, 40 / 22050, "high"), sg.butter(1, [0.1, 0.2], "band"), sg.butter(2, [0.22, 0.41], "band")):
+        assert np.max(np.abs(oc.filtfilt_explicit(b, a, x) - sg.filtfilt(b, a, x))) < 1e-12
