@@ -1,0 +1,732 @@
+// C ABI (include/mm_b200.h): context management, stage entry points, whole chains, host-buffer
+// drop-in.  Every entry point names the reference function it replaces in the header.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+#include "context.h"
+#include "pw_args.h"
+#include "stages_internal.h"
+
+namespace mm {
+const char* get_error();
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) {
+        cudaGetDevice(&prev);
+        if (prev != dev) cudaSetDevice(dev);
+        else prev = -1;
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+// ---- per-track stats assembly ---------------------------------------------------------------------
+struct StatsArgs {
+    mm_track_stats* out;
+    int tracks, channels;
+    const double *lufs_in, *lufs_mid, *lufs_out, *gain_db, *peak_in, *peak_out, *mean_row, *nonfinite;
+};
+__global__ void stats_kernel(const StatsArgs P) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= P.tracks) return;
+    const double nan = __longlong_as_double(0x7ff8000000000000LL);
+    mm_track_stats s;
+    s.lufs_in = P.lufs_in ? P.lufs_in[t] : nan;
+    s.lufs_mid = P.lufs_mid ? P.lufs_mid[t] : nan;
+    s.lufs_out = P.lufs_out ? P.lufs_out[t] : nan;
+    s.gain_db = P.gain_db ? P.gain_db[t] : nan;
+    s.peak_in = P.peak_in ? P.peak_in[t] : nan;
+    s.peak_out = P.peak_out ? P.peak_out[t] : nan;
+    s.mean[0] = P.mean_row ? P.mean_row[t * P.channels] : nan;
+    s.mean[1] = P.mean_row ? P.mean_row[t * P.channels + (P.channels > 1)] : nan;
+    s.nonfinite = P.nonfinite ? P.nonfinite[t] : 0.0;
+    P.out[t] = s;
+}
+
+static void set_identity_dyn(DynParams* d) { memset(d, 0, sizeof(*d)); }
+
+static int pw_base(PwArgs* A, const float* in, float* out, int mode) {
+    memset(A, 0, sizeof(*A));
+    A->in = in;
+    A->out = out;
+    A->mode = mode;
+    set_identity_dyn(&A->dyn);
+    return 0;
+}
+
+static inline size_t batch_floats(const mm_geom* g) { return (size_t)g->tracks * g->channels * (size_t)g->stride; }
+
+static int fade_len(const mm_geom* g, double fade_ms) {
+    // apply_output_edge_fade_in (backend/app/pipeline.py:152-167)
+    if (fade_ms <= 0 || g->sr <= 0) return 0;
+    long long nf = (long long)std::nearbyint((double)g->sr * (fade_ms / 1000.0));
+    nf = std::max<long long>(2, std::min<long long>(nf, (long long)((double)g->sr * 0.1)));
+    return (int)std::min<long long>(nf, g->n);
+}
+
+static int upload_doubles(mm_ctx* c, int slot, const double* host, size_t count, double** dev) {
+    MM_TRY(arena(c, slot, count, dev));
+    // small parameter vectors: synchronous copy from a host temporary is fine (KBs)
+    MM_CUDA(cudaMemcpyAsync(*dev, host, count * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    MM_CUDA(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// whole chains
+// ---------------------------------------------------------------------------------------------------
+struct StyleSig {
+    double eq[5], exciter_db, width, par_mix;
+    bool operator==(const StyleSig& o) const { return memcmp(this, &o, sizeof(StyleSig)) == 0; }
+};
+
+static int master_impl(mm_ctx* c, const mm_geom* g, int chain, const mm_style* styles, const float* in, float* out,
+                       int16_t* pcm, const float* noise, uint64_t seed, mm_track_stats* stats_dev, uint32_t flags) {
+    MM_TRY(check_geom(g));
+    if (chain != MM_CHAIN_V1 && chain != MM_CHAIN_V2) { set_error("unknown chain id %d", chain); return 1; }
+    if (!styles || !in || !out) { set_error("mm_dev_master: styles, in and out are required"); return 1; }
+    const int T = g->tracks, C = g->channels, rows = T * C;
+    const bool v1 = chain == MM_CHAIN_V1;
+
+    // per-track parameter vectors
+    std::vector<double> h_target(T), h_width(T), h_parmix(rows);
+    std::vector<StyleSig> sig(T);
+    for (int t = 0; t < T; ++t) {
+        const mm_style& s = styles[t];
+        h_target[t] = s.target_lufs;
+        memset(&sig[t], 0, sizeof(StyleSig));
+        for (int b = 0; b < 5; ++b) sig[t].eq[b] = s.eq_gain_db[b];
+        // gates: v1 pipeline.py:1889 (exciter_db > 0.05), :1894 (|w - 1| > 0.01), :1856 (mix > 0.01);
+        //        v2 chain.py:120-121 (enabled flags |db| >= 0.05, |w - 1| >= 0.01)
+        const bool exc = v1 ? (s.exciter_db > 0.05) : (std::fabs(s.exciter_db) >= 0.05);
+        const bool img = C == 2 && (v1 ? (std::fabs(s.imager_width - 1.0) > 0.01) : (std::fabs(s.imager_width - 1.0) >= 0.01));
+        const bool par = v1 && s.parallel_mix > 0.01;
+        sig[t].exciter_db = exc ? s.exciter_db : 0.0;
+        sig[t].width = img ? s.imager_width : 1.0;
+        sig[t].par_mix = par ? std::min(std::max(s.parallel_mix, 0.0), 1.0) : 0.0;
+        h_width[t] = sig[t].width;
+        for (int ch = 0; ch < C; ++ch) h_parmix[t * C + ch] = sig[t].par_mix;
+    }
+    bool any_par = false, any_img = false;
+    for (int t = 0; t < T; ++t) { any_par |= sig[t].par_mix >= 0.01; any_img |= sig[t].width != 1.0; }
+
+    double *d_target, *d_width, *d_parmix = nullptr;
+    MM_TRY(upload_doubles(c, SL_TARGET, h_target.data(), T, &d_target));
+    MM_TRY(upload_doubles(c, SL_WIDTH, h_width.data(), T, &d_width));
+    if (any_par) MM_TRY(upload_doubles(c, SL_PARMIX, h_parmix.data(), rows, &d_parmix));
+
+    double *d_sub, *d_mul, *d_gain, *d_mulout, *d_lufs_mid, *d_gaindb, *d_peakin, *d_peakout, *d_mean, *d_nonfinite;
+    double *d_lufs_in = nullptr, *d_lufs_out = nullptr;
+    float* d_peakbits;
+    MM_TRY(arena(c, SL_SUB, (size_t)rows, &d_sub));
+    MM_TRY(arena(c, SL_MUL, (size_t)rows, &d_mul));
+    MM_TRY(arena(c, SL_GAIN, (size_t)rows, &d_gain));
+    MM_TRY(arena(c, SL_MUL_OUT, (size_t)rows, &d_mulout));
+    MM_TRY(arena(c, SL_LUFS, (size_t)T, &d_lufs_mid));
+    MM_TRY(arena(c, SL_GAINDB, (size_t)T, &d_gaindb));
+    MM_TRY(arena(c, SL_PEAKIN, (size_t)T, &d_peakin));
+    MM_TRY(arena(c, SL_MISC, (size_t)T, &d_peakout));
+    MM_TRY(arena(c, SL_MEAN, (size_t)rows, &d_mean));
+    MM_TRY(arena(c, SL_NONFINITE, (size_t)T, &d_nonfinite));
+    MM_TRY(arena(c, SL_PEAKBITS, (size_t)T, &d_peakbits));
+    MM_CUDA(cudaMemsetAsync(d_nonfinite, 0, (size_t)T * sizeof(double), c->stream));
+
+    // 1. remove_dc_offset + remove_intersample_peaks(0.5): one statistics read; the affine map rides
+    //    as the prologue of the first sweeps (pipeline.py:134-149, :1833-1837; chain.py:112-113)
+    RowStats* st;
+    MM_TRY(run_row_stats(c, g, in, &st));
+    MM_TRY(run_in_scalars(c, g, st, 1, 1, 0.5, d_sub, d_mul, d_peakin, d_mean));
+    Pro pin;
+    pin.mode = PRO_SUBMUL_F32;
+    pin.sub = d_sub;
+    pin.mul = d_mul;
+    if (flags & MM_FLAG_MEASURE_IN) {
+        MM_TRY(arena(c, SL_LUFS2, (size_t)T, &d_lufs_in));
+        Pro none;
+        MM_TRY(st_lufs(c, g, in, none, d_lufs_in, nullptr, nullptr, nullptr));
+    }
+    // 2. apply_target_curve (pipeline.py:1841 / chain.py:114)
+    MM_TRY(st_target_curve(c, g, in, out, pin));
+    // 3. v1 only: apply_deesser (pipeline.py:1845)
+    if (v1) MM_TRY(st_deesser(c, g, out, out, -6.0, 3.0, 5000.0, 9000.0, 4.0, 85.0));
+    // 4. apply_dynamics (+ style-driven parallel compression in v1, pipeline.py:1850-1858)
+    {
+        const double v2x[3] = {214.0, 2230.0, 10000.0};   // chain.py:116
+        MM_TRY(st_dynamics(c, g, out, out, 6.0, v1 ? nullptr : v2x, nullptr, 12.0, any_par ? d_parmix : nullptr, nullptr));
+    }
+    // 5. normalize_lufs: measure, derive the gain; the multiply rides as the next prologue
+    Pro none;
+    MM_TRY(st_lufs(c, g, out, none, d_lufs_mid, d_target, d_gain, d_gaindb));
+    Pro pgain;
+    pgain.mode = PRO_MUL_F64;
+    pgain.mul = d_gain;
+    // 6. apply_final_spectral_balance; the output peak is tracked by the last epilogue that touches
+    //    a track's samples
+    MM_CUDA(cudaMemsetAsync(d_peakbits, 0, (size_t)T * sizeof(float), c->stream));
+    MM_TRY(st_final_balance(c, g, out, out, pgain, d_peakbits));
+    // 7./8. apply_style_eq, apply_harmonic_exciter on runs of tracks that share a style signature
+    for (int t0 = 0; t0 < T;) {
+        int t1 = t0 + 1;
+        while (t1 < T && sig[t1] == sig[t0]) ++t1;
+        mm_geom sub = *g;
+        sub.tracks = t1 - t0;
+        float* base = out + (size_t)t0 * C * (size_t)g->stride;
+        float* pk = d_peakbits + t0;
+        bool fires = false;
+        for (int b = 0; b < 5; ++b) fires |= std::fabs(sig[t0].eq[b]) >= 0.05;
+        fires |= sig[t0].exciter_db != 0.0;
+        if (fires) {
+            int fired = 0;
+            // a later stage re-tracks the peak from scratch for these tracks
+            MM_TRY(st_style_eq(c, &sub, base, base, sig[t0].eq, pk, &fired, /*reset_peak=*/1));
+            if (sig[t0].exciter_db != 0.0) {
+                MM_CUDA(cudaMemsetAsync(pk, 0, (size_t)sub.tracks * sizeof(float), c->stream));
+                MM_TRY(st_exciter(c, &sub, base, base, sig[t0].exciter_db, 0, pk));
+            }
+        }
+        t0 = t1;
+    }
+    // 9. apply_stereo_imager: folded into the final pass; tracks with an active imager need their
+    //    post-imager peak first (read-only pass over those runs)
+    if (any_img) {
+        for (int t0 = 0; t0 < T;) {
+            int t1 = t0 + 1;
+            const bool on = sig[t0].width != 1.0;
+            while (t1 < T && (sig[t1].width != 1.0) == on) ++t1;
+            if (on) {
+                mm_geom sub = *g;
+                sub.tracks = t1 - t0;
+                MM_CUDA(cudaMemsetAsync(d_peakbits + t0, 0, (size_t)sub.tracks * sizeof(float), c->stream));
+                PwArgs A;
+                pw_base(&A, out + (size_t)t0 * C * (size_t)g->stride, nullptr, PW_PEAK);
+                A.width = d_width + t0;
+                A.peak = d_peakbits + t0;
+                MM_TRY(run_pointwise(c, &sub, A, "peak_after_imager"));
+            }
+            t0 = t1;
+        }
+    }
+    // 10. remove_intersample_peaks(0.5) + clip/nan_to_num + 6 ms fade-in (+ TPDF dither to int16)
+    {
+        OutScalarArgs O;
+        O.peak_bits = d_peakbits; O.tracks = T; O.channels = C;
+        O.limit = (float)std::pow(10.0, -0.5 / 20.0);
+        O.mul = d_mulout; O.peak_track = d_peakout;
+        MM_TRY(run_out_scalars(c, O));
+        PwArgs A;
+        pw_base(&A, out, out, PW_FINALIZE);
+        A.mul = d_mulout;
+        A.width = any_img ? d_width : nullptr;
+        const bool fade = v1 || !(flags & MM_FLAG_NO_JOB_FADE);
+        A.n_fade = fade ? fade_len(g, 6.0) : 0;
+        A.fade_step = A.n_fade > 1 ? 1.0 / (double)(A.n_fade - 1) : 0.0;
+        A.pcm = pcm;
+        A.noise = noise;
+        A.seed = seed;
+        A.nonfinite = d_nonfinite;
+        MM_TRY(run_pointwise(c, g, A, pcm ? "finalize_dither_int16" : "finalize"));
+    }
+    if (flags & MM_FLAG_MEASURE_OUT) {
+        MM_TRY(arena(c, SL_LUFS3, (size_t)T, &d_lufs_out));
+        MM_TRY(st_lufs(c, g, out, none, d_lufs_out, nullptr, nullptr, nullptr));
+    }
+    if (stats_dev) {
+        StatsArgs S;
+        S.out = stats_dev; S.tracks = T; S.channels = C;
+        S.lufs_in = d_lufs_in; S.lufs_mid = d_lufs_mid; S.lufs_out = d_lufs_out; S.gain_db = d_gaindb;
+        S.peak_in = d_peakin; S.peak_out = d_peakout; S.mean_row = d_mean; S.nonfinite = d_nonfinite;
+        KernelScope ks(c, "track_stats");
+        stats_kernel<<<(T + 127) / 128, 128, 0, c->stream>>>(S);
+        MM_CUDA(cudaGetLastError());
+    }
+    return 0;
+}
+
+}  // namespace mm
+
+using namespace mm;
+
+#define MM_API_BEGIN(ctx)                                   \
+    if (!(ctx)) { mm::set_error("null context"); return 1; } \
+    mm::DeviceGuard _guard((ctx)->device);
+
+extern "C" {
+
+int mm_abi_version(void) { return MM_ABI_VERSION; }
+const char* mm_last_error(void) { return mm::get_error(); }
+
+int64_t mm_row_stride(int64_t n) {
+    if (n < 0) n = 0;
+    return ((int64_t)kLead + n + 32 + 31) & ~(int64_t)31;
+}
+
+int mm_ctx_create(int device, void* stream, mm_ctx** out) {
+    if (!out) { set_error("mm_ctx_create: out is null"); return 1; }
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count <= 0) {
+        set_error("no CUDA device available (%s); this library has no CPU fallback", cudaGetErrorString(e));
+        return 1;
+    }
+    if (device < 0 || device >= count) { set_error("device %d out of range (%d devices)", device, count); return 1; }
+    MM_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    MM_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) { set_error("device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor); return 1; }
+    mm_ctx* c = new mm_ctx();
+    c->device = device;
+    if (stream) {
+        c->stream = (cudaStream_t)stream;
+        c->own_stream = false;
+    } else {
+        if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; set_error("cudaStreamCreate failed"); return 1; }
+        c->own_stream = true;
+    }
+    if (cudaMalloc(&c->ticket, sizeof(unsigned)) != cudaSuccess || cudaMalloc(&c->err, sizeof(int)) != cudaSuccess) {
+        delete c; set_error("cudaMalloc(context scalars) failed"); return 1;
+    }
+    cudaMemsetAsync(c->ticket, 0, sizeof(unsigned), c->stream);
+    cudaMemsetAsync(c->err, 0, sizeof(int), c->stream);
+    if (cudaStreamSynchronize(c->stream) != cudaSuccess) { delete c; set_error("context initialisation failed"); return 1; }
+    *out = c;
+    return 0;
+}
+
+void mm_ctx_destroy(mm_ctx* c) {
+    if (!c) return;
+    DeviceGuard guard(c->device);
+    cudaStreamSynchronize(c->stream);
+    for (int i = 0; i < SL_COUNT; ++i) if (c->slots[i].p) cudaFree(c->slots[i].p);
+    for (auto& kv : c->plans) if (kv.second.dev) cudaFree(kv.second.dev);
+    for (auto& kv : c->lufs_plans) {
+        cudaFree(kv.second.bnd); cudaFree(kv.second.tile_seg); cudaFree(kv.second.blk_lo); cudaFree(kv.second.blk_hi);
+    }
+    for (auto& k : c->ktimes) { cudaEventDestroy(k.a); cudaEventDestroy(k.b); }
+    if (c->agg) cudaFree(c->agg);
+    if (c->flag) cudaFree(c->flag);
+    if (c->ticket) cudaFree(c->ticket);
+    if (c->err) cudaFree(c->err);
+    if (c->own_stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+int mm_ctx_sync(mm_ctx* c) {
+    MM_API_BEGIN(c);
+    MM_CUDA(cudaStreamSynchronize(c->stream));
+    int err = 0;
+    MM_CUDA(cudaMemcpy(&err, c->err, sizeof(int), cudaMemcpyDeviceToHost));
+    if (err != 0) {
+        cudaMemset(c->err, 0, sizeof(int));
+        set_error("scan look-back timed out waiting for a predecessor tile (device error flag %d)", err);
+        return 1;
+    }
+    return 0;
+}
+
+int64_t mm_ctx_launch_count(mm_ctx* c) { return c ? c->launches : 0; }
+
+int mm_ctx_timing(mm_ctx* c, int enable) {
+    MM_API_BEGIN(c);
+    MM_CUDA(cudaStreamSynchronize(c->stream));
+    for (auto& k : c->ktimes) { cudaEventDestroy(k.a); cudaEventDestroy(k.b); }
+    c->ktimes.clear();
+    c->kacc.clear();
+    c->timing = enable != 0;
+    return 0;
+}
+
+int mm_ctx_kernel_times(mm_ctx* c, mm_ktime* out, int cap, int* count) {
+    MM_API_BEGIN(c);
+    MM_CUDA(cudaStreamSynchronize(c->stream));
+    for (auto& k : c->ktimes) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, k.a, k.b) == cudaSuccess) {
+            auto& acc = c->kacc[k.name];
+            acc.first += (double)ms;
+            acc.second += 1;
+        }
+        cudaEventDestroy(k.a);
+        cudaEventDestroy(k.b);
+    }
+    c->ktimes.clear();
+    int i = 0;
+    for (auto& kv : c->kacc) {
+        if (i < cap && out) {
+            memset(&out[i], 0, sizeof(mm_ktime));
+            strncpy(out[i].name, kv.first.c_str(), sizeof(out[i].name) - 1);
+            out[i].ms = kv.second.first;
+            out[i].launches = kv.second.second;
+        }
+        ++i;
+    }
+    if (count) *count = i;
+    return 0;
+}
+
+int64_t mm_ctx_workspace_bytes(mm_ctx* c) { return c ? c->workspace_bytes : 0; }
+
+int64_t mm_master_workspace_bytes(const mm_geom* g, int chain) {
+    if (!g) return 0;
+    const int64_t buf = (int64_t)g->tracks * g->channels * g->stride * 4;
+    const int64_t ntiles = (g->n + 64 + kL) / kL + 1;
+    const int64_t carry = (int64_t)4 * g->tracks * g->channels * ntiles * (kMaxOrder * 8 + 4) * 5 / 4;
+    return buf * (chain == MM_CHAIN_V1 ? 9 : 9) + carry + (1 << 20);
+}
+
+// ---- pinned host memory for the host-buffer entry points ----------------------------------------
+int mm_host_alloc(void** out, int64_t bytes) {
+    if (!out || bytes <= 0) { set_error("mm_host_alloc: bad arguments"); return 1; }
+    MM_CUDA(cudaMallocHost(out, (size_t)bytes));
+    return 0;
+}
+int mm_host_free(void* p) {
+    if (p) MM_CUDA(cudaFreeHost(p));
+    return 0;
+}
+
+// ---- layout helpers ---------------------------------------------------------------------------
+int mm_dev_deinterleave(mm_ctx* c, const mm_geom* g, const float* il, float* pl) {
+    MM_API_BEGIN(c);
+    MM_TRY(check_geom(g));
+    return run_layout(c, g, il, pl, 0);
+}
+int mm_dev_interleave(mm_ctx* c, const mm_geom* g, const float* pl, float* il) {
+    MM_API_BEGIN(c);
+    MM_TRY(check_geom(g));
+    return run_layout(c, g, il, const_cast<float*>(pl), 1);
+}
+
+// ---- stage functions ----------------------------------------------------------------------------
+int mm_dev_remove_dc_offset(mm_ctx* c, const mm_geom* g, const float* in, float* out) {
+    MM_API_BEGIN(c);
+    MM_TRY(check_geom(g));
+    const int rows = g->tracks * g->channels;
+    double *sub, *mul;
+    MM_TRY(arena(c, SL_SUB, (size_t)rows, &sub));
+    MM_TRY(arena(c, SL_MUL, (size_t)rows, &mul));
+    RowStats* st;
+    MM_TRY(run_row_stats(c, g, in, &st));
+    MM_TRY(run_in_scalars(c, g, st, 1, 0, 0.0, sub, mul, nullptr, nullptr));
+    PwArgs A;
+    pw_base(&A, in, out, PW_AFFINE);
+    A.sub = sub;
+    A.mul = mul;
+    return run_pointwise(c, g, A, "remove_dc_offset");
+}
+
+int mm_dev_remove_intersample_peaks(mm_ctx* c, const mm_geom* g, const float* in, float* out, double headroom_db) {
+    MM_API_BEGIN(c);
+    MM_TRY(check_geom(g));
+    const int rows = g->tracks * g->channels;
+    double *sub, *mul;
+    MM_TRY(arena(c, SL_SUB, (size_t)rows, &sub));
+    MM_TRY(arena(c, SL_MUL, (size_t)rows, &mul));
+    RowStats* st;
+    MM_TRY(run_row_stats(c, g, in, &st));
+    MM_TRY(run_in_scalars(c, g, st, 0, 1, headroom_db, sub, mul, nullptr, nullptr));
+    PwArgs A;
+    pw_base(&A, in, out, PW_AFFINE);
+    A.sub = sub;
+    A.mul = mul;
+    A.clip = 1;
+    return run_pointwise(c, g, A, "remove_intersample_peaks");
+}
+
+int mm_dev_fade_in(mm_ctx* c, const mm_geom* g, const float* in, float* out, double fade_ms) {
+    MM_API_BEGIN(c);
+    MM_TRY(check_geom(g));
+    PwArgs A;
+    pw_base(&A, in, out, PW_FADE);
+    A.n_fade = fade_len(g, fade_ms);
+    A.fade_step = A.n_fade > 1 ? 1.0 / (double)(A.n_fade - 1) : 0.0;
+    return run_pointwise(c, g, A, "fade_in");
+}
+
+int mm_dev_apply_target_curve(mm_ctx* c, const mm_geom* g, const float* in, float* out, int eq_ms) {
+    MM_API_BEGIN(c);
+    MM_TRY(check_geom(g));
+    if (eq_ms && g->channels == 2) {
+        // pipeline.py:248-255: EQ on mid/side, then decode and clip
+        Bufs B;
+        MM_TRY(get_bufs(c, g, &B));
+        float* ms = B.T[1];
+        PwArgs A;
+        pw_base(&A, in, ms, PW_MS_ENCODE);
+        MM_TRY(run_pointwise(c, g, A, "ms_encode"));
+        Pro none;
+        MM_TRY(st_target_curve(c, g, ms, ms, none));
+        PwArgs D;
+        pw_base(&D, ms, out, PW_MS_DECODE);
+        return run_pointwise(c, g, D, "ms_decode_clip");
+    }
+    Pro none;
+    return st_target_curve(c, g, in, out, none);
+}
+
+int mm_dev_apply_deesser(mm_ctx* c, const mm_geom* g, const float* in, float* out, double threshold_db, double ratio,
+                         double freq_lo, double freq_hi, double attack_ms, double release_ms) {
+    MM_API_BEGIN(c);
+    MM_TRY(check_geom(g));
+    return st_deesser(c, g, in, out, threshold_db, ratio, freq_lo, freq_hi, attack_ms, release_ms);
+}
+
+int mm_dev_apply_dynamics(mm_ctx* c, const mm_geom* g, const float* in, float* out, double knee_db, const double* crossovers_hz,
+                          const double* band_ratios, double max_upward_boost_db) {
+    MM_API_BEGIN(c);
+    MM_TRY(check_geom(g));
+    return st_dynamics(c, g, in, out, knee_db, crossovers_hz, band_ratios, max_upward_boost_db, nullptr, nullptr);
+}
+
+int mm_dev_apply_maximizer(mm_ctx* c, const mm_geom* g, const float* in, float* out) {
+    MM_API_BEGIN(c);
+    MM_TRY(check_geom(g));
+    PwArgs A;
+    pw_base(&A, in, out, PW_MAXIMIZER);
+    fill_dyn(&A.dyn, 6.0, nullptr, 12.0);
+    A.dyn.tp_lim = 3.0e38f;   // maximizer alone: no limiter behind it
+    return run_pointwise(c, g, A, "apply_maximizer");
+}
+
+int mm_dev_apply_parallel_compression(mm_ctx* c, const mm_geom* g, const float* in, float* out, double mix, double ratio,
+                                      double threshold_db) {
+    MM_API_BEGIN(c);
+    MM_TRY(check_geom(g));
+    mix = std::min(std::max(mix, 0.0), 1.0);
+    if (mix < 0.01) {   // pipeline.py:1787-1788: unchanged
+        if (in != out) MM_CUDA(cudaMemcpyAsync(out, in, batch_floats(g) * sizeof(float), cudaMemcpyDeviceToDevice, c->stream));
+        return 0;
+    }
+    PwArgs A;
+    pw_base(&A, in, out, PW_PARALLEL);
+    fill_dyn(&A.dyn, 6.0, nullptr, 12.0);
+    fill_parallel(&A.dyn, ratio, threshold_db);
+    A.par_mix = mix;
+    return run_pointwise(c, g, A, "apply_parallel_compression");
+}
+
+int mm_dev_measure_lufs(mm_ctx* c, const mm_geom* g, const float* in, double* lufs_dev) {
+    MM_API_BEGIN(c);
+    MM_TRY(check_geom(g));
+    Pro none;
+    return st_lufs(c, g, in, none, lufs_dev, nullptr, nullptr, nullptr);
+}
+
+int mm_dev_normalize_lufs(mm_ctx* c, const mm_geom* g, const float* in, float* out, const double* target_lufs_host) {
+    MM_API_BEGIN(c);
+    MM_TRY(check_geom(g));
+    const int rows = g->tracks * g->channels;
+    double *target, *gain, *lufs, *gdb;
+    MM_TRY(upload_doubles(c, SL_TARGET, target_lufs_host, (size_t)g->tracks, &target));
+    MM_TRY(arena(c, SL_GAIN, (size_t)rows, &gain));
+    MM_TRY(arena(c, SL_LUFS, (size_t)g->tracks, &lufs));
+    MM_TRY(arena(c, SL_GAINDB, (size_t)g->tracks, &gdb));
+    Pro none;
+    MM_TRY(st_lufs(c, g, in, none, lufs, target, gain, gdb));
+    PwArgs A;
+    pw_base(&A, in, out, PW_GAIN_F64);
+    A.mul = gain;
+    return run_pointwise(c, g, A, "normalize_lufs_gain");
+}
+
+int mm_dev_apply_final_spectral_balance(mm_ctx* c, const mm_geom* g, const float* in, float* out) {
+    MM_API_BEGIN(c);
+    MM_TRY(check_geom(g));
+    Pro none;
+    return st_final_balance(c, g, in, out, none, nullptr);
+}
+
+int mm_dev_apply_style_eq(mm_ctx* c, const mm_geom* g, const float* in, float* out, const double* eq_gain_db) {
+    MM_API_BEGIN(c);
+    MM_TRY(check_geom(g));
+    return st_style_eq(c, g, in, out, eq_gain_db, nullptr, nullptr, 0);
+}
+
+int mm_dev_apply_harmonic_exciter(mm_ctx* c, const mm_geom* g, const float* in, float* out, double exciter_db, int mode) {
+    MM_API_BEGIN(c);
+    MM_TRY(check_geom(g));
+    if (std::fabs(exciter_db) < 0.05) {   // pipeline.py:1282-1283
+        if (in != out) MM_CUDA(cudaMemcpyAsync(out, in, batch_floats(g) * sizeof(float), cudaMemcpyDeviceToDevice, c->stream));
+        return 0;
+    }
+    return st_exciter(c, g, in, out, exciter_db, mode, nullptr);
+}
+
+int mm_dev_apply_stereo_imager(mm_ctx* c, const mm_geom* g, const float* in, float* out, double width) {
+    MM_API_BEGIN(c);
+    MM_TRY(check_geom(g));
+    if (g->channels != 2) {   // pipeline.py:1355-1356
+        if (in != out) MM_CUDA(cudaMemcpyAsync(out, in, batch_floats(g) * sizeof(float), cudaMemcpyDeviceToDevice, c->stream));
+        return 0;
+    }
+    std::vector<double> w((size_t)g->tracks, width);
+    double* dw;
+    MM_TRY(upload_doubles(c, SL_WIDTH, w.data(), w.size(), &dw));
+    PwArgs A;
+    pw_base(&A, in, out, PW_IMAGER);
+    A.width = dw;
+    A.force_imager = 1;
+    return run_pointwise(c, g, A, "apply_stereo_imager");
+}
+
+int mm_dev_apply_rumble_filter(mm_ctx* c, const mm_geom* g, const float* in, float* out, double cutoff_hz) {
+    MM_API_BEGIN(c);
+    MM_TRY(check_geom(g));
+    // pipeline.py:1449-1469: butter(2, clip(cutoff,20,300)/nyq <= 0.99, 'high') through filtfilt
+    const double nyq = g->sr / 2.0;
+    const double fc = std::min(std::max(cutoff_hz, 20.0), 300.0);
+    const FilterPlan* p = plan_butter(c, 2, kHigh, std::min(fc / nyq, 0.99), 0);
+    if (!p) return 1;
+    Epi e;
+    Pro none;
+    return st_filtfilt_combine(c, g, p, in, out, e, none);
+}
+
+int mm_dev_iir(mm_ctx* c, const mm_geom* g, const float* in, float* out, const double* b, const double* a, int ncoef,
+               int zero_phase) {
+    MM_API_BEGIN(c);
+    MM_TRY(check_geom(g));
+    if ((ncoef != 3 && ncoef != 5) || !b || !a || a[0] == 0.0) { set_error("mm_dev_iir: ncoef must be 3 or 5 and a[0] != 0"); return 1; }
+    Ba ba;
+    memset(&ba, 0, sizeof(ba));
+    ba.m = ncoef - 1;
+    for (int i = 0; i < ncoef; ++i) { ba.b[i] = b[i] / a[0]; ba.a[i] = a[i] / a[0]; }
+    const FilterPlan* p = get_plan(c, ba);
+    if (!p) return 1;
+    Epi e;
+    Pro none;
+    if (zero_phase) return st_filtfilt_combine(c, g, p, in, out, e, none);
+    const FilterPlan* pl[1] = {p};
+    const float* i1[1] = {in};
+    float* o1[1] = {out};
+    if (in == out) {   // the causal sweep reads its odd... no extension here, but tiles must not race: go through E0
+        Bufs B;
+        MM_TRY(get_bufs(c, g, &B));
+        o1[0] = B.E[0];
+        MM_TRY(sweep_fwd(c, g, 1, 1, pl, i1, o1, none, 0));
+        MM_CUDA(cudaMemcpyAsync(out, B.E[0], batch_floats(g) * sizeof(float), cudaMemcpyDeviceToDevice, c->stream));
+        return 0;
+    }
+    return sweep_fwd(c, g, 1, 1, pl, i1, o1, none, 0);
+}
+
+// ---- export -------------------------------------------------------------------------------------
+int mm_dev_quantize_int16(mm_ctx* c, const mm_geom* g, const float* in, int16_t* pcm, const float* noise, uint64_t seed) {
+    MM_API_BEGIN(c);
+    MM_TRY(check_geom(g));
+    QuantArgs Q;
+    Q.in = in; Q.n = g->n; Q.stride = g->stride; Q.tracks = g->tracks; Q.channels = g->channels;
+    Q.pcm = pcm; Q.noise = noise; Q.seed = seed;
+    return run_quantize(c, Q);
+}
+
+// ---- analyzers ----------------------------------------------------------------------------------
+int mm_dev_true_peak(mm_ctx* c, const mm_geom* g, const float* in, double* tp) {
+    MM_API_BEGIN(c);
+    MM_TRY(check_geom(g));
+    return st_true_peak(c, g, in, tp);
+}
+int mm_dev_spectrum_bars(mm_ctx* c, const mm_geom* g, const float* in, int view, double* bars) {
+    MM_API_BEGIN(c);
+    MM_TRY(check_geom(g));
+    return st_spectrum_bars(c, g, in, view, bars);
+}
+int mm_dev_stereo_correlation(mm_ctx* c, const mm_geom* g, const float* in, double* corr, double* peak) {
+    MM_API_BEGIN(c);
+    MM_TRY(check_geom(g));
+    return st_correlation(c, g, in, corr, peak);
+}
+
+// ---- chains ---------------------------------------------------------------------------------------
+int mm_dev_master(mm_ctx* c, const mm_geom* g, int chain, const mm_style* styles, const float* in, float* out,
+                  int16_t* pcm, const float* noise, uint64_t seed, mm_track_stats* stats_dev, uint32_t flags) {
+    MM_API_BEGIN(c);
+    return master_impl(c, g, chain, styles, in, out, pcm, noise, seed, stats_dev, flags);
+}
+
+int mm_master_host(mm_ctx* c, int chain, int32_t tracks, int64_t n, int32_t channels, int32_t sr, const mm_style* styles,
+                   const float* audio_in, float* audio_out, int16_t* pcm16_out, const float* noise_host, uint64_t seed,
+                   mm_track_stats* stats_host, uint32_t flags) {
+    MM_API_BEGIN(c);
+    mm_geom g;
+    g.n = n; g.stride = mm_row_stride(n); g.tracks = tracks; g.channels = channels; g.sr = sr; g._pad = 0;
+    MM_TRY(check_geom(&g));
+    if (!audio_in) { set_error("mm_master_host: audio_in is null"); return 1; }
+    const size_t frames = (size_t)tracks * (size_t)n * channels;
+    float *il, *pl, *nz = nullptr;
+    int16_t* pcm = nullptr;
+    mm_track_stats* st = nullptr;
+    MM_TRY(arena(c, SL_STAGE_IL, frames, &il));
+    MM_TRY(arena(c, SL_STAGE_PL, batch_floats(&g), &pl));
+    if (pcm16_out) MM_TRY(arena(c, SL_STAGE_PCM, frames, &pcm));
+    if (noise_host) MM_TRY(arena(c, SL_STAGE_NOISE, frames, &nz));
+    if (stats_host) MM_TRY(arena(c, SL_STATS, (size_t)tracks, &st));
+    MM_CUDA(cudaMemcpyAsync(il, audio_in, frames * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    if (noise_host) MM_CUDA(cudaMemcpyAsync(nz, noise_host, frames * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    MM_TRY(mm_dev_deinterleave(c, &g, il, pl));
+    MM_TRY(master_impl(c, &g, chain, styles, pl, pl, pcm, nz, seed, st, flags));
+    if (audio_out) {
+        MM_TRY(mm_dev_interleave(c, &g, pl, il));
+        MM_CUDA(cudaMemcpyAsync(audio_out, il, frames * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    }
+    if (pcm16_out) MM_CUDA(cudaMemcpyAsync(pcm16_out, pcm, frames * sizeof(int16_t), cudaMemcpyDeviceToHost, c->stream));
+    if (stats_host) MM_CUDA(cudaMemcpyAsync(stats_host, st, (size_t)tracks * sizeof(mm_track_stats), cudaMemcpyDeviceToHost, c->stream));
+    return mm_ctx_sync(c);
+}
+
+// ---- filter design ----------------------------------------------------------------------------
+int mm_design_butter(int order, int btype, const double* wn, double* b, double* a) {
+    Ba f;
+    memset(&f, 0, sizeof(f));
+    if (!wn || !b || !a || btype < 0 || btype > 2) { set_error("mm_design_butter: bad arguments"); return -1; }
+    if (!butter(order, (BType)btype, wn, &f)) { set_error("mm_design_butter: unsupported order or critical frequencies"); return -1; }
+    for (int i = 0; i <= f.m; ++i) { b[i] = f.b[i]; a[i] = f.a[i]; }
+    return f.m + 1;
+}
+
+int mm_design_lfilter_zi(const double* b, const double* a, int ncoef, double* zi) {
+    if (!b || !a || !zi || ncoef < 2 || ncoef > kMaxOrder + 1 || a[0] == 0.0) { set_error("mm_design_lfilter_zi: bad arguments"); return 1; }
+    Ba f;
+    memset(&f, 0, sizeof(f));
+    f.m = ncoef - 1;
+    for (int i = 0; i < ncoef; ++i) { f.b[i] = b[i] / a[0]; f.a[i] = a[i] / a[0]; }
+    if (!lfilter_zi(f, zi)) { set_error("mm_design_lfilter_zi: singular system"); return 1; }
+    return 0;
+}
+
+int mm_design_k_weighting(int stage, double rate, double* b, double* a) {
+    if (!b || !a || stage < 0 || stage > 1 || !(rate > 0)) { set_error("mm_design_k_weighting: bad arguments"); return 1; }
+    Ba f = k_weighting_stage(stage, rate);
+    for (int i = 0; i < 3; ++i) { b[i] = f.b[i]; a[i] = f.a[i]; }
+    return 0;
+}
+
+// Scan tables of a section, for host-side verification of the tile decomposition (tests/):
+// returns the look-back window W; g[kS*m], Pw[5*m*m], Plane[32*m*m], Qpow[(kNW+1)*m*m],
+// Mpow[cap_w*m*m] (first min(W, cap_w) powers), Apow[(kS+1)*m*m], zi[m].
+int mm_design_scan_tables(const double* b, const double* a, int ncoef, double* g_, double* Pw, double* Plane, double* Qpow,
+                          double* Mpow, int cap_w, double* Apow, double* zi, int* S, int* T) {
+    if (!b || !a || (ncoef != 3 && ncoef != 5)) { set_error("mm_design_scan_tables: ncoef must be 3 or 5"); return -1; }
+    Ba f;
+    memset(&f, 0, sizeof(f));
+    f.m = ncoef - 1;
+    for (int i = 0; i < ncoef; ++i) { f.b[i] = b[i] / a[0]; f.a[i] = a[i] / a[0]; }
+    ScanTables t;
+    if (!build_scan_tables(f, kS, kT, &t)) { set_error("mm_design_scan_tables: pole too close to the unit circle"); return -1; }
+    const int mm2 = f.m * f.m;
+    if (g_) std::copy(t.g.begin(), t.g.end(), g_);
+    if (Pw) std::copy(t.Pw.begin(), t.Pw.end(), Pw);
+    if (Plane) std::copy(t.Plane.begin(), t.Plane.end(), Plane);
+    if (Qpow) std::copy(t.Qpow.begin(), t.Qpow.end(), Qpow);
+    if (Mpow) std::copy(t.Mpow.begin(), t.Mpow.begin() + (size_t)std::min(t.W, cap_w) * mm2, Mpow);
+    if (Apow) std::copy(t.Apow.begin(), t.Apow.end(), Apow);
+    if (zi) for (int i = 0; i < f.m; ++i) zi[i] = t.zi[i];
+    if (S) *S = kS;
+    if (T) *T = kT;
+    return t.W;
+}
+
+}  // extern "C"

@@ -1,0 +1,171 @@
+#include "context.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstring>
+
+#include "common.cuh"
+
+namespace mm {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+const char* get_error() { return g_err; }
+
+int arena_get(mm_ctx* c, int slot, size_t bytes, void** out) {
+    Slot& s = c->slots[slot];
+    if (bytes == 0) bytes = 16;
+    if (s.cap < bytes) {
+        if (s.p) {
+            MM_CUDA(cudaStreamSynchronize(c->stream));
+            MM_CUDA(cudaFree(s.p));
+            c->workspace_bytes -= (int64_t)s.cap;
+            s.p = nullptr;
+            s.cap = 0;
+        }
+        size_t want = (bytes + 255) & ~(size_t)255;
+        MM_CUDA(cudaMalloc(&s.p, want));
+        s.cap = want;
+        c->workspace_bytes += (int64_t)want;
+    }
+    *out = s.p;
+    return 0;
+}
+
+int ensure_carry(mm_ctx* c, size_t slots) {
+    if (c->carry_slots >= slots) return 0;
+    if (c->agg) {
+        MM_CUDA(cudaStreamSynchronize(c->stream));
+        MM_CUDA(cudaFree(c->agg));
+        MM_CUDA(cudaFree(c->flag));
+        c->workspace_bytes -= (int64_t)(c->carry_slots * (kMaxOrder * sizeof(double) + sizeof(unsigned)));
+    }
+    size_t want = slots + slots / 4 + 1024;
+    MM_CUDA(cudaMalloc(&c->agg, want * kMaxOrder * sizeof(double)));
+    MM_CUDA(cudaMalloc(&c->flag, want * sizeof(unsigned)));
+    MM_CUDA(cudaMemsetAsync(c->flag, 0, want * sizeof(unsigned), c->stream));
+    c->carry_slots = want;
+    c->epoch = 0;    // flags are all zero again; epochs restart at 1
+    c->workspace_bytes += (int64_t)(want * (kMaxOrder * sizeof(double) + sizeof(unsigned)));
+    return 0;
+}
+
+template <int M> static void pack_tables(const ScanTables& t, std::vector<double>& h) {
+    typedef Tab<M> TB;
+    h.assign((size_t)TB::Mpow + (size_t)t.W * TB::MM, 0.0);
+    std::copy(t.Pw.begin(), t.Pw.end(), h.begin() + TB::Pw);
+    std::copy(t.Plane.begin(), t.Plane.end(), h.begin() + TB::Plane);
+    std::copy(t.Qpow.begin(), t.Qpow.end(), h.begin() + TB::Qpow);
+    for (int i = 0; i < M; ++i) h[TB::Zi + i] = t.zi[i];
+    std::copy(t.Apow.begin(), t.Apow.end(), h.begin() + TB::Apow);
+    std::copy(t.Mpow.begin(), t.Mpow.end(), h.begin() + TB::Mpow);
+}
+
+const FilterPlan* get_plan(mm_ctx* c, const Ba& ba) {
+    std::string key((const char*)&ba, sizeof(Ba));
+    auto it = c->plans.find(key);
+    if (it != c->plans.end()) return &it->second;
+    FilterPlan p;
+    p.ba = ba;
+    if (ba.m != 2 && ba.m != 4) { set_error("unsupported section order %d (2 or 4)", ba.m); return nullptr; }
+    if (!build_scan_tables(ba, kS, kT, &p.tabs)) {
+        set_error("scan tables: pole too close to the unit circle for the %d-sample tile", kL);
+        return nullptr;
+    }
+    p.pad = 3 * (ba.m + 1);
+    std::vector<double> h;
+    if (ba.m == 2) pack_tables<2>(p.tabs, h); else pack_tables<4>(p.tabs, h);
+    if (cudaMalloc(&p.dev, h.size() * sizeof(double)) != cudaSuccess) { set_error("cudaMalloc(filter tables) failed"); return nullptr; }
+    if (cudaMemcpyAsync(p.dev, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream) != cudaSuccess ||
+        cudaStreamSynchronize(c->stream) != cudaSuccess) {
+        set_error("upload of filter tables failed");
+        return nullptr;
+    }
+    auto res = c->plans.emplace(key, p);
+    return &res.first->second;
+}
+
+template <class T> static int upload_vec(mm_ctx* c, const std::vector<T>& v, T** dev) {
+    MM_CUDA(cudaMalloc(dev, std::max<size_t>(v.size(), 1) * sizeof(T)));
+    if (!v.empty()) MM_CUDA(cudaMemcpyAsync(*dev, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, c->stream));
+    MM_CUDA(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+// pyloudnorm block bounds (meter.py integrated_loudness): T_g = 0.4, step = 0.25,
+//   numBlocks = int(round((T - T_g) / (T_g * step)) + 1),  l_j = int(T_g*(j*step)*rate),
+//   u_j = int(T_g*(j*step + 1)*rate)   -- evaluated in the same float64 order here.
+int get_lufs_plan(mm_ctx* c, long long n, int sr, const LufsPlan** out) {
+    char keyb[64];
+    snprintf(keyb, sizeof(keyb), "%lld:%d", n, sr);
+    auto it = c->lufs_plans.find(keyb);
+    if (it != c->lufs_plans.end()) { *out = &it->second; return 0; }
+    LufsPlan p;
+    const double rate = (double)sr, T_g = 0.4, step = 1.0 - 0.75;
+    p.valid = !((double)n < T_g * rate);
+    p.scale = 1.0 / (T_g * rate);
+    const long long q_last = kLead + n - 1;
+    p.ntiles = (int)((q_last + kL) / kL);
+    std::vector<long long> lo, hi, bnd;
+    if (p.valid) {
+        const double T = (double)n / rate;
+        const long long nb = (long long)std::nearbyint((T - T_g) / (T_g * step)) + 1;   // np.round = half-to-even
+        for (long long j = 0; j < nb; ++j) {
+            const long long l = (long long)(T_g * ((double)j * step) * rate);
+            long long u = (long long)(T_g * ((double)j * step + 1.0) * rate);
+            lo.push_back(l);
+            hi.push_back(std::min(u, n));      // numpy slicing clamps at the array end
+        }
+        bnd = lo;
+        bnd.insert(bnd.end(), hi.begin(), hi.end());
+        std::sort(bnd.begin(), bnd.end());
+        bnd.erase(std::unique(bnd.begin(), bnd.end()), bnd.end());
+    }
+    if (bnd.size() < 2) { bnd.clear(); bnd.push_back(0); bnd.push_back(0); p.valid = p.valid && false; }
+    p.nseg = (int)bnd.size() - 1;
+    p.nblocks = (int)lo.size();
+    std::vector<int> blo(lo.size()), bhi(lo.size());
+    for (size_t j = 0; j < lo.size(); ++j) {
+        blo[j] = (int)(std::lower_bound(bnd.begin(), bnd.end(), lo[j]) - bnd.begin());
+        bhi[j] = (int)(std::lower_bound(bnd.begin(), bnd.end(), hi[j]) - bnd.begin());
+    }
+    std::vector<int> tseg(p.ntiles);
+    for (int t = 0; t < p.ntiles; ++t) {
+        long long i0 = std::max<long long>((long long)t * kL - kLead, 0);
+        int s = (int)(std::upper_bound(bnd.begin(), bnd.end(), i0) - bnd.begin()) - 1;
+        tseg[t] = std::min(std::max(s, 0), p.nseg);
+    }
+    MM_TRY(upload_vec(c, bnd, &p.bnd));
+    MM_TRY(upload_vec(c, tseg, &p.tile_seg));
+    MM_TRY(upload_vec(c, blo, &p.blk_lo));
+    MM_TRY(upload_vec(c, bhi, &p.blk_hi));
+    auto res = c->lufs_plans.emplace(keyb, p);
+    *out = &res.first->second;
+    return 0;
+}
+
+KernelScope::KernelScope(mm_ctx* ctx, const char* nm) : c(ctx), name(nm) {
+    c->launches += 1;
+    if (c->timing) {
+        cudaEventCreate(&a);
+        cudaEventCreate(&b);
+        cudaEventRecord(a, c->stream);
+    }
+}
+KernelScope::~KernelScope() {
+    if (c->timing && a) {
+        cudaEventRecord(b, c->stream);
+        KTime k;
+        k.name = name; k.a = a; k.b = b;
+        c->ktimes.push_back(k);
+    }
+}
+
+}  // namespace mm

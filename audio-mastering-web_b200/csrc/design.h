@@ -1,0 +1,48 @@
+// Host-side filter design and scan tables (float64 / long double), no CUDA dependency.
+//
+// Restates the closed-form maths behind scipy.signal.butter(N, Wn, btype, output="ba") and
+// scipy.signal.lfilter_zi, which the reference calls at backend/app/pipeline.py:175-183,
+// :345-353, :590-599, :1231, :1303, :1427, :1463, and the RBJ K-weighting biquads pyloudnorm
+// evaluates per sample rate (call sites pipeline.py:646-648).
+#pragma once
+#include <cstdint>
+#include <vector>
+
+namespace mm {
+
+constexpr int kMaxOrder = 4;            // state dimension of the widest section (de-esser BP4)
+
+struct Ba {
+    int m = 0;                          // order = state dimension; ncoef = m + 1
+    double b[kMaxOrder + 1] = {0};
+    double a[kMaxOrder + 1] = {0};      // a[0] == 1
+};
+
+enum BType { kLow = 0, kHigh = 1, kBand = 2 };
+
+// scipy.signal.butter(order, wn, btype, analog=False, output="ba"); wn normalised to Nyquist.
+bool butter(int order, BType bt, const double* wn, Ba* out);
+// scipy.signal.lfilter_zi(b, a): steady-state DF2T state of the unit step response.
+bool lfilter_zi(const Ba& f, double* zi);
+// pyloudnorm IIRfilter coefficients: stage 0 = high shelf (+4 dB, Q 1/sqrt2, 1500 Hz),
+// stage 1 = high pass (Q 0.5, 38 Hz).
+Ba k_weighting_stage(int stage, double rate);
+
+// DF2T as a state-space system  z[n] = A z[n-1] + B x[n],  y[n] = z[n-1][0] + b0 x[n]
+// A = companion(a)^T (row-major m x m), B[i] = b[i+1] - a[i+1] b0.
+struct ScanTables {
+    int m = 0;
+    int S = 0, T = 0;                   // samples per thread, threads per tile
+    int W = 0;                          // look-back window (tiles) after which A^(L*W) < 1e-18
+    std::vector<double> g;              // [S][m]      g[j] = A^(S-1-j) B
+    std::vector<double> Pw;             // [5][m*m]    (A^S)^(2^d)
+    std::vector<double> Plane;          // [32][m*m]   (A^S)^l
+    std::vector<double> Qpow;           // [T/32+1][m*m]  (A^(32 S))^w
+    std::vector<double> Mpow;           // [W][m*m]    (A^(S*T))^j
+    std::vector<double> Apow;           // [S+1][m*m]  A^j   (dead-head handling)
+    double zi[kMaxOrder] = {0};
+    double pole_radius = 0;
+};
+bool build_scan_tables(const Ba& f, int S, int T, ScanTables* out, int max_window = 4096);
+
+}  // namespace mm

@@ -1,0 +1,290 @@
+// Reductions and pointwise passes of the chain: input statistics, peak guards, imager,
+// finalise (+ TPDF dither to int16), layout conversion.
+#pragma once
+#include "pointwise.cuh"
+#include "pw_args.h"
+
+namespace mm {
+
+
+// ---- per-row sum / min / max (remove_dc_offset + remove_intersample_peaks, pipeline.py:134-149) ----
+
+__global__ void __launch_bounds__(kPwThreads) row_stats_kernel(const float* __restrict__ in, long long n, long long stride,
+                                                               RowStats* __restrict__ st) {
+    const int row = blockIdx.y;
+    const float* src = in + (size_t)row * (size_t)stride + kLead;
+    const long long base = (long long)blockIdx.x * kPwFramesPerBlock;
+    double s = 0.0;
+    float mn = __int_as_float(0x7f800000), mx = -__int_as_float(0x7f800000);
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const long long i = base + 4LL * (threadIdx.x + kPwThreads * r);
+        if (i + 3 < n) {
+            const float4 v = __ldcs(reinterpret_cast<const float4*>(src + i));
+            s += ((double)v.x + (double)v.y) + ((double)v.z + (double)v.w);
+            mn = fminf(fminf(mn, v.x), fminf(v.y, fminf(v.z, v.w)));
+            mx = fmaxf(fmaxf(mx, v.x), fmaxf(v.y, fmaxf(v.z, v.w)));
+        } else {
+            for (int c = 0; c < 4; ++c)
+                if (i + c < n) { const float x = src[i + c]; s += (double)x; mn = fminf(mn, x); mx = fmaxf(mx, x); }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        s += shfl_xor_d(s, o);
+        mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    }
+    __shared__ double ss[kPwThreads / 32];
+    __shared__ float smn[kPwThreads / 32], smx[kPwThreads / 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) { ss[warp] = s; smn[warp] = mn; smx[warp] = mx; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < kPwThreads / 32; ++w) { s += ss[w]; mn = fminf(mn, smn[w]); mx = fmaxf(mx, smx[w]); }
+        atomicAdd(&st[row].sum, s);
+        atomicMin(&st[row].mn, f2ord(mn));
+        atomicMax(&st[row].mx, f2ord(mx));
+    }
+}
+
+__global__ void row_stats_init_kernel(RowStats* st, int rows) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < rows) { st[r].sum = 0.0; st[r].mn = 0xffffffffu; st[r].mx = 0u; st[r].pad = 0; }
+}
+
+// mean / peak -> per-row (sub, mul) of the float32 prologue  y = (x - mean) * scale
+//   use_dc: subtract the channel mean (remove_dc_offset); use_guard: scale to -headroom if the
+//   track peak exceeds it (remove_intersample_peaks).  Float32 steps as numpy takes them.
+__global__ void in_scalars_kernel(const InScalarArgs P) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= P.tracks) return;
+    float peak = 0.f;
+    bool nan = false;
+    for (int c = 0; c < P.channels; ++c) {
+        const int row = t * P.channels + c;
+        const float mean = P.use_dc ? (float)(P.st[row].sum / (double)P.n) : 0.f;
+        const float hi = __fsub_rn(ord2f(P.st[row].mx), mean);
+        const float lo = __fsub_rn(ord2f(P.st[row].mn), mean);
+        peak = fmaxf(peak, fmaxf(fabsf(hi), fabsf(lo)));
+        nan = nan || !(hi == hi) || !(lo == lo);
+        P.sub[row] = (double)mean;
+        if (P.mean_row) P.mean_row[row] = (double)mean;
+    }
+    float scale = 1.f;
+    if (P.use_guard && !nan && peak <= 3.0e38f && peak > 1e-12f && peak > P.limit) scale = __fdiv_rn(P.limit, peak);
+    for (int c = 0; c < P.channels; ++c) P.mul[t * P.channels + c] = (double)scale;
+    if (P.peak_track) P.peak_track[t] = (double)peak;
+}
+
+// Output guard scalars from an already accumulated per-track |x| max (float bits).
+__global__ void out_scalars_kernel(const OutScalarArgs P) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= P.tracks) return;
+    const float peak = P.peak_bits[t];
+    float scale = 1.f;
+    if (peak == peak && peak <= 3.0e38f && peak > 1e-12f && peak > P.limit) scale = __fdiv_rn(P.limit, peak);
+    for (int c = 0; c < P.channels; ++c) P.mul[t * P.channels + c] = (double)scale;
+    if (P.peak_track) P.peak_track[t] = (double)peak;
+}
+
+// ---- generic pointwise pass over (track, frames); both channels of a track in one thread -------------
+
+
+__device__ __forceinline__ void philox4x32_10(unsigned c0, unsigned c1, unsigned c2, unsigned c3, unsigned k0, unsigned k1,
+                                              unsigned (&out)[4]) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const unsigned hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        const unsigned hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        const unsigned n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+// _write_wav_16bit_dithered quantiser (pipeline.py:887-898): float64(x) * 32767 + float32 noise,
+// round half to even, clip.
+__device__ __forceinline__ int16_t quantize16(float x, float noise) {
+    if (x != x) x = 0.f;
+    x = fminf(fmaxf(x, -1.f), 1.f);
+    double d = __dadd_rn(__dmul_rn((double)x, 32767.0), (double)noise);
+    d = rint(d);
+    d = fmin(fmax(d, -32768.0), 32767.0);
+    return (int16_t)(int)d;
+}
+__device__ __forceinline__ float tpdf_from_bits(unsigned a, unsigned b) {
+    // (rand + rand - 1.0).astype(float32), pipeline.py:830-832, with 32-bit uniforms
+    const double u = (double)a * 2.3283064365386963e-10 + (double)b * 2.3283064365386963e-10 - 1.0;
+    return (float)u;
+}
+
+__global__ void __launch_bounds__(kPwThreads) pointwise_kernel(const PwArgs P) {
+    const int track = blockIdx.y;
+    const int C = P.channels;
+    const long long base = (long long)blockIdx.x * kPwFramesPerBlock;
+    const size_t r0 = (size_t)(track * C) * (size_t)P.stride + kLead;
+    const size_t r1 = r0 + (C > 1 ? (size_t)P.stride : 0);
+    float sub0 = 0.f, sub1 = 0.f, mul0 = 1.f, mul1 = 1.f;
+    if (P.sub) { sub0 = (float)P.sub[track * C]; sub1 = (float)P.sub[track * C + (C > 1)]; }
+    if (P.mul) { mul0 = (float)P.mul[track * C]; mul1 = (float)P.mul[track * C + (C > 1)]; }
+    const bool imager = (P.width != nullptr) && C == 2 && (P.force_imager || fabs(P.width[track] - 1.0) > 0.0);
+    const double muld0 = (P.mode == PW_GAIN_F64 && P.mul) ? P.mul[track * C] : 1.0;
+    const double muld1 = (P.mode == PW_GAIN_F64 && P.mul) ? P.mul[track * C + (C > 1)] : 1.0;
+    const float wf = imager ? (float)P.width[track] : 1.f;
+    float pk = 0.f;
+    double bad = 0.0;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const long long i = base + 4LL * (threadIdx.x + kPwThreads * r);
+        if (i >= P.n) continue;
+        const bool full = i + 3 < P.n;
+        float a[4] = {0, 0, 0, 0}, b[4] = {0, 0, 0, 0};
+        if (full) {
+            const float4 v = __ldcs(reinterpret_cast<const float4*>(P.in + r0 + i));
+            a[0] = v.x; a[1] = v.y; a[2] = v.z; a[3] = v.w;
+            if (C > 1) { const float4 w = __ldcs(reinterpret_cast<const float4*>(P.in + r1 + i)); b[0] = w.x; b[1] = w.y; b[2] = w.z; b[3] = w.w; }
+        } else {
+            for (int c = 0; c < 4; ++c) if (i + c < P.n) { a[c] = P.in[r0 + i + c]; if (C > 1) b[c] = P.in[r1 + i + c]; }
+        }
+        int16_t q[8];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            float l = a[c], rr = b[c];
+            if (P.mode == PW_AFFINE) {
+                l = __fmul_rn(__fsub_rn(l, sub0), mul0); rr = __fmul_rn(__fsub_rn(rr, sub1), mul1);
+                if (P.clip) { l = fminf(fmaxf(l, -1.f), 1.f); rr = fminf(fmaxf(rr, -1.f), 1.f); }
+            } else if (P.mode == PW_MAXIMIZER) {
+                // apply_maximizer alone (no limiter): tp_lim is set to +inf by the host
+                l = maximize_limit(l, P.dyn); rr = maximize_limit(rr, P.dyn);
+            } else if (P.mode == PW_PARALLEL) {
+                l = parallel_compress(l, P.par_mix, P.dyn); rr = parallel_compress(rr, P.par_mix, P.dyn);
+            } else if (P.mode == PW_GAIN_F64) {
+                // normalize_lufs (pipeline.py:654-655): float32 array * float64 scalar -> float64 -> float32
+                l = (float)((double)l * muld0); rr = (float)((double)rr * muld1);
+            } else if (P.mode == PW_MS_ENCODE) {
+                // pipeline.py:249-250: mid = (L + R) * 0.5, side = (L - R) * 0.5 (float32)
+                const float m = __fmul_rn(__fadd_rn(l, rr), 0.5f), sd = __fmul_rn(__fsub_rn(l, rr), 0.5f);
+                l = m; rr = sd;
+            } else if (P.mode == PW_MS_DECODE) {
+                // pipeline.py:253-254: L = clip(m + s), R = clip(m - s)
+                const float lo = fminf(fmaxf(__fadd_rn(l, rr), -1.f), 1.f), ro = fminf(fmaxf(__fsub_rn(l, rr), -1.f), 1.f);
+                l = lo; rr = ro;
+            } else if (P.mode == PW_FADE) {
+                if (i + c < P.n_fade) {
+                    const float ramp = (i + c == P.n_fade - 1) ? 1.f : (float)((double)(i + c) * P.fade_step);
+                    l = __fmul_rn(l, ramp); rr = __fmul_rn(rr, ramp);
+                }
+            } else {   // PW_IMAGER, PW_PEAK, PW_FINALIZE share the imager front end
+                if (imager) {
+                    const float mid = __fmul_rn(__fadd_rn(l, rr), 0.5f);
+                    const float side = __fmul_rn(__fmul_rn(__fsub_rn(l, rr), 0.5f), wf);
+                    l = fminf(fmaxf(__fadd_rn(mid, side), -1.f), 1.f);
+                    rr = fminf(fmaxf(__fsub_rn(mid, side), -1.f), 1.f);
+                }
+                if (P.mode == PW_PEAK) {
+                    if (i + c < P.n) { pk = fmaxf(pk, fabsf(l)); if (C > 1) pk = fmaxf(pk, fabsf(rr)); }
+                } else if (P.mode == PW_FINALIZE) {
+                    if (i + c < P.n) { if (!(fabsf(l) <= 3.4e38f)) bad += 1.0; if (C > 1 && !(fabsf(rr) <= 3.4e38f)) bad += 1.0; }
+                    l = __fmul_rn(l, mul0); rr = __fmul_rn(rr, mul1);
+                    l = (l != l) ? 0.f : fminf(fmaxf(l, -1.f), 1.f);
+                    rr = (rr != rr) ? 0.f : fminf(fmaxf(rr, -1.f), 1.f);
+                    if (i + c < P.n_fade) {
+                        const float ramp = (i + c == P.n_fade - 1) ? 1.f : (float)((double)(i + c) * P.fade_step);
+                        l = __fmul_rn(l, ramp); rr = __fmul_rn(rr, ramp);
+                    }
+                    if (P.pcm) {
+                        float n0, n1 = 0.f;
+                        const size_t fi = (size_t)track * (size_t)P.n + (size_t)(i + c);
+                        if (P.noise) {
+                            if (i + c < P.n) { n0 = P.noise[fi * C]; if (C > 1) n1 = P.noise[fi * C + 1]; } else n0 = 0.f;
+                        } else {
+                            unsigned rnd[4];
+                            const unsigned long long fr = (unsigned long long)(i + c);
+                            philox4x32_10((unsigned)fr, (unsigned)(fr >> 32), (unsigned)track, 0u,
+                                          (unsigned)P.seed, (unsigned)(P.seed >> 32), rnd);
+                            n0 = tpdf_from_bits(rnd[0], rnd[1]); n1 = tpdf_from_bits(rnd[2], rnd[3]);
+                        }
+                        q[c * C] = quantize16(l, n0);
+                        if (C > 1) q[c * C + 1] = quantize16(rr, n1);
+                    }
+                }
+            }
+            a[c] = l; b[c] = rr;
+        }
+        if (P.out) {
+            if (full) {
+                __stcs(reinterpret_cast<float4*>(P.out + r0 + i), make_float4(a[0], a[1], a[2], a[3]));
+                if (C > 1) __stcs(reinterpret_cast<float4*>(P.out + r1 + i), make_float4(b[0], b[1], b[2], b[3]));
+            } else {
+                for (int c = 0; c < 4; ++c) if (i + c < P.n) { P.out[r0 + i + c] = a[c]; if (C > 1) P.out[r1 + i + c] = b[c]; }
+            }
+        }
+        if (P.mode == PW_FINALIZE && P.pcm) {
+            int16_t* dst = P.pcm + ((size_t)track * (size_t)P.n + (size_t)i) * C;
+            if (full && C == 2) {
+                // 4 frames x 2 channels = 16 bytes; base offset is 4-frame aligned but the track origin
+                // need not be 16-byte aligned (odd n), so fall back to 4-byte stores when it is not
+                if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+                    int4 pk4;
+                    pk4.x = (int)(uint16_t)q[0] | ((int)(uint16_t)q[1] << 16);
+                    pk4.y = (int)(uint16_t)q[2] | ((int)(uint16_t)q[3] << 16);
+                    pk4.z = (int)(uint16_t)q[4] | ((int)(uint16_t)q[5] << 16);
+                    pk4.w = (int)(uint16_t)q[6] | ((int)(uint16_t)q[7] << 16);
+                    *reinterpret_cast<int4*>(dst) = pk4;
+                } else {
+                    for (int c = 0; c < 8; ++c) dst[c] = q[c];
+                }
+            } else {
+                for (int c = 0; c < 4; ++c) if (i + c < P.n) for (int k = 0; k < C; ++k) dst[c * C + k] = q[c * C + k];
+            }
+        }
+    }
+    if (P.mode == PW_PEAK && P.peak) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) pk = fmaxf(pk, __shfl_xor_sync(0xffffffffu, pk, o));
+        if ((threadIdx.x & 31) == 0 && pk > 0.f) atomicMax(reinterpret_cast<int*>(P.peak + track), __float_as_int(pk));
+    }
+    if (P.mode == PW_FINALIZE && P.nonfinite) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) bad += shfl_xor_d(bad, o);
+        if ((threadIdx.x & 31) == 0 && bad > 0.0) atomicAdd(P.nonfinite + track, bad);
+    }
+}
+
+// standalone quantiser for an already final float32 buffer (export_audio on its own)
+__global__ void __launch_bounds__(kPwThreads) quantize_kernel(const QuantArgs P) {
+    const int track = blockIdx.y, C = P.channels;
+    const long long i = ((long long)blockIdx.x * kPwThreads + threadIdx.x);
+    if (i >= P.n) return;
+    const size_t fi = (size_t)track * (size_t)P.n + (size_t)i;
+    unsigned rnd[4] = {0, 0, 0, 0};
+    if (!P.noise) philox4x32_10((unsigned)i, (unsigned)((unsigned long long)i >> 32), (unsigned)track, 0u,
+                                (unsigned)P.seed, (unsigned)(P.seed >> 32), rnd);
+    for (int c = 0; c < C; ++c) {
+        const float x = P.in[(size_t)(track * C + c) * (size_t)P.stride + kLead + i];
+        const float nz = P.noise ? P.noise[fi * C + c] : tpdf_from_bits(rnd[2 * c], rnd[2 * c + 1]);
+        P.pcm[fi * C + c] = quantize16(x, nz);
+    }
+}
+
+// ---- layout conversion ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kPwThreads) deinterleave_kernel(const float* __restrict__ il, float* __restrict__ pl,
+                                                                  long long n, long long stride, int channels) {
+    const int track = blockIdx.y;
+    const long long i = (long long)blockIdx.x * kPwThreads + threadIdx.x;
+    if (i >= n) return;
+    const float* src = il + ((size_t)track * (size_t)n + (size_t)i) * channels;
+    for (int c = 0; c < channels; ++c) pl[(size_t)(track * channels + c) * (size_t)stride + kLead + i] = src[c];
+}
+__global__ void __launch_bounds__(kPwThreads) interleave_kernel(const float* __restrict__ pl, float* __restrict__ il,
+                                                                long long n, long long stride, int channels) {
+    const int track = blockIdx.y;
+    const long long i = (long long)blockIdx.x * kPwThreads + threadIdx.x;
+    if (i >= n) return;
+    float* dst = il + ((size_t)track * (size_t)n + (size_t)i) * channels;
+    for (int c = 0; c < channels; ++c) dst[c] = pl[(size_t)(track * channels + c) * (size_t)stride + kLead + i];
+}
+
+}  // namespace mm

@@ -1,0 +1,539 @@
+// Stage functions and chains: host orchestration of the sweep / reduction / pointwise kernels.
+// Every stage cites the reference function it reproduces (paths relative to the reference tree).
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+#include "context.h"
+#include "lufs_kernel.cuh"
+#include "misc_kernels.cuh"
+#include "stages_internal.h"
+#include "sweep_kernel.cuh"
+
+namespace mm {
+
+// ---------------------------------------------------------------------------------------------------
+// launch helpers
+// ---------------------------------------------------------------------------------------------------
+static inline int tiles_fwd(long long n, int pad) { return (int)((kLead + n + pad - 1 + kL) / kL); }
+static inline int tiles_bwd(long long n, int pad) {
+    const long long q_last = kLead + n + pad - 1, q_first = kLead - pad;
+    const long long qend = (q_last + 4) & ~3LL;
+    return (int)((qend - q_first + kL - 1) / kL);
+}
+
+template <int M> static void fill_filter(FiltK<M>& fk, const FilterPlan* p) {
+    for (int i = 0; i <= M; ++i) fk.b[i] = p->ba.b[i];
+    for (int i = 0; i < M; ++i) fk.a[i] = p->ba.a[i + 1];
+    for (int j = 0; j < kS; ++j)
+        for (int i = 0; i < M; ++i) fk.g[j][i] = p->tabs.g[(size_t)j * M + i];
+}
+
+template <int M, int NF, int NIN, int DIR>
+static int launch_sweep(mm_ctx* c, SweepArgs<M, NF>& A, const char* name) {
+    static bool attr_done = false;
+    const size_t smem = (size_t)NF * kTileFloats * sizeof(float);
+    if (!attr_done) {
+        MM_CUDA(cudaFuncSetAttribute(sweep_kernel<M, NF, NIN, DIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_done = true;
+    }
+    A.ntiles = DIR > 0 ? tiles_fwd(A.n, A.pad) : tiles_bwd(A.n, A.pad);
+    const size_t items = (size_t)A.rows * (size_t)A.ntiles;
+    if (items == 0) return 0;
+    if (items > 0x7fffffffULL) { set_error("batch too large for one sweep (%zu tiles)", items); return 1; }
+    MM_TRY(ensure_carry(c, (size_t)NF * items));
+    A.agg = c->agg;
+    A.flag = c->flag;
+    A.epoch = ++c->epoch;
+    A.ticket = c->ticket;
+    A.ticket_base = c->ticket_total;
+    c->ticket_total += (unsigned)items;
+    A.err = c->err;
+    {
+        KernelScope ks(c, name);
+        sweep_kernel<M, NF, NIN, DIR><<<(unsigned)items, kT, smem, c->stream>>>(A);
+    }
+    MM_CUDA(cudaGetLastError());
+    return 0;
+}
+
+template <int M, int NF>
+static void fill_common(SweepArgs<M, NF>& A, const mm_geom* g, const FilterPlan* const* plans, const float* const* in, int nin,
+                        float* const* out, int nout, const Pro& pro, const Epi& epi, int pad) {
+    memset(&A, 0, sizeof(A));
+    for (int f = 0; f < NF; ++f) {
+        fill_filter<M>(A.f[f], plans[f]);
+        A.tab[f] = plans[f]->dev;
+        A.W[f] = plans[f]->tabs.W;
+        A.in[f] = in[f < nin ? f : nin - 1];
+        A.out[f] = out[f < nout ? f : nout - 1];
+        A.w[f] = epi.w[f];
+    }
+    A.aux[0] = epi.aux0;
+    A.aux[1] = epi.aux1;
+    A.n = g->n;
+    A.stride = g->stride;
+    A.rows = g->tracks * g->channels;
+    A.pad = pad;
+    A.channels = g->channels;
+    A.pro_mode = pro.mode;
+    A.pro_sub = pro.sub;
+    A.pro_mul = pro.mul;
+    A.aux_pro = epi.aux_pro;
+    A.epi = epi.mode;
+    A.wc = epi.wc;
+    A.trim = epi.trim;
+    if (epi.dyn) A.dyn = *epi.dyn;
+    A.exc_gain = epi.exc_gain;
+    A.exc_k = epi.exc_k;
+    A.exc_mode = epi.exc_mode;
+    A.peak = epi.peak;
+}
+
+int sweep_fwd(mm_ctx* c, const mm_geom* g, int nf, int nin, const FilterPlan* const* plans, const float* const* in,
+              float* const* out, const Pro& pro, int pad) {
+    Epi epi;
+    const int m = plans[0]->ba.m;
+    for (int f = 0; f < nf; ++f)
+        if (plans[f]->ba.m != m) { set_error("mixed section orders in one sweep"); return 1; }
+#define MM_FWD(M_, NF_, NIN_)                                                     \
+    {                                                                             \
+        SweepArgs<M_, NF_> A;                                                     \
+        fill_common<M_, NF_>(A, g, plans, in, nin, out, nf, pro, epi, pad);       \
+        return launch_sweep<M_, NF_, NIN_, +1>(c, A, "sweep_fwd_m" #M_ "_f" #NF_ "_i" #NIN_); \
+    }
+    if (m == 2 && nf == 1 && nin == 1) MM_FWD(2, 1, 1)
+    if (m == 2 && nf == 2 && nin == 1) MM_FWD(2, 2, 1)
+    if (m == 2 && nf == 2 && nin == 2) MM_FWD(2, 2, 2)
+    if (m == 2 && nf == 4 && nin == 1) MM_FWD(2, 4, 1)
+    if (m == 4 && nf == 1 && nin == 1) MM_FWD(4, 1, 1)
+#undef MM_FWD
+    set_error("no forward sweep instantiation for order %d, %d filters, %d inputs", m, nf, nin);
+    return 1;
+}
+
+int sweep_bwd(mm_ctx* c, const mm_geom* g, int nf, const FilterPlan* const* plans, const float* const* in,
+              float* const* out, int nout, const Epi& epi, int pad) {
+    const int m = plans[0]->ba.m;
+#define MM_BWD(M_, NF_)                                                           \
+    {                                                                             \
+        SweepArgs<M_, NF_> A;                                                     \
+        fill_common<M_, NF_>(A, g, plans, in, nf, out, nout, epi.auxp, epi, pad); \
+        return launch_sweep<M_, NF_, NF_, -1>(c, A, "sweep_bwd_m" #M_ "_f" #NF_); \
+    }
+    if (m == 2 && nf == 1) MM_BWD(2, 1)
+    if (m == 2 && nf == 2) MM_BWD(2, 2)
+    if (m == 2 && nf == 4) MM_BWD(2, 4)
+    if (m == 4 && nf == 1) MM_BWD(4, 1)
+#undef MM_BWD
+    set_error("no backward sweep instantiation for order %d, %d filters", m, nf);
+    return 1;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// plans
+// ---------------------------------------------------------------------------------------------------
+const FilterPlan* plan_butter(mm_ctx* c, int order, BType bt, double w0, double w1) {
+    Ba ba;
+    memset(&ba, 0, sizeof(ba));
+    double wn[2] = {w0, w1};
+    if (!butter(order, bt, wn, &ba)) { set_error("butter(%d, [%g, %g], type %d): bad critical frequencies", order, w0, w1, (int)bt); return nullptr; }
+    return get_plan(c, ba);
+}
+
+int get_bufs(mm_ctx* c, const mm_geom* g, Bufs* B) {
+    const size_t fl = (size_t)g->tracks * g->channels * (size_t)g->stride;
+    for (int i = 0; i < 4; ++i) MM_TRY(arena(c, SL_E0 + i, fl, &B->E[i]));
+    for (int i = 0; i < 5; ++i) MM_TRY(arena(c, SL_T0 + i, fl, &B->T[i]));
+    return 0;
+}
+
+int check_geom(const mm_geom* g) {
+    if (!g || g->n <= 0 || g->tracks <= 0 || (g->channels != 1 && g->channels != 2) || g->sr <= 0) {
+        set_error("bad geometry (n > 0, tracks > 0, channels in {1,2}, sr > 0 required)");
+        return 1;
+    }
+    if (g->stride < mm_row_stride(g->n) || (g->stride & 3)) { set_error("stride must be >= mm_row_stride(n) and a multiple of 4"); return 1; }
+    return 0;
+}
+
+static int need_len(const mm_geom* g, int pad, const char* what) {
+    if (g->n <= pad) {
+        set_error("%s: %lld frames is not longer than scipy filtfilt's padlen %d (the reference would degrade to lfilter; use mm_dev_iir)",
+                  what, (long long)g->n, pad);
+        return 1;
+    }
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// reductions / scalars
+// ---------------------------------------------------------------------------------------------------
+int run_row_stats(mm_ctx* c, const mm_geom* g, const float* in, RowStats** st_out) {
+    const int rows = g->tracks * g->channels;
+    RowStats* st;
+    MM_TRY(arena(c, SL_ROWSTATS, (size_t)rows, &st));
+    {
+        KernelScope ks(c, "row_stats_init");
+        row_stats_init_kernel<<<(rows + 255) / 256, 256, 0, c->stream>>>(st, rows);
+    }
+    dim3 grid((unsigned)((g->n + kPwFramesPerBlock - 1) / kPwFramesPerBlock), (unsigned)rows);
+    {
+        KernelScope ks(c, "row_stats");
+        row_stats_kernel<<<grid, kPwThreads, 0, c->stream>>>(in, g->n, g->stride, st);
+    }
+    MM_CUDA(cudaGetLastError());
+    *st_out = st;
+    return 0;
+}
+
+int run_in_scalars(mm_ctx* c, const mm_geom* g, const RowStats* st, int use_dc, int use_guard, double headroom_db,
+                   double* sub, double* mul, double* peak_track, double* mean_row) {
+    InScalarArgs A;
+    A.st = st; A.n = g->n; A.tracks = g->tracks; A.channels = g->channels;
+    A.use_dc = use_dc; A.use_guard = use_guard;
+    A.limit = (float)std::pow(10.0, -headroom_db / 20.0);
+    A.sub = sub; A.mul = mul; A.peak_track = peak_track; A.mean_row = mean_row;
+    KernelScope ks(c, "in_scalars");
+    in_scalars_kernel<<<(g->tracks + 127) / 128, 128, 0, c->stream>>>(A);
+    MM_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int run_pointwise(mm_ctx* c, const mm_geom* g, PwArgs& A, const char* name) {
+    A.n = g->n; A.stride = g->stride; A.tracks = g->tracks; A.channels = g->channels;
+    dim3 grid((unsigned)((g->n + kPwFramesPerBlock - 1) / kPwFramesPerBlock), (unsigned)g->tracks);
+    KernelScope ks(c, name);
+    pointwise_kernel<<<grid, kPwThreads, 0, c->stream>>>(A);
+    MM_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int run_out_scalars(mm_ctx* c, const OutScalarArgs& O) {
+    KernelScope ks(c, "out_scalars");
+    out_scalars_kernel<<<(O.tracks + 127) / 128, 128, 0, c->stream>>>(O);
+    MM_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int run_quantize(mm_ctx* c, const QuantArgs& Q) {
+    dim3 grid((unsigned)((Q.n + kPwThreads - 1) / kPwThreads), (unsigned)Q.tracks);
+    KernelScope ks(c, "quantize_int16");
+    quantize_kernel<<<grid, kPwThreads, 0, c->stream>>>(Q);
+    MM_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int run_layout(mm_ctx* c, const mm_geom* g, const float* interleaved, float* planar, int dir) {
+    dim3 grid((unsigned)((g->n + kPwThreads - 1) / kPwThreads), (unsigned)g->tracks);
+    KernelScope ks(c, dir ? "interleave" : "deinterleave");
+    if (dir) interleave_kernel<<<grid, kPwThreads, 0, c->stream>>>(planar, const_cast<float*>(interleaved), g->n, g->stride, g->channels);
+    else deinterleave_kernel<<<grid, kPwThreads, 0, c->stream>>>(interleaved, planar, g->n, g->stride, g->channels);
+    MM_CUDA(cudaGetLastError());
+    return 0;
+}
+
+void fill_dyn(DynParams* d, double knee_db, const double* band_ratios, double max_upward_boost_db) {
+    static const double cfg[4][4] = {{-7.2, 1.0, -7.2, 1.5}, {-18.5, 2.2, -18.5, 1.8}, {-17.0, 1.55, -17.0, 1.65}, {-15.0, 1.35, -15.0, 1.2}};
+    memset(d, 0, sizeof(*d));
+    knee_db = std::max(0.0, knee_db);
+    for (int i = 0; i < 4; ++i) {
+        DynBand& b = d->band[i];
+        const double lim_db = cfg[i][0], thr_db = cfg[i][2], gain = cfg[i][3];
+        const double ratio = band_ratios ? band_ratios[i] : cfg[i][1];
+        b.thr_db = thr_db;
+        b.thr = std::pow(10.0, thr_db / 20.0);
+        b.ratio = ratio;
+        b.max_boost_db = std::max(0.1, max_upward_boost_db);
+        b.lower = b.thr * std::pow(10.0, -knee_db / 20.0);
+        b.upper = b.thr * std::pow(10.0, knee_db / 20.0);
+        b.slope = (b.upper > b.lower) ? (b.thr + (b.upper - b.thr) / ratio - b.lower) / (b.upper - b.lower) : 1.0;
+        b.lim = (float)std::pow(10.0, lim_db / 20.0);
+        b.gain = (float)gain;
+        if (ratio <= 0.0 || ratio == 1.0) b.mode = 0;
+        else if (ratio < 1.0) b.mode = 3;
+        else if (knee_db < 0.5) b.mode = 1;
+        else b.mode = 2;
+    }
+    const double thr = std::pow(10.0, -2.5 / 20.0), ceil_ = std::pow(10.0, -0.3 / 20.0);
+    d->max_thr = (float)thr;
+    d->max_ceil = (float)ceil_;
+    d->max_num = (float)(ceil_ - thr);
+    d->max_den = (float)(1.0 - thr);
+    d->tp_lim = (float)std::pow(10.0, -1.5 / 20.0);
+    d->par_mix = nullptr;
+    fill_parallel(d, 8.0, -20.0);
+}
+
+void fill_parallel(DynParams* d, double ratio, double threshold_db) {
+    const double thr = std::pow(10.0, threshold_db / 20.0);
+    const double lower = thr * std::pow(10.0, -6.0 / 20.0), upper = thr * std::pow(10.0, 6.0 / 20.0);
+    d->par_thr = (float)thr;
+    d->par_lower = (float)lower;
+    d->par_upper = (float)upper;
+    d->par_slope = (float)((thr + (upper - thr) / ratio - lower) / (upper - lower));
+    d->par_ratio = (float)ratio;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// stages
+// ---------------------------------------------------------------------------------------------------
+// apply_target_curve, IIR path (backend/app/pipeline.py:238-273, designs :170-184)
+int st_target_curve(mm_ctx* c, const mm_geom* g, const float* in, float* out, const Pro& pro) {
+    const double nyq = g->sr / 2.0;
+    const FilterPlan* hp = plan_butter(c, 2, kHigh, std::min(40.0 / nyq, 0.99), 0);
+    const FilterPlan* lp = plan_butter(c, 2, kLow, std::min(18000.0 / nyq, 0.99), 0);
+    const double fp = std::min(3000.0 / nyq, 0.99), fm = std::min(300.0 / nyq, 0.99);
+    const FilterPlan* pres = plan_butter(c, 1, kBand, fp * 0.7, fp * 1.3);
+    const FilterPlan* mud = plan_butter(c, 1, kBand, fm * 0.7, fm * 1.3);
+    if (!hp || !lp || !pres || !mud) return 1;
+    MM_TRY(need_len(g, 9, "apply_target_curve"));
+    Bufs B;
+    MM_TRY(get_bufs(c, g, &B));
+    const double gp = std::pow(10.0, 0.35 / 20.0), gm = std::pow(10.0, -0.25 / 20.0);
+    Pro none;
+    Epi store;
+    {
+        const FilterPlan* p[1] = {hp};
+        const float* i1[1] = {in};
+        float* o1[1] = {B.E[0]};
+        MM_TRY(sweep_fwd(c, g, 1, 1, p, i1, o1, pro, 9));
+        const float* i2[1] = {B.E[0]};
+        float* o2[1] = {B.T[0]};
+        MM_TRY(sweep_bwd(c, g, 1, p, i2, o2, 1, store, 9));
+    }
+    {
+        const FilterPlan* p[1] = {lp};
+        const float* i1[1] = {B.T[0]};
+        float* o1[1] = {B.E[0]};
+        MM_TRY(sweep_fwd(c, g, 1, 1, p, i1, o1, none, 9));
+        const float* i2[1] = {B.E[0]};
+        float* o2[1] = {B.T[0]};
+        MM_TRY(sweep_bwd(c, g, 1, p, i2, o2, 1, store, 9));
+    }
+    {
+        const FilterPlan* p[2] = {pres, mud};
+        const float* i1[1] = {B.T[0]};
+        float* o1[2] = {B.E[0], B.E[1]};
+        MM_TRY(sweep_fwd(c, g, 2, 1, p, i1, o1, none, 9));
+        const float* i2[2] = {B.E[0], B.E[1]};
+        float* o2[1] = {out};
+        Epi e;
+        e.mode = EPI_COMBINE;
+        e.aux0 = B.T[0];
+        e.w[0] = gp - 1.0;
+        e.w[1] = gm - 1.0;
+        MM_TRY(sweep_bwd(c, g, 2, p, i2, o2, 1, e, 9));
+    }
+    return 0;
+}
+
+// apply_dynamics = apply_multiband_dynamics (numpy branch) + apply_maximizer + hard limiter
+// (backend/app/pipeline.py:610-641, :414-481, :333-364)
+int st_dynamics(mm_ctx* c, const mm_geom* g, const float* in, float* out, double knee_db, const double* crossovers_hz,
+                const double* band_ratios, double max_upward_boost_db, const double* par_mix_rows, float* peak) {
+    double cross[3] = {214.0, 3500.0, 10000.0};
+    if (crossovers_hz) {
+        double t[3];
+        for (int i = 0; i < 3; ++i) t[i] = std::min(std::max(crossovers_hz[i], 20.0), 20000.0);
+        if (!(t[0] >= t[1] || t[1] >= t[2])) { cross[0] = t[0]; cross[1] = t[1]; cross[2] = t[2]; }
+    }
+    const double nyq = g->sr / 2.0;
+    double f[3];
+    for (int i = 0; i < 3; ++i) f[i] = std::min(cross[i] / nyq, 0.99);
+    const FilterPlan* lp1 = plan_butter(c, 2, kLow, f[0], 0);
+    const FilterPlan* hp1 = plan_butter(c, 2, kHigh, f[0], 0);
+    const FilterPlan* lp2 = plan_butter(c, 2, kLow, f[1], 0);
+    const FilterPlan* hp2 = plan_butter(c, 2, kHigh, f[1], 0);
+    const FilterPlan* lp3 = plan_butter(c, 2, kLow, f[2], 0);
+    const FilterPlan* hp3 = plan_butter(c, 2, kHigh, f[2], 0);
+    if (!lp1 || !hp1 || !lp2 || !hp2 || !lp3 || !hp3) return 1;
+    MM_TRY(need_len(g, 9, "apply_dynamics"));
+    Bufs B;
+    MM_TRY(get_bufs(c, g, &B));
+    Pro none;
+    Epi store;
+    {
+        const FilterPlan* p[4] = {lp1, hp1, hp2, hp3};
+        const float* i1[1] = {in};
+        float* o1[4] = {B.E[0], B.E[1], B.E[2], B.E[3]};
+        MM_TRY(sweep_fwd(c, g, 4, 1, p, i1, o1, none, 9));
+        const float* i2[4] = {B.E[0], B.E[1], B.E[2], B.E[3]};
+        float* o2[4] = {B.T[1], B.T[2], B.T[3], B.T[4]};
+        MM_TRY(sweep_bwd(c, g, 4, p, i2, o2, 4, store, 9));
+    }
+    {
+        const FilterPlan* p[2] = {lp2, lp3};
+        const float* i1[2] = {B.T[2], B.T[3]};
+        float* o1[2] = {B.E[0], B.E[1]};
+        MM_TRY(sweep_fwd(c, g, 2, 2, p, i1, o1, none, 9));
+        DynParams d;
+        fill_dyn(&d, knee_db, band_ratios, max_upward_boost_db);
+        d.par_mix = par_mix_rows;
+        Epi e;
+        e.mode = EPI_DYNAMICS;
+        e.aux0 = B.T[1];
+        e.aux1 = B.T[4];
+        e.dyn = &d;
+        e.peak = peak;
+        const float* i2[2] = {B.E[0], B.E[1]};
+        float* o2[1] = {out};
+        MM_TRY(sweep_bwd(c, g, 2, p, i2, o2, 1, e, 9));
+    }
+    return 0;
+}
+
+// pyloudnorm.Meter(sr).integrated_loudness (+ the gain normalize_lufs derives from it,
+// backend/app/pipeline.py:644-664)
+int st_lufs(mm_ctx* c, const mm_geom* g, const float* in, const Pro& pro, double* lufs_dev, const double* target_dev,
+            double* gain_row, double* gain_db) {
+    const LufsPlan* lp;
+    MM_TRY(get_lufs_plan(c, g->n, g->sr, &lp));
+    const int rows = g->tracks * g->channels;
+    double* segsum;
+    MM_TRY(arena(c, SL_SEGSUM, (size_t)rows * (size_t)std::max(lp->nseg, 1), &segsum));
+    if (lp->valid) {
+        const FilterPlan* k0 = get_plan(c, k_weighting_stage(0, (double)g->sr));
+        const FilterPlan* k1 = get_plan(c, k_weighting_stage(1, (double)g->sr));
+        if (!k0 || !k1) return 1;
+        MM_CUDA(cudaMemsetAsync(segsum, 0, (size_t)rows * lp->nseg * sizeof(double), c->stream));
+        LufsArgs A;
+        memset(&A, 0, sizeof(A));
+        fill_filter<2>(A.f[0], k0);
+        fill_filter<2>(A.f[1], k1);
+        A.tab[0] = k0->dev; A.tab[1] = k1->dev;
+        A.W[0] = k0->tabs.W; A.W[1] = k1->tabs.W;
+        A.in = in; A.n = g->n; A.stride = g->stride; A.rows = rows; A.ntiles = lp->ntiles; A.channels = g->channels;
+        A.pro_mode = pro.mode; A.pro_sub = pro.sub; A.pro_mul = pro.mul;
+        A.bnd = lp->bnd; A.nseg = lp->nseg; A.tile_seg = lp->tile_seg; A.segsum = segsum;
+        const size_t items = (size_t)rows * (size_t)lp->ntiles;
+        MM_TRY(ensure_carry(c, 2 * items));
+        A.agg = c->agg; A.flag = c->flag; A.epoch = ++c->epoch;
+        A.ticket = c->ticket; A.ticket_base = c->ticket_total; c->ticket_total += (unsigned)items;
+        A.err = c->err;
+        {
+            KernelScope ks(c, "lufs_kweight_blocks");
+            lufs_kernel<<<(unsigned)items, kT, 0, c->stream>>>(A);
+        }
+        MM_CUDA(cudaGetLastError());
+    }
+    GateArgs G;
+    memset(&G, 0, sizeof(G));
+    G.segsum = segsum; G.nseg = std::max(lp->nseg, 1); G.nblocks = lp->nblocks; G.channels = g->channels; G.tracks = g->tracks;
+    G.blk_lo = lp->blk_lo; G.blk_hi = lp->blk_hi; G.scale = lp->scale; G.valid = lp->valid;
+    G.lufs = lufs_dev; G.target = target_dev; G.gain_row = gain_row; G.gain_db = gain_db;
+    {
+        KernelScope ks(c, "lufs_gate");
+        gate_kernel<<<g->tracks, 256, 0, c->stream>>>(G);
+    }
+    MM_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// apply_final_spectral_balance (backend/app/pipeline.py:576-607); `pro` scales the input first
+// (normalize_lufs's gain folds in here at zero traffic)
+int st_final_balance(mm_ctx* c, const mm_geom* g, const float* in, float* out, const Pro& pro, float* peak) {
+    const double nyq = g->sr / 2.0;
+    const double f3 = std::min(3000.0 / nyq, 0.99), f8 = std::min(8000.0 / nyq, 0.99);
+    const FilterPlan* p3 = plan_butter(c, 1, kBand, f3 * 0.8, f3 * 1.2);
+    const FilterPlan* p16 = plan_butter(c, 2, kHigh, std::min(16000.0 / nyq, 0.99), 0);
+    const FilterPlan* plo = plan_butter(c, 2, kLow, std::min(180.0 / nyq, 0.99), 0);
+    const FilterPlan* p8 = plan_butter(c, 1, kBand, f8 * 0.8, f8 * 1.2);
+    if (!p3 || !p16 || !plo || !p8) return 1;
+    MM_TRY(need_len(g, 9, "apply_final_spectral_balance"));
+    Bufs B;
+    MM_TRY(get_bufs(c, g, &B));
+    const FilterPlan* p[4] = {p3, p16, plo, p8};
+    const float* i1[1] = {in};
+    float* o1[4] = {B.E[0], B.E[1], B.E[2], B.E[3]};
+    MM_TRY(sweep_fwd(c, g, 4, 1, p, i1, o1, pro, 9));
+    Epi e;
+    e.mode = EPI_COMBINE;
+    e.aux0 = in;
+    e.auxp = pro;
+    e.aux_pro = pro.mode != PRO_NONE;
+    e.w[0] = (std::pow(10.0, -0.5 / 20.0) - 1.0) * 0.25;
+    e.w[1] = (std::pow(10.0, -0.3 / 20.0) - 1.0) * 0.25;
+    e.w[2] = (std::pow(10.0, 0.3 / 20.0) - 1.0) * 0.25;
+    e.w[3] = (std::pow(10.0, 0.2 / 20.0) - 1.0) * 0.25;
+    e.trim = std::pow(10.0, 0.5 / 20.0);
+    e.peak = peak;
+    const float* i2[4] = {B.E[0], B.E[1], B.E[2], B.E[3]};
+    float* o2[1] = {out};
+    MM_TRY(sweep_bwd(c, g, 4, p, i2, o2, 1, e, 9));
+    return 0;
+}
+
+// one zero-phase section with "x + w * filtered" recombination: a style-EQ band
+// (pipeline.py:1427-1431), the exciter's high-pass (:1303-1315), or plain filtfilt (w_x = 0, w = 1)
+int st_filtfilt_combine(mm_ctx* c, const mm_geom* g, const FilterPlan* plan, const float* in, float* out, const Epi& epi_in,
+                        const Pro& pro) {
+    MM_TRY(need_len(g, plan->pad, "zero-phase section"));
+    Bufs B;
+    MM_TRY(get_bufs(c, g, &B));
+    const FilterPlan* p[1] = {plan};
+    const float* i1[1] = {in};
+    float* o1[1] = {B.E[0]};
+    MM_TRY(sweep_fwd(c, g, 1, 1, p, i1, o1, pro, plan->pad));
+    const float* i2[1] = {B.E[0]};
+    float* o2[1] = {out};
+    MM_TRY(sweep_bwd(c, g, 1, p, i2, o2, 1, epi_in, plan->pad));
+    return 0;
+}
+
+// apply_style_eq (backend/app/pipeline.py:1401-1434)
+int st_style_eq(mm_ctx* c, const mm_geom* g, const float* in, float* out, const double* gain_db, float* peak, int* fired,
+                int reset_peak) {
+    const double nyq = g->sr / 2.0;
+    const double lo[5] = {30.0, 90.0, 700.0, 2800.0, 10000.0};
+    const double hi[5] = {90.0, 280.0, 2800.0, 9000.0, std::min(g->sr * 0.46, 18000.0)};
+    int last = -1;
+    for (int b = 0; b < 5; ++b) {
+        if (std::fabs(gain_db[b]) < 0.05) continue;
+        const double l = std::min(lo[b] / nyq, 0.98), h = std::min(hi[b] / nyq, 0.98);
+        if (l >= h) continue;
+        last = b;
+    }
+    const float* cur = in;
+    int n_fired = 0;
+    for (int b = 0; b < 5; ++b) {
+        if (std::fabs(gain_db[b]) < 0.05) continue;
+        const double l = std::min(lo[b] / nyq, 0.98), h = std::min(hi[b] / nyq, 0.98);
+        if (l >= h) continue;
+        const FilterPlan* p = plan_butter(c, 1, kBand, l, h);
+        if (!p) return 1;
+        Epi e;
+        e.mode = EPI_COMBINE;
+        e.aux0 = cur;
+        e.w[0] = std::pow(10.0, gain_db[b] / 20.0) - 1.0;
+        e.peak = (b == last) ? peak : nullptr;
+        if (e.peak && reset_peak) MM_CUDA(cudaMemsetAsync(peak, 0, (size_t)g->tracks * sizeof(float), c->stream));
+        Pro none;
+        MM_TRY(st_filtfilt_combine(c, g, p, cur, out, e, none));
+        cur = out;
+        ++n_fired;
+    }
+    if (fired) *fired = n_fired;
+    if (n_fired == 0 && in != out) {
+        MM_CUDA(cudaMemcpyAsync(out, in, (size_t)g->tracks * g->channels * g->stride * sizeof(float), cudaMemcpyDeviceToDevice, c->stream));
+    }
+    return 0;
+}
+
+// apply_harmonic_exciter, oversample == 1 (backend/app/pipeline.py:1267-1326)
+int st_exciter(mm_ctx* c, const mm_geom* g, const float* in, float* out, double exciter_db, int mode, float* peak) {
+    const double nyq = g->sr / 2.0;
+    const FilterPlan* p = plan_butter(c, 2, kHigh, std::min(6000.0 / nyq, 0.97), 0);
+    if (!p) return 1;
+    Epi e;
+    e.mode = EPI_EXCITER;
+    e.aux0 = in;
+    e.exc_gain = std::pow(10.0, exciter_db / 20.0) - 1.0;
+    e.exc_mode = (mode >= 0 && mode <= 4) ? mode : 0;
+    e.exc_k = (e.exc_mode == 0) ? 2.5 : 2.0;
+    e.peak = peak;
+    Pro none;
+    return st_filtfilt_combine(c, g, p, in, out, e, none);
+}
+
+}  // namespace mm

@@ -1,0 +1,71 @@
+// Internal (C++) stage interface shared by stages.cu, analyzers.cu and capi.cu.
+#pragma once
+#include "common.cuh"
+#include "context.h"
+#include "pw_args.h"
+
+namespace mm {
+
+
+struct Pro {                     // prologue applied while loading x-domain samples
+    int mode = PRO_NONE;
+    const double* sub = nullptr;
+    const double* mul = nullptr;
+};
+
+struct Epi {                     // epilogue of a backward sweep
+    int mode = EPI_STORE;
+    const float* aux0 = nullptr;
+    const float* aux1 = nullptr;
+    Pro auxp;                    // prologue applied to aux0 when aux_pro != 0
+    int aux_pro = 0;
+    double w[4] = {0, 0, 0, 0};
+    double wc = 1.0, trim = 1.0;
+    const DynParams* dyn = nullptr;
+    double exc_gain = 0, exc_k = 2.5;
+    int exc_mode = 0;
+    float* peak = nullptr;
+};
+
+struct Bufs { float* E[4]; float* T[5]; };
+
+int check_geom(const mm_geom* g);
+int get_bufs(mm_ctx* c, const mm_geom* g, Bufs* B);
+const FilterPlan* plan_butter(mm_ctx* c, int order, BType bt, double w0, double w1);
+
+int sweep_fwd(mm_ctx* c, const mm_geom* g, int nf, int nin, const FilterPlan* const* plans, const float* const* in,
+              float* const* out, const Pro& pro, int pad);
+int sweep_bwd(mm_ctx* c, const mm_geom* g, int nf, const FilterPlan* const* plans, const float* const* in,
+              float* const* out, int nout, const Epi& epi, int pad);
+
+int run_row_stats(mm_ctx* c, const mm_geom* g, const float* in, RowStats** st_out);
+int run_in_scalars(mm_ctx* c, const mm_geom* g, const RowStats* st, int use_dc, int use_guard, double headroom_db,
+                   double* sub, double* mul, double* peak_track, double* mean_row);
+int run_pointwise(mm_ctx* c, const mm_geom* g, PwArgs& A, const char* name);
+int run_out_scalars(mm_ctx* c, const OutScalarArgs& O);
+int run_quantize(mm_ctx* c, const QuantArgs& Q);
+// dir 0: interleaved -> planar, 1: planar -> interleaved
+int run_layout(mm_ctx* c, const mm_geom* g, const float* interleaved, float* planar, int dir);
+void fill_dyn(DynParams* d, double knee_db, const double* band_ratios, double max_upward_boost_db);
+void fill_parallel(DynParams* d, double ratio, double threshold_db);
+
+int st_target_curve(mm_ctx* c, const mm_geom* g, const float* in, float* out, const Pro& pro);
+int st_dynamics(mm_ctx* c, const mm_geom* g, const float* in, float* out, double knee_db, const double* crossovers_hz,
+                const double* band_ratios, double max_upward_boost_db, const double* par_mix_rows, float* peak);
+int st_lufs(mm_ctx* c, const mm_geom* g, const float* in, const Pro& pro, double* lufs_dev, const double* target_dev,
+            double* gain_row, double* gain_db);
+int st_final_balance(mm_ctx* c, const mm_geom* g, const float* in, float* out, const Pro& pro, float* peak);
+int st_filtfilt_combine(mm_ctx* c, const mm_geom* g, const FilterPlan* plan, const float* in, float* out, const Epi& epi,
+                        const Pro& pro);
+int st_style_eq(mm_ctx* c, const mm_geom* g, const float* in, float* out, const double* gain_db, float* peak, int* fired,
+                int reset_peak);
+int st_exciter(mm_ctx* c, const mm_geom* g, const float* in, float* out, double exciter_db, int mode, float* peak);
+
+// analyzers.cu / deesser.cu
+int st_deesser(mm_ctx* c, const mm_geom* g, const float* in, float* out, double threshold_db, double ratio, double freq_lo,
+               double freq_hi, double attack_ms, double release_ms);
+int st_true_peak(mm_ctx* c, const mm_geom* g, const float* in, double* tp_dev);
+int st_spectrum_bars(mm_ctx* c, const mm_geom* g, const float* in, int view, double* bars_dev);
+int st_correlation(mm_ctx* c, const mm_geom* g, const float* in, double* corr_dev, double* peak_dev);
+
+}  // namespace mm

@@ -1,0 +1,235 @@
+"""Host side of the CUDA path: a context, device-resident planar batches, stage calls.
+
+PyTorch is used for device memory and streams only; every computation is a call into
+``libmm_b200.so`` through the C ABI (``include/mm_b200.h``).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import threading
+
+import numpy as np
+
+from . import _lib
+from ._lib import Geom, Style, TrackStats, MMError  # noqa: F401  (re-exported)
+
+
+def _torch():
+    import torch
+    return torch
+
+
+class Batch:
+    """Planar device batch: rows ``[track*channels + c]`` of ``stride`` floats, sample i at ``MM_LEAD + i``."""
+
+    def __init__(self, tensor, tracks, channels, n, sr):
+        self.t = tensor                       # torch float32 (rows, stride)
+        self.tracks, self.channels, self.n, self.sr = int(tracks), int(channels), int(n), int(sr)
+
+    @property
+    def stride(self):
+        return int(self.t.shape[1])
+
+    @property
+    def geom(self):
+        return Geom(self.n, self.stride, self.tracks, self.channels, self.sr, 0)
+
+    @property
+    def ptr(self):
+        return C.c_void_p(self.t.data_ptr())
+
+    def live(self):
+        """View of the samples only: (rows, n)."""
+        return self.t[:, _lib.MM_LEAD:_lib.MM_LEAD + self.n]
+
+
+class Engine:
+    """One CUDA context (stream + workspace) on one device.  Not shared between threads: use
+    :func:`get_engine` for a per-thread instance."""
+
+    def __init__(self, device: int = 0):
+        torch = _torch()
+        if not torch.cuda.is_available():
+            raise MMError("no CUDA device: mm_b200 has no CPU fallback")
+        self.lib = _lib.load()
+        self.device = int(device)
+        self.tdev = torch.device("cuda", self.device)
+        self.stream = torch.cuda.Stream(device=self.tdev)
+        ctx = C.c_void_p()
+        _lib.check(self.lib.mm_ctx_create(self.device, C.c_void_p(self.stream.cuda_stream), C.byref(ctx)))
+        self.ctx = ctx
+
+    def close(self):
+        if getattr(self, "ctx", None):
+            self.lib.mm_ctx_destroy(self.ctx)
+            self.ctx = None
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- memory ---------------------------------------------------------------------------------
+    def row_stride(self, n: int) -> int:
+        return int(self.lib.mm_row_stride(int(n)))
+
+    def empty(self, tracks, channels, n, sr) -> Batch:
+        torch = _torch()
+        with torch.cuda.stream(self.stream):
+            t = torch.empty((tracks * channels, self.row_stride(n)), dtype=torch.float32, device=self.tdev)
+        return Batch(t, tracks, channels, n, sr)
+
+    def like(self, b: Batch) -> Batch:
+        return self.empty(b.tracks, b.channels, b.n, b.sr)
+
+    def upload(self, tracks_np, sr) -> Batch:
+        """list of (n,) / (n, ch) float32 arrays of identical shape (or one 3-D array) -> Batch."""
+        torch = _torch()
+        arr = np.stack([np.asarray(a, dtype=np.float32).reshape(len(a), -1) for a in tracks_np], axis=0)
+        tracks, n, ch = arr.shape
+        b = self.empty(tracks, ch, n, sr)
+        with torch.cuda.stream(self.stream):
+            il = torch.from_numpy(np.ascontiguousarray(arr)).to(self.tdev, non_blocking=False)
+            g = b.geom
+            _lib.check(self.lib.mm_dev_deinterleave(self.ctx, C.byref(g), C.c_void_p(il.data_ptr()), b.ptr))
+            self.sync()
+        return b
+
+    def download(self, b: Batch) -> np.ndarray:
+        """Batch -> float32 array (tracks, n, channels)."""
+        torch = _torch()
+        with torch.cuda.stream(self.stream):
+            il = torch.empty((b.tracks, b.n, b.channels), dtype=torch.float32, device=self.tdev)
+            g = b.geom
+            _lib.check(self.lib.mm_dev_interleave(self.ctx, C.byref(g), b.ptr, C.c_void_p(il.data_ptr())))
+            self.sync()
+            return il.cpu().numpy()
+
+    def sync(self):
+        _lib.check(self.lib.mm_ctx_sync(self.ctx))
+
+    # ---- generic stage call -----------------------------------------------------------------------
+    def stage(self, name: str, src: Batch, *args, out: Batch | None = None) -> Batch:
+        """Call ``mm_dev_<name>(ctx, geom, in, out, *args)``; returns the output batch."""
+        dst = out if out is not None else self.like(src)
+        g = src.geom
+        fn = getattr(self.lib, "mm_dev_" + name)
+        _lib.check(fn(self.ctx, C.byref(g), src.ptr, dst.ptr, *args))
+        return dst
+
+    # ---- reductions / analyzers -------------------------------------------------------------------
+    def _doubles(self, count):
+        torch = _torch()
+        with torch.cuda.stream(self.stream):
+            return torch.empty(count, dtype=torch.float64, device=self.tdev)
+
+    def _to_host(self, t):
+        self.sync()
+        with _torch().cuda.stream(self.stream):
+            return t.cpu().numpy()
+
+    def measure_lufs(self, b: Batch) -> np.ndarray:
+        out = self._doubles(b.tracks)
+        g = b.geom
+        _lib.check(self.lib.mm_dev_measure_lufs(self.ctx, C.byref(g), b.ptr, C.c_void_p(out.data_ptr())))
+        return self._to_host(out)
+
+    def true_peak(self, b: Batch) -> np.ndarray:
+        out = self._doubles(b.tracks)
+        g = b.geom
+        _lib.check(self.lib.mm_dev_true_peak(self.ctx, C.byref(g), b.ptr, C.c_void_p(out.data_ptr())))
+        return self._to_host(out)
+
+    def spectrum_bars(self, b: Batch, view: int = 0) -> np.ndarray:
+        out = self._doubles(b.tracks * 64)
+        g = b.geom
+        _lib.check(self.lib.mm_dev_spectrum_bars(self.ctx, C.byref(g), b.ptr, int(view), C.c_void_p(out.data_ptr())))
+        return self._to_host(out).reshape(b.tracks, 64)
+
+    def stereo_correlation(self, b: Batch):
+        corr, peak = self._doubles(b.tracks), self._doubles(b.tracks)
+        g = b.geom
+        _lib.check(self.lib.mm_dev_stereo_correlation(self.ctx, C.byref(g), b.ptr, C.c_void_p(corr.data_ptr()),
+                                                      C.c_void_p(peak.data_ptr())))
+        return self._to_host(corr), self._to_host(peak)
+
+    def quantize_int16(self, b: Batch, noise: np.ndarray | None = None, seed: int = 0) -> np.ndarray:
+        """-> int16 (tracks, n, channels); ``noise`` float32 of that shape selects the bit-exact mode."""
+        torch = _torch()
+        with torch.cuda.stream(self.stream):
+            pcm = torch.empty((b.tracks, b.n, b.channels), dtype=torch.int16, device=self.tdev)
+            nz = None
+            if noise is not None:
+                nz = torch.from_numpy(np.ascontiguousarray(noise, dtype=np.float32).reshape(b.tracks, b.n, b.channels)).to(self.tdev)
+            g = b.geom
+            _lib.check(self.lib.mm_dev_quantize_int16(self.ctx, C.byref(g), b.ptr, C.c_void_p(pcm.data_ptr()),
+                                                      C.c_void_p(nz.data_ptr()) if nz is not None else None, int(seed)))
+            self.sync()
+            return pcm.cpu().numpy()
+
+    # ---- whole chains -----------------------------------------------------------------------------
+    def master(self, src: Batch, chain: int, styles, *, out: Batch | None = None, want_int16=False, noise=None,
+               seed: int = 0, flags: int = 0, want_stats=True):
+        """Run ``mm_dev_master``.  ``styles``: list of ``Style`` (one per track).
+        Returns (out_batch, pcm_tensor_or_None, stats_array_or_None)."""
+        torch = _torch()
+        dst = out if out is not None else self.like(src)
+        arr = (Style * src.tracks)(*styles)
+        with torch.cuda.stream(self.stream):
+            pcm = torch.empty((src.tracks, src.n, src.channels), dtype=torch.int16, device=self.tdev) if want_int16 else None
+            nz = None
+            if noise is not None:
+                nz = noise if torch.is_tensor(noise) else torch.from_numpy(
+                    np.ascontiguousarray(noise, dtype=np.float32).reshape(src.tracks, src.n, src.channels)).to(self.tdev)
+            st = torch.empty(src.tracks * C.sizeof(TrackStats), dtype=torch.uint8, device=self.tdev) if want_stats else None
+            g = src.geom
+            _lib.check(self.lib.mm_dev_master(
+                self.ctx, C.byref(g), int(chain), arr, src.ptr, dst.ptr,
+                C.c_void_p(pcm.data_ptr()) if pcm is not None else None,
+                C.c_void_p(nz.data_ptr()) if nz is not None else None, int(seed),
+                C.c_void_p(st.data_ptr()) if st is not None else None, int(flags)))
+            stats = None
+            if st is not None:
+                self.sync()
+                raw = st.cpu().numpy().tobytes()
+                stats = (TrackStats * src.tracks).from_buffer_copy(raw)
+        return dst, pcm, stats
+
+    def kernel_times(self):
+        cap = 256
+        buf = (_lib.KTime * cap)()
+        cnt = C.c_int(0)
+        _lib.check(self.lib.mm_ctx_kernel_times(self.ctx, buf, cap, C.byref(cnt)))
+        return {buf[i].name.decode(): (buf[i].ms, buf[i].launches) for i in range(min(cnt.value, cap))}
+
+    def timing(self, on: bool):
+        _lib.check(self.lib.mm_ctx_timing(self.ctx, 1 if on else 0))
+
+    def launch_count(self) -> int:
+        return int(self.lib.mm_ctx_launch_count(self.ctx))
+
+
+_tls = threading.local()
+
+
+def get_engine(device: int = 0) -> Engine:
+    """Per-thread engine (the reference's job functions run in worker threads)."""
+    engines = getattr(_tls, "engines", None)
+    if engines is None:
+        engines = _tls.engines = {}
+    if device not in engines:
+        engines[device] = Engine(device)
+    return engines[device]
+
+
+def style_struct(cfg: dict, target_lufs: float) -> Style:
+    """STYLE_CONFIGS row (dict) + target -> C struct."""
+    s = Style()
+    s.target_lufs = float(target_lufs)
+    for i, k in enumerate(("sub", "bass", "mids", "presence", "air")):
+        s.eq_gain_db[i] = float(cfg.get(k, 0.0))
+    s.exciter_db = float(cfg.get("exciter_db", 0.0))
+    s.imager_width = float(cfg.get("imager_width", 1.0))
+    s.parallel_mix = float(cfg.get("parallel_mix", 0.0))
+    return s

@@ -1,0 +1,294 @@
+"""Drop-in for the reference's ``backend/app/pipeline.py`` function surface, hosted on the GPU.
+
+Same names, positional/keyword signatures, defaults, return shapes and error conventions as the
+reference functions cited in each docstring; arrays are numpy ``(n,)`` mono or ``(n, ch)``
+interleaved float32 at this edge, planar float32 on the device.  Every function launches CUDA
+kernels through ``libmm_b200.so``; there is no CPU implementation behind any of them.  The
+``*_batch`` helpers at the bottom are additive (the reference has no batching).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import io
+from typing import Callable, Optional
+
+import numpy as np
+
+from . import _lib, wavio
+from .engine import Batch, Engine, get_engine, style_struct
+
+# ---- presets / constants (backend/app/pipeline.py:56-110) -----------------------------------------
+PRESET_LUFS = {"spotify": -14.0, "youtube": -14.0, "apple": -16.0, "club": -9.0, "broadcast": -24.0}
+
+STYLE_CONFIGS = {
+    "standard": {"lufs": -14.0, "sub": 0.0, "bass": 0.0, "mids": 0.0, "presence": 0.0, "air": 0.0, "comp_mult": 1.0,
+                 "exciter_db": 0.0, "imager_width": 1.0, "parallel_mix": 0.0},
+    "edm": {"lufs": -9.0, "sub": 1.8, "bass": 0.9, "mids": -0.3, "presence": 0.6, "air": 0.9, "comp_mult": 1.3,
+            "exciter_db": 0.6, "imager_width": 1.25, "parallel_mix": 0.3},
+    "hiphop": {"lufs": -13.0, "sub": 1.4, "bass": 0.7, "mids": 0.5, "presence": 0.3, "air": 0.2, "comp_mult": 1.2,
+               "exciter_db": 0.3, "imager_width": 1.1, "parallel_mix": 0.35},
+    "classical": {"lufs": -18.0, "sub": -0.5, "bass": 0.0, "mids": 0.0, "presence": 0.3, "air": 0.6, "comp_mult": 0.45,
+                  "exciter_db": 0.0, "imager_width": 1.05, "parallel_mix": 0.0},
+    "podcast": {"lufs": -16.0, "sub": -1.2, "bass": -0.4, "mids": 0.9, "presence": 0.7, "air": 0.0, "comp_mult": 1.1,
+                "exciter_db": 0.0, "imager_width": 1.0, "parallel_mix": 0.2},
+    "lofi": {"lufs": -18.0, "sub": 0.4, "bass": 0.6, "mids": -0.6, "presence": -1.0, "air": -1.8, "comp_mult": 0.65,
+             "exciter_db": 0.2, "imager_width": 0.9, "parallel_mix": 0.0},
+    "house_basic": {"lufs": -10.0, "sub": 1.8, "bass": 0.9, "mids": -0.5, "presence": 0.8, "air": 1.0, "comp_mult": 1.35,
+                    "exciter_db": 0.8, "imager_width": 1.3, "parallel_mix": 0.3},
+    "dry_vocal": {"lufs": -14.0, "sub": 0.0, "bass": 0.0, "mids": 0.0, "presence": 0.0, "air": 0.0, "comp_mult": 1.0,
+                  "exciter_db": 0.0, "imager_width": 1.0, "parallel_mix": 0.0},
+}
+
+TRUE_PEAK_LIMIT_DB = -1.5
+MULTIBAND_CROSSOVERS_HZ = (214.0, 3500.0, 10000.0)
+MULTIBAND_CONFIG = [(-7.2, 1.0, -7.2, 1.5), (-18.5, 2.2, -18.5, 1.8), (-17.0, 1.55, -17.0, 1.65), (-15.0, 1.35, -15.0, 1.2)]
+DENOISE_PRESETS = {"light": 0.25, "medium": 0.5, "aggressive": 0.8}
+
+_EXCITER_MODES = {"warm": 0, "tape": 1, "tube": 2, "transistor": 3, "digital": 4}
+
+
+# ---- host <-> device edge -------------------------------------------------------------------------
+def _up(audio, sr, eng: Optional[Engine] = None):
+    eng = eng or get_engine()
+    a = np.asarray(audio)
+    mono = a.ndim == 1
+    a2 = np.ascontiguousarray(a.reshape(a.shape[0], -1), dtype=np.float32)
+    if a2.shape[1] not in (1, 2):
+        raise ValueError("mm_b200 supports mono or stereo audio")
+    return eng, eng.upload([a2], int(sr)), mono
+
+
+def _down(eng: Engine, b: Batch, mono: bool) -> np.ndarray:
+    out = eng.download(b)[0]
+    return out[:, 0] if mono else out
+
+
+def _stage(name, audio, sr, *args):
+    eng, b, mono = _up(audio, sr)
+    return _down(eng, eng.stage(name, b, *args, out=b), mono)
+
+
+# ---- stages -----------------------------------------------------------------------------------------
+def remove_dc_offset(audio: np.ndarray) -> np.ndarray:
+    """backend/app/pipeline.py:134-138."""
+    return _stage("remove_dc_offset", audio, 44100)
+
+
+def remove_intersample_peaks(audio: np.ndarray, headroom_db: float = 0.5) -> np.ndarray:
+    """backend/app/pipeline.py:141-149."""
+    return _stage("remove_intersample_peaks", audio, 44100, C.c_double(headroom_db))
+
+
+def apply_output_edge_fade_in(audio: np.ndarray, sr: int, fade_ms: float = 6.0) -> np.ndarray:
+    """backend/app/pipeline.py:152-167."""
+    if fade_ms <= 0 or sr <= 0 or np.size(audio) == 0:
+        return audio
+    return _stage("fade_in", audio, sr, C.c_double(fade_ms))
+
+
+def apply_target_curve(audio: np.ndarray, sr: int, phase_mode: str = "minimum", eq_ms: bool = False) -> np.ndarray:
+    """backend/app/pipeline.py:238-273 (IIR path; the linear-phase FFT variant :220-235 is second-wave)."""
+    if phase_mode == "linear_phase":
+        raise NotImplementedError("linear-phase target curve is second-wave scope (SURVEY 8f)")
+    a = np.asarray(audio)
+    ms = bool(eq_ms) and a.ndim == 2 and a.shape[1] == 2
+    return _stage("apply_target_curve", audio, sr, 1 if ms else 0)
+
+
+def apply_deesser(audio: np.ndarray, sr: int, threshold_db: float = -6.0, ratio: float = 3.0, freq_lo: float = 5000.0,
+                  freq_hi: float = 9000.0, attack_ms: float = 4.0, release_ms: float = 85.0) -> np.ndarray:
+    """backend/app/pipeline.py:1200-1264."""
+    return _stage("apply_deesser", audio, sr, *(C.c_double(v) for v in (threshold_db, ratio, freq_lo, freq_hi, attack_ms, release_ms)))
+
+
+def apply_dynamics(samples: np.ndarray, sr: int, knee_db: float = 6.0, crossovers_hz=None, band_ratios=None,
+                   max_upward_boost_db: float = 12.0) -> np.ndarray:
+    """backend/app/pipeline.py:610-641 (numpy compressor branch :466-474; the pedalboard/JUCE branch is
+    parity-unpinned and not offered)."""
+    cx = _lib.darr(crossovers_hz) if crossovers_hz is not None and len(crossovers_hz) == 3 else None
+    br = _lib.darr(band_ratios) if band_ratios is not None and len(band_ratios) == 4 else None
+    return _stage("apply_dynamics", samples, sr, C.c_double(knee_db), cx, br, C.c_double(max_upward_boost_db))
+
+
+def apply_maximizer(audio: np.ndarray) -> np.ndarray:
+    """backend/app/pipeline.py:484-492 (module constants -2.5 / -0.3 dB)."""
+    return _stage("apply_maximizer", audio, 44100)
+
+
+def apply_parallel_compression(audio: np.ndarray, sr: int, mix: float = 0.3, ratio: float = 8.0,
+                               threshold_db: float = -20.0) -> np.ndarray:
+    """backend/app/pipeline.py:1771-1797."""
+    if float(np.clip(mix, 0.0, 1.0)) < 0.01:
+        return audio
+    return _stage("apply_parallel_compression", audio, sr, C.c_double(mix), C.c_double(ratio), C.c_double(threshold_db))
+
+
+def measure_lufs(audio: np.ndarray, sr: int) -> float:
+    """backend/app/pipeline.py:658-664: NaN when the meter cannot run (shorter than one 400 ms block)."""
+    a = np.asarray(audio)
+    if a.size == 0 or a.shape[0] < 0.4 * sr:
+        return float("nan")
+    eng, b, _ = _up(a, sr)       # device/driver errors propagate: no silent fallback
+    return float(eng.measure_lufs(b)[0])
+
+
+def normalize_lufs(audio: np.ndarray, sr: int, target_lufs: float) -> np.ndarray:
+    """backend/app/pipeline.py:644-655: input returned unchanged when the meter cannot run."""
+    a = np.asarray(audio)
+    if a.shape[0] < 0.4 * sr:
+        return audio
+    return _stage("normalize_lufs", audio, sr, _lib.darr([target_lufs]))
+
+
+def apply_final_spectral_balance(audio: np.ndarray, sr: int) -> np.ndarray:
+    """backend/app/pipeline.py:576-607."""
+    return _stage("apply_final_spectral_balance", audio, sr)
+
+
+def apply_style_eq(audio: np.ndarray, sr: int, style: str = "standard") -> np.ndarray:
+    """backend/app/pipeline.py:1401-1434."""
+    cfg = STYLE_CONFIGS.get(style, STYLE_CONFIGS["standard"])
+    return _stage("apply_style_eq", audio, sr, _lib.darr([cfg[k] for k in ("sub", "bass", "mids", "presence", "air")]))
+
+
+def apply_harmonic_exciter(audio: np.ndarray, sr: int, exciter_db: float = 0.0, mode: str = "warm", oversample: int = 1) -> np.ndarray:
+    """backend/app/pipeline.py:1267-1326 (oversample == 1; FFT-resampled variant is second-wave)."""
+    if abs(exciter_db) < 0.05:
+        return audio
+    if max(1, min(4, int(oversample))) > 1:
+        raise NotImplementedError("oversampled exciter is second-wave scope (SURVEY 8f)")
+    return _stage("apply_harmonic_exciter", audio, sr, C.c_double(exciter_db), _EXCITER_MODES.get(mode, 0))
+
+
+def apply_stereo_imager(audio: np.ndarray, width: float = 1.0, stereoize_delay_ms: float = 0.0, stereoize_mix: float = 0.12,
+                        sr=None, band_widths=None, crossovers_hz=None) -> np.ndarray:
+    """backend/app/pipeline.py:1339-1398, plain width mode (4-band / Haas modes are second-wave)."""
+    a = np.asarray(audio)
+    if a.ndim == 1 or a.shape[1] == 1:
+        return audio
+    if band_widths is not None or (stereoize_delay_ms and stereoize_delay_ms > 0):
+        raise NotImplementedError("multiband / Haas imager is second-wave scope (SURVEY 8f)")
+    return _stage("apply_stereo_imager", audio, sr or 44100, C.c_double(width))
+
+
+def apply_rumble_filter(audio: np.ndarray, sr: int, cutoff_hz: float = 80.0) -> np.ndarray:
+    """backend/app/pipeline.py:1449-1469."""
+    return _stage("apply_rumble_filter", audio, sr, C.c_double(cutoff_hz))
+
+
+_SILENT_MSG = ("Обработка дала тишину. Отключите часть доп. настроек и попробуйте снова.")
+_NONFINITE_MSG = ("Обработка дала недопустимые значения (NaN/Inf). Отключите доп. модули и попробуйте снова.")
+
+
+def validate_mastered_not_silent(mastered: np.ndarray, *, trace_ctx=None, trace_sr: int = 44100) -> None:
+    """backend/app/pipeline.py:939-962: ValueError on an empty, non-finite or silent (< 1e-5 peak) result
+    (the reference's tests match "тишину" / "Отключите", backend/tests/test_pipeline.py:369-384)."""
+    m = np.asarray(mastered)
+    if m.size == 0:
+        raise ValueError(_SILENT_MSG)
+    eng, b, _ = _up(m, trace_sr)
+    _, peak = eng.stereo_correlation(b)       # device reduction: max |x| (NaN/Inf propagate into it)
+    pk = float(peak[0])
+    if not np.isfinite(pk) or not np.all(np.isfinite(m)):
+        raise ValueError(_NONFINITE_MSG)
+    if pk < 1e-5:
+        raise ValueError(_SILENT_MSG)
+
+
+# ---- analyzers ----------------------------------------------------------------------------------------
+def compute_spectrum_bars(audio: np.ndarray, sr: int, n_fft: int = 4096, n_bars: int = 64, min_hz: float = 20.0,
+                          max_hz: float = 20000.0) -> list:
+    """backend/app/pipeline.py:700-739 (the kernel is specialised to the reference's defaults)."""
+    if (n_fft, n_bars, min_hz, max_hz) != (4096, 64, 20.0, 20000.0):
+        raise NotImplementedError("spectrum kernel is built for n_fft=4096, 64 bars, 20 Hz..20 kHz")
+    if np.size(audio) < n_fft:
+        return [-80.0] * n_bars
+    eng, b, _ = _up(audio, sr)
+    return [float(v) for v in eng.spectrum_bars(b, 0)[0]]
+
+
+def measure_stereo_correlation(audio: np.ndarray) -> Optional[float]:
+    """backend/app/pipeline.py:766-791."""
+    a = np.asarray(audio)
+    if a.ndim != 2 or a.shape[1] != 2 or a.size < 4:
+        return None
+    eng, b, _ = _up(a, 44100)
+    corr, _ = eng.stereo_correlation(b)
+    return None if np.isnan(corr[0]) else float(corr[0])
+
+
+def true_peak_dbfs(audio: np.ndarray, sr: int = 44100) -> float:
+    """backend/app/routers/tools.py:44-54 (``_true_peak_dbfs``)."""
+    if np.size(audio) == 0:
+        return -120.0
+    eng, b, _ = _up(audio, sr)
+    return float(eng.true_peak(b)[0])
+
+
+# ---- chains -----------------------------------------------------------------------------------------
+_V1_PROGRESS = [(5, "dc_offset"), (10, "peak_guard"), (15, "target_curve"), (32, "deesser"), (38, "dynamics"),
+                (52, "normalize_lufs"), (65, "final_spectral_balance"), (72, "style_eq"), (82, "peak_guard"),
+                (95, "fade_in"), (97, "done")]
+
+
+def run_mastering_pipeline(audio: np.ndarray, sr: int, target_lufs: float = -14.0, style: str = "standard",
+                           progress_callback: Optional[Callable[[int, str], None]] = None, denoise_strength: float = 0.0,
+                           transient_attack: float = 1.0, transient_sustain: float = 1.0, reference_audio=None,
+                           reference_sr=None, reference_strength: float = 0.8, trace_ctx=None) -> np.ndarray:
+    """backend/app/pipeline.py:1800-1909 (default path: no denoise / reference match / transient designer)."""
+    if denoise_strength > 0 or reference_audio is not None or abs(transient_attack - 1.0) > 0.01 or abs(transient_sustain - 1.0) > 0.01:
+        raise NotImplementedError("denoise / reference match / transient designer are second-wave scope (SURVEY 8f)")
+    style = style if style in STYLE_CONFIGS else "standard"
+    out = master_batch([audio], sr, [style], [target_lufs], chain="v1")["audio"][0]
+    if progress_callback is not None:      # stage boundaries are fused on the device; report them in order
+        for pct, msg in _V1_PROGRESS:
+            progress_callback(pct, msg)
+    return out
+
+
+def export_audio(samples: np.ndarray, sr: int, channels: int, out_format: str = "wav", dither_type: str = "tpdf",
+                 auto_blank_sec: float = 0.0, bitrate=None, noise: Optional[np.ndarray] = None, seed: int = 0) -> bytes:
+    """backend/app/pipeline.py:965-991, WAV/TPDF branch (``noise=`` is additive: bit-exact test hook)."""
+    if out_format.lower() != "wav":
+        raise NotImplementedError("only the WAV branch is on the hot path (codecs are host-side I/O, SURVEY L0)")
+    if dither_type not in ("tpdf", None, ""):
+        raise NotImplementedError("noise-shaped dither (ns_e / ns_itu) is second-wave scope (SURVEY 8f)")
+    if auto_blank_sec:
+        raise NotImplementedError("auto_blank_sec is second-wave scope")
+    eng, b, _ = _up(samples, sr)
+    pcm = eng.quantize_int16(b, noise=noise, seed=seed)[0]
+    return wavio.pack_wav_pcm16(pcm, sr)
+
+
+def load_audio_from_bytes(data: bytes, fmt: str = "wav"):
+    """backend/app/pipeline.py:802-827, WAV only (container I/O is outside the hot path)."""
+    if fmt.lower().lstrip(".") != "wav":
+        raise NotImplementedError("only WAV decoding is provided")
+    return wavio.unpack_wav(data)
+
+
+# ---- additive: batched entry point ------------------------------------------------------------------
+def master_batch(tracks, sr, styles, targets=None, chain="v2", want_int16=False, noise=None, seed=0, job_fade=True,
+                 measure=False, eng: Optional[Engine] = None):
+    """Master equally-shaped tracks as one device batch.
+
+    tracks: list of (n,) / (n, ch) float32 arrays; styles: list of style names; targets: list of LUFS
+    (default: the style's own).  Returns dict(audio=[...], int16=[...] or None, stats=[dict,...])."""
+    eng = eng or get_engine()
+    mono = np.asarray(tracks[0]).ndim == 1
+    b = eng.upload(tracks, int(sr))
+    names = [s if s in STYLE_CONFIGS else "standard" for s in styles]
+    if targets is None:
+        targets = [STYLE_CONFIGS[s]["lufs"] for s in names]
+    sts = [style_struct(STYLE_CONFIGS[s], t) for s, t in zip(names, targets)]
+    flags = (0 if job_fade else _lib.FLAG_NO_JOB_FADE) | ((_lib.FLAG_MEASURE_IN | _lib.FLAG_MEASURE_OUT) if measure else 0)
+    out, pcm, stats = eng.master(b, _lib.CHAIN_V1 if chain == "v1" else _lib.CHAIN_V2, sts, out=b, want_int16=want_int16,
+                                 noise=noise, seed=seed, flags=flags)
+    audio = eng.download(out)
+    res = {"audio": [a[:, 0] if mono else a for a in audio], "int16": None, "stats": []}
+    if pcm is not None:
+        eng.sync()
+        res["int16"] = list(pcm.cpu().numpy())
+    for s in stats:
+        res["stats"].append({k: (list(getattr(s, k)) if k == "mean" else getattr(s, k)) for k, _ in s._fields_})
+    return res

@@ -1,0 +1,201 @@
+/* mm_b200.h -- C ABI of the B200-native Magic Master mastering hot path.
+ *
+ * The reference (denisok-ai/audio-mastering-web) has no FFI of its own: its hot path is the
+ * Python module backend/app/pipeline.py, called in-process by the FastAPI routes.  This header
+ * is the boundary a maintainer binds instead (ctypes stub in INTEGRATION.md); every entry point
+ * names the reference function it replaces (file:line relative to the reference tree).
+ *
+ * Conventions
+ *  - All functions return 0 on success, non-zero on failure; mm_last_error() (thread-local)
+ *    holds the message.  There is NO CPU fallback: without a CUDA device mm_ctx_create fails.
+ *  - "dev" entry points take DEVICE pointers to planar batches:
+ *        row r = track * channels + channel,   row pointer = base + r * stride,
+ *        sample i of a row lives at float offset MM_LEAD + i,
+ *        stride = mm_row_stride(n)  (multiple of 32 floats, >= MM_LEAD + n + 32).
+ *    The lead-in/lead-out floats of a row are scratch (their content is ignored and may be
+ *    overwritten).  All work is enqueued on the context's stream; nothing synchronises unless
+ *    stated.  out may alias in for every stage function.
+ *  - "host" entry points take HOST pointers in the reference's own layout: float32, C-order,
+ *    (n, channels) interleaved -- what soundfile.read(always_2d=True) returns -- and include
+ *    the host<->device copies.
+ */
+#ifndef MM_B200_H
+#define MM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MM_LEAD 32
+#define MM_ABI_VERSION 1
+
+typedef struct mm_ctx mm_ctx;
+
+/* Geometry of a device-resident batch: every track has n frames, `channels` channels, rate sr. */
+typedef struct mm_geom {
+    int64_t n;        /* frames per track */
+    int64_t stride;   /* floats per row, = mm_row_stride(n) */
+    int32_t tracks;
+    int32_t channels; /* 1 or 2 */
+    int32_t sr;       /* sample rate, Hz */
+    int32_t _pad;
+} mm_geom;
+
+/* STYLE_CONFIGS row (backend/app/pipeline.py:69-86) + target; one per track. */
+typedef struct mm_style {
+    double target_lufs;
+    double eq_gain_db[5];   /* sub, bass, mids, presence, air */
+    double exciter_db;
+    double imager_width;
+    double parallel_mix;    /* v1 only (pipeline.py:1856) */
+} mm_style;
+
+/* Per-track results gathered by the chain (device array of these, or host copy). */
+typedef struct mm_track_stats {
+    double lufs_in;        /* measure_lufs(input)  (routers/mastering.py:491); NaN if too short */
+    double lufs_mid;       /* loudness seen by normalize_lufs (pipeline.py:648) */
+    double lufs_out;       /* measure_lufs(output) (routers/mastering.py:587) */
+    double gain_db;        /* gain normalize_lufs applied, clipped to +-20 dB */
+    double peak_in;        /* max|x - mean| seen by the input peak guard */
+    double peak_out;       /* max|x| seen by the output peak guard */
+    double mean[2];        /* DC offset removed per channel */
+    double nonfinite;      /* count of non-finite samples in the final buffer (trace hook) */
+} mm_track_stats;
+
+/* ---- context ------------------------------------------------------------------------------ */
+int         mm_abi_version(void);
+const char* mm_last_error(void);
+int64_t     mm_row_stride(int64_t n);
+/* stream: a cudaStream_t (as void*) owned by the caller, or NULL for a private stream. */
+int  mm_ctx_create(int device, void* stream, mm_ctx** out);
+void mm_ctx_destroy(mm_ctx* ctx);
+int  mm_ctx_sync(mm_ctx* ctx);
+/* Number of kernels this context has launched so far (bench.py's gpu_launches). */
+int64_t mm_ctx_launch_count(mm_ctx* ctx);
+/* Device-time accounting: when enabled, every kernel is bracketed by CUDA events on the
+ * context's stream; mm_ctx_kernel_times fills up to `cap` entries (name, total ms, launches). */
+int  mm_ctx_timing(mm_ctx* ctx, int enable);
+typedef struct mm_ktime { char name[48]; double ms; int64_t launches; } mm_ktime;
+int  mm_ctx_kernel_times(mm_ctx* ctx, mm_ktime* out, int cap, int* count);
+
+/* ---- layout helpers -------------------------------------------------------------------------*/
+/* interleaved (n, ch) device buffer <-> planar rows */
+int mm_dev_deinterleave(mm_ctx*, const mm_geom*, const float* interleaved /*[tracks][n][ch]*/, float* planar);
+int mm_dev_interleave(mm_ctx*, const mm_geom*, const float* planar, float* interleaved);
+
+/* ---- stage functions (device batches); each mirrors one pipeline.py function ----------------*/
+/* remove_dc_offset                     backend/app/pipeline.py:134-138 */
+int mm_dev_remove_dc_offset(mm_ctx*, const mm_geom*, const float* in, float* out);
+/* remove_intersample_peaks             backend/app/pipeline.py:141-149 */
+int mm_dev_remove_intersample_peaks(mm_ctx*, const mm_geom*, const float* in, float* out, double headroom_db);
+/* apply_output_edge_fade_in            backend/app/pipeline.py:152-167 */
+int mm_dev_fade_in(mm_ctx*, const mm_geom*, const float* in, float* out, double fade_ms);
+/* apply_target_curve (IIR, minimum)    backend/app/pipeline.py:238-273; eq_ms -> :248-255 */
+int mm_dev_apply_target_curve(mm_ctx*, const mm_geom*, const float* in, float* out, int eq_ms);
+/* apply_deesser                        backend/app/pipeline.py:1200-1264 */
+int mm_dev_apply_deesser(mm_ctx*, const mm_geom*, const float* in, float* out,
+                         double threshold_db, double ratio, double freq_lo, double freq_hi,
+                         double attack_ms, double release_ms);
+/* apply_dynamics (numpy compressor branch) backend/app/pipeline.py:610-641, :414-481 */
+int mm_dev_apply_dynamics(mm_ctx*, const mm_geom*, const float* in, float* out, double knee_db,
+                          const double* crossovers_hz /*3 or NULL*/, const double* band_ratios /*4 or NULL*/,
+                          double max_upward_boost_db);
+/* apply_maximizer                      backend/app/pipeline.py:484-492 */
+int mm_dev_apply_maximizer(mm_ctx*, const mm_geom*, const float* in, float* out);
+/* apply_parallel_compression           backend/app/pipeline.py:1771-1797 */
+int mm_dev_apply_parallel_compression(mm_ctx*, const mm_geom*, const float* in, float* out,
+                                      double mix, double ratio, double threshold_db);
+/* measure_lufs                         backend/app/pipeline.py:658-664 (pyloudnorm BS.1770-4)
+ * lufs_dev: device array [tracks] of double. */
+int mm_dev_measure_lufs(mm_ctx*, const mm_geom*, const float* in, double* lufs_dev);
+/* normalize_lufs                       backend/app/pipeline.py:644-655; target per track (host array) */
+int mm_dev_normalize_lufs(mm_ctx*, const mm_geom*, const float* in, float* out, const double* target_lufs_host);
+/* apply_final_spectral_balance         backend/app/pipeline.py:576-607 */
+int mm_dev_apply_final_spectral_balance(mm_ctx*, const mm_geom*, const float* in, float* out);
+/* apply_style_eq                       backend/app/pipeline.py:1401-1434; one gain set for the batch */
+int mm_dev_apply_style_eq(mm_ctx*, const mm_geom*, const float* in, float* out, const double* eq_gain_db /*5*/);
+/* apply_harmonic_exciter (warm, oversample 1) backend/app/pipeline.py:1267-1326 */
+int mm_dev_apply_harmonic_exciter(mm_ctx*, const mm_geom*, const float* in, float* out, double exciter_db, int mode);
+/* apply_stereo_imager (width mode)     backend/app/pipeline.py:1339-1398 */
+int mm_dev_apply_stereo_imager(mm_ctx*, const mm_geom*, const float* in, float* out, double width);
+/* apply_rumble_filter                  backend/app/pipeline.py:1449-1469 */
+int mm_dev_apply_rumble_filter(mm_ctx*, const mm_geom*, const float* in, float* out, double cutoff_hz);
+/* generic zero-phase / causal IIR on every row: scipy filtfilt / lfilter semantics of
+ * _safe_filtfilt (backend/app/pipeline.py:36-52). nb == na in {3, 5}; zero_phase 0 -> lfilter. */
+int mm_dev_iir(mm_ctx*, const mm_geom*, const float* in, float* out,
+               const double* b, const double* a, int ncoef, int zero_phase);
+
+/* ---- export ---------------------------------------------------------------------------------*/
+/* _write_wav_16bit_dithered quantiser  backend/app/pipeline.py:880-898
+ * planar float rows -> interleaved int16 [tracks][n][ch].
+ * noise: NULL -> TPDF from counter-based Philox4x32-10 keyed by (seed, track);
+ *        else device float32 [tracks][n][ch] interleaved (bit-exact mode, _dither_noise_tpdf :830). */
+int mm_dev_quantize_int16(mm_ctx*, const mm_geom*, const float* in, int16_t* out_interleaved,
+                          const float* noise_interleaved, uint64_t seed);
+
+/* ---- analyzers ------------------------------------------------------------------------------*/
+/* _true_peak_dbfs                      backend/app/routers/tools.py:44-54; out: device double[tracks] (dBFS) */
+int mm_dev_true_peak(mm_ctx*, const mm_geom*, const float* in, double* tp_dbfs_dev);
+/* compute_spectrum_bars                backend/app/pipeline.py:700-739
+ * view: 0 = mean of channels, 1 = mid (L+R)/2, 2 = side (L-R)/2; out: device double[tracks][64] */
+int mm_dev_spectrum_bars(mm_ctx*, const mm_geom*, const float* in, int view, double* bars_dev);
+/* measure_stereo_correlation           backend/app/pipeline.py:766-791; out: device double[tracks]
+ * (NaN encodes the reference's None), plus sample peak per track (double[tracks], may be NULL) */
+int mm_dev_stereo_correlation(mm_ctx*, const mm_geom*, const float* in, double* corr_dev, double* sample_peak_dev);
+
+/* ---- whole chains (fused sweep plan; what bench.py times) ------------------------------------*/
+#define MM_CHAIN_V1 1   /* run_mastering_pipeline            backend/app/pipeline.py:1800-1909 */
+#define MM_CHAIN_V2 2   /* MasteringChain.default_chain(...).process + job fade-in
+                           backend/app/chain.py:66-134, backend/app/routers/mastering.py:583 */
+#define MM_FLAG_MEASURE_IN   1u  /* also measure_lufs(input)  */
+#define MM_FLAG_MEASURE_OUT  2u  /* also measure_lufs(output) */
+#define MM_FLAG_NO_JOB_FADE  4u  /* v2: return chain.process output without the job's fade-in */
+/* styles: host array, one per track.  out_f32 planar (may alias in); out_i16 interleaved int16 or
+ * NULL; noise as in mm_dev_quantize_int16; stats_dev: device mm_track_stats[tracks] or NULL. */
+int mm_dev_master(mm_ctx*, const mm_geom*, int chain, const mm_style* styles_host,
+                  const float* in, float* out_f32, int16_t* out_i16,
+                  const float* noise_interleaved, uint64_t dither_seed,
+                  mm_track_stats* stats_dev, uint32_t flags);
+
+/* Host-buffer drop-in for one call of run_mastering_pipeline / chain.process (+ optional
+ * export): audio_in/out are (n, channels) interleaved float32 HOST arrays; pcm16_out may be NULL.
+ * Copies in, masters `tracks` equally-shaped tracks stored back to back, copies out, syncs. */
+int mm_master_host(mm_ctx*, int chain, int32_t tracks, int64_t n, int32_t channels, int32_t sr,
+                   const mm_style* styles_host, const float* audio_in, float* audio_out,
+                   int16_t* pcm16_out, const float* noise_host, uint64_t dither_seed,
+                   mm_track_stats* stats_host, uint32_t flags);
+
+/* Pinned host memory for the host-buffer entry point (cudaMallocHost / cudaFreeHost). */
+int mm_host_alloc(void** out, int64_t bytes);
+int mm_host_free(void* p);
+
+/* Bytes of device workspace the context currently holds (for sizing sub-batches). */
+int64_t mm_ctx_workspace_bytes(mm_ctx*);
+/* Workspace the chain needs for a geometry (rows * stride * 4 * k + carries). */
+int64_t mm_master_workspace_bytes(const mm_geom*, int chain);
+
+/* ---- filter design (host, float64) -- scipy.signal.butter(order, Wn, btype, output="ba") and
+ * lfilter_zi as used at backend/app/pipeline.py:175-183, :345-353, :590-599, :1231, :1303, :1427 */
+#define MM_LOWPASS 0
+#define MM_HIGHPASS 1
+#define MM_BANDPASS 2
+/* wn: 1 value (low/high) or 2 (band), normalised to Nyquist. b,a receive ncoef = order+1
+ * (low/high) or 2*order+1 (band) values. Returns ncoef, or <0 on error. */
+int mm_design_butter(int order, int btype, const double* wn, double* b, double* a);
+int mm_design_lfilter_zi(const double* b, const double* a, int ncoef, double* zi);
+/* pyloudnorm K-weighting stage (0 = high shelf, 1 = high pass) for a sample rate; b[3], a[3]
+ * (call sites backend/app/pipeline.py:646-648). */
+int mm_design_k_weighting(int stage, double rate, double* b, double* a);
+/* Tables of the chunked linear-recurrence scan for one section (host-side verification of the
+ * tile decomposition in tests/): returns the look-back window W (tiles), <0 on error.
+ * g[S*m], Pw[5*m*m], Plane[32*m*m], Qpow[(T/32+1)*m*m], Mpow[cap_w*m*m], Apow[(S+1)*m*m], zi[m];
+ * S = samples per thread, T = threads per tile. Any output pointer may be NULL. */
+int mm_design_scan_tables(const double* b, const double* a, int ncoef, double* g, double* Pw, double* Plane,
+                          double* Qpow, double* Mpow, int cap_w, double* Apow, double* zi, int* S, int* T);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MM_B200_H */

@@ -1,0 +1,132 @@
+"""Whole chains on the GPU against the reference goldens and the oracle."""
+import numpy as np
+import pytest
+
+from conftest import load_golden, tpdf_noise
+
+pytestmark = pytest.mark.gpu
+
+CHAIN_CASES = [
+    ("v1_edm_44k", "v1", "edm"),
+    ("v1_standard_96k", "v1", "standard"),
+    ("v2_standard_48k", "v2", "standard"),
+    ("v2_hiphop_44k_mono", "v2", "hiphop"),
+    ("v1_podcast_48k", "v1", "podcast"),
+    ("v2_house_44k", "v2", "house_basic"),
+]
+
+
+def _err(a, b):
+    return float(np.max(np.abs(np.asarray(a, dtype=np.float64) - np.asarray(b, dtype=np.float64))))
+
+
+@pytest.fixture(scope="module")
+def P(gpu_lib):
+    from mm_b200 import pipeline
+    return pipeline
+
+
+@pytest.mark.parametrize("name,which,style", CHAIN_CASES, ids=[c[0] for c in CHAIN_CASES])
+def test_chain_matches_reference_golden(P, name, which, style):
+    g = load_golden(name)
+    sr, target = int(g["sr"]), float(g["target"])
+    x = g["input"]
+    shape2d = g["int16"].shape
+    noise = tpdf_noise(g["noise_seed"], shape2d)
+    res = P.master_batch([x], sr, [style], [target], chain=which, want_int16=True, noise=noise[None], measure=True)
+    out = res["audio"][0]
+    assert out.shape == g["out"].shape and out.dtype == np.float32
+    e = _err(out, g["out"])
+    st = res["stats"][0]
+    print(f"[parity] chain {name}: max|gpu-ref| = {e:.3e}  lufs_in {st['lufs_in']:.4f}/{float(g['lufs_in']):.4f} "
+          f"lufs_out {st['lufs_out']:.4f}/{float(g['lufs_out']):.4f}")
+    assert e <= 1e-4, (name, e)                                     # north_star: 1e-4 absolute
+    assert abs(st["lufs_in"] - float(g["lufs_in"])) <= 0.01         # +-0.01 LU
+    assert abs(st["lufs_out"] - float(g["lufs_out"])) <= 0.01
+    assert abs(P.true_peak_dbfs(out, sr) - float(g["true_peak_out"])) <= 0.01   # +-0.01 dB
+    # int16: bit-exact for the quantiser given identical float32 samples and noise ...
+    from mm_b200.engine import get_engine
+    eng = get_engine()
+    q = eng.quantize_int16(eng.upload([g["out"].reshape(shape2d)], sr), noise=noise[None])[0]
+    assert np.array_equal(q, g["int16"])
+    # ... and the fused export equals quantising the chain's own float32 output
+    q_own = eng.quantize_int16(eng.upload([out.reshape(shape2d)], sr), noise=noise[None])[0]
+    assert np.array_equal(res["int16"][0], q_own)
+    assert np.max(np.abs(res["int16"][0].astype(np.int32) - g["int16"].astype(np.int32))) <= 4
+
+
+def test_v1_stagewise_against_golden(P):
+    """Stage by stage on the v1/edm golden: each GPU stage is fed the reference's own previous-stage
+    output, so errors cannot hide behind each other."""
+    g = load_golden("v1_edm_44k")
+    sr = int(g["sr"])
+    cfg = P.STYLE_CONFIGS["edm"]
+    steps = [
+        ("dc_offset", "input", lambda a: P.remove_dc_offset(a)),
+        ("peak_guard_in", "stage_dc_offset", lambda a: P.remove_intersample_peaks(a, 0.5)),
+        ("target_eq", "stage_peak_guard_in", lambda a: P.apply_target_curve(a, sr)),
+        ("deesser", "stage_target_eq", lambda a: P.apply_deesser(a, sr)),
+        ("dynamics", "stage_deesser", lambda a: P.apply_dynamics(a, sr)),
+        ("parallel_compress", "stage_dynamics", lambda a: P.apply_parallel_compression(a, sr, mix=cfg["parallel_mix"])),
+        ("normalize_lufs", "stage_parallel_compress", lambda a: P.normalize_lufs(a, sr, float(g["target"]))),
+        ("final_spectral_balance", "stage_normalize_lufs", lambda a: P.apply_final_spectral_balance(a, sr)),
+        ("style_eq", "stage_final_spectral_balance", lambda a: P.apply_style_eq(a, sr, "edm")),
+        ("harmonic_exciter", "stage_style_eq", lambda a: P.apply_harmonic_exciter(a, sr, cfg["exciter_db"])),
+        ("stereo_imager", "stage_harmonic_exciter", lambda a: P.apply_stereo_imager(a, cfg["imager_width"])),
+        ("peak_guard_out", "stage_stereo_imager", lambda a: P.remove_intersample_peaks(a, 0.5)),
+        ("output_fade_in", "stage_peak_guard_out", lambda a: P.apply_output_edge_fade_in(a, sr, 6.0)),
+    ]
+    worst = {}
+    for name, src, fn in steps:
+        got = fn(g[src])
+        worst[name] = _err(got, g["stage_" + name])
+        print(f"[parity] v1 stage {name}: {worst[name]:.3e}")
+    assert max(worst.values()) <= 5e-6, worst
+
+
+def test_batch_of_mixed_styles_equals_single_runs(P):
+    """Tracks are independent: a mixed-style batch gives, per track, exactly the single-track result."""
+    from mm_b200 import synth
+    sr = 44100
+    styles = ["standard", "edm", "edm", "classical", "podcast", "standard", "lofi", "house_basic"]
+    tracks = [synth.numpy_track(20 + i, sr, 0.7) for i in range(len(styles))]
+    for chain in ("v1", "v2"):
+        batch = P.master_batch(tracks, sr, styles, chain=chain)
+        for i, (t, s) in enumerate(zip(tracks, styles)):
+            single = P.master_batch([t], sr, [s], chain=chain)
+            assert np.array_equal(batch["audio"][i], single["audio"][0]), (chain, i, s)
+
+
+def test_chain_vs_oracle_longer_track(P):
+    """6 s track (several tiles, several gating blocks) against the CPU oracle, both chains."""
+    from mm_b200 import synth
+    from oracle import chain as oc
+    sr = 44100
+    x = synth.numpy_track(1, sr, 6.0)
+    for which, style in (("v2", "standard"), ("v1", "edm"), ("v2", "house_basic")):
+        target = P.STYLE_CONFIGS[style]["lufs"]
+        ref = (oc.run_v1 if which == "v1" else oc.run_v2)(x.copy(), sr, target, style)
+        res = P.master_batch([x], sr, [style], [target], chain=which, measure=True)
+        e = _err(res["audio"][0], ref)
+        print(f"[parity] {which}/{style} 6 s: max|gpu-oracle| = {e:.3e}")
+        assert e <= 1e-4
+        assert abs(res["stats"][0]["lufs_out"] - oc.measure_lufs(ref, sr)) <= 0.01
+        assert abs(res["stats"][0]["lufs_in"] - oc.measure_lufs(x, sr)) <= 0.01
+
+
+def test_run_mastering_pipeline_contract(P):
+    """The reference's own property tests (backend/tests/test_pipeline.py:204-223, :480-487)."""
+    sr = 44100
+    t = np.arange(sr * 2) / sr
+    x = (0.3 * np.sin(2 * np.pi * 440 * t)).astype(np.float32)
+    x = np.stack([x, x], axis=1)
+    calls = []
+    out = P.run_mastering_pipeline(x, sr, target_lufs=-14.0, progress_callback=lambda p, m: calls.append(p))
+    assert out.shape == x.shape and out.dtype == np.float32
+    assert np.all(np.isfinite(out)) and np.max(np.abs(out)) <= 1.01
+    assert len(calls) >= 5
+    assert abs(float(out[0, 0])) < 1e-6          # fade-in: first sample ~ 0
+    lufs = P.measure_lufs(out, sr)
+    assert -50 < lufs < 0
+    mono = P.run_mastering_pipeline(x[:, 0].copy(), sr, style="dry_vocal")
+    assert mono.shape == (x.shape[0],)

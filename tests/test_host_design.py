@@ -1,0 +1,185 @@
+"""Host-side logic that needs no GPU: the C-ABI library loads and exports every declared symbol;
+filter design matches scipy; the scan tables reproduce scipy.lfilter when the tile decomposition
+of csrc/sweep.cuh is replayed in numpy."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+from scipy import signal as sg
+
+from conftest import REPO
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from mm_b200 import _lib
+    if not os.path.exists(_lib.LIB_PATH):
+        from mm_b200 import build
+        build.build()
+    return _lib.load()
+
+
+def test_library_exports_every_declared_symbol(lib):
+    from mm_b200 import _lib
+    hdr = open(os.path.join(REPO, "include", "mm_b200.h")).read()
+    declared = set(re.findall(r"\b(mm_[a-z0-9_]+)\s*\(", hdr))
+    declared -= {"mm_ctx", "mm_geom", "mm_style", "mm_track_stats", "mm_ktime"}
+    assert declared, "no declarations parsed"
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} declared in include/mm_b200.h but not exported"
+        assert name in _lib.SIGNATURES, f"{name} has no ctypes signature"
+    assert lib.mm_abi_version() == 1
+    assert lib.mm_row_stride(1) % 32 == 0 and lib.mm_row_stride(7_938_000) >= 7_938_000 + 64
+
+
+def test_no_cuda_device_fails_loudly(lib):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from mm_b200 import _lib
+    ctx = C.c_void_p()
+    assert lib.mm_ctx_create(0, None, C.byref(ctx)) != 0
+    assert "no CPU fallback" in _lib.last_error() or "CUDA" in _lib.last_error()
+    from mm_b200.engine import Engine, MMError
+    with pytest.raises(MMError):
+        Engine(0)
+
+
+def _butter(lib, order, btype, wn):
+    from mm_b200 import _lib
+    b = (C.c_double * 5)()
+    a = (C.c_double * 5)()
+    n = lib.mm_design_butter(order, btype, _lib.darr(wn), b, a)
+    assert n > 0, _lib.last_error()
+    return np.array(b[:n]), np.array(a[:n])
+
+
+@pytest.mark.parametrize("sr", [22050, 44100, 48000, 88200, 96000, 192000])
+def test_butter_and_zi_match_scipy(lib, sr):
+    from mm_b200 import _lib
+    nyq = sr / 2
+    cases = [(2, 1, [40 / nyq], "high"), (2, 0, [min(18000 / nyq, 0.99)], "low"), (2, 0, [180 / nyq], "low"),
+             (2, 1, [min(16000 / nyq, .99)], "high"), (1, 2, [30 / nyq, 90 / nyq], "band"),
+             (1, 2, [min(3000 / nyq, .99) * 0.7, min(3000 / nyq, .99) * 1.3], "band"),
+             (2, 2, [min(5000 / nyq, .97) * 0.999, min(9000 / nyq, .97)], "band"),
+             (2, 0, [214 / nyq], "low"), (2, 1, [min(10000 / nyq, .99)], "high")]
+    for order, bt, wn, name in cases:
+        if len(wn) == 2 and wn[0] >= wn[1]:
+            continue
+        b, a = _butter(lib, order, bt, wn)
+        rb, ra = sg.butter(order, wn if len(wn) == 2 else wn[0], name)
+        assert np.allclose(b, rb, rtol=1e-12, atol=1e-16), (sr, order, name, b, rb)
+        assert np.allclose(a, ra, rtol=1e-12, atol=1e-15), (sr, order, name, a, ra)
+        zi = (C.c_double * 4)()
+        assert lib.mm_design_lfilter_zi(_lib.darr(rb), _lib.darr(ra), len(rb), zi) == 0
+        assert np.allclose(np.array(zi[:len(rb) - 1]), sg.lfilter_zi(rb, ra), rtol=1e-9, atol=1e-12)
+
+
+def test_k_weighting_matches_oracle(lib):
+    from oracle import bs1770
+    for sr in (22050, 44100, 48000, 96000, 192000):
+        ref = bs1770.k_weighting_coeffs(sr)
+        for stage in (0, 1):
+            b = (C.c_double * 3)()
+            a = (C.c_double * 3)()
+            assert lib.mm_design_k_weighting(stage, float(sr), b, a) == 0
+            assert np.allclose(np.array(b[:]), ref[stage][0], rtol=1e-13)
+            assert np.allclose(np.array(a[:]), ref[stage][1], rtol=1e-13)
+
+
+def _tables(lib, b, a):
+    from mm_b200 import _lib
+    m = len(b) - 1
+    mm2 = m * m
+    capw = 64
+    g = (C.c_double * (32 * m))()
+    Pw = (C.c_double * (5 * mm2))()
+    Plane = (C.c_double * (32 * mm2))()
+    Qpow = (C.c_double * (5 * mm2))()
+    Mpow = (C.c_double * (capw * mm2))()
+    Apow = (C.c_double * (33 * mm2))()
+    zi = (C.c_double * m)()
+    S, T = C.c_int(), C.c_int()
+    W = lib.mm_design_scan_tables(_lib.darr(b), _lib.darr(a), len(b), g, Pw, Plane, Qpow, Mpow, capw, Apow, zi, C.byref(S), C.byref(T))
+    assert W > 0, _lib.last_error()
+    assert (S.value, T.value) == (32, 128)
+    r = lambda arr, k: np.array(arr[:]).reshape(k, m, m)  # noqa: E731
+    return dict(m=m, W=W, g=np.array(g[:]).reshape(32, m), Pw=r(Pw, 5), Plane=r(Plane, 32), Qpow=r(Qpow, 5),
+                Mpow=r(Mpow, capw)[:min(W, capw)], Apow=r(Apow, 33), zi=np.array(zi[:]))
+
+
+def _replay_tile_scan(tb, b, a, x, zi_scale):
+    """numpy replay of csrc/sweep.cuh tile_scan (forward direction, one row) over len(x) samples that
+    start `dead` = 0 samples into tile 0; initial state zi * zi_scale injected at sample 0."""
+    m, S, T = tb["m"], 32, 128
+    L = S * T
+    n = len(x)
+    ntiles = (n + L - 1) // L
+    xp = np.zeros(ntiles * L)
+    xp[:n] = x
+    A = tb["Apow"][1]
+    y = np.zeros(ntiles * L)
+    aggs = []
+    for tile in range(ntiles):
+        ch = xp[tile * L:(tile + 1) * L].reshape(T, S)
+        E = ch @ tb["g"]                                  # zero-state end state per thread  (T, m)
+        if tile == 0:
+            s_init = tb["zi"] * zi_scale
+            E[0] = E[0] + tb["Apow"][S] @ s_init          # dead = 0: state injected before sample 0
+        # warp scans (Kogge-Stone with Pw) == sequential inclusive prefix inside each warp
+        inc = np.zeros_like(E)
+        for w in range(T // 32):
+            e = E[w * 32:(w + 1) * 32].copy()
+            for d in range(5):
+                sh = np.zeros_like(e)
+                sh[1 << d:] = e[:-(1 << d)]
+                e = e + sh @ tb["Pw"][d].T * (np.arange(32)[:, None] >= (1 << d))
+            inc[w * 32:(w + 1) * 32] = e
+        tot = inc[31::32]
+        base = np.zeros((T // 32, m))
+        for w in range(1, T // 32):
+            base[w] = tot[w - 1] + tb["Qpow"][1] @ base[w - 1]
+        agg = tot[-1] + tb["Qpow"][1] @ base[-1]
+        aggs.append(agg)
+        Cin = np.zeros(m)
+        for j in range(min(tb["W"], tile, len(tb["Mpow"]))):
+            Cin = Cin + tb["Mpow"][j] @ aggs[tile - 1 - j]
+        for t in range(T):
+            w, l = divmod(t, 32)
+            bw = base[w] + tb["Qpow"][w] @ Cin
+            z = (inc[t - 1] if l > 0 else np.zeros(m)) + tb["Plane"][l] @ bw
+            if tile == 0 and t == 0:
+                z = tb["zi"] * zi_scale
+            z = z.copy()
+            for j in range(S):                            # DF2T, as df2t_step
+                xv = ch[t, j]
+                yv = b[0] * xv + z[0]
+                for i in range(m):
+                    nxt = z[i + 1] if i + 1 < m else 0.0
+                    z[i] = b[i + 1] * xv - a[i + 1] * yv + nxt
+                y[tile * L + t * S + j] = yv
+        assert np.allclose(A, tb["Apow"][1])
+    return y[:n]
+
+
+@pytest.mark.parametrize("design", ["hp40_96k", "bp30_90_96k", "lp18k_44k", "bp4_deess_48k", "kw_hp38_192k"])
+def test_scan_tables_replay_equals_lfilter(lib, design):
+    from oracle import bs1770
+    b, a = {
+        "hp40_96k": sg.butter(2, 40 / 48000, "high"),
+        "bp30_90_96k": sg.butter(1, [30 / 48000, 90 / 48000], "band"),
+        "lp18k_44k": sg.butter(2, 18000 / 22050, "low"),
+        "bp4_deess_48k": sg.butter(2, [5000 / 24000, 9000 / 24000], "band"),
+        "kw_hp38_192k": bs1770.k_weighting_coeffs(192000)[1],
+    }[design]
+    tb = _tables(lib, b, a)
+    rng = np.random.default_rng(11)
+    n = 4096 * 3 + 1717 if tb["W"] <= 3 else 4096 * (tb["W"] + 2) + 5
+    n = min(n, 4096 * 9)
+    x = 0.2 * rng.standard_normal(n) + 0.3
+    y = _replay_tile_scan(tb, b, a, x, zi_scale=x[0])
+    ref, _ = sg.lfilter(b, a, x, zi=sg.lfilter_zi(b, a) * x[0])
+    assert tb["W"] >= 1
+    assert np.max(np.abs(y - ref)) <= 1e-10 * max(1.0, np.max(np.abs(ref))), (design, tb["W"], np.max(np.abs(y - ref)))
