@@ -42,6 +42,7 @@ enum { EPI_STORE = 0, EPI_COMBINE = 1, EPI_DYNAMICS = 2, EPI_EXCITER = 3 };
 struct DynBand {           // one band of MULTIBAND_CONFIG after host-side preparation
     double thr_db, thr, ratio, lower, upper, slope, max_boost_db;
     float lim, gain;
+    float thr_f, inv_ratio_f, lower_f, upper_f, slope_f;   // float32 copies for the downward knee
     int mode;              // 0 bypass (ratio == 1 or <= 0), 1 hard knee, 2 soft knee, 3 upward
 };
 struct DynParams {

@@ -236,9 +236,11 @@ bool build_scan_tables(const Ba& f, int S, int T, ScanTables* out, int max_windo
     out->Mpow.clear();
     mat_eye(m, X);
     int W = 0;
+    out->Wh = 0;
     for (; W < max_window; ++W) {
         long double mx = 0.0L;
         for (int i = 0; i < mm2; ++i) mx = fmaxl(mx, fabsl(X[i]));
+        if (W > 0 && out->Wh == 0 && mx < 1e-13L) out->Wh = W;
         if (W > 0 && mx < 1e-18L) break;
         out->Mpow.resize((size_t)(W + 1) * mm2);
         put(out->Mpow, (size_t)W * mm2, mm2, X);
@@ -246,6 +248,7 @@ bool build_scan_tables(const Ba& f, int S, int T, ScanTables* out, int max_windo
     }
     if (W >= max_window) return false;   // pole too close to the unit circle for this tile size
     out->W = W;
+    if (out->Wh == 0) out->Wh = W;
     if (!lfilter_zi(f, out->zi)) {
         for (int i = 0; i < m; ++i) out->zi[i] = 0.0;   // scipy would raise LinAlgError; callers decide
     }

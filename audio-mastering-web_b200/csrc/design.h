@@ -34,6 +34,7 @@ struct ScanTables {
     int m = 0;
     int S = 0, T = 0;                   // samples per thread, threads per tile
     int W = 0;                          // look-back window (tiles) after which A^(L*W) < 1e-18
+    int Wh = 0;                         // halo length (tiles): every entry of A^(L*Wh) below 1e-13
     std::vector<double> g;              // [S][m]      g[j] = A^(S-1-j) B
     std::vector<double> Pw;             // [5][m*m]    (A^S)^(2^d)
     std::vector<double> Plane;          // [32][m*m]   (A^S)^l

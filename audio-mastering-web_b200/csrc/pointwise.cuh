@@ -29,18 +29,31 @@ __device__ __forceinline__ float compress_band_f64(double x, const DynBand& b, d
 }
 
 // band -> compress -> hard clip at lim_db -> * gain, all as the numpy branch does it
-// (backend/app/pipeline.py:466-474)
+// (backend/app/pipeline.py:466-474).  The downward soft/hard knee (the default configuration) runs in
+// float32: the band itself is float32 here (HBM storage), the reference's float64 knee arithmetic
+// followed by its float32 cast differs from this by at most one float32 ulp of the band sample.
+// The upward (ratio < 1) branch needs log10/pow and stays in float64.
 __device__ __forceinline__ float band_chain(float y, const DynBand& b) {
-    double raw;
-    const float c = compress_band_f64((double)y, b, &raw);
-    float l;
-    if (b.mode == 0) {
-        const double lim = (double)b.lim;   // bypassed band is still float64 when it is clipped
-        l = (float)fmin(fmax(raw, -lim), lim);
-    } else {
-        l = fminf(fmaxf(c, -b.lim), b.lim);
+    if (b.mode == 0) {          // ratio == 1: the float64 band is only clipped
+        return __fmul_rn(fminf(fmaxf(y, -b.lim), b.lim), b.gain);
     }
-    return __fmul_rn(l, b.gain);
+    if (b.mode == 3) {
+        double raw;
+        const float c = compress_band_f64((double)y, b, &raw);
+        return __fmul_rn(fminf(fmaxf(c, -b.lim), b.lim), b.gain);
+    }
+    const float ax = fabsf(y);
+    float o;
+    if (b.mode == 1) {
+        o = fminf(ax, fmaf(fmaxf(ax - b.thr_f, 0.f), b.inv_ratio_f, b.thr_f));
+    } else {
+        const float hi = fmaf(ax - b.thr_f, b.inv_ratio_f, b.thr_f);
+        const float mid = fmaf(ax - b.lower_f, b.slope_f, b.lower_f);
+        o = ax <= b.lower_f ? ax : (ax >= b.upper_f ? hi : mid);
+        o = fmaxf(o, 0.f);
+    }
+    o = fminf(o, b.lim);        // clip(+-lim) of sign * o
+    return __fmul_rn(copysignf(o, y), b.gain);
 }
 
 // apply_maximizer + hard limiter at TRUE_PEAK_LIMIT_DB on float32 (pipeline.py:484-492, :636)

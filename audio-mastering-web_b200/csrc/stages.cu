@@ -2,13 +2,15 @@
 // Every stage cites the reference function it reproduces (paths relative to the reference tree).
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 #include "context.h"
+#include "sweep.cuh"
 #include "lufs_kernel.cuh"
 #include "misc_kernels.cuh"
 #include "stages_internal.h"
-#include "sweep_kernel.cuh"
+#include "sweep3.cuh"
 
 namespace mm {
 
@@ -29,32 +31,64 @@ template <int M> static void fill_filter(FiltK<M>& fk, const FilterPlan* p) {
         for (int i = 0; i < M; ++i) fk.g[j][i] = p->tabs.g[(size_t)j * M + i];
 }
 
-template <int M, int NF, int NIN, int DIR>
-static int launch_sweep(mm_ctx* c, SweepArgs<M, NF>& A, const char* name) {
-    static bool attr_done = false;
-    const size_t smem = (size_t)NF * kTileFloats * sizeof(float);
-    if (!attr_done) {
-        MM_CUDA(cudaFuncSetAttribute(sweep_kernel<M, NF, NIN, DIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_done = true;
+// Segments per row: minimise  waves * (tiles per segment + halo)  over the segment count.
+static void choose_segments(int rows, int ntiles, int whalo, int capacity, int* nseg_out, int* seglen_out) {
+    long long best_cost = -1;
+    int best = 1;
+    const int max_seg = std::min(ntiles, std::max(1, (capacity * 4 + rows - 1) / rows));
+    for (int ns = 1; ns <= max_seg; ++ns) {
+        const int len = (ntiles + ns - 1) / ns;
+        const int real_ns = (ntiles + len - 1) / len;
+        if (real_ns != ns) continue;
+        const long long items = (long long)rows * ns;
+        const long long waves = (items + capacity - 1) / capacity;
+        const long long cost = waves * (long long)(len + (ns > 1 ? whalo : 0)) * 64 + ns;   // mild preference for fewer segments
+        if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = ns; }
+    }
+    *nseg_out = best;
+    *seglen_out = (ntiles + best - 1) / best;
+}
+
+template <int M, int NF, int NIN, int DIR, int EPI, int NAUX, int ST>
+static int launch_sweep2(mm_ctx* c, SweepArgs<M, NF>& A, int whalo, const char* name) {
+    typedef Sweep2Cfg<M, NF, NIN, DIR, EPI, NAUX, ST> Cfg;
+    static int blocks_per_sm = 0;          // per instantiation; one device kind per process
+    static int num_sms = 0;
+    auto kern = sweep2_kernel<M, NF, NIN, DIR, EPI, NAUX, ST>;
+    const size_t smem = Cfg::kBytes;
+    if (blocks_per_sm == 0) {
+        MM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        MM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        int bps = 0;
+        MM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, kT, smem));
+        if (bps < 1) { set_error("sweep kernel %s does not fit on an SM (%zu bytes of shared memory)", name, smem); return 1; }
+        cudaDeviceProp prop;
+        MM_CUDA(cudaGetDeviceProperties(&prop, c->device));
+        num_sms = prop.multiProcessorCount;
+        blocks_per_sm = bps;
+        if (getenv("MM_DEBUG")) fprintf(stderr, "[mm] %s: %zu B smem, %d CTAs/SM x %d SMs\n", name, smem, bps, num_sms);
     }
     A.ntiles = DIR > 0 ? tiles_fwd(A.n, A.pad) : tiles_bwd(A.n, A.pad);
-    const size_t items = (size_t)A.rows * (size_t)A.ntiles;
-    if (items == 0) return 0;
-    if (items > 0x7fffffffULL) { set_error("batch too large for one sweep (%zu tiles)", items); return 1; }
-    MM_TRY(ensure_carry(c, (size_t)NF * items));
-    A.agg = c->agg;
-    A.flag = c->flag;
-    A.epoch = ++c->epoch;
-    A.ticket = c->ticket;
-    A.ticket_base = c->ticket_total;
-    c->ticket_total += (unsigned)items;
-    A.err = c->err;
+    if ((size_t)A.rows * (size_t)A.ntiles == 0) return 0;
+    const int capacity = num_sms * blocks_per_sm;
+    Sweep2Args<M, NF> PP;
+    PP.whalo = whalo;
+    choose_segments(A.rows, A.ntiles, whalo, capacity, &PP.nseg, &PP.seglen);
+    const long long items = (long long)A.rows * PP.nseg;
+    const unsigned grid = (unsigned)std::min<long long>(items, capacity);
+    PP.a = A;
     {
         KernelScope ks(c, name);
-        sweep_kernel<M, NF, NIN, DIR><<<(unsigned)items, kT, smem, c->stream>>>(A);
+        kern<<<grid, kT, smem, c->stream>>>(PP);
     }
     MM_CUDA(cudaGetLastError());
     return 0;
+}
+
+static int halo_tiles(const FilterPlan* const* plans, int nf) {
+    int w = 1;
+    for (int f = 0; f < nf; ++f) w = std::max(w, plans[f]->tabs.W);   // 1e-18: results do not depend on the segmentation
+    return w;
 }
 
 template <int M, int NF>
@@ -96,17 +130,17 @@ int sweep_fwd(mm_ctx* c, const mm_geom* g, int nf, int nin, const FilterPlan* co
     const int m = plans[0]->ba.m;
     for (int f = 0; f < nf; ++f)
         if (plans[f]->ba.m != m) { set_error("mixed section orders in one sweep"); return 1; }
-#define MM_FWD(M_, NF_, NIN_)                                                     \
+#define MM_FWD(M_, NF_, NIN_, ST_)                                                \
     {                                                                             \
         SweepArgs<M_, NF_> A;                                                     \
         fill_common<M_, NF_>(A, g, plans, in, nin, out, nf, pro, epi, pad);       \
-        return launch_sweep<M_, NF_, NIN_, +1>(c, A, "sweep_fwd_m" #M_ "_f" #NF_ "_i" #NIN_); \
+        return launch_sweep2<M_, NF_, NIN_, +1, EPI_STORE, 0, ST_>(c, A, halo_tiles(plans, nf), "sweep_fwd_m" #M_ "_f" #NF_ "_i" #NIN_); \
     }
-    if (m == 2 && nf == 1 && nin == 1) MM_FWD(2, 1, 1)
-    if (m == 2 && nf == 2 && nin == 1) MM_FWD(2, 2, 1)
-    if (m == 2 && nf == 2 && nin == 2) MM_FWD(2, 2, 2)
-    if (m == 2 && nf == 4 && nin == 1) MM_FWD(2, 4, 1)
-    if (m == 4 && nf == 1 && nin == 1) MM_FWD(4, 1, 1)
+    if (m == 2 && nf == 1 && nin == 1) MM_FWD(2, 1, 1, 2)
+    if (m == 2 && nf == 2 && nin == 1) MM_FWD(2, 2, 1, 2)
+    if (m == 2 && nf == 2 && nin == 2) MM_FWD(2, 2, 2, 2)
+    if (m == 2 && nf == 4 && nin == 1) MM_FWD(2, 4, 1, 2)
+    if (m == 4 && nf == 1 && nin == 1) MM_FWD(4, 1, 1, 2)
 #undef MM_FWD
     set_error("no forward sweep instantiation for order %d, %d filters, %d inputs", m, nf, nin);
     return 1;
@@ -115,18 +149,29 @@ int sweep_fwd(mm_ctx* c, const mm_geom* g, int nf, int nin, const FilterPlan* co
 int sweep_bwd(mm_ctx* c, const mm_geom* g, int nf, const FilterPlan* const* plans, const float* const* in,
               float* const* out, int nout, const Epi& epi, int pad) {
     const int m = plans[0]->ba.m;
-#define MM_BWD(M_, NF_)                                                           \
+    const int naux = (epi.mode == EPI_STORE) ? 0 : ((epi.aux1 != nullptr) ? 2 : 1);
+    if (epi.mode != EPI_STORE && epi.aux0 == nullptr) { set_error("backward sweep epilogue needs its x-domain stream"); return 1; }
+#define MM_BWD(M_, NF_, EPI_, NAUX_, ST_, TAG_)                                   \
     {                                                                             \
         SweepArgs<M_, NF_> A;                                                     \
         fill_common<M_, NF_>(A, g, plans, in, nf, out, nout, epi.auxp, epi, pad); \
-        return launch_sweep<M_, NF_, NF_, -1>(c, A, "sweep_bwd_m" #M_ "_f" #NF_); \
+        return launch_sweep2<M_, NF_, NF_, -1, EPI_, NAUX_, ST_>(c, A, halo_tiles(plans, nf), "sweep_bwd_m" #M_ "_f" #NF_ TAG_); \
     }
-    if (m == 2 && nf == 1) MM_BWD(2, 1)
-    if (m == 2 && nf == 2) MM_BWD(2, 2)
-    if (m == 2 && nf == 4) MM_BWD(2, 4)
-    if (m == 4 && nf == 1) MM_BWD(4, 1)
+    if (m == 2 && nf == 1 && epi.mode == EPI_STORE) MM_BWD(2, 1, EPI_STORE, 0, 2, "_store")
+    if (m == 2 && nf == 1 && epi.mode == EPI_COMBINE && naux == 1) MM_BWD(2, 1, EPI_COMBINE, 1, 2, "_combine")
+    if (m == 2 && nf == 1 && epi.mode == EPI_EXCITER && naux == 1) MM_BWD(2, 1, EPI_EXCITER, 1, 2, "_exciter")
+    if (m == 2 && nf == 2 && epi.mode == EPI_STORE) MM_BWD(2, 2, EPI_STORE, 0, 2, "_store")
+    if (m == 2 && nf == 2 && epi.mode == EPI_COMBINE && naux == 1) MM_BWD(2, 2, EPI_COMBINE, 1, 2, "_combine")
+    if (m == 2 && nf == 2 && epi.mode == EPI_DYNAMICS && naux == 2) MM_BWD(2, 2, EPI_DYNAMICS, 2, 2, "_dynamics")
+    if (m == 2 && nf == 4 && epi.mode == EPI_COMBINE && naux == 1) MM_BWD(2, 4, EPI_COMBINE, 1, 1, "_combine")
+    if (m == 4 && nf == 1 && epi.mode == EPI_STORE) MM_BWD(4, 1, EPI_STORE, 0, 2, "_store")
 #undef MM_BWD
-    set_error("no backward sweep instantiation for order %d, %d filters", m, nf);
+    if (m == 2 && nf == 4 && epi.mode == EPI_STORE && nout == 4) {
+        // four independent sections: two 2-section sweeps move the same bytes and fit two CTAs per SM
+        MM_TRY(sweep_bwd(c, g, 2, plans, in, out, 2, epi, pad));
+        return sweep_bwd(c, g, 2, plans + 2, in + 2, out + 2, 2, epi, pad);
+    }
+    set_error("no backward sweep instantiation for order %d, %d filters, epilogue %d, %d aux", m, nf, epi.mode, naux);
     return 1;
 }
 
@@ -250,6 +295,11 @@ void fill_dyn(DynParams* d, double knee_db, const double* band_ratios, double ma
         b.slope = (b.upper > b.lower) ? (b.thr + (b.upper - b.thr) / ratio - b.lower) / (b.upper - b.lower) : 1.0;
         b.lim = (float)std::pow(10.0, lim_db / 20.0);
         b.gain = (float)gain;
+        b.thr_f = (float)b.thr;
+        b.inv_ratio_f = (float)(1.0 / ratio);
+        b.lower_f = (float)b.lower;
+        b.upper_f = (float)b.upper;
+        b.slope_f = (float)b.slope;
         if (ratio <= 0.0 || ratio == 1.0) b.mode = 0;
         else if (ratio < 1.0) b.mode = 3;
         else if (knee_db < 0.5) b.mode = 1;

@@ -1,0 +1,568 @@
+// Persistent, software-pipelined zero-phase / causal IIR sweep kernel ("kernel (1)" of the north star).
+//
+// One CTA owns a stream of tiles (ticket order, tile-major across rows, see sweep.cuh for why that
+// order guarantees forward progress of the look-back).  Per tile of kL = 4096 samples of one row:
+//
+//   cp.async ring (kST stages)  : the NIN input streams of the NEXT tile land in shared memory while the
+//                                  current tile is being scanned; the x-domain aux streams an epilogue needs
+//                                  are fetched asynchronously at tile start and waited for only before use
+//   pass 1   (per thread)        : zero-state end state of its 32 samples, E = sum_j g[j] x_j   (2 DFMA/sample)
+//   warp scan / tile Horner      : 2x2 (4x4) state-transfer powers, tables in shared memory
+//   look-back (warp f = filter f): truncated decoupled look-back over zero-state aggregates
+//   pass 2   (per thread)        : the DF2T recurrence from the resolved state, float32 results into smem
+//   epilogue                     : coalesced float4 stores / recombination / dynamics / exciter, peak tracking
+//
+// Shared-memory tiles are stored as 1024 16-byte vectors with the 128-byte XOR swizzle
+//   phys(chunk, u) = chunk * 8 + (u ^ (chunk & 7))
+// so that both access patterns are bank-conflict free: the coalesced one (8 consecutive threads touch one
+// chunk) and the scan one (thread t walks chunk t).
+#pragma once
+#include "pointwise.cuh"
+#include "sweep.cuh"
+
+namespace mm {
+
+constexpr int kWcap = 16;          // look-back powers kept in shared memory (longer windows read the global table)
+constexpr int kTileVecs = kL / 4;  // float4 per stream tile
+
+template <int M> struct SmemTab {
+    double Pw[5][M * M];
+    double Plane[32][M * M];
+    double Qpow[kNW + 1][M * M];
+    double Mpow[kWcap][M * M];
+};
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
+
+__device__ __forceinline__ int swz(int v) { return (v & ~7) | ((v ^ (v >> 3)) & 7); }   // v = chunk * 8 + u
+
+template <int M> __device__ __forceinline__ void matvec_acc_s(const double* p, const double (&v)[M], double (&acc)[M]) {
+#pragma unroll
+    for (int i = 0; i < M; ++i) {
+        double s = acc[i];
+#pragma unroll
+        for (int k = 0; k < M; ++k) s = fma(p[i * M + k], v[k], s);
+        acc[i] = s;
+    }
+}
+
+template <int M, int NF> struct Sweep2Args {
+    SweepArgs<M, NF> a;
+    unsigned total;       // number of (row, tile) work items
+};
+
+template <int M, int NF, int NIN, int DIR, int EPI, int NAUX, int ST>
+struct Sweep2Cfg {
+    static constexpr int kExtra = NF > NIN ? NF - NIN : 0;
+    static constexpr size_t kTileBytes = (size_t)kL * sizeof(float);
+    static constexpr size_t kRing = (size_t)ST * NIN * kTileBytes;
+    static constexpr size_t kExtraOff = kRing;
+    static constexpr size_t kAuxOff = kExtraOff + kExtra * kTileBytes;
+    static constexpr size_t kTabOff = kAuxOff + NAUX * kTileBytes;
+    static constexpr size_t kBytes = kTabOff + NF * sizeof(SmemTab<M>);
+};
+
+template <int M, int NF> struct Scratch2 {
+    double tot[NF][kNW][M];
+    double carry[NF][M];
+    unsigned next_ticket;
+};
+
+// prologue helpers (see common.cuh PRO_*)
+__device__ __forceinline__ float pro1(int mode, float x, float subf, float mulf, double muld) {
+    if (mode == PRO_SUBMUL_F32) return __fmul_rn(__fsub_rn(x, subf), mulf);
+    if (mode == PRO_MUL_F64) return (float)((double)x * muld);
+    return x;
+}
+
+template <int M, int NF, int NIN, int DIR, int EPI, int NAUX, int ST>
+__global__ void __launch_bounds__(kT) sweep2_kernel(const __grid_constant__ Sweep2Args<M, NF> PP) {
+    typedef Sweep2Cfg<M, NF, NIN, DIR, EPI, NAUX, ST> Cfg;
+    const SweepArgs<M, NF>& P = PP.a;
+    extern __shared__ __align__(128) unsigned char smraw[];
+    float* ring = reinterpret_cast<float*>(smraw);
+    float* extra = reinterpret_cast<float*>(smraw + Cfg::kExtraOff);
+    float* auxs = reinterpret_cast<float*>(smraw + Cfg::kAuxOff);
+    SmemTab<M>* tab = reinterpret_cast<SmemTab<M>*>(smraw + Cfg::kTabOff);
+    __shared__ Scratch2<M, NF> sh;
+    constexpr int MM = M * M;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    // ---- one-time: scan tables into shared memory -------------------------------------------------
+#pragma unroll 1
+    for (int f = 0; f < NF; ++f) {
+        const double* g = P.tab[f];
+        double* d = reinterpret_cast<double*>(&tab[f]);
+        for (int i = tid; i < (5 + 32 + kNW + 1) * MM; i += kT) d[i] = __ldg(g + i);   // Pw, Plane, Qpow are contiguous
+        const int wn = min(P.W[f], kWcap);
+        for (int i = tid; i < wn * MM; i += kT) tab[f].Mpow[0][i] = __ldg(g + Tab<M>::Mpow + i);
+    }
+
+    const long long q_first = kLead - P.pad;
+    const long long q_last = kLead + P.n + P.pad - 1;
+    const long long qend = (q_last + 4) & ~3LL;             // BWD: one past the last tile-0 position
+    const int dead0 = (DIR > 0) ? (int)q_first : (int)(qend - 1 - q_last);
+    // store range of this sweep (inclusive)
+    const long long st_lo = (DIR > 0) ? q_first : (long long)kLead;
+    const long long st_hi = (DIR > 0) ? q_last : (long long)(kLead + P.n - 1);
+
+    auto tile_origin = [&](int tile) -> long long {
+        return (DIR > 0) ? (long long)tile * kL : qend - (long long)(tile + 1) * kL;
+    };
+    // can the tile's inputs be fetched with unconditional 16-byte async copies?
+    auto fast_in = [&](long long lo) -> bool {
+        return (DIR > 0) ? (lo >= kLead && lo + kL <= kLead + P.n) : (lo >= q_first && lo + kL - 1 <= q_last);
+    };
+    auto fast_out = [&](long long lo) -> bool { return lo >= st_lo && lo + kL - 1 <= st_hi; };
+
+    // ---- loaders ------------------------------------------------------------------------------------
+    auto issue_inputs = [&](unsigned ticket, int slot) {
+        const int tile = (int)(ticket / (unsigned)P.rows);
+        const int row = (int)(ticket - (unsigned)tile * (unsigned)P.rows);
+        const long long lo = tile_origin(tile);
+        const size_t rowoff = (size_t)row * (size_t)P.stride;
+        if (fast_in(lo)) {
+#pragma unroll
+            for (int s = 0; s < NIN; ++s) {
+                const float* src = P.in[s] + rowoff + lo;
+                float* dst = ring + ((size_t)slot * NIN + s) * kL;
+#pragma unroll
+                for (int r = 0; r < kTileVecs / kT; ++r) {
+                    const int v = tid + kT * r;
+                    cp_async16(dst + 4 * swz(v), src + 4 * v);
+                }
+            }
+        } else {
+            // edge tile: synchronous, with prologue, scipy's odd extension and dead zeros applied here
+            float subf = 0.f, mulf = 1.f;
+            double muld = 1.0;
+            if (P.pro_mode != PRO_NONE) {
+                if (P.pro_sub) subf = (float)__ldg(P.pro_sub + row);
+                if (P.pro_mul) { muld = __ldg(P.pro_mul + row); mulf = (float)muld; }
+            }
+#pragma unroll 1
+            for (int s = 0; s < NIN; ++s) {
+                const float* src = P.in[s] + rowoff;
+                float* dst = ring + ((size_t)slot * NIN + s) * kL;
+#pragma unroll 1
+                for (int r = 0; r < kTileVecs / kT; ++r) {
+                    const int v = tid + kT * r;
+                    const long long q = lo + 4 * v;
+                    float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (q + 3 >= q_first && q <= q_last) {
+                        if (DIR > 0) {
+                            const float x_lo = pro1(P.pro_mode, src[kLead], subf, mulf, muld);
+                            const float x_hi = pro1(P.pro_mode, src[kLead + P.n - 1], subf, mulf, muld);
+#pragma unroll
+                            for (int c = 0; c < 4; ++c) {
+                                const long long i = q + c - kLead;
+                                float e = 0.f;
+                                if (i >= 0 && i < P.n) e = pro1(P.pro_mode, src[kLead + i], subf, mulf, muld);
+                                else if (i < 0 && i >= -(long long)P.pad)
+                                    e = __fsub_rn(__fmul_rn(2.f, x_lo), pro1(P.pro_mode, src[kLead - i], subf, mulf, muld));
+                                else if (i >= P.n && i < P.n + P.pad)
+                                    e = __fsub_rn(__fmul_rn(2.f, x_hi), pro1(P.pro_mode, src[kLead + 2 * (P.n - 1) - i], subf, mulf, muld));
+                                setcomp4(val, c, e);
+                            }
+                        } else {
+#pragma unroll
+                            for (int c = 0; c < 4; ++c) {
+                                const long long qq = q + c;
+                                setcomp4(val, c, (qq >= q_first && qq <= q_last) ? src[qq] : 0.f);
+                            }
+                        }
+                    }
+                    *reinterpret_cast<float4*>(dst + 4 * swz(v)) = val;
+                }
+            }
+        }
+    };
+    auto issue_aux = [&](int row, long long lo) {
+        if (NAUX == 0) return;
+        if (!fast_out(lo)) return;     // edge tiles read aux straight from global in the epilogue
+        const size_t rowoff = (size_t)row * (size_t)P.stride;
+#pragma unroll
+        for (int s = 0; s < NAUX; ++s) {
+            const float* src = P.aux[s] + rowoff + lo;
+            float* dst = auxs + (size_t)s * kL;
+#pragma unroll
+            for (int r = 0; r < kTileVecs / kT; ++r) {
+                const int v = tid + kT * r;
+                cp_async16(dst + 4 * swz(v), src + 4 * v);
+            }
+        }
+    };
+
+    // ---- ticket pipeline ----------------------------------------------------------------------------
+    if (tid == 0) sh.next_ticket = atomicAdd(P.ticket, 1u) - P.ticket_base;
+    __syncthreads();
+    unsigned cur = sh.next_ticket;
+    int slot = 0;
+    if (cur < PP.total) issue_inputs(cur, 0);
+    cp_async_commit();
+    __syncthreads();                                   // everyone has read next_ticket
+    if (tid == 0 && cur < PP.total) sh.next_ticket = (ST > 1) ? atomicAdd(P.ticket, 1u) - P.ticket_base : 0xffffffffu;
+
+#pragma unroll 1
+    while (cur < PP.total) {
+        __syncthreads();                               // (A) previous tile fully stored; next_ticket visible
+        const int tile = (int)(cur / (unsigned)P.rows);
+        const int row = (int)(cur - (unsigned)tile * (unsigned)P.rows);
+        const long long tile_lo = tile_origin(tile);
+        const size_t rowoff = (size_t)row * (size_t)P.stride;
+        unsigned nxt = 0xffffffffu;
+        issue_aux(row, tile_lo);
+        cp_async_commit();                             // group: aux(cur)
+        if (ST > 1) {
+            nxt = sh.next_ticket;
+            if (nxt < PP.total) issue_inputs(nxt, slot ^ 1);
+            cp_async_commit();                         // group: inputs(next)
+            cp_async_wait<2>();                        // inputs(cur) have landed (this thread's part)
+        } else {
+            cp_async_wait<1>();
+        }
+        __syncthreads();                               // (B) inputs(cur) visible to all threads
+        // claim the ticket after next now, publish it late (before barrier (E)): the atomic's round trip
+        // to L2 then overlaps the whole scan instead of stalling warp 0
+        unsigned claimed = 0xffffffffu;
+        if (tid == 0 && (ST == 1 || nxt < PP.total)) claimed = atomicAdd(P.ticket, 1u) - P.ticket_base;
+
+        float* tin = ring + (size_t)slot * NIN * kL;
+        const bool in_fast = fast_in(tile_lo);
+        const bool inject = (tile == 0) && (P.pad > 0);
+        const int dead = (tile == 0) ? dead0 : 0;
+        const int d0 = dead;                           // dead < kS always (pad <= 15, lead 32)
+        const bool inj_thread = inject && tid == 0;
+
+        // prologue constants: edge tiles were transformed by their loader already
+        int pmode = PRO_NONE;
+        float subf = 0.f, mulf = 1.f;
+        double muld = 1.0;
+        if (DIR > 0 && in_fast && P.pro_mode != PRO_NONE) {
+            pmode = P.pro_mode;
+            if (P.pro_sub) subf = (float)__ldg(P.pro_sub + row);
+            if (P.pro_mul) { muld = __ldg(P.pro_mul + row); mulf = (float)muld; }
+        }
+
+        const int chunk = (DIR > 0) ? tid : (kT - 1 - tid);
+        const int cbase = chunk * 32;                  // float index of this thread's chunk
+        const int cx = (chunk & 7) << 2;               // float-index XOR of the swizzle
+        // address of logical vec u of this chunk in stream buffer b: b + cbase + ((4u) ^ cx)
+
+        // ---- pass 1 -----------------------------------------------------------------------------------
+        double E[NF][M];
+#pragma unroll
+        for (int f = 0; f < NF; ++f)
+#pragma unroll
+            for (int i = 0; i < M; ++i) E[f][i] = 0.0;
+#pragma unroll
+        for (int u = 0; u < kS / 4; ++u) {
+            const int uu = (DIR > 0) ? u : (kS / 4 - 1 - u);
+            float4 xv[NIN];
+#pragma unroll
+            for (int s = 0; s < NIN; ++s) {
+                float* p = tin + (size_t)s * kL + cbase + ((4 * uu) ^ cx);
+                xv[s] = *reinterpret_cast<const float4*>(p);
+                if (pmode != PRO_NONE) {
+                    xv[s].x = pro1(pmode, xv[s].x, subf, mulf, muld);
+                    xv[s].y = pro1(pmode, xv[s].y, subf, mulf, muld);
+                    xv[s].z = pro1(pmode, xv[s].z, subf, mulf, muld);
+                    xv[s].w = pro1(pmode, xv[s].w, subf, mulf, muld);
+                    *reinterpret_cast<float4*>(p) = xv[s];
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const int cc = (DIR > 0) ? c : (3 - c);
+                const int j = 4 * u + c;
+                double xd[NIN];
+#pragma unroll
+                for (int s = 0; s < NIN; ++s) xd[s] = (double)comp4(xv[s], cc);
+#pragma unroll
+                for (int f = 0; f < NF; ++f)
+#pragma unroll
+                    for (int i = 0; i < M; ++i) E[f][i] = fma(P.f[f].g[j][i], xd[NIN == 1 ? 0 : f], E[f][i]);
+            }
+        }
+        if (inj_thread) {
+            // scipy's filtfilt start: state zi * x_first, injected `d0` samples into this chunk
+            const int mi = (DIR > 0) ? d0 : (kS - 1 - d0);
+            const int off = cbase + (((mi >> 2) << 2) ^ cx) + (mi & 3);
+#pragma unroll
+            for (int f = 0; f < NF; ++f) {
+                const float x0 = tin[(size_t)(NIN == 1 ? 0 : f) * kL + off];
+                double si[M];
+#pragma unroll
+                for (int i = 0; i < M; ++i) si[i] = __ldg(P.tab[f] + Tab<M>::Zi + i) * (double)x0;
+                matvec_acc<M>(P.tab[f] + Tab<M>::Apow + (kS - d0) * MM, si, E[f]);
+            }
+        }
+
+        // ---- warp scan ----------------------------------------------------------------------------------
+#pragma unroll
+        for (int d = 0; d < 5; ++d) {
+#pragma unroll
+            for (int f = 0; f < NF; ++f) {
+                double pe[M];
+#pragma unroll
+                for (int i = 0; i < M; ++i) pe[i] = shfl_up_d(E[f][i], 1 << d);
+                if (lane >= (1 << d)) matvec_acc_s<M>(tab[f].Pw[d], pe, E[f]);
+            }
+        }
+        if (lane == 31) {
+#pragma unroll
+            for (int f = 0; f < NF; ++f)
+#pragma unroll
+                for (int i = 0; i < M; ++i) sh.tot[f][warp][i] = E[f][i];
+        }
+        __syncthreads();                               // (C)
+
+        double base[NF][M];
+#pragma unroll
+        for (int f = 0; f < NF; ++f) {
+#pragma unroll
+            for (int i = 0; i < M; ++i) base[f][i] = 0.0;
+            for (int v = 0; v < warp; ++v) {
+                double nb[M];
+#pragma unroll
+                for (int i = 0; i < M; ++i) nb[i] = sh.tot[f][v][i];
+                matvec_acc_s<M>(tab[f].Qpow[1], base[f], nb);
+#pragma unroll
+                for (int i = 0; i < M; ++i) base[f][i] = nb[i];
+            }
+        }
+
+        // ---- publish the zero-state aggregate, look back ---------------------------------------------------
+        const size_t fstride = (size_t)P.rows * (size_t)P.ntiles;
+        const size_t slot0 = (size_t)row * (size_t)P.ntiles + tile;
+        if (tid == kT - 1) {
+#pragma unroll
+            for (int f = 0; f < NF; ++f) {
+                double ag[M];
+#pragma unroll
+                for (int i = 0; i < M; ++i) ag[i] = E[f][i];
+                matvec_acc_s<M>(tab[f].Qpow[1], base[f], ag);
+                double* dst = P.agg + (slot0 + f * fstride) * M;
+#pragma unroll
+                for (int i = 0; i < M; ++i) __stcg(dst + i, ag[i]);
+            }
+            __threadfence();
+#pragma unroll
+            for (int f = 0; f < NF; ++f) *reinterpret_cast<volatile unsigned*>(P.flag + slot0 + f * fstride) = P.epoch;
+        }
+        if (warp < NF) {
+            const int f = warp;
+            double C[M];
+#pragma unroll
+            for (int i = 0; i < M; ++i) C[i] = 0.0;
+            const int Wf = P.W[f];
+            for (int j0 = 0; j0 < Wf && j0 < tile; j0 += 32) {
+                const int j = j0 + lane;
+                double c[M];
+#pragma unroll
+                for (int i = 0; i < M; ++i) c[i] = 0.0;
+                if (j < Wf && j < tile) {
+                    const size_t sl = slot0 + f * fstride - 1 - j;
+                    unsigned spins = 0;
+                    while (ld_volatile_u32(P.flag + sl) != P.epoch) {
+                        if (++spins > (1u << 22)) { atomicExch(P.err, 1); break; }
+                        __nanosleep(20);
+                    }
+                    __threadfence();
+                    double a[M];
+#pragma unroll
+                    for (int i = 0; i < M; ++i) a[i] = __ldcg(P.agg + sl * M + i);
+                    if (j < kWcap) matvec_acc_s<M>(tab[f].Mpow[j], a, c);
+                    else matvec_acc<M>(P.tab[f] + Tab<M>::Mpow + j * MM, a, c);
+                }
+#pragma unroll
+                for (int i = 0; i < M; ++i) {
+                    double v = c[i];
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) v += shfl_xor_d(v, o);
+                    C[i] += v;
+                }
+            }
+            if (lane == 0) {
+#pragma unroll
+                for (int i = 0; i < M; ++i) sh.carry[f][i] = C[i];
+            }
+        }
+        __syncthreads();                               // (D)
+
+        // ---- incoming state of this thread -------------------------------------------------------------------
+        double z[NF][M];
+#pragma unroll
+        for (int f = 0; f < NF; ++f) {
+            double C[M];
+#pragma unroll
+            for (int i = 0; i < M; ++i) C[i] = sh.carry[f][i];
+            matvec_acc_s<M>(tab[f].Qpow[warp], C, base[f]);
+#pragma unroll
+            for (int i = 0; i < M; ++i) {
+                const double up = shfl_up_d(E[f][i], 1);
+                z[f][i] = (lane > 0) ? up : 0.0;
+            }
+            matvec_acc_s<M>(tab[f].Plane[lane], base[f], z[f]);
+        }
+
+        // ---- pass 2 ------------------------------------------------------------------------------------------
+        float* tout[NF];
+#pragma unroll
+        for (int f = 0; f < NF; ++f) tout[f] = (f < NIN) ? (tin + (size_t)f * kL) : (extra + (size_t)(f - NIN) * kL);
+        if (!inj_thread) {
+#pragma unroll
+            for (int u = 0; u < kS / 4; ++u) {
+                const int uu = (DIR > 0) ? u : (kS / 4 - 1 - u);
+                const int off = cbase + ((4 * uu) ^ cx);
+                float4 xv[NIN];
+#pragma unroll
+                for (int s = 0; s < NIN; ++s) xv[s] = *reinterpret_cast<const float4*>(tin + (size_t)s * kL + off);
+                float4 yv[NF];
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const int cc = (DIR > 0) ? c : (3 - c);
+                    double xd[NIN];
+#pragma unroll
+                    for (int s = 0; s < NIN; ++s) xd[s] = (double)comp4(xv[s], cc);
+#pragma unroll
+                    for (int f = 0; f < NF; ++f) {
+                        const double y = df2t_step<M>(P.f[f], xd[NIN == 1 ? 0 : f], z[f]);
+                        setcomp4(yv[f], cc, (float)y);
+                    }
+                }
+#pragma unroll
+                for (int f = 0; f < NF; ++f) *reinterpret_cast<float4*>(tout[f] + off) = yv[f];
+            }
+        } else {
+            // the one thread of tile 0 that starts from zi * x_first after `d0` dead samples
+#pragma unroll 1
+            for (int j = 0; j < kS; ++j) {
+                const int mi = (DIR > 0) ? j : (kS - 1 - j);
+                const int off = cbase + (((mi >> 2) << 2) ^ cx) + (mi & 3);
+                float xs[NIN];
+#pragma unroll
+                for (int s = 0; s < NIN; ++s) xs[s] = tin[(size_t)s * kL + off];
+                if (j == d0) {
+#pragma unroll
+                    for (int f = 0; f < NF; ++f)
+#pragma unroll
+                        for (int i = 0; i < M; ++i) z[f][i] = __ldg(P.tab[f] + Tab<M>::Zi + i) * (double)xs[NIN == 1 ? 0 : f];
+                }
+#pragma unroll
+                for (int f = 0; f < NF; ++f) {
+                    const double y = df2t_step<M>(P.f[f], (double)xs[NIN == 1 ? 0 : f], z[f]);
+                    tout[f][off] = (float)y;
+                }
+            }
+        }
+        if (NAUX > 0) { if (ST > 1) cp_async_wait<1>(); else cp_async_wait<0>(); }   // aux(cur) landed
+        if (tid == 0) sh.next_ticket = claimed;        // read after barrier (A) of the next iteration
+        __syncthreads();                               // (E) results (and aux) visible
+
+        // ---- epilogue / store -----------------------------------------------------------------------------------
+        const bool out_fast = fast_out(tile_lo);
+        float aux_subf = 0.f, aux_mulf = 1.f;
+        double aux_muld = 1.0;
+        if (EPI != EPI_STORE && P.aux_pro && P.pro_mode != PRO_NONE) {
+            if (P.pro_sub) aux_subf = (float)__ldg(P.pro_sub + row);
+            if (P.pro_mul) { aux_muld = __ldg(P.pro_mul + row); aux_mulf = (float)aux_muld; }
+        }
+        float pk = 0.f;
+#pragma unroll 2
+        for (int r = 0; r < kTileVecs / kT; ++r) {
+            const int v = tid + kT * r;
+            const long long q = tile_lo + 4 * v;
+            if (!out_fast && (q + 3 < st_lo || q > st_hi)) continue;
+            const bool full = out_fast || (q >= st_lo && q + 3 <= st_hi);
+            const int so = 4 * swz(v);
+            float4 y[NF];
+#pragma unroll
+            for (int f = 0; f < NF; ++f) y[f] = *reinterpret_cast<const float4*>(tout[f] + so);
+            if (EPI == EPI_STORE) {
+#pragma unroll
+                for (int f = 0; f < NF; ++f) {
+                    float* dst = P.out[f] + rowoff;
+                    if (full) __stcs(reinterpret_cast<float4*>(dst + q), y[f]);
+                    else {
+#pragma unroll
+                        for (int c = 0; c < 4; ++c)
+                            if (q + c >= st_lo && q + c <= st_hi) dst[q + c] = comp4(y[f], c);
+                    }
+                }
+            } else {
+                float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0, o;
+                if (out_fast) {
+                    if (NAUX > 0) a0 = *reinterpret_cast<const float4*>(auxs + so);
+                    if (NAUX > 1) a1 = *reinterpret_cast<const float4*>(auxs + kL + so);
+                } else {
+                    const float* x0 = (NAUX > 0) ? P.aux[0] + rowoff : nullptr;
+                    const float* x1 = (NAUX > 1) ? P.aux[1] + rowoff : nullptr;
+#pragma unroll
+                    for (int c = 0; c < 4; ++c)
+                        if (q + c >= st_lo && q + c <= st_hi) {
+                            if (NAUX > 0) setcomp4(a0, c, x0[q + c]);
+                            if (NAUX > 1) setcomp4(a1, c, x1[q + c]);
+                        }
+                }
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    float xa = comp4(a0, c);
+                    if (P.aux_pro) xa = pro1(P.pro_mode, xa, aux_subf, aux_mulf, aux_muld);
+                    float res;
+                    if (EPI == EPI_COMBINE) {
+                        double acc = P.wc * (double)xa;
+#pragma unroll
+                        for (int f = 0; f < NF; ++f) acc += P.w[f] * (double)comp4(y[f], c);
+                        res = (float)(acc * P.trim);
+                    } else if (EPI == EPI_EXCITER) {
+                        const double hf = (double)comp4(y[0], c);
+                        const double sat = exciter_sat(hf, P.exc_mode, P.exc_k);
+                        res = (float)((double)xa + (sat - hf) * P.exc_gain * 0.25);
+                    } else {   // EPI_DYNAMICS: aux0 = band 1, y0 = band 2, y1 = band 3, aux1 = band 4
+                        float s = band_chain(xa, P.dyn.band[0]);
+                        s = __fadd_rn(s, band_chain(comp4(y[0], c), P.dyn.band[1]));
+                        s = __fadd_rn(s, band_chain(comp4(y[NF > 1 ? 1 : 0], c), P.dyn.band[2]));
+                        s = __fadd_rn(s, band_chain(comp4(a1, c), P.dyn.band[3]));
+                        res = maximize_limit(s, P.dyn);
+                        if (P.dyn.par_mix) {
+                            const double mix = __ldg(P.dyn.par_mix + row);
+                            if (mix >= 0.01) res = parallel_compress(res, mix, P.dyn);
+                        }
+                    }
+                    setcomp4(o, c, res);
+                    if (full || (q + c >= st_lo && q + c <= st_hi)) pk = fmaxf(pk, fabsf(res));
+                }
+                float* dst = P.out[0] + rowoff;
+                if (full) __stcs(reinterpret_cast<float4*>(dst + q), o);
+                else {
+#pragma unroll
+                    for (int c = 0; c < 4; ++c)
+                        if (q + c >= st_lo && q + c <= st_hi) dst[q + c] = comp4(o, c);
+                }
+            }
+        }
+        if (EPI != EPI_STORE && P.peak != nullptr) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) pk = fmaxf(pk, __shfl_xor_sync(0xffffffffu, pk, o));
+            if (lane == 0 && pk > 0.f) atomicMax(reinterpret_cast<int*>(P.peak + row / P.channels), __float_as_int(pk));
+        }
+
+        if (ST > 1) { cur = nxt; slot ^= 1; }
+        else {
+            __syncthreads();                           // single stage: everyone done with the buffer, ticket visible
+            cur = sh.next_ticket;
+            if (cur < PP.total) issue_inputs(cur, 0);
+            cp_async_commit();
+        }
+    }
+    cp_async_wait<0>();
+}
+
+}  // namespace mm

@@ -42,11 +42,17 @@ def test_lufs_edge_cases(P):
     assert np.isnan(P.measure_lufs(np.zeros((1000, 2), np.float32), sr))        # shorter than one block
     v = P.measure_lufs(np.zeros((sr, 2), np.float32), sr)                        # silence: -inf (tests accept <= -50)
     assert np.isnan(v) or v <= -50
-    # BS.1770 known answer: 997 Hz full-scale sine in both channels reads 0.0 LKFS (-3.01 in one)
+    # BS.1770 known answer: 997 Hz full-scale sine in both channels reads 0.0 LKFS (-3.01 in one);
+    # pyloudnorm's RBJ-form K-weighting is ~0.04 dB off the standard's table at 997 Hz, the oracle
+    # restates pyloudnorm, and the kernel must follow the oracle closely
+    from oracle import chain as oc
     t = np.arange(sr * 3) / sr
     s = np.sin(2 * np.pi * 997 * t).astype(np.float32)
-    assert abs(P.measure_lufs(np.stack([s, s], axis=1), sr) - 0.0) <= 0.02
-    assert abs(P.measure_lufs(np.stack([s, np.zeros_like(s)], axis=1), sr) - (-3.01)) <= 0.02
+    both, one = np.stack([s, s], axis=1), np.stack([s, np.zeros_like(s)], axis=1)
+    assert abs(P.measure_lufs(both, sr) - 0.0) <= 0.06
+    assert abs(P.measure_lufs(one, sr) - (-3.01)) <= 0.06
+    assert abs(P.measure_lufs(both, sr) - oc.measure_lufs(both, sr)) <= 1e-4
+    assert abs(P.measure_lufs(one, sr) - oc.measure_lufs(one, sr)) <= 1e-4
 
 
 def test_lufs_many_blocks_vs_oracle(P):
