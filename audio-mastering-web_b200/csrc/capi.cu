@@ -216,18 +216,9 @@ static int master_impl(mm_ctx* c, const mm_geom* g, int chain, const mm_style* s
         O.limit = (float)std::pow(10.0, -0.5 / 20.0);
         O.mul = d_mulout; O.peak_track = d_peakout;
         MM_TRY(run_out_scalars(c, O));
-        PwArgs A;
-        pw_base(&A, out, out, PW_FINALIZE);
-        A.mul = d_mulout;
-        A.width = any_img ? d_width : nullptr;
         const bool fade = v1 || !(flags & MM_FLAG_NO_JOB_FADE);
-        A.n_fade = fade ? fade_len(g, 6.0) : 0;
-        A.fade_step = A.n_fade > 1 ? 1.0 / (double)(A.n_fade - 1) : 0.0;
-        A.pcm = pcm;
-        A.noise = noise;
-        A.seed = seed;
-        A.nonfinite = d_nonfinite;
-        MM_TRY(run_pointwise(c, g, A, pcm ? "finalize_dither_int16" : "finalize"));
+        MM_TRY(run_finalize(c, g, out, out, d_mulout, any_img ? d_width : nullptr, fade ? fade_len(g, 6.0) : 0, pcm, noise, seed,
+                            d_nonfinite));
     }
     if (flags & MM_FLAG_MEASURE_OUT) {
         MM_TRY(arena(c, SL_LUFS3, (size_t)T, &d_lufs_out));
@@ -286,12 +277,6 @@ int mm_ctx_create(int device, void* stream, mm_ctx** out) {
         if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; set_error("cudaStreamCreate failed"); return 1; }
         c->own_stream = true;
     }
-    if (cudaMalloc(&c->ticket, sizeof(unsigned)) != cudaSuccess || cudaMalloc(&c->err, sizeof(int)) != cudaSuccess) {
-        delete c; set_error("cudaMalloc(context scalars) failed"); return 1;
-    }
-    cudaMemsetAsync(c->ticket, 0, sizeof(unsigned), c->stream);
-    cudaMemsetAsync(c->err, 0, sizeof(int), c->stream);
-    if (cudaStreamSynchronize(c->stream) != cudaSuccess) { delete c; set_error("context initialisation failed"); return 1; }
     *out = c;
     return 0;
 }
@@ -306,10 +291,6 @@ void mm_ctx_destroy(mm_ctx* c) {
         cudaFree(kv.second.bnd); cudaFree(kv.second.tile_seg); cudaFree(kv.second.blk_lo); cudaFree(kv.second.blk_hi);
     }
     for (auto& k : c->ktimes) { cudaEventDestroy(k.a); cudaEventDestroy(k.b); }
-    if (c->agg) cudaFree(c->agg);
-    if (c->flag) cudaFree(c->flag);
-    if (c->ticket) cudaFree(c->ticket);
-    if (c->err) cudaFree(c->err);
     if (c->own_stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -317,13 +298,6 @@ void mm_ctx_destroy(mm_ctx* c) {
 int mm_ctx_sync(mm_ctx* c) {
     MM_API_BEGIN(c);
     MM_CUDA(cudaStreamSynchronize(c->stream));
-    int err = 0;
-    MM_CUDA(cudaMemcpy(&err, c->err, sizeof(int), cudaMemcpyDeviceToHost));
-    if (err != 0) {
-        cudaMemset(c->err, 0, sizeof(int));
-        set_error("scan look-back timed out waiting for a predecessor tile (device error flag %d)", err);
-        return 1;
-    }
     return 0;
 }
 
@@ -372,9 +346,8 @@ int64_t mm_ctx_workspace_bytes(mm_ctx* c) { return c ? c->workspace_bytes : 0; }
 int64_t mm_master_workspace_bytes(const mm_geom* g, int chain) {
     if (!g) return 0;
     const int64_t buf = (int64_t)g->tracks * g->channels * g->stride * 4;
-    const int64_t ntiles = (g->n + 64 + kL) / kL + 1;
-    const int64_t carry = (int64_t)4 * g->tracks * g->channels * ntiles * (kMaxOrder * 8 + 4) * 5 / 4;
-    return buf * (chain == MM_CHAIN_V1 ? 9 : 9) + carry + (1 << 20);
+    (void)chain;
+    return buf * 9 + (1 << 20);   // E0..E3, T0..T4 (stages.cu get_bufs) + scalars
 }
 
 // ---- pinned host memory for the host-buffer entry points ----------------------------------------

@@ -12,18 +12,16 @@ constexpr int kT = 128;                  // threads per tile
 constexpr int kNW = kT / 32;             // warps per tile
 constexpr int kL = kS * kT;              // samples per tile (4096)
 constexpr int kLead = 32;                // == MM_LEAD: float offset of sample 0 inside a row
-constexpr int kChunk = kS + 4;           // padded per-thread chunk in shared memory (bank-conflict-free LDS.128)
-constexpr int kTileFloats = kT * kChunk; // floats of shared memory per staged stream
 
 // Offsets (in doubles) inside a per-filter device table, see design.h ScanTables.
 template <int M> struct Tab {
     static constexpr int MM = M * M;
     static constexpr int Pw = 0;                         // [5][MM]
     static constexpr int Plane = Pw + 5 * MM;            // [32][MM]
-    static constexpr int Qpow = Plane + 32 * MM;         // [kNW+1][MM]
+    static constexpr int Qpow = Plane + 32 * MM;         // [kNW+1][MM]   Qpow[kNW] = A^kL
     static constexpr int Zi = Qpow + (kNW + 1) * MM;     // [M]
     static constexpr int Apow = Zi + M;                  // [kS+1][MM]
-    static constexpr int Mpow = Apow + (kS + 1) * MM;    // [W][MM]
+    static constexpr int Mpow = Apow + (kS + 1) * MM;    // [W][MM]  (A^kL)^j, kept for host-side verification
 };
 
 // Per-filter constants that ride in the kernel parameter block (constant bank): the compiler folds
@@ -47,7 +45,7 @@ struct DynBand {           // one band of MULTIBAND_CONFIG after host-side prepa
 };
 struct DynParams {
     DynBand band[4];
-    float max_thr, max_ceil, max_num, max_den;   // maximizer (pipeline.py:484-492) in float32 terms
+    float max_thr, max_ceil, max_num, max_den, max_k;   // maximizer (pipeline.py:484-492) in float32 terms; max_k = num / den
     float tp_lim;                                 // TRUE_PEAK_LIMIT_DB hard limit
     // optional parallel compression folded behind the limiter (v1, pipeline.py:1771-1797)
     const double* par_mix;                        // per-row mix (device) or nullptr
@@ -73,11 +71,6 @@ template <int M, int NF> struct SweepArgs {
     double exc_gain, exc_k;
     int exc_mode;
     float* peak;             // per track |out| max (float bits, atomicMax) or null
-    double* agg;
-    unsigned* flag;
-    unsigned epoch, ticket_base;
-    unsigned* ticket;
-    int* err;
 };
 
 __device__ __forceinline__ double shfl_up_d(double v, int d) {
@@ -98,7 +91,18 @@ __device__ __forceinline__ float comp4(const float4& v, int c) {
 __device__ __forceinline__ void setcomp4(float4& v, int c, float x) {
     if (c == 0) v.x = x; else if (c == 1) v.y = x; else if (c == 2) v.z = x; else v.w = x;
 }
-__device__ __forceinline__ int pm(int mi) { return (mi >> 5) * kChunk + (mi & 31); }
+
+// One DF2T step: y = b0 x + z0 ; z_i = b_{i+1} x - a_{i+1} y + z_{i+1}
+template <int M> __device__ __forceinline__ double df2t_step(const FiltK<M>& fk, double x, double (&z)[M]) {
+    const double y = fma(fk.b[0], x, z[0]);
+#pragma unroll
+    for (int i = 0; i < M; ++i) {
+        double t = (i + 1 < M) ? z[i + 1] : 0.0;
+        t = fma(fk.b[i + 1], x, t);
+        z[i] = fma(-fk.a[i], y, t);
+    }
+    return y;
+}
 
 // y = Mat(MxM, row-major at p) * v, added into acc
 template <int M> __device__ __forceinline__ void matvec_acc(const double* __restrict__ p, const double (&v)[M], double (&acc)[M]) {

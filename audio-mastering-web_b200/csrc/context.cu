@@ -39,24 +39,6 @@ int arena_get(mm_ctx* c, int slot, size_t bytes, void** out) {
     return 0;
 }
 
-int ensure_carry(mm_ctx* c, size_t slots) {
-    if (c->carry_slots >= slots) return 0;
-    if (c->agg) {
-        MM_CUDA(cudaStreamSynchronize(c->stream));
-        MM_CUDA(cudaFree(c->agg));
-        MM_CUDA(cudaFree(c->flag));
-        c->workspace_bytes -= (int64_t)(c->carry_slots * (kMaxOrder * sizeof(double) + sizeof(unsigned)));
-    }
-    size_t want = slots + slots / 4 + 1024;
-    MM_CUDA(cudaMalloc(&c->agg, want * kMaxOrder * sizeof(double)));
-    MM_CUDA(cudaMalloc(&c->flag, want * sizeof(unsigned)));
-    MM_CUDA(cudaMemsetAsync(c->flag, 0, want * sizeof(unsigned), c->stream));
-    c->carry_slots = want;
-    c->epoch = 0;    // flags are all zero again; epochs restart at 1
-    c->workspace_bytes += (int64_t)(want * (kMaxOrder * sizeof(double) + sizeof(unsigned)));
-    return 0;
-}
-
 template <int M> static void pack_tables(const ScanTables& t, std::vector<double>& h) {
     typedef Tab<M> TB;
     h.assign((size_t)TB::Mpow + (size_t)t.W * TB::MM, 0.0);

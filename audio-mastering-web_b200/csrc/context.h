@@ -1,4 +1,4 @@
-// Host-side context: stream, device arena, filter-plan cache, carry workspace, launch accounting.
+// Host-side context: stream, device arena, filter-plan cache, launch accounting.
 #pragma once
 #include <cuda_runtime.h>
 
@@ -66,14 +66,6 @@ struct mm_ctx {
     mm::Slot slots[mm::SL_COUNT];
     std::map<std::string, mm::FilterPlan> plans;
     std::map<std::string, mm::LufsPlan> lufs_plans;
-    // carry workspace for the look-back
-    double* agg = nullptr;
-    unsigned* flag = nullptr;
-    size_t carry_slots = 0;      // in units of one (filter,row,tile) entry of kMaxOrder doubles
-    unsigned epoch = 0;
-    unsigned ticket_total = 0;
-    unsigned* ticket = nullptr;
-    int* err = nullptr;
     int64_t launches = 0;
     bool timing = false;
     std::vector<mm::KTime> ktimes;
@@ -90,7 +82,6 @@ template <class T> inline int arena(mm_ctx* c, int slot, size_t count, T** out) 
     *out = reinterpret_cast<T*>(p);
     return r;
 }
-int ensure_carry(mm_ctx* c, size_t slots);
 const FilterPlan* get_plan(mm_ctx* c, const Ba& ba);
 int get_lufs_plan(mm_ctx* c, long long n, int sr, const LufsPlan** out);
 

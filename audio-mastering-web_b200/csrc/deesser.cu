@@ -23,68 +23,109 @@
 
 namespace mm {
 
+__device__ __forceinline__ void cp_async16_env(void* smem_dst, const void* gsrc) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gsrc) : "memory");
+}
+
 struct EnvArgs {
     const float* sc;       // planar side-chain rows
     float* gain;           // planar pre-smoothing gain rows (same geometry)
     long long n, stride;
     int rows;
-    long long chunk, halo; // multiples of 4
-    int nchunks;
+    long long chunk, halo; // multiples of 32 samples (one 128-byte line)
+    int nchunks;           // per row
     float atk, one_m_atk, rel, one_m_rel;
-    float thr, ratio;
+    float thr, inv_ratio;
 };
 
-__device__ __forceinline__ float deess_gain(float env, float thr, float ratio) {
+__device__ __forceinline__ float deess_gain(float env, float thr, float inv_ratio) {
     // pipeline.py:1247-1252 in float32 (thr / ratio are Python floats -> weak -> float32 arithmetic)
-    const float red = env > thr ? __fadd_rn(thr, __fdiv_rn(__fsub_rn(env, thr), ratio)) : env;
-    float g = env > 1e-10f ? __fdiv_rn(red, __fadd_rn(env, 1e-12f)) : 1.0f;
+    const float red = env > thr ? fmaf(env - thr, inv_ratio, thr) : env;
+    const float g = env > 1e-10f ? __fdividef(red, env + 1e-12f) : 1.0f;
     return fminf(fmaxf(g, 0.35f), 1.0f);
 }
 
 __device__ __forceinline__ float env_step(float e, float v, const EnvArgs& P) {
-    const float a = __fmaf_rn(P.atk, e, __fmul_rn(P.one_m_atk, v));
-    const float r = __fmaf_rn(P.rel, e, __fmul_rn(P.one_m_rel, v));
+    // max of the attack and the release update == the reference's branch on v > e (atk < rel)
+    const float a = fmaf(P.atk, e, P.one_m_atk * v);
+    const float r = fmaf(P.rel, e, P.one_m_rel * v);
     return fmaxf(a, r);
 }
 
-// one thread = one chunk of one row; rows in blockIdx.y
-__global__ void __launch_bounds__(128) envelope_gain_kernel(const EnvArgs P) {
-    const int chunk = blockIdx.x * blockDim.x + threadIdx.x;
-    if (chunk >= P.nchunks) return;
-    const int row = blockIdx.y;
+// One thread = one chunk (+ its halo) of one row: a strictly sequential recurrence, so the kernel is
+// latency bound by design; each thread streams its samples through a private ring of 128-byte lines in
+// shared memory (cp.async, kEnvDepth lines in flight) so that HBM latency never sits on the chain.
+constexpr int kEnvDepth = 8;
+constexpr int kEnvThreads = 32;
+
+__global__ void __launch_bounds__(kEnvThreads) envelope_gain_kernel(const EnvArgs P) {
+    __shared__ __align__(128) float ring[kEnvDepth][kEnvThreads][32];
+    const int lane = threadIdx.x;
+    const long long gid = (long long)blockIdx.x * kEnvThreads + lane;
+    const long long total = (long long)P.rows * P.nchunks;
+    const bool active = gid < total;
+    const int row = active ? (int)(gid / P.nchunks) : 0;
+    const int chunk = active ? (int)(gid % P.nchunks) : 0;
     const float* src = P.sc + (size_t)row * (size_t)P.stride + kLead;
     float* dst = P.gain + (size_t)row * (size_t)P.stride + kLead;
     const long long live0 = (long long)chunk * P.chunk;
-    const long long live1 = min(live0 + P.chunk, P.n);
-    long long i = max(live0 - P.halo, 0LL);
-    float e = fabsf(src[i]);                 // env[0] = |v0| (exact for i == 0, start-up guess otherwise)
-    // warm-up over the halo: no stores
-    for (; i + 3 < live0; i += 4) {
-        const float4 v = *reinterpret_cast<const float4*>(src + i);
-        if (i != 0) e = env_step(e, fabsf(v.x), P);
-        e = env_step(e, fabsf(v.y), P);
-        e = env_step(e, fabsf(v.z), P);
-        e = env_step(e, fabsf(v.w), P);
+    const long long live1 = active ? min(live0 + P.chunk, P.n) : live0;
+    const long long start = max(live0 - P.halo, 0LL);
+    const int nlines = active ? (int)((live1 - start + 31) / 32) : 0;
+    const int sx = lane & 7;                                   // 16-byte unit swizzle of this thread's lines
+    auto fetch = [&](int line) {
+        if (line < nlines) {
+            const float* g = src + start + 32LL * line;
+            float* s = &ring[line % kEnvDepth][lane][0];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) cp_async16_env(s + 4 * (u ^ sx), g + 4 * u);
+        }
+        asm volatile("cp.async.commit_group;\n" ::: "memory");
+    };
+#pragma unroll
+    for (int l = 0; l < kEnvDepth - 1; ++l) fetch(l);
+    // env[0] = |v0|: starting from e = |v0| the first update returns |v0| again (to within one ulp), so the
+    // recurrence below needs no special case for the chunk's first sample
+    float e = active ? fabsf(__ldg(src + start)) : 0.f;
+    const int halo_lines = active ? (int)((live0 - start) / 32) : 0;
+    // halo: only the state matters -- 5 instructions per sample, all but two of them off the dependency chain
+#pragma unroll 1
+    for (int line = 0; line < halo_lines; ++line) {
+        fetch(line + kEnvDepth - 1);
+        asm volatile("cp.async.wait_group %0;\n" ::"n"(kEnvDepth - 1) : "memory");
+        const float* s = &ring[line % kEnvDepth][lane][0];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const float4 v = *reinterpret_cast<const float4*>(s + 4 * (u ^ sx));
+            e = env_step(e, fabsf(v.x), P);
+            e = env_step(e, fabsf(v.y), P);
+            e = env_step(e, fabsf(v.z), P);
+            e = env_step(e, fabsf(v.w), P);
+        }
     }
-    // live part (live0 is a multiple of 4, so is i here)
-#pragma unroll 2
-    for (; i + 3 < live1; i += 4) {
-        const float4 v = *reinterpret_cast<const float4*>(src + i);
-        float4 g;
-        if (i != 0) e = env_step(e, fabsf(v.x), P);
-        g.x = deess_gain(e, P.thr, P.ratio);
-        e = env_step(e, fabsf(v.y), P);
-        g.y = deess_gain(e, P.thr, P.ratio);
-        e = env_step(e, fabsf(v.z), P);
-        g.z = deess_gain(e, P.thr, P.ratio);
-        e = env_step(e, fabsf(v.w), P);
-        g.w = deess_gain(e, P.thr, P.ratio);
-        *reinterpret_cast<float4*>(dst + i) = g;
+#pragma unroll 1
+    for (int line = halo_lines; line < nlines; ++line) {
+        fetch(line + kEnvDepth - 1);
+        asm volatile("cp.async.wait_group %0;\n" ::"n"(kEnvDepth - 1) : "memory");
+        const float* s = &ring[line % kEnvDepth][lane][0];
+        const long long i0 = start + 32LL * line;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const float4 v = *reinterpret_cast<const float4*>(s + 4 * (u ^ sx));
+            float4 g;
+            e = env_step(e, fabsf(v.x), P); g.x = deess_gain(e, P.thr, P.inv_ratio);
+            e = env_step(e, fabsf(v.y), P); g.y = deess_gain(e, P.thr, P.inv_ratio);
+            e = env_step(e, fabsf(v.z), P); g.z = deess_gain(e, P.thr, P.inv_ratio);
+            e = env_step(e, fabsf(v.w), P); g.w = deess_gain(e, P.thr, P.inv_ratio);
+            const long long i = i0 + 4 * u;
+            if (i + 3 < P.n) *reinterpret_cast<float4*>(dst + i) = g;
+            else {
+                for (int c = 0; c < 4; ++c) if (i + c < P.n) dst[i + c] = comp4(g, c);
+            }
+        }
     }
-    for (; i < live1; ++i) {
-        if (i != 0) e = env_step(e, fabsf(src[i]), P);
-        dst[i] = deess_gain(e, P.thr, P.ratio);
-    }
+    asm volatile("cp.async.wait_group 0;\n" ::: "memory");
 }
 
 // box smoothing of the gain (np.convolve(g, ones(k)/k, mode="same"), zero padding) + recombination
@@ -97,36 +138,70 @@ struct ApplyArgs {
     int k;            // odd
     float kerf;       // float32(1 / k)
 };
-constexpr int kApplyThreads = 128;
-constexpr int kApplyPer = 16;                                  // outputs per thread
+constexpr int kApplyThreads = 256;
+constexpr int kApplyPer = 8;                                   // consecutive outputs per thread (two float4)
 constexpr int kApplyTile = kApplyThreads * kApplyPer;          // 2048 outputs per CTA
 constexpr int kApplyMaxHalf = 256;                             // supports k <= 513 (sr <= 342 kHz)
 
+// padded index: one spare word per 8 so that thread t's window (base 8 t) walks distinct banks
+__device__ __forceinline__ int padi(int i) { return i + (i >> 3); }
+
 __global__ void __launch_bounds__(kApplyThreads) deesser_apply_kernel(const ApplyArgs P) {
-    __shared__ float sg[kApplyTile + 2 * kApplyMaxHalf];
+    __shared__ float sg[kApplyTile + 2 * kApplyMaxHalf + (kApplyTile + 2 * kApplyMaxHalf) / 8 + 8];
     const int row = blockIdx.y;
     const long long base = (long long)blockIdx.x * kApplyTile;
     const int half = P.k / 2;
     const size_t ro = (size_t)row * (size_t)P.stride + kLead;
     const int span = kApplyTile + 2 * half;
-    for (int j = threadIdx.x; j < span; j += kApplyThreads) {
-        const long long i = base - half + j;
-        sg[j] = (i >= 0 && i < P.n) ? P.gain[ro + i] : 0.f;
+    // sg[padi(j)] = g[base - lead + j] with lead = half rounded up to a multiple of 4 (keeps float4 alignment)
+    const int lead = (half + 3) & ~3;
+    for (int j4 = threadIdx.x * 4; j4 < span + (lead - half) + 3; j4 += kApplyThreads * 4) {
+        const long long i = base - lead + j4;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (i >= 0 && i + 3 < P.n) v = __ldcs(reinterpret_cast<const float4*>(P.gain + ro + i));
+        else {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) if (i + c >= 0 && i + c < P.n) setcomp4(v, c, P.gain[ro + i + c]);
+        }
+#pragma unroll
+        for (int c = 0; c < 4; ++c) sg[padi(j4 + c)] = comp4(v, c);
+    }
+    // x and side chain of this thread's 8 outputs: issued before the barrier so they overlap the window sums
+    const int o0 = threadIdx.x * kApplyPer;
+    const long long i0 = base + o0;
+    float xs[8], ss[8];
+    if (i0 + 7 < P.n) {
+        const float4 x0 = __ldcs(reinterpret_cast<const float4*>(P.x + ro + i0)), x1 = __ldcs(reinterpret_cast<const float4*>(P.x + ro + i0 + 4));
+        const float4 s0 = __ldcs(reinterpret_cast<const float4*>(P.sc + ro + i0)), s1 = __ldcs(reinterpret_cast<const float4*>(P.sc + ro + i0 + 4));
+        xs[0] = x0.x; xs[1] = x0.y; xs[2] = x0.z; xs[3] = x0.w; xs[4] = x1.x; xs[5] = x1.y; xs[6] = x1.z; xs[7] = x1.w;
+        ss[0] = s0.x; ss[1] = s0.y; ss[2] = s0.z; ss[3] = s0.w; ss[4] = s1.x; ss[5] = s1.y; ss[6] = s1.z; ss[7] = s1.w;
+    } else {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const bool ok = i0 + u < P.n;
+            xs[u] = ok ? P.x[ro + i0 + u] : 0.f;
+            ss[u] = ok ? P.sc[ro + i0 + u] : 0.f;
+        }
     }
     __syncthreads();
-    const int o0 = threadIdx.x * kApplyPer;
+    // window of output o covers g[o - half .. o + half] = sg index (o - half + lead) .. (+ k - 1)
+    const int w0 = o0 + lead - half;
     double acc = 0.0;
-    for (int j = 0; j < P.k; ++j) acc += (double)sg[o0 + j];
+    for (int j = 0; j < P.k; ++j) acc += (double)sg[padi(w0 + j)];
+    float res[8];
 #pragma unroll
     for (int u = 0; u < kApplyPer; ++u) {
-        const long long i = base + o0 + u;
-        if (i < P.n) {
-            float g = (float)(acc * (double)P.kerf);
-            g = fminf(fmaxf(g, 0.35f), 1.0f);
-            const float x = P.x[ro + i], s = P.sc[ro + i];
-            P.out[ro + i] = __fadd_rn(__fsub_rn(x, s), __fmul_rn(s, g));
-        }
-        acc += (double)sg[o0 + u + P.k] - (double)sg[o0 + u];
+        float g = (float)(acc * (double)P.kerf);
+        g = fminf(fmaxf(g, 0.35f), 1.0f);
+        res[u] = __fadd_rn(__fsub_rn(xs[u], ss[u]), __fmul_rn(ss[u], g));
+        acc += (double)sg[padi(w0 + u + P.k)] - (double)sg[padi(w0 + u)];
+    }
+    if (i0 + 7 < P.n) {
+        __stcs(reinterpret_cast<float4*>(P.out + ro + i0), make_float4(res[0], res[1], res[2], res[3]));
+        __stcs(reinterpret_cast<float4*>(P.out + ro + i0 + 4), make_float4(res[4], res[5], res[6], res[7]));
+    } else {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) if (i0 + u < P.n) P.out[ro + i0 + u] = res[u];
     }
 }
 
@@ -168,16 +243,20 @@ int st_deesser(mm_ctx* c, const mm_geom* g, const float* in, float* out, double 
         A.atk = (float)atk; A.one_m_atk = (float)(1.0 - atk);
         A.rel = (float)rel; A.one_m_rel = (float)(1.0 - rel);
         A.thr = (float)std::pow(10.0, threshold_db / 20.0);
-        A.ratio = (float)ratio;
+        A.inv_ratio = (float)(1.0 / ratio);
         const double slow = std::max(atk, rel);
-        long long halo = slow < 1.0 ? (long long)std::ceil(17.5 / -std::log(slow)) : g->n;
-        halo = std::min<long long>(((halo + 3) / 4) * 4, ((g->n + 3) / 4) * 4);
+        const long long nceil = ((g->n + 31) / 32) * 32;
+        long long halo = slow < 1.0 ? (long long)std::ceil(17.5 / -std::log(slow)) : nceil;
+        halo = std::min<long long>(((halo + 31) / 32) * 32, nceil);
         A.halo = halo;
-        A.chunk = std::max<long long>(halo, 4096);
+        // chunk = halo / 2 (three times the work, short critical path) until the grid exceeds ~8 warps per SM
+        long long chunk = std::max<long long>(((halo / 2 + 31) / 32) * 32, 4096);
+        while ((long long)rows * ((g->n + chunk - 1) / chunk) > 148LL * 8 * 32 && chunk < nceil) chunk *= 2;
+        A.chunk = chunk;
         A.nchunks = (int)((g->n + A.chunk - 1) / A.chunk);
-        dim3 grid((unsigned)((A.nchunks + 127) / 128), (unsigned)rows);
+        const long long total = (long long)rows * A.nchunks;
         KernelScope ks(c, "envelope_gain");
-        envelope_gain_kernel<<<grid, 128, 0, c->stream>>>(A);
+        envelope_gain_kernel<<<(unsigned)((total + kEnvThreads - 1) / kEnvThreads), kEnvThreads, 0, c->stream>>>(A);
         MM_CUDA(cudaGetLastError());
     }
     {

@@ -1,123 +1,246 @@
 // ITU-R BS.1770 K-weighting (two causal biquads, zero initial state) fused with the 400 ms block
 // mean-square partial sums, followed by the two-pass gating -- pyloudnorm.Meter.integrated_loudness
 // as called at backend/app/pipeline.py:646-648 / :660-662.
+//
+// Same decomposition as the sweep kernel (sweep3.cuh): a CTA walks a segment of tiles of one row with
+// the filter states carried in shared memory; the state at the segment start is rebuilt from a halo of
+// W(shelf) + W(high-pass) tiles.  Per tile the shelf is scanned in place, rounded to float32 (pyloudnorm
+// writes each stage back into a copy of its float32 input), then the high-pass; the squares of the
+// result are summed per 100 ms hop into 64-bit fixed-point accumulators (integer atomics are
+// associative, so the loudness -- and the gain derived from it -- is bit-reproducible).
 #pragma once
-#include "sweep.cuh"
+#include "sweep3.cuh"
 
 namespace mm {
+
+constexpr double kSqScale = 1099511627776.0;        // 2^40: fixed-point scale of the square sums
 
 struct LufsArgs {
     FiltK<2> f[2];
     const double* tab[2];
-    int W[2];
     const float* in;
     long long n, stride;
     int rows, ntiles, channels;
+    int seglen, nseg, whalo;
     int pro_mode;
     const double* pro_sub;
     const double* pro_mul;
-    // segment bookkeeping: sample i belongs to segment s iff bnd[s] <= i < bnd[s+1]
-    const long long* bnd;    // [nseg + 1]
-    int nseg;
-    const int* tile_seg;     // [ntiles] segment of max(first sample of tile, 0), clamped to nseg
-    double* segsum;          // [rows][nseg]
-    double* agg;
-    unsigned* flag;
-    unsigned epoch, ticket_base;
-    unsigned* ticket;
-    int* err;
+    // hop bookkeeping: sample i belongs to hop s iff bnd[s] <= i < bnd[s+1]
+    const long long* bnd;    // [nhop + 1]
+    int nhop;
+    const int* tile_seg;     // [ntiles] hop of max(first sample of tile, 0), clamped to nhop
+    unsigned long long* segsum;   // [rows][nhop] fixed-point sums of squares
 };
 
+struct LufsScratch {
+    double tot[kNW][2];
+    double carry[2][2][2];   // [tile parity][filter][state]
+};
+
+// Round a double to float32 precision on the FP64 pipe (Dekker/Veltkamp split, 2^29 + 1): what pyloudnorm's
+// write-back of a float64 lfilter result into its float32 buffer does, without the two conversions
+// (F2F runs at 15 lanes/clk/SM and is this kernel's scarcest pipe).  Differs from a true cast only in
+// how exact ties break and for values outside float32's normal range -- irrelevant at +-0.01 LU.
+__device__ __forceinline__ double round_to_f32(double y) {
+    const double t = y * 536870913.0;
+    return t - (t - y);
+}
+
+constexpr int kLufsSmem = kL * (int)sizeof(double) + 2 * (int)sizeof(SmemTab<2>);
+
 __global__ void __launch_bounds__(kT) lufs_kernel(const __grid_constant__ LufsArgs P) {
-    __shared__ __align__(16) float smem[kTileFloats];
-    __shared__ ScanScratch<2, 1> sh;
-    __shared__ unsigned s_ticket;
-    const int tid = threadIdx.x, lane = tid & 31;
-    if (tid == 0) s_ticket = atomicAdd(P.ticket, 1u) - P.ticket_base;
-    __syncthreads();
-    const unsigned ticket = s_ticket;
-    const int tile = (int)(ticket / (unsigned)P.rows);
-    const int row = (int)(ticket - (unsigned)tile * (unsigned)P.rows);
-    const long long tile_lo = (long long)tile * kL;
-    const float* src = P.in + (size_t)row * (size_t)P.stride;
+    // the tile lives in shared memory as float32 while it is being loaded (first half of the buffer) and is
+    // widened in place to float64 by the shelf's pass 2, so the high-pass stage needs no conversions at all
+    extern __shared__ __align__(128) unsigned char lufs_smem[];
+    float* tile_s = reinterpret_cast<float*>(lufs_smem);
+    double* tile_d = reinterpret_cast<double*>(lufs_smem);
+    SmemTab<2>* tab = reinterpret_cast<SmemTab<2>*>(lufs_smem + kL * sizeof(double));
+    __shared__ LufsScratch sh;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int MM = 4;
+#pragma unroll 1
+    for (int f = 0; f < 2; ++f) {
+        double* d = reinterpret_cast<double*>(&tab[f]);
+        for (int i = tid; i < (5 + 32 + kNW + 1) * MM; i += kT) d[i] = __ldg(P.tab[f] + i);
+    }
+    const int cbase = tid * 32, cx = (tid & 7) << 2;
+    // float64 layout of this thread's chunk: 16 vectors of 2 doubles at dbase + ((2 w) ^ dx), conflict free
+    // for 16-byte accesses (8 consecutive threads cover all 8 16-byte bank groups)
+    const int dbase = tid * 32, dx = (tid & 7) << 1;
+    const int items = P.rows * P.nseg;
+#pragma unroll 1
+    for (int item = blockIdx.x; item < items; item += gridDim.x) {
+        const int row = item % P.rows, seg = item / P.rows;
+        const int t_live = seg * P.seglen;
+        const int t_end = min(P.ntiles, t_live + P.seglen);
+        const int t_first = max(0, t_live - P.whalo);
+        const float* src = P.in + (size_t)row * (size_t)P.stride;
+        float subf = 0.f, mulf = 1.f;
+        double muld = 1.0;
+        if (P.pro_mode != PRO_NONE) {
+            if (P.pro_sub) subf = (float)__ldg(P.pro_sub + row);
+            if (P.pro_mul) { muld = __ldg(P.pro_mul + row); mulf = (float)muld; }
+        }
+        __syncthreads();
+        if (tid < 4) sh.carry[t_first & 1][tid >> 1][tid & 1] = 0.0;
+        unsigned long long* dst = P.segsum + (size_t)row * (size_t)P.nhop;
+#pragma unroll 1
+        for (int tile = t_first; tile < t_end; ++tile) {
+            const bool live = tile >= t_live;
+            const long long tile_lo = (long long)tile * kL;
+            const bool interior = tile_lo >= kLead && tile_lo + kL <= kLead + P.n;
+            __syncthreads();                               // previous tile done with the buffer
+            if (interior) {
+                const float* s4 = src + tile_lo + 4 * tid;
+                float* d4 = tile_s + 4 * swz(tid);
+#pragma unroll
+                for (int r = 0; r < kTileVecs / kT; ++r) cp_async16(d4 + 4 * kT * r, s4 + 4 * kT * r);
+                cp_async_commit();
+                cp_async_wait<0>();
+            } else {
+#pragma unroll 1
+                for (int r = 0; r < kTileVecs / kT; ++r) {
+                    const int v = tid + kT * r;
+                    const long long q = tile_lo + 4 * v;
+                    float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                    for (int c = 0; c < 4; ++c)
+                        if (q + c >= kLead && q + c < kLead + P.n) setcomp4(val, c, src[q + c]);
+                    *reinterpret_cast<float4*>(tile_s + 4 * swz(v)) = val;
+                }
+            }
+            __syncthreads();
 
-    float subf = 0.f, mulf = 1.f;
-    double muld = 1.0;
-    if (P.pro_mode != PRO_NONE) {
-        if (P.pro_sub) subf = (float)__ldg(P.pro_sub + row);
-        if (P.pro_mul) { muld = __ldg(P.pro_mul + row); mulf = (float)muld; }
-    }
+            // ================= stage 0: high shelf, float32 in -> float32-rounded float64 out ===============
+            // this thread's 32 input samples leave shared memory here: every thread reads its float chunk
+            // before anybody overwrites the buffer with doubles (barrier below)
+            float xin[32];
 #pragma unroll
-    for (int r = 0; r < kL / (4 * kT); ++r) {
-        const int mi = 4 * (tid + kT * r);
-        const long long q = tile_lo + mi;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (q >= kLead && q + 3 < kLead + P.n) {
-            v = __ldcs(reinterpret_cast<const float4*>(src + q));
-        } else if (q + 3 >= kLead && q < kLead + P.n) {
+            for (int u = 0; u < kS / 4; ++u) {
+                float4 xv = *reinterpret_cast<const float4*>(tile_s + cbase + ((4 * u) ^ cx));
+                if (P.pro_mode != PRO_NONE) {
+                    const long long q0 = tile_lo + cbase + 4 * u;      // dead positions of edge tiles stay exactly zero
 #pragma unroll
-            for (int c = 0; c < 4; ++c)
-                if (q + c >= kLead && q + c < kLead + P.n) setcomp4(v, c, src[q + c]);
-        }
-        if (P.pro_mode == PRO_SUBMUL_F32) {
-            v.x = __fmul_rn(__fsub_rn(v.x, subf), mulf); v.y = __fmul_rn(__fsub_rn(v.y, subf), mulf);
-            v.z = __fmul_rn(__fsub_rn(v.z, subf), mulf); v.w = __fmul_rn(__fsub_rn(v.w, subf), mulf);
-        } else if (P.pro_mode == PRO_MUL_F64) {
-            v.x = (float)((double)v.x * muld); v.y = (float)((double)v.y * muld);
-            v.z = (float)((double)v.z * muld); v.w = (float)((double)v.w * muld);
-        }
-        // dead positions must stay exactly zero after the prologue
-        if (!(q >= kLead && q + 3 < kLead + P.n)) {
+                    for (int c = 0; c < 4; ++c) {
+                        const bool in_range = interior || (q0 + c >= kLead && q0 + c < kLead + P.n);
+                        if (in_range) setcomp4(xv, c, pro1(P.pro_mode, comp4(xv, c), subf, mulf, muld));
+                    }
+                }
+                xin[4 * u] = xv.x; xin[4 * u + 1] = xv.y; xin[4 * u + 2] = xv.z; xin[4 * u + 3] = xv.w;
+            }
+            double E[2] = {0.0, 0.0};
 #pragma unroll
-            for (int c = 0; c < 4; ++c)
-                if (!(q + c >= kLead && q + c < kLead + P.n)) setcomp4(v, c, 0.f);
-        }
-        *reinterpret_cast<float4*>(smem + pm(mi)) = v;
-    }
-    __syncthreads();
-    // shelf, then high-pass; the float32 round trip between the stages is pyloudnorm's own
-    // (it writes each stage back into a copy of the float32 input)
-    tile_scan<2, 1, 1, +1, 0>(P, smem, sh, row, tile, false, 0);
-    tile_scan<2, 1, 1, +1, 1>(P, smem, sh, row, tile, false, 0);
+            for (int j = 0; j < kS; ++j) {
+                const double x = (double)xin[j];
+                E[0] = fma(P.f[0].g[j][0], x, E[0]);
+                E[1] = fma(P.f[0].g[j][1], x, E[1]);
+            }
+            double base[2], cin[2], z[2];
+            auto resolve = [&](int f) {
+                // warp scan, tile Horner, carry update; leaves the state entering this thread's chunk in z
+#pragma unroll
+                for (int d = 0; d < 5; ++d) {
+                    double pe[2];
+                    pe[0] = shfl_up_d(E[0], 1 << d);
+                    pe[1] = shfl_up_d(E[1], 1 << d);
+                    if (lane >= (1 << d)) matvec_acc_s<2>(tab[f].Pw[d], pe, E);
+                }
+                if (lane == 31) { sh.tot[warp][0] = E[0]; sh.tot[warp][1] = E[1]; }
+                __syncthreads();
+                base[0] = 0.0; base[1] = 0.0;
+                for (int v = 0; v < warp; ++v) {
+                    double nb[2] = {sh.tot[v][0], sh.tot[v][1]};
+                    matvec_acc_s<2>(tab[f].Qpow[1], base, nb);
+                    base[0] = nb[0]; base[1] = nb[1];
+                }
+                cin[0] = sh.carry[tile & 1][f][0]; cin[1] = sh.carry[tile & 1][f][1];
+                if (tid == kT - 1) {
+                    double ag[2] = {E[0], E[1]};
+                    matvec_acc_s<2>(tab[f].Qpow[1], base, ag);
+                    matvec_acc_s<2>(tab[f].Qpow[kNW], cin, ag);
+                    sh.carry[(tile + 1) & 1][f][0] = ag[0];
+                    sh.carry[(tile + 1) & 1][f][1] = ag[1];
+                }
+                matvec_acc_s<2>(tab[f].Qpow[warp], cin, base);
+                z[0] = shfl_up_d(E[0], 1);
+                z[1] = shfl_up_d(E[1], 1);
+                if (lane == 0) { z[0] = 0.0; z[1] = 0.0; }
+                matvec_acc_s<2>(tab[f].Plane[lane], base, z);
+            };
+            resolve(0);          // contains a barrier: every thread holds its inputs in registers by now
+            double E1[2] = {0.0, 0.0};
+#pragma unroll
+            for (int w = 0; w < kS / 2; ++w) {
+                const double y0 = round_to_f32(df2t_step<2>(P.f[0], (double)xin[2 * w], z));
+                const double y1 = round_to_f32(df2t_step<2>(P.f[0], (double)xin[2 * w + 1], z));
+                // stage 1's pass 1 rides along: zero-state end state of the high-pass over this chunk
+                E1[0] = fma(P.f[1].g[2 * w][0], y0, E1[0]);
+                E1[1] = fma(P.f[1].g[2 * w][1], y0, E1[1]);
+                E1[0] = fma(P.f[1].g[2 * w + 1][0], y1, E1[0]);
+                E1[1] = fma(P.f[1].g[2 * w + 1][1], y1, E1[1]);
+                *reinterpret_cast<double2*>(tile_d + dbase + ((2 * w) ^ dx)) = make_double2(y0, y1);
+            }
+            // ================= stage 1: high-pass on the float64 tile ======================================
+            E[0] = E1[0]; E[1] = E1[1];
+            __syncthreads();     // sh.tot of stage 0 has been consumed by everybody
+            resolve(1);
+            if (!live) continue;                           // halo: only the carried states were needed
 
-    // ---- squared sums per segment ------------------------------------------------------------------------
-    const long long i0 = tile_lo + (long long)tid * kS - kLead;     // first sample index of this thread
-    const long long iw = tile_lo + (long long)(tid & ~31) * kS - kLead;   // first sample of this warp
-    int sw = __ldg(P.tile_seg + tile);
-    while (sw < P.nseg && __ldg(P.bnd + sw + 1) <= iw) ++sw;
-    int s = sw;
-    while (s < P.nseg && __ldg(P.bnd + s + 1) <= i0) ++s;
-    long long nb = (s < P.nseg) ? __ldg(P.bnd + s + 1) : (long long)0x7fffffffffffffffLL;
-    double accA = 0.0, accB = 0.0, acc = 0.0;
-    const float* cb = smem + tid * kChunk;
-    double* dst = P.segsum + (size_t)row * (size_t)P.nseg;
-#pragma unroll 4
-    for (int j = 0; j < kS; ++j) {
-        const long long i = i0 + j;
-        if (i >= nb) {
-            if (s == sw) accA += acc; else if (s == sw + 1) accB += acc; else if (s < P.nseg && acc != 0.0) atomicAdd(dst + s, acc);
-            acc = 0.0;
-            while (s < P.nseg && __ldg(P.bnd + s + 1) <= i) ++s;
-            nb = (s < P.nseg) ? __ldg(P.bnd + s + 1) : (long long)0x7fffffffffffffffLL;
-        }
-        const double y = (double)cb[j];
-        if (i >= 0) acc = fma(y, y, acc);
-    }
-    if (s == sw) accA += acc; else if (s == sw + 1) accB += acc; else if (s < P.nseg && acc != 0.0) atomicAdd(dst + s, acc);
+            // pass 2 fused with the squared sums per hop (the squares use the float32-rounded output)
+            const long long i0 = tile_lo + (long long)tid * kS - kLead;          // first sample index of this thread
+            const long long iw = tile_lo + (long long)(tid & ~31) * kS - kLead;   // first sample of this warp
+            int sw = __ldg(P.tile_seg + tile);
+            while (sw < P.nhop && __ldg(P.bnd + sw + 1) <= iw) ++sw;
+            int s = sw;
+            while (s < P.nhop && __ldg(P.bnd + s + 1) <= i0) ++s;
+            long long nb = (s < P.nhop) ? __ldg(P.bnd + s + 1) : (long long)0x7fffffffffffffffLL;
+            double accA = 0.0, accB = 0.0, acc = 0.0;
+            auto flush = [&](int hop, double v) {
+                if (hop == sw) accA += v;
+                else if (hop == sw + 1) accB += v;
+                else if (hop < P.nhop && v != 0.0) atomicAdd(dst + hop, (unsigned long long)__double2ll_rn(v * kSqScale));
+            };
+            const bool whole = (i0 >= 0) && (i0 + kS <= P.n) && (i0 + kS <= nb);   // chunk inside the row and one hop
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) { accA += shfl_xor_d(accA, o); accB += shfl_xor_d(accB, o); }
-    if (lane == 0) {
-        if (sw < P.nseg && accA != 0.0) atomicAdd(dst + sw, accA);
-        if (sw + 1 < P.nseg && accB != 0.0) atomicAdd(dst + sw + 1, accB);
+            for (int w = 0; w < kS / 2; ++w) {
+                const double2 xv = *reinterpret_cast<const double2*>(tile_d + dbase + ((2 * w) ^ dx));
+                const double y0 = round_to_f32(df2t_step<2>(P.f[1], xv.x, z));
+                const double y1 = round_to_f32(df2t_step<2>(P.f[1], xv.y, z));
+                if (whole) {
+                    acc = fma(y0, y0, acc);
+                    acc = fma(y1, y1, acc);
+                } else {
+#pragma unroll
+                    for (int c = 0; c < 2; ++c) {
+                        const long long i = i0 + 2 * w + c;
+                        if (i >= nb) {
+                            flush(s, acc);
+                            acc = 0.0;
+                            while (s < P.nhop && __ldg(P.bnd + s + 1) <= i) ++s;
+                            nb = (s < P.nhop) ? __ldg(P.bnd + s + 1) : (long long)0x7fffffffffffffffLL;
+                        }
+                        const double y = c == 0 ? y0 : y1;
+                        if (i >= 0 && i < P.n) acc = fma(y, y, acc);
+                    }
+                }
+            }
+            flush(s, acc);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) { accA += shfl_xor_d(accA, o); accB += shfl_xor_d(accB, o); }
+            if (lane == 0) {
+                if (sw < P.nhop && accA != 0.0) atomicAdd(dst + sw, (unsigned long long)__double2ll_rn(accA * kSqScale));
+                if (sw + 1 < P.nhop && accB != 0.0) atomicAdd(dst + sw + 1, (unsigned long long)__double2ll_rn(accB * kSqScale));
+            }
+        }
     }
 }
 
 // Two-pass gating; one CTA per track.
 struct GateArgs {
-    const double* segsum;    // [rows][nseg]
+    const unsigned long long* segsum;   // [rows][nseg] fixed-point
     int nseg, nblocks, channels, tracks;
-    const int* blk_lo;       // [nblocks] first segment of block j
-    const int* blk_hi;       // [nblocks] one past the last segment of block j
+    const int* blk_lo;       // [nblocks] first hop of block j
+    const int* blk_hi;       // [nblocks] one past the last hop of block j
     double scale;            // 1 / (0.4 * rate)
     int valid;               // 0: signal shorter than one block (pyloudnorm raises)
     double* lufs;            // [tracks]
@@ -146,16 +269,17 @@ __global__ void __launch_bounds__(256) gate_kernel(const GateArgs P) {
     if (!P.valid) {
         lufs = __longlong_as_double(0x7ff8000000000000LL);
     } else {
-        const double* s0 = P.segsum + (size_t)(track * C) * P.nseg;
-        const double* s1 = s0 + (C > 1 ? P.nseg : 0);
+        const unsigned long long* s0 = P.segsum + (size_t)(track * C) * P.nseg;
+        const unsigned long long* s1 = s0 + (C > 1 ? P.nseg : 0);
+        const double inv = 1.0 / kSqScale;
         double gamma_r = 0.0;
         double result = 0.0;
         for (int pass = 0; pass < 2; ++pass) {
             double a0 = 0.0, a1 = 0.0, cnt = 0.0;
             for (int j = threadIdx.x; j < P.nblocks; j += blockDim.x) {
-                double z0 = 0.0, z1 = 0.0;
-                for (int s = P.blk_lo[j]; s < P.blk_hi[j]; ++s) { z0 += s0[s]; if (C > 1) z1 += s1[s]; }
-                z0 *= P.scale; z1 *= P.scale;
+                unsigned long long u0 = 0, u1 = 0;
+                for (int s = P.blk_lo[j]; s < P.blk_hi[j]; ++s) { u0 += s0[s]; if (C > 1) u1 += s1[s]; }
+                const double z0 = (double)u0 * inv * P.scale, z1 = (double)u1 * inv * P.scale;
                 const double l = -0.691 + 10.0 * log10(z0 + (C > 1 ? z1 : 0.0));
                 const bool keep = pass == 0 ? (l >= -70.0) : (l > gamma_r && l > -70.0);
                 if (keep) { a0 += z0; a1 += z1; cnt += 1.0; }

@@ -104,20 +104,24 @@ __device__ __forceinline__ void philox4x32_10(unsigned c0, unsigned c1, unsigned
     out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
 
-// _write_wav_16bit_dithered quantiser (pipeline.py:887-898): float64(x) * 32767 + float32 noise,
-// round half to even, clip.
-__device__ __forceinline__ int16_t quantize16(float x, float noise) {
+// _write_wav_16bit_dithered quantiser (pipeline.py:887-898): float64(x) * 32767 + noise, round half to
+// even, clip.  x * 32767 needs 39 significant bits, hence float64.  The rounding is the 1.5 * 2^52 magic
+// add on the FP64 pipe (round-to-nearest-even, exactly numpy's np.round for |d| < 2^31) instead of
+// rint + a double->int conversion: conversions run at 15 lanes/clk/SM on this part.
+__device__ __forceinline__ int16_t quantize16(float x, double noise) {
     if (x != x) x = 0.f;
     x = fminf(fmaxf(x, -1.f), 1.f);
-    double d = __dadd_rn(__dmul_rn((double)x, 32767.0), (double)noise);
-    d = rint(d);
-    d = fmin(fmax(d, -32768.0), 32767.0);
-    return (int16_t)(int)d;
+    const double d = __dadd_rn(__dmul_rn((double)x, 32767.0), noise);
+    const int q = __double2loint(__dadd_rn(d, 6755399441055744.0));
+    return (int16_t)min(max(q, -32768), 32767);
 }
-__device__ __forceinline__ float tpdf_from_bits(unsigned a, unsigned b) {
-    // (rand + rand - 1.0).astype(float32), pipeline.py:830-832, with 32-bit uniforms
-    const double u = (double)a * 2.3283064365386963e-10 + (double)b * 2.3283064365386963e-10 - 1.0;
-    return (float)u;
+// (rand + rand - 1.0), pipeline.py:830-832, from 2 x 32 counter-based random bits.  The uniforms are
+// built in the exponent-1 binade by bit placement ([1, 2) - 1), no integer->float conversion; unlike the
+// reference the sum is not rounded to float32 (finer noise resolution, same triangular distribution).
+__device__ __forceinline__ double tpdf_from_bits(unsigned a, unsigned b) {
+    const double ua = __hiloint2double((int)(0x3FF00000u | (a >> 12)), (int)(a << 20));
+    const double ub = __hiloint2double((int)(0x3FF00000u | (b >> 12)), (int)(b << 20));
+    return (ua + ub) - 3.0;
 }
 
 __global__ void __launch_bounds__(kPwThreads) pointwise_kernel(const PwArgs P) {
@@ -195,10 +199,10 @@ __global__ void __launch_bounds__(kPwThreads) pointwise_kernel(const PwArgs P) {
                         l = __fmul_rn(l, ramp); rr = __fmul_rn(rr, ramp);
                     }
                     if (P.pcm) {
-                        float n0, n1 = 0.f;
+                        double n0, n1 = 0.0;
                         const size_t fi = (size_t)track * (size_t)P.n + (size_t)(i + c);
                         if (P.noise) {
-                            if (i + c < P.n) { n0 = P.noise[fi * C]; if (C > 1) n1 = P.noise[fi * C + 1]; } else n0 = 0.f;
+                            if (i + c < P.n) { n0 = (double)P.noise[fi * C]; if (C > 1) n1 = (double)P.noise[fi * C + 1]; } else n0 = 0.0;
                         } else {
                             unsigned rnd[4];
                             const unsigned long long fr = (unsigned long long)(i + c);
@@ -253,6 +257,139 @@ __global__ void __launch_bounds__(kPwThreads) pointwise_kernel(const PwArgs P) {
     }
 }
 
+// ---- final pass of a chain: imager -> output peak guard scale -> clip / nan_to_num -> fade-in -> float32 out
+//      (+ TPDF dither to interleaved int16).  remove_intersample_peaks (pipeline.py:141-149), the chain's final
+//      clip (:1906-1908 / chain.py:93-94), apply_output_edge_fade_in (:152-167), _write_wav_16bit_dithered (:880-898).
+struct FinalArgs {
+    const float* in;
+    float* out;
+    long long n, stride;
+    int tracks;
+    const double* mul;          // per row output-guard scale
+    const double* width;        // per track imager width or null
+    int n_fade;
+    double fade_step;
+    int16_t* pcm;               // interleaved [tracks][n][C] or null
+    const float* noise;         // interleaved float32 noise or null (-> Philox)
+    unsigned long long seed;
+    double* nonfinite;          // per track or null
+};
+
+constexpr int kFinThreads = 256;
+constexpr int kFinVec = 4;                                   // float4 per thread per channel
+constexpr int kFinFrames = kFinThreads * kFinVec * 4;        // frames per block
+
+template <int C, bool PCM, bool NOISE>
+__global__ void __launch_bounds__(kFinThreads) finalize_kernel(const FinalArgs P) {
+    const int track = blockIdx.y;
+    const long long base = (long long)blockIdx.x * kFinFrames;
+    const size_t r0 = (size_t)(track * C) * (size_t)P.stride + kLead;
+    const size_t r1 = r0 + (C > 1 ? (size_t)P.stride : 0);
+    const float mul0 = (float)__ldg(P.mul + track * C), mul1 = (float)__ldg(P.mul + track * C + (C > 1));
+    const bool imager = C == 2 && P.width != nullptr && __ldg(P.width + track) != 1.0;
+    const float wf = imager ? (float)__ldg(P.width + track) : 1.f;
+    float4 a[kFinVec], b[kFinVec];
+    // all loads first: 2 * kFinVec independent 16-byte requests per thread in flight
+#pragma unroll
+    for (int r = 0; r < kFinVec; ++r) {
+        const long long i = base + 4LL * (threadIdx.x + kFinThreads * r);
+        a[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+        b[r] = a[r];
+        if (i + 3 < P.n) {
+            a[r] = __ldcs(reinterpret_cast<const float4*>(P.in + r0 + i));
+            if (C > 1) b[r] = __ldcs(reinterpret_cast<const float4*>(P.in + r1 + i));
+        } else {
+            for (int c = 0; c < 4; ++c)
+                if (i + c < P.n) { setcomp4(a[r], c, P.in[r0 + i + c]); if (C > 1) setcomp4(b[r], c, P.in[r1 + i + c]); }
+        }
+    }
+    double bad = 0.0;
+#pragma unroll
+    for (int r = 0; r < kFinVec; ++r) {
+        const long long i = base + 4LL * (threadIdx.x + kFinThreads * r);
+        if (i >= P.n) continue;
+        const bool full = i + 3 < P.n;
+        int16_t q[8];
+        float4 nz0 = make_float4(0.f, 0.f, 0.f, 0.f), nz1 = nz0;
+        if (PCM && NOISE) {
+            const float* np_ = P.noise + ((size_t)track * (size_t)P.n + (size_t)i) * C;
+            if (full && ((reinterpret_cast<uintptr_t>(np_) & 15) == 0)) {
+                nz0 = __ldcs(reinterpret_cast<const float4*>(np_));
+                if (C > 1) nz1 = __ldcs(reinterpret_cast<const float4*>(np_ + 4));
+            } else {
+                for (int k = 0; k < 4 * C; ++k)
+                    if (i + k / C < P.n) { if (k < 4) setcomp4(nz0, k, np_[k]); else setcomp4(nz1, k - 4, np_[k]); }
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            float l = comp4(a[r], c), rr = comp4(b[r], c);
+            if (imager) {
+                const float mid = __fmul_rn(__fadd_rn(l, rr), 0.5f);
+                const float side = __fmul_rn(__fmul_rn(__fsub_rn(l, rr), 0.5f), wf);
+                l = fminf(fmaxf(__fadd_rn(mid, side), -1.f), 1.f);
+                rr = fminf(fmaxf(__fsub_rn(mid, side), -1.f), 1.f);
+            }
+            if (P.nonfinite && i + c < P.n) {
+                if (!(fabsf(l) <= 3.4e38f)) bad += 1.0;
+                if (C > 1 && !(fabsf(rr) <= 3.4e38f)) bad += 1.0;
+            }
+            l = __fmul_rn(l, mul0); rr = __fmul_rn(rr, mul1);
+            l = (l != l) ? 0.f : fminf(fmaxf(l, -1.f), 1.f);
+            rr = (rr != rr) ? 0.f : fminf(fmaxf(rr, -1.f), 1.f);
+            if (i + c < P.n_fade) {
+                const float ramp = (i + c == P.n_fade - 1) ? 1.f : (float)((double)(i + c) * P.fade_step);
+                l = __fmul_rn(l, ramp); rr = __fmul_rn(rr, ramp);
+            }
+            setcomp4(a[r], c, l);
+            setcomp4(b[r], c, rr);
+            if (PCM) {
+                double n0, n1 = 0.0;
+                if (NOISE) {
+                    // interleaved: frame c of this vector holds elements c*C .. c*C + C - 1
+                    const int e0 = c * C, e1 = c * C + 1;
+                    n0 = (double)(e0 < 4 ? comp4(nz0, e0) : comp4(nz1, e0 - 4));
+                    if (C > 1) n1 = (double)(e1 < 4 ? comp4(nz0, e1) : comp4(nz1, e1 - 4));
+                } else {
+                    unsigned rnd[4];
+                    const unsigned long long fr = (unsigned long long)(i + c);
+                    philox4x32_10((unsigned)fr, (unsigned)(fr >> 32), (unsigned)track, 0u, (unsigned)P.seed, (unsigned)(P.seed >> 32), rnd);
+                    n0 = tpdf_from_bits(rnd[0], rnd[1]);
+                    n1 = tpdf_from_bits(rnd[2], rnd[3]);
+                }
+                q[c * C] = quantize16(l, n0);
+                if (C > 1) q[c * C + 1] = quantize16(rr, n1);
+            }
+        }
+        if (full) {
+            __stcs(reinterpret_cast<float4*>(P.out + r0 + i), a[r]);
+            if (C > 1) __stcs(reinterpret_cast<float4*>(P.out + r1 + i), b[r]);
+        } else {
+            for (int c = 0; c < 4; ++c)
+                if (i + c < P.n) { P.out[r0 + i + c] = comp4(a[r], c); if (C > 1) P.out[r1 + i + c] = comp4(b[r], c); }
+        }
+        if (PCM) {
+            int16_t* dst = P.pcm + ((size_t)track * (size_t)P.n + (size_t)i) * C;
+            if (full && C == 2 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+                int4 pk4;
+                pk4.x = (int)(uint16_t)q[0] | ((int)(uint16_t)q[1] << 16);
+                pk4.y = (int)(uint16_t)q[2] | ((int)(uint16_t)q[3] << 16);
+                pk4.z = (int)(uint16_t)q[4] | ((int)(uint16_t)q[5] << 16);
+                pk4.w = (int)(uint16_t)q[6] | ((int)(uint16_t)q[7] << 16);
+                __stcs(reinterpret_cast<int4*>(dst), pk4);
+            } else {
+                for (int c = 0; c < 4; ++c)
+                    if (i + c < P.n) for (int k = 0; k < C; ++k) dst[c * C + k] = q[c * C + k];
+            }
+        }
+    }
+    if (P.nonfinite) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) bad += shfl_xor_d(bad, o);
+        if ((threadIdx.x & 31) == 0 && bad > 0.0) atomicAdd(P.nonfinite + track, bad);
+    }
+}
+
 // standalone quantiser for an already final float32 buffer (export_audio on its own)
 __global__ void __launch_bounds__(kPwThreads) quantize_kernel(const QuantArgs P) {
     const int track = blockIdx.y, C = P.channels;
@@ -264,7 +401,7 @@ __global__ void __launch_bounds__(kPwThreads) quantize_kernel(const QuantArgs P)
                                 (unsigned)P.seed, (unsigned)(P.seed >> 32), rnd);
     for (int c = 0; c < C; ++c) {
         const float x = P.in[(size_t)(track * C + c) * (size_t)P.stride + kLead + i];
-        const float nz = P.noise ? P.noise[fi * C + c] : tpdf_from_bits(rnd[2 * c], rnd[2 * c + 1]);
+        const double nz = P.noise ? (double)P.noise[fi * C + c] : tpdf_from_bits(rnd[2 * c], rnd[2 * c + 1]);
         P.pcm[fi * C + c] = quantize16(x, nz);
     }
 }

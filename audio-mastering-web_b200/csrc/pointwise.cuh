@@ -29,30 +29,25 @@ __device__ __forceinline__ float compress_band_f64(double x, const DynBand& b, d
 }
 
 // band -> compress -> hard clip at lim_db -> * gain, all as the numpy branch does it
-// (backend/app/pipeline.py:466-474).  The downward soft/hard knee (the default configuration) runs in
-// float32: the band itself is float32 here (HBM storage), the reference's float64 knee arithmetic
-// followed by its float32 cast differs from this by at most one float32 ulp of the band sample.
-// The upward (ratio < 1) branch needs log10/pow and stays in float64.
+// (backend/app/pipeline.py:466-474).  The downward knee (ratio >= 1, the default configuration) is one
+// branch-free piecewise-linear map in float32,
+//     o = |y| <= lower ? |y| : (|y| >= upper ? thr + (|y| - thr)/ratio : lower + (|y| - lower) * slope),
+// with lower = +inf for a bypassed band (ratio == 1) and lower = upper = thr for a hard knee.  The band
+// itself is float32 here (HBM storage); the reference's float64 knee followed by its float32 cast differs
+// from this by at most one float32 ulp of the band sample.  The upward branch (ratio < 1) needs
+// log10/pow, stays in float64 and out of line so that the hot loop stays small in the instruction cache.
+__device__ __noinline__ float band_chain_upward(float y, const DynBand& b) {
+    double raw;
+    const float c = compress_band_f64((double)y, b, &raw);
+    return __fmul_rn(fminf(fmaxf(c, -b.lim), b.lim), b.gain);
+}
 __device__ __forceinline__ float band_chain(float y, const DynBand& b) {
-    if (b.mode == 0) {          // ratio == 1: the float64 band is only clipped
-        return __fmul_rn(fminf(fmaxf(y, -b.lim), b.lim), b.gain);
-    }
-    if (b.mode == 3) {
-        double raw;
-        const float c = compress_band_f64((double)y, b, &raw);
-        return __fmul_rn(fminf(fmaxf(c, -b.lim), b.lim), b.gain);
-    }
+    if (b.mode == 3) return band_chain_upward(y, b);
     const float ax = fabsf(y);
-    float o;
-    if (b.mode == 1) {
-        o = fminf(ax, fmaf(fmaxf(ax - b.thr_f, 0.f), b.inv_ratio_f, b.thr_f));
-    } else {
-        const float hi = fmaf(ax - b.thr_f, b.inv_ratio_f, b.thr_f);
-        const float mid = fmaf(ax - b.lower_f, b.slope_f, b.lower_f);
-        o = ax <= b.lower_f ? ax : (ax >= b.upper_f ? hi : mid);
-        o = fmaxf(o, 0.f);
-    }
-    o = fminf(o, b.lim);        // clip(+-lim) of sign * o
+    const float hi = fmaf(ax - b.thr_f, b.inv_ratio_f, b.thr_f);
+    const float mid = fmaf(ax - b.lower_f, b.slope_f, b.lower_f);
+    float o = ax <= b.lower_f ? ax : (ax >= b.upper_f ? hi : mid);
+    o = fminf(fmaxf(o, 0.f), b.lim);        // clip(+-lim) of sign * o
     return __fmul_rn(copysignf(o, y), b.gain);
 }
 
@@ -62,7 +57,7 @@ __device__ __forceinline__ float maximize_limit(float s, const DynParams& d) {
     const float sgn = (s > 0.f) ? 1.f : ((s < 0.f) ? -1.f : 0.f);
     float o = ax;
     if (!(ax <= d.max_thr)) {
-        o = __fadd_rn(d.max_thr, __fdiv_rn(__fmul_rn(__fsub_rn(ax, d.max_thr), d.max_num), d.max_den));
+        o = fmaf(__fsub_rn(ax, d.max_thr), d.max_k, d.max_thr);      // thr + (|x| - thr) * (ceil - thr) / (1 - thr)
     }
     o = fminf(o, d.max_ceil);
     const float v = __fmul_rn(sgn, o);
@@ -86,15 +81,18 @@ __device__ __forceinline__ float parallel_compress(float x, double mixd, const D
     return fminf(fmaxf(out, -1.f), 1.f);
 }
 
-// _exciter_saturate "warm"/tape/tube/transistor/digital in float64 (pipeline.py:1179-1197)
-__device__ __forceinline__ double exciter_sat(double x, int mode, double k) {
-    x = fmin(fmax(x, -1.0), 1.0);
+// _exciter_saturate "warm"/tape/tube/transistor/digital (pipeline.py:1179-1197).  The reference evaluates
+// it in float64; here the saturator runs in float32 (tanhf, full-precision variant): what reaches the
+// output is (sat - hf) * gain * 0.25 with gain = 10^(dB/20) - 1 <= ~0.1, so a float32 ulp of `sat`
+// (6e-8 |hf|) moves the output by < 2e-9.
+__device__ __forceinline__ float exciter_sat(float x, int mode, float k) {
+    x = fminf(fmaxf(x, -1.f), 1.f);
     switch (mode) {
-        case 1: return tanh(k * x) / (k + 1e-8);                         // tape
-        case 2: return x + 0.3 * (x * x);                                // tube
-        case 3: return x - (x * x * x) / 3.0;                            // transistor
-        case 4: return x;                                                // digital (|x| <= 1 after the clip)
-        default: return 0.5 * (tanh(k * x) / (k + 1e-8) + x + 0.3 * (x * x));  // warm
+        case 1: return tanhf(k * x) / (k + 1e-8f);                          // tape
+        case 2: return x + 0.3f * (x * x);                                  // tube
+        case 3: return x - (x * x * x) / 3.0f;                              // transistor
+        case 4: return x;                                                   // digital (|x| <= 1 after the clip)
+        default: return 0.5f * (tanhf(k * x) / (k + 1e-8f) + x + 0.3f * (x * x));  // warm
     }
 }
 

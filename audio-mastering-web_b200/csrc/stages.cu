@@ -6,11 +6,10 @@
 #include <cstring>
 
 #include "context.h"
-#include "sweep.cuh"
+#include "sweep3.cuh"
 #include "lufs_kernel.cuh"
 #include "misc_kernels.cuh"
 #include "stages_internal.h"
-#include "sweep3.cuh"
 
 namespace mm {
 
@@ -85,6 +84,16 @@ static int launch_sweep2(mm_ctx* c, SweepArgs<M, NF>& A, int whalo, const char* 
     return 0;
 }
 
+// ring depth: the per-kernel default, or MM_ST=1|2 from the environment (tuning experiments)
+static int stage_override(int dflt) {
+    static int forced = -1;
+    if (forced < 0) {
+        const char* e = getenv("MM_ST");
+        forced = e ? atoi(e) : 0;
+    }
+    return (forced == 1 || forced == 2) ? forced : dflt;
+}
+
 static int halo_tiles(const FilterPlan* const* plans, int nf) {
     int w = 1;
     for (int f = 0; f < nf; ++f) w = std::max(w, plans[f]->tabs.W);   // 1e-18: results do not depend on the segmentation
@@ -134,13 +143,15 @@ int sweep_fwd(mm_ctx* c, const mm_geom* g, int nf, int nin, const FilterPlan* co
     {                                                                             \
         SweepArgs<M_, NF_> A;                                                     \
         fill_common<M_, NF_>(A, g, plans, in, nin, out, nf, pro, epi, pad);       \
-        return launch_sweep2<M_, NF_, NIN_, +1, EPI_STORE, 0, ST_>(c, A, halo_tiles(plans, nf), "sweep_fwd_m" #M_ "_f" #NF_ "_i" #NIN_); \
+        if (stage_override(ST_) == 1)                                             \
+            return launch_sweep2<M_, NF_, NIN_, +1, EPI_STORE, 0, 1>(c, A, halo_tiles(plans, nf), "sweep_fwd_m" #M_ "_f" #NF_ "_i" #NIN_); \
+        return launch_sweep2<M_, NF_, NIN_, +1, EPI_STORE, 0, 2>(c, A, halo_tiles(plans, nf), "sweep_fwd_m" #M_ "_f" #NF_ "_i" #NIN_); \
     }
-    if (m == 2 && nf == 1 && nin == 1) MM_FWD(2, 1, 1, 2)
-    if (m == 2 && nf == 2 && nin == 1) MM_FWD(2, 2, 1, 2)
-    if (m == 2 && nf == 2 && nin == 2) MM_FWD(2, 2, 2, 2)
-    if (m == 2 && nf == 4 && nin == 1) MM_FWD(2, 4, 1, 2)
-    if (m == 4 && nf == 1 && nin == 1) MM_FWD(4, 1, 1, 2)
+    if (m == 2 && nf == 1 && nin == 1) MM_FWD(2, 1, 1, 1)
+    if (m == 2 && nf == 2 && nin == 1) MM_FWD(2, 2, 1, 1)
+    if (m == 2 && nf == 2 && nin == 2) MM_FWD(2, 2, 2, 1)
+    if (m == 2 && nf == 4 && nin == 1) MM_FWD(2, 4, 1, 1)
+    if (m == 4 && nf == 1 && nin == 1) MM_FWD(4, 1, 1, 1)
 #undef MM_FWD
     set_error("no forward sweep instantiation for order %d, %d filters, %d inputs", m, nf, nin);
     return 1;
@@ -155,16 +166,22 @@ int sweep_bwd(mm_ctx* c, const mm_geom* g, int nf, const FilterPlan* const* plan
     {                                                                             \
         SweepArgs<M_, NF_> A;                                                     \
         fill_common<M_, NF_>(A, g, plans, in, nf, out, nout, epi.auxp, epi, pad); \
-        return launch_sweep2<M_, NF_, NF_, -1, EPI_, NAUX_, ST_>(c, A, halo_tiles(plans, nf), "sweep_bwd_m" #M_ "_f" #NF_ TAG_); \
+        if (stage_override(ST_) == 1)                                             \
+            return launch_sweep2<M_, NF_, NF_, -1, EPI_, NAUX_, 1>(c, A, halo_tiles(plans, nf), "sweep_bwd_m" #M_ "_f" #NF_ TAG_); \
+        return launch_sweep2<M_, NF_, NF_, -1, EPI_, NAUX_, 2>(c, A, halo_tiles(plans, nf), "sweep_bwd_m" #M_ "_f" #NF_ TAG_); \
     }
-    if (m == 2 && nf == 1 && epi.mode == EPI_STORE) MM_BWD(2, 1, EPI_STORE, 0, 2, "_store")
-    if (m == 2 && nf == 1 && epi.mode == EPI_COMBINE && naux == 1) MM_BWD(2, 1, EPI_COMBINE, 1, 2, "_combine")
-    if (m == 2 && nf == 1 && epi.mode == EPI_EXCITER && naux == 1) MM_BWD(2, 1, EPI_EXCITER, 1, 2, "_exciter")
-    if (m == 2 && nf == 2 && epi.mode == EPI_STORE) MM_BWD(2, 2, EPI_STORE, 0, 2, "_store")
-    if (m == 2 && nf == 2 && epi.mode == EPI_COMBINE && naux == 1) MM_BWD(2, 2, EPI_COMBINE, 1, 2, "_combine")
-    if (m == 2 && nf == 2 && epi.mode == EPI_DYNAMICS && naux == 2) MM_BWD(2, 2, EPI_DYNAMICS, 2, 2, "_dynamics")
-    if (m == 2 && nf == 4 && epi.mode == EPI_COMBINE && naux == 1) MM_BWD(2, 4, EPI_COMBINE, 1, 1, "_combine")
-    if (m == 4 && nf == 1 && epi.mode == EPI_STORE) MM_BWD(4, 1, EPI_STORE, 0, 2, "_store")
+    if (m == 2 && nf == 1 && epi.mode == EPI_STORE) MM_BWD(2, 1, EPI_STORE, 0, 1, "_store")
+    if (m == 2 && nf == 1 && epi.mode == EPI_COMBINE && naux == 1) MM_BWD(2, 1, EPI_COMBINE, 1, 1, "_combine")
+    if (m == 2 && nf == 1 && epi.mode == EPI_EXCITER && naux == 1) MM_BWD(2, 1, EPI_EXCITER, 1, 1, "_exciter")
+    if (m == 2 && nf == 2 && epi.mode == EPI_STORE) MM_BWD(2, 2, EPI_STORE, 0, 1, "_store")
+    if (m == 2 && nf == 2 && epi.mode == EPI_COMBINE && naux == 1) MM_BWD(2, 2, EPI_COMBINE, 1, 1, "_combine")
+    if (m == 2 && nf == 2 && epi.mode == EPI_DYNAMICS && naux == 2) MM_BWD(2, 2, EPI_DYNAMICS, 2, 1, "_dynamics")
+    if (m == 2 && nf == 4 && epi.mode == EPI_COMBINE && naux == 1) {
+        SweepArgs<2, 4> A;
+        fill_common<2, 4>(A, g, plans, in, nf, out, nout, epi.auxp, epi, pad);
+        return launch_sweep2<2, 4, 4, -1, EPI_COMBINE, 1, 1>(c, A, halo_tiles(plans, nf), "sweep_bwd_m2_f4_combine");
+    }
+    if (m == 4 && nf == 1 && epi.mode == EPI_STORE) MM_BWD(4, 1, EPI_STORE, 0, 1, "_store")
 #undef MM_BWD
     if (m == 2 && nf == 4 && epi.mode == EPI_STORE && nout == 4) {
         // four independent sections: two 2-section sweeps move the same bytes and fit two CTAs per SM
@@ -261,6 +278,25 @@ int run_out_scalars(mm_ctx* c, const OutScalarArgs& O) {
     return 0;
 }
 
+int run_finalize(mm_ctx* c, const mm_geom* g, const float* in, float* out, const double* mul, const double* width, int n_fade,
+                 int16_t* pcm, const float* noise, unsigned long long seed, double* nonfinite) {
+    FinalArgs A;
+    A.in = in; A.out = out; A.n = g->n; A.stride = g->stride; A.tracks = g->tracks; A.mul = mul; A.width = width;
+    A.n_fade = n_fade; A.fade_step = n_fade > 1 ? 1.0 / (double)(n_fade - 1) : 0.0;
+    A.pcm = pcm; A.noise = noise; A.seed = seed; A.nonfinite = nonfinite;
+    dim3 grid((unsigned)((g->n + kFinFrames - 1) / kFinFrames), (unsigned)g->tracks);
+    KernelScope ks(c, pcm ? "finalize_dither_int16" : "finalize");
+#define MM_FIN(C_, PCM_, NZ_) finalize_kernel<C_, PCM_, NZ_><<<grid, kFinThreads, 0, c->stream>>>(A)
+    if (g->channels == 2) {
+        if (!pcm) MM_FIN(2, false, false); else if (noise) MM_FIN(2, true, true); else MM_FIN(2, true, false);
+    } else {
+        if (!pcm) MM_FIN(1, false, false); else if (noise) MM_FIN(1, true, true); else MM_FIN(1, true, false);
+    }
+#undef MM_FIN
+    MM_CUDA(cudaGetLastError());
+    return 0;
+}
+
 int run_quantize(mm_ctx* c, const QuantArgs& Q) {
     dim3 grid((unsigned)((Q.n + kPwThreads - 1) / kPwThreads), (unsigned)Q.tracks);
     KernelScope ks(c, "quantize_int16");
@@ -296,13 +332,13 @@ void fill_dyn(DynParams* d, double knee_db, const double* band_ratios, double ma
         b.lim = (float)std::pow(10.0, lim_db / 20.0);
         b.gain = (float)gain;
         b.thr_f = (float)b.thr;
-        b.inv_ratio_f = (float)(1.0 / ratio);
+        b.inv_ratio_f = ratio > 0.0 ? (float)(1.0 / ratio) : 1.f;
         b.lower_f = (float)b.lower;
         b.upper_f = (float)b.upper;
         b.slope_f = (float)b.slope;
-        if (ratio <= 0.0 || ratio == 1.0) b.mode = 0;
+        if (ratio <= 0.0 || ratio == 1.0) { b.mode = 0; b.lower_f = __builtin_inff(); b.upper_f = __builtin_inff(); }
         else if (ratio < 1.0) b.mode = 3;
-        else if (knee_db < 0.5) b.mode = 1;
+        else if (knee_db < 0.5) { b.mode = 1; b.lower_f = b.thr_f; b.upper_f = b.thr_f; }
         else b.mode = 2;
     }
     const double thr = std::pow(10.0, -2.5 / 20.0), ceil_ = std::pow(10.0, -0.3 / 20.0);
@@ -310,6 +346,7 @@ void fill_dyn(DynParams* d, double knee_db, const double* band_ratios, double ma
     d->max_ceil = (float)ceil_;
     d->max_num = (float)(ceil_ - thr);
     d->max_den = (float)(1.0 - thr);
+    d->max_k = (float)((ceil_ - thr) / (1.0 - thr));
     d->tp_lim = (float)std::pow(10.0, -1.5 / 20.0);
     d->par_mix = nullptr;
     fill_parallel(d, 8.0, -20.0);
@@ -440,30 +477,39 @@ int st_lufs(mm_ctx* c, const mm_geom* g, const float* in, const Pro& pro, double
     const LufsPlan* lp;
     MM_TRY(get_lufs_plan(c, g->n, g->sr, &lp));
     const int rows = g->tracks * g->channels;
-    double* segsum;
+    unsigned long long* segsum;
     MM_TRY(arena(c, SL_SEGSUM, (size_t)rows * (size_t)std::max(lp->nseg, 1), &segsum));
     if (lp->valid) {
         const FilterPlan* k0 = get_plan(c, k_weighting_stage(0, (double)g->sr));
         const FilterPlan* k1 = get_plan(c, k_weighting_stage(1, (double)g->sr));
         if (!k0 || !k1) return 1;
-        MM_CUDA(cudaMemsetAsync(segsum, 0, (size_t)rows * lp->nseg * sizeof(double), c->stream));
+        MM_CUDA(cudaMemsetAsync(segsum, 0, (size_t)rows * lp->nseg * sizeof(unsigned long long), c->stream));
+        static int capacity = 0;
+        if (capacity == 0) {
+            int bps = 0;
+            MM_CUDA(cudaFuncSetAttribute(lufs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kLufsSmem));
+            MM_CUDA(cudaFuncSetAttribute(lufs_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+            MM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, lufs_kernel, kT, kLufsSmem));
+            cudaDeviceProp prop;
+            MM_CUDA(cudaGetDeviceProperties(&prop, c->device));
+            capacity = std::max(1, bps) * prop.multiProcessorCount;
+        }
         LufsArgs A;
         memset(&A, 0, sizeof(A));
         fill_filter<2>(A.f[0], k0);
         fill_filter<2>(A.f[1], k1);
         A.tab[0] = k0->dev; A.tab[1] = k1->dev;
-        A.W[0] = k0->tabs.W; A.W[1] = k1->tabs.W;
         A.in = in; A.n = g->n; A.stride = g->stride; A.rows = rows; A.ntiles = lp->ntiles; A.channels = g->channels;
         A.pro_mode = pro.mode; A.pro_sub = pro.sub; A.pro_mul = pro.mul;
-        A.bnd = lp->bnd; A.nseg = lp->nseg; A.tile_seg = lp->tile_seg; A.segsum = segsum;
-        const size_t items = (size_t)rows * (size_t)lp->ntiles;
-        MM_TRY(ensure_carry(c, 2 * items));
-        A.agg = c->agg; A.flag = c->flag; A.epoch = ++c->epoch;
-        A.ticket = c->ticket; A.ticket_base = c->ticket_total; c->ticket_total += (unsigned)items;
-        A.err = c->err;
+        A.bnd = lp->bnd; A.nhop = lp->nseg; A.tile_seg = lp->tile_seg; A.segsum = segsum;
+        // the high-pass forgets its own start-up in W1 tiles, but is fed the shelf's start-up for W0 tiles first
+        A.whalo = k0->tabs.W + k1->tabs.W;
+        choose_segments(rows, lp->ntiles, A.whalo, capacity, &A.nseg, &A.seglen);
+        const long long items = (long long)rows * A.nseg;
+        const unsigned grid = (unsigned)std::min<long long>(items, capacity);
         {
             KernelScope ks(c, "lufs_kweight_blocks");
-            lufs_kernel<<<(unsigned)items, kT, 0, c->stream>>>(A);
+            lufs_kernel<<<grid, kT, kLufsSmem, c->stream>>>(A);
         }
         MM_CUDA(cudaGetLastError());
     }

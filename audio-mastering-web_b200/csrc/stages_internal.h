@@ -43,6 +43,9 @@ int run_in_scalars(mm_ctx* c, const mm_geom* g, const RowStats* st, int use_dc, 
                    double* sub, double* mul, double* peak_track, double* mean_row);
 int run_pointwise(mm_ctx* c, const mm_geom* g, PwArgs& A, const char* name);
 int run_out_scalars(mm_ctx* c, const OutScalarArgs& O);
+struct FinalArgs;
+int run_finalize(mm_ctx* c, const mm_geom* g, const float* in, float* out, const double* mul, const double* width, int n_fade,
+                 int16_t* pcm, const float* noise, unsigned long long seed, double* nonfinite);
 int run_quantize(mm_ctx* c, const QuantArgs& Q);
 // dir 0: interleaved -> planar, 1: planar -> interleaved
 int run_layout(mm_ctx* c, const mm_geom* g, const float* interleaved, float* planar, int dir);

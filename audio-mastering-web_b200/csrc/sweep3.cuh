@@ -25,11 +25,17 @@
 // chunk) and the scan one (thread t walks chunk t).
 #pragma once
 #include "pointwise.cuh"
-#include "sweep.cuh"   // df2t_step
+#include "common.cuh"
 
 namespace mm {
 
 constexpr int kTileVecs = kL / 4;  // float4 per stream tile
+
+// float -> double widening.  Measured on B200 (tools/microbench.cu): F2F runs at ~15 lanes/clk/SM, an
+// integer-pipe emulation (shift/add/select, 6-7 instructions) is slower at saturation and costs issue
+// slots this kernel does not have, so the conversion unit it is.
+__device__ __forceinline__ double f2d_bits(float x) { return (double)x; }
+
 
 template <int M> struct SmemTab {
     double Pw[5][M * M];
@@ -82,7 +88,7 @@ template <int M, int NF> struct Scratch2 {
 // prologue helpers (see common.cuh PRO_*)
 __device__ __forceinline__ float pro1(int mode, float x, float subf, float mulf, double muld) {
     if (mode == PRO_SUBMUL_F32) return __fmul_rn(__fsub_rn(x, subf), mulf);
-    if (mode == PRO_MUL_F64) return (float)((double)x * muld);
+    if (mode == PRO_MUL_F64) return (float)(f2d_bits(x) * muld);
     return x;
 }
 
@@ -132,13 +138,11 @@ __global__ void __launch_bounds__(kT) sweep2_kernel(const __grid_constant__ Swee
         if (fast_in(lo)) {
 #pragma unroll
             for (int s = 0; s < NIN; ++s) {
-                const float* src = P.in[s] + rowoff + lo;
-                float* dst = ring + ((size_t)slot * NIN + s) * kL;
+                // swz(tid + kT r) = swz(tid) + kT r (kT is a multiple of 8): base + immediate addressing
+                const float* src = P.in[s] + rowoff + lo + 4 * tid;
+                float* dst = ring + ((size_t)slot * NIN + s) * kL + 4 * swz(tid);
 #pragma unroll
-                for (int r = 0; r < kTileVecs / kT; ++r) {
-                    const int v = tid + kT * r;
-                    cp_async16(dst + 4 * swz(v), src + 4 * v);
-                }
+                for (int r = 0; r < kTileVecs / kT; ++r) cp_async16(dst + 4 * kT * r, src + 4 * kT * r);
             }
         } else {
             // edge tile: synchronous, with prologue, scipy's odd extension and dead zeros applied here
@@ -191,13 +195,10 @@ __global__ void __launch_bounds__(kT) sweep2_kernel(const __grid_constant__ Swee
         const size_t rowoff = (size_t)row * (size_t)P.stride;
 #pragma unroll
         for (int s = 0; s < NAUX; ++s) {
-            const float* src = P.aux[s] + rowoff + lo;
-            float* dst = auxs + (size_t)s * kL;
+            const float* src = P.aux[s] + rowoff + lo + 4 * tid;
+            float* dst = auxs + (size_t)s * kL + 4 * swz(tid);
 #pragma unroll
-            for (int r = 0; r < kTileVecs / kT; ++r) {
-                const int v = tid + kT * r;
-                cp_async16(dst + 4 * swz(v), src + 4 * v);
-            }
+            for (int r = 0; r < kTileVecs / kT; ++r) cp_async16(dst + 4 * kT * r, src + 4 * kT * r);
         }
     };
 
@@ -283,7 +284,7 @@ __global__ void __launch_bounds__(kT) sweep2_kernel(const __grid_constant__ Swee
                 const int j = 4 * u + c;
                 double xd[NIN];
 #pragma unroll
-                for (int s = 0; s < NIN; ++s) xd[s] = (double)comp4(xv[s], cc);
+                for (int s = 0; s < NIN; ++s) xd[s] = f2d_bits(comp4(xv[s], cc));
 #pragma unroll
                 for (int f = 0; f < NF; ++f)
 #pragma unroll
@@ -395,7 +396,7 @@ __global__ void __launch_bounds__(kT) sweep2_kernel(const __grid_constant__ Swee
                     const int cc = (DIR > 0) ? c : (3 - c);
                     double xd[NIN];
 #pragma unroll
-                    for (int s = 0; s < NIN; ++s) xd[s] = (double)comp4(xv[s], cc);
+                    for (int s = 0; s < NIN; ++s) xd[s] = f2d_bits(comp4(xv[s], cc));
 #pragma unroll
                     for (int f = 0; f < NF; ++f) {
                         const double y = df2t_step<M>(P.f[f], xd[NIN == 1 ? 0 : f], z[f]);
@@ -439,76 +440,98 @@ __global__ void __launch_bounds__(kT) sweep2_kernel(const __grid_constant__ Swee
             if (P.pro_mul) { aux_muld = __ldg(P.pro_mul + row); aux_mulf = (float)aux_muld; }
         }
         float pk = 0.f;
-#pragma unroll 2
-        for (int r = 0; r < kTileVecs / kT; ++r) {
-            const int v = tid + kT * r;
-            const long long q = tile_lo + 4 * v;
-            if (!out_fast && (q + 3 < st_lo || q > st_hi)) continue;
-            const bool full = out_fast || (q >= st_lo && q + 3 <= st_hi);
-            const int so = 4 * swz(v);
-            float4 y[NF];
+        // one output element of a recombining epilogue (float64 where the reference's numpy arithmetic is)
+        auto epi_value = [&](float xa_raw, float a1c, const float (&yc)[NF]) -> float {
+            float xa = xa_raw;
+            if (P.aux_pro) xa = pro1(P.pro_mode, xa, aux_subf, aux_mulf, aux_muld);
+            if (EPI == EPI_COMBINE) {
+                double acc = P.wc * f2d_bits(xa);
 #pragma unroll
-            for (int f = 0; f < NF; ++f) y[f] = *reinterpret_cast<const float4*>(tout[f] + so);
+                for (int f = 0; f < NF; ++f) acc = fma(P.w[f], f2d_bits(yc[f]), acc);
+                return (float)(acc * P.trim);
+            } else if (EPI == EPI_EXCITER) {
+                const float hf = yc[0];
+                const float sat = exciter_sat(hf, P.exc_mode, (float)P.exc_k);
+                return (float)fma((double)(sat - hf), P.exc_gain * 0.25, (double)xa);
+            } else {   // EPI_DYNAMICS: aux0 = band 1, y0 = band 2, y1 = band 3, aux1 = band 4
+                float sacc = band_chain(xa, P.dyn.band[0]);
+                sacc = __fadd_rn(sacc, band_chain(yc[0], P.dyn.band[1]));
+                sacc = __fadd_rn(sacc, band_chain(yc[NF > 1 ? 1 : 0], P.dyn.band[2]));
+                sacc = __fadd_rn(sacc, band_chain(a1c, P.dyn.band[3]));
+                float res = maximize_limit(sacc, P.dyn);
+                if (P.dyn.par_mix) {
+                    const double mix = __ldg(P.dyn.par_mix + row);
+                    if (mix >= 0.01) res = parallel_compress(res, mix, P.dyn);
+                }
+                return res;
+            }
+        };
+        if (out_fast) {
+            // interior tile: every vector is complete; base + immediate addressing (swz(tid + kT r) = swz(tid) + kT r)
+            const int so0 = 4 * swz(tid);
+            const size_t go0 = rowoff + (size_t)tile_lo + 4 * tid;
             if (EPI == EPI_STORE) {
 #pragma unroll
-                for (int f = 0; f < NF; ++f) {
-                    float* dst = P.out[f] + rowoff;
-                    if (full) __stcs(reinterpret_cast<float4*>(dst + q), y[f]);
-                    else {
+                for (int r = 0; r < kTileVecs / kT; ++r) {
+#pragma unroll
+                    for (int f = 0; f < NF; ++f)
+                        __stcs(reinterpret_cast<float4*>(P.out[f] + go0 + 4 * kT * r),
+                               *reinterpret_cast<const float4*>(tout[f] + so0 + 4 * kT * r));
+                }
+            } else {
+                float* dst = P.out[0] + go0;
+#pragma unroll 4
+                for (int r = 0; r < kTileVecs / kT; ++r) {
+                    float4 y[NF];
+#pragma unroll
+                    for (int f = 0; f < NF; ++f) y[f] = *reinterpret_cast<const float4*>(tout[f] + so0 + 4 * kT * r);
+                    float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0, o;
+                    if (NAUX > 0) a0 = *reinterpret_cast<const float4*>(auxs + so0 + 4 * kT * r);
+                    if (NAUX > 1) a1 = *reinterpret_cast<const float4*>(auxs + kL + so0 + 4 * kT * r);
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        float yc[NF];
+#pragma unroll
+                        for (int f = 0; f < NF; ++f) yc[f] = comp4(y[f], c);
+                        const float res = epi_value(comp4(a0, c), comp4(a1, c), yc);
+                        setcomp4(o, c, res);
+                        pk = fmaxf(pk, fabsf(res));
+                    }
+                    __stcs(reinterpret_cast<float4*>(dst + 4 * kT * r), o);
+                }
+            }
+        } else {
+#pragma unroll 1
+            for (int r = 0; r < kTileVecs / kT; ++r) {
+                const int v = tid + kT * r;
+                const long long q = tile_lo + 4 * v;
+                if (q + 3 < st_lo || q > st_hi) continue;
+                const int so = 4 * swz(v);
+                float4 y[NF];
+#pragma unroll
+                for (int f = 0; f < NF; ++f) y[f] = *reinterpret_cast<const float4*>(tout[f] + so);
+                if (EPI == EPI_STORE) {
+#pragma unroll
+                    for (int f = 0; f < NF; ++f) {
+                        float* dst = P.out[f] + rowoff;
 #pragma unroll
                         for (int c = 0; c < 4; ++c)
                             if (q + c >= st_lo && q + c <= st_hi) dst[q + c] = comp4(y[f], c);
                     }
-                }
-            } else {
-                float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0, o;
-                if (out_fast) {
-                    if (NAUX > 0) a0 = *reinterpret_cast<const float4*>(auxs + so);
-                    if (NAUX > 1) a1 = *reinterpret_cast<const float4*>(auxs + kL + so);
                 } else {
                     const float* x0 = (NAUX > 0) ? P.aux[0] + rowoff : nullptr;
                     const float* x1 = (NAUX > 1) ? P.aux[1] + rowoff : nullptr;
+                    float* dst = P.out[0] + rowoff;
 #pragma unroll
-                    for (int c = 0; c < 4; ++c)
-                        if (q + c >= st_lo && q + c <= st_hi) {
-                            if (NAUX > 0) setcomp4(a0, c, x0[q + c]);
-                            if (NAUX > 1) setcomp4(a1, c, x1[q + c]);
-                        }
-                }
+                    for (int c = 0; c < 4; ++c) {
+                        if (q + c < st_lo || q + c > st_hi) continue;
+                        float yc[NF];
 #pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    float xa = comp4(a0, c);
-                    if (P.aux_pro) xa = pro1(P.pro_mode, xa, aux_subf, aux_mulf, aux_muld);
-                    float res;
-                    if (EPI == EPI_COMBINE) {
-                        double acc = P.wc * (double)xa;
-#pragma unroll
-                        for (int f = 0; f < NF; ++f) acc += P.w[f] * (double)comp4(y[f], c);
-                        res = (float)(acc * P.trim);
-                    } else if (EPI == EPI_EXCITER) {
-                        const double hf = (double)comp4(y[0], c);
-                        const double sat = exciter_sat(hf, P.exc_mode, P.exc_k);
-                        res = (float)((double)xa + (sat - hf) * P.exc_gain * 0.25);
-                    } else {   // EPI_DYNAMICS: aux0 = band 1, y0 = band 2, y1 = band 3, aux1 = band 4
-                        float s = band_chain(xa, P.dyn.band[0]);
-                        s = __fadd_rn(s, band_chain(comp4(y[0], c), P.dyn.band[1]));
-                        s = __fadd_rn(s, band_chain(comp4(y[NF > 1 ? 1 : 0], c), P.dyn.band[2]));
-                        s = __fadd_rn(s, band_chain(comp4(a1, c), P.dyn.band[3]));
-                        res = maximize_limit(s, P.dyn);
-                        if (P.dyn.par_mix) {
-                            const double mix = __ldg(P.dyn.par_mix + row);
-                            if (mix >= 0.01) res = parallel_compress(res, mix, P.dyn);
-                        }
+                        for (int f = 0; f < NF; ++f) yc[f] = comp4(y[f], c);
+                        const float res = epi_value(NAUX > 0 ? x0[q + c] : 0.f, NAUX > 1 ? x1[q + c] : 0.f, yc);
+                        pk = fmaxf(pk, fabsf(res));
+                        dst[q + c] = res;
                     }
-                    setcomp4(o, c, res);
-                    if (full || (q + c >= st_lo && q + c <= st_hi)) pk = fmaxf(pk, fabsf(res));
-                }
-                float* dst = P.out[0] + rowoff;
-                if (full) __stcs(reinterpret_cast<float4*>(dst + q), o);
-                else {
-#pragma unroll
-                    for (int c = 0; c < 4; ++c)
-                        if (q + c >= st_lo && q + c <= st_hi) dst[q + c] = comp4(o, c);
                 }
             }
         }
