@@ -419,6 +419,16 @@ int mm_dev_fade_in(mm_ctx* c, const mm_geom* g, const float* in, float* out, dou
     return run_pointwise(c, g, A, "fade_in");
 }
 
+int mm_dev_blend(mm_ctx* c, const mm_geom* g, const float* dry, float* out, const float* processed, double amount) {
+    MM_API_BEGIN(c);
+    MM_TRY(check_geom(g));
+    PwArgs A;
+    pw_base(&A, dry, out, PW_BLEND);
+    A.in2 = processed;
+    A.blend = (float)std::min(std::max(amount, 0.0), 1.0);
+    return run_pointwise(c, g, A, "module_blend");
+}
+
 int mm_dev_apply_target_curve(mm_ctx* c, const mm_geom* g, const float* in, float* out, int eq_ms) {
     MM_API_BEGIN(c);
     MM_TRY(check_geom(g));

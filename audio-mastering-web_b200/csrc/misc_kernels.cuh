@@ -164,6 +164,13 @@ __global__ void __launch_bounds__(kPwThreads) pointwise_kernel(const PwArgs P) {
                 l = maximize_limit(l, P.dyn); rr = maximize_limit(rr, P.dyn);
             } else if (P.mode == PW_PARALLEL) {
                 l = parallel_compress(l, P.par_mix, P.dyn); rr = parallel_compress(rr, P.par_mix, P.dyn);
+            } else if (P.mode == PW_BLEND) {
+                // BaseModule.process (modules/base.py:44-46): audio * (1 - amount) + processed * amount, float32
+                const size_t o = (size_t)i + c;
+                const float pl = (i + c < P.n) ? P.in2[r0 + o] : 0.f, pr = (C > 1 && i + c < P.n) ? P.in2[r1 + o] : 0.f;
+                const float one_m = (float)(1.0 - (double)P.blend);
+                l = __fadd_rn(__fmul_rn(l, one_m), __fmul_rn(pl, P.blend));
+                rr = __fadd_rn(__fmul_rn(rr, one_m), __fmul_rn(pr, P.blend));
             } else if (P.mode == PW_GAIN_F64) {
                 // normalize_lufs (pipeline.py:654-655): float32 array * float64 scalar -> float64 -> float32
                 l = (float)((double)l * muld0); rr = (float)((double)rr * muld1);

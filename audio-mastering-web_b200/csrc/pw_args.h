@@ -29,10 +29,12 @@ struct OutScalarArgs {
 };
 
 enum { PW_AFFINE = 0, PW_MAXIMIZER = 1, PW_PARALLEL = 2, PW_IMAGER = 3, PW_FINALIZE = 4, PW_PEAK = 5, PW_FADE = 6,
-       PW_MS_ENCODE = 7, PW_MS_DECODE = 8, PW_GAIN_F64 = 9 };
+       PW_MS_ENCODE = 7, PW_MS_DECODE = 8, PW_GAIN_F64 = 9, PW_BLEND = 10 };
 
 struct PwArgs {
     const float* in;
+    const float* in2;           // PW_BLEND: the processed signal
+    float blend;                // PW_BLEND: amount in [0, 1]
     float* out;                 // planar (may be null for PW_PEAK)
     long long n, stride;
     int tracks, channels, mode;

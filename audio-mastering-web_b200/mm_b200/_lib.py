@@ -60,6 +60,7 @@ SIGNATURES = {
     "mm_dev_remove_dc_offset": (_i, [_vp, _gp, _vp, _vp]),
     "mm_dev_remove_intersample_peaks": (_i, [_vp, _gp, _vp, _vp, _d]),
     "mm_dev_fade_in": (_i, [_vp, _gp, _vp, _vp, _d]),
+    "mm_dev_blend": (_i, [_vp, _gp, _vp, _vp, _vp, _d]),
     "mm_dev_apply_target_curve": (_i, [_vp, _gp, _vp, _vp, _i]),
     "mm_dev_apply_deesser": (_i, [_vp, _gp, _vp, _vp, _d, _d, _d, _d, _d, _d]),
     "mm_dev_apply_dynamics": (_i, [_vp, _gp, _vp, _vp, _d, _dp, _dp, _d]),

@@ -1,0 +1,301 @@
+"""Drop-in for the reference's ``backend/app/chain.py`` + ``backend/app/modules/*.py`` (v2 chain).
+
+``MasteringChain.from_config`` / ``default_config`` / ``default_chain`` / ``process`` keep the
+reference's signatures and semantics (chain.py:40-134): modules run in list order, disabled modules
+pass audio through, ``amount < 1`` blends processed with dry (modules/base.py:32-46), ``target_lufs`` /
+``style`` keyword arguments override the module's own parameters (modules/normalize_lufs.py:30-32,
+modules/equalizer.py:83-85), and the result is clipped to +-1 with nan_to_num (chain.py:93-94).
+
+The audio is uploaded once, every module is a CUDA stage call on the device-resident batch, and the
+result is downloaded once.  When the configuration is exactly ``default_config(target, style)`` the
+whole chain runs as the fused sweep plan (``mm_dev_master``), which is what ``bench.py`` times.
+Second-wave modules (reverb, transient-aware maximizer, linear-phase EQ) raise
+``NotImplementedError`` when enabled instead of silently passing audio through.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Any, Callable, Optional
+
+import numpy as np
+
+from . import _lib
+from . import pipeline as P
+from .engine import Batch, Engine, MMError, get_engine, style_struct
+
+
+class BaseModule:
+    """modules/base.py:7-50 on a device batch."""
+
+    module_id = "base"
+
+    def __init__(self, enabled: bool = True, amount: float = 1.0, ms_mode: str = "both", **kwargs: Any):
+        self.enabled = bool(enabled)
+        self.amount = float(np.clip(amount, 0.0, 1.0))
+        self.ms_mode = str(ms_mode)
+        self.params = kwargs
+
+    @classmethod
+    def from_config(cls, config: dict) -> "BaseModule":
+        return cls(**config)
+
+    # -- numpy edge (same call shape as the reference) ------------------------------------------------
+    def process(self, audio: np.ndarray, sr: int, **kwargs: Any) -> np.ndarray:
+        if not self.enabled:
+            return audio
+        eng, b, mono = P._up(audio, sr)
+        out = self.process_batch(eng, b, **kwargs)
+        return audio if out is b else P._down(eng, out, mono)
+
+    # -- device path ------------------------------------------------------------------------------------
+    def process_batch(self, eng: Engine, b: Batch, **kwargs: Any) -> Batch:
+        if not self.enabled:
+            return b
+        try:
+            processed = self._process(eng, b, **kwargs)
+        except (NotImplementedError, MMError, ImportError):
+            raise                      # never hide a missing kernel or a device failure
+        except Exception:
+            return b                   # modules/base.py:40-43: any other failure passes the audio through
+        if self.amount >= 1.0 or processed is b:
+            return processed
+        g = b.geom
+        _lib.check(eng.lib.mm_dev_blend(eng.ctx, C.byref(g), b.ptr, processed.ptr, processed.ptr, C.c_double(self.amount)))
+        return processed
+
+    def _process(self, eng: Engine, b: Batch, **kwargs: Any) -> Batch:
+        return b
+
+
+def _d(v):
+    return C.c_double(float(v))
+
+
+class DCOffsetModule(BaseModule):
+    module_id = "dc_offset"
+
+    def _process(self, eng, b, **kw):
+        return eng.stage("remove_dc_offset", b)
+
+
+class PeakGuardModule(BaseModule):
+    module_id = "peak_guard"
+
+    def __init__(self, enabled=True, amount=1.0, headroom_db=0.5, **kwargs):
+        super().__init__(enabled=enabled, amount=amount, **kwargs)
+        self.headroom_db = float(headroom_db)
+
+    def _process(self, eng, b, **kw):
+        return eng.stage("remove_intersample_peaks", b, _d(self.headroom_db))
+
+
+class TargetCurveModule(BaseModule):
+    module_id = "target_curve"
+
+    def __init__(self, enabled=True, amount=1.0, ms_mode="both", phase_mode="minimum", eq_ms=False, **kwargs):
+        super().__init__(enabled=enabled, amount=amount, ms_mode=ms_mode, **kwargs)
+        self.phase_mode, self.eq_ms = str(phase_mode), bool(eq_ms)
+
+    def _process(self, eng, b, **kw):
+        if kw.get("phase_mode", self.phase_mode) == "linear_phase":
+            raise NotImplementedError("linear-phase target curve is second-wave scope (SURVEY 8f)")
+        ms = bool(kw.get("eq_ms", self.eq_ms)) and b.channels == 2
+        return eng.stage("apply_target_curve", b, 1 if ms else 0)
+
+
+class DynamicsModule(BaseModule):
+    module_id = "dynamics"
+
+    def __init__(self, enabled=True, amount=1.0, knee_db=6.0, crossovers_hz=None, band_ratios=None, max_upward_boost_db=12.0, **kwargs):
+        super().__init__(enabled=enabled, amount=amount, **kwargs)
+        self.knee_db = float(knee_db)
+        self.crossovers_hz = tuple(float(x) for x in crossovers_hz) if crossovers_hz else None
+        self.band_ratios = tuple(float(x) for x in band_ratios) if band_ratios else None
+        self.max_upward_boost_db = float(max_upward_boost_db)
+
+    def _process(self, eng, b, **kw):
+        cx = _lib.darr(self.crossovers_hz) if self.crossovers_hz and len(self.crossovers_hz) == 3 else None
+        br = _lib.darr(self.band_ratios) if self.band_ratios and len(self.band_ratios) == 4 else None
+        return eng.stage("apply_dynamics", b, _d(self.knee_db), cx, br, _d(self.max_upward_boost_db))
+
+
+class MaximizerModule(BaseModule):
+    module_id = "maximizer"
+
+    def __init__(self, enabled=True, amount=1.0, sensitivity=0.5, **kwargs):
+        super().__init__(enabled=enabled, amount=amount, **kwargs)
+        self.sensitivity = float(sensitivity)
+
+    def _process(self, eng, b, **kw):
+        raise NotImplementedError("apply_maximizer_transient_aware is second-wave scope (SURVEY 8f)")
+
+
+class NormalizeLUFSModule(BaseModule):
+    module_id = "normalize_lufs"
+
+    def __init__(self, enabled=True, amount=1.0, target_lufs=-14.0, **kwargs):
+        super().__init__(enabled=enabled, amount=amount, **kwargs)
+        self.target_lufs = float(target_lufs)
+
+    def _process(self, eng, b, **kw):
+        if b.n < 0.4 * b.sr:
+            return b                                   # pipeline.py:647-650: the meter cannot run
+        target = float(kw.get("target_lufs", self.target_lufs))
+        return eng.stage("normalize_lufs", b, _lib.darr([target] * b.tracks))
+
+
+class FinalSpectralBalanceModule(BaseModule):
+    module_id = "final_spectral_balance"
+
+    def _process(self, eng, b, **kw):
+        return eng.stage("apply_final_spectral_balance", b)
+
+
+class StyleEQModule(BaseModule):
+    module_id = "style_eq"
+
+    def __init__(self, enabled=True, amount=1.0, style="standard", **kwargs):
+        super().__init__(enabled=enabled, amount=amount, **kwargs)
+        self.style = str(style)
+
+    def _process(self, eng, b, **kw):
+        cfg = P.STYLE_CONFIGS.get(kw.get("style", self.style), P.STYLE_CONFIGS["standard"])
+        return eng.stage("apply_style_eq", b, _lib.darr([cfg[k] for k in ("sub", "bass", "mids", "presence", "air")]))
+
+
+class ExciterModule(BaseModule):
+    module_id = "exciter"
+
+    def __init__(self, enabled=True, amount=1.0, exciter_db=0.0, mode="warm", oversample=1, **kwargs):
+        super().__init__(enabled=enabled, amount=amount, **kwargs)
+        self.exciter_db, self.mode, self.oversample = float(exciter_db), str(mode), int(oversample)
+
+    def _process(self, eng, b, **kw):
+        if abs(self.exciter_db) < 0.05:
+            return b
+        if max(1, min(4, self.oversample)) > 1:
+            raise NotImplementedError("oversampled exciter is second-wave scope (SURVEY 8f)")
+        return eng.stage("apply_harmonic_exciter", b, _d(self.exciter_db), P._EXCITER_MODES.get(self.mode, 0))
+
+
+class ImagerModule(BaseModule):
+    module_id = "imager"
+
+    def __init__(self, enabled=True, amount=1.0, width=1.0, stereoize_delay_ms=0.0, stereoize_mix=0.12, band_widths=None,
+                 crossovers_hz=None, **kwargs):
+        super().__init__(enabled=enabled, amount=amount, **kwargs)
+        self.width, self.stereoize_delay_ms, self.band_widths = float(width), float(stereoize_delay_ms or 0.0), band_widths
+
+    def _process(self, eng, b, **kw):
+        if b.channels != 2:
+            return b
+        if self.band_widths is not None or self.stereoize_delay_ms > 0:
+            raise NotImplementedError("multiband / Haas imager is second-wave scope (SURVEY 8f)")
+        return eng.stage("apply_stereo_imager", b, _d(self.width))
+
+
+class ReverbModule(BaseModule):
+    module_id = "reverb"
+
+    def __init__(self, enabled=False, amount=1.0, **kwargs):
+        super().__init__(enabled=enabled, amount=amount, **kwargs)
+
+    def _process(self, eng, b, **kw):
+        raise NotImplementedError("apply_reverb is second-wave scope (SURVEY 8f); it is disabled in the default chain")
+
+
+MODULE_REGISTRY = {m.module_id: m for m in (
+    DCOffsetModule, PeakGuardModule, TargetCurveModule, DynamicsModule, MaximizerModule, NormalizeLUFSModule,
+    FinalSpectralBalanceModule, StyleEQModule, ExciterModule, ImagerModule, ReverbModule)}
+
+
+class MasteringChain:
+    """chain.py:40-134."""
+
+    def __init__(self, modules, config: Optional[dict] = None):
+        self.modules = modules
+        self._config = config
+
+    @classmethod
+    def from_config(cls, config: dict) -> "MasteringChain":
+        modules = []
+        for item in config.get("modules", []):
+            item = dict(item)
+            mid = item.pop("id", None)
+            if not mid or mid not in MODULE_REGISTRY:
+                continue
+            modules.append(MODULE_REGISTRY[mid].from_config(item))
+        return cls(modules, config=config)
+
+    @classmethod
+    def default_config(cls, target_lufs: float = -14.0, style: str = "standard") -> dict:
+        cfg = P.STYLE_CONFIGS.get(style, P.STYLE_CONFIGS["standard"])
+        exciter_db, width = cfg.get("exciter_db", 0.0), cfg.get("imager_width", 1.0)
+        return {"modules": [
+            {"id": "dc_offset", "enabled": True, "amount": 1.0},
+            {"id": "peak_guard", "enabled": True, "headroom_db": 0.5, "amount": 1.0},
+            {"id": "target_curve", "enabled": True, "phase_mode": "minimum", "eq_ms": False, "amount": 1.0},
+            {"id": "dynamics", "enabled": True, "knee_db": 6.0, "crossovers_hz": [214.0, 2230.0, 10000.0], "amount": 1.0},
+            {"id": "normalize_lufs", "enabled": True, "target_lufs": target_lufs, "amount": 1.0},
+            {"id": "final_spectral_balance", "enabled": True, "amount": 1.0},
+            {"id": "style_eq", "enabled": True, "style": style, "amount": 1.0},
+            {"id": "exciter", "enabled": abs(exciter_db) >= 0.05, "exciter_db": exciter_db, "mode": "warm", "oversample": 1, "amount": 1.0},
+            {"id": "imager", "enabled": abs(width - 1.0) >= 0.01, "width": width, "stereoize_delay_ms": 0.0, "stereoize_mix": 0.12,
+             "band_widths": None, "crossovers_hz": [214.0, 2230.0, 10000.0], "amount": 1.0},
+            {"id": "reverb", "enabled": False, "reverb_type": "plate", "decay_sec": 1.2, "mix": 0.15, "mix_mid": None, "mix_side": None, "amount": 1.0},
+            {"id": "peak_guard", "enabled": True, "headroom_db": 0.5, "amount": 1.0},
+        ]}
+
+    @classmethod
+    def default_chain(cls, target_lufs: float = -14.0, style: str = "standard") -> "MasteringChain":
+        return cls.from_config(cls.default_config(target_lufs=target_lufs, style=style))
+
+    def _fused_plan(self, target_lufs, style):
+        """(target, style) when this chain is exactly the default one for them, else None."""
+        if self._config is None:
+            return None
+        try:
+            mods = self._config["modules"]
+            st = style if style is not None else next(m["style"] for m in mods if m.get("id") == "style_eq")
+            tg = target_lufs if target_lufs is not None else next(m["target_lufs"] for m in mods if m.get("id") == "normalize_lufs")
+        except (KeyError, StopIteration):
+            return None
+        if st not in P.STYLE_CONFIGS:
+            return None
+        ref = self.default_config(target_lufs=float(tg), style=st)
+        mine = {"modules": [dict(m) for m in mods]}
+        for m in mine["modules"]:                 # process() kwargs override these two fields anyway
+            if m.get("id") == "normalize_lufs":
+                m["target_lufs"] = float(tg)
+            if m.get("id") == "style_eq":
+                m["style"] = st
+        # the exciter / imager entries of the default config depend on the style the chain was built with
+        return (float(tg), st) if mine == ref else None
+
+    def process(self, audio: np.ndarray, sr: int, *, target_lufs: Optional[float] = None, style: Optional[str] = None,
+                progress_callback: Optional[Callable[[int, str], None]] = None, trace_ctx=None, **kwargs: Any) -> np.ndarray:
+        total = len(self.modules)
+        plan = self._fused_plan(target_lufs, style) if not kwargs else None
+        if plan is not None:
+            # the reference reports one progress tick per module (chain.py:80-82); same ticks, fused execution
+            if progress_callback:
+                for i, mod in enumerate(self.modules):
+                    progress_callback(5 + int(90 * (i / total)), getattr(mod, "module_id", "module"))
+            out = P.master_batch([audio], sr, [plan[1]], [plan[0]], chain="v2", job_fade=False)["audio"][0]
+        else:
+            eng, b, mono = P._up(audio, sr)
+            for i, mod in enumerate(self.modules):
+                if progress_callback and total > 0:
+                    progress_callback(5 + int(90 * (i / total)), getattr(mod, "module_id", "module"))
+                kw = dict(kwargs)
+                if target_lufs is not None:
+                    kw["target_lufs"] = target_lufs
+                if style is not None:
+                    kw["style"] = style
+                b = mod.process_batch(eng, b, **kw)
+            out = P._down(eng, b, mono)
+            out = np.ascontiguousarray(np.clip(out, -1.0, 1.0).astype(np.float32))
+            np.nan_to_num(out, copy=False, nan=0.0, posinf=1.0, neginf=-1.0)
+        if progress_callback:
+            progress_callback(98, "Готово")
+        return out

@@ -92,6 +92,8 @@ int mm_dev_remove_dc_offset(mm_ctx*, const mm_geom*, const float* in, float* out
 int mm_dev_remove_intersample_peaks(mm_ctx*, const mm_geom*, const float* in, float* out, double headroom_db);
 /* apply_output_edge_fade_in            backend/app/pipeline.py:152-167 */
 int mm_dev_fade_in(mm_ctx*, const mm_geom*, const float* in, float* out, double fade_ms);
+/* BaseModule.process blend                backend/app/modules/base.py:44-46: out = dry*(1-amount) + processed*amount */
+int mm_dev_blend(mm_ctx*, const mm_geom*, const float* dry, float* out, const float* processed, double amount);
 /* apply_target_curve (IIR, minimum)    backend/app/pipeline.py:238-273; eq_ms -> :248-255 */
 int mm_dev_apply_target_curve(mm_ctx*, const mm_geom*, const float* in, float* out, int eq_ms);
 /* apply_deesser                        backend/app/pipeline.py:1200-1264 */

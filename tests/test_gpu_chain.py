@@ -130,3 +130,47 @@ def test_run_mastering_pipeline_contract(P):
     assert -50 < lufs < 0
     mono = P.run_mastering_pipeline(x[:, 0].copy(), sr, style="dry_vocal")
     assert mono.shape == (x.shape[0],)
+
+
+def test_mastering_chain_api_default_and_custom(P):
+    """MasteringChain mirror (backend/app/chain.py): default chain == fused plan == reference golden;
+    a re-ordered / partially blended configuration runs module by module and matches the oracle."""
+    from mm_b200 import chain as mc
+    from oracle import chain as oc
+    g = load_golden("v2_standard_48k")
+    sr, target = int(g["sr"]), float(g["target"])
+    x = g["input"]
+    ticks = []
+    ch = mc.MasteringChain.default_chain(target_lufs=target, style="standard")
+    out = ch.process(x.copy(), sr, target_lufs=target, style="standard", progress_callback=lambda p, m: ticks.append((p, m)))
+    assert _err(out, g["chain_out"]) <= 1e-4
+    assert ticks[0] == (5, "dc_offset") and ticks[-1][0] == 98 and len(ticks) == 12
+    # from_config round trip of the default config
+    out2 = mc.MasteringChain.from_config(mc.MasteringChain.default_config(target, "standard")).process(x.copy(), sr)
+    assert np.array_equal(out, out2)
+    # custom: no dynamics, style EQ blended at 50 %, exciter forced on, different order
+    cfg = {"modules": [
+        {"id": "dc_offset", "enabled": True},
+        {"id": "target_curve", "enabled": True, "eq_ms": True},
+        {"id": "dynamics", "enabled": False},
+        {"id": "style_eq", "enabled": True, "style": "edm", "amount": 0.5},
+        {"id": "exciter", "enabled": True, "exciter_db": 0.8, "mode": "warm", "oversample": 1},
+        {"id": "normalize_lufs", "enabled": True, "target_lufs": -16.0},
+        {"id": "imager", "enabled": True, "width": 1.2},
+        {"id": "unknown_module", "enabled": True},
+        {"id": "peak_guard", "enabled": True, "headroom_db": 1.0},
+    ]}
+    got = mc.MasteringChain.from_config(cfg).process(x.copy(), sr)
+    a = oc.remove_dc_offset(x)
+    a = oc.apply_target_curve(a, sr, eq_ms=True)
+    e = oc.apply_style_eq(a, sr, "edm")
+    a = (a * (1.0 - 0.5) + e * 0.5).astype(np.float32)
+    a = oc.apply_harmonic_exciter(a, sr, 0.8)
+    a = oc.normalize_lufs(a, sr, -16.0)
+    a = oc.apply_stereo_imager(a, 1.2)
+    a = oc.remove_intersample_peaks(a, 1.0)
+    ref = np.clip(a, -1, 1).astype(np.float32)
+    assert _err(got, ref) <= 5e-6
+    # second-wave modules fail loudly instead of passing audio through
+    with pytest.raises(NotImplementedError):
+        mc.MasteringChain.from_config({"modules": [{"id": "reverb", "enabled": True}]}).process(x.copy(), sr)
