@@ -470,7 +470,7 @@ int mm_dev_apply_maximizer(mm_ctx* c, const mm_geom* g, const float* in, float* 
     PwArgs A;
     pw_base(&A, in, out, PW_MAXIMIZER);
     fill_dyn(&A.dyn, 6.0, nullptr, 12.0);
-    A.dyn.tp_lim = 3.0e38f;   // maximizer alone: no limiter behind it
+    A.dyn.max_top = (float)std::pow(10.0, -0.3 / 20.0);   // maximizer alone: the ceiling only, no limiter behind it
     return run_pointwise(c, g, A, "apply_maximizer");
 }
 

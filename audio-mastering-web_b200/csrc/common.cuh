@@ -35,21 +35,20 @@ template <int M> struct FiltK {
 // prologue applied to samples as they are loaded
 enum { PRO_NONE = 0, PRO_SUBMUL_F32 = 1, PRO_MUL_F64 = 2 };
 // epilogue of a sweep
-enum { EPI_STORE = 0, EPI_COMBINE = 1, EPI_DYNAMICS = 2, EPI_EXCITER = 3 };
+enum { EPI_STORE = 0, EPI_COMBINE = 1, EPI_DYNAMICS = 2, EPI_EXCITER = 3, EPI_DYNAMICS_GEN = 4 };   // _GEN: upward bands and/or parallel mix
 
 struct DynBand {           // one band of MULTIBAND_CONFIG after host-side preparation
     double thr_db, thr, ratio, lower, upper, slope, max_boost_db;
     float lim, gain;
-    float thr_f, inv_ratio_f, lower_f, upper_f, slope_f;   // float32 copies for the downward knee
+    float s_mid, c_mid, s_hi, c_hi;   // float32 lines of the downward knee: knee segment and above-knee segment
     int mode;              // 0 bypass (ratio == 1 or <= 0), 1 hard knee, 2 soft knee, 3 upward
 };
 struct DynParams {
     DynBand band[4];
-    float max_thr, max_ceil, max_num, max_den, max_k;   // maximizer (pipeline.py:484-492) in float32 terms; max_k = num / den
-    float tp_lim;                                 // TRUE_PEAK_LIMIT_DB hard limit
+    float max_k, max_c, max_top;                  // maximizer line k |s| + c (pipeline.py:484-492) and min(ceil, TRUE_PEAK_LIMIT) cap
     // optional parallel compression folded behind the limiter (v1, pipeline.py:1771-1797)
     const double* par_mix;                        // per-row mix (device) or nullptr
-    float par_thr, par_lower, par_upper, par_slope, par_ratio;
+    float par_slope, par_cmid, par_shi, par_chi;  // knee / above-knee lines of the parallel compressor
 };
 
 template <int M, int NF> struct SweepArgs {

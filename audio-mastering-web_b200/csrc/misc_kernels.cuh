@@ -163,7 +163,7 @@ __global__ void __launch_bounds__(kPwThreads) pointwise_kernel(const PwArgs P) {
                 // apply_maximizer alone (no limiter): tp_lim is set to +inf by the host
                 l = maximize_limit(l, P.dyn); rr = maximize_limit(rr, P.dyn);
             } else if (P.mode == PW_PARALLEL) {
-                l = parallel_compress(l, P.par_mix, P.dyn); rr = parallel_compress(rr, P.par_mix, P.dyn);
+                l = parallel_compress(l, (float)P.par_mix, (float)(1.0 - P.par_mix), P.dyn); rr = parallel_compress(rr, (float)P.par_mix, (float)(1.0 - P.par_mix), P.dyn);
             } else if (P.mode == PW_BLEND) {
                 // BaseModule.process (modules/base.py:44-46): audio * (1 - amount) + processed * amount, float32
                 const size_t o = (size_t)i + c;

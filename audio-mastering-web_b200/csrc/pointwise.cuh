@@ -31,8 +31,9 @@ __device__ __forceinline__ float compress_band_f64(double x, const DynBand& b, d
 // band -> compress -> hard clip at lim_db -> * gain, all as the numpy branch does it
 // (backend/app/pipeline.py:466-474).  The downward knee (ratio >= 1, the default configuration) is one
 // branch-free piecewise-linear map in float32,
-//     o = |y| <= lower ? |y| : (|y| >= upper ? thr + (|y| - thr)/ratio : lower + (|y| - lower) * slope),
-// with lower = +inf for a bypassed band (ratio == 1) and lower = upper = thr for a hard knee.  The band
+//     o = |y| <= lower ? |y| : (|y| >= upper ? thr + (|y| - thr)/ratio : lower + (|y| - lower) * slope)
+// = min(|y|, knee line, above-knee line) (the map is concave); a bypassed band (ratio == 1) uses the
+// identity for all three lines, a hard knee the above-knee line twice.  The band
 // itself is float32 here (HBM storage); the reference's float64 knee followed by its float32 cast differs
 // from this by at most one float32 ulp of the band sample.  The upward branch (ratio < 1) needs
 // log10/pow, stays in float64 and out of line so that the hot loop stays small in the instruction cache.
@@ -41,43 +42,36 @@ __device__ __noinline__ float band_chain_upward(float y, const DynBand& b) {
     const float c = compress_band_f64((double)y, b, &raw);
     return __fmul_rn(fminf(fmaxf(c, -b.lim), b.lim), b.gain);
 }
+// downward knee only (modes 0..2): branch free.  A downward knee is concave piecewise linear, i.e. the
+// minimum of its three lines (identity, knee segment, above-knee segment).
 __device__ __forceinline__ float band_chain(float y, const DynBand& b) {
-    if (b.mode == 3) return band_chain_upward(y, b);
     const float ax = fabsf(y);
-    const float hi = fmaf(ax - b.thr_f, b.inv_ratio_f, b.thr_f);
-    const float mid = fmaf(ax - b.lower_f, b.slope_f, b.lower_f);
-    float o = ax <= b.lower_f ? ax : (ax >= b.upper_f ? hi : mid);
+    float o = fminf(ax, fminf(fmaf(ax, b.s_mid, b.c_mid), fmaf(ax, b.s_hi, b.c_hi)));
     o = fminf(fmaxf(o, 0.f), b.lim);        // clip(+-lim) of sign * o
     return __fmul_rn(copysignf(o, y), b.gain);
 }
-
-// apply_maximizer + hard limiter at TRUE_PEAK_LIMIT_DB on float32 (pipeline.py:484-492, :636)
-__device__ __forceinline__ float maximize_limit(float s, const DynParams& d) {
-    const float ax = fabsf(s);
-    const float sgn = (s > 0.f) ? 1.f : ((s < 0.f) ? -1.f : 0.f);
-    float o = ax;
-    if (!(ax <= d.max_thr)) {
-        o = fmaf(__fsub_rn(ax, d.max_thr), d.max_k, d.max_thr);      // thr + (|x| - thr) * (ceil - thr) / (1 - thr)
-    }
-    o = fminf(o, d.max_ceil);
-    const float v = __fmul_rn(sgn, o);
-    return fminf(fmaxf(v, -d.tp_lim), d.tp_lim);
+// any mode, including the upward branch (ratio < 1)
+__device__ __forceinline__ float band_chain_gen(float y, const DynBand& b) {
+    if (b.mode == 3) return band_chain_upward(y, b);
+    return band_chain(y, b);
 }
 
-// apply_parallel_compression on float32 (pipeline.py:1771-1797; soft knee 6 dB, float32 arithmetic)
-__device__ __forceinline__ float parallel_compress(float x, double mixd, const DynParams& d) {
-    const float mix = (float)mixd;
-    const float one_minus = (float)(1.0 - mixd);          // python float (1.0 - mix), then weak-cast to float32
+// apply_maximizer + hard limiter at TRUE_PEAK_LIMIT_DB on float32 (pipeline.py:484-492, :636):
+//   |s| <= thr ? |s| : thr + (|s| - thr) * (ceil - thr) / (1 - thr), then min(ceil), sign, clip(+-tp_lim)
+// = copysign(min(|s|, line(|s|), ceil, tp_lim), s): concave again (the line has slope < 1).
+__device__ __forceinline__ float maximize_limit(float s, const DynParams& d) {
+    const float ax = fabsf(s);
+    const float o = fminf(fminf(ax, fmaf(ax, d.max_k, d.max_c)), d.max_top);
+    return copysignf(o, s);
+}
+
+// apply_parallel_compression on float32 (pipeline.py:1771-1797; soft knee 6 dB): x (1 - mix) + comp mix, clip +-1
+__device__ __forceinline__ float parallel_compress(float x, float mix, float one_minus, const DynParams& d) {
     const float ax = fabsf(x);
-    const float sgn = (x > 0.f) ? 1.f : ((x < 0.f) ? -1.f : 0.f);
-    float o;
-    if (ax <= d.par_lower) o = ax;
-    else if (ax >= d.par_upper) o = __fadd_rn(d.par_thr, __fdiv_rn(__fsub_rn(ax, d.par_thr), d.par_ratio));
-    else o = __fadd_rn(d.par_lower, __fmul_rn(__fsub_rn(ax, d.par_lower), d.par_slope));
+    float o = fminf(ax, fminf(fmaf(ax, d.par_slope, d.par_cmid), fmaf(ax, d.par_shi, d.par_chi)));
     o = fmaxf(o, 0.f);
-    const float comp = __fmul_rn(sgn, o);
-    const float dry = __fmul_rn(x, one_minus);
-    const float out = __fadd_rn(dry, __fmul_rn(comp, mix));
+    const float comp = copysignf(o, x);
+    const float out = __fadd_rn(__fmul_rn(x, one_minus), __fmul_rn(comp, mix));
     return fminf(fmaxf(out, -1.f), 1.f);
 }
 

@@ -76,11 +76,28 @@ static int launch_sweep2(mm_ctx* c, SweepArgs<M, NF>& A, int whalo, const char* 
     const long long items = (long long)A.rows * PP.nseg;
     const unsigned grid = (unsigned)std::min<long long>(items, capacity);
     PP.a = A;
+    PP.dbg = nullptr;
+    static long long* dbg_dev = nullptr;
+    const bool dbg = getenv("MM_PHASES") != nullptr;
+    if (dbg) {
+        if (!dbg_dev) MM_CUDA(cudaMalloc(&dbg_dev, 8 * sizeof(long long)));
+        MM_CUDA(cudaMemsetAsync(dbg_dev, 0, 8 * sizeof(long long), c->stream));
+        PP.dbg = dbg_dev;
+    }
     {
         KernelScope ks(c, name);
         kern<<<grid, kT, smem, c->stream>>>(PP);
     }
     MM_CUDA(cudaGetLastError());
+    if (dbg) {
+        long long h[8];
+        MM_CUDA(cudaMemcpyAsync(h, dbg_dev, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+        MM_CUDA(cudaStreamSynchronize(c->stream));
+        const int tiles = PP.seglen + whalo;
+        fprintf(stderr, "[phases] %-28s seg %d tiles(+%d halo) x%d items/cta~%lld | wait(A) %lld load+B %lld pass1 %lld scan %lld barC %lld horner+pass2 %lld barE %lld epilogue %lld (cycles per tile, CTA 0)\n",
+                name, PP.seglen, whalo, PP.nseg, (long long)((items + grid - 1) / grid), h[0] / tiles, h[1] / tiles, h[2] / tiles, h[3] / tiles, h[4] / tiles,
+                h[5] / tiles, h[6] / tiles, h[7] / tiles);
+    }
     return 0;
 }
 
@@ -176,6 +193,7 @@ int sweep_bwd(mm_ctx* c, const mm_geom* g, int nf, const FilterPlan* const* plan
     if (m == 2 && nf == 2 && epi.mode == EPI_STORE) MM_BWD(2, 2, EPI_STORE, 0, 1, "_store")
     if (m == 2 && nf == 2 && epi.mode == EPI_COMBINE && naux == 1) MM_BWD(2, 2, EPI_COMBINE, 1, 1, "_combine")
     if (m == 2 && nf == 2 && epi.mode == EPI_DYNAMICS && naux == 2) MM_BWD(2, 2, EPI_DYNAMICS, 2, 1, "_dynamics")
+    if (m == 2 && nf == 2 && epi.mode == EPI_DYNAMICS_GEN && naux == 2) MM_BWD(2, 2, EPI_DYNAMICS_GEN, 2, 1, "_dynamics_gen")
     if (m == 2 && nf == 4 && epi.mode == EPI_COMBINE && naux == 1) {
         SweepArgs<2, 4> A;
         fill_common<2, 4>(A, g, plans, in, nf, out, nout, epi.auxp, epi, pad);
@@ -331,23 +349,22 @@ void fill_dyn(DynParams* d, double knee_db, const double* band_ratios, double ma
         b.slope = (b.upper > b.lower) ? (b.thr + (b.upper - b.thr) / ratio - b.lower) / (b.upper - b.lower) : 1.0;
         b.lim = (float)std::pow(10.0, lim_db / 20.0);
         b.gain = (float)gain;
-        b.thr_f = (float)b.thr;
-        b.inv_ratio_f = ratio > 0.0 ? (float)(1.0 / ratio) : 1.f;
-        b.lower_f = (float)b.lower;
-        b.upper_f = (float)b.upper;
-        b.slope_f = (float)b.slope;
-        if (ratio <= 0.0 || ratio == 1.0) { b.mode = 0; b.lower_f = __builtin_inff(); b.upper_f = __builtin_inff(); }
+        // lines of the concave downward knee (band_chain): identity by default
+        b.s_mid = 1.f; b.c_mid = 0.f; b.s_hi = 1.f; b.c_hi = 0.f;
+        if (ratio <= 0.0 || ratio == 1.0) b.mode = 0;
         else if (ratio < 1.0) b.mode = 3;
-        else if (knee_db < 0.5) { b.mode = 1; b.lower_f = b.thr_f; b.upper_f = b.thr_f; }
-        else b.mode = 2;
+        else {
+            b.s_hi = (float)(1.0 / ratio);
+            b.c_hi = (float)(b.thr * (1.0 - 1.0 / ratio));
+            if (knee_db < 0.5) { b.mode = 1; b.s_mid = b.s_hi; b.c_mid = b.c_hi; }
+            else { b.mode = 2; b.s_mid = (float)b.slope; b.c_mid = (float)(b.lower * (1.0 - b.slope)); }
+        }
     }
     const double thr = std::pow(10.0, -2.5 / 20.0), ceil_ = std::pow(10.0, -0.3 / 20.0);
-    d->max_thr = (float)thr;
-    d->max_ceil = (float)ceil_;
-    d->max_num = (float)(ceil_ - thr);
-    d->max_den = (float)(1.0 - thr);
-    d->max_k = (float)((ceil_ - thr) / (1.0 - thr));
-    d->tp_lim = (float)std::pow(10.0, -1.5 / 20.0);
+    const double k = (ceil_ - thr) / (1.0 - thr);
+    d->max_k = (float)k;
+    d->max_c = (float)(thr * (1.0 - k));
+    d->max_top = (float)std::min(ceil_, std::pow(10.0, -1.5 / 20.0));   // min(ceil) then clip(+-TRUE_PEAK_LIMIT_DB)
     d->par_mix = nullptr;
     fill_parallel(d, 8.0, -20.0);
 }
@@ -355,11 +372,11 @@ void fill_dyn(DynParams* d, double knee_db, const double* band_ratios, double ma
 void fill_parallel(DynParams* d, double ratio, double threshold_db) {
     const double thr = std::pow(10.0, threshold_db / 20.0);
     const double lower = thr * std::pow(10.0, -6.0 / 20.0), upper = thr * std::pow(10.0, 6.0 / 20.0);
-    d->par_thr = (float)thr;
-    d->par_lower = (float)lower;
-    d->par_upper = (float)upper;
-    d->par_slope = (float)((thr + (upper - thr) / ratio - lower) / (upper - lower));
-    d->par_ratio = (float)ratio;
+    const double slope = (thr + (upper - thr) / ratio - lower) / (upper - lower);
+    d->par_slope = (float)slope;
+    d->par_cmid = (float)(lower * (1.0 - slope));
+    d->par_shi = (float)(1.0 / ratio);
+    d->par_chi = (float)(thr * (1.0 - 1.0 / ratio));
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -457,8 +474,10 @@ int st_dynamics(mm_ctx* c, const mm_geom* g, const float* in, float* out, double
         DynParams d;
         fill_dyn(&d, knee_db, band_ratios, max_upward_boost_db);
         d.par_mix = par_mix_rows;
+        bool general = par_mix_rows != nullptr;
+        for (int i = 0; i < 4; ++i) general |= d.band[i].mode == 3;
         Epi e;
-        e.mode = EPI_DYNAMICS;
+        e.mode = general ? EPI_DYNAMICS_GEN : EPI_DYNAMICS;
         e.aux0 = B.T[1];
         e.aux1 = B.T[4];
         e.dyn = &d;

@@ -67,6 +67,7 @@ template <int M, int NF> struct Sweep2Args {
     int seglen;           // live tiles per segment
     int nseg;             // segments per row
     int whalo;            // halo tiles read before a segment (max over the sweep's sections)
+    long long* dbg;       // phase clocks of CTA 0 / thread 0 (tuning; null in production)
 };
 
 template <int M, int NF, int NIN, int DIR, int EPI, int NAUX, int ST>
@@ -78,6 +79,9 @@ struct Sweep2Cfg {
     static constexpr size_t kAuxOff = kExtraOff + kExtra * kTileBytes;
     static constexpr size_t kTabOff = kAuxOff + NAUX * kTileBytes;
     static constexpr size_t kBytes = kTabOff + NF * sizeof(SmemTab<M>);
+    // CTAs per SM the shared-memory footprint allows (227 KB usable): the register allocator is held to it
+    static constexpr int kFit = (int)((227u * 1024u) / (kBytes + 1024u));
+    static constexpr int kMinBlocks = kFit < 1 ? 1 : (kFit > 6 ? 6 : kFit);
 };
 
 template <int M, int NF> struct Scratch2 {
@@ -93,7 +97,7 @@ __device__ __forceinline__ float pro1(int mode, float x, float subf, float mulf,
 }
 
 template <int M, int NF, int NIN, int DIR, int EPI, int NAUX, int ST>
-__global__ void __launch_bounds__(kT) sweep2_kernel(const __grid_constant__ Sweep2Args<M, NF> PP) {
+__global__ void __launch_bounds__(kT, Sweep2Cfg<M, NF, NIN, DIR, EPI, NAUX, ST>::kMinBlocks) sweep2_kernel(const __grid_constant__ Sweep2Args<M, NF> PP) {
     typedef Sweep2Cfg<M, NF, NIN, DIR, EPI, NAUX, ST> Cfg;
     const SweepArgs<M, NF>& P = PP.a;
     extern __shared__ __align__(128) unsigned char smraw[];
@@ -191,17 +195,39 @@ __global__ void __launch_bounds__(kT) sweep2_kernel(const __grid_constant__ Swee
     };
     auto issue_aux = [&](int row, long long lo) {
         if (NAUX == 0) return;
-        if (!fast_out(lo)) return;     // edge tiles read aux straight from global in the epilogue
         const size_t rowoff = (size_t)row * (size_t)P.stride;
+        if (fast_out(lo)) {
 #pragma unroll
-        for (int s = 0; s < NAUX; ++s) {
-            const float* src = P.aux[s] + rowoff + lo + 4 * tid;
-            float* dst = auxs + (size_t)s * kL + 4 * swz(tid);
+            for (int s = 0; s < NAUX; ++s) {
+                const float* src = P.aux[s] + rowoff + lo + 4 * tid;
+                float* dst = auxs + (size_t)s * kL + 4 * swz(tid);
 #pragma unroll
-            for (int r = 0; r < kTileVecs / kT; ++r) cp_async16(dst + 4 * kT * r, src + 4 * kT * r);
+                for (int r = 0; r < kTileVecs / kT; ++r) cp_async16(dst + 4 * kT * r, src + 4 * kT * r);
+            }
+        } else {
+            // edge tile: synchronous, zeros outside the x-domain
+#pragma unroll 1
+            for (int s = 0; s < NAUX; ++s) {
+                const float* src = P.aux[s] + rowoff;
+#pragma unroll 1
+                for (int r = 0; r < kTileVecs / kT; ++r) {
+                    const int v = tid + kT * r;
+                    const long long q = lo + 4 * v;
+                    float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                    for (int c = 0; c < 4; ++c)
+                        if (q + c >= st_lo && q + c <= st_hi) setcomp4(val, c, src[q + c]);
+                    *reinterpret_cast<float4*>(auxs + (size_t)s * kL + 4 * swz(v)) = val;
+                }
+            }
         }
     };
 
+    long long t_ph[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    long long t_last = 0;
+    const bool dbg_on = PP.dbg != nullptr && blockIdx.x == 0 && tid == 0;
+#define MM_TICK(k) do { if (dbg_on) { const long long _t = clock64(); t_ph[k] += _t - t_last; t_last = _t; } } while (0)
+    if (dbg_on) t_last = clock64();
     // ---- segment loop --------------------------------------------------------------------------------
     const int items = P.rows * PP.nseg;
 #pragma unroll 1
@@ -222,6 +248,7 @@ __global__ void __launch_bounds__(kT) sweep2_kernel(const __grid_constant__ Swee
     for (int tile = t_first; tile < t_end; ++tile) {
         const bool live = tile >= t_live;
         __syncthreads();                               // (A) previous tile fully stored; carry visible
+        MM_TICK(0);
         const long long tile_lo = tile_origin(tile);
         if (live) issue_aux(row, tile_lo);
         cp_async_commit();                             // group: aux(tile)
@@ -233,6 +260,7 @@ __global__ void __launch_bounds__(kT) sweep2_kernel(const __grid_constant__ Swee
             cp_async_wait<1>();
         }
         __syncthreads();                               // (B) inputs(tile) visible to all threads
+        MM_TICK(1);
 
         float* tin = ring + (size_t)slot * NIN * kL;
         const bool in_fast = fast_in(tile_lo);
@@ -305,16 +333,21 @@ __global__ void __launch_bounds__(kT) sweep2_kernel(const __grid_constant__ Swee
             }
         }
 
-        // ---- warp scan ----------------------------------------------------------------------------------
+        MM_TICK(2);
+        // ---- warp scan: branch-free (lanes below the stride shuffle in zeros), sections interleaved --------
 #pragma unroll
         for (int d = 0; d < 5; ++d) {
+            const bool act = lane >= (1 << d);
+            double pe[NF][M];
 #pragma unroll
-            for (int f = 0; f < NF; ++f) {
-                double pe[M];
+            for (int f = 0; f < NF; ++f)
 #pragma unroll
-                for (int i = 0; i < M; ++i) pe[i] = shfl_up_d(E[f][i], 1 << d);
-                if (lane >= (1 << d)) matvec_acc_s<M>(tab[f].Pw[d], pe, E[f]);
-            }
+                for (int i = 0; i < M; ++i) {
+                    const double v = shfl_up_d(E[f][i], 1 << d);
+                    pe[f][i] = act ? v : 0.0;
+                }
+#pragma unroll
+            for (int f = 0; f < NF; ++f) matvec_acc_s<M>(tab[f].Pw[d], pe[f], E[f]);
         }
         if (lane == 31) {
 #pragma unroll
@@ -322,20 +355,29 @@ __global__ void __launch_bounds__(kT) sweep2_kernel(const __grid_constant__ Swee
 #pragma unroll
                 for (int i = 0; i < M; ++i) sh.tot[f][warp][i] = E[f][i];
         }
-        __syncthreads();                               // (C)
+        // the x-domain aux streams of a recombining epilogue are consumed inside pass 2
+        if (NAUX > 0) { if (ST > 1) cp_async_wait<1>(); else cp_async_wait<0>(); }
+        MM_TICK(3);
+        __syncthreads();                               // (C) warp totals (and aux tiles) visible
+        MM_TICK(4);
 
         double base[NF][M];
 #pragma unroll
-        for (int f = 0; f < NF; ++f) {
+        for (int f = 0; f < NF; ++f)
 #pragma unroll
             for (int i = 0; i < M; ++i) base[f][i] = 0.0;
-            for (int v = 0; v < warp; ++v) {
-                double nb[M];
 #pragma unroll
-                for (int i = 0; i < M; ++i) nb[i] = sh.tot[f][v][i];
-                matvec_acc_s<M>(tab[f].Qpow[1], base[f], nb);
+        for (int v = 0; v < kNW - 1; ++v) {
+            if (v < warp) {                            // warp-uniform
 #pragma unroll
-                for (int i = 0; i < M; ++i) base[f][i] = nb[i];
+                for (int f = 0; f < NF; ++f) {
+                    double nb[M];
+#pragma unroll
+                    for (int i = 0; i < M; ++i) nb[i] = sh.tot[f][v][i];
+                    matvec_acc_s<M>(tab[f].Qpow[1], base[f], nb);
+#pragma unroll
+                    for (int i = 0; i < M; ++i) base[f][i] = nb[i];
+                }
             }
         }
 
@@ -378,33 +420,93 @@ __global__ void __launch_bounds__(kT) sweep2_kernel(const __grid_constant__ Swee
             matvec_acc_s<M>(tab[f].Plane[lane], base[f], z[f]);
         }
 
-        // ---- pass 2 ------------------------------------------------------------------------------------------
+        // ---- pass 2 (+ the recombining epilogue, evaluated on the float64 section outputs) --------------------
+        constexpr int NOUT = (EPI == EPI_STORE) ? NF : 1;
         float* tout[NF];
 #pragma unroll
         for (int f = 0; f < NF; ++f) tout[f] = (f < NIN) ? (tin + (size_t)f * kL) : (extra + (size_t)(f - NIN) * kL);
-        if (!inj_thread) {
+        const bool out_fast = fast_out(tile_lo);
+        float aux_subf = 0.f, aux_mulf = 1.f;
+        double aux_muld = 1.0;
+        if (EPI != EPI_STORE && P.aux_pro && P.pro_mode != PRO_NONE) {
+            if (P.pro_sub) aux_subf = (float)__ldg(P.pro_sub + row);
+            if (P.pro_mul) { aux_muld = __ldg(P.pro_mul + row); aux_mulf = (float)aux_muld; }
+        }
+        float par_mix = 0.f, par_one_minus = 1.f;
+        if (EPI == EPI_DYNAMICS_GEN && P.dyn.par_mix) {
+            const double mixd = __ldg(P.dyn.par_mix + row);
+            par_mix = (float)mixd;
+            par_one_minus = (float)(1.0 - mixd);      // Python float (1.0 - mix), then weak-cast to float32
+        }
+        float pk = 0.f;
+        // one output element of a recombining epilogue; y[] are this sample's section outputs in float64
+        auto epi_value = [&](float xa_raw, float a1c, const double (&y)[NF]) -> float {
+            float xa = xa_raw;
+            if (P.aux_pro) xa = pro1(P.pro_mode, xa, aux_subf, aux_mulf, aux_muld);
+            if (EPI == EPI_COMBINE) {
+                // pipeline.py:273 / :603-606 / :1431: float64 recombination, one cast to float32
+                double acc = P.wc * (double)xa;
 #pragma unroll
+                for (int f = 0; f < NF; ++f) acc = fma(P.w[f], y[f], acc);
+                return (float)(acc * P.trim);
+            } else if (EPI == EPI_EXCITER) {
+                const float hf = (float)y[0];
+                const float sat = exciter_sat(hf, P.exc_mode, (float)P.exc_k);
+                return (float)fma((double)(sat - hf), P.exc_gain * 0.25, (double)xa);
+            } else if (EPI == EPI_DYNAMICS) {   // aux0 = band 1, y0 = band 2, y1 = band 3, aux1 = band 4; downward knees only
+                float sacc = band_chain(xa, P.dyn.band[0]);
+                sacc = __fadd_rn(sacc, band_chain((float)y[0], P.dyn.band[1]));
+                sacc = __fadd_rn(sacc, band_chain((float)y[NF > 1 ? 1 : 0], P.dyn.band[2]));
+                sacc = __fadd_rn(sacc, band_chain(a1c, P.dyn.band[3]));
+                return maximize_limit(sacc, P.dyn);
+            } else {                             // EPI_DYNAMICS_GEN: upward bands and/or the v1 parallel compressor
+                float sacc = band_chain_gen(xa, P.dyn.band[0]);
+                sacc = __fadd_rn(sacc, band_chain_gen((float)y[0], P.dyn.band[1]));
+                sacc = __fadd_rn(sacc, band_chain_gen((float)y[NF > 1 ? 1 : 0], P.dyn.band[2]));
+                sacc = __fadd_rn(sacc, band_chain_gen(a1c, P.dyn.band[3]));
+                float res = maximize_limit(sacc, P.dyn);
+                if (par_mix >= 0.01f) res = parallel_compress(res, par_mix, par_one_minus, P.dyn);
+                return res;
+            }
+        };
+        if (!inj_thread) {
+            // a recombining epilogue keeps the loop rolled (2 float4 groups in flight): fully unrolled, the
+            // hoisted aux / input loads cost ~100 extra registers and halve the occupancy
+#pragma unroll (EPI == EPI_STORE ? kS / 4 : 2)
             for (int u = 0; u < kS / 4; ++u) {
                 const int uu = (DIR > 0) ? u : (kS / 4 - 1 - u);
                 const int off = cbase + ((4 * uu) ^ cx);
                 float4 xv[NIN];
 #pragma unroll
                 for (int s = 0; s < NIN; ++s) xv[s] = *reinterpret_cast<const float4*>(tin + (size_t)s * kL + off);
-                float4 yv[NF];
+                float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;
+                if (EPI != EPI_STORE && NAUX > 0) a0 = *reinterpret_cast<const float4*>(auxs + off);
+                if (EPI != EPI_STORE && NAUX > 1) a1 = *reinterpret_cast<const float4*>(auxs + kL + off);
+                float4 yv[NOUT];
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
                     const int cc = (DIR > 0) ? c : (3 - c);
                     double xd[NIN];
 #pragma unroll
                     for (int s = 0; s < NIN; ++s) xd[s] = f2d_bits(comp4(xv[s], cc));
+                    double y[NF];
 #pragma unroll
-                    for (int f = 0; f < NF; ++f) {
-                        const double y = df2t_step<M>(P.f[f], xd[NIN == 1 ? 0 : f], z[f]);
-                        setcomp4(yv[f], cc, (float)y);
+                    for (int f = 0; f < NF; ++f) y[f] = df2t_step<M>(P.f[f], xd[NIN == 1 ? 0 : f], z[f]);
+                    if (EPI == EPI_STORE) {
+#pragma unroll
+                        for (int f = 0; f < NF; ++f) setcomp4(yv[f < NOUT ? f : 0], cc, (float)y[f]);
+                    } else {
+                        const float res = epi_value(comp4(a0, cc), comp4(a1, cc), y);
+                        setcomp4(yv[0], cc, res);
+                        if (out_fast) pk = fmaxf(pk, fabsf(res));
+                        else {
+                            const long long q = tile_lo + cbase + 4 * uu + cc;
+                            if (q >= st_lo && q <= st_hi) pk = fmaxf(pk, fabsf(res));
+                        }
                     }
                 }
 #pragma unroll
-                for (int f = 0; f < NF; ++f) *reinterpret_cast<float4*>(tout[f] + off) = yv[f];
+                for (int f = 0; f < NOUT; ++f) *reinterpret_cast<float4*>(tout[f] + off) = yv[f];
             }
         } else {
             // the one thread of tile 0 that starts from zi * x_first after `d0` dead samples
@@ -421,84 +523,35 @@ __global__ void __launch_bounds__(kT) sweep2_kernel(const __grid_constant__ Swee
 #pragma unroll
                         for (int i = 0; i < M; ++i) z[f][i] = __ldg(P.tab[f] + Tab<M>::Zi + i) * (double)xs[NIN == 1 ? 0 : f];
                 }
+                double y[NF];
 #pragma unroll
-                for (int f = 0; f < NF; ++f) {
-                    const double y = df2t_step<M>(P.f[f], (double)xs[NIN == 1 ? 0 : f], z[f]);
-                    tout[f][off] = (float)y;
+                for (int f = 0; f < NF; ++f) y[f] = df2t_step<M>(P.f[f], (double)xs[NIN == 1 ? 0 : f], z[f]);
+                if (EPI == EPI_STORE) {
+#pragma unroll
+                    for (int f = 0; f < NF; ++f) tout[f][off] = (float)y[f];
+                } else {
+                    const float res = epi_value(NAUX > 0 ? auxs[off] : 0.f, NAUX > 1 ? auxs[kL + off] : 0.f, y);
+                    tout[0][off] = res;
+                    const long long q = tile_lo + cbase + mi;
+                    if (q >= st_lo && q <= st_hi) pk = fmaxf(pk, fabsf(res));
                 }
             }
         }
-        if (NAUX > 0) { if (ST > 1) cp_async_wait<1>(); else cp_async_wait<0>(); }   // aux(cur) landed
-        __syncthreads();                               // (E) results (and aux) visible
+        MM_TICK(5);
+        __syncthreads();                               // (E) results visible
+        MM_TICK(6);
 
-        // ---- epilogue / store -----------------------------------------------------------------------------------
-        const bool out_fast = fast_out(tile_lo);
-        float aux_subf = 0.f, aux_mulf = 1.f;
-        double aux_muld = 1.0;
-        if (EPI != EPI_STORE && P.aux_pro && P.pro_mode != PRO_NONE) {
-            if (P.pro_sub) aux_subf = (float)__ldg(P.pro_sub + row);
-            if (P.pro_mul) { aux_muld = __ldg(P.pro_mul + row); aux_mulf = (float)aux_muld; }
-        }
-        float pk = 0.f;
-        // one output element of a recombining epilogue (float64 where the reference's numpy arithmetic is)
-        auto epi_value = [&](float xa_raw, float a1c, const float (&yc)[NF]) -> float {
-            float xa = xa_raw;
-            if (P.aux_pro) xa = pro1(P.pro_mode, xa, aux_subf, aux_mulf, aux_muld);
-            if (EPI == EPI_COMBINE) {
-                double acc = P.wc * f2d_bits(xa);
-#pragma unroll
-                for (int f = 0; f < NF; ++f) acc = fma(P.w[f], f2d_bits(yc[f]), acc);
-                return (float)(acc * P.trim);
-            } else if (EPI == EPI_EXCITER) {
-                const float hf = yc[0];
-                const float sat = exciter_sat(hf, P.exc_mode, (float)P.exc_k);
-                return (float)fma((double)(sat - hf), P.exc_gain * 0.25, (double)xa);
-            } else {   // EPI_DYNAMICS: aux0 = band 1, y0 = band 2, y1 = band 3, aux1 = band 4
-                float sacc = band_chain(xa, P.dyn.band[0]);
-                sacc = __fadd_rn(sacc, band_chain(yc[0], P.dyn.band[1]));
-                sacc = __fadd_rn(sacc, band_chain(yc[NF > 1 ? 1 : 0], P.dyn.band[2]));
-                sacc = __fadd_rn(sacc, band_chain(a1c, P.dyn.band[3]));
-                float res = maximize_limit(sacc, P.dyn);
-                if (P.dyn.par_mix) {
-                    const double mix = __ldg(P.dyn.par_mix + row);
-                    if (mix >= 0.01) res = parallel_compress(res, mix, P.dyn);
-                }
-                return res;
-            }
-        };
+        // ---- store: NOUT finished float32 streams, coalesced -----------------------------------------------------
         if (out_fast) {
             // interior tile: every vector is complete; base + immediate addressing (swz(tid + kT r) = swz(tid) + kT r)
             const int so0 = 4 * swz(tid);
             const size_t go0 = rowoff + (size_t)tile_lo + 4 * tid;
-            if (EPI == EPI_STORE) {
 #pragma unroll
-                for (int r = 0; r < kTileVecs / kT; ++r) {
+            for (int r = 0; r < kTileVecs / kT; ++r) {
 #pragma unroll
-                    for (int f = 0; f < NF; ++f)
-                        __stcs(reinterpret_cast<float4*>(P.out[f] + go0 + 4 * kT * r),
-                               *reinterpret_cast<const float4*>(tout[f] + so0 + 4 * kT * r));
-                }
-            } else {
-                float* dst = P.out[0] + go0;
-#pragma unroll 4
-                for (int r = 0; r < kTileVecs / kT; ++r) {
-                    float4 y[NF];
-#pragma unroll
-                    for (int f = 0; f < NF; ++f) y[f] = *reinterpret_cast<const float4*>(tout[f] + so0 + 4 * kT * r);
-                    float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0, o;
-                    if (NAUX > 0) a0 = *reinterpret_cast<const float4*>(auxs + so0 + 4 * kT * r);
-                    if (NAUX > 1) a1 = *reinterpret_cast<const float4*>(auxs + kL + so0 + 4 * kT * r);
-#pragma unroll
-                    for (int c = 0; c < 4; ++c) {
-                        float yc[NF];
-#pragma unroll
-                        for (int f = 0; f < NF; ++f) yc[f] = comp4(y[f], c);
-                        const float res = epi_value(comp4(a0, c), comp4(a1, c), yc);
-                        setcomp4(o, c, res);
-                        pk = fmaxf(pk, fabsf(res));
-                    }
-                    __stcs(reinterpret_cast<float4*>(dst + 4 * kT * r), o);
-                }
+                for (int f = 0; f < NOUT; ++f)
+                    __stcs(reinterpret_cast<float4*>(P.out[f] + go0 + 4 * kT * r),
+                           *reinterpret_cast<const float4*>(tout[f] + so0 + 4 * kT * r));
             }
         } else {
 #pragma unroll 1
@@ -507,31 +560,13 @@ __global__ void __launch_bounds__(kT) sweep2_kernel(const __grid_constant__ Swee
                 const long long q = tile_lo + 4 * v;
                 if (q + 3 < st_lo || q > st_hi) continue;
                 const int so = 4 * swz(v);
-                float4 y[NF];
 #pragma unroll
-                for (int f = 0; f < NF; ++f) y[f] = *reinterpret_cast<const float4*>(tout[f] + so);
-                if (EPI == EPI_STORE) {
+                for (int f = 0; f < NOUT; ++f) {
+                    const float4 yv = *reinterpret_cast<const float4*>(tout[f] + so);
+                    float* dst = P.out[f] + rowoff;
 #pragma unroll
-                    for (int f = 0; f < NF; ++f) {
-                        float* dst = P.out[f] + rowoff;
-#pragma unroll
-                        for (int c = 0; c < 4; ++c)
-                            if (q + c >= st_lo && q + c <= st_hi) dst[q + c] = comp4(y[f], c);
-                    }
-                } else {
-                    const float* x0 = (NAUX > 0) ? P.aux[0] + rowoff : nullptr;
-                    const float* x1 = (NAUX > 1) ? P.aux[1] + rowoff : nullptr;
-                    float* dst = P.out[0] + rowoff;
-#pragma unroll
-                    for (int c = 0; c < 4; ++c) {
-                        if (q + c < st_lo || q + c > st_hi) continue;
-                        float yc[NF];
-#pragma unroll
-                        for (int f = 0; f < NF; ++f) yc[f] = comp4(y[f], c);
-                        const float res = epi_value(NAUX > 0 ? x0[q + c] : 0.f, NAUX > 1 ? x1[q + c] : 0.f, yc);
-                        pk = fmaxf(pk, fabsf(res));
-                        dst[q + c] = res;
-                    }
+                    for (int c = 0; c < 4; ++c)
+                        if (q + c >= st_lo && q + c <= st_hi) dst[q + c] = comp4(yv, c);
                 }
             }
         }
@@ -541,6 +576,7 @@ __global__ void __launch_bounds__(kT) sweep2_kernel(const __grid_constant__ Swee
             if (lane == 0 && pk > 0.f) atomicMax(reinterpret_cast<int*>(P.peak + row / P.channels), __float_as_int(pk));
         }
 
+        MM_TICK(7);
         if (ST > 1) slot ^= 1;
         else {
             __syncthreads();                           // single stage: everyone done with the buffer
@@ -550,6 +586,11 @@ __global__ void __launch_bounds__(kT) sweep2_kernel(const __grid_constant__ Swee
     }   // tiles
     cp_async_wait<0>();
     }   // items
+    if (dbg_on) {
+        MM_TICK(7);
+        for (int k = 0; k < 8; ++k) PP.dbg[k] = t_ph[k];
+    }
+#undef MM_TICK
 }
 
 }  // namespace mm
