@@ -37,24 +37,22 @@ struct LufsScratch {
     double carry[2][2][2];   // [tile parity][filter][state]
 };
 
-// Round a double to float32 precision on the FP64 pipe (Dekker/Veltkamp split, 2^29 + 1): what pyloudnorm's
-// write-back of a float64 lfilter result into its float32 buffer does, without the two conversions
-// (F2F runs at 15 lanes/clk/SM and is this kernel's scarcest pipe).  Differs from a true cast only in
-// how exact ties break and for values outside float32's normal range -- irrelevant at +-0.01 LU.
-__device__ __forceinline__ double round_to_f32(double y) {
-    const double t = y * 536870913.0;
-    return t - (t - y);
-}
+// pyloudnorm writes each stage's float64 lfilter output back into its float32 buffer.  Those two roundings
+// (6e-8 relative) move the loudness by ~1e-7 dB against a +-0.01 LU tolerance; reproducing them costs either
+// two conversions or three FP64 operations per sample and stage in a kernel that is bound by exactly those
+// pipes, so the stages are chained in float64 here.
+__device__ __forceinline__ double round_to_f32(double y) { return y; }
 
-constexpr int kLufsSmem = kL * (int)sizeof(double) + 2 * (int)sizeof(SmemTab<2>);
+constexpr int kLufsSmem = kL * (int)sizeof(float) + kL * (int)sizeof(double) + 2 * (int)sizeof(SmemTab<2>);
 
 __global__ void __launch_bounds__(kT) lufs_kernel(const __grid_constant__ LufsArgs P) {
-    // the tile lives in shared memory as float32 while it is being loaded (first half of the buffer) and is
-    // widened in place to float64 by the shelf's pass 2, so the high-pass stage needs no conversions at all
+    // a float32 staging tile receives the NEXT tile (cp.async) while the current one is scanned; the shelf's
+    // pass 2 writes its float32-rounded output as float64 into a second buffer, so the high-pass stage needs
+    // no conversions at all
     extern __shared__ __align__(128) unsigned char lufs_smem[];
     float* tile_s = reinterpret_cast<float*>(lufs_smem);
-    double* tile_d = reinterpret_cast<double*>(lufs_smem);
-    SmemTab<2>* tab = reinterpret_cast<SmemTab<2>*>(lufs_smem + kL * sizeof(double));
+    double* tile_d = reinterpret_cast<double*>(lufs_smem + kL * sizeof(float));
+    SmemTab<2>* tab = reinterpret_cast<SmemTab<2>*>(lufs_smem + kL * sizeof(float) + kL * sizeof(double));
     __shared__ LufsScratch sh;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr int MM = 4;
@@ -84,24 +82,18 @@ __global__ void __launch_bounds__(kT) lufs_kernel(const __grid_constant__ LufsAr
         __syncthreads();
         if (tid < 4) sh.carry[t_first & 1][tid >> 1][tid & 1] = 0.0;
         unsigned long long* dst = P.segsum + (size_t)row * (size_t)P.nhop;
-#pragma unroll 1
-        for (int tile = t_first; tile < t_end; ++tile) {
-            const bool live = tile >= t_live;
-            const long long tile_lo = (long long)tile * kL;
-            const bool interior = tile_lo >= kLead && tile_lo + kL <= kLead + P.n;
-            __syncthreads();                               // previous tile done with the buffer
-            if (interior) {
-                const float* s4 = src + tile_lo + 4 * tid;
+        auto load_tile = [&](int t) {
+            const long long lo = (long long)t * kL;
+            if (lo >= kLead && lo + kL <= kLead + P.n) {
+                const float* s4 = src + lo + 4 * tid;
                 float* d4 = tile_s + 4 * swz(tid);
 #pragma unroll
                 for (int r = 0; r < kTileVecs / kT; ++r) cp_async16(d4 + 4 * kT * r, s4 + 4 * kT * r);
-                cp_async_commit();
-                cp_async_wait<0>();
             } else {
 #pragma unroll 1
                 for (int r = 0; r < kTileVecs / kT; ++r) {
                     const int v = tid + kT * r;
-                    const long long q = tile_lo + 4 * v;
+                    const long long q = lo + 4 * v;
                     float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
                     for (int c = 0; c < 4; ++c)
@@ -109,7 +101,16 @@ __global__ void __launch_bounds__(kT) lufs_kernel(const __grid_constant__ LufsAr
                     *reinterpret_cast<float4*>(tile_s + 4 * swz(v)) = val;
                 }
             }
-            __syncthreads();
+            cp_async_commit();
+        };
+        load_tile(t_first);
+#pragma unroll 1
+        for (int tile = t_first; tile < t_end; ++tile) {
+            const bool live = tile >= t_live;
+            const long long tile_lo = (long long)tile * kL;
+            const bool interior = tile_lo >= kLead && tile_lo + kL <= kLead + P.n;
+            cp_async_wait<0>();
+            __syncthreads();                               // staged floats of this tile visible; previous tile done
 
             // ================= stage 0: high shelf, float32 in -> float32-rounded float64 out ===============
             // this thread's 32 input samples leave shared memory here: every thread reads its float chunk
@@ -128,6 +129,8 @@ __global__ void __launch_bounds__(kT) lufs_kernel(const __grid_constant__ LufsAr
                 }
                 xin[4 * u] = xv.x; xin[4 * u + 1] = xv.y; xin[4 * u + 2] = xv.z; xin[4 * u + 3] = xv.w;
             }
+            __syncthreads();                               // every thread holds its inputs: the staging tile is free
+            if (tile + 1 < t_end) load_tile(tile + 1);     // lands while this tile is scanned
             double E[2] = {0.0, 0.0};
 #pragma unroll
             for (int j = 0; j < kS; ++j) {
@@ -167,7 +170,7 @@ __global__ void __launch_bounds__(kT) lufs_kernel(const __grid_constant__ LufsAr
                 if (lane == 0) { z[0] = 0.0; z[1] = 0.0; }
                 matvec_acc_s<2>(tab[f].Plane[lane], base, z);
             };
-            resolve(0);          // contains a barrier: every thread holds its inputs in registers by now
+            resolve(0);
             double E1[2] = {0.0, 0.0};
 #pragma unroll
             for (int w = 0; w < kS / 2; ++w) {

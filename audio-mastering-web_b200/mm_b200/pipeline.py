@@ -225,6 +225,88 @@ def true_peak_dbfs(audio: np.ndarray, sr: int = 44100) -> float:
     return float(eng.true_peak(b)[0])
 
 
+def compute_lufs_timeline(audio: np.ndarray, sr: int, block_sec: float = 0.4, max_points: int = 300):
+    """backend/app/pipeline.py:667-697: integrated loudness of sliding ``block_sec`` segments.  The segments
+    are gathered on the device into one batch (one row set per segment) and metered by one kernel launch."""
+    import torch
+    a = np.asarray(audio)
+    duration_sec = len(a) / sr
+    block = int(sr * block_sec)
+    if duration_sec <= block_sec or a.size < block:
+        v = measure_lufs(a, sr)
+        return ([round(v, 2)] if not np.isnan(v) else [None], 0.0)
+    n_points = min(max_points, max(1, int((duration_sec - block_sec) / (block_sec * 0.25)) + 1))
+    step_sec = (duration_sec - block_sec) / max(n_points - 1, 1)
+    step = int(sr * step_sec)
+    count = 0
+    pos = 0
+    while pos + block <= len(a) and count < max_points:     # same loop bounds as the reference
+        count += 1
+        pos += step
+        if step == 0:
+            count = max_points
+    if block < 0.4 * sr:                                       # pyloudnorm raises for every segment -> None
+        return [None] * count, round(step_sec, 4)
+    eng, b, _ = _up(a, sr)
+    seg = eng.empty(count, b.channels, block, sr)
+    with torch.cuda.stream(eng.stream):
+        live = b.live()                                        # (channels, n)
+        if step > 0:
+            win = live.unfold(1, block, step)[:, :count]       # (channels, count, block) view
+        else:
+            win = live[:, None, :block].expand(-1, count, -1)
+        seg.live().view(count, b.channels, block).copy_(win.permute(1, 0, 2))
+    vals = eng.measure_lufs(seg)
+    return [None if np.isnan(v) else round(float(v), 2) for v in vals], round(step_sec, 4)
+
+
+def loudness_range_lu(audio: np.ndarray, sr: int) -> float:
+    """backend/app/routers/tools.py:57-65 (``_loudness_range_lu``): p95 - p10 of the 3 s block loudness values."""
+    timeline, _ = compute_lufs_timeline(audio, sr, block_sec=3.0, max_points=200)
+    vals = [v for v in timeline if v is not None and v > -70]
+    if len(vals) < 2:
+        return 0.0
+    arr = np.array(vals, dtype=np.float64)
+    p10, p95 = np.percentile(arr, 10), np.percentile(arr, 95)
+    return float(max(0.0, p95 - p10))
+
+
+def compute_vectorscope_points(audio: np.ndarray, max_points: int = 1000) -> list:
+    """backend/app/pipeline.py:742-763: at most ``max_points`` decimated [l, r] pairs, clipped, 5 decimals.
+    A pure index gather of <= 1000 frames of the caller's own host array: no kernel involved."""
+    a = np.asarray(audio)
+    if a.ndim != 2 or a.shape[1] != 2 or a.size < 4:
+        return []
+    n = a.shape[0]
+    step = max(1, n // max_points)
+    idx = np.arange(0, n, step)[:max_points]
+    pts = np.clip(a[idx].astype(np.float64), -1.0, 1.0)
+    return [[round(float(l), 5), round(float(r), 5)] for l, r in pts]
+
+
+def analyze_batch(tracks, sr, spectrum=True, eng: Optional[Engine] = None) -> list:
+    """Additive: the analyzer set of /api/v2/analyze and /api/tools/lufs-analyze (routers/mastering.py:1198-1302,
+    routers/tools.py:85-152) for equally-shaped tracks as one device batch: one upload, one kernel per metric."""
+    eng = eng or get_engine()
+    b = eng.upload(tracks, int(sr))
+    lufs = eng.measure_lufs(b)
+    tp = eng.true_peak(b)
+    corr, peak = eng.stereo_correlation(b)
+    bars = [eng.spectrum_bars(b, v) for v in ((0, 1, 2) if (spectrum and b.channels == 2) else ((0,) if spectrum else ()))]
+    out = []
+    for t in range(b.tracks):
+        rec = {"lufs": float(lufs[t]), "true_peak_dbfs": float(tp[t]), "sample_peak": float(peak[t]),
+               "peak_dbfs": float(20 * np.log10(max(float(peak[t]), 1e-12))),
+               "correlation": None if np.isnan(corr[t]) else float(corr[t])}
+        if bars:
+            rec["spectrum_bars"] = [float(v) for v in bars[0][t]]
+            if len(bars) == 3:
+                rec["spectrum_bars_mid"] = [float(v) for v in bars[1][t]]
+                rec["spectrum_bars_side"] = [float(v) for v in bars[2][t]]
+        out.append(rec)
+    return out
+
+
 # ---- chains -----------------------------------------------------------------------------------------
 _V1_PROGRESS = [(5, "dc_offset"), (10, "peak_guard"), (15, "target_curve"), (32, "deesser"), (38, "dynamics"),
                 (52, "normalize_lufs"), (65, "final_spectral_balance"), (72, "style_eq"), (82, "peak_guard"),

@@ -122,3 +122,37 @@ def test_correlation_conventions(P):
     assert abs(P.measure_stereo_correlation(np.stack([s, -s], 1)) + 1.0) < 1e-9
     assert P.measure_stereo_correlation(np.zeros((n, 2), np.float32)) is None
     assert P.measure_stereo_correlation(np.stack([s, np.full(n, 0.25, np.float32)], 1)) == 0.0
+
+
+def test_timeline_lra_vectorscope_and_batch_analyzer(P):
+    from oracle import chain as oc
+    from mm_b200 import synth
+    g = load_golden("analyzers")
+    for tag in "abc":
+        x, sr = g[f"{tag}_input"], int(g[f"{tag}_sr"])
+        tl, step = P.compute_lufs_timeline(x, sr)
+        ref = g[f"{tag}_timeline"]
+        assert len(tl) == len(ref) and step == float(g[f"{tag}_timeline_step"])
+        for a, b in zip(tl, ref):
+            assert (a is None and np.isnan(b)) or abs(a - b) <= 0.011          # both sides round to 0.01
+        assert np.allclose(np.array(P.compute_vectorscope_points(x)), g[f"{tag}_vscope"])
+    # a longer track: many sliding segments, 3 s blocks for the loudness range
+    sr = 44100
+    x = synth.numpy_track(9, sr, 14.0)
+    tl, step = P.compute_lufs_timeline(x, sr)
+    rtl, rstep = oc.compute_lufs_timeline(x, sr)
+    assert step == rstep and len(tl) == len(rtl)
+    assert max(abs(a - b) for a, b in zip(tl, rtl)) <= 0.011
+    tl3, _ = oc.compute_lufs_timeline(x, sr, block_sec=3.0, max_points=200)
+    vals = np.array([v for v in tl3 if v is not None and v > -70])
+    lra_ref = max(0.0, float(np.percentile(vals, 95) - np.percentile(vals, 10)))
+    assert abs(P.loudness_range_lu(x, sr) - lra_ref) <= 0.03
+    # batch analyzer == per-track calls
+    tracks = [synth.numpy_track(30 + i, sr, 1.2) for i in range(5)]
+    recs = P.analyze_batch(tracks, sr)
+    for t, r in zip(tracks, recs):
+        assert abs(r["lufs"] - oc.measure_lufs(t, sr)) <= 0.01
+        assert abs(r["true_peak_dbfs"] - oc.true_peak_dbfs(t)) <= 0.01
+        assert abs(r["correlation"] - oc.measure_stereo_correlation(t)) <= 1e-6
+        assert abs(r["sample_peak"] - float(np.max(np.abs(t)))) <= 1e-7
+        assert len(r["spectrum_bars"]) == 64 and len(r["spectrum_bars_side"]) == 64
