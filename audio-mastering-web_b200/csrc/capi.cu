@@ -287,6 +287,7 @@ void mm_ctx_destroy(mm_ctx* c) {
     cudaStreamSynchronize(c->stream);
     for (int i = 0; i < SL_COUNT; ++i) if (c->slots[i].p) cudaFree(c->slots[i].p);
     for (auto& kv : c->plans) if (kv.second.dev) cudaFree(kv.second.dev);
+    for (auto& kv : c->kw_plans) if (kv.second.dev) cudaFree(kv.second.dev);
     for (auto& kv : c->lufs_plans) {
         cudaFree(kv.second.bnd); cudaFree(kv.second.tile_seg); cudaFree(kv.second.blk_lo); cudaFree(kv.second.blk_hi);
     }
@@ -709,6 +710,34 @@ int mm_design_scan_tables(const double* b, const double* a, int ncoef, double* g
     if (zi) for (int i = 0; i < f.m; ++i) zi[i] = t.zi[i];
     if (S) *S = kS;
     if (T) *T = kT;
+    return t.W;
+}
+
+// Same tables for a chosen realization (0 = float64 DF2T, 1 = balanced coordinates of the float32 pass 2) plus
+// the realization itself: ss = [A (m*m), B (m), C (m), D, ||A||_2]  (design.h).
+int mm_design_scan_tables2(const double* b, const double* a, int ncoef, int mode, double* g_, double* Pw, double* Plane,
+                           double* Qpow, double* Mpow, int cap_w, double* Apow, double* zi, double* ss) {
+    if (!b || !a || (ncoef != 3 && ncoef != 5) || mode < 0 || mode > 1) { set_error("mm_design_scan_tables2: bad arguments"); return -1; }
+    Ba f;
+    f.m = ncoef - 1;
+    for (int i = 0; i < ncoef; ++i) { f.b[i] = b[i] / a[0]; f.a[i] = a[i] / a[0]; }
+    ScanTables t;
+    const bool ok = mode == kBalancedF32 ? build_scan_tables_balanced(f, kS, kT, &t) : build_scan_tables(f, kS, kT, &t);
+    if (!ok) { set_error("mm_design_scan_tables2: section cannot be tabulated in this realization"); return -1; }
+    const int m = f.m, mm2 = m * m;
+    if (g_) std::copy(t.g.begin(), t.g.end(), g_);
+    if (Pw) std::copy(t.Pw.begin(), t.Pw.end(), Pw);
+    if (Plane) std::copy(t.Plane.begin(), t.Plane.end(), Plane);
+    if (Qpow) std::copy(t.Qpow.begin(), t.Qpow.end(), Qpow);
+    if (Mpow) std::copy(t.Mpow.begin(), t.Mpow.begin() + (size_t)std::min(t.W, cap_w) * mm2, Mpow);
+    if (Apow) std::copy(t.Apow.begin(), t.Apow.end(), Apow);
+    if (zi) for (int i = 0; i < m; ++i) zi[i] = t.zi[i];
+    if (ss) {
+        for (int i = 0; i < mm2; ++i) ss[i] = t.A[i];
+        for (int i = 0; i < m; ++i) { ss[mm2 + i] = t.B[i]; ss[mm2 + m + i] = t.C[i]; }
+        ss[mm2 + 2 * m] = t.D;
+        ss[mm2 + 2 * m + 1] = mode == kBalancedF32 ? t.norm2 : balanced_norm(f);
+    }
     return t.W;
 }
 

@@ -30,7 +30,28 @@ template <int M> struct FiltK {
     double b[M + 1];
     double a[M];          // a[1..M]
     double g[kS][M];      // g[j] = A^(kS-1-j) B   (zero-state end state = sum_j g[j] x_j)
+    // float32 copy of the realization the tables are expressed in (balanced coordinates when the section's
+    // pass 2 runs in float32, see design.h): s' = A s + B x, y = C s + D x
+    float A32[M][M], B32[M], C32[M], D32;
 };
+
+// Two float32 sections evaluated in lock step with Blackwell's packed FFMA2 (fma.rn.f32x2): lane .x belongs to
+// the first section of the pair, .y to the second.  Same realization as FiltK::A32.. (balanced coordinates).
+struct PairK {
+    float2 A[2][2], B[2], C[2], D;
+    float2 g[kS][2];      // float32 pass 1: g[j][i] = (A^(kS-1-j) B)_i of both sections
+};
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+__device__ __forceinline__ float2 fmul2(float2 a, float2 b) { return __fmul2_rn(a, b); }
+// one packed step of a pair of 2-state sections: returns (y_a, y_b), advances (s0, s1)
+__device__ __forceinline__ float2 pair_step(const PairK& k, float2 x, float2& s0, float2& s1) {
+    const float2 y = ffma2(k.C[0], s0, ffma2(k.C[1], s1, fmul2(k.D, x)));
+    const float2 n0 = ffma2(k.A[0][0], s0, ffma2(k.A[0][1], s1, fmul2(k.B[0], x)));
+    const float2 n1 = ffma2(k.A[1][0], s0, ffma2(k.A[1][1], s1, fmul2(k.B[1], x)));
+    s0 = n0;
+    s1 = n1;
+    return y;
+}
 
 // prologue applied to samples as they are loaded
 enum { PRO_NONE = 0, PRO_SUBMUL_F32 = 1, PRO_MUL_F64 = 2 };
@@ -66,6 +87,8 @@ template <int M, int NF> struct SweepArgs {
     int aux_pro;             // apply the prologue to aux[0] too
     int epi;
     double w[NF], wc, trim;
+    float w32[NF];
+    PairK pr[(NF + 1) / 2];  // packed float32 sections (pairs 2p, 2p+1 with 2p+1 < NF32)
     DynParams dyn;
     double exc_gain, exc_k;
     int exc_mode;
@@ -100,6 +123,25 @@ template <int M> __device__ __forceinline__ double df2t_step(const FiltK<M>& fk,
         t = fma(fk.b[i + 1], x, t);
         z[i] = fma(-fk.a[i], y, t);
     }
+    return y;
+}
+
+// One float32 step of a section in its (balanced) state-space form.  The start state of every 32-sample chunk
+// comes from the float64 scan, so round-off only accumulates inside a chunk.
+template <int M> __device__ __forceinline__ float ss32_step(const FiltK<M>& fk, float x, float (&s)[M]) {
+    float y = fk.D32 * x;
+#pragma unroll
+    for (int i = M - 1; i >= 0; --i) y = fmaf(fk.C32[i], s[i], y);      // same association as pair_step
+    float sn[M];
+#pragma unroll
+    for (int i = 0; i < M; ++i) {
+        float t = fk.B32[i] * x;
+#pragma unroll
+        for (int k = M - 1; k >= 0; --k) t = fmaf(fk.A32[i][k], s[k], t);
+        sn[i] = t;
+    }
+#pragma unroll
+    for (int i = 0; i < M; ++i) s[i] = sn[i];
     return y;
 }
 

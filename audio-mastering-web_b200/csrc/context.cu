@@ -3,6 +3,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdarg>
+#include <cstdlib>
 #include <cstring>
 
 #include "common.cuh"
@@ -50,14 +51,48 @@ template <int M> static void pack_tables(const ScanTables& t, std::vector<double
     std::copy(t.Mpow.begin(), t.Mpow.end(), h.begin() + TB::Mpow);
 }
 
-const FilterPlan* get_plan(mm_ctx* c, const Ba& ba) {
+static int pass2_policy() {            // -1 auto (default), 0 force float64, 1 force float32
+    static int pol = -2;
+    if (pol == -2) {
+        const char* e = getenv("MM_PASS2");
+        pol = -1;
+        if (e && !strcmp(e, "f64")) pol = 0;
+        if (e && !strcmp(e, "f32")) pol = 1;
+    }
+    return pol;
+}
+
+const FilterPlan* get_plan(mm_ctx* c, const Ba& ba, int prec) {
+    int mode = kDf2tF64;
+    if (ba.m == 2) {
+        const int pol = pass2_policy();
+        if (pol == 1) mode = kBalancedF32;
+        else if (pol == -1) {
+            if (prec == PREC_F32) mode = kBalancedF32;
+            else if (prec == PREC_AUTO) mode = balanced_norm(ba) < 0.97 ? kBalancedF32 : kDf2tF64;
+        }
+    }
+    return get_plan_mode(c, ba, mode);
+}
+
+const FilterPlan* get_plan_mode(mm_ctx* c, const Ba& ba, int mode) {
+    if (ba.m != 2 && ba.m != 4) { set_error("unsupported section order %d (2 or 4)", ba.m); return nullptr; }
+    if (ba.m != 2) mode = kDf2tF64;
     std::string key((const char*)&ba, sizeof(Ba));
+    key.push_back((char)('0' + mode));
     auto it = c->plans.find(key);
     if (it != c->plans.end()) return &it->second;
     FilterPlan p;
     p.ba = ba;
-    if (ba.m != 2 && ba.m != 4) { set_error("unsupported section order %d (2 or 4)", ba.m); return nullptr; }
-    if (!build_scan_tables(ba, kS, kT, &p.tabs)) {
+    bool ok = false;
+    if (mode == kBalancedF32) ok = build_scan_tables_balanced(ba, kS, kT, &p.tabs);
+    if (!ok) {
+        if (mode == kBalancedF32) {         // not balanceable (non-minimal section): float64 DF2T instead
+            return get_plan_mode(c, ba, kDf2tF64);
+        }
+        ok = build_scan_tables(ba, kS, kT, &p.tabs);
+    }
+    if (!ok) {
         set_error("scan tables: pole too close to the unit circle for the %d-sample tile", kL);
         return nullptr;
     }
@@ -71,6 +106,34 @@ const FilterPlan* get_plan(mm_ctx* c, const Ba& ba) {
         return nullptr;
     }
     auto res = c->plans.emplace(key, p);
+    return &res.first->second;
+}
+
+const KwPlan* get_kw_plan(mm_ctx* c, int sr) {
+    auto it = c->kw_plans.find(sr);
+    if (it != c->kw_plans.end()) return &it->second;
+    KwPlan p;
+    StateSpace s0, s1, cas;
+    const Ba f0 = k_weighting_stage(0, (double)sr), f1 = k_weighting_stage(1, (double)sr);
+    if (!balanced_realization(f0, &s0, nullptr) || !balanced_realization(f1, &s1, nullptr)) {
+        set_error("K-weighting at %d Hz: balanced realization failed", sr);
+        return nullptr;
+    }
+    cascade_realization(s0, s1, &cas);
+    if (!build_scan_tables_ss(cas, kS, kT, &p.tabs) || !build_scan_tables_ss(s0, kS, kT, &p.sec[0]) ||
+        !build_scan_tables_ss(s1, kS, kT, &p.sec[1])) {
+        set_error("K-weighting at %d Hz: pole too close to the unit circle for the %d-sample tile", sr, kL);
+        return nullptr;
+    }
+    std::vector<double> h;
+    pack_tables<4>(p.tabs, h);
+    if (cudaMalloc(&p.dev, h.size() * sizeof(double)) != cudaSuccess) { set_error("cudaMalloc(K-weighting tables) failed"); return nullptr; }
+    if (cudaMemcpyAsync(p.dev, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream) != cudaSuccess ||
+        cudaStreamSynchronize(c->stream) != cudaSuccess) {
+        set_error("upload of K-weighting tables failed");
+        return nullptr;
+    }
+    auto res = c->kw_plans.emplace(sr, p);
     return &res.first->second;
 }
 
@@ -113,6 +176,9 @@ int get_lufs_plan(mm_ctx* c, long long n, int sr, const LufsPlan** out) {
     if (bnd.size() < 2) { bnd.clear(); bnd.push_back(0); bnd.push_back(0); p.valid = p.valid && false; }
     p.nseg = (int)bnd.size() - 1;
     p.nblocks = (int)lo.size();
+    // the loudness kernel splits a 32-sample chunk over at most three hops (lufs_kernel.cuh)
+    for (size_t s2 = 0; p.valid && s2 + 2 < bnd.size(); ++s2)
+        if (bnd[s2 + 2] - bnd[s2] < kS) { set_error("loudness: %d Hz is too low a sample rate for the block partition of this kernel", sr); return 1; }
     std::vector<int> blo(lo.size()), bhi(lo.size());
     for (size_t j = 0; j < lo.size(); ++j) {
         blo[j] = (int)(std::lower_bound(bnd.begin(), bnd.end(), lo[j]) - bnd.begin());

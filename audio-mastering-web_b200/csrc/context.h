@@ -29,11 +29,27 @@ void set_error(const char* fmt, ...);
         if (_r != 0) return _r; \
     } while (0)
 
+// How a section's pass 2 (the per-sample recurrence inside a 32-sample chunk) is evaluated.  The chunk-start
+// states always come from the float64 scan.
+//   PREC_F64  : float64 DF2T, bit-for-bit the arithmetic of scipy's lfilter up to summation order
+//   PREC_F32  : float32 on the balanced realization -- for sections whose output reaches the signal only through a
+//               small recombination weight (EQ bands, exciter side chain) and for the loudness meter
+//   PREC_AUTO : float32 when state errors die within a chunk (||A_balanced||_2 < 0.97: cut-offs above ~1 kHz),
+//               float64 otherwise -- for sections the full signal passes through
+// MM_PASS2=f64 forces float64 everywhere, MM_PASS2=f32 float32 wherever a float32 kernel exists (experiments).
+enum Prec { PREC_F64 = 0, PREC_F32 = 1, PREC_AUTO = 2 };
+
 struct FilterPlan {
     Ba ba;
     ScanTables tabs;
     double* dev = nullptr;      // device copy laid out as common.cuh Tab<M>
     int pad = 0;                // filtfilt padlen = 3 * max(len(a), len(b))
+};
+
+struct KwPlan {                 // K-weighting cascade (shelf -> high-pass) of one sample rate as a 4-state system
+    ScanTables tabs;            // tables of the cascade in [balanced shelf; balanced high-pass] coordinates
+    ScanTables sec[2];          // the two sections' balanced realizations (A, B, C, D used)
+    double* dev = nullptr;
 };
 
 struct LufsPlan {               // per (n, sr): gating blocks expressed over merged segments
@@ -66,6 +82,7 @@ struct mm_ctx {
     mm::Slot slots[mm::SL_COUNT];
     std::map<std::string, mm::FilterPlan> plans;
     std::map<std::string, mm::LufsPlan> lufs_plans;
+    std::map<int, mm::KwPlan> kw_plans;
     int64_t launches = 0;
     bool timing = false;
     std::vector<mm::KTime> ktimes;
@@ -82,8 +99,10 @@ template <class T> inline int arena(mm_ctx* c, int slot, size_t count, T** out) 
     *out = reinterpret_cast<T*>(p);
     return r;
 }
-const FilterPlan* get_plan(mm_ctx* c, const Ba& ba);
+const FilterPlan* get_plan(mm_ctx* c, const Ba& ba, int prec = PREC_F64);
+const FilterPlan* get_plan_mode(mm_ctx* c, const Ba& ba, int mode);   // mode: design.h Realization
 int get_lufs_plan(mm_ctx* c, long long n, int sr, const LufsPlan** out);
+const KwPlan* get_kw_plan(mm_ctx* c, int sr);
 
 struct KernelScope {            // brackets a launch with events when timing is on
     mm_ctx* c; const char* name; cudaEvent_t a = nullptr, b = nullptr;

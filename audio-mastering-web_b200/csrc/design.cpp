@@ -190,13 +190,182 @@ static void put(std::vector<double>& v, size_t at, int mm_, const long double* X
     for (int i = 0; i < mm_; ++i) v[at + i] = (double)X[i];
 }
 
-bool build_scan_tables(const Ba& f, int S, int T, ScanTables* out, int max_window) {
-    const int m = f.m;
+void df2t_realization(const Ba& f, StateSpace* out) {
+    out->m = f.m;
+    state_matrices(f, out->A, out->B);
+    for (int i = 0; i < f.m; ++i) out->C[i] = (i == 0) ? 1.0L : 0.0L;
+    out->D = (long double)f.b[0];
+}
+
+void cascade_realization(const StateSpace& s1, const StateSpace& s2, StateSpace* out) {
+    const int m1 = s1.m, m2 = s2.m, m = m1 + m2;
+    StateSpace r;
+    r.m = m;
+    for (int i = 0; i < m * m; ++i) r.A[i] = 0.0L;
+    for (int i = 0; i < m1; ++i) {
+        for (int j = 0; j < m1; ++j) r.A[i * m + j] = s1.A[i * m1 + j];
+        r.B[i] = s1.B[i];
+        r.C[i] = s2.D * s1.C[i];
+    }
+    for (int i = 0; i < m2; ++i) {
+        for (int j = 0; j < m1; ++j) r.A[(m1 + i) * m + j] = s2.B[i] * s1.C[j];     // the second section sees y1 = C1 s1 + D1 x
+        for (int j = 0; j < m2; ++j) r.A[(m1 + i) * m + m1 + j] = s2.A[i * m2 + j];
+        r.B[m1 + i] = s2.B[i] * s1.D;
+        r.C[m1 + i] = s2.C[i];
+    }
+    r.D = s2.D * s1.D;
+    *out = r;
+}
+
+// X = A X A^T + Q  (discrete Lyapunov), m <= 4: (I - A (x) A) vec(X) = vec(Q)
+static bool solve_dlyap(int m, const long double* A, const long double* Q, long double* X) {
+    const int n = m * m;
+    long double K[256], rhs[16];
+    for (int i = 0; i < m; ++i)
+        for (int j = 0; j < m; ++j) {
+            const int r = i * m + j;
+            for (int k = 0; k < m; ++k)
+                for (int l = 0; l < m; ++l) K[r * n + k * m + l] = ((r == k * m + l) ? 1.0L : 0.0L) - A[i * m + k] * A[j * m + l];
+            rhs[r] = Q[r];
+        }
+    if (!solve_small(n, K, rhs)) return false;
+    for (int i = 0; i < m; ++i)
+        for (int j = 0; j < m; ++j) X[i * m + j] = 0.5L * (rhs[i * m + j] + rhs[j * m + i]);
+    return true;
+}
+
+// cyclic Jacobi eigen-decomposition of a symmetric m x m matrix: S = U diag(ev) U^T
+static void jacobi_eig(int m, long double* S, long double* U, long double* ev) {
+    mat_eye(m, U);
+    for (int sweep = 0; sweep < 60; ++sweep) {
+        long double off = 0.0L, diag = 0.0L;
+        for (int i = 0; i < m; ++i)
+            for (int j = 0; j < m; ++j) (i == j ? diag : off) += S[i * m + j] * S[i * m + j];
+        if (off <= 1e-40L * diag || off == 0.0L) break;
+        for (int p = 0; p < m; ++p)
+            for (int q = p + 1; q < m; ++q) {
+                if (S[p * m + q] == 0.0L) continue;
+                const long double theta = (S[q * m + q] - S[p * m + p]) / (2.0L * S[p * m + q]);
+                const long double t = (theta >= 0 ? 1.0L : -1.0L) / (fabsl(theta) + sqrtl(theta * theta + 1.0L));
+                const long double cs = 1.0L / sqrtl(t * t + 1.0L), sn = t * cs;
+                for (int k = 0; k < m; ++k) {      // columns p, q
+                    const long double a = S[k * m + p], b = S[k * m + q];
+                    S[k * m + p] = cs * a - sn * b;
+                    S[k * m + q] = sn * a + cs * b;
+                }
+                for (int k = 0; k < m; ++k) {      // rows p, q
+                    const long double a = S[p * m + k], b = S[q * m + k];
+                    S[p * m + k] = cs * a - sn * b;
+                    S[q * m + k] = sn * a + cs * b;
+                }
+                for (int k = 0; k < m; ++k) {
+                    const long double a = U[k * m + p], b = U[k * m + q];
+                    U[k * m + p] = cs * a - sn * b;
+                    U[k * m + q] = sn * a + cs * b;
+                }
+            }
+    }
+    for (int i = 0; i < m; ++i) ev[i] = S[i * m + i];
+}
+
+bool balanced_realization(const Ba& f, StateSpace* out, long double* Tmap) {
+    StateSpace d;
+    df2t_realization(f, &d);
+    const int m = d.m;
+    if (m < 1 || m > kMaxOrder) return false;
+    long double Q[16], At[16], Wc[16], Wo[16];
+    for (int i = 0; i < m; ++i)
+        for (int j = 0; j < m; ++j) { Q[i * m + j] = d.B[i] * d.B[j]; At[i * m + j] = d.A[j * m + i]; }
+    if (!solve_dlyap(m, d.A, Q, Wc)) return false;
+    for (int i = 0; i < m; ++i)
+        for (int j = 0; j < m; ++j) Q[i * m + j] = d.C[i] * d.C[j];
+    if (!solve_dlyap(m, At, Q, Wo)) return false;
+    // Cholesky Wc = L L^T
+    long double L[16];
+    for (int i = 0; i < m * m; ++i) L[i] = 0.0L;
+    for (int j = 0; j < m; ++j) {
+        long double s = Wc[j * m + j];
+        for (int k = 0; k < j; ++k) s -= L[j * m + k] * L[j * m + k];
+        if (!(s > 0.0L)) return false;
+        L[j * m + j] = sqrtl(s);
+        for (int i = j + 1; i < m; ++i) {
+            long double t = Wc[i * m + j];
+            for (int k = 0; k < j; ++k) t -= L[i * m + k] * L[j * m + k];
+            L[i * m + j] = t / L[j * m + j];
+        }
+    }
+    // S = L^T Wo L = U diag(hsv^2) U^T
+    long double Lt[16], S[16], U[16], ev[4], tmp[16];
+    for (int i = 0; i < m; ++i)
+        for (int j = 0; j < m; ++j) Lt[i * m + j] = L[j * m + i];
+    mat_mul(m, Lt, Wo, tmp);
+    mat_mul(m, tmp, L, S);
+    for (int i = 0; i < m; ++i)
+        for (int j = i + 1; j < m; ++j) S[i * m + j] = S[j * m + i] = 0.5L * (S[i * m + j] + S[j * m + i]);
+    jacobi_eig(m, S, U, ev);
+    for (int i = 0; i < m; ++i)
+        if (!(ev[i] > 0.0L)) return false;
+    // Tinv = L U diag(ev^-1/4),  T = diag(ev^1/4) U^T L^-1
+    long double Tinv[16], T[16], Linv[16];
+    for (int c = 0; c < m; ++c) {          // L^-1 by forward substitution on unit vectors
+        for (int i = 0; i < m; ++i) {
+            long double s = (i == c) ? 1.0L : 0.0L;
+            for (int k = 0; k < i; ++k) s -= L[i * m + k] * Linv[k * m + c];
+            Linv[i * m + c] = s / L[i * m + i];
+        }
+    }
+    mat_mul(m, L, U, Tinv);
+    for (int i = 0; i < m; ++i)
+        for (int j = 0; j < m; ++j) Tinv[i * m + j] *= powl(ev[j], -0.25L);
+    long double Ut[16];
+    for (int i = 0; i < m; ++i)
+        for (int j = 0; j < m; ++j) Ut[i * m + j] = U[j * m + i];
+    mat_mul(m, Ut, Linv, T);
+    for (int i = 0; i < m; ++i)
+        for (int j = 0; j < m; ++j) T[i * m + j] *= powl(ev[i], 0.25L);
+    StateSpace r;
+    r.m = m;
+    mat_mul(m, T, d.A, tmp);
+    mat_mul(m, tmp, Tinv, r.A);
+    for (int i = 0; i < m; ++i) {
+        long double sb = 0.0L, sc = 0.0L;
+        for (int k = 0; k < m; ++k) { sb += T[i * m + k] * d.B[k]; sc += d.C[k] * Tinv[k * m + i]; }
+        r.B[i] = sb;
+        r.C[i] = sc;
+    }
+    r.D = d.D;
+    *out = r;
+    if (Tmap) for (int i = 0; i < m * m; ++i) Tmap[i] = T[i];
+    return true;
+}
+
+static double spectral_norm(int m, const long double* A) {
+    long double At[16], S[16], U[16], ev[4];
+    for (int i = 0; i < m; ++i)
+        for (int j = 0; j < m; ++j) At[i * m + j] = A[j * m + i];
+    mat_mul(m, At, A, S);
+    jacobi_eig(m, S, U, ev);
+    long double mx = 0.0L;
+    for (int i = 0; i < m; ++i) mx = fmaxl(mx, ev[i]);
+    return (double)sqrtl(mx);
+}
+
+double balanced_norm(const Ba& f) {
+    StateSpace s;
+    if (!balanced_realization(f, &s, nullptr)) return 1.0;
+    return spectral_norm(s.m, s.A);
+}
+
+bool build_scan_tables_ss(const StateSpace& ss, int S, int T, ScanTables* out, int max_window) {
+    const int m = ss.m;
     if (m < 1 || m > kMaxOrder || T % 32 != 0) return false;
-    long double A[kMaxOrder * kMaxOrder], B[kMaxOrder];
-    state_matrices(f, A, B);
+    const long double* A = ss.A;
+    const long double* B = ss.B;
     out->m = m; out->S = S; out->T = T;
     const int mm2 = m * m;
+    for (int i = 0; i < mm2; ++i) out->A[i] = (double)ss.A[i];
+    for (int i = 0; i < m; ++i) { out->B[i] = (double)ss.B[i]; out->C[i] = (double)ss.C[i]; }
+    out->D = (double)ss.D;
     // g[j] = A^(S-1-j) B, built backwards from j = S-1
     out->g.assign((size_t)S * m, 0.0);
     {
@@ -249,14 +418,46 @@ bool build_scan_tables(const Ba& f, int S, int T, ScanTables* out, int max_windo
     if (W >= max_window) return false;   // pole too close to the unit circle for this tile size
     out->W = W;
     if (out->Wh == 0) out->Wh = W;
-    if (!lfilter_zi(f, out->zi)) {
-        for (int i = 0; i < m; ++i) out->zi[i] = 0.0;   // scipy would raise LinAlgError; callers decide
-    }
+    for (int i = 0; i < m; ++i) out->zi[i] = 0.0;
     // spectral radius estimate from M's decay: r ~ (max|M|)^(1/L)
     {
         long double mx = 0.0L;
         for (int i = 0; i < mm2; ++i) mx = fmaxl(mx, fabsl(M[i]));
         out->pole_radius = mx > 0 ? (double)expl(logl(mx) / (long double)((int64_t)S * T)) : 0.0;
+    }
+    return true;
+}
+
+bool build_scan_tables(const Ba& f, int S, int T, ScanTables* out, int max_window) {
+    StateSpace ss;
+    if (f.m < 1 || f.m > kMaxOrder) return false;
+    df2t_realization(f, &ss);
+    if (!build_scan_tables_ss(ss, S, T, out, max_window)) return false;
+    out->mode = kDf2tF64;
+    if (!lfilter_zi(f, out->zi)) {
+        for (int i = 0; i < f.m; ++i) out->zi[i] = 0.0;   // scipy would raise LinAlgError; callers decide
+    }
+    return true;
+}
+
+bool build_scan_tables_balanced(const Ba& f, int S, int T, ScanTables* out, int max_window) {
+    StateSpace ss;
+    long double Tm[kMaxOrder * kMaxOrder];
+    if (f.m < 1 || f.m > kMaxOrder) return false;
+    if (!balanced_realization(f, &ss, Tm)) return false;
+    if (!build_scan_tables_ss(ss, S, T, out, max_window)) return false;
+    out->mode = kBalancedF32;
+    out->norm2 = spectral_norm(ss.m, ss.A);
+    // steady state of the unit-step response in these coordinates: (I - A) s = B
+    {
+        const int m = ss.m;
+        long double I_A[kMaxOrder * kMaxOrder], rhs[kMaxOrder];
+        for (int i = 0; i < m; ++i) {
+            for (int j = 0; j < m; ++j) I_A[i * m + j] = (i == j ? 1.0L : 0.0L) - ss.A[i * m + j];
+            rhs[i] = ss.B[i];
+        }
+        if (solve_small(m, I_A, rhs))
+            for (int i = 0; i < m; ++i) out->zi[i] = (double)rhs[i];
     }
     return true;
 }

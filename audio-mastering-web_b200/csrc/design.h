@@ -30,7 +30,29 @@ Ba k_weighting_stage(int stage, double rate);
 
 // DF2T as a state-space system  z[n] = A z[n-1] + B x[n],  y[n] = z[n-1][0] + b0 x[n]
 // A = companion(a)^T (row-major m x m), B[i] = b[i+1] - a[i+1] b0.
+// A section as a general state-space system  s[n] = A s[n-1] + B x[n],  y[n] = C s[n-1] + D x[n]
+// (row-major A).  DF2T is the special case A = companion(a)^T, C = e_0, D = b0.
+struct StateSpace {
+    int m = 0;
+    long double A[kMaxOrder * kMaxOrder] = {0};
+    long double B[kMaxOrder] = {0};
+    long double C[kMaxOrder] = {0};
+    long double D = 0;
+};
+void df2t_realization(const Ba& f, StateSpace* out);
+// Internally balanced realization (equal, diagonal controllability / observability Gramians): ||A||_2 <= 1 and
+// the round-off noise gain of a float32 state update is O(1) instead of O(1/(1-r)^2) for DF2T.  T (m x m,
+// row-major) maps DF2T states into the balanced coordinates, s_bal = T z.  False if the section is not minimal.
+bool balanced_realization(const Ba& f, StateSpace* out, long double* T);
+// y2(y1(x)): state [s1; s2]
+void cascade_realization(const StateSpace& s1, const StateSpace& s2, StateSpace* out);
+
+enum Realization { kDf2tF64 = 0, kBalancedF32 = 1 };
+
 struct ScanTables {
+    int mode = kDf2tF64;                // coordinates the tables are expressed in
+    double A[kMaxOrder * kMaxOrder] = {0}, B[kMaxOrder] = {0}, C[kMaxOrder] = {0}, D = 0;   // the realization
+    double norm2 = 0;                   // ||A||_2 of the balanced realization (0 if not computed)
     int m = 0;
     int S = 0, T = 0;                   // samples per thread, threads per tile
     int W = 0;                          // look-back window (tiles) after which A^(L*W) < 1e-18
@@ -45,5 +67,11 @@ struct ScanTables {
     double pole_radius = 0;
 };
 bool build_scan_tables(const Ba& f, int S, int T, ScanTables* out, int max_window = 4096);
+// Tables of an arbitrary realization; zi (DF2T steady state of the unit step, or null) is mapped through T_map (or identity).
+bool build_scan_tables_ss(const StateSpace& ss, int S, int T, ScanTables* out, int max_window = 4096);
+// Same section in balanced coordinates for the float32 pass 2 (falls back to false if balancing fails).
+bool build_scan_tables_balanced(const Ba& f, int S, int T, ScanTables* out, int max_window = 4096);
+// ||A||_2 of the balanced realization of f (1.0 if balancing fails): the precision policy's "how long do state errors live"
+double balanced_norm(const Ba& f);
 
 }  // namespace mm

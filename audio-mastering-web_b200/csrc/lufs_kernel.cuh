@@ -3,11 +3,16 @@
 // as called at backend/app/pipeline.py:646-648 / :660-662.
 //
 // Same decomposition as the sweep kernel (sweep3.cuh): a CTA walks a segment of tiles of one row with
-// the filter states carried in shared memory; the state at the segment start is rebuilt from a halo of
-// W(shelf) + W(high-pass) tiles.  Per tile the shelf is scanned in place, rounded to float32 (pyloudnorm
-// writes each stage back into a copy of its float32 input), then the high-pass; the squares of the
-// result are summed per 100 ms hop into 64-bit fixed-point accumulators (integer atomics are
-// associative, so the loudness -- and the gain derived from it -- is bit-reproducible).
+// the filter state carried in shared memory; the state at the segment start is rebuilt from a halo.
+// The shelf -> high-pass cascade is ONE 4-state linear system here: pass 1 (float64) forms the zero-state
+// end state of each 32-sample chunk straight from the input samples, one 4x4 scan resolves the state
+// entering every chunk, and pass 2 runs the two sections in float32 on their balanced realizations
+// (design.h) from that exact start state, squaring and summing as it goes.  Round-off therefore never
+// accumulates beyond 32 samples; the measured loudness moves by < 1e-5 LU against the +-0.01 LU
+// tolerance.  (pyloudnorm also rounds each stage's output to float32; that 6e-8 relative rounding is
+// not reproduced, as before.)  The squares are summed per 100 ms hop into 64-bit fixed-point
+// accumulators (integer atomics are associative, so the loudness -- and the gain derived from it -- is
+// bit-reproducible).
 #pragma once
 #include "sweep3.cuh"
 
@@ -16,8 +21,9 @@ namespace mm {
 constexpr double kSqScale = 1099511627776.0;        // 2^40: fixed-point scale of the square sums
 
 struct LufsArgs {
-    FiltK<2> f[2];
-    const double* tab[2];
+    PairK k;                 // .x = shelf, .y = high-pass (balanced realizations); g[j] = cascade pass-1 weights:
+                             // g[j][0] = states (0, 1) of the shelf, g[j][1] = states (2, 3) of the high-pass
+    const double* tab;       // Tab<4> of the cascade (device)
     const float* in;
     long long n, stride;
     int rows, ntiles, channels;
@@ -32,39 +38,29 @@ struct LufsArgs {
     unsigned long long* segsum;   // [rows][nhop] fixed-point sums of squares
 };
 
+struct LufsTab {             // scan tables of the 4-state cascade in shared memory
+    double Pw[5][16];
+    double PlaneT[16][32];   // Plane[lane][k] transposed: lane-contiguous, conflict free
+    double Qpow[kNW + 1][16];
+};
 struct LufsScratch {
-    double tot[kNW][2];
-    double carry[2][2][2];   // [tile parity][filter][state]
+    double tot[kNW][4];
+    double carry[2][4];      // [tile parity][state]
 };
 
-// pyloudnorm writes each stage's float64 lfilter output back into its float32 buffer.  Those two roundings
-// (6e-8 relative) move the loudness by ~1e-7 dB against a +-0.01 LU tolerance; reproducing them costs either
-// two conversions or three FP64 operations per sample and stage in a kernel that is bound by exactly those
-// pipes, so the stages are chained in float64 here.
-__device__ __forceinline__ double round_to_f32(double y) { return y; }
+constexpr int kLufsSmem = kL * (int)sizeof(float) + (int)sizeof(LufsTab);
 
-constexpr int kLufsSmem = kL * (int)sizeof(float) + kL * (int)sizeof(double) + 2 * (int)sizeof(SmemTab<2>);
-
-__global__ void __launch_bounds__(kT) lufs_kernel(const __grid_constant__ LufsArgs P) {
-    // a float32 staging tile receives the NEXT tile (cp.async) while the current one is scanned; the shelf's
-    // pass 2 writes its float32-rounded output as float64 into a second buffer, so the high-pass stage needs
-    // no conversions at all
+__global__ void __launch_bounds__(kT, 6) lufs_kernel(const __grid_constant__ LufsArgs P) {
+    // a float32 staging tile receives the NEXT tile (cp.async) while the current one is scanned
     extern __shared__ __align__(128) unsigned char lufs_smem[];
     float* tile_s = reinterpret_cast<float*>(lufs_smem);
-    double* tile_d = reinterpret_cast<double*>(lufs_smem + kL * sizeof(float));
-    SmemTab<2>* tab = reinterpret_cast<SmemTab<2>*>(lufs_smem + kL * sizeof(float) + kL * sizeof(double));
+    LufsTab* tab = reinterpret_cast<LufsTab*>(lufs_smem + kL * sizeof(float));
     __shared__ LufsScratch sh;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    constexpr int MM = 4;
-#pragma unroll 1
-    for (int f = 0; f < 2; ++f) {
-        double* d = reinterpret_cast<double*>(&tab[f]);
-        for (int i = tid; i < (5 + 32 + kNW + 1) * MM; i += kT) d[i] = __ldg(P.tab[f] + i);
-    }
+    for (int i = tid; i < 5 * 16; i += kT) tab->Pw[i / 16][i % 16] = __ldg(P.tab + Tab<4>::Pw + i);
+    for (int i = tid; i < 32 * 16; i += kT) tab->PlaneT[i % 16][i / 16] = __ldg(P.tab + Tab<4>::Plane + i);
+    for (int i = tid; i < (kNW + 1) * 16; i += kT) tab->Qpow[i / 16][i % 16] = __ldg(P.tab + Tab<4>::Qpow + i);
     const int cbase = tid * 32, cx = (tid & 7) << 2;
-    // float64 layout of this thread's chunk: 16 vectors of 2 doubles at dbase + ((2 w) ^ dx), conflict free
-    // for 16-byte accesses (8 consecutive threads cover all 8 16-byte bank groups)
-    const int dbase = tid * 32, dx = (tid & 7) << 1;
     const int items = P.rows * P.nseg;
 #pragma unroll 1
     for (int item = blockIdx.x; item < items; item += gridDim.x) {
@@ -80,7 +76,7 @@ __global__ void __launch_bounds__(kT) lufs_kernel(const __grid_constant__ LufsAr
             if (P.pro_mul) { muld = __ldg(P.pro_mul + row); mulf = (float)muld; }
         }
         __syncthreads();
-        if (tid < 4) sh.carry[t_first & 1][tid >> 1][tid & 1] = 0.0;
+        if (tid < 4) sh.carry[t_first & 1][tid] = 0.0;
         unsigned long long* dst = P.segsum + (size_t)row * (size_t)P.nhop;
         auto load_tile = [&](int t) {
             const long long lo = (long long)t * kL;
@@ -112,9 +108,7 @@ __global__ void __launch_bounds__(kT) lufs_kernel(const __grid_constant__ LufsAr
             cp_async_wait<0>();
             __syncthreads();                               // staged floats of this tile visible; previous tile done
 
-            // ================= stage 0: high shelf, float32 in -> float32-rounded float64 out ===============
-            // this thread's 32 input samples leave shared memory here: every thread reads its float chunk
-            // before anybody overwrites the buffer with doubles (barrier below)
+            // this thread's 32 input samples leave shared memory here
             float xin[32];
 #pragma unroll
             for (int u = 0; u < kS / 4; ++u) {
@@ -131,103 +125,138 @@ __global__ void __launch_bounds__(kT) lufs_kernel(const __grid_constant__ LufsAr
             }
             __syncthreads();                               // every thread holds its inputs: the staging tile is free
             if (tile + 1 < t_end) load_tile(tile + 1);     // lands while this tile is scanned
-            double E[2] = {0.0, 0.0};
+
+            // ---- pass 1 (packed float32): zero-state end state of the 4-state cascade over this chunk ----
+            float2 E01 = make_float2(0.f, 0.f), E23 = E01;
 #pragma unroll
             for (int j = 0; j < kS; ++j) {
-                const double x = (double)xin[j];
-                E[0] = fma(P.f[0].g[j][0], x, E[0]);
-                E[1] = fma(P.f[0].g[j][1], x, E[1]);
+                const float2 X = make_float2(xin[j], xin[j]);
+                E01 = ffma2(P.k.g[j][0], X, E01);
+                E23 = ffma2(P.k.g[j][1], X, E23);
             }
-            double base[2], cin[2], z[2];
-            auto resolve = [&](int f) {
-                // warp scan, tile Horner, carry update; leaves the state entering this thread's chunk in z
+            double E[4] = {(double)E01.x, (double)E01.y, (double)E23.x, (double)E23.y};
+            // ---- warp scan, tile Horner, carry update (float64) ----
 #pragma unroll
-                for (int d = 0; d < 5; ++d) {
-                    double pe[2];
-                    pe[0] = shfl_up_d(E[0], 1 << d);
-                    pe[1] = shfl_up_d(E[1], 1 << d);
-                    if (lane >= (1 << d)) matvec_acc_s<2>(tab[f].Pw[d], pe, E);
-                }
-                if (lane == 31) { sh.tot[warp][0] = E[0]; sh.tot[warp][1] = E[1]; }
-                __syncthreads();
-                base[0] = 0.0; base[1] = 0.0;
-                for (int v = 0; v < warp; ++v) {
-                    double nb[2] = {sh.tot[v][0], sh.tot[v][1]};
-                    matvec_acc_s<2>(tab[f].Qpow[1], base, nb);
-                    base[0] = nb[0]; base[1] = nb[1];
-                }
-                cin[0] = sh.carry[tile & 1][f][0]; cin[1] = sh.carry[tile & 1][f][1];
-                if (tid == kT - 1) {
-                    double ag[2] = {E[0], E[1]};
-                    matvec_acc_s<2>(tab[f].Qpow[1], base, ag);
-                    matvec_acc_s<2>(tab[f].Qpow[kNW], cin, ag);
-                    sh.carry[(tile + 1) & 1][f][0] = ag[0];
-                    sh.carry[(tile + 1) & 1][f][1] = ag[1];
-                }
-                matvec_acc_s<2>(tab[f].Qpow[warp], cin, base);
-                z[0] = shfl_up_d(E[0], 1);
-                z[1] = shfl_up_d(E[1], 1);
-                if (lane == 0) { z[0] = 0.0; z[1] = 0.0; }
-                matvec_acc_s<2>(tab[f].Plane[lane], base, z);
-            };
-            resolve(0);
-            double E1[2] = {0.0, 0.0};
+            for (int d = 0; d < 5; ++d) {
+                double pe[4];
 #pragma unroll
-            for (int w = 0; w < kS / 2; ++w) {
-                const double y0 = round_to_f32(df2t_step<2>(P.f[0], (double)xin[2 * w], z));
-                const double y1 = round_to_f32(df2t_step<2>(P.f[0], (double)xin[2 * w + 1], z));
-                // stage 1's pass 1 rides along: zero-state end state of the high-pass over this chunk
-                E1[0] = fma(P.f[1].g[2 * w][0], y0, E1[0]);
-                E1[1] = fma(P.f[1].g[2 * w][1], y0, E1[1]);
-                E1[0] = fma(P.f[1].g[2 * w + 1][0], y1, E1[0]);
-                E1[1] = fma(P.f[1].g[2 * w + 1][1], y1, E1[1]);
-                *reinterpret_cast<double2*>(tile_d + dbase + ((2 * w) ^ dx)) = make_double2(y0, y1);
+                for (int i = 0; i < 4; ++i) {
+                    const double v = shfl_up_d(E[i], 1 << d);
+                    pe[i] = (lane >= (1 << d)) ? v : 0.0;
+                }
+                matvec_acc_s<4>(tab->Pw[d], pe, E);
             }
-            // ================= stage 1: high-pass on the float64 tile ======================================
-            E[0] = E1[0]; E[1] = E1[1];
-            __syncthreads();     // sh.tot of stage 0 has been consumed by everybody
-            resolve(1);
-            if (!live) continue;                           // halo: only the carried states were needed
+            if (lane == 31) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) sh.tot[warp][i] = E[i];
+            }
+            __syncthreads();
+            double base[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+            for (int v = 0; v < kNW - 1; ++v) {
+                if (v < warp) {
+                    double nb[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) nb[i] = sh.tot[v][i];
+                    matvec_acc_s<4>(tab->Qpow[1], base, nb);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) base[i] = nb[i];
+                }
+            }
+            double cin[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) cin[i] = sh.carry[tile & 1][i];
+            if (tid == kT - 1) {
+                double ag[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) ag[i] = E[i];
+                matvec_acc_s<4>(tab->Qpow[1], base, ag);
+                matvec_acc_s<4>(tab->Qpow[kNW], cin, ag);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) sh.carry[(tile + 1) & 1][i] = ag[i];
+            }
+            if (!live) continue;                           // halo: only the carried state was needed
+            matvec_acc_s<4>(tab->Qpow[warp], cin, base);
+            double z[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const double up = shfl_up_d(E[i], 1);
+                z[i] = (lane > 0) ? up : 0.0;
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                double acc = z[i];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) acc = fma(tab->PlaneT[i * 4 + k][lane], base[k], acc);
+                z[i] = acc;
+            }
 
-            // pass 2 fused with the squared sums per hop (the squares use the float32-rounded output)
+            // ---- pass 2 (packed float32, the high-pass runs one sample behind the shelf) + squared sums per hop ----
             const long long i0 = tile_lo + (long long)tid * kS - kLead;          // first sample index of this thread
             const long long iw = tile_lo + (long long)(tid & ~31) * kS - kLead;   // first sample of this warp
             int sw = __ldg(P.tile_seg + tile);
             while (sw < P.nhop && __ldg(P.bnd + sw + 1) <= iw) ++sw;
             int s = sw;
             while (s < P.nhop && __ldg(P.bnd + s + 1) <= i0) ++s;
-            long long nb = (s < P.nhop) ? __ldg(P.bnd + s + 1) : (long long)0x7fffffffffffffffLL;
-            double accA = 0.0, accB = 0.0, acc = 0.0;
-            auto flush = [&](int hop, double v) {
-                if (hop == sw) accA += v;
-                else if (hop == sw + 1) accB += v;
-                else if (hop < P.nhop && v != 0.0) atomicAdd(dst + hop, (unsigned long long)__double2ll_rn(v * kSqScale));
-            };
-            const bool whole = (i0 >= 0) && (i0 + kS <= P.n) && (i0 + kS <= nb);   // chunk inside the row and one hop
+            const long long kBig = 0x3fffffffffffffffLL;
+            const long long nb1 = (s < P.nhop) ? __ldg(P.bnd + s + 1) : kBig;
+            const long long nb2 = (s + 1 < P.nhop) ? __ldg(P.bnd + s + 2) : kBig;
+            const bool whole = (i0 >= 0) && (i0 + kS <= P.n) && (i0 + kS <= nb1);   // chunk inside the row and one hop
+            float2 S0 = make_float2((float)z[0], (float)z[2]);
+            float2 S1 = make_float2((float)z[1], (float)z[3]);
+            // step 0: the shelf alone (lane .y idles on a zero-weight copy of itself)
+            float u_prev;
+            {
+                const float u = fmaf(P.k.C[0].x, S0.x, fmaf(P.k.C[1].x, S1.x, P.k.D.x * xin[0]));
+                const float n0 = fmaf(P.k.A[0][0].x, S0.x, fmaf(P.k.A[0][1].x, S1.x, P.k.B[0].x * xin[0]));
+                const float n1 = fmaf(P.k.A[1][0].x, S0.x, fmaf(P.k.A[1][1].x, S1.x, P.k.B[1].x * xin[0]));
+                S0.x = n0; S1.x = n1;
+                u_prev = u;
+            }
+            float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f;
+            if (__all_sync(0xffffffffu, whole)) {
 #pragma unroll
-            for (int w = 0; w < kS / 2; ++w) {
-                const double2 xv = *reinterpret_cast<const double2*>(tile_d + dbase + ((2 * w) ^ dx));
-                const double y0 = round_to_f32(df2t_step<2>(P.f[1], xv.x, z));
-                const double y1 = round_to_f32(df2t_step<2>(P.f[1], xv.y, z));
-                if (whole) {
-                    acc = fma(y0, y0, acc);
-                    acc = fma(y1, y1, acc);
-                } else {
+                for (int j = 1; j < kS; ++j) {
+                    const float2 Y = pair_step(P.k, make_float2(xin[j], u_prev), S0, S1);   // Y.x = shelf(j), Y.y = K-weighted(j-1)
+                    u_prev = Y.x;
+                    if (j & 1) acc0 = fmaf(Y.y, Y.y, acc0); else acc1 = fmaf(Y.y, Y.y, acc1);
+                }
+                const float yl = fmaf(P.k.C[0].y, S0.y, fmaf(P.k.C[1].y, S1.y, P.k.D.y * u_prev));
+                acc1 = fmaf(yl, yl, acc1);
+                acc0 += acc1; acc1 = 0.f;
+            } else {
+                // chunks cut by hop boundaries (at most two: the host plan guarantees it) or by the row's end:
+                // samples [0, j1) -> hop s, [j1, j2) -> hop s+1, [j2, jv) -> hop s+2; samples >= jv lie beyond the row
+                const int jv = (int)max(0LL, min((long long)kS, P.n - i0));
+                const int j1 = (int)max(0LL, min((long long)jv, nb1 - i0));
+                const int j2 = (int)max((long long)j1, min((long long)jv, nb2 - i0));
 #pragma unroll
-                    for (int c = 0; c < 2; ++c) {
-                        const long long i = i0 + 2 * w + c;
-                        if (i >= nb) {
-                            flush(s, acc);
-                            acc = 0.0;
-                            while (s < P.nhop && __ldg(P.bnd + s + 1) <= i) ++s;
-                            nb = (s < P.nhop) ? __ldg(P.bnd + s + 1) : (long long)0x7fffffffffffffffLL;
-                        }
-                        const double y = c == 0 ? y0 : y1;
-                        if (i >= 0 && i < P.n) acc = fma(y, y, acc);
+                for (int j = 1; j <= kS; ++j) {
+                    float yk;
+                    if (j < kS) {
+                        const float2 Y = pair_step(P.k, make_float2(xin[j], u_prev), S0, S1);
+                        u_prev = Y.x;
+                        yk = Y.y;
+                    } else {
+                        yk = fmaf(P.k.C[0].y, S0.y, fmaf(P.k.C[1].y, S1.y, P.k.D.y * u_prev));
                     }
+                    const float t = yk * yk;
+                    const int js = j - 1;                  // sample this output belongs to
+                    acc0 += (js < j1) ? t : 0.f;
+                    acc1 += (js >= j1 && js < j2) ? t : 0.f;
+                    acc2 += (js >= j2 && js < jv) ? t : 0.f;
                 }
             }
-            flush(s, acc);
+            double accA = 0.0, accB = 0.0;
+            auto flush = [&](int hop, float v) {
+                if (v == 0.f) return;
+                if (hop == sw) accA += (double)v;
+                else if (hop == sw + 1) accB += (double)v;
+                else if (hop < P.nhop) atomicAdd(dst + hop, (unsigned long long)__double2ll_rn((double)v * kSqScale));
+            };
+            flush(s, acc0);
+            flush(s + 1, acc1);
+            flush(s + 2, acc2);
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) { accA += shfl_xor_d(accA, o); accB += shfl_xor_d(accB, o); }
             if (lane == 0) {

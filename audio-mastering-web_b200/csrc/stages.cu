@@ -28,6 +28,12 @@ template <int M> static void fill_filter(FiltK<M>& fk, const FilterPlan* p) {
     for (int i = 0; i < M; ++i) fk.a[i] = p->ba.a[i + 1];
     for (int j = 0; j < kS; ++j)
         for (int i = 0; i < M; ++i) fk.g[j][i] = p->tabs.g[(size_t)j * M + i];
+    for (int i = 0; i < M; ++i) {
+        for (int k = 0; k < M; ++k) fk.A32[i][k] = (float)p->tabs.A[i * M + k];
+        fk.B32[i] = (float)p->tabs.B[i];
+        fk.C32[i] = (float)p->tabs.C[i];
+    }
+    fk.D32 = (float)p->tabs.D;
 }
 
 // Segments per row: minimise  waves * (tiles per segment + halo)  over the segment count.
@@ -48,12 +54,12 @@ static void choose_segments(int rows, int ntiles, int whalo, int capacity, int* 
     *seglen_out = (ntiles + best - 1) / best;
 }
 
-template <int M, int NF, int NIN, int DIR, int EPI, int NAUX, int ST>
+template <int M, int NF, int NIN, int DIR, int EPI, int NAUX, int ST, int NF32>
 static int launch_sweep2(mm_ctx* c, SweepArgs<M, NF>& A, int whalo, const char* name) {
     typedef Sweep2Cfg<M, NF, NIN, DIR, EPI, NAUX, ST> Cfg;
     static int blocks_per_sm = 0;          // per instantiation; one device kind per process
     static int num_sms = 0;
-    auto kern = sweep2_kernel<M, NF, NIN, DIR, EPI, NAUX, ST>;
+    auto kern = sweep2_kernel<M, NF, NIN, DIR, EPI, NAUX, ST, NF32>;
     const size_t smem = Cfg::kBytes;
     if (blocks_per_sm == 0) {
         MM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -65,7 +71,7 @@ static int launch_sweep2(mm_ctx* c, SweepArgs<M, NF>& A, int whalo, const char* 
         MM_CUDA(cudaGetDeviceProperties(&prop, c->device));
         num_sms = prop.multiProcessorCount;
         blocks_per_sm = bps;
-        if (getenv("MM_DEBUG")) fprintf(stderr, "[mm] %s: %zu B smem, %d CTAs/SM x %d SMs\n", name, smem, bps, num_sms);
+        if (getenv("MM_DEBUG")) fprintf(stderr, "[mm] %s (%d float32 sections): %zu B smem, %d CTAs/SM x %d SMs\n", name, NF32, smem, bps, num_sms);
     }
     A.ntiles = DIR > 0 ? tiles_fwd(A.n, A.pad) : tiles_bwd(A.n, A.pad);
     if ((size_t)A.rows * (size_t)A.ntiles == 0) return 0;
@@ -101,16 +107,6 @@ static int launch_sweep2(mm_ctx* c, SweepArgs<M, NF>& A, int whalo, const char* 
     return 0;
 }
 
-// ring depth: the per-kernel default, or MM_ST=1|2 from the environment (tuning experiments)
-static int stage_override(int dflt) {
-    static int forced = -1;
-    if (forced < 0) {
-        const char* e = getenv("MM_ST");
-        forced = e ? atoi(e) : 0;
-    }
-    return (forced == 1 || forced == 2) ? forced : dflt;
-}
-
 static int halo_tiles(const FilterPlan* const* plans, int nf) {
     int w = 1;
     for (int f = 0; f < nf; ++f) w = std::max(w, plans[f]->tabs.W);   // 1e-18: results do not depend on the segmentation
@@ -128,6 +124,20 @@ static void fill_common(SweepArgs<M, NF>& A, const mm_geom* g, const FilterPlan*
         A.in[f] = in[f < nin ? f : nin - 1];
         A.out[f] = out[f < nout ? f : nout - 1];
         A.w[f] = epi.w[f];
+        A.w32[f] = (float)epi.w[f];
+    }
+    if (M == 2) {
+        for (int p = 0; 2 * p + 1 < NF; ++p) {
+            const ScanTables &ta = plans[2 * p]->tabs, &tb = plans[2 * p + 1]->tabs;
+            PairK& k = A.pr[p];
+            for (int i = 0; i < 2; ++i) {
+                for (int j = 0; j < 2; ++j) k.A[i][j] = make_float2((float)ta.A[i * 2 + j], (float)tb.A[i * 2 + j]);
+                k.B[i] = make_float2((float)ta.B[i], (float)tb.B[i]);
+                k.C[i] = make_float2((float)ta.C[i], (float)tb.C[i]);
+                for (int j = 0; j < kS; ++j) k.g[j][i] = make_float2((float)ta.g[(size_t)j * 2 + i], (float)tb.g[(size_t)j * 2 + i]);
+            }
+            k.D = make_float2((float)ta.D, (float)tb.D);
+        }
     }
     A.aux[0] = epi.aux0;
     A.aux[1] = epi.aux1;
@@ -150,25 +160,77 @@ static void fill_common(SweepArgs<M, NF>& A, const mm_geom* g, const FilterPlan*
     A.peak = epi.peak;
 }
 
+// One sweep's sections put in launch order: the float32-pass-2 sections first (the kernel's NF32 counts a
+// prefix).  `allowed` is the bit set of prefix lengths the kernel family is instantiated for; surplus float32
+// sections fall back to their float64 plan.  Streams and weights follow their section unless the epilogue
+// binds positions (dynamics: y0 = band 2, y1 = band 3), in which case it is all or nothing.
+struct Arranged {
+    const FilterPlan* plans[4];
+    const float* in[4];
+    float* out[4];
+    Epi epi;
+    int n32 = 0;
+};
+static int arrange(mm_ctx* c, int nf, const FilterPlan* const* plans, const float* const* in, int nin, float* const* out, int nout,
+                   const Epi& epi, unsigned allowed, bool positional, Arranged* R) {
+    const FilterPlan* pl[4];
+    int n32 = 0;
+    for (int f = 0; f < nf; ++f) { pl[f] = plans[f]; n32 += plans[f]->tabs.mode == kBalancedF32; }
+    int want = n32;
+    while (want > 0 && !((allowed >> want) & 1u)) --want;
+    if (positional && want != nf) want = 0;
+    // demote the float32 sections with the longest-lived state errors first
+    while (n32 > want) {
+        int worst = -1;
+        for (int f = 0; f < nf; ++f)
+            if (pl[f]->tabs.mode == kBalancedF32 && (worst < 0 || pl[f]->tabs.norm2 >= pl[worst]->tabs.norm2)) worst = f;
+        pl[worst] = get_plan_mode(c, pl[worst]->ba, kDf2tF64);
+        if (!pl[worst]) return 1;
+        --n32;
+    }
+    int order[4], k = 0;
+    for (int f = 0; f < nf; ++f) if (pl[f]->tabs.mode == kBalancedF32) order[k++] = f;
+    for (int f = 0; f < nf; ++f) if (pl[f]->tabs.mode != kBalancedF32) order[k++] = f;
+    R->epi = epi;
+    for (int j = 0; j < nf; ++j) {
+        const int f = order[j];
+        R->plans[j] = pl[f];
+        R->in[j] = in[nin == nf ? f : 0];
+        R->out[j] = out[nout == nf ? f : 0];
+        R->epi.w[j] = epi.w[f];
+    }
+    R->n32 = n32;
+    return 0;
+}
+
+template <int M, int NF, int NIN, int DIR, int EPI, int NAUX, int NF32>
+static int run_sweep(mm_ctx* c, const mm_geom* g, const Arranged& R, int nout, const Pro& pro, int pad, const char* name) {
+    SweepArgs<M, NF> A;
+    fill_common<M, NF>(A, g, R.plans, R.in, NIN, R.out, nout, pro, R.epi, pad);
+    return launch_sweep2<M, NF, NIN, DIR, EPI, NAUX, 1, NF32>(c, A, halo_tiles(R.plans, NF), name);
+}
+
 int sweep_fwd(mm_ctx* c, const mm_geom* g, int nf, int nin, const FilterPlan* const* plans, const float* const* in,
               float* const* out, const Pro& pro, int pad) {
     Epi epi;
     const int m = plans[0]->ba.m;
     for (int f = 0; f < nf; ++f)
         if (plans[f]->ba.m != m) { set_error("mixed section orders in one sweep"); return 1; }
-#define MM_FWD(M_, NF_, NIN_, ST_)                                                \
-    {                                                                             \
-        SweepArgs<M_, NF_> A;                                                     \
-        fill_common<M_, NF_>(A, g, plans, in, nin, out, nf, pro, epi, pad);       \
-        if (stage_override(ST_) == 1)                                             \
-            return launch_sweep2<M_, NF_, NIN_, +1, EPI_STORE, 0, 1>(c, A, halo_tiles(plans, nf), "sweep_fwd_m" #M_ "_f" #NF_ "_i" #NIN_); \
-        return launch_sweep2<M_, NF_, NIN_, +1, EPI_STORE, 0, 2>(c, A, halo_tiles(plans, nf), "sweep_fwd_m" #M_ "_f" #NF_ "_i" #NIN_); \
-    }
-    if (m == 2 && nf == 1 && nin == 1) MM_FWD(2, 1, 1, 1)
-    if (m == 2 && nf == 2 && nin == 1) MM_FWD(2, 2, 1, 1)
-    if (m == 2 && nf == 2 && nin == 2) MM_FWD(2, 2, 2, 1)
-    if (m == 2 && nf == 4 && nin == 1) MM_FWD(2, 4, 1, 1)
-    if (m == 4 && nf == 1 && nin == 1) MM_FWD(4, 1, 1, 1)
+    if (nf > 4 || (nin != 1 && nin != nf)) { set_error("forward sweep: %d filters / %d inputs unsupported", nf, nin); return 1; }
+    unsigned allowed = 1u;
+    if (m == 2 && nf == 1) allowed = 0x3;
+    if (m == 2 && nf == 2) allowed = 0x7;
+    if (m == 2 && nf == 4) allowed = 0x15;
+    Arranged R;
+    MM_TRY(arrange(c, nf, plans, in, nin, out, nf, epi, allowed, false, &R));
+#define MM_FWD(M_, NF_, NIN_, N32_) \
+    if (m == M_ && nf == NF_ && nin == NIN_ && R.n32 == N32_) \
+        return run_sweep<M_, NF_, NIN_, +1, EPI_STORE, 0, N32_>(c, g, R, nf, pro, pad, "sweep_fwd_m" #M_ "_f" #NF_ "_i" #NIN_);
+    MM_FWD(2, 1, 1, 0) MM_FWD(2, 1, 1, 1)
+    MM_FWD(2, 2, 1, 0) MM_FWD(2, 2, 1, 1) MM_FWD(2, 2, 1, 2)
+    MM_FWD(2, 2, 2, 0) MM_FWD(2, 2, 2, 1) MM_FWD(2, 2, 2, 2)
+    MM_FWD(2, 4, 1, 0) MM_FWD(2, 4, 1, 2) MM_FWD(2, 4, 1, 4)
+    MM_FWD(4, 1, 1, 0)
 #undef MM_FWD
     set_error("no forward sweep instantiation for order %d, %d filters, %d inputs", m, nf, nin);
     return 1;
@@ -179,33 +241,32 @@ int sweep_bwd(mm_ctx* c, const mm_geom* g, int nf, const FilterPlan* const* plan
     const int m = plans[0]->ba.m;
     const int naux = (epi.mode == EPI_STORE) ? 0 : ((epi.aux1 != nullptr) ? 2 : 1);
     if (epi.mode != EPI_STORE && epi.aux0 == nullptr) { set_error("backward sweep epilogue needs its x-domain stream"); return 1; }
-#define MM_BWD(M_, NF_, EPI_, NAUX_, ST_, TAG_)                                   \
-    {                                                                             \
-        SweepArgs<M_, NF_> A;                                                     \
-        fill_common<M_, NF_>(A, g, plans, in, nf, out, nout, epi.auxp, epi, pad); \
-        if (stage_override(ST_) == 1)                                             \
-            return launch_sweep2<M_, NF_, NF_, -1, EPI_, NAUX_, 1>(c, A, halo_tiles(plans, nf), "sweep_bwd_m" #M_ "_f" #NF_ TAG_); \
-        return launch_sweep2<M_, NF_, NF_, -1, EPI_, NAUX_, 2>(c, A, halo_tiles(plans, nf), "sweep_bwd_m" #M_ "_f" #NF_ TAG_); \
-    }
-    if (m == 2 && nf == 1 && epi.mode == EPI_STORE) MM_BWD(2, 1, EPI_STORE, 0, 1, "_store")
-    if (m == 2 && nf == 1 && epi.mode == EPI_COMBINE && naux == 1) MM_BWD(2, 1, EPI_COMBINE, 1, 1, "_combine")
-    if (m == 2 && nf == 1 && epi.mode == EPI_EXCITER && naux == 1) MM_BWD(2, 1, EPI_EXCITER, 1, 1, "_exciter")
-    if (m == 2 && nf == 2 && epi.mode == EPI_STORE) MM_BWD(2, 2, EPI_STORE, 0, 1, "_store")
-    if (m == 2 && nf == 2 && epi.mode == EPI_COMBINE && naux == 1) MM_BWD(2, 2, EPI_COMBINE, 1, 1, "_combine")
-    if (m == 2 && nf == 2 && epi.mode == EPI_DYNAMICS && naux == 2) MM_BWD(2, 2, EPI_DYNAMICS, 2, 1, "_dynamics")
-    if (m == 2 && nf == 2 && epi.mode == EPI_DYNAMICS_GEN && naux == 2) MM_BWD(2, 2, EPI_DYNAMICS_GEN, 2, 1, "_dynamics_gen")
-    if (m == 2 && nf == 4 && epi.mode == EPI_COMBINE && naux == 1) {
-        SweepArgs<2, 4> A;
-        fill_common<2, 4>(A, g, plans, in, nf, out, nout, epi.auxp, epi, pad);
-        return launch_sweep2<2, 4, 4, -1, EPI_COMBINE, 1, 1>(c, A, halo_tiles(plans, nf), "sweep_bwd_m2_f4_combine");
-    }
-    if (m == 4 && nf == 1 && epi.mode == EPI_STORE) MM_BWD(4, 1, EPI_STORE, 0, 1, "_store")
-#undef MM_BWD
+    if (nf > 4) { set_error("backward sweep: %d filters unsupported", nf); return 1; }
     if (m == 2 && nf == 4 && epi.mode == EPI_STORE && nout == 4) {
-        // four independent sections: two 2-section sweeps move the same bytes and fit two CTAs per SM
+        // four independent sections: two 2-section sweeps move the same bytes and fit more CTAs per SM
         MM_TRY(sweep_bwd(c, g, 2, plans, in, out, 2, epi, pad));
         return sweep_bwd(c, g, 2, plans + 2, in + 2, out + 2, 2, epi, pad);
     }
+    const bool positional = epi.mode == EPI_DYNAMICS || epi.mode == EPI_DYNAMICS_GEN;
+    unsigned allowed = 1u;
+    if (m == 2 && nf == 1) allowed = 0x3;
+    if (m == 2 && nf == 2) allowed = (epi.mode == EPI_STORE) ? 0x7 : 0x5;
+    if (m == 2 && nf == 4) allowed = 0x11;
+    Arranged R;
+    MM_TRY(arrange(c, nf, plans, in, nf, out, nout, epi, allowed, positional, &R));
+#define MM_BWD(M_, NF_, EPI_, NAUX_, N32_, TAG_) \
+    if (m == M_ && nf == NF_ && epi.mode == EPI_ && naux == NAUX_ && R.n32 == N32_) \
+        return run_sweep<M_, NF_, NF_, -1, EPI_, NAUX_, N32_>(c, g, R, nout, epi.auxp, pad, "sweep_bwd_m" #M_ "_f" #NF_ TAG_);
+    MM_BWD(2, 1, EPI_STORE, 0, 0, "_store") MM_BWD(2, 1, EPI_STORE, 0, 1, "_store")
+    MM_BWD(2, 1, EPI_COMBINE, 1, 0, "_combine") MM_BWD(2, 1, EPI_COMBINE, 1, 1, "_combine")
+    MM_BWD(2, 1, EPI_EXCITER, 1, 0, "_exciter") MM_BWD(2, 1, EPI_EXCITER, 1, 1, "_exciter")
+    MM_BWD(2, 2, EPI_STORE, 0, 0, "_store") MM_BWD(2, 2, EPI_STORE, 0, 1, "_store") MM_BWD(2, 2, EPI_STORE, 0, 2, "_store")
+    MM_BWD(2, 2, EPI_COMBINE, 1, 0, "_combine") MM_BWD(2, 2, EPI_COMBINE, 1, 2, "_combine")
+    MM_BWD(2, 2, EPI_DYNAMICS, 2, 0, "_dynamics") MM_BWD(2, 2, EPI_DYNAMICS, 2, 2, "_dynamics")
+    MM_BWD(2, 2, EPI_DYNAMICS_GEN, 2, 0, "_dynamics_gen") MM_BWD(2, 2, EPI_DYNAMICS_GEN, 2, 2, "_dynamics_gen")
+    MM_BWD(2, 4, EPI_COMBINE, 1, 0, "_combine") MM_BWD(2, 4, EPI_COMBINE, 1, 4, "_combine")
+    MM_BWD(4, 1, EPI_STORE, 0, 0, "_store")
+#undef MM_BWD
     set_error("no backward sweep instantiation for order %d, %d filters, epilogue %d, %d aux", m, nf, epi.mode, naux);
     return 1;
 }
@@ -213,12 +274,12 @@ int sweep_bwd(mm_ctx* c, const mm_geom* g, int nf, const FilterPlan* const* plan
 // ---------------------------------------------------------------------------------------------------
 // plans
 // ---------------------------------------------------------------------------------------------------
-const FilterPlan* plan_butter(mm_ctx* c, int order, BType bt, double w0, double w1) {
+const FilterPlan* plan_butter(mm_ctx* c, int order, BType bt, double w0, double w1, int prec) {
     Ba ba;
     memset(&ba, 0, sizeof(ba));
     double wn[2] = {w0, w1};
     if (!butter(order, bt, wn, &ba)) { set_error("butter(%d, [%g, %g], type %d): bad critical frequencies", order, w0, w1, (int)bt); return nullptr; }
-    return get_plan(c, ba);
+    return get_plan(c, ba, prec);
 }
 
 int get_bufs(mm_ctx* c, const mm_geom* g, Bufs* B) {
@@ -388,8 +449,8 @@ int st_target_curve(mm_ctx* c, const mm_geom* g, const float* in, float* out, co
     const FilterPlan* hp = plan_butter(c, 2, kHigh, std::min(40.0 / nyq, 0.99), 0);
     const FilterPlan* lp = plan_butter(c, 2, kLow, std::min(18000.0 / nyq, 0.99), 0);
     const double fp = std::min(3000.0 / nyq, 0.99), fm = std::min(300.0 / nyq, 0.99);
-    const FilterPlan* pres = plan_butter(c, 1, kBand, fp * 0.7, fp * 1.3);
-    const FilterPlan* mud = plan_butter(c, 1, kBand, fm * 0.7, fm * 1.3);
+    const FilterPlan* pres = plan_butter(c, 1, kBand, fp * 0.7, fp * 1.3, PREC_F32);   // enter through weights of 0.04 / 0.03
+    const FilterPlan* mud = plan_butter(c, 1, kBand, fm * 0.7, fm * 1.3, PREC_F32);
     if (!hp || !lp || !pres || !mud) return 1;
     MM_TRY(need_len(g, 9, "apply_target_curve"));
     Bufs B;
@@ -499,9 +560,8 @@ int st_lufs(mm_ctx* c, const mm_geom* g, const float* in, const Pro& pro, double
     unsigned long long* segsum;
     MM_TRY(arena(c, SL_SEGSUM, (size_t)rows * (size_t)std::max(lp->nseg, 1), &segsum));
     if (lp->valid) {
-        const FilterPlan* k0 = get_plan(c, k_weighting_stage(0, (double)g->sr));
-        const FilterPlan* k1 = get_plan(c, k_weighting_stage(1, (double)g->sr));
-        if (!k0 || !k1) return 1;
+        const KwPlan* kw = get_kw_plan(c, g->sr);
+        if (!kw) return 1;
         MM_CUDA(cudaMemsetAsync(segsum, 0, (size_t)rows * lp->nseg * sizeof(unsigned long long), c->stream));
         static int capacity = 0;
         if (capacity == 0) {
@@ -512,17 +572,25 @@ int st_lufs(mm_ctx* c, const mm_geom* g, const float* in, const Pro& pro, double
             cudaDeviceProp prop;
             MM_CUDA(cudaGetDeviceProperties(&prop, c->device));
             capacity = std::max(1, bps) * prop.multiProcessorCount;
+            if (getenv("MM_DEBUG")) fprintf(stderr, "[mm] lufs_kernel: %d B smem, %d CTAs/SM\n", kLufsSmem, bps);
         }
         LufsArgs A;
         memset(&A, 0, sizeof(A));
-        fill_filter<2>(A.f[0], k0);
-        fill_filter<2>(A.f[1], k1);
-        A.tab[0] = k0->dev; A.tab[1] = k1->dev;
+        for (int i = 0; i < 2; ++i) {
+            for (int k = 0; k < 2; ++k) A.k.A[i][k] = make_float2((float)kw->sec[0].A[i * 2 + k], (float)kw->sec[1].A[i * 2 + k]);
+            A.k.B[i] = make_float2((float)kw->sec[0].B[i], (float)kw->sec[1].B[i]);
+            A.k.C[i] = make_float2((float)kw->sec[0].C[i], (float)kw->sec[1].C[i]);
+        }
+        A.k.D = make_float2((float)kw->sec[0].D, (float)kw->sec[1].D);
+        for (int j = 0; j < kS; ++j) {
+            A.k.g[j][0] = make_float2((float)kw->tabs.g[(size_t)j * 4 + 0], (float)kw->tabs.g[(size_t)j * 4 + 1]);
+            A.k.g[j][1] = make_float2((float)kw->tabs.g[(size_t)j * 4 + 2], (float)kw->tabs.g[(size_t)j * 4 + 3]);
+        }
+        A.tab = kw->dev;
         A.in = in; A.n = g->n; A.stride = g->stride; A.rows = rows; A.ntiles = lp->ntiles; A.channels = g->channels;
         A.pro_mode = pro.mode; A.pro_sub = pro.sub; A.pro_mul = pro.mul;
         A.bnd = lp->bnd; A.nhop = lp->nseg; A.tile_seg = lp->tile_seg; A.segsum = segsum;
-        // the high-pass forgets its own start-up in W1 tiles, but is fed the shelf's start-up for W0 tiles first
-        A.whalo = k0->tabs.W + k1->tabs.W;
+        A.whalo = kw->tabs.W;
         choose_segments(rows, lp->ntiles, A.whalo, capacity, &A.nseg, &A.seglen);
         const long long items = (long long)rows * A.nseg;
         const unsigned grid = (unsigned)std::min<long long>(items, capacity);
@@ -550,10 +618,10 @@ int st_lufs(mm_ctx* c, const mm_geom* g, const float* in, const Pro& pro, double
 int st_final_balance(mm_ctx* c, const mm_geom* g, const float* in, float* out, const Pro& pro, float* peak) {
     const double nyq = g->sr / 2.0;
     const double f3 = std::min(3000.0 / nyq, 0.99), f8 = std::min(8000.0 / nyq, 0.99);
-    const FilterPlan* p3 = plan_butter(c, 1, kBand, f3 * 0.8, f3 * 1.2);
-    const FilterPlan* p16 = plan_butter(c, 2, kHigh, std::min(16000.0 / nyq, 0.99), 0);
-    const FilterPlan* plo = plan_butter(c, 2, kLow, std::min(180.0 / nyq, 0.99), 0);
-    const FilterPlan* p8 = plan_butter(c, 1, kBand, f8 * 0.8, f8 * 1.2);
+    const FilterPlan* p3 = plan_butter(c, 1, kBand, f3 * 0.8, f3 * 1.2, PREC_F32);      // all four enter through weights <= 0.015
+    const FilterPlan* p16 = plan_butter(c, 2, kHigh, std::min(16000.0 / nyq, 0.99), 0, PREC_F32);
+    const FilterPlan* plo = plan_butter(c, 2, kLow, std::min(180.0 / nyq, 0.99), 0, PREC_F32);
+    const FilterPlan* p8 = plan_butter(c, 1, kBand, f8 * 0.8, f8 * 1.2, PREC_F32);
     if (!p3 || !p16 || !plo || !p8) return 1;
     MM_TRY(need_len(g, 9, "apply_final_spectral_balance"));
     Bufs B;
@@ -615,12 +683,13 @@ int st_style_eq(mm_ctx* c, const mm_geom* g, const float* in, float* out, const 
         if (std::fabs(gain_db[b]) < 0.05) continue;
         const double l = std::min(lo[b] / nyq, 0.98), h = std::min(hi[b] / nyq, 0.98);
         if (l >= h) continue;
-        const FilterPlan* p = plan_butter(c, 1, kBand, l, h);
+        const double wb = std::pow(10.0, gain_db[b] / 20.0) - 1.0;
+        const FilterPlan* p = plan_butter(c, 1, kBand, l, h, std::fabs(wb) <= 0.3 ? PREC_F32 : PREC_AUTO);
         if (!p) return 1;
         Epi e;
         e.mode = EPI_COMBINE;
         e.aux0 = cur;
-        e.w[0] = std::pow(10.0, gain_db[b] / 20.0) - 1.0;
+        e.w[0] = wb;
         e.peak = (b == last) ? peak : nullptr;
         if (e.peak && reset_peak) MM_CUDA(cudaMemsetAsync(peak, 0, (size_t)g->tracks * sizeof(float), c->stream));
         Pro none;
@@ -638,7 +707,7 @@ int st_style_eq(mm_ctx* c, const mm_geom* g, const float* in, float* out, const 
 // apply_harmonic_exciter, oversample == 1 (backend/app/pipeline.py:1267-1326)
 int st_exciter(mm_ctx* c, const mm_geom* g, const float* in, float* out, double exciter_db, int mode, float* peak) {
     const double nyq = g->sr / 2.0;
-    const FilterPlan* p = plan_butter(c, 2, kHigh, std::min(6000.0 / nyq, 0.97), 0);
+    const FilterPlan* p = plan_butter(c, 2, kHigh, std::min(6000.0 / nyq, 0.97), 0, PREC_F32);   // side chain, scaled by (10^(dB/20) - 1) / 4
     if (!p) return 1;
     Epi e;
     e.mode = EPI_EXCITER;

@@ -31,7 +31,7 @@ struct Bufs { float* E[4]; float* T[5]; };
 
 int check_geom(const mm_geom* g);
 int get_bufs(mm_ctx* c, const mm_geom* g, Bufs* B);
-const FilterPlan* plan_butter(mm_ctx* c, int order, BType bt, double w0, double w1);
+const FilterPlan* plan_butter(mm_ctx* c, int order, BType bt, double w0, double w1, int prec = PREC_AUTO);
 
 int sweep_fwd(mm_ctx* c, const mm_geom* g, int nf, int nin, const FilterPlan* const* plans, const float* const* in,
               float* const* out, const Pro& pro, int pad);

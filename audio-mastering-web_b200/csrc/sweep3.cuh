@@ -96,7 +96,9 @@ __device__ __forceinline__ float pro1(int mode, float x, float subf, float mulf,
     return x;
 }
 
-template <int M, int NF, int NIN, int DIR, int EPI, int NAUX, int ST>
+// NF32: the first NF32 sections run pass 2 in float32 on their balanced realization (tables and g in those
+// coordinates), the others in float64 DF2T.  Pass 1 and the scan are float64 for both.
+template <int M, int NF, int NIN, int DIR, int EPI, int NAUX, int ST, int NF32>
 __global__ void __launch_bounds__(kT, Sweep2Cfg<M, NF, NIN, DIR, EPI, NAUX, ST>::kMinBlocks) sweep2_kernel(const __grid_constant__ Sweep2Args<M, NF> PP) {
     typedef Sweep2Cfg<M, NF, NIN, DIR, EPI, NAUX, ST> Cfg;
     const SweepArgs<M, NF>& P = PP.a;
@@ -285,11 +287,17 @@ __global__ void __launch_bounds__(kT, Sweep2Cfg<M, NF, NIN, DIR, EPI, NAUX, ST>:
         // address of logical vec u of this chunk in stream buffer b: b + cbase + ((4u) ^ cx)
 
         // ---- pass 1 -----------------------------------------------------------------------------------
+        // packed float32 sections (pairs 2p, 2p+1 below 2 NP) accumulate their zero-state end states in float32
+        // too: the balanced coordinates keep that as accurate as the float32 pass 2 itself (design.h)
+        constexpr int NP = (M == 2) ? NF32 / 2 : 0;
         double E[NF][M];
 #pragma unroll
         for (int f = 0; f < NF; ++f)
 #pragma unroll
             for (int i = 0; i < M; ++i) E[f][i] = 0.0;
+        float2 Ep[NP > 0 ? NP : 1][2];
+#pragma unroll
+        for (int p = 0; p < NP; ++p) Ep[p][0] = Ep[p][1] = make_float2(0.f, 0.f);
 #pragma unroll
         for (int u = 0; u < kS / 4; ++u) {
             const int uu = (DIR > 0) ? u : (kS / 4 - 1 - u);
@@ -310,14 +318,24 @@ __global__ void __launch_bounds__(kT, Sweep2Cfg<M, NF, NIN, DIR, EPI, NAUX, ST>:
             for (int c = 0; c < 4; ++c) {
                 const int cc = (DIR > 0) ? c : (3 - c);
                 const int j = 4 * u + c;
-                double xd[NIN];
 #pragma unroll
-                for (int s = 0; s < NIN; ++s) xd[s] = f2d_bits(comp4(xv[s], cc));
+                for (int p = 0; p < NP; ++p) {
+                    const float2 X = make_float2(comp4(xv[NIN == 1 ? 0 : 2 * p], cc), comp4(xv[NIN == 1 ? 0 : 2 * p + 1], cc));
+                    Ep[p][0] = ffma2(P.pr[p].g[j][0], X, Ep[p][0]);
+                    Ep[p][1] = ffma2(P.pr[p].g[j][1], X, Ep[p][1]);
+                }
 #pragma unroll
-                for (int f = 0; f < NF; ++f)
+                for (int f = 2 * NP; f < NF; ++f) {
+                    const double xd = f2d_bits(comp4(xv[NIN == 1 ? 0 : f], cc));
 #pragma unroll
-                    for (int i = 0; i < M; ++i) E[f][i] = fma(P.f[f].g[j][i], xd[NIN == 1 ? 0 : f], E[f][i]);
+                    for (int i = 0; i < M; ++i) E[f][i] = fma(P.f[f].g[j][i], xd, E[f][i]);
+                }
             }
+        }
+#pragma unroll
+        for (int p = 0; p < NP; ++p) {
+            E[2 * p][0] = (double)Ep[p][0].x; E[2 * p + 1][0] = (double)Ep[p][0].y;
+            E[2 * p][M > 1 ? 1 : 0] = (double)Ep[p][1].x; E[2 * p + 1][M > 1 ? 1 : 0] = (double)Ep[p][1].y;
         }
         if (inj_thread) {
             // scipy's filtfilt start: state zi * x_first, injected `d0` samples into this chunk
@@ -439,36 +457,58 @@ __global__ void __launch_bounds__(kT, Sweep2Cfg<M, NF, NIN, DIR, EPI, NAUX, ST>:
             par_one_minus = (float)(1.0 - mixd);      // Python float (1.0 - mix), then weak-cast to float32
         }
         float pk = 0.f;
-        // one output element of a recombining epilogue; y[] are this sample's section outputs in float64
-        auto epi_value = [&](float xa_raw, float a1c, const double (&y)[NF]) -> float {
+        // one output element of a recombining epilogue; this sample's section outputs are yf[f] (float32 sections,
+        // f < NF32) and yd[f] (float64 sections)
+        auto epi_value = [&](float xa_raw, float a1c, const float (&yf)[NF], const double (&yd)[NF]) -> float {
             float xa = xa_raw;
             if (P.aux_pro) xa = pro1(P.pro_mode, xa, aux_subf, aux_mulf, aux_muld);
+            auto yflt = [&](int f) -> float { return f < NF32 ? yf[f] : (float)yd[f]; };
             if (EPI == EPI_COMBINE) {
-                // pipeline.py:273 / :603-606 / :1431: float64 recombination, one cast to float32
+                // pipeline.py:273 / :603-606 / :1431: float64 recombination, one cast to float32.  The float32
+                // sections enter through their (small) weights: their weighted sum is formed in float32 and
+                // widened once
                 double acc = P.wc * (double)xa;
+                if (NF32 > 0) {
+                    float accf = 0.f;
 #pragma unroll
-                for (int f = 0; f < NF; ++f) acc = fma(P.w[f], y[f], acc);
+                    for (int f = 0; f < NF32; ++f) accf = fmaf(P.w32[f], yf[f], accf);
+                    acc += (double)accf;
+                }
+#pragma unroll
+                for (int f = NF32; f < NF; ++f) acc = fma(P.w[f], yd[f], acc);
                 return (float)(acc * P.trim);
             } else if (EPI == EPI_EXCITER) {
-                const float hf = (float)y[0];
+                const float hf = yflt(0);
                 const float sat = exciter_sat(hf, P.exc_mode, (float)P.exc_k);
                 return (float)fma((double)(sat - hf), P.exc_gain * 0.25, (double)xa);
             } else if (EPI == EPI_DYNAMICS) {   // aux0 = band 1, y0 = band 2, y1 = band 3, aux1 = band 4; downward knees only
                 float sacc = band_chain(xa, P.dyn.band[0]);
-                sacc = __fadd_rn(sacc, band_chain((float)y[0], P.dyn.band[1]));
-                sacc = __fadd_rn(sacc, band_chain((float)y[NF > 1 ? 1 : 0], P.dyn.band[2]));
+                sacc = __fadd_rn(sacc, band_chain(yflt(0), P.dyn.band[1]));
+                sacc = __fadd_rn(sacc, band_chain(yflt(NF > 1 ? 1 : 0), P.dyn.band[2]));
                 sacc = __fadd_rn(sacc, band_chain(a1c, P.dyn.band[3]));
                 return maximize_limit(sacc, P.dyn);
             } else {                             // EPI_DYNAMICS_GEN: upward bands and/or the v1 parallel compressor
                 float sacc = band_chain_gen(xa, P.dyn.band[0]);
-                sacc = __fadd_rn(sacc, band_chain_gen((float)y[0], P.dyn.band[1]));
-                sacc = __fadd_rn(sacc, band_chain_gen((float)y[NF > 1 ? 1 : 0], P.dyn.band[2]));
+                sacc = __fadd_rn(sacc, band_chain_gen(yflt(0), P.dyn.band[1]));
+                sacc = __fadd_rn(sacc, band_chain_gen(yflt(NF > 1 ? 1 : 0), P.dyn.band[2]));
                 sacc = __fadd_rn(sacc, band_chain_gen(a1c, P.dyn.band[3]));
                 float res = maximize_limit(sacc, P.dyn);
                 if (par_mix >= 0.01f) res = parallel_compress(res, par_mix, par_one_minus, P.dyn);
                 return res;
             }
         };
+        // float32 sections start every chunk from the float64-resolved state
+        float sf[NF32 > 0 ? NF32 : 1][M];
+#pragma unroll
+        for (int f = 0; f < NF32; ++f)
+#pragma unroll
+            for (int i = 0; i < M; ++i) sf[f][i] = (float)z[f][i];
+        float2 S0[NP > 0 ? NP : 1], S1[NP > 0 ? NP : 1];
+#pragma unroll
+        for (int p = 0; p < NP; ++p) {
+            S0[p] = make_float2(sf[2 * p][0], sf[2 * p + 1][0]);
+            S1[p] = make_float2(sf[2 * p][M > 1 ? 1 : 0], sf[2 * p + 1][M > 1 ? 1 : 0]);
+        }
         if (!inj_thread) {
             // a recombining epilogue keeps the loop rolled (2 float4 groups in flight): fully unrolled, the
             // hoisted aux / input loads cost ~100 extra registers and halve the occupancy
@@ -486,17 +526,26 @@ __global__ void __launch_bounds__(kT, Sweep2Cfg<M, NF, NIN, DIR, EPI, NAUX, ST>:
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
                     const int cc = (DIR > 0) ? c : (3 - c);
-                    double xd[NIN];
+                    float yf[NF];
+                    double yd[NF];
 #pragma unroll
-                    for (int s = 0; s < NIN; ++s) xd[s] = f2d_bits(comp4(xv[s], cc));
-                    double y[NF];
+                    for (int p = 0; p < NP; ++p) {
+                        const float2 X = make_float2(comp4(xv[NIN == 1 ? 0 : 2 * p], cc), comp4(xv[NIN == 1 ? 0 : 2 * p + 1], cc));
+                        const float2 Y = pair_step(P.pr[p], X, S0[p], S1[p]);
+                        yf[2 * p] = Y.x; yf[2 * p + 1] = Y.y;
+                        yd[2 * p] = 0.0; yd[2 * p + 1] = 0.0;
+                    }
 #pragma unroll
-                    for (int f = 0; f < NF; ++f) y[f] = df2t_step<M>(P.f[f], xd[NIN == 1 ? 0 : f], z[f]);
+                    for (int f = 2 * NP; f < NF; ++f) {
+                        const float xs = comp4(xv[NIN == 1 ? 0 : f], cc);
+                        if (f < NF32) { yf[f] = ss32_step<M>(P.f[f], xs, sf[f < NF32 ? f : 0]); yd[f] = 0.0; }
+                        else { yd[f] = df2t_step<M>(P.f[f], f2d_bits(xs), z[f]); yf[f] = 0.f; }
+                    }
                     if (EPI == EPI_STORE) {
 #pragma unroll
-                        for (int f = 0; f < NF; ++f) setcomp4(yv[f < NOUT ? f : 0], cc, (float)y[f]);
+                        for (int f = 0; f < NF; ++f) setcomp4(yv[f < NOUT ? f : 0], cc, f < NF32 ? yf[f] : (float)yd[f]);
                     } else {
-                        const float res = epi_value(comp4(a0, cc), comp4(a1, cc), y);
+                        const float res = epi_value(comp4(a0, cc), comp4(a1, cc), yf, yd);
                         setcomp4(yv[0], cc, res);
                         if (out_fast) pk = fmaxf(pk, fabsf(res));
                         else {
@@ -521,16 +570,24 @@ __global__ void __launch_bounds__(kT, Sweep2Cfg<M, NF, NIN, DIR, EPI, NAUX, ST>:
 #pragma unroll
                     for (int f = 0; f < NF; ++f)
 #pragma unroll
-                        for (int i = 0; i < M; ++i) z[f][i] = __ldg(P.tab[f] + Tab<M>::Zi + i) * (double)xs[NIN == 1 ? 0 : f];
+                        for (int i = 0; i < M; ++i) {
+                            z[f][i] = __ldg(P.tab[f] + Tab<M>::Zi + i) * (double)xs[NIN == 1 ? 0 : f];
+                            if (f < NF32) sf[f < NF32 ? f : 0][i] = (float)z[f][i];
+                        }
                 }
-                double y[NF];
+                float yf[NF];
+                double yd[NF];
 #pragma unroll
-                for (int f = 0; f < NF; ++f) y[f] = df2t_step<M>(P.f[f], (double)xs[NIN == 1 ? 0 : f], z[f]);
+                for (int f = 0; f < NF; ++f) {
+                    const float xq = xs[NIN == 1 ? 0 : f];
+                    if (f < NF32) { yf[f] = ss32_step<M>(P.f[f], xq, sf[f < NF32 ? f : 0]); yd[f] = 0.0; }
+                    else { yd[f] = df2t_step<M>(P.f[f], (double)xq, z[f]); yf[f] = 0.f; }
+                }
                 if (EPI == EPI_STORE) {
 #pragma unroll
-                    for (int f = 0; f < NF; ++f) tout[f][off] = (float)y[f];
+                    for (int f = 0; f < NF; ++f) tout[f][off] = f < NF32 ? yf[f] : (float)yd[f];
                 } else {
-                    const float res = epi_value(NAUX > 0 ? auxs[off] : 0.f, NAUX > 1 ? auxs[kL + off] : 0.f, y);
+                    const float res = epi_value(NAUX > 0 ? auxs[off] : 0.f, NAUX > 1 ? auxs[kL + off] : 0.f, yf, yd);
                     tout[0][off] = res;
                     const long long q = tile_lo + cbase + mi;
                     if (q >= st_lo && q <= st_hi) pk = fmaxf(pk, fabsf(res));

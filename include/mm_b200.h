@@ -197,6 +197,13 @@ int mm_design_k_weighting(int stage, double rate, double* b, double* a);
 int mm_design_scan_tables(const double* b, const double* a, int ncoef, double* g, double* Pw, double* Plane,
                           double* Qpow, double* Mpow, int cap_w, double* Apow, double* zi, int* S, int* T);
 
+/* The same tables in a chosen realization: mode 0 = float64 DF2T (as above), 1 = the internally balanced
+ * realization whose per-chunk recurrence the kernels evaluate in float32 (EQ-weighted sections, sections with
+ * cut-offs above ~1 kHz, the loudness meter).  ss receives [A (m*m), B (m), C (m), D, ||A_balanced||_2]:
+ * s[n] = A s[n-1] + B x[n], y[n] = C s[n-1] + D x[n]; zi is expressed in the same coordinates. */
+int mm_design_scan_tables2(const double* b, const double* a, int ncoef, int mode, double* g, double* Pw, double* Plane,
+                           double* Qpow, double* Mpow, int cap_w, double* Apow, double* zi, double* ss);
+
 #ifdef __cplusplus
 }
 #endif

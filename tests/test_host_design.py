@@ -183,3 +183,94 @@ def test_scan_tables_replay_equals_lfilter(lib, design):
     ref, _ = sg.lfilter(b, a, x, zi=sg.lfilter_zi(b, a) * x[0])
     assert tb["W"] >= 1
     assert np.max(np.abs(y - ref)) <= 1e-10 * max(1.0, np.max(np.abs(ref))), (design, tb["W"], np.max(np.abs(y - ref)))
+
+
+# ---- float32 pass 2 on the balanced realization (csrc/sweep3.cuh NF32 sections, csrc/lufs_kernel.cuh) ----------
+def _tables2(lib, b, a, mode):
+    from mm_b200 import _lib
+    m = len(b) - 1
+    mm2 = m * m
+    g = (C.c_double * (32 * m))()
+    Plane = (C.c_double * (32 * mm2))()
+    Apow = (C.c_double * (33 * mm2))()
+    zi = (C.c_double * m)()
+    ss = (C.c_double * (mm2 + 2 * m + 2))()
+    W = lib.mm_design_scan_tables2(_lib.darr(b), _lib.darr(a), len(b), mode, g, None, Plane, None, None, 0, Apow, zi, ss)
+    assert W > 0, _lib.last_error()
+    ssv = np.array(ss[:])
+    return dict(m=m, W=W, g=np.array(g[:]).reshape(32, m), Plane=np.array(Plane[:]).reshape(32, m, m),
+                Apow=np.array(Apow[:]).reshape(33, m, m), zi=np.array(zi[:]), A=ssv[:mm2].reshape(m, m), B=ssv[mm2:mm2 + m],
+                C=ssv[mm2 + m:mm2 + 2 * m], D=ssv[mm2 + 2 * m], norm2=ssv[mm2 + 2 * m + 1])
+
+
+def _chunked_f32_pass2(tb, x, zi_scale):
+    """Chunk-start states exactly as the float64 scan resolves them (here: a float64 run of the realization),
+    then the float32 recurrence of ss32_step inside every 32-sample chunk."""
+    A, B, Cv, D = tb["A"], tb["B"], tb["C"], tb["D"]
+    n = len(x)
+    s = tb["zi"] * zi_scale
+    starts = np.zeros((n // 32 + 1, tb["m"]))
+    for i in range(n):
+        if i % 32 == 0:
+            starts[i // 32] = s
+        s = A @ s + B * x[i]
+    A32, B32, C32, D32 = A.astype(np.float32), B.astype(np.float32), Cv.astype(np.float32), np.float32(D)
+    y = np.zeros(n, np.float32)
+    x32 = x.astype(np.float32)
+    for c0 in range(0, n, 32):
+        sf = starts[c0 // 32].astype(np.float32)
+        for i in range(c0, min(c0 + 32, n)):
+            acc = np.float32(D32 * x32[i])
+            for k in range(tb["m"] - 1, -1, -1):
+                acc = np.float32(np.float64(C32[k]) * np.float64(sf[k]) + np.float64(acc))      # fmaf
+            y[i] = acc
+            sn = np.zeros_like(sf)
+            for r in range(tb["m"]):
+                t = np.float32(B32[r] * x32[i])
+                for k in range(tb["m"]):
+                    t = np.float32(np.float64(A32[r, k]) * np.float64(sf[k]) + np.float64(t))   # fmaf
+                sn[r] = t
+            sf = sn
+    return y
+
+
+@pytest.mark.parametrize("design,tol", [("lp18k_44k", 2.5e-7), ("hp2230_96k", 4e-7), ("hp10k_48k", 2.5e-7), ("bp_pres_44k", 3e-7),
+                                        ("hp40_96k", 2.5e-6), ("lp180_48k", 2.5e-6), ("kw_shelf_48k", 5e-7), ("kw_hp38_44k", 2.5e-6)])
+def test_balanced_realization_float32_pass2(lib, design, tol):
+    """The balanced realization is the same filter (float64), a contraction (||A||_2 <= 1), and its float32
+    per-chunk recurrence stays within `tol` of scipy's float64 lfilter on a loud mix of 55 Hz + 3 kHz + noise:
+    ~1e-7 where state errors die inside a chunk, ~1e-6 for the low cut-offs (which the kernels only run in
+    float32 behind recombination weights <= 0.3 or inside the loudness meter)."""
+    from oracle import bs1770
+    b, a = {
+        "lp18k_44k": sg.butter(2, 18000 / 22050, "low"), "hp2230_96k": sg.butter(2, 2230 / 48000, "high"),
+        "hp10k_48k": sg.butter(2, 10000 / 24000, "high"), "bp_pres_44k": sg.butter(1, [2100 / 22050, 3900 / 22050], "band"),
+        "hp40_96k": sg.butter(2, 40 / 48000, "high"), "lp180_48k": sg.butter(2, 180 / 24000, "low"),
+        "kw_shelf_48k": bs1770.k_weighting_coeffs(48000)[0], "kw_hp38_44k": bs1770.k_weighting_coeffs(44100)[1],
+    }[design]
+    sr = {"44k": 44100, "48k": 48000, "96k": 96000}[design.rsplit("_", 1)[1]]
+    tb = _tables2(lib, b, a, 1)
+    td = _tables2(lib, b, a, 0)
+    assert tb["norm2"] <= 1.0 + 1e-12 and abs(td["norm2"] - tb["norm2"]) < 1e-9
+    assert np.allclose(np.linalg.eigvals(tb["A"]), np.linalg.eigvals(td["A"]), atol=1e-9) or \
+        np.allclose(sorted(np.linalg.eigvals(tb["A"]), key=lambda v: (v.real, v.imag)),
+                    sorted(np.linalg.eigvals(td["A"]), key=lambda v: (v.real, v.imag)), atol=1e-7)
+    # g and Plane are expressed in the balanced coordinates
+    assert np.allclose(tb["g"][31], tb["B"], rtol=1e-12, atol=1e-15)
+    assert np.allclose(tb["g"][30], tb["A"] @ tb["B"], rtol=1e-10, atol=1e-15)
+    assert np.allclose(tb["Plane"][1], np.linalg.matrix_power(tb["A"], 32), rtol=1e-9, atol=1e-14)
+    rng = np.random.default_rng(5)
+    n = 32 * 900
+    t = np.arange(n) / sr
+    x = (0.5 * np.sin(2 * np.pi * 55 * t) + 0.3 * np.sin(2 * np.pi * 3000 * t) + 0.05 * rng.standard_normal(n)).astype(np.float32).astype(np.float64)
+    ref, _ = sg.lfilter(b, a, x, zi=sg.lfilter_zi(b, a) * x[0])
+    # float64 run of the realization == the filter (including the mapped zi)
+    s = tb["zi"] * x[0]
+    y64 = np.zeros(n)
+    for i in range(n):
+        y64[i] = tb["C"] @ s + tb["D"] * x[i]
+        s = tb["A"] @ s + tb["B"] * x[i]
+    assert np.max(np.abs(y64 - ref)) < 1e-10
+    y32 = _chunked_f32_pass2(tb, x, x[0])
+    err = np.max(np.abs(y32.astype(np.float64) - ref))
+    assert err <= tol, (design, err)
