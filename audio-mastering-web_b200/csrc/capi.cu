@@ -292,6 +292,8 @@ void mm_ctx_destroy(mm_ctx* c) {
         cudaFree(kv.second.bnd); cudaFree(kv.second.tile_seg); cudaFree(kv.second.blk_lo); cudaFree(kv.second.blk_hi);
     }
     for (auto& k : c->ktimes) { cudaEventDestroy(k.a); cudaEventDestroy(k.b); }
+    if (c->h2d_stream) cudaStreamDestroy(c->h2d_stream);
+    if (c->d2h_stream) cudaStreamDestroy(c->d2h_stream);
     if (c->own_stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -603,7 +605,7 @@ int mm_dev_quantize_int16(mm_ctx* c, const mm_geom* g, const float* in, int16_t*
     MM_TRY(check_geom(g));
     QuantArgs Q;
     Q.in = in; Q.n = g->n; Q.stride = g->stride; Q.tracks = g->tracks; Q.channels = g->channels;
-    Q.pcm = pcm; Q.noise = noise; Q.seed = seed;
+    Q.pcm = pcm; Q.noise = noise; Q.seed = seed; Q.track_base = g->track_base;
     return run_quantize(c, Q);
 }
 
@@ -631,34 +633,102 @@ int mm_dev_master(mm_ctx* c, const mm_geom* g, int chain, const mm_style* styles
     return master_impl(c, g, chain, styles, in, out, pcm, noise, seed, stats_dev, flags);
 }
 
+// Host-buffer entry point.  The batch is cut into chunks of tracks that flow through a three-stage pipeline --
+// host->device copy (copy stream), mastering chain (context stream), device->host copy (second copy stream) -- so
+// that on a PCIe-attached GPU the call costs about max(copy in, compute, copy out) instead of their sum.  Staging
+// buffers are double-buffered per direction; the chain's own workspace is sized for one chunk.  Results do not
+// depend on the chunking: the dither counter is keyed by the track's index in the whole call.
 int mm_master_host(mm_ctx* c, int chain, int32_t tracks, int64_t n, int32_t channels, int32_t sr, const mm_style* styles,
                    const float* audio_in, float* audio_out, int16_t* pcm16_out, const float* noise_host, uint64_t seed,
                    mm_track_stats* stats_host, uint32_t flags) {
     MM_API_BEGIN(c);
     mm_geom g;
-    g.n = n; g.stride = mm_row_stride(n); g.tracks = tracks; g.channels = channels; g.sr = sr; g._pad = 0;
+    g.n = n; g.stride = mm_row_stride(n); g.tracks = tracks; g.channels = channels; g.sr = sr; g.track_base = 0;
     MM_TRY(check_geom(&g));
     if (!audio_in) { set_error("mm_master_host: audio_in is null"); return 1; }
-    const size_t frames = (size_t)tracks * (size_t)n * channels;
-    float *il, *pl, *nz = nullptr;
-    int16_t* pcm = nullptr;
+    if (!c->h2d_stream) MM_CUDA(cudaStreamCreateWithFlags(&c->h2d_stream, cudaStreamNonBlocking));
+    if (!c->d2h_stream) MM_CUDA(cudaStreamCreateWithFlags(&c->d2h_stream, cudaStreamNonBlocking));
+    const size_t per_track = (size_t)n * channels;                  // interleaved samples of one track
+    int tc = 0;                                                     // tracks per chunk: ~512 MB of float32 input
+    if (const char* e = getenv("MM_HOST_CHUNK")) tc = atoi(e);
+    if (tc <= 0) tc = (int)std::max<size_t>(1, ((size_t)512 << 20) / std::max<size_t>(per_track * sizeof(float), 1));
+    tc = std::min(tc, (int)tracks);
+    const int nchunks = (tracks + tc - 1) / tc;
+    const size_t cframes = (size_t)tc * per_track;
+    float *il[2] = {nullptr, nullptr}, *ol[2] = {nullptr, nullptr}, *nz[2] = {nullptr, nullptr}, *pl = nullptr;
+    int16_t* pcm[2] = {nullptr, nullptr};
     mm_track_stats* st = nullptr;
-    MM_TRY(arena(c, SL_STAGE_IL, frames, &il));
-    MM_TRY(arena(c, SL_STAGE_PL, batch_floats(&g), &pl));
-    if (pcm16_out) MM_TRY(arena(c, SL_STAGE_PCM, frames, &pcm));
-    if (noise_host) MM_TRY(arena(c, SL_STAGE_NOISE, frames, &nz));
+    mm_geom gc = g;
+    gc.tracks = tc;
+    MM_TRY(arena(c, SL_STAGE_IL, cframes, &il[0]));
+    if (nchunks > 1) MM_TRY(arena(c, SL_STAGE_IL1, cframes, &il[1]));
+    MM_TRY(arena(c, SL_STAGE_PL, batch_floats(&gc), &pl));
+    if (pcm16_out) { MM_TRY(arena(c, SL_STAGE_PCM, cframes, &pcm[0])); if (nchunks > 1) MM_TRY(arena(c, SL_STAGE_PCM1, cframes, &pcm[1])); }
+    if (noise_host) { MM_TRY(arena(c, SL_STAGE_NOISE, cframes, &nz[0])); if (nchunks > 1) MM_TRY(arena(c, SL_STAGE_NOISE1, cframes, &nz[1])); }
+    if (audio_out) { MM_TRY(arena(c, SL_STAGE_OL, cframes, &ol[0])); if (nchunks > 1) MM_TRY(arena(c, SL_STAGE_OL1, cframes, &ol[1])); }
     if (stats_host) MM_TRY(arena(c, SL_STATS, (size_t)tracks, &st));
-    MM_CUDA(cudaMemcpyAsync(il, audio_in, frames * sizeof(float), cudaMemcpyHostToDevice, c->stream));
-    if (noise_host) MM_CUDA(cudaMemcpyAsync(nz, noise_host, frames * sizeof(float), cudaMemcpyHostToDevice, c->stream));
-    MM_TRY(mm_dev_deinterleave(c, &g, il, pl));
-    MM_TRY(master_impl(c, &g, chain, styles, pl, pl, pcm, nz, seed, st, flags));
-    if (audio_out) {
-        MM_TRY(mm_dev_interleave(c, &g, pl, il));
-        MM_CUDA(cudaMemcpyAsync(audio_out, il, frames * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+
+    std::vector<cudaEvent_t> ev_in(nchunks), ev_deint(nchunks), ev_done(nchunks), ev_out(nchunks);
+    for (int k = 0; k < nchunks; ++k) {
+        MM_CUDA(cudaEventCreateWithFlags(&ev_in[k], cudaEventDisableTiming));
+        MM_CUDA(cudaEventCreateWithFlags(&ev_deint[k], cudaEventDisableTiming));
+        MM_CUDA(cudaEventCreateWithFlags(&ev_done[k], cudaEventDisableTiming));
+        MM_CUDA(cudaEventCreateWithFlags(&ev_out[k], cudaEventDisableTiming));
     }
-    if (pcm16_out) MM_CUDA(cudaMemcpyAsync(pcm16_out, pcm, frames * sizeof(int16_t), cudaMemcpyDeviceToHost, c->stream));
-    if (stats_host) MM_CUDA(cudaMemcpyAsync(stats_host, st, (size_t)tracks * sizeof(mm_track_stats), cudaMemcpyDeviceToHost, c->stream));
-    return mm_ctx_sync(c);
+    int rc = 0;
+    // everything queued earlier on the context stream (the caller's own work, buffer growth) precedes the copies
+    cudaEvent_t ev_start;
+    MM_CUDA(cudaEventCreateWithFlags(&ev_start, cudaEventDisableTiming));
+    MM_CUDA(cudaEventRecord(ev_start, c->stream));
+    MM_CUDA(cudaStreamWaitEvent(c->h2d_stream, ev_start, 0));
+    MM_CUDA(cudaStreamWaitEvent(c->d2h_stream, ev_start, 0));
+    auto copy_in = [&](int k) -> int {
+        const int t0 = k * tc, tn = std::min(tc, (int)tracks - t0);
+        const size_t off = (size_t)t0 * per_track, cnt = (size_t)tn * per_track;
+        if (k >= 2) MM_CUDA(cudaStreamWaitEvent(c->h2d_stream, ev_deint[k - 2], 0));    // staging buffer k & 1 is free again
+        MM_CUDA(cudaMemcpyAsync(il[k & 1], audio_in + off, cnt * sizeof(float), cudaMemcpyHostToDevice, c->h2d_stream));
+        if (noise_host) {
+            if (k >= 2) MM_CUDA(cudaStreamWaitEvent(c->h2d_stream, ev_done[k - 2], 0));
+            MM_CUDA(cudaMemcpyAsync(nz[k & 1], noise_host + off, cnt * sizeof(float), cudaMemcpyHostToDevice, c->h2d_stream));
+        }
+        MM_CUDA(cudaEventRecord(ev_in[k], c->h2d_stream));
+        return 0;
+    };
+    rc = copy_in(0);
+    for (int k = 0; k < nchunks && rc == 0; ++k) {
+        const int t0 = k * tc, tn = std::min(tc, (int)tracks - t0);
+        const size_t off = (size_t)t0 * per_track, cnt = (size_t)tn * per_track;
+        if (k + 1 < nchunks && (rc = copy_in(k + 1)) != 0) break;
+        mm_geom gk = g;
+        gk.tracks = tn;
+        gk.track_base = t0;                                  // index of the chunk's first track in the call (dither counter)
+        if ((rc = cudaStreamWaitEvent(c->stream, ev_in[k], 0) != cudaSuccess)) { set_error("cudaStreamWaitEvent failed"); break; }
+        if ((rc = mm_dev_deinterleave(c, &gk, il[k & 1], pl)) != 0) break;
+        cudaEventRecord(ev_deint[k], c->stream);
+        if (k >= 2) cudaStreamWaitEvent(c->stream, ev_out[k - 2], 0);     // pcm / ol staging k & 1 has left the device
+        if ((rc = master_impl(c, &gk, chain, styles + t0, pl, pl, pcm16_out ? pcm[k & 1] : nullptr, noise_host ? nz[k & 1] : nullptr, seed,
+                              st ? st + t0 : nullptr, flags)) != 0) break;
+        if (audio_out && (rc = mm_dev_interleave(c, &gk, pl, ol[k & 1])) != 0) break;
+        cudaEventRecord(ev_done[k], c->stream);
+        cudaStreamWaitEvent(c->d2h_stream, ev_done[k], 0);
+        if (audio_out) cudaMemcpyAsync(audio_out + off, ol[k & 1], cnt * sizeof(float), cudaMemcpyDeviceToHost, c->d2h_stream);
+        if (pcm16_out) cudaMemcpyAsync(pcm16_out + off, pcm[k & 1], cnt * sizeof(int16_t), cudaMemcpyDeviceToHost, c->d2h_stream);
+        cudaEventRecord(ev_out[k], c->d2h_stream);
+    }
+    if (rc == 0 && stats_host) {
+        if (cudaMemcpyAsync(stats_host, st, (size_t)tracks * sizeof(mm_track_stats), cudaMemcpyDeviceToHost, c->stream) != cudaSuccess) {
+            set_error("copy of the track stats failed");
+            rc = 1;
+        }
+    }
+    cudaError_t e1 = cudaStreamSynchronize(c->h2d_stream), e2 = cudaStreamSynchronize(c->stream), e3 = cudaStreamSynchronize(c->d2h_stream);
+    for (int k = 0; k < nchunks; ++k) { cudaEventDestroy(ev_in[k]); cudaEventDestroy(ev_deint[k]); cudaEventDestroy(ev_done[k]); cudaEventDestroy(ev_out[k]); }
+    cudaEventDestroy(ev_start);
+    if (rc == 0 && (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess)) {
+        set_error("mm_master_host: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : (e2 != cudaSuccess ? e2 : e3)));
+        rc = 1;
+    }
+    return rc;
 }
 
 // ---- filter design ----------------------------------------------------------------------------

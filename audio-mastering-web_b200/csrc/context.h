@@ -68,6 +68,7 @@ enum SlotId {
     SL_ROWSTATS, SL_SUB, SL_MUL, SL_GAIN, SL_MUL_OUT, SL_SEGSUM, SL_LUFS, SL_TARGET, SL_GAINDB,
     SL_PEAKBITS, SL_WIDTH, SL_PARMIX, SL_PEAKIN, SL_MEAN, SL_NONFINITE, SL_LUFS2, SL_LUFS3,
     SL_STAGE_IL, SL_STAGE_PCM, SL_STAGE_NOISE, SL_STAGE_PL, SL_STATS, SL_ENV0, SL_ENV1, SL_MISC,
+    SL_STAGE_IL1, SL_STAGE_PCM1, SL_STAGE_NOISE1, SL_STAGE_OL, SL_STAGE_OL1,
     SL_COUNT
 };
 
@@ -79,6 +80,7 @@ struct mm_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
+    cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;   // copy streams of the host-buffer entry point (lazy)
     mm::Slot slots[mm::SL_COUNT];
     std::map<std::string, mm::FilterPlan> plans;
     std::map<std::string, mm::LufsPlan> lufs_plans;

@@ -213,7 +213,7 @@ __global__ void __launch_bounds__(kPwThreads) pointwise_kernel(const PwArgs P) {
                         } else {
                             unsigned rnd[4];
                             const unsigned long long fr = (unsigned long long)(i + c);
-                            philox4x32_10((unsigned)fr, (unsigned)(fr >> 32), (unsigned)track, 0u,
+                            philox4x32_10((unsigned)fr, (unsigned)(fr >> 32), (unsigned)(track + P.track_base), 0u,
                                           (unsigned)P.seed, (unsigned)(P.seed >> 32), rnd);
                             n0 = tpdf_from_bits(rnd[0], rnd[1]); n1 = tpdf_from_bits(rnd[2], rnd[3]);
                         }
@@ -280,6 +280,7 @@ struct FinalArgs {
     const float* noise;         // interleaved float32 noise or null (-> Philox)
     unsigned long long seed;
     double* nonfinite;          // per track or null
+    int track_base;             // mm_geom::track_base: keeps the dither stream independent of host-side chunking
 };
 
 constexpr int kFinThreads = 256;
@@ -360,7 +361,7 @@ __global__ void __launch_bounds__(kFinThreads) finalize_kernel(const FinalArgs P
                 } else {
                     unsigned rnd[4];
                     const unsigned long long fr = (unsigned long long)(i + c);
-                    philox4x32_10((unsigned)fr, (unsigned)(fr >> 32), (unsigned)track, 0u, (unsigned)P.seed, (unsigned)(P.seed >> 32), rnd);
+                    philox4x32_10((unsigned)fr, (unsigned)(fr >> 32), (unsigned)(track + P.track_base), 0u, (unsigned)P.seed, (unsigned)(P.seed >> 32), rnd);
                     n0 = tpdf_from_bits(rnd[0], rnd[1]);
                     n1 = tpdf_from_bits(rnd[2], rnd[3]);
                 }
@@ -404,7 +405,7 @@ __global__ void __launch_bounds__(kPwThreads) quantize_kernel(const QuantArgs P)
     if (i >= P.n) return;
     const size_t fi = (size_t)track * (size_t)P.n + (size_t)i;
     unsigned rnd[4] = {0, 0, 0, 0};
-    if (!P.noise) philox4x32_10((unsigned)i, (unsigned)((unsigned long long)i >> 32), (unsigned)track, 0u,
+    if (!P.noise) philox4x32_10((unsigned)i, (unsigned)((unsigned long long)i >> 32), (unsigned)(track + P.track_base), 0u,
                                 (unsigned)P.seed, (unsigned)(P.seed >> 32), rnd);
     for (int c = 0; c < C; ++c) {
         const float x = P.in[(size_t)(track * C + c) * (size_t)P.stride + kLead + i];

@@ -53,11 +53,13 @@ struct PwArgs {
     const float* noise;         // interleaved float noise or null (-> Philox)
     unsigned long long seed;
     double* nonfinite;          // per track count of non-finite samples seen before nan_to_num (or null)
+    int track_base;             // mm_geom::track_base (dither counter)
 };
 
 struct QuantArgs {
     const float* in; long long n, stride; int tracks, channels;
     int16_t* pcm; const float* noise; unsigned long long seed;
+    int track_base;
 };
 
 }  // namespace mm

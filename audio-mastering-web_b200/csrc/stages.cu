@@ -54,12 +54,13 @@ static void choose_segments(int rows, int ntiles, int whalo, int capacity, int* 
     *seglen_out = (ntiles + best - 1) / best;
 }
 
-template <int M, int NF, int NIN, int DIR, int EPI, int NAUX, int ST, int NF32>
-static int launch_sweep2(mm_ctx* c, SweepArgs<M, NF>& A, int whalo, const char* name) {
+template <int M, int NF, int NIN, int DIR, int EPI, int NAUX, int ST, int NF32, int NSET = 1>
+static int launch_sweep2(mm_ctx* c, SweepArgs<M, NF>* As, int whalo, const char* name) {
     typedef Sweep2Cfg<M, NF, NIN, DIR, EPI, NAUX, ST> Cfg;
     static int blocks_per_sm = 0;          // per instantiation; one device kind per process
     static int num_sms = 0;
-    auto kern = sweep2_kernel<M, NF, NIN, DIR, EPI, NAUX, ST, NF32>;
+    auto kern = sweep2_kernel<M, NF, NIN, DIR, EPI, NAUX, ST, NF32, NSET>;
+    SweepArgs<M, NF>& A = As[0];
     const size_t smem = Cfg::kBytes;
     if (blocks_per_sm == 0) {
         MM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -73,16 +74,21 @@ static int launch_sweep2(mm_ctx* c, SweepArgs<M, NF>& A, int whalo, const char* 
         blocks_per_sm = bps;
         if (getenv("MM_DEBUG")) fprintf(stderr, "[mm] %s (%d float32 sections): %zu B smem, %d CTAs/SM x %d SMs\n", name, NF32, smem, bps, num_sms);
     }
-    A.ntiles = DIR > 0 ? tiles_fwd(A.n, A.pad) : tiles_bwd(A.n, A.pad);
+    for (int k = 0; k < NSET; ++k) As[k].ntiles = DIR > 0 ? tiles_fwd(A.n, A.pad) : tiles_bwd(A.n, A.pad);
     if ((size_t)A.rows * (size_t)A.ntiles == 0) return 0;
-    const int capacity = num_sms * blocks_per_sm;
-    Sweep2Args<M, NF> PP;
+    const int capacity = std::max(1, num_sms * blocks_per_sm / NSET);      // work items in flight (NSET CTAs each)
+    Sweep2Args<M, NF, NSET> PP;
     PP.whalo = whalo;
     choose_segments(A.rows, A.ntiles, whalo, capacity, &PP.nseg, &PP.seglen);
     const long long items = (long long)A.rows * PP.nseg;
-    const unsigned grid = (unsigned)std::min<long long>(items, capacity);
-    PP.a = A;
+    const unsigned grid = (unsigned)std::min<long long>(items, capacity) * NSET;
+    for (int k = 0; k < NSET; ++k) PP.a[k] = As[k];
     PP.dbg = nullptr;
+    {
+        static int skip = -1;
+        if (skip < 0) { const char* e = getenv("MM_SKIP"); skip = e ? atoi(e) : 0; }
+        PP.skip = skip;
+    }
     static long long* dbg_dev = nullptr;
     const bool dbg = getenv("MM_PHASES") != nullptr;
     if (dbg) {
@@ -207,7 +213,25 @@ template <int M, int NF, int NIN, int DIR, int EPI, int NAUX, int NF32>
 static int run_sweep(mm_ctx* c, const mm_geom* g, const Arranged& R, int nout, const Pro& pro, int pad, const char* name) {
     SweepArgs<M, NF> A;
     fill_common<M, NF>(A, g, R.plans, R.in, NIN, R.out, nout, pro, R.epi, pad);
-    return launch_sweep2<M, NF, NIN, DIR, EPI, NAUX, 1, NF32>(c, A, halo_tiles(R.plans, NF), name);
+    return launch_sweep2<M, NF, NIN, DIR, EPI, NAUX, 1, NF32>(c, &A, halo_tiles(R.plans, NF), name);
+}
+
+// Four sections of one input (forward, EPI_STORE) as two sets of two: arranged sections (0, 2) and (1, 3), so that both
+// sets hold the same number of float32 sections (n32 / 2 each).
+template <int N32SET>
+static int run_fwd4_split(mm_ctx* c, const mm_geom* g, const Arranged& R, const Pro& pro, int pad, const char* name) {
+    SweepArgs<2, 2> A[2];
+    for (int k = 0; k < 2; ++k) {
+        Arranged S;
+        S.epi = R.epi;
+        for (int j = 0; j < 2; ++j) {
+            S.plans[j] = R.plans[k + 2 * j];
+            S.in[j] = R.in[0];
+            S.out[j] = R.out[k + 2 * j];
+        }
+        fill_common<2, 2>(A[k], g, S.plans, S.in, 1, S.out, 2, pro, S.epi, pad);
+    }
+    return launch_sweep2<2, 2, 1, +1, EPI_STORE, 0, 1, N32SET, 2>(c, A, halo_tiles(R.plans, 4), name);
 }
 
 int sweep_fwd(mm_ctx* c, const mm_geom* g, int nf, int nin, const FilterPlan* const* plans, const float* const* in,
@@ -229,6 +253,11 @@ int sweep_fwd(mm_ctx* c, const mm_geom* g, int nf, int nin, const FilterPlan* co
     MM_FWD(2, 1, 1, 0) MM_FWD(2, 1, 1, 1)
     MM_FWD(2, 2, 1, 0) MM_FWD(2, 2, 1, 1) MM_FWD(2, 2, 1, 2)
     MM_FWD(2, 2, 2, 0) MM_FWD(2, 2, 2, 1) MM_FWD(2, 2, 2, 2)
+    if (m == 2 && nf == 4 && nin == 1 && getenv("MM_SPLIT4")) {   // experiment: measured slower than one 4-section CTA
+        if (R.n32 == 0) return run_fwd4_split<0>(c, g, R, pro, pad, "sweep_fwd_m2_f4_i1");
+        if (R.n32 == 2) return run_fwd4_split<1>(c, g, R, pro, pad, "sweep_fwd_m2_f4_i1");
+        if (R.n32 == 4) return run_fwd4_split<2>(c, g, R, pro, pad, "sweep_fwd_m2_f4_i1");
+    }
     MM_FWD(2, 4, 1, 0) MM_FWD(2, 4, 1, 2) MM_FWD(2, 4, 1, 4)
     MM_FWD(4, 1, 1, 0)
 #undef MM_FWD
@@ -342,7 +371,7 @@ int run_in_scalars(mm_ctx* c, const mm_geom* g, const RowStats* st, int use_dc, 
 }
 
 int run_pointwise(mm_ctx* c, const mm_geom* g, PwArgs& A, const char* name) {
-    A.n = g->n; A.stride = g->stride; A.tracks = g->tracks; A.channels = g->channels;
+    A.n = g->n; A.stride = g->stride; A.tracks = g->tracks; A.channels = g->channels; A.track_base = g->track_base;
     dim3 grid((unsigned)((g->n + kPwFramesPerBlock - 1) / kPwFramesPerBlock), (unsigned)g->tracks);
     KernelScope ks(c, name);
     pointwise_kernel<<<grid, kPwThreads, 0, c->stream>>>(A);
@@ -362,7 +391,7 @@ int run_finalize(mm_ctx* c, const mm_geom* g, const float* in, float* out, const
     FinalArgs A;
     A.in = in; A.out = out; A.n = g->n; A.stride = g->stride; A.tracks = g->tracks; A.mul = mul; A.width = width;
     A.n_fade = n_fade; A.fade_step = n_fade > 1 ? 1.0 / (double)(n_fade - 1) : 0.0;
-    A.pcm = pcm; A.noise = noise; A.seed = seed; A.nonfinite = nonfinite;
+    A.pcm = pcm; A.noise = noise; A.seed = seed; A.nonfinite = nonfinite; A.track_base = g->track_base;
     dim3 grid((unsigned)((g->n + kFinFrames - 1) / kFinFrames), (unsigned)g->tracks);
     KernelScope ks(c, pcm ? "finalize_dither_int16" : "finalize");
 #define MM_FIN(C_, PCM_, NZ_) finalize_kernel<C_, PCM_, NZ_><<<grid, kFinThreads, 0, c->stream>>>(A)

@@ -62,12 +62,16 @@ template <int M> __device__ __forceinline__ void matvec_acc_s(const double* p, c
     }
 }
 
-template <int M, int NF> struct Sweep2Args {
-    SweepArgs<M, NF> a;
+// NSET > 1: the sections of one sweep are dealt out to NSET CTAs per tile range (a[0], a[1], ... differ only in their
+// sections and output streams).  CTA b serves set b % NSET, so the CTAs that share an input tile run side by side
+// and the second read of it hits L2; each CTA stages only its own NF outputs in shared memory.
+template <int M, int NF, int NSET = 1> struct Sweep2Args {
+    SweepArgs<M, NF> a[NSET];
     int seglen;           // live tiles per segment
     int nseg;             // segments per row
     int whalo;            // halo tiles read before a segment (max over the sweep's sections)
     long long* dbg;       // phase clocks of CTA 0 / thread 0 (tuning; null in production)
+    int skip;             // tuning only (MM_SKIP): 1 no global stores, 2 no interior loads, 4 no pass 2, 8 no warp scan
 };
 
 template <int M, int NF, int NIN, int DIR, int EPI, int NAUX, int ST>
@@ -98,10 +102,10 @@ __device__ __forceinline__ float pro1(int mode, float x, float subf, float mulf,
 
 // NF32: the first NF32 sections run pass 2 in float32 on their balanced realization (tables and g in those
 // coordinates), the others in float64 DF2T.  Pass 1 and the scan are float64 for both.
-template <int M, int NF, int NIN, int DIR, int EPI, int NAUX, int ST, int NF32>
-__global__ void __launch_bounds__(kT, Sweep2Cfg<M, NF, NIN, DIR, EPI, NAUX, ST>::kMinBlocks) sweep2_kernel(const __grid_constant__ Sweep2Args<M, NF> PP) {
+template <int M, int NF, int NIN, int DIR, int EPI, int NAUX, int ST, int NF32, int NSET = 1>
+__global__ void __launch_bounds__(kT, Sweep2Cfg<M, NF, NIN, DIR, EPI, NAUX, ST>::kMinBlocks) sweep2_kernel(const __grid_constant__ Sweep2Args<M, NF, NSET> PP) {
     typedef Sweep2Cfg<M, NF, NIN, DIR, EPI, NAUX, ST> Cfg;
-    const SweepArgs<M, NF>& P = PP.a;
+    const SweepArgs<M, NF>& P = PP.a[NSET > 1 ? (blockIdx.x % NSET) : 0];
     extern __shared__ __align__(128) unsigned char smraw[];
     float* ring = reinterpret_cast<float*>(smraw);
     float* extra = reinterpret_cast<float*>(smraw + Cfg::kExtraOff);
@@ -142,6 +146,7 @@ __global__ void __launch_bounds__(kT, Sweep2Cfg<M, NF, NIN, DIR, EPI, NAUX, ST>:
         const long long lo = tile_origin(tile);
         const size_t rowoff = (size_t)row * (size_t)P.stride;
         if (fast_in(lo)) {
+            if (PP.skip & 2) return;
 #pragma unroll
             for (int s = 0; s < NIN; ++s) {
                 // swz(tid + kT r) = swz(tid) + kT r (kT is a multiple of 8): base + immediate addressing
@@ -233,7 +238,7 @@ __global__ void __launch_bounds__(kT, Sweep2Cfg<M, NF, NIN, DIR, EPI, NAUX, ST>:
     // ---- segment loop --------------------------------------------------------------------------------
     const int items = P.rows * PP.nseg;
 #pragma unroll 1
-    for (int item = blockIdx.x; item < items; item += gridDim.x) {
+    for (int item = blockIdx.x / NSET; item < items; item += gridDim.x / NSET) {
     const int row = item % P.rows;
     const int seg = item / P.rows;
     const int t_live = seg * PP.seglen;
@@ -306,11 +311,13 @@ __global__ void __launch_bounds__(kT, Sweep2Cfg<M, NF, NIN, DIR, EPI, NAUX, ST>:
             for (int s = 0; s < NIN; ++s) {
                 float* p = tin + (size_t)s * kL + cbase + ((4 * uu) ^ cx);
                 xv[s] = *reinterpret_cast<const float4*>(p);
-                if (pmode != PRO_NONE) {
-                    xv[s].x = pro1(pmode, xv[s].x, subf, mulf, muld);
-                    xv[s].y = pro1(pmode, xv[s].y, subf, mulf, muld);
-                    xv[s].z = pro1(pmode, xv[s].z, subf, mulf, muld);
-                    xv[s].w = pro1(pmode, xv[s].w, subf, mulf, muld);
+                if (pmode == PRO_SUBMUL_F32) {
+                    xv[s].x = __fmul_rn(__fsub_rn(xv[s].x, subf), mulf); xv[s].y = __fmul_rn(__fsub_rn(xv[s].y, subf), mulf);
+                    xv[s].z = __fmul_rn(__fsub_rn(xv[s].z, subf), mulf); xv[s].w = __fmul_rn(__fsub_rn(xv[s].w, subf), mulf);
+                    *reinterpret_cast<float4*>(p) = xv[s];
+                } else if (pmode == PRO_MUL_F64) {
+                    xv[s].x = (float)((double)xv[s].x * muld); xv[s].y = (float)((double)xv[s].y * muld);
+                    xv[s].z = (float)((double)xv[s].z * muld); xv[s].w = (float)((double)xv[s].w * muld);
                     *reinterpret_cast<float4*>(p) = xv[s];
                 }
             }
@@ -355,6 +362,7 @@ __global__ void __launch_bounds__(kT, Sweep2Cfg<M, NF, NIN, DIR, EPI, NAUX, ST>:
         // ---- warp scan: branch-free (lanes below the stride shuffle in zeros), sections interleaved --------
 #pragma unroll
         for (int d = 0; d < 5; ++d) {
+            if (PP.skip & 8) break;
             const bool act = lane >= (1 << d);
             double pe[NF][M];
 #pragma unroll
@@ -446,6 +454,7 @@ __global__ void __launch_bounds__(kT, Sweep2Cfg<M, NF, NIN, DIR, EPI, NAUX, ST>:
         const bool out_fast = fast_out(tile_lo);
         float aux_subf = 0.f, aux_mulf = 1.f;
         double aux_muld = 1.0;
+        const int aux_pmode = (EPI != EPI_STORE && P.aux_pro) ? P.pro_mode : PRO_NONE;
         if (EPI != EPI_STORE && P.aux_pro && P.pro_mode != PRO_NONE) {
             if (P.pro_sub) aux_subf = (float)__ldg(P.pro_sub + row);
             if (P.pro_mul) { aux_muld = __ldg(P.pro_mul + row); aux_mulf = (float)aux_muld; }
@@ -460,19 +469,20 @@ __global__ void __launch_bounds__(kT, Sweep2Cfg<M, NF, NIN, DIR, EPI, NAUX, ST>:
         // one output element of a recombining epilogue; this sample's section outputs are yf[f] (float32 sections,
         // f < NF32) and yd[f] (float64 sections)
         auto epi_value = [&](float xa_raw, float a1c, const float (&yf)[NF], const double (&yd)[NF]) -> float {
-            float xa = xa_raw;
-            if (P.aux_pro) xa = pro1(P.pro_mode, xa, aux_subf, aux_mulf, aux_muld);
+            const float xa = xa_raw;            // the aux prologue was applied to the whole float4 group by the caller
             auto yflt = [&](int f) -> float { return f < NF32 ? yf[f] : (float)yd[f]; };
             if (EPI == EPI_COMBINE) {
                 // pipeline.py:273 / :603-606 / :1431: float64 recombination, one cast to float32.  The float32
                 // sections enter through their (small) weights: their weighted sum is formed in float32 and
                 // widened once
-                double acc = P.wc * (double)xa;
+                double acc;
                 if (NF32 > 0) {
                     float accf = 0.f;
 #pragma unroll
                     for (int f = 0; f < NF32; ++f) accf = fmaf(P.w32[f], yf[f], accf);
-                    acc += (double)accf;
+                    acc = fma(P.wc, (double)xa, (double)accf);     // wc == 1 at every call site: exact product
+                } else {
+                    acc = P.wc * (double)xa;
                 }
 #pragma unroll
                 for (int f = NF32; f < NF; ++f) acc = fma(P.w[f], yd[f], acc);
@@ -509,7 +519,8 @@ __global__ void __launch_bounds__(kT, Sweep2Cfg<M, NF, NIN, DIR, EPI, NAUX, ST>:
             S0[p] = make_float2(sf[2 * p][0], sf[2 * p + 1][0]);
             S1[p] = make_float2(sf[2 * p][M > 1 ? 1 : 0], sf[2 * p + 1][M > 1 ? 1 : 0]);
         }
-        if (!inj_thread) {
+        if (PP.skip & 4) {
+        } else if (!inj_thread) {
             // a recombining epilogue keeps the loop rolled (2 float4 groups in flight): fully unrolled, the
             // hoisted aux / input loads cost ~100 extra registers and halve the occupancy
 #pragma unroll (EPI == EPI_STORE ? kS / 4 : 2)
@@ -522,6 +533,13 @@ __global__ void __launch_bounds__(kT, Sweep2Cfg<M, NF, NIN, DIR, EPI, NAUX, ST>:
                 float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;
                 if (EPI != EPI_STORE && NAUX > 0) a0 = *reinterpret_cast<const float4*>(auxs + off);
                 if (EPI != EPI_STORE && NAUX > 1) a1 = *reinterpret_cast<const float4*>(auxs + kL + off);
+                if (EPI != EPI_STORE && aux_pmode == PRO_SUBMUL_F32) {
+                    a0.x = __fmul_rn(__fsub_rn(a0.x, aux_subf), aux_mulf); a0.y = __fmul_rn(__fsub_rn(a0.y, aux_subf), aux_mulf);
+                    a0.z = __fmul_rn(__fsub_rn(a0.z, aux_subf), aux_mulf); a0.w = __fmul_rn(__fsub_rn(a0.w, aux_subf), aux_mulf);
+                } else if (EPI != EPI_STORE && aux_pmode == PRO_MUL_F64) {
+                    a0.x = (float)((double)a0.x * aux_muld); a0.y = (float)((double)a0.y * aux_muld);
+                    a0.z = (float)((double)a0.z * aux_muld); a0.w = (float)((double)a0.w * aux_muld);
+                }
                 float4 yv[NOUT];
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
@@ -547,11 +565,16 @@ __global__ void __launch_bounds__(kT, Sweep2Cfg<M, NF, NIN, DIR, EPI, NAUX, ST>:
                     } else {
                         const float res = epi_value(comp4(a0, cc), comp4(a1, cc), yf, yd);
                         setcomp4(yv[0], cc, res);
-                        if (out_fast) pk = fmaxf(pk, fabsf(res));
-                        else {
-                            const long long q = tile_lo + cbase + 4 * uu + cc;
-                            if (q >= st_lo && q <= st_hi) pk = fmaxf(pk, fabsf(res));
-                        }
+                    }
+                }
+                if (EPI != EPI_STORE) {     // output peak: one decision per float4 group
+                    if (out_fast) {
+                        pk = fmaxf(fmaxf(pk, fmaxf(fabsf(yv[0].x), fabsf(yv[0].y))), fmaxf(fabsf(yv[0].z), fabsf(yv[0].w)));
+                    } else {
+                        const long long q = tile_lo + cbase + 4 * uu;
+#pragma unroll
+                        for (int c = 0; c < 4; ++c)
+                            if (q + c >= st_lo && q + c <= st_hi) pk = fmaxf(pk, fabsf(comp4(yv[0], c)));
                     }
                 }
 #pragma unroll
@@ -587,7 +610,9 @@ __global__ void __launch_bounds__(kT, Sweep2Cfg<M, NF, NIN, DIR, EPI, NAUX, ST>:
 #pragma unroll
                     for (int f = 0; f < NF; ++f) tout[f][off] = f < NF32 ? yf[f] : (float)yd[f];
                 } else {
-                    const float res = epi_value(NAUX > 0 ? auxs[off] : 0.f, NAUX > 1 ? auxs[kL + off] : 0.f, yf, yd);
+                    float xa0 = NAUX > 0 ? auxs[off] : 0.f;
+                    if (aux_pmode != PRO_NONE) xa0 = pro1(aux_pmode, xa0, aux_subf, aux_mulf, aux_muld);
+                    const float res = epi_value(xa0, NAUX > 1 ? auxs[kL + off] : 0.f, yf, yd);
                     tout[0][off] = res;
                     const long long q = tile_lo + cbase + mi;
                     if (q >= st_lo && q <= st_hi) pk = fmaxf(pk, fabsf(res));
@@ -599,7 +624,8 @@ __global__ void __launch_bounds__(kT, Sweep2Cfg<M, NF, NIN, DIR, EPI, NAUX, ST>:
         MM_TICK(6);
 
         // ---- store: NOUT finished float32 streams, coalesced -----------------------------------------------------
-        if (out_fast) {
+        if (out_fast && (PP.skip & 1)) {
+        } else if (out_fast) {
             // interior tile: every vector is complete; base + immediate addressing (swz(tid + kT r) = swz(tid) + kT r)
             const int so0 = 4 * swz(tid);
             const size_t go0 = rowoff + (size_t)tile_lo + 4 * tid;

@@ -18,7 +18,7 @@ class MMError(RuntimeError):
 
 class Geom(C.Structure):
     _fields_ = [("n", C.c_int64), ("stride", C.c_int64), ("tracks", C.c_int32), ("channels", C.c_int32),
-                ("sr", C.c_int32), ("_pad", C.c_int32)]
+                ("sr", C.c_int32), ("track_base", C.c_int32)]
 
 
 class Style(C.Structure):

@@ -40,7 +40,7 @@ typedef struct mm_geom {
     int32_t tracks;
     int32_t channels; /* 1 or 2 */
     int32_t sr;       /* sample rate, Hz */
-    int32_t _pad;
+    int32_t track_base; /* index of track 0 inside a larger logical batch (dither counter only); normally 0 */
 } mm_geom;
 
 /* STYLE_CONFIGS row (backend/app/pipeline.py:69-86) + target; one per track. */

@@ -174,3 +174,37 @@ def test_mastering_chain_api_default_and_custom(P):
     # second-wave modules fail loudly instead of passing audio through
     with pytest.raises(NotImplementedError):
         mc.MasteringChain.from_config({"modules": [{"id": "reverb", "enabled": True}]}).process(x.copy(), sr)
+
+
+def test_master_host_pipelined_chunks_equal_one_shot(P, monkeypatch):
+    """mm_master_host (host buffers in / out): the copy-compute-copy pipeline over chunks of tracks returns, bit for
+    bit, what one chunk returns -- float32 audio, Philox-dithered int16 (counter keyed by the track's index in the
+    call) and stats -- and the audio equals the device-resident entry point's."""
+    import ctypes as C
+    from mm_b200 import _lib, synth
+    from mm_b200.engine import get_engine, style_struct, TrackStats
+    eng = get_engine()
+    sr, dur = 44100, 0.6
+    names = ["standard", "edm", "classical", "podcast", "lofi", "standard", "house_basic"]
+    tracks = [synth.numpy_track(40 + i, sr, dur) for i in range(len(names))]
+    n = tracks[0].shape[0]
+    hin = np.ascontiguousarray(np.stack(tracks), dtype=np.float32)                     # (T, n, 2) interleaved
+    styles = (_lib.Style * len(names))(*[style_struct(P.STYLE_CONFIGS[s], P.STYLE_CONFIGS[s]["lufs"]) for s in names])
+
+    def run(chunk):
+        monkeypatch.setenv("MM_HOST_CHUNK", str(chunk))
+        out = np.zeros_like(hin)
+        pcm = np.zeros(hin.shape, dtype=np.int16)
+        st = (TrackStats * len(names))()
+        _lib.check(eng.lib.mm_master_host(eng.ctx, _lib.CHAIN_V2, len(names), n, 2, sr, styles, hin.ctypes.data_as(C.c_void_p),
+                                          out.ctypes.data_as(C.c_void_p), pcm.ctypes.data_as(C.c_void_p), None, 77, st,
+                                          _lib.FLAG_MEASURE_OUT))
+        return out, pcm, np.frombuffer(bytes(st), dtype=np.uint8).copy()
+
+    one = run(len(names))
+    for chunk in (1, 3):
+        got = run(chunk)
+        assert np.array_equal(got[0], one[0]) and np.array_equal(got[1], one[1]) and np.array_equal(got[2], one[2]), chunk
+    dev = P.master_batch(tracks, sr, names, chain="v2")
+    for i in range(len(names)):
+        assert np.array_equal(one[0][i], dev["audio"][i]), i
