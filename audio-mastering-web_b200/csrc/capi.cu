@@ -138,6 +138,13 @@ static int master_impl(mm_ctx* c, const mm_geom* g, int chain, const mm_style* s
     //    as the prologue of the first sweeps (pipeline.py:134-149, :1833-1837; chain.py:112-113)
     RowStats* st;
     MM_TRY(run_row_stats(c, g, in, &st));
+    const mm_slice* sl = c->slice;
+    auto reduce = [&](void* ptr, int64_t count, int dtype, int op, const char* what) -> int {
+        if (!sl || !sl->allreduce) return 0;
+        if (sl->allreduce(sl->user, ptr, count, dtype, op) != 0) { set_error("allreduce of %s failed", what); return 1; }
+        return 0;
+    };
+    MM_TRY(exchange_row_stats(c, st, rows));     // time slices: sums / minima / maxima over every rank's own frames
     MM_TRY(run_in_scalars(c, g, st, 1, 1, 0.5, d_sub, d_mul, d_peakin, d_mean));
     Pro pin;
     pin.mode = PRO_SUBMUL_F32;
@@ -201,7 +208,8 @@ static int master_impl(mm_ctx* c, const mm_geom* g, int chain, const mm_style* s
                 sub.tracks = t1 - t0;
                 MM_CUDA(cudaMemsetAsync(d_peakbits + t0, 0, (size_t)sub.tracks * sizeof(float), c->stream));
                 PwArgs A;
-                pw_base(&A, out + (size_t)t0 * C * (size_t)g->stride, nullptr, PW_PEAK);
+                pw_base(&A, out + (size_t)t0 * C * (size_t)g->stride + (sl ? sl->own_lo : 0), nullptr, PW_PEAK);
+                if (sl) sub.n = sl->own_hi - sl->own_lo;
                 A.width = d_width + t0;
                 A.peak = d_peakbits + t0;
                 MM_TRY(run_pointwise(c, &sub, A, "peak_after_imager"));
@@ -211,12 +219,13 @@ static int master_impl(mm_ctx* c, const mm_geom* g, int chain, const mm_style* s
     }
     // 10. remove_intersample_peaks(0.5) + clip/nan_to_num + 6 ms fade-in (+ TPDF dither to int16)
     {
+        MM_TRY(reduce(d_peakbits, T, 2, 2, "the output peak"));
         OutScalarArgs O;
         O.peak_bits = d_peakbits; O.tracks = T; O.channels = C;
         O.limit = (float)std::pow(10.0, -0.5 / 20.0);
         O.mul = d_mulout; O.peak_track = d_peakout;
         MM_TRY(run_out_scalars(c, O));
-        const bool fade = v1 || !(flags & MM_FLAG_NO_JOB_FADE);
+        const bool fade = (v1 || !(flags & MM_FLAG_NO_JOB_FADE)) && !(sl && sl->global_off != 0);   // the file's first frames only
         MM_TRY(run_finalize(c, g, out, out, d_mulout, any_img ? d_width : nullptr, fade ? fade_len(g, 6.0) : 0, pcm, noise, seed,
                             d_nonfinite));
     }
@@ -631,6 +640,32 @@ int mm_dev_master(mm_ctx* c, const mm_geom* g, int chain, const mm_style* styles
                   int16_t* pcm, const float* noise, uint64_t seed, mm_track_stats* stats_dev, uint32_t flags) {
     MM_API_BEGIN(c);
     return master_impl(c, g, chain, styles, in, out, pcm, noise, seed, stats_dev, flags);
+}
+
+int64_t mm_slice_margin(int32_t sr) {
+    // every sweep's start-up (odd extension / zero state at a cut instead of the true neighbourhood) dies within a
+    // few time constants of its slowest pole; the chain strings ~16 low-cut-off sweeps per direction together
+    // (edm, 30-90 Hz band: ~3 tiles each at 96 kHz).  128 tiles at 96 kHz, scaled with the rate.
+    const long long tiles = std::max<long long>(64, (128LL * std::max(sr, 1) + 95999) / 96000);
+    return tiles * kL;
+}
+
+int mm_dev_master_slice(mm_ctx* c, const mm_geom* g, int chain, const mm_style* style, const float* in, float* out,
+                        int16_t* pcm, const float* noise, uint64_t seed, mm_track_stats* stats_dev, uint32_t flags,
+                        const mm_slice* slice) {
+    MM_API_BEGIN(c);
+    if (!slice) return master_impl(c, g, chain, style, in, out, pcm, noise, seed, stats_dev, flags);
+    MM_TRY(check_geom(g));
+    if (g->tracks != 1) { set_error("mm_dev_master_slice: one track (file) per call"); return 1; }
+    if (slice->own_lo < 0 || slice->own_hi > g->n || slice->own_lo >= slice->own_hi || (slice->own_lo & 3) || slice->global_off < 0 ||
+        slice->global_off + g->n > slice->global_n) {
+        set_error("mm_dev_master_slice: bad slice (own frames must lie inside the slice, own_lo a multiple of 4, slice inside the file)");
+        return 1;
+    }
+    c->slice = slice;
+    const int rc = master_impl(c, g, chain, style, in, out, pcm, noise, seed, stats_dev, flags);
+    c->slice = nullptr;
+    return rc;
 }
 
 // Host-buffer entry point.  The batch is cut into chunks of tracks that flow through a three-stage pipeline --

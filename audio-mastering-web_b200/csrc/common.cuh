@@ -93,6 +93,7 @@ template <int M, int NF> struct SweepArgs {
     double exc_gain, exc_k;
     int exc_mode;
     float* peak;             // per track |out| max (float bits, atomicMax) or null
+    long long pk_lo, pk_hi;  // row positions (inclusive) whose outputs count towards the peak (a time slice's own frames)
 };
 
 __device__ __forceinline__ double shfl_up_d(double v, int d) {

@@ -147,16 +147,17 @@ template <class T> static int upload_vec(mm_ctx* c, const std::vector<T>& v, T**
 // pyloudnorm block bounds (meter.py integrated_loudness): T_g = 0.4, step = 0.25,
 //   numBlocks = int(round((T - T_g) / (T_g * step)) + 1),  l_j = int(T_g*(j*step)*rate),
 //   u_j = int(T_g*(j*step + 1)*rate)   -- evaluated in the same float64 order here.
-int get_lufs_plan(mm_ctx* c, long long n, int sr, const LufsPlan** out) {
-    char keyb[64];
-    snprintf(keyb, sizeof(keyb), "%lld:%d", n, sr);
+int get_lufs_plan(mm_ctx* c, long long n, int sr, const LufsPlan** out, long long goff, long long n_local) {
+    char keyb[96];
+    if (n_local < 0) n_local = n;
+    snprintf(keyb, sizeof(keyb), "%lld:%d:%lld:%lld", n, sr, goff, n_local);
     auto it = c->lufs_plans.find(keyb);
     if (it != c->lufs_plans.end()) { *out = &it->second; return 0; }
     LufsPlan p;
     const double rate = (double)sr, T_g = 0.4, step = 1.0 - 0.75;
     p.valid = !((double)n < T_g * rate);
     p.scale = 1.0 / (T_g * rate);
-    const long long q_last = kLead + n - 1;
+    const long long q_last = kLead + n_local - 1;
     p.ntiles = (int)((q_last + kL) / kL);
     std::vector<long long> lo, hi, bnd;
     if (p.valid) {
@@ -186,7 +187,7 @@ int get_lufs_plan(mm_ctx* c, long long n, int sr, const LufsPlan** out) {
     }
     std::vector<int> tseg(p.ntiles);
     for (int t = 0; t < p.ntiles; ++t) {
-        long long i0 = std::max<long long>((long long)t * kL - kLead, 0);
+        long long i0 = std::max<long long>((long long)t * kL - kLead, 0) + goff;
         int s = (int)(std::upper_bound(bnd.begin(), bnd.end(), i0) - bnd.begin()) - 1;
         tseg[t] = std::min(std::max(s, 0), p.nseg);
     }

@@ -68,7 +68,7 @@ enum SlotId {
     SL_ROWSTATS, SL_SUB, SL_MUL, SL_GAIN, SL_MUL_OUT, SL_SEGSUM, SL_LUFS, SL_TARGET, SL_GAINDB,
     SL_PEAKBITS, SL_WIDTH, SL_PARMIX, SL_PEAKIN, SL_MEAN, SL_NONFINITE, SL_LUFS2, SL_LUFS3,
     SL_STAGE_IL, SL_STAGE_PCM, SL_STAGE_NOISE, SL_STAGE_PL, SL_STATS, SL_ENV0, SL_ENV1, SL_MISC,
-    SL_STAGE_IL1, SL_STAGE_PCM1, SL_STAGE_NOISE1, SL_STAGE_OL, SL_STAGE_OL1,
+    SL_STAGE_IL1, SL_STAGE_PCM1, SL_STAGE_NOISE1, SL_STAGE_OL, SL_STAGE_OL1, SL_XCHG,
     SL_COUNT
 };
 
@@ -80,7 +80,8 @@ struct mm_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
-    cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;   // copy streams of the host-buffer entry point (lazy)
+    cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
+    const mm_slice* slice = nullptr;    // set for the duration of mm_dev_master_slice: the batch is a time slice of one file   // copy streams of the host-buffer entry point (lazy)
     mm::Slot slots[mm::SL_COUNT];
     std::map<std::string, mm::FilterPlan> plans;
     std::map<std::string, mm::LufsPlan> lufs_plans;
@@ -103,7 +104,8 @@ template <class T> inline int arena(mm_ctx* c, int slot, size_t count, T** out) 
 }
 const FilterPlan* get_plan(mm_ctx* c, const Ba& ba, int prec = PREC_F64);
 const FilterPlan* get_plan_mode(mm_ctx* c, const Ba& ba, int mode);   // mode: design.h Realization
-int get_lufs_plan(mm_ctx* c, long long n, int sr, const LufsPlan** out);
+// n, sr: the (whole) signal the gating blocks are laid over; local tiles cover [goff, goff + n_local) of it
+int get_lufs_plan(mm_ctx* c, long long n, int sr, const LufsPlan** out, long long goff = 0, long long n_local = -1);
 const KwPlan* get_kw_plan(mm_ctx* c, int sr);
 
 struct KernelScope {            // brackets a launch with events when timing is on

@@ -35,6 +35,8 @@ struct LufsArgs {
     const long long* bnd;    // [nhop + 1]
     int nhop;
     const int* tile_seg;     // [ntiles] hop of max(first sample of tile, 0), clamped to nhop
+    long long goff;          // index of the row's sample 0 in the signal the hops are laid over (time slices; else 0)
+    long long own_lo, own_hi;   // samples of the row that are counted (time slices; else 0, n)
     unsigned long long* segsum;   // [rows][nhop] fixed-point sums of squares
 };
 
@@ -194,14 +196,15 @@ __global__ void __launch_bounds__(kT, 6) lufs_kernel(const __grid_constant__ Luf
             // ---- pass 2 (packed float32, the high-pass runs one sample behind the shelf) + squared sums per hop ----
             const long long i0 = tile_lo + (long long)tid * kS - kLead;          // first sample index of this thread
             const long long iw = tile_lo + (long long)(tid & ~31) * kS - kLead;   // first sample of this warp
+            const long long ig0 = i0 + P.goff, igw = iw + P.goff;                    // the same in hop coordinates
             int sw = __ldg(P.tile_seg + tile);
-            while (sw < P.nhop && __ldg(P.bnd + sw + 1) <= iw) ++sw;
+            while (sw < P.nhop && __ldg(P.bnd + sw + 1) <= igw) ++sw;
             int s = sw;
-            while (s < P.nhop && __ldg(P.bnd + s + 1) <= i0) ++s;
+            while (s < P.nhop && __ldg(P.bnd + s + 1) <= ig0) ++s;
             const long long kBig = 0x3fffffffffffffffLL;
-            const long long nb1 = (s < P.nhop) ? __ldg(P.bnd + s + 1) : kBig;
-            const long long nb2 = (s + 1 < P.nhop) ? __ldg(P.bnd + s + 2) : kBig;
-            const bool whole = (i0 >= 0) && (i0 + kS <= P.n) && (i0 + kS <= nb1);   // chunk inside the row and one hop
+            const long long nb1 = (s < P.nhop) ? __ldg(P.bnd + s + 1) - P.goff : kBig;     // row-local hop ends
+            const long long nb2 = (s + 1 < P.nhop) ? __ldg(P.bnd + s + 2) - P.goff : kBig;
+            const bool whole = (i0 >= P.own_lo) && (i0 + kS <= P.own_hi) && (i0 + kS <= nb1);   // chunk inside the counted range and one hop
             float2 S0 = make_float2((float)z[0], (float)z[2]);
             float2 S1 = make_float2((float)z[1], (float)z[3]);
             // step 0: the shelf alone (lane .y idles on a zero-weight copy of itself)
@@ -226,8 +229,9 @@ __global__ void __launch_bounds__(kT, 6) lufs_kernel(const __grid_constant__ Luf
                 acc0 += acc1; acc1 = 0.f;
             } else {
                 // chunks cut by hop boundaries (at most two: the host plan guarantees it) or by the row's end:
-                // samples [0, j1) -> hop s, [j1, j2) -> hop s+1, [j2, jv) -> hop s+2; samples >= jv lie beyond the row
-                const int jv = (int)max(0LL, min((long long)kS, P.n - i0));
+                // samples [jlo, j1) -> hop s, [j1, j2) -> hop s+1, [j2, jv) -> hop s+2; the rest is not counted
+                const int jv = (int)max(0LL, min((long long)kS, P.own_hi - i0));
+                const int jlo = (int)max(0LL, min((long long)kS, P.own_lo - i0));       // samples before it are not counted
                 const int j1 = (int)max(0LL, min((long long)jv, nb1 - i0));
                 const int j2 = (int)max((long long)j1, min((long long)jv, nb2 - i0));
 #pragma unroll
@@ -242,9 +246,9 @@ __global__ void __launch_bounds__(kT, 6) lufs_kernel(const __grid_constant__ Luf
                     }
                     const float t = yk * yk;
                     const int js = j - 1;                  // sample this output belongs to
-                    acc0 += (js < j1) ? t : 0.f;
-                    acc1 += (js >= j1 && js < j2) ? t : 0.f;
-                    acc2 += (js >= j2 && js < jv) ? t : 0.f;
+                    acc0 += (js >= jlo && js < j1) ? t : 0.f;
+                    acc1 += (js >= jlo && js >= j1 && js < j2) ? t : 0.f;
+                    acc2 += (js >= jlo && js >= j2 && js < jv) ? t : 0.f;
                 }
             }
             double accA = 0.0, accB = 0.0;

@@ -48,6 +48,16 @@ __global__ void __launch_bounds__(kPwThreads) row_stats_kernel(const float* __re
     }
 }
 
+// RowStats <-> three float64 vectors [sum | min | max] for the cross-rank reduction of a time-sliced file
+__global__ void row_stats_pack_kernel(const RowStats* st, int rows, double* buf) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < rows) { buf[r] = st[r].sum; buf[rows + r] = (double)ord2f(st[r].mn); buf[2 * rows + r] = (double)ord2f(st[r].mx); }
+}
+__global__ void row_stats_unpack_kernel(RowStats* st, int rows, const double* buf) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < rows) { st[r].sum = buf[r]; st[r].mn = f2ord((float)buf[rows + r]); st[r].mx = f2ord((float)buf[2 * rows + r]); }
+}
+
 __global__ void row_stats_init_kernel(RowStats* st, int rows) {
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r < rows) { st[r].sum = 0.0; st[r].mn = 0xffffffffu; st[r].mx = 0u; st[r].pad = 0; }
@@ -281,6 +291,7 @@ struct FinalArgs {
     unsigned long long seed;
     double* nonfinite;          // per track or null
     int track_base;             // mm_geom::track_base: keeps the dither stream independent of host-side chunking
+    long long frame_base;       // index of frame 0 in the whole file (time slices): dither counter
 };
 
 constexpr int kFinThreads = 256;
@@ -360,7 +371,7 @@ __global__ void __launch_bounds__(kFinThreads) finalize_kernel(const FinalArgs P
                     if (C > 1) n1 = (double)(e1 < 4 ? comp4(nz0, e1) : comp4(nz1, e1 - 4));
                 } else {
                     unsigned rnd[4];
-                    const unsigned long long fr = (unsigned long long)(i + c);
+                    const unsigned long long fr = (unsigned long long)(i + c + P.frame_base);
                     philox4x32_10((unsigned)fr, (unsigned)(fr >> 32), (unsigned)(track + P.track_base), 0u, (unsigned)P.seed, (unsigned)(P.seed >> 32), rnd);
                     n0 = tpdf_from_bits(rnd[0], rnd[1]);
                     n1 = tpdf_from_bits(rnd[2], rnd[3]);

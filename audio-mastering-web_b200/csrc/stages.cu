@@ -120,9 +120,11 @@ static int halo_tiles(const FilterPlan* const* plans, int nf) {
 }
 
 template <int M, int NF>
-static void fill_common(SweepArgs<M, NF>& A, const mm_geom* g, const FilterPlan* const* plans, const float* const* in, int nin,
+static void fill_common(const mm_ctx* c, SweepArgs<M, NF>& A, const mm_geom* g, const FilterPlan* const* plans, const float* const* in, int nin,
                         float* const* out, int nout, const Pro& pro, const Epi& epi, int pad) {
     memset(&A, 0, sizeof(A));
+    A.pk_lo = kLead + (c->slice ? c->slice->own_lo : 0);
+    A.pk_hi = kLead + (c->slice ? c->slice->own_hi : g->n) - 1;
     for (int f = 0; f < NF; ++f) {
         fill_filter<M>(A.f[f], plans[f]);
         A.tab[f] = plans[f]->dev;
@@ -212,7 +214,7 @@ static int arrange(mm_ctx* c, int nf, const FilterPlan* const* plans, const floa
 template <int M, int NF, int NIN, int DIR, int EPI, int NAUX, int NF32>
 static int run_sweep(mm_ctx* c, const mm_geom* g, const Arranged& R, int nout, const Pro& pro, int pad, const char* name) {
     SweepArgs<M, NF> A;
-    fill_common<M, NF>(A, g, R.plans, R.in, NIN, R.out, nout, pro, R.epi, pad);
+    fill_common<M, NF>(c, A, g, R.plans, R.in, NIN, R.out, nout, pro, R.epi, pad);
     return launch_sweep2<M, NF, NIN, DIR, EPI, NAUX, 1, NF32>(c, &A, halo_tiles(R.plans, NF), name);
 }
 
@@ -229,7 +231,7 @@ static int run_fwd4_split(mm_ctx* c, const mm_geom* g, const Arranged& R, const 
             S.in[j] = R.in[0];
             S.out[j] = R.out[k + 2 * j];
         }
-        fill_common<2, 2>(A[k], g, S.plans, S.in, 1, S.out, 2, pro, S.epi, pad);
+        fill_common<2, 2>(c, A[k], g, S.plans, S.in, 1, S.out, 2, pro, S.epi, pad);
     }
     return launch_sweep2<2, 2, 1, +1, EPI_STORE, 0, 1, N32SET, 2>(c, A, halo_tiles(R.plans, 4), name);
 }
@@ -347,20 +349,39 @@ int run_row_stats(mm_ctx* c, const mm_geom* g, const float* in, RowStats** st_ou
         KernelScope ks(c, "row_stats_init");
         row_stats_init_kernel<<<(rows + 255) / 256, 256, 0, c->stream>>>(st, rows);
     }
-    dim3 grid((unsigned)((g->n + kPwFramesPerBlock - 1) / kPwFramesPerBlock), (unsigned)rows);
+    // a time slice contributes its own frames only (own_lo is a multiple of 4: the float4 loads stay aligned)
+    const long long lo = c->slice ? c->slice->own_lo : 0, cnt = c->slice ? c->slice->own_hi - c->slice->own_lo : g->n;
+    dim3 grid((unsigned)((cnt + kPwFramesPerBlock - 1) / kPwFramesPerBlock), (unsigned)rows);
     {
         KernelScope ks(c, "row_stats");
-        row_stats_kernel<<<grid, kPwThreads, 0, c->stream>>>(in, g->n, g->stride, st);
+        row_stats_kernel<<<grid, kPwThreads, 0, c->stream>>>(in + lo, cnt, g->stride, st);
     }
     MM_CUDA(cudaGetLastError());
     *st_out = st;
     return 0;
 }
 
+int exchange_row_stats(mm_ctx* c, RowStats* st, int rows) {
+    const mm_slice* sl = c->slice;
+    if (!sl || !sl->allreduce) return 0;
+    double* xb;
+    MM_TRY(arena(c, SL_XCHG, (size_t)rows * 3, &xb));
+    row_stats_pack_kernel<<<(rows + 127) / 128, 128, 0, c->stream>>>(st, rows, xb);
+    MM_CUDA(cudaGetLastError());
+    if (sl->allreduce(sl->user, xb, rows, 0, 0) != 0 || sl->allreduce(sl->user, xb + rows, rows, 0, 1) != 0 ||
+        sl->allreduce(sl->user, xb + 2 * rows, rows, 0, 2) != 0) {
+        set_error("allreduce of the channel statistics failed");
+        return 1;
+    }
+    row_stats_unpack_kernel<<<(rows + 127) / 128, 128, 0, c->stream>>>(st, rows, xb);
+    MM_CUDA(cudaGetLastError());
+    return 0;
+}
+
 int run_in_scalars(mm_ctx* c, const mm_geom* g, const RowStats* st, int use_dc, int use_guard, double headroom_db,
                    double* sub, double* mul, double* peak_track, double* mean_row) {
     InScalarArgs A;
-    A.st = st; A.n = g->n; A.tracks = g->tracks; A.channels = g->channels;
+    A.st = st; A.n = c->slice ? c->slice->global_n : g->n; A.tracks = g->tracks; A.channels = g->channels;
     A.use_dc = use_dc; A.use_guard = use_guard;
     A.limit = (float)std::pow(10.0, -headroom_db / 20.0);
     A.sub = sub; A.mul = mul; A.peak_track = peak_track; A.mean_row = mean_row;
@@ -392,6 +413,7 @@ int run_finalize(mm_ctx* c, const mm_geom* g, const float* in, float* out, const
     A.in = in; A.out = out; A.n = g->n; A.stride = g->stride; A.tracks = g->tracks; A.mul = mul; A.width = width;
     A.n_fade = n_fade; A.fade_step = n_fade > 1 ? 1.0 / (double)(n_fade - 1) : 0.0;
     A.pcm = pcm; A.noise = noise; A.seed = seed; A.nonfinite = nonfinite; A.track_base = g->track_base;
+    A.frame_base = c->slice ? c->slice->global_off : 0;
     dim3 grid((unsigned)((g->n + kFinFrames - 1) / kFinFrames), (unsigned)g->tracks);
     KernelScope ks(c, pcm ? "finalize_dither_int16" : "finalize");
 #define MM_FIN(C_, PCM_, NZ_) finalize_kernel<C_, PCM_, NZ_><<<grid, kFinThreads, 0, c->stream>>>(A)
@@ -584,7 +606,9 @@ int st_dynamics(mm_ctx* c, const mm_geom* g, const float* in, float* out, double
 int st_lufs(mm_ctx* c, const mm_geom* g, const float* in, const Pro& pro, double* lufs_dev, const double* target_dev,
             double* gain_row, double* gain_db) {
     const LufsPlan* lp;
-    MM_TRY(get_lufs_plan(c, g->n, g->sr, &lp));
+    const mm_slice* sl = c->slice;
+    if (sl) MM_TRY(get_lufs_plan(c, sl->global_n, g->sr, &lp, sl->global_off, g->n));
+    else MM_TRY(get_lufs_plan(c, g->n, g->sr, &lp));
     const int rows = g->tracks * g->channels;
     unsigned long long* segsum;
     MM_TRY(arena(c, SL_SEGSUM, (size_t)rows * (size_t)std::max(lp->nseg, 1), &segsum));
@@ -619,6 +643,9 @@ int st_lufs(mm_ctx* c, const mm_geom* g, const float* in, const Pro& pro, double
         A.in = in; A.n = g->n; A.stride = g->stride; A.rows = rows; A.ntiles = lp->ntiles; A.channels = g->channels;
         A.pro_mode = pro.mode; A.pro_sub = pro.sub; A.pro_mul = pro.mul;
         A.bnd = lp->bnd; A.nhop = lp->nseg; A.tile_seg = lp->tile_seg; A.segsum = segsum;
+        A.goff = sl ? sl->global_off : 0;
+        A.own_lo = sl ? sl->own_lo : 0;
+        A.own_hi = sl ? sl->own_hi : g->n;
         A.whalo = kw->tabs.W;
         choose_segments(rows, lp->ntiles, A.whalo, capacity, &A.nseg, &A.seglen);
         const long long items = (long long)rows * A.nseg;
@@ -628,6 +655,9 @@ int st_lufs(mm_ctx* c, const mm_geom* g, const float* in, const Pro& pro, double
             lufs_kernel<<<grid, kT, kLufsSmem, c->stream>>>(A);
         }
         MM_CUDA(cudaGetLastError());
+    }
+    if (sl && sl->allreduce && lp->valid) {      // block sums of the other ranks' frames (exact: 64-bit fixed point)
+        if (sl->allreduce(sl->user, segsum, (int64_t)rows * lp->nseg, 1, 0) != 0) { set_error("allreduce of the loudness block sums failed"); return 1; }
     }
     GateArgs G;
     memset(&G, 0, sizeof(G));

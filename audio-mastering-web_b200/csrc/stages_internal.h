@@ -39,6 +39,7 @@ int sweep_bwd(mm_ctx* c, const mm_geom* g, int nf, const FilterPlan* const* plan
               float* const* out, int nout, const Epi& epi, int pad);
 
 int run_row_stats(mm_ctx* c, const mm_geom* g, const float* in, RowStats** st_out);
+int exchange_row_stats(mm_ctx* c, RowStats* st, int rows);
 int run_in_scalars(mm_ctx* c, const mm_geom* g, const RowStats* st, int use_dc, int use_guard, double headroom_db,
                    double* sub, double* mul, double* peak_track, double* mean_row);
 int run_pointwise(mm_ctx* c, const mm_geom* g, PwArgs& A, const char* name);

@@ -452,6 +452,7 @@ __global__ void __launch_bounds__(kT, Sweep2Cfg<M, NF, NIN, DIR, EPI, NAUX, ST>:
 #pragma unroll
         for (int f = 0; f < NF; ++f) tout[f] = (f < NIN) ? (tin + (size_t)f * kL) : (extra + (size_t)(f - NIN) * kL);
         const bool out_fast = fast_out(tile_lo);
+        const bool pk_fast = tile_lo >= P.pk_lo && tile_lo + kL - 1 <= P.pk_hi;
         float aux_subf = 0.f, aux_mulf = 1.f;
         double aux_muld = 1.0;
         const int aux_pmode = (EPI != EPI_STORE && P.aux_pro) ? P.pro_mode : PRO_NONE;
@@ -568,13 +569,13 @@ __global__ void __launch_bounds__(kT, Sweep2Cfg<M, NF, NIN, DIR, EPI, NAUX, ST>:
                     }
                 }
                 if (EPI != EPI_STORE) {     // output peak: one decision per float4 group
-                    if (out_fast) {
+                    if (pk_fast) {
                         pk = fmaxf(fmaxf(pk, fmaxf(fabsf(yv[0].x), fabsf(yv[0].y))), fmaxf(fabsf(yv[0].z), fabsf(yv[0].w)));
                     } else {
                         const long long q = tile_lo + cbase + 4 * uu;
 #pragma unroll
                         for (int c = 0; c < 4; ++c)
-                            if (q + c >= st_lo && q + c <= st_hi) pk = fmaxf(pk, fabsf(comp4(yv[0], c)));
+                            if (q + c >= P.pk_lo && q + c <= P.pk_hi) pk = fmaxf(pk, fabsf(comp4(yv[0], c)));
                     }
                 }
 #pragma unroll
@@ -615,7 +616,7 @@ __global__ void __launch_bounds__(kT, Sweep2Cfg<M, NF, NIN, DIR, EPI, NAUX, ST>:
                     const float res = epi_value(xa0, NAUX > 1 ? auxs[kL + off] : 0.f, yf, yd);
                     tout[0][off] = res;
                     const long long q = tile_lo + cbase + mi;
-                    if (q >= st_lo && q <= st_hi) pk = fmaxf(pk, fabsf(res));
+                    if (q >= P.pk_lo && q <= P.pk_hi) pk = fmaxf(pk, fabsf(res));
                 }
             }
         }

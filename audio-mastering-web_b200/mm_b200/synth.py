@@ -105,3 +105,35 @@ def torch_batch(track_ids, sr: int, dur_sec: float, device, channels: int = 2, o
         for c, ch in enumerate(chans):
             view[j * channels + c].copy_((ch * (p["peak"] / max(pk, 1e-30))).to(torch.float32))
     return out
+
+
+def torch_long_slice(t: int, sr: int, start: int, stop: int, device, out_rows, lead: int = 0, block: int = 1 << 22):
+    """Frames [start, stop) of the LONG-FORM variant of track ``t`` (BASELINE config 5) written into the two planar rows
+    ``out_rows`` (float32 tensor (2, >= lead + stop - start)).  Same partials / envelope / DC as ``numpy_track``; so that
+    every rank of a time-split run sees identical samples where slices overlap, the noise is white noise keyed by
+    (seed, 2^20-frame block index, channel) -- generated on the device per block -- and the level is fixed analytically
+    (peak target / bound on the partial sum) instead of by a pass over the whole file."""
+    import torch
+
+    p = track_params(t)
+    nb = 1 << 20
+    for c in range(2):
+        f, a, ph = (p["f_l"], p["a_l"], p["ph_l"]) if c == 0 else (p["f_r"], p["a_r"], p["ph_r"])
+        gain = float(p["peak"]) / (float(np.sum(a)) + 0.35 + 2e-3)
+        for b0 in range(start, stop, block):
+            b1 = min(stop, b0 + block)
+            tt = torch.arange(b0, b1, dtype=torch.float64, device=device) / sr
+            s = torch.zeros(b1 - b0, dtype=torch.float64, device=device)
+            for i in range(6):
+                s += float(a[i]) * torch.sin(2 * math.pi * float(f[i]) * tt + float(ph[i]))
+            env = 0.55 + 0.45 * torch.sin(2 * math.pi * p["env_rate"] * tt + p["env_phase"])
+            wn = torch.empty(b1 - b0, dtype=torch.float32, device=device)
+            for k in range(b0 // nb, (b1 - 1) // nb + 1):
+                g = torch.Generator(device=device)
+                g.manual_seed((int(p["noise_seed"]) * 2 + c) * 1_000_003 + k)
+                blk = torch.randn(nb, dtype=torch.float32, device=device, generator=g)
+                lo, hi = max(b0, k * nb), min(b1, (k + 1) * nb)
+                wn[lo - b0:hi - b0] = blk[lo - k * nb:hi - k * nb]
+            x = (env * (s + 0.08 * wn.to(torch.float64)) + float(p["dc"][c])) * gain
+            out_rows[c, lead + b0 - start:lead + b1 - start].copy_(x.to(torch.float32))
+    return out_rows

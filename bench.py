@@ -337,6 +337,151 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+# -------------------------------------------------------------------------------------------------------
+# BASELINE configs[4]: one 2-hour 96 kHz stereo file, time-split over the ranks (strong scaling)
+# -------------------------------------------------------------------------------------------------------
+def run_longform(args):
+    import ctypes as C
+
+    import torch
+    import torch.distributed as dist
+
+    from mm_b200 import _lib, longform, pipeline as P, synth
+    from mm_b200.engine import Engine, style_struct, TrackStats
+    from mm_b200.shard import stats_to_records
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (mm_b200 has no CPU fallback)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    eng = Engine(local)
+    sr, dur = 96000, args.sec if args.sec != DUR else 7200.0
+    n = int(round(sr * dur))
+    plan = longform.plan_slices(n, world, longform.slice_margin(sr))[rank]
+    ns = plan["stop"] - plan["start"]
+    src = eng.empty(1, 2, ns, sr)
+    with torch.cuda.stream(eng.stream):
+        src.t.zero_()
+        synth.torch_long_slice(0, sr, plan["start"], plan["stop"], eng.tdev, src.t, lead=_lib.MM_LEAD)
+        pcm = torch.empty((1, ns, 2), dtype=torch.int16, device=eng.tdev)
+        st = torch.empty(C.sizeof(TrackStats), dtype=torch.uint8, device=eng.tdev)
+    out = eng.like(src)
+    cb = longform.torch_allreduce(eng.stream, eng.tdev) if world > 1 else longform._ALLREDUCE_T()
+    sl = longform.Slice(n, plan["start"], plan["own_lo"], plan["own_hi"], cb, None)
+    style = (_lib.Style * 1)(style_struct(P.STYLE_CONFIGS["standard"], -14.0))
+    chain = _lib.CHAIN_V1 if args.chain == "v1" else _lib.CHAIN_V2
+    g = src.geom
+
+    def step(i):
+        _lib.check(eng.lib.mm_dev_master_slice(eng.ctx, C.byref(g), chain, style, src.ptr, out.ptr, C.c_void_p(pcm.data_ptr()), None,
+                                               1234 + i, C.c_void_p(st.data_ptr()), _lib.FLAG_MEASURE_OUT, C.byref(sl)))
+
+    def barrier():
+        eng.sync()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        step(i)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    eng.timing(True)
+    l0 = eng.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(eng.stream)
+    for i in range(args.steps):
+        step(args.warmup + i)
+    e1.record(eng.stream)
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = eng.launch_count() - l0
+    ktimes = eng.kernel_times()
+    eng.timing(False)
+    clocks = sampler.stop() if rank == 0 else None
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=eng.tdev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    value = dur * args.steps / (ms * 1e-3)
+    rec = stats_to_records(np.frombuffer(st.cpu().numpy().tobytes(), dtype=np.float64).reshape(1, -1))[0]
+
+    # end to end: the rank's slice from pinned host memory, its own frames' int16 back to pinned host memory
+    own = plan["own_hi"] - plan["own_lo"]
+    hin = torch.empty((ns, 2), dtype=torch.float32, pin_memory=True)
+    hpcm = torch.empty((own, 2), dtype=torch.int16, pin_memory=True)
+    with torch.cuda.stream(eng.stream):
+        il = torch.empty((1, ns, 2), dtype=torch.float32, device=eng.tdev)
+        _lib.check(eng.lib.mm_dev_interleave(eng.ctx, C.byref(g), src.ptr, C.c_void_p(il.data_ptr())))
+        eng.sync()
+        hin.copy_(il[0])
+
+        def e2e_step(i):
+            il[0].copy_(hin, non_blocking=True)
+            _lib.check(eng.lib.mm_dev_deinterleave(eng.ctx, C.byref(g), C.c_void_p(il.data_ptr()), src.ptr))
+            step(100 + i)
+            hpcm.copy_(pcm[0, plan["own_lo"]:plan["own_hi"]], non_blocking=True)
+            eng.sync()
+
+        e2e_step(0)
+        barrier()
+        t0 = time.perf_counter()
+        reps = max(1, min(args.steps, 2))
+        for i in range(reps):
+            e2e_step(1 + i)
+        torch.cuda.synchronize()
+        wall = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([wall], dtype=torch.float64, device=eng.tdev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        wall = float(t.item())
+    e2e = {"value": dur * reps / wall, "unit": UNIT, "h2d_bytes_per_step": ns * 2 * 4, "d2h_bytes_per_step": own * 2 * 2,
+           "api": "mm_dev_master_slice on a slice copied from / to pinned host memory (per rank)"}
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    peak, peak_src = measured_peak_gbs()
+    top = max(ktimes.items(), key=lambda kv: kv[1][0])
+    kname, (kms, kcnt) = top
+    alg_bytes = STREAMS.get(kname, 2) * 4.0 * 2 * ns
+    chain_gbs = CHAIN_BYTES_PER_FRAME[args.chain] * ns * args.steps / (ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": kname, "achieved": alg_bytes / (kms / kcnt * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                "frac": alg_bytes / (kms / kcnt * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": alg_bytes,
+                "chain": {"algorithmic_bytes_per_stereo_frame": CHAIN_BYTES_PER_FRAME[args.chain], "achieved": chain_gbs,
+                          "frac": chain_gbs / peak, "note": "rank 0: its slice including margins"}}
+    cb_line = None
+    if world == 1 and not args.no_cpu:
+        from oracle import chain as oc
+        x = synth.numpy_track(0, sr, 20.0)
+        t0 = time.time()
+        o = (oc.run_v1 if args.chain == "v1" else oc.run_v2)(x, sr, -14.0, "standard")
+        rng = np.random.default_rng(0)
+        oc.quantize_int16(o, (rng.random(o.shape) + rng.random(o.shape) - 1.0).astype(np.float32))
+        cb_line = {"value": 20.0 / (time.time() - t0), "unit": UNIT, "cores": 1, "kind": "port",
+                   "sample": "20 s of 96 kHz stereo through the oracle (numpy/scipy), v2 chain + TPDF int16"}
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": f"configs[4]: one {dur:.0f} s {sr} Hz stereo file, {args.chain} default chain + TPDF int16 + after-LUFS, "
+                               f"split in time over {world} GPU(s) ({longform.slice_margin(sr)} margin frames per cut side)",
+                   "chain": args.chain, "frames": n, "slice_frames_rank0": ns, "cache": "slice (GBs) exceeds L2; no flush needed"},
+        "roofline": roofline, "cpu_baseline": cb_line, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+        "check": {"lufs_out": rec["lufs_out"], "gain_db": rec["gain_db"], "peak_out": rec["peak_out"], "nonfinite": rec["nonfinite"]},
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -348,10 +493,14 @@ def main():
     ap.add_argument("--sec", type=float, default=DUR)
     ap.add_argument("--e2e-tracks", type=int, default=TRACKS)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--workload", default="batch", choices=["batch", "longform"],
+                    help="batch = BASELINE configs[1] (default, what the driver times); longform = configs[4], one long file split in time")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "longform":
+        run_longform(args)
     else:
         run_ours(args)
 

@@ -161,6 +161,31 @@ int mm_dev_master(mm_ctx*, const mm_geom*, int chain, const mm_style* styles_hos
                   const float* noise_interleaved, uint64_t dither_seed,
                   mm_track_stats* stats_dev, uint32_t flags);
 
+/* ---- one long file split in time over several GPUs (BASELINE config 5) --------------------------
+ * Each rank holds a SLICE of one track: its own frames [own_lo, own_hi) (slice-local indices) plus margins on the
+ * cut sides that are wide enough for every recurrence on the chain to forget its start (mm_slice_margin).  The
+ * slice is mastered like a track of its own; the only coupling between ranks is the chain's global scalars --
+ * channel means and peak (pipeline.py:134-149), the BS.1770 block sums (:644-664) and the output peak (:1899) --
+ * which are reduced over the ranks' OWN frames through `allreduce` (NCCL in production: mm_b200/longform.py).
+ * geom.tracks must be 1; geom.n is the slice length including margins.
+ * allreduce(user, dev_ptr, count, dtype, op): in-place over the ranks, ordered after the work already queued on
+ * the context's stream; dtype 0 = float64, 1 = int64, 2 = float32; op 0 = sum, 1 = min, 2 = max; returns 0 on
+ * success.  NULL = single rank. */
+typedef int (*mm_allreduce_fn)(void* user, void* dev_ptr, int64_t count, int dtype, int op);
+typedef struct mm_slice {
+    int64_t global_n;     /* frames of the whole file */
+    int64_t global_off;   /* index in the file of the slice's frame 0 */
+    int64_t own_lo, own_hi; /* frames of the slice this rank owns (multiples of 4 except at the file's end) */
+    mm_allreduce_fn allreduce;
+    void* user;
+} mm_slice;
+/* Margin (frames, multiple of 4096) a cut side needs at this sample rate. */
+int64_t mm_slice_margin(int32_t sr);
+int mm_dev_master_slice(mm_ctx*, const mm_geom*, int chain, const mm_style* style_host,
+                        const float* in, float* out_f32, int16_t* out_i16,
+                        const float* noise_interleaved, uint64_t dither_seed,
+                        mm_track_stats* stats_dev, uint32_t flags, const mm_slice* slice);
+
 /* Host-buffer drop-in for one call of run_mastering_pipeline / chain.process (+ optional
  * export): audio_in/out are (n, channels) interleaved float32 HOST arrays; pcm16_out may be NULL.
  * Copies in, masters `tracks` equally-shaped tracks stored back to back, copies out, syncs. */
