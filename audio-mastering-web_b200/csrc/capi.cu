@@ -580,6 +580,55 @@ int mm_dev_apply_rumble_filter(mm_ctx* c, const mm_geom* g, const float* in, flo
     return st_filtfilt_combine(c, g, p, in, out, e, none);
 }
 
+int mm_dev_apply_transient_designer(mm_ctx* c, const mm_geom* g, const float* in, float* out, double attack_gain, double sustain_gain) {
+    MM_API_BEGIN(c);
+    MM_TRY(check_geom(g));
+    // pipeline.py:1749-1752: gains clipped to [0.1, 3]; both within 0.02 of 1 -> the input object is returned
+    attack_gain = std::min(std::max(attack_gain, 0.1), 3.0);
+    sustain_gain = std::min(std::max(sustain_gain, 0.1), 3.0);
+    if (std::fabs(attack_gain - 1.0) < 0.02 && std::fabs(sustain_gain - 1.0) < 0.02) {
+        if (in != out) MM_CUDA(cudaMemcpyAsync(out, in, batch_floats(g) * sizeof(float), cudaMemcpyDeviceToDevice, c->stream));
+        return 0;
+    }
+    return st_transient_designer(c, g, in, out, attack_gain, sustain_gain);
+}
+
+int mm_dev_apply_maximizer_transient_aware(mm_ctx* c, const mm_geom* g, const float* in, float* out, double sensitivity) {
+    MM_API_BEGIN(c);
+    MM_TRY(check_geom(g));
+    return st_maximizer_transient_aware(c, g, in, out, sensitivity);
+}
+
+int mm_dev_apply_high_freq_trim(mm_ctx* c, const mm_geom* g, const float* in, float* out, double crossover_hz, double high_gain) {
+    MM_API_BEGIN(c);
+    MM_TRY(check_geom(g));
+    if (std::fabs(high_gain - 1.0) < 0.001) {     // pipeline.py:1719-1720
+        if (in != out) MM_CUDA(cudaMemcpyAsync(out, in, batch_floats(g) * sizeof(float), cudaMemcpyDeviceToDevice, c->stream));
+        return 0;
+    }
+    // low + g (x - low) = g x + (1 - g) low, then clip (pipeline.py:1724-1730)
+    const FilterPlan* p = plan_butter(c, 2, kLow, std::min(crossover_hz / (g->sr / 2.0), 0.98), 0);
+    if (!p) return 1;
+    Epi e;
+    e.mode = EPI_COMBINE;
+    e.aux0 = in;
+    e.wc = high_gain;
+    e.w[0] = 1.0 - high_gain;
+    e.clip = 1;
+    Pro none;
+    return st_filtfilt_combine(c, g, p, in, out, e, none);
+}
+
+int mm_dev_apply_stereoize(mm_ctx* c, const mm_geom* g, const float* in, float* out, double width, double delay_ms, double mix) {
+    MM_API_BEGIN(c);
+    MM_TRY(check_geom(g));
+    if (g->channels != 2) {   // pipeline.py:1355-1356
+        if (in != out) MM_CUDA(cudaMemcpyAsync(out, in, batch_floats(g) * sizeof(float), cudaMemcpyDeviceToDevice, c->stream));
+        return 0;
+    }
+    return st_haas_imager(c, g, in, out, width, delay_ms, mix);
+}
+
 int mm_dev_iir(mm_ctx* c, const mm_geom* g, const float* in, float* out, const double* b, const double* a, int ncoef,
                int zero_phase) {
     MM_API_BEGIN(c);

@@ -86,6 +86,7 @@ template <int M, int NF> struct SweepArgs {
     const double* pro_mul;   // per row (may be null)
     int aux_pro;             // apply the prologue to aux[0] too
     int epi;
+    int epi_clip;            // EPI_COMBINE: clip the result to +-1
     double w[NF], wc, trim;
     float w32[NF];
     PairK pr[(NF + 1) / 2];  // packed float32 sections (pairs 2p, 2p+1 with 2p+1 < NF32)

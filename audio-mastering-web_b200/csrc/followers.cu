@@ -1,0 +1,242 @@
+// Stages built on a pair of attack/release envelope followers (_envelope_follower_core, backend/app/pipeline.py:495-518):
+//   apply_transient_designer        (pipeline.py:1736-1768)   per channel: fast (0.5 / 5 ms) and slow (5 / 100 ms) follower of |x|
+//   apply_maximizer_transient_aware (pipeline.py:521-545)     per track: fast (0.5 / 2 ms) and slow (10 / 40 ms) follower of mean |x|
+// plus two small first-wave neighbours that needed no new kernel class:
+//   apply_high_freq_trim            (pipeline.py:1705-1733)   zero-phase low-pass + weighted recombination + clip
+//   Haas "stereoize" branch of apply_stereo_imager (pipeline.py:1388-1398)
+//
+// The follower has no associative operator; as in deesser.cu a unit (row or track) is cut into chunks that start
+// `halo` samples early from the state |v|: one step contracts the distance between two states by at least the
+// release coefficient, so after halo = 17.5 / -ln(slowest coefficient) samples the start-up error is e^-17.5 = 2.5e-8
+// of the signal peak.  Chunk 0 starts at sample 0 with the reference's own initial state and is exact.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+#include "context.h"
+#include "pointwise.cuh"
+#include "stages_internal.h"
+
+namespace mm {
+
+enum { FOL_TRANSIENT = 0, FOL_MAXIMIZER_TA = 1 };
+
+struct FolArgs {
+    const float* x;
+    float* out;
+    long long n, stride;
+    int units;             // rows (transient designer) or tracks (maximizer)
+    long long chunk, halo; // multiples of 32 samples
+    int nchunks;           // per unit
+    double f_atk, f_1matk, f_rel, f_1mrel;   // fast follower: float64 coefficients and products, float32 state --
+    double s_atk, s_1matk, s_rel, s_1mrel;   // slow follower     what numba compiles pipeline.py:495-507 to
+    float attack_gain, sustain_gain;         // transient designer
+    float sensitivity;                       // maximizer
+    DynParams dyn;                           // maximizer line (max_k, max_c, max_top)
+};
+
+__device__ __forceinline__ float fol_step_branch(float e, float v, double atk, double omatk, double rel, double omrel) {
+    const double ed = (double)e, vd = (double)v;
+    return v > e ? (float)(atk * ed + omatk * vd) : (float)(rel * ed + omrel * vd);
+}
+
+constexpr int kFolDepth = 4;
+constexpr int kFolThreads = 32;
+
+template <int MODE, int C>
+__global__ void __launch_bounds__(kFolThreads) dual_follower_kernel(const FolArgs P) {
+    __shared__ __align__(128) float ring[C][kFolDepth][kFolThreads][32];
+    const int lane = threadIdx.x;
+    const long long gid = (long long)blockIdx.x * kFolThreads + lane;
+    const long long total = (long long)P.units * P.nchunks;
+    const bool active = gid < total;
+    const int unit = active ? (int)(gid / P.nchunks) : 0;
+    const int chunk = active ? (int)(gid % P.nchunks) : 0;
+    const size_t r0 = (size_t)(unit * C) * (size_t)P.stride + kLead;
+    const long long live0 = (long long)chunk * P.chunk;
+    const long long live1 = active ? min(live0 + P.chunk, P.n) : live0;
+    const long long start = max(live0 - P.halo, 0LL);
+    const int nlines = active ? (int)((live1 - start + 31) / 32) : 0;
+    const int sx = lane & 7;
+    auto fetch = [&](int line) {
+        if (line < nlines) {
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+                const float* g = P.x + r0 + (size_t)c * (size_t)P.stride + start + 32LL * line;
+                float* s = &ring[c][line % kFolDepth][lane][0];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const unsigned d = (unsigned)__cvta_generic_to_shared(s + 4 * (u ^ sx));
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(g + 4 * u) : "memory");
+                }
+            }
+        }
+        asm volatile("cp.async.commit_group;\n" ::: "memory");
+    };
+#pragma unroll
+    for (int l = 0; l < kFolDepth - 1; ++l) fetch(l);
+    auto detector = [&](float a, float b) -> float {
+        if (MODE == FOL_TRANSIENT || C == 1) return fabsf(a);
+        return __fmul_rn(__fadd_rn(fabsf(a), fabsf(b)), 0.5f);      // np.mean(np.abs(audio), axis=1) in float32
+    };
+    float ef = 0.f, es = 0.f;
+    if (active) {
+        const float a = __ldg(P.x + r0 + start), b = C > 1 ? __ldg(P.x + r0 + (size_t)P.stride + start) : 0.f;
+        ef = es = detector(a, b);                                  // env[0] = |v0| (pipeline.py:499)
+    }
+    const int halo_lines = active ? (int)((live0 - start) / 32) : 0;
+    // the very first sample of the unit keeps env[0] = |v0| exactly: the recurrence starts at sample 1 there
+    const bool first_exact = active && start == 0;
+#pragma unroll 1
+    for (int line = 0; line < nlines; ++line) {
+        fetch(line + kFolDepth - 1);
+        asm volatile("cp.async.wait_group %0;\n" ::"n"(kFolDepth - 1) : "memory");
+        const bool livel = line >= halo_lines;
+        const long long i0 = start + 32LL * line;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const float4 va = *reinterpret_cast<const float4*>(&ring[0][line % kFolDepth][lane][4 * (u ^ sx)]);
+            float4 vb = va;
+            if (C > 1) vb = *reinterpret_cast<const float4*>(&ring[C > 1 ? 1 : 0][line % kFolDepth][lane][4 * (u ^ sx)]);
+            float4 oa, ob;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const float xa = comp4(va, c), xb = comp4(vb, c);
+                const float v = detector(xa, xb);
+                if (!(first_exact && line == 0 && u == 0 && c == 0)) {
+                    ef = fol_step_branch(ef, v, P.f_atk, P.f_1matk, P.f_rel, P.f_1mrel);
+                    es = fol_step_branch(es, v, P.s_atk, P.s_1matk, P.s_rel, P.s_1mrel);
+                }
+                if (MODE == FOL_TRANSIENT) {
+                    // pipeline.py:1761-1765, float32 throughout (Python-float gains are weak scalars)
+                    const float tr = fmaxf(__fsub_rn(ef, es), 0.f);
+                    const float ne = __fadd_rn(__fmul_rn(tr, P.attack_gain), __fmul_rn(es, P.sustain_gain));
+                    const float gain = fminf(fmaxf(__fdiv_rn(ne, __fadd_rn(ef, 1e-12f)), 0.f), 4.f);
+                    setcomp4(oa, c, fminf(fmaxf(__fmul_rn(xa, gain), -1.f), 1.f));
+                } else {
+                    // pipeline.py:533-541
+                    const float diff = fmaxf(__fsub_rn(ef, es), 0.f);
+                    const float mask = fminf(fmaxf(__fmul_rn(__fdiv_rn(diff, __fadd_rn(es, 1e-12f)), P.sensitivity), 0.f), 1.f);
+                    const float om = __fsub_rn(1.0f, mask);
+                    const float la = maximize_limit(xa, P.dyn);
+                    setcomp4(oa, c, fminf(fmaxf(__fadd_rn(__fmul_rn(la, om), __fmul_rn(xa, mask)), -1.f), 1.f));
+                    if (C > 1) {
+                        const float lb = maximize_limit(xb, P.dyn);
+                        setcomp4(ob, c, fminf(fmaxf(__fadd_rn(__fmul_rn(lb, om), __fmul_rn(xb, mask)), -1.f), 1.f));
+                    }
+                }
+            }
+            if (livel) {
+                const long long i = i0 + 4 * u;
+                float* da = P.out + r0 + i;
+                if (i + 3 < P.n) {
+                    *reinterpret_cast<float4*>(da) = oa;
+                    if (MODE == FOL_MAXIMIZER_TA && C > 1) *reinterpret_cast<float4*>(da + P.stride) = ob;
+                } else {
+                    for (int c = 0; c < 4; ++c)
+                        if (i + c < P.n) { da[c] = comp4(oa, c); if (MODE == FOL_MAXIMIZER_TA && C > 1) da[P.stride + c] = comp4(ob, c); }
+                }
+            }
+        }
+    }
+    asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+}
+
+static double fol_coef(double sr, double t) { return std::exp(-1.0 / std::max(1e-6, sr * t)); }
+
+static void fol_geometry(FolArgs& A, const mm_geom* g, double slowest) {
+    const long long nceil = ((g->n + 31) / 32) * 32;
+    long long halo = slowest < 1.0 ? (long long)std::ceil(17.5 / -std::log(slowest)) : nceil;
+    halo = std::min<long long>(((halo + 31) / 32) * 32, nceil);
+    A.halo = halo;
+    long long chunk = std::max<long long>(((halo / 2 + 31) / 32) * 32, 4096);
+    while ((long long)A.units * ((g->n + chunk - 1) / chunk) > 148LL * 8 * 32 && chunk < nceil) chunk *= 2;
+    A.chunk = chunk;
+    A.nchunks = (int)((g->n + chunk - 1) / chunk);
+}
+
+static void fol_set(FolArgs& A, double sr, double fa, double fr, double sa, double srl) {
+    const double c0 = fol_coef(sr, fa), c1 = fol_coef(sr, fr), c2 = fol_coef(sr, sa), c3 = fol_coef(sr, srl);
+    A.f_atk = c0; A.f_1matk = 1.0 - c0; A.f_rel = c1; A.f_1mrel = 1.0 - c1;
+    A.s_atk = c2; A.s_1matk = 1.0 - c2; A.s_rel = c3; A.s_1mrel = 1.0 - c3;
+}
+
+int st_transient_designer(mm_ctx* c, const mm_geom* g, const float* in, float* out, double attack_gain, double sustain_gain) {
+    FolArgs A;
+    memset(&A, 0, sizeof(A));
+    A.x = in; A.out = out; A.n = g->n; A.stride = g->stride; A.units = g->tracks * g->channels;
+    fol_set(A, (double)g->sr, 0.0005, 0.005, 0.005, 0.1);
+    A.attack_gain = (float)attack_gain; A.sustain_gain = (float)sustain_gain;
+    fol_geometry(A, g, fol_coef((double)g->sr, 0.1));
+    const long long total = (long long)A.units * A.nchunks;
+    KernelScope ks(c, "transient_designer");
+    dual_follower_kernel<FOL_TRANSIENT, 1><<<(unsigned)((total + kFolThreads - 1) / kFolThreads), kFolThreads, 0, c->stream>>>(A);
+    MM_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int st_maximizer_transient_aware(mm_ctx* c, const mm_geom* g, const float* in, float* out, double sensitivity) {
+    FolArgs A;
+    memset(&A, 0, sizeof(A));
+    A.x = in; A.out = out; A.n = g->n; A.stride = g->stride; A.units = g->tracks;
+    fol_set(A, (double)g->sr, 0.0005, 0.002, 0.01, 0.04);
+    A.sensitivity = (float)sensitivity;
+    fill_dyn(&A.dyn, 6.0, nullptr, 12.0);
+    A.dyn.max_top = (float)std::pow(10.0, -0.3 / 20.0);          // apply_maximizer alone: the ceiling, no limiter behind it
+    fol_geometry(A, g, fol_coef((double)g->sr, 0.04));
+    const long long total = (long long)A.units * A.nchunks;
+    const unsigned grid = (unsigned)((total + kFolThreads - 1) / kFolThreads);
+    KernelScope ks(c, "maximizer_transient_aware");
+    if (g->channels == 2) dual_follower_kernel<FOL_MAXIMIZER_TA, 2><<<grid, kFolThreads, 0, c->stream>>>(A);
+    else dual_follower_kernel<FOL_MAXIMIZER_TA, 1><<<grid, kFolThreads, 0, c->stream>>>(A);
+    MM_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// ---- Haas "stereoize" (pipeline.py:1388-1398) on the width-processed pair, one pass -------------------------------
+struct HaasArgs {
+    const float* in;
+    float* out;
+    long long n, stride;
+    int tracks;
+    float width, mix;
+    long long delay;
+    int apply_width;
+};
+__global__ void __launch_bounds__(256) haas_kernel(const HaasArgs P) {
+    const int track = blockIdx.y;
+    const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+    if (i >= P.n) return;
+    const size_t r0 = (size_t)(track * 2) * (size_t)P.stride + kLead, r1 = r0 + (size_t)P.stride;
+    auto widened = [&](long long k, float& l, float& r) {
+        l = P.in[r0 + k]; r = P.in[r1 + k];
+        // _imager_apply_width_stereo (pipeline.py:1329-1336)
+        const float mid = __fmul_rn(__fadd_rn(l, r), 0.5f);
+        const float side = __fmul_rn(__fmul_rn(__fsub_rn(l, r), 0.5f), P.width);
+        l = fminf(fmaxf(__fadd_rn(mid, side), -1.f), 1.f);
+        r = fminf(fmaxf(__fsub_rn(mid, side), -1.f), 1.f);
+    };
+    float l, r, dl = 0.f, dr = 0.f;
+    widened(i, l, r);
+    if (i >= P.delay) widened(i - P.delay, dl, dr);
+    P.out[r0 + i] = fminf(fmaxf(__fadd_rn(l, __fmul_rn(P.mix, dr)), -1.f), 1.f);
+    P.out[r1 + i] = fminf(fmaxf(__fadd_rn(r, __fmul_rn(P.mix, dl)), -1.f), 1.f);
+}
+
+int st_haas_imager(mm_ctx* c, const mm_geom* g, const float* in, float* out, double width, double delay_ms, double mix) {
+    if (in == out) { set_error("stereoize: in-place operation is not supported (the delayed tap reads behind the writer)"); return 1; }
+    HaasArgs A;
+    A.in = in; A.out = out; A.n = g->n; A.stride = g->stride; A.tracks = g->tracks;
+    A.width = (float)width;
+    A.mix = (float)std::min(0.35, std::max(0.0, mix));
+    long long d = std::min<long long>((long long)((double)g->sr * delay_ms / 1000.0), g->n - 1);
+    A.delay = std::max<long long>(0, d);
+    A.apply_width = 1;
+    dim3 grid((unsigned)((g->n + 255) / 256), (unsigned)g->tracks);
+    KernelScope ks(c, "stereoize_haas");
+    haas_kernel<<<grid, 256, 0, c->stream>>>(A);
+    MM_CUDA(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace mm

@@ -37,7 +37,7 @@ __device__ __forceinline__ float compress_band_f64(double x, const DynBand& b, d
 // itself is float32 here (HBM storage); the reference's float64 knee followed by its float32 cast differs
 // from this by at most one float32 ulp of the band sample.  The upward branch (ratio < 1) needs
 // log10/pow, stays in float64 and out of line so that the hot loop stays small in the instruction cache.
-__device__ __noinline__ float band_chain_upward(float y, const DynBand& b) {
+static __device__ __noinline__ float band_chain_upward(float y, const DynBand& b) {
     double raw;
     const float c = compress_band_f64((double)y, b, &raw);
     return __fmul_rn(fminf(fmaxf(c, -b.lim), b.lim), b.gain);

@@ -159,6 +159,7 @@ static void fill_common(const mm_ctx* c, SweepArgs<M, NF>& A, const mm_geom* g, 
     A.pro_mul = pro.mul;
     A.aux_pro = epi.aux_pro;
     A.epi = epi.mode;
+    A.epi_clip = epi.clip;
     A.wc = epi.wc;
     A.trim = epi.trim;
     if (epi.dyn) A.dyn = *epi.dyn;

@@ -25,6 +25,7 @@ struct Epi {                     // epilogue of a backward sweep
     double exc_gain = 0, exc_k = 2.5;
     int exc_mode = 0;
     float* peak = nullptr;
+    int clip = 0;                // clip the recombined output to +-1 (apply_high_freq_trim)
 };
 
 struct Bufs { float* E[4]; float* T[5]; };
@@ -64,6 +65,11 @@ int st_filtfilt_combine(mm_ctx* c, const mm_geom* g, const FilterPlan* plan, con
 int st_style_eq(mm_ctx* c, const mm_geom* g, const float* in, float* out, const double* gain_db, float* peak, int* fired,
                 int reset_peak);
 int st_exciter(mm_ctx* c, const mm_geom* g, const float* in, float* out, double exciter_db, int mode, float* peak);
+
+// followers.cu
+int st_transient_designer(mm_ctx* c, const mm_geom* g, const float* in, float* out, double attack_gain, double sustain_gain);
+int st_maximizer_transient_aware(mm_ctx* c, const mm_geom* g, const float* in, float* out, double sensitivity);
+int st_haas_imager(mm_ctx* c, const mm_geom* g, const float* in, float* out, double width, double delay_ms, double mix);
 
 // analyzers.cu / deesser.cu
 int st_deesser(mm_ctx* c, const mm_geom* g, const float* in, float* out, double threshold_db, double ratio, double freq_lo,

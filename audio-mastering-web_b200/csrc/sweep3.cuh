@@ -481,13 +481,14 @@ __global__ void __launch_bounds__(kT, Sweep2Cfg<M, NF, NIN, DIR, EPI, NAUX, ST>:
                     float accf = 0.f;
 #pragma unroll
                     for (int f = 0; f < NF32; ++f) accf = fmaf(P.w32[f], yf[f], accf);
-                    acc = fma(P.wc, (double)xa, (double)accf);     // wc == 1 at every call site: exact product
+                    acc = fma(P.wc, (double)xa, (double)accf);     // wc == 1 on the chains (exact product); 0.9 in apply_high_freq_trim
                 } else {
                     acc = P.wc * (double)xa;
                 }
 #pragma unroll
                 for (int f = NF32; f < NF; ++f) acc = fma(P.w[f], yd[f], acc);
-                return (float)(acc * P.trim);
+                const float res = (float)(acc * P.trim);
+                return P.epi_clip ? fminf(fmaxf(res, -1.f), 1.f) : res;
             } else if (EPI == EPI_EXCITER) {
                 const float hf = yflt(0);
                 const float sat = exciter_sat(hf, P.exc_mode, (float)P.exc_k);

@@ -79,6 +79,10 @@ SIGNATURES = {
     "mm_dev_spectrum_bars": (_i, [_vp, _gp, _vp, _i, _vp]),
     "mm_dev_stereo_correlation": (_i, [_vp, _gp, _vp, _vp, _vp]),
     "mm_dev_master": (_i, [_vp, _gp, _i, C.POINTER(Style), _vp, _vp, _vp, _vp, _u64, _vp, _u32]),
+    "mm_dev_apply_transient_designer": (_i, [_vp, _gp, _vp, _vp, _d, _d]),
+    "mm_dev_apply_maximizer_transient_aware": (_i, [_vp, _gp, _vp, _vp, _d]),
+    "mm_dev_apply_high_freq_trim": (_i, [_vp, _gp, _vp, _vp, _d, _d]),
+    "mm_dev_apply_stereoize": (_i, [_vp, _gp, _vp, _vp, _d, _d, _d]),
     "mm_slice_margin": (_i64, [C.c_int32]),
     "mm_dev_master_slice": (_i, [_vp, _gp, _i, C.POINTER(Style), _vp, _vp, _vp, _vp, _u64, _vp, _u32, _vp]),
     "mm_master_host": (_i, [_vp, _i, C.c_int32, _i64, C.c_int32, C.c_int32, C.POINTER(Style), _vp, _vp, _vp, _vp, _u64,

@@ -9,7 +9,7 @@ modules/equalizer.py:83-85), and the result is clipped to +-1 with nan_to_num (c
 The audio is uploaded once, every module is a CUDA stage call on the device-resident batch, and the
 result is downloaded once.  When the configuration is exactly ``default_config(target, style)`` the
 whole chain runs as the fused sweep plan (``mm_dev_master``), which is what ``bench.py`` times.
-Second-wave modules (reverb, transient-aware maximizer, linear-phase EQ) raise
+Second-wave modules (reverb, linear-phase EQ) raise
 ``NotImplementedError`` when enabled instead of silently passing audio through.
 """
 from __future__ import annotations
@@ -127,7 +127,7 @@ class MaximizerModule(BaseModule):
         self.sensitivity = float(sensitivity)
 
     def _process(self, eng, b, **kw):
-        raise NotImplementedError("apply_maximizer_transient_aware is second-wave scope (SURVEY 8f)")
+        return eng.stage("apply_maximizer_transient_aware", b, _d(self.sensitivity))      # modules/maximizer.py -> pipeline.py:521-545
 
 
 class NormalizeLUFSModule(BaseModule):

@@ -162,13 +162,43 @@ def apply_harmonic_exciter(audio: np.ndarray, sr: int, exciter_db: float = 0.0, 
 
 def apply_stereo_imager(audio: np.ndarray, width: float = 1.0, stereoize_delay_ms: float = 0.0, stereoize_mix: float = 0.12,
                         sr=None, band_widths=None, crossovers_hz=None) -> np.ndarray:
-    """backend/app/pipeline.py:1339-1398, plain width mode (4-band / Haas modes are second-wave)."""
+    """backend/app/pipeline.py:1339-1398: plain width mode and the Haas "stereoize" cross-delay (the 4-band mode is
+    second-wave)."""
     a = np.asarray(audio)
     if a.ndim == 1 or a.shape[1] == 1:
         return audio
-    if band_widths is not None or (stereoize_delay_ms and stereoize_delay_ms > 0):
-        raise NotImplementedError("multiband / Haas imager is second-wave scope (SURVEY 8f)")
+    if band_widths is not None and len(band_widths) == 4 and sr and sr > 0:
+        raise NotImplementedError("4-band imager is second-wave scope (SURVEY 8f)")
+    if stereoize_delay_ms and stereoize_delay_ms > 0 and sr and sr > 0 and stereoize_mix > 0 and \
+            min(int(sr * stereoize_delay_ms / 1000.0), a.shape[0] - 1) > 0:
+        eng, b, mono = _up(audio, sr)         # the delayed tap reads behind the writer: not in place
+        return _down(eng, eng.stage("apply_stereoize", b, C.c_double(width), C.c_double(stereoize_delay_ms), C.c_double(stereoize_mix)), mono)
     return _stage("apply_stereo_imager", audio, sr or 44100, C.c_double(width))
+
+
+def apply_transient_designer(audio: np.ndarray, sr: int, attack_gain: float = 1.0, sustain_gain: float = 1.0) -> np.ndarray:
+    """backend/app/pipeline.py:1736-1768."""
+    ag, sg_ = float(np.clip(attack_gain, 0.1, 3.0)), float(np.clip(sustain_gain, 0.1, 3.0))
+    if abs(ag - 1.0) < 0.02 and abs(sg_ - 1.0) < 0.02:
+        return audio                      # the reference returns the very same object
+    return _stage("apply_transient_designer", audio, sr, C.c_double(ag), C.c_double(sg_))
+
+
+def apply_maximizer_transient_aware(audio: np.ndarray, sr: int, sensitivity: float = 0.5) -> np.ndarray:
+    """backend/app/pipeline.py:521-545."""
+    return _stage("apply_maximizer_transient_aware", audio, sr, C.c_double(float(sensitivity)))
+
+
+HIGH_FREQ_TRIM_CROSSOVER_HZ = 5000.0
+HIGH_FREQ_TRIM_GAIN = 0.9
+
+
+def apply_high_freq_trim(audio: np.ndarray, sr: int, crossover_hz: float = HIGH_FREQ_TRIM_CROSSOVER_HZ,
+                         high_gain: float = HIGH_FREQ_TRIM_GAIN) -> np.ndarray:
+    """backend/app/pipeline.py:1705-1733."""
+    if abs(high_gain - 1.0) < 0.001:
+        return audio
+    return _stage("apply_high_freq_trim", audio, sr, C.c_double(crossover_hz), C.c_double(high_gain))
 
 
 def apply_rumble_filter(audio: np.ndarray, sr: int, cutoff_hz: float = 80.0) -> np.ndarray:
@@ -317,15 +347,44 @@ def run_mastering_pipeline(audio: np.ndarray, sr: int, target_lufs: float = -14.
                            progress_callback: Optional[Callable[[int, str], None]] = None, denoise_strength: float = 0.0,
                            transient_attack: float = 1.0, transient_sustain: float = 1.0, reference_audio=None,
                            reference_sr=None, reference_strength: float = 0.8, trace_ctx=None) -> np.ndarray:
-    """backend/app/pipeline.py:1800-1909 (default path: no denoise / reference match / transient designer)."""
-    if denoise_strength > 0 or reference_audio is not None or abs(transient_attack - 1.0) > 0.01 or abs(transient_sustain - 1.0) > 0.01:
-        raise NotImplementedError("denoise / reference match / transient designer are second-wave scope (SURVEY 8f)")
+    """backend/app/pipeline.py:1800-1909.  The default path is one fused device call; a transient-designer request
+    (which sits between the style EQ and the exciter, :1879-1889) takes the stage-by-stage path.  Denoise and
+    reference match are second-wave (FFT-class stages)."""
+    if denoise_strength > 0 or reference_audio is not None:
+        raise NotImplementedError("spectral denoise / reference match are second-wave scope (SURVEY 8f)")
     style = style if style in STYLE_CONFIGS else "standard"
-    out = master_batch([audio], sr, [style], [target_lufs], chain="v1")["audio"][0]
+    if abs(transient_attack - 1.0) > 0.02 or abs(transient_sustain - 1.0) > 0.02:
+        out = _run_v1_stagewise(audio, sr, target_lufs, style, transient_attack, transient_sustain)
+    else:
+        out = master_batch([audio], sr, [style], [target_lufs], chain="v1")["audio"][0]
     if progress_callback is not None:      # stage boundaries are fused on the device; report them in order
         for pct, msg in _V1_PROGRESS:
             progress_callback(pct, msg)
     return out
+
+
+def _run_v1_stagewise(audio, sr, target_lufs, style, transient_attack, transient_sustain):
+    """run_mastering_pipeline stage by stage (pipeline.py:1833-1909), for the options the fused chain does not carry."""
+    cfg = STYLE_CONFIGS[style]
+    a = remove_dc_offset(audio)
+    a = remove_intersample_peaks(a, headroom_db=0.5)
+    a = apply_target_curve(a, sr)
+    a = apply_deesser(a, sr)
+    a = apply_dynamics(a, sr)
+    if cfg.get("parallel_mix", 0.0) > 0.01:
+        a = apply_parallel_compression(a, sr, mix=cfg["parallel_mix"])
+    a = normalize_lufs(a, sr, target_lufs)
+    a = apply_final_spectral_balance(a, sr)
+    a = apply_style_eq(a, sr, style)
+    a = apply_transient_designer(a, sr, attack_gain=transient_attack, sustain_gain=transient_sustain)
+    if cfg.get("exciter_db", 0.0) > 0.05:
+        a = apply_harmonic_exciter(a, sr, cfg["exciter_db"])
+    if abs(cfg.get("imager_width", 1.0) - 1.0) > 0.01:
+        a = apply_stereo_imager(a, cfg["imager_width"])
+    a = remove_intersample_peaks(a, headroom_db=0.5)
+    a = apply_output_edge_fade_in(a, sr, fade_ms=6.0)
+    a = np.clip(a, -1.0, 1.0).astype(np.float32)
+    return np.nan_to_num(a, nan=0.0, posinf=1.0, neginf=-1.0)
 
 
 def export_audio(samples: np.ndarray, sr: int, channels: int, out_format: str = "wav", dither_type: str = "tpdf",

@@ -54,6 +54,30 @@ def measured_peak_gbs():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+class _StdoutToStderr:
+    """NCCL prints its version banner to stdout when it initialises; the contract is ONE JSON line there."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+
+    def __exit__(self, *a):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+
+
+def _init_nccl(local):
+    import torch
+    import torch.distributed as dist
+    with _StdoutToStderr():
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        t = torch.zeros(1, device=torch.device("cuda", local))
+        dist.all_reduce(t)                 # communicator creation (and its banner) happens here
+        torch.cuda.synchronize()
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
 
@@ -179,7 +203,7 @@ def run_ours(args):
         raise SystemExit("bench.py: no CUDA device (mm_b200 has no CPU fallback)")
     torch.cuda.set_device(local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        _init_nccl(local)
     eng = Engine(local)
     tracks, dur, sr = args.tracks, args.sec, SR
     n = int(round(sr * dur))
@@ -357,7 +381,7 @@ def run_longform(args):
         raise SystemExit("bench.py: no CUDA device (mm_b200 has no CPU fallback)")
     torch.cuda.set_device(local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        _init_nccl(local)
     eng = Engine(local)
     sr, dur = 96000, args.sec if args.sec != DUR else 7200.0
     n = int(round(sr * dur))

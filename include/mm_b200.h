@@ -124,6 +124,15 @@ int mm_dev_apply_harmonic_exciter(mm_ctx*, const mm_geom*, const float* in, floa
 int mm_dev_apply_stereo_imager(mm_ctx*, const mm_geom*, const float* in, float* out, double width);
 /* apply_rumble_filter                  backend/app/pipeline.py:1449-1469 */
 int mm_dev_apply_rumble_filter(mm_ctx*, const mm_geom*, const float* in, float* out, double cutoff_hz);
+/* second-wave stages built on the same two primitives */
+/* apply_transient_designer             backend/app/pipeline.py:1736-1768 */
+int mm_dev_apply_transient_designer(mm_ctx*, const mm_geom*, const float* in, float* out, double attack_gain, double sustain_gain);
+/* apply_maximizer_transient_aware      backend/app/pipeline.py:521-545 */
+int mm_dev_apply_maximizer_transient_aware(mm_ctx*, const mm_geom*, const float* in, float* out, double sensitivity);
+/* apply_high_freq_trim                 backend/app/pipeline.py:1705-1733 */
+int mm_dev_apply_high_freq_trim(mm_ctx*, const mm_geom*, const float* in, float* out, double crossover_hz, double high_gain);
+/* apply_stereo_imager with stereoize_delay_ms > 0 (single-band width + Haas cross-delay), :1339-1398; in != out */
+int mm_dev_apply_stereoize(mm_ctx*, const mm_geom*, const float* in, float* out, double width, double delay_ms, double mix);
 /* generic zero-phase / causal IIR on every row: scipy filtfilt / lfilter semantics of
  * _safe_filtfilt (backend/app/pipeline.py:36-52). nb == na in {3, 5}; zero_phase 0 -> lfilter. */
 int mm_dev_iir(mm_ctx*, const mm_geom*, const float* in, float* out,

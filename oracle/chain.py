@@ -469,6 +469,77 @@ def apply_stereo_imager(audio, width=1.0):
 
 
 # -- chains -------------------------------------------------------------------------------------
+# -- second-wave stages on the same primitives ----------------------------------
+def apply_transient_designer(audio, sr, attack_gain=1.0, sustain_gain=1.0):
+    """pipeline.py:1736-1768: fast (0.5 / 5 ms) and slow (5 / 100 ms) followers of |x| per channel."""
+    attack_gain = float(np.clip(attack_gain, 0.1, 3.0))
+    sustain_gain = float(np.clip(sustain_gain, 0.1, 3.0))
+    if abs(attack_gain - 1.0) < 0.02 and abs(sustain_gain - 1.0) < 0.02:
+        return audio
+    a, mono = _cols(audio)
+    out = np.zeros_like(a, dtype=np.float32)
+    for ch in range(a.shape[1]):
+        x = a[:, ch].astype(np.float32)
+        ax = np.abs(x)
+        fast = envelope_follower(ax, float(sr), 0.0005, 0.005)
+        slow = envelope_follower(ax, float(sr), 0.005, 0.1)
+        transient = np.maximum(fast - slow, 0.0)
+        new_env = transient * attack_gain + slow * sustain_gain
+        gain = np.clip(new_env / (fast + 1e-12), 0.0, 4.0).astype(np.float32)
+        out[:, ch] = np.clip(x * gain, -1.0, 1.0)
+    return _uncols(out, mono)
+
+
+def apply_maximizer_transient_aware(audio, sr, sensitivity=0.5):
+    """pipeline.py:521-545: the maximizer backs off where a fast follower of mean |x| runs ahead of a slow one."""
+    a, mono = _cols(audio)
+    a = a.astype(np.float32)
+    limited = np.array(apply_maximizer(a), dtype=np.float32).reshape(a.shape)
+    det = np.mean(np.abs(a), axis=1).astype(np.float32)
+    fast = envelope_follower(det, float(sr), 0.0005, 0.002)
+    slow = envelope_follower(det, float(sr), 0.01, 0.04)
+    diff = np.maximum(fast - slow, 0.0)
+    mask = np.clip(diff / (slow + 1e-12) * float(sensitivity), 0.0, 1.0)
+    mask = np.minimum(mask, 1.0)
+    for ch in range(a.shape[1]):
+        limited[:, ch] = limited[:, ch] * (1.0 - mask) + a[:, ch] * mask
+    return _uncols(np.clip(limited, -1.0, 1.0).astype(np.float32), mono)
+
+
+def apply_high_freq_trim(audio, sr, crossover_hz=5000.0, high_gain=0.9):
+    """pipeline.py:1705-1733: low = filtfilt(butter(2, fc)), out = low + high_gain * (x - low), clip."""
+    if abs(high_gain - 1.0) < 0.001:
+        return audio
+    a, mono = _cols(audio)
+    b_lp, a_lp = sg.butter(2, min(crossover_hz / (sr / 2.0), 0.98), btype="low", output="ba")
+    out = a.copy().astype(np.float32)
+    for ch in range(out.shape[1]):
+        low = zero_phase(b_lp, a_lp, out[:, ch].astype(np.float64)).astype(np.float32)
+        high = out[:, ch].astype(np.float32) - low
+        out[:, ch] = low + high_gain * high
+    return _uncols(np.clip(out, -1.0, 1.0).astype(np.float32), mono)
+
+
+def apply_stereoize(audio, sr, width=1.0, delay_ms=8.0, mix=0.12):
+    """apply_stereo_imager with the Haas cross-delay (pipeline.py:1339-1398, single-band width)."""
+    if audio.ndim == 1 or audio.shape[1] == 1:
+        return audio
+    wide = np.asarray(apply_stereo_imager(audio, width) if True else audio, dtype=np.float32)
+    if width == 1.0:      # the reference still runs the mid/side arithmetic (and its clip) for width 1
+        left, right = audio[:, 0].astype(np.float32), audio[:, 1].astype(np.float32)
+        mid = (left + right) * np.float32(0.5)
+        side = (left - right) * np.float32(0.5) * np.float32(width)
+        wide = np.column_stack([np.clip(mid + side, -1.0, 1.0), np.clip(mid - side, -1.0, 1.0)]).astype(np.float32)
+    out_l, out_r = wide[:, 0], wide[:, 1]
+    delay_n = max(0, min(int(sr * delay_ms / 1000.0), audio.shape[0] - 1))
+    m = min(0.35, max(0.0, float(mix)))
+    if delay_ms > 0 and m > 0 and delay_n > 0:
+        dr = np.concatenate([np.zeros(delay_n, dtype=out_r.dtype), out_r[:-delay_n]])
+        dl = np.concatenate([np.zeros(delay_n, dtype=out_l.dtype), out_l[:-delay_n]])
+        out_l, out_r = np.clip(out_l + m * dr, -1.0, 1.0), np.clip(out_r + m * dl, -1.0, 1.0)
+    return np.column_stack([out_l, out_r]).astype(np.float32)
+
+
 def _finalize(a):
     out = np.ascontiguousarray(np.clip(a, -1.0, 1.0).astype(np.float32))
     np.nan_to_num(out, copy=False, nan=0.0, posinf=1.0, neginf=-1.0)

@@ -1,0 +1,52 @@
+#!/usr/bin/env python
+"""Golden vectors of the second-wave ("PRO") stages, produced by the UNMODIFIED reference (build container only):
+
+    python tests/golden/make_golden_pro.py      ->  tests/golden/pro_stages_48k.npz
+
+Same harness as make_golden.py (oracle/ref_harness.py).  Input: the reference's own seeded recipe
+(backend/tests/test_mastering_regression_windows.py:32-36: default_rng(42), 48 kHz, sigma 0.04), plain and x6.
+"""
+from __future__ import annotations
+
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REPO = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, REPO)
+sys.path.insert(0, os.path.join(REPO, "audio-mastering-web_b200"))
+
+from oracle import ref_harness  # noqa: E402
+
+
+def main():
+    P = ref_harness.load().pipeline
+    sr, n = 48000, 24000
+    x = (0.04 * np.random.default_rng(42).standard_normal((n, 2))).astype(np.float32)
+    x[:, 1] = (0.6 * x[:, 0] + 0.8 * x[:, 1]).astype(np.float32)
+    loud = (x * np.float32(6.0)).astype(np.float32)
+    # a percussive variant: bursts make the fast and the slow follower part ways
+    env = (np.arange(n) % 6000 < 600).astype(np.float32) * 0.9 + 0.1
+    perc = (loud * env[:, None]).astype(np.float32)
+    st = {
+        "input": x, "sr": np.int64(sr), "perc": perc,
+        "transient_punch": P.apply_transient_designer(perc, sr, attack_gain=1.6, sustain_gain=0.8),
+        "transient_soft": P.apply_transient_designer(perc, sr, attack_gain=0.7, sustain_gain=1.3),
+        "transient_mono": P.apply_transient_designer(np.ascontiguousarray(perc[:, 0]), sr, attack_gain=1.4, sustain_gain=1.0),
+        "maximizer_ta": P.apply_maximizer_transient_aware(perc, sr, sensitivity=0.5),
+        "maximizer_ta_mono": P.apply_maximizer_transient_aware(np.ascontiguousarray(perc[:, 0]), sr, sensitivity=0.8),
+        "hf_trim": P.apply_high_freq_trim(loud, sr),
+        "hf_trim_custom": P.apply_high_freq_trim(x, sr, crossover_hz=3000.0, high_gain=0.8),
+        "haas": P.apply_stereo_imager(x, 1.2, stereoize_delay_ms=8.0, stereoize_mix=0.12, sr=sr),
+        "haas_loud": P.apply_stereo_imager(loud, 1.0, stereoize_delay_ms=12.0, stereoize_mix=0.3, sr=sr),
+    }
+    st = {k: (np.asarray(v, dtype=np.float32) if isinstance(v, np.ndarray) else v) for k, v in st.items()}
+    path = os.path.join(HERE, "pro_stages_48k.npz")
+    np.savez_compressed(path, **st)
+    print({k: np.shape(v) for k, v in st.items()}, "%.0f KB" % (os.path.getsize(path) / 1024))
+
+
+if __name__ == "__main__":
+    main()

@@ -121,3 +121,46 @@ def test_scan_is_deterministic_and_linear(gpu_lib):
     # spot check the tail against scipy on the last 200k samples' worth of context
     ref = sg.filtfilt(bb, aa, x[:, 0].astype(np.float64))
     assert _err(y1[:, 0], ref) <= 1e-6
+
+
+def test_pro_stages_against_reference_golden(gpu_lib):
+    """Second-wave stages (transient designer, transient-aware maximizer, high-frequency trim, Haas
+    stereoize) against the reference's own outputs (tests/golden/make_golden_pro.py)."""
+    from mm_b200 import pipeline as P
+    g = load_golden("pro_stages_48k")
+    sr, x, perc = int(g["sr"]), g["input"], g["perc"]
+    loud = (x * np.float32(6.0)).astype(np.float32)
+    got = {
+        "transient_punch": P.apply_transient_designer(perc, sr, 1.6, 0.8),
+        "transient_soft": P.apply_transient_designer(perc, sr, 0.7, 1.3),
+        "transient_mono": P.apply_transient_designer(np.ascontiguousarray(perc[:, 0]), sr, 1.4, 1.0),
+        "maximizer_ta": P.apply_maximizer_transient_aware(perc, sr, 0.5),
+        "maximizer_ta_mono": P.apply_maximizer_transient_aware(np.ascontiguousarray(perc[:, 0]), sr, 0.8),
+        "hf_trim": P.apply_high_freq_trim(loud, sr),
+        "hf_trim_custom": P.apply_high_freq_trim(x, sr, 3000.0, 0.8),
+        "haas": P.apply_stereo_imager(x, 1.2, stereoize_delay_ms=8.0, stereoize_mix=0.12, sr=sr),
+        "haas_loud": P.apply_stereo_imager(loud, 1.0, stereoize_delay_ms=12.0, stereoize_mix=0.3, sr=sr),
+    }
+    worst = {}
+    for k, v in got.items():
+        assert np.shape(v) == g[k].shape and np.asarray(v).dtype == np.float32, k
+        worst[k] = float(np.max(np.abs(np.asarray(v, dtype=np.float64) - g[k])))
+        print(f"[parity] {k}: {worst[k]:.3e}")
+    assert max(worst.values()) <= 2e-6, worst
+    # bypass conventions (pipeline.py:1751-1752, :1719-1720): the very same object comes back
+    assert P.apply_transient_designer(x, sr, 1.0, 1.01) is x
+    assert P.apply_high_freq_trim(x, sr, high_gain=1.0) is x
+
+
+def test_follower_chunking_is_invisible(gpu_lib):
+    """The dual-follower kernel cuts rows into chunks with a contraction halo: a long row (many chunks) must equal the
+    oracle's single sequential pass."""
+    from mm_b200 import pipeline as P, synth
+    from oracle import chain as oc
+    sr = 44100
+    x = synth.numpy_track(9, sr, 12.0)
+    x = (x * (0.2 + 0.8 * (np.arange(x.shape[0]) % 11025 < 1500))[:, None]).astype(np.float32)
+    e1 = float(np.max(np.abs(P.apply_transient_designer(x, sr, 1.8, 0.6).astype(np.float64) - oc.apply_transient_designer(x, sr, 1.8, 0.6))))
+    e2 = float(np.max(np.abs(P.apply_maximizer_transient_aware(x, sr, 0.7).astype(np.float64) - oc.apply_maximizer_transient_aware(x, sr, 0.7))))
+    print(f"[parity] 12 s transient designer {e1:.3e}, transient-aware maximizer {e2:.3e}")
+    assert e1 <= 2e-6 and e2 <= 2e-6

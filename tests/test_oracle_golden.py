@@ -68,6 +68,28 @@ def test_single_stages_match_reference_golden():
         assert err <= 2e-7, (k, err)
 
 
+def test_pro_stages_match_reference_golden():
+    """Second-wave stages against tests/golden/make_golden_pro.py's run of the reference."""
+    g = load_golden("pro_stages_48k")
+    sr, x, perc = int(g["sr"]), g["input"], g["perc"]
+    loud = (x * np.float32(6.0)).astype(np.float32)
+    got = {
+        "transient_punch": oc.apply_transient_designer(perc, sr, 1.6, 0.8),
+        "transient_soft": oc.apply_transient_designer(perc, sr, 0.7, 1.3),
+        "transient_mono": oc.apply_transient_designer(np.ascontiguousarray(perc[:, 0]), sr, 1.4, 1.0),
+        "maximizer_ta": oc.apply_maximizer_transient_aware(perc, sr, 0.5),
+        "maximizer_ta_mono": oc.apply_maximizer_transient_aware(np.ascontiguousarray(perc[:, 0]), sr, 0.8),
+        "hf_trim": oc.apply_high_freq_trim(loud, sr),
+        "hf_trim_custom": oc.apply_high_freq_trim(x, sr, 3000.0, 0.8),
+        "haas": oc.apply_stereoize(x, sr, 1.2, 8.0, 0.12),
+        "haas_loud": oc.apply_stereoize(loud, sr, 1.0, 12.0, 0.3),
+    }
+    for k, v in got.items():
+        assert np.shape(v) == g[k].shape, k
+        err = np.max(np.abs(np.asarray(v, dtype=np.float64) - g[k]))
+        assert err <= 1e-7, (k, err)      # measured: bit equal (numba's fastmath does not change these roundings here)
+
+
 def test_analyzers_match_reference_golden():
     g = load_golden("analyzers")
     for tag in "abc":
