@@ -706,7 +706,7 @@ int mm_dev_master_slice(mm_ctx* c, const mm_geom* g, int chain, const mm_style* 
     if (!slice) return master_impl(c, g, chain, style, in, out, pcm, noise, seed, stats_dev, flags);
     MM_TRY(check_geom(g));
     if (g->tracks != 1) { set_error("mm_dev_master_slice: one track (file) per call"); return 1; }
-    if (slice->own_lo < 0 || slice->own_hi > g->n || slice->own_lo >= slice->own_hi || (slice->own_lo & 3) || slice->global_off < 0 ||
+    if (slice->own_lo < 0 || slice->own_hi > g->n || slice->own_lo >= slice->own_hi || (slice->own_lo & 3) || slice->global_off < 0 || (slice->global_off & 1) ||
         slice->global_off + g->n > slice->global_n) {
         set_error("mm_dev_master_slice: bad slice (own frames must lie inside the slice, own_lo a multiple of 4, slice inside the file)");
         return 1;

@@ -125,13 +125,20 @@ __device__ __forceinline__ int16_t quantize16(float x, double noise) {
     const int q = __double2loint(__dadd_rn(d, 6755399441055744.0));
     return (int16_t)min(max(q, -32768), 32767);
 }
-// (rand + rand - 1.0), pipeline.py:830-832, from 2 x 32 counter-based random bits.  The uniforms are
-// built in the exponent-1 binade by bit placement ([1, 2) - 1), no integer->float conversion; unlike the
-// reference the sum is not rounded to float32 (finer noise resolution, same triangular distribution).
-__device__ __forceinline__ double tpdf_from_bits(unsigned a, unsigned b) {
-    const double ua = __hiloint2double((int)(0x3FF00000u | (a >> 12)), (int)(a << 20));
-    const double ub = __hiloint2double((int)(0x3FF00000u | (b >> 12)), (int)(b << 20));
-    return (ua + ub) - 3.0;
+
+// TPDF dither noise (rand + rand - 1.0, pipeline.py:830-832) from counter-based random bits.
+// One Philox4x32-10 call serves TWO frames: each 32-bit word gives one TPDF sample from its two 16-bit halves,
+//   n = (hi16 + lo16) / 65536 - 1  in (-1, 1)   (triangular on a 2^-16 LSB lattice).
+// Counter = (frame >> 1, track); word (frame & 1) * 2 + channel.  The 10 rounds are ~100 integer instructions, which
+// made the finalise pass ALU bound at one call per frame.
+__device__ __forceinline__ double tpdf16(unsigned w) {
+    const unsigned s = (w >> 16) + (w & 0xffffu);                       // 0 .. 131070
+    const double d = __hiloint2double(0x43300000, (int)s) - 4503599627370496.0;   // exactly s (2^52 bit placement)
+    return fma(d, 1.0 / 65536.0, -1.0);
+}
+__device__ __forceinline__ void dither_words(unsigned long long frame, int track, unsigned long long seed, unsigned (&rnd)[4]) {
+    const unsigned long long pair = frame >> 1;
+    philox4x32_10((unsigned)pair, (unsigned)(pair >> 32), (unsigned)track, 0u, (unsigned)seed, (unsigned)(seed >> 32), rnd);
 }
 
 __global__ void __launch_bounds__(kPwThreads) pointwise_kernel(const PwArgs P) {
@@ -223,9 +230,8 @@ __global__ void __launch_bounds__(kPwThreads) pointwise_kernel(const PwArgs P) {
                         } else {
                             unsigned rnd[4];
                             const unsigned long long fr = (unsigned long long)(i + c);
-                            philox4x32_10((unsigned)fr, (unsigned)(fr >> 32), (unsigned)(track + P.track_base), 0u,
-                                          (unsigned)P.seed, (unsigned)(P.seed >> 32), rnd);
-                            n0 = tpdf_from_bits(rnd[0], rnd[1]); n1 = tpdf_from_bits(rnd[2], rnd[3]);
+                            dither_words(fr, track + P.track_base, P.seed, rnd);
+                            n0 = tpdf16(rnd[(fr & 1) * 2]); n1 = tpdf16(rnd[(fr & 1) * 2 + 1]);
                         }
                         q[c * C] = quantize16(l, n0);
                         if (C > 1) q[c * C + 1] = quantize16(rr, n1);
@@ -329,6 +335,7 @@ __global__ void __launch_bounds__(kFinThreads) finalize_kernel(const FinalArgs P
         if (i >= P.n) continue;
         const bool full = i + 3 < P.n;
         int16_t q[8];
+        unsigned rnd[4] = {0u, 0u, 0u, 0u};
         float4 nz0 = make_float4(0.f, 0.f, 0.f, 0.f), nz1 = nz0;
         if (PCM && NOISE) {
             const float* np_ = P.noise + ((size_t)track * (size_t)P.n + (size_t)i) * C;
@@ -370,11 +377,11 @@ __global__ void __launch_bounds__(kFinThreads) finalize_kernel(const FinalArgs P
                     n0 = (double)(e0 < 4 ? comp4(nz0, e0) : comp4(nz1, e0 - 4));
                     if (C > 1) n1 = (double)(e1 < 4 ? comp4(nz0, e1) : comp4(nz1, e1 - 4));
                 } else {
-                    unsigned rnd[4];
+                    // i and frame_base are even: frames (c, c + 1) of an even c share one Philox call
                     const unsigned long long fr = (unsigned long long)(i + c + P.frame_base);
-                    philox4x32_10((unsigned)fr, (unsigned)(fr >> 32), (unsigned)(track + P.track_base), 0u, (unsigned)P.seed, (unsigned)(P.seed >> 32), rnd);
-                    n0 = tpdf_from_bits(rnd[0], rnd[1]);
-                    n1 = tpdf_from_bits(rnd[2], rnd[3]);
+                    if ((c & 1) == 0) dither_words(fr, track + P.track_base, P.seed, rnd);
+                    n0 = tpdf16(rnd[(c & 1) * 2]);
+                    n1 = tpdf16(rnd[(c & 1) * 2 + 1]);
                 }
                 q[c * C] = quantize16(l, n0);
                 if (C > 1) q[c * C + 1] = quantize16(rr, n1);
@@ -416,11 +423,10 @@ __global__ void __launch_bounds__(kPwThreads) quantize_kernel(const QuantArgs P)
     if (i >= P.n) return;
     const size_t fi = (size_t)track * (size_t)P.n + (size_t)i;
     unsigned rnd[4] = {0, 0, 0, 0};
-    if (!P.noise) philox4x32_10((unsigned)i, (unsigned)((unsigned long long)i >> 32), (unsigned)(track + P.track_base), 0u,
-                                (unsigned)P.seed, (unsigned)(P.seed >> 32), rnd);
+    if (!P.noise) dither_words((unsigned long long)i, track + P.track_base, P.seed, rnd);
     for (int c = 0; c < C; ++c) {
         const float x = P.in[(size_t)(track * C + c) * (size_t)P.stride + kLead + i];
-        const double nz = P.noise ? (double)P.noise[fi * C + c] : tpdf_from_bits(rnd[2 * c], rnd[2 * c + 1]);
+        const double nz = P.noise ? (double)P.noise[fi * C + c] : tpdf16(rnd[(i & 1) * 2 + c]);
         P.pcm[fi * C + c] = quantize16(x, nz);
     }
 }

@@ -256,10 +256,20 @@ int sweep_fwd(mm_ctx* c, const mm_geom* g, int nf, int nin, const FilterPlan* co
     MM_FWD(2, 1, 1, 0) MM_FWD(2, 1, 1, 1)
     MM_FWD(2, 2, 1, 0) MM_FWD(2, 2, 1, 1) MM_FWD(2, 2, 1, 2)
     MM_FWD(2, 2, 2, 0) MM_FWD(2, 2, 2, 1) MM_FWD(2, 2, 2, 2)
-    if (m == 2 && nf == 4 && nin == 1 && getenv("MM_SPLIT4")) {   // experiment: measured slower than one 4-section CTA
+    if (m == 2 && nf == 4 && nin == 1 && getenv("MM_SPLIT4") && atoi(getenv("MM_SPLIT4")) == 2) {   // experiment: co-scheduled half-section CTAs, measured slower
         if (R.n32 == 0) return run_fwd4_split<0>(c, g, R, pro, pad, "sweep_fwd_m2_f4_i1");
         if (R.n32 == 2) return run_fwd4_split<1>(c, g, R, pro, pad, "sweep_fwd_m2_f4_i1");
         if (R.n32 == 4) return run_fwd4_split<2>(c, g, R, pro, pad, "sweep_fwd_m2_f4_i1");
+    }
+    if (m == 2 && nf == 4 && nin == 1 && getenv("MM_SPLIT4") && atoi(getenv("MM_SPLIT4")) == 1) {
+        // two 2-section sweeps over the same input (6 streams instead of 5, but 6 CTAs per SM instead of 3)
+        const FilterPlan* pa[2] = {R.plans[0], R.plans[2]};
+        const FilterPlan* pb[2] = {R.plans[1], R.plans[3]};
+        float* oa[2] = {R.out[0], R.out[2]};
+        float* ob[2] = {R.out[1], R.out[3]};
+        const float* i1[1] = {R.in[0]};
+        MM_TRY(sweep_fwd(c, g, 2, 1, pa, i1, oa, pro, pad));
+        return sweep_fwd(c, g, 2, 1, pb, i1, ob, pro, pad);
     }
     MM_FWD(2, 4, 1, 0) MM_FWD(2, 4, 1, 2) MM_FWD(2, 4, 1, 4)
     MM_FWD(4, 1, 1, 0)

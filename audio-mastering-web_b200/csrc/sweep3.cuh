@@ -525,7 +525,7 @@ __global__ void __launch_bounds__(kT, Sweep2Cfg<M, NF, NIN, DIR, EPI, NAUX, ST>:
         } else if (!inj_thread) {
             // a recombining epilogue keeps the loop rolled (2 float4 groups in flight): fully unrolled, the
             // hoisted aux / input loads cost ~100 extra registers and halve the occupancy
-#pragma unroll (EPI == EPI_STORE ? kS / 4 : 2)
+#pragma unroll (EPI == EPI_STORE ? kS / 4 : (NF32 == NF ? 4 : 2))
             for (int u = 0; u < kS / 4; ++u) {
                 const int uu = (DIR > 0) ? u : (kS / 4 - 1 - u);
                 const int off = cbase + ((4 * uu) ^ cx);
