@@ -650,6 +650,13 @@ int st_lufs(mm_ctx* c, const mm_geom* g, const float* in, const Pro& pro, double
             A.k.g[j][0] = make_float2((float)kw->tabs.g[(size_t)j * 4 + 0], (float)kw->tabs.g[(size_t)j * 4 + 1]);
             A.k.g[j][1] = make_float2((float)kw->tabs.g[(size_t)j * 4 + 2], (float)kw->tabs.g[(size_t)j * 4 + 3]);
         }
+        for (int k = 0; k < 4; ++k)
+            for (int h = 0; h < 2; ++h) {
+                for (int d = 0; d < 5; ++d)
+                    A.Pw2[d][k][h] = make_float2((float)kw->tabs.Pw[(size_t)d * 16 + (2 * h) * 4 + k], (float)kw->tabs.Pw[(size_t)d * 16 + (2 * h + 1) * 4 + k]);
+                for (int w = 0; w <= kNW; ++w)
+                    A.Qw2[w][k][h] = make_float2((float)kw->tabs.Qpow[(size_t)w * 16 + (2 * h) * 4 + k], (float)kw->tabs.Qpow[(size_t)w * 16 + (2 * h + 1) * 4 + k]);
+            }
         A.tab = kw->dev;
         A.in = in; A.n = g->n; A.stride = g->stride; A.rows = rows; A.ntiles = lp->ntiles; A.channels = g->channels;
         A.pro_mode = pro.mode; A.pro_sub = pro.sub; A.pro_mul = pro.mul;
