@@ -174,27 +174,65 @@ static int master_impl(mm_ctx* c, const mm_geom* g, int chain, const mm_style* s
     //    a track's samples
     MM_CUDA(cudaMemsetAsync(d_peakbits, 0, (size_t)T * sizeof(float), c->stream));
     MM_TRY(st_final_balance(c, g, out, out, pgain, d_peakbits));
-    // 7./8. apply_style_eq, apply_harmonic_exciter on runs of tracks that share a style signature
-    for (int t0 = 0; t0 < T;) {
-        int t1 = t0 + 1;
-        while (t1 < T && sig[t1] == sig[t0]) ++t1;
-        mm_geom sub = *g;
-        sub.tracks = t1 - t0;
-        float* base = out + (size_t)t0 * C * (size_t)g->stride;
-        float* pk = d_peakbits + t0;
-        bool fires = false;
-        for (int b = 0; b < 5; ++b) fires |= std::fabs(sig[t0].eq[b]) >= 0.05;
-        fires |= sig[t0].exciter_db != 0.0;
-        if (fires) {
-            int fired = 0;
-            // a later stage re-tracks the peak from scratch for these tracks
-            MM_TRY(st_style_eq(c, &sub, base, base, sig[t0].eq, pk, &fired, /*reset_peak=*/1));
-            if (sig[t0].exciter_db != 0.0) {
-                MM_CUDA(cudaMemsetAsync(pk, 0, (size_t)sub.tracks * sizeof(float), c->stream));
-                MM_TRY(st_exciter(c, &sub, base, base, sig[t0].exciter_db, 0, pk));
-            }
+    // 7./8. apply_style_eq, apply_harmonic_exciter per GROUP of tracks that share a style signature (wherever they sit
+    //       in the batch: the sweeps visit a group's rows through a device row list, one launch per sweep and group)
+    {
+        std::vector<int> group(T, -1);
+        int ngroups = 0;
+        std::vector<int> rep;
+        for (int t = 0; t < T; ++t) {
+            for (int k = 0; k < ngroups && group[t] < 0; ++k)
+                if (sig[rep[k]] == sig[t]) group[t] = k;
+            if (group[t] < 0) { group[t] = ngroups++; rep.push_back(t); }
         }
-        t0 = t1;
+        std::vector<int> rowlist;
+        std::vector<int> off(ngroups + 1, 0);
+        for (int k = 0; k < ngroups; ++k) {
+            for (int t = 0; t < T; ++t)
+                if (group[t] == k) for (int ch = 0; ch < C; ++ch) rowlist.push_back(t * C + ch);
+            off[k + 1] = (int)rowlist.size();
+        }
+        int* d_rows = nullptr;
+        bool any_fires = false;
+        for (int k = 0; k < ngroups; ++k) {
+            for (int b = 0; b < 5; ++b) any_fires |= std::fabs(sig[rep[k]].eq[b]) >= 0.05;
+            any_fires |= sig[rep[k]].exciter_db != 0.0;
+        }
+        if (any_fires && ngroups > 1) {
+            MM_TRY(arena(c, SL_ROWMAP, rowlist.size(), &d_rows));
+            MM_CUDA(cudaMemcpyAsync(d_rows, rowlist.data(), rowlist.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+            MM_CUDA(cudaStreamSynchronize(c->stream));      // rowlist is a host temporary
+        }
+        for (int k = 0; k < ngroups; ++k) {
+            const StyleSig& sg_ = sig[rep[k]];
+            bool fires = false;
+            for (int b = 0; b < 5; ++b) fires |= std::fabs(sg_.eq[b]) >= 0.05;
+            fires |= sg_.exciter_db != 0.0;
+            if (!fires) continue;
+            if (d_rows) { c->row_map = d_rows + off[k]; c->row_map_rows = off[k + 1] - off[k]; }
+            // the group's tracks re-track their output peak from scratch in the last stage that touches them
+            std::vector<int> members;
+            for (int t = 0; t < T; ++t) if (group[t] == k) members.push_back(t);
+            auto reset_peaks = [&]() -> int {
+                for (size_t a0 = 0; a0 < members.size();) {
+                    size_t a1 = a0 + 1;
+                    while (a1 < members.size() && members[a1] == members[a1 - 1] + 1) ++a1;
+                    MM_CUDA(cudaMemsetAsync(d_peakbits + members[a0], 0, (a1 - a0) * sizeof(float), c->stream));
+                    a0 = a1;
+                }
+                return 0;
+            };
+            int rc = reset_peaks();
+            int fired = 0;
+            if (rc == 0) rc = st_style_eq(c, g, out, out, sg_.eq, d_peakbits, &fired, /*reset_peak=*/0);
+            if (rc == 0 && sg_.exciter_db != 0.0) {
+                rc = reset_peaks();
+                if (rc == 0) rc = st_exciter(c, g, out, out, sg_.exciter_db, 0, d_peakbits);
+            }
+            c->row_map = nullptr;
+            c->row_map_rows = 0;
+            if (rc != 0) return rc;
+        }
     }
     // 9. apply_stereo_imager: folded into the final pass; tracks with an active imager need their
     //    post-imager peak first (read-only pass over those runs)

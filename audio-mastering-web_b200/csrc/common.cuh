@@ -94,6 +94,7 @@ template <int M, int NF> struct SweepArgs {
     double exc_gain, exc_k;
     int exc_mode;
     float* peak;             // per track |out| max (float bits, atomicMax) or null
+    const int* row_map;      // optional: the sweep visits rows row_map[0 .. rows) of the batch (tracks that share a style)
     long long pk_lo, pk_hi;  // row positions (inclusive) whose outputs count towards the peak (a time slice's own frames)
 };
 

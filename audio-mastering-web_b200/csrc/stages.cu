@@ -123,6 +123,7 @@ template <int M, int NF>
 static void fill_common(const mm_ctx* c, SweepArgs<M, NF>& A, const mm_geom* g, const FilterPlan* const* plans, const float* const* in, int nin,
                         float* const* out, int nout, const Pro& pro, const Epi& epi, int pad) {
     memset(&A, 0, sizeof(A));
+    A.row_map = c->row_map;
     A.pk_lo = kLead + (c->slice ? c->slice->own_lo : 0);
     A.pk_hi = kLead + (c->slice ? c->slice->own_hi : g->n) - 1;
     for (int f = 0; f < NF; ++f) {
@@ -151,7 +152,7 @@ static void fill_common(const mm_ctx* c, SweepArgs<M, NF>& A, const mm_geom* g, 
     A.aux[1] = epi.aux1;
     A.n = g->n;
     A.stride = g->stride;
-    A.rows = g->tracks * g->channels;
+    A.rows = c->row_map ? c->row_map_rows : g->tracks * g->channels;
     A.pad = pad;
     A.channels = g->channels;
     A.pro_mode = pro.mode;

@@ -239,7 +239,7 @@ __global__ void __launch_bounds__(kT, Sweep2Cfg<M, NF, NIN, DIR, EPI, NAUX, ST>:
     const int items = P.rows * PP.nseg;
 #pragma unroll 1
     for (int item = blockIdx.x / NSET; item < items; item += gridDim.x / NSET) {
-    const int row = item % P.rows;
+    const int row = P.row_map ? __ldg(P.row_map + item % P.rows) : item % P.rows;
     const int seg = item / P.rows;
     const int t_live = seg * PP.seglen;
     const int t_end = min(P.ntiles, t_live + PP.seglen);

@@ -206,6 +206,10 @@ def run_ours(args):
         _init_nccl(local)
     eng = Engine(local)
     tracks, dur, sr = args.tracks, args.sec, SR
+    mixed = args.workload == "mixed"
+    if mixed:      # BASELINE configs[2]: 48 kHz, genre presets cycling over the GLOBAL track index, 128 tracks per GPU
+        sr = 48000
+        tracks = args.tracks if args.tracks != TRACKS else 128
     n = int(round(sr * dur))
     chain = _lib.CHAIN_V1 if args.chain == "v1" else _lib.CHAIN_V2
 
@@ -216,7 +220,17 @@ def run_ours(args):
         src.t.zero_()
         synth.torch_batch(ids, sr, dur, eng.tdev, out=src.t, row_stride=src.stride, lead=_lib.MM_LEAD)
     out = eng.like(src)
-    styles = [style_struct(P.STYLE_CONFIGS["standard"], -14.0) for _ in range(tracks)]
+    names = list(P.STYLE_CONFIGS)
+    style_names = [names[t % len(names)] if mixed else "standard" for t in ids]
+    styles = [style_struct(P.STYLE_CONFIGS[s], P.STYLE_CONFIGS[s]["lufs"] if mixed else -14.0) for s in style_names]
+    # algorithmic bytes per stereo frame of each track: 8 (W_base + 5 n_style_bands + 5 [exciter fires])
+    wbase = 64.5 if args.chain == "v1" else 54.5
+    def _alg_bytes(sn):
+        cfg = P.STYLE_CONFIGS[sn]
+        nb = sum(1 for k in ("sub", "bass", "mids", "presence", "air") if abs(cfg.get(k, 0.0)) >= 0.05)
+        exc = (cfg.get("exciter_db", 0.0) > 0.05) if args.chain == "v1" else (abs(cfg.get("exciter_db", 0.0)) >= 0.05)
+        return 8.0 * (wbase + 5 * nb + 5 * (1 if exc else 0))
+    alg_per_frame = float(np.mean([_alg_bytes(sn) for sn in style_names]))
     arr = (_lib.Style * tracks)(*styles)
     with torch.cuda.stream(eng.stream):
         pcm = torch.empty((tracks, n, 2), dtype=torch.int16, device=eng.tdev)
@@ -287,6 +301,7 @@ def run_ours(args):
             del il
         torch.cuda.synchronize()
         earr = (_lib.Style * e_tracks)(*styles[:e_tracks])
+        e_sr = sr
 
         def e2e_step(i):
             _lib.check(eng.lib.mm_master_host(eng.ctx, chain, e_tracks, n, 2, sr, earr, C.c_void_p(hin.data_ptr()), None,
@@ -329,11 +344,11 @@ def run_ours(args):
         except Exception:
             traffic = None
     ksum = sum(v[0] for v in ktimes.values())
-    chain_gbs = CHAIN_BYTES_PER_FRAME[args.chain] * tracks * n * world * args.steps / (ms * 1e-3) / 1e9
+    chain_gbs = alg_per_frame * tracks * n * world * args.steps / (ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
                 "kernel_share_of_step": kms / ksum,
-                "chain": {"algorithmic_bytes_per_stereo_frame": CHAIN_BYTES_PER_FRAME[args.chain], "achieved": chain_gbs / world,
+                "chain": {"algorithmic_bytes_per_stereo_frame": alg_per_frame, "achieved": chain_gbs / world,
                           "frac": chain_gbs / world / peak},
                 "kernels": {k: {"ms_per_launch": v[0] / v[1], "launches_per_step": v[1] / args.steps,
                                 "gbs": STREAMS.get(k, 0) * 4.0 * rows_n / (v[0] / v[1] * 1e-3) / 1e9} for k, v in
@@ -348,10 +363,13 @@ def run_ours(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"configs[1]: {tracks} synthetic {dur:.0f} s {sr} Hz stereo tracks per GPU, {args.chain} default chain "
-                               f"(style standard, -14 LUFS) + TPDF dither to int16 + after-LUFS",
+        "config": {"workload": (f"configs[2]: {tracks} synthetic {dur:.0f} s {sr} Hz stereo tracks per GPU, genre presets cycling over the "
+                                f"global track index (STYLE_CONFIGS order) at their own LUFS targets, {args.chain} chain + TPDF int16 + after-LUFS"
+                                if mixed else
+                                f"configs[1]: {tracks} synthetic {dur:.0f} s {sr} Hz stereo tracks per GPU, {args.chain} default chain "
+                                f"(style standard, -14 LUFS) + TPDF dither to int16 + after-LUFS"),
                    "chain": args.chain, "tracks_per_gpu": tracks, "frames_per_track": n,
-                   "cache": "inputs (4.06 GB per GPU) exceed L2; no flush needed", "storage": "float32 streams, float64 recurrence state"},
+                   "cache": f"inputs ({tracks * n * 8 / 1e9:.2f} GB per GPU) exceed L2; no flush needed", "storage": "float32 streams, float64 recurrence state"},
         "roofline": roofline, "cpu_baseline": cb, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
         "check": {"lufs_out_mean": float(np.mean(lufs_out)), "lufs_out_min": float(np.min(lufs_out)),
                   "lufs_out_max": float(np.max(lufs_out)), "nonfinite": nonfinite},
@@ -506,6 +524,151 @@ def run_longform(args):
         dist.destroy_process_group()
 
 
+# -------------------------------------------------------------------------------------------------------
+# BASELINE configs[3]: analyzer-only path over 30 s clips (LUFS + gating, 4x true peak, correlation, spectrum bars)
+# -------------------------------------------------------------------------------------------------------
+def run_analyze(args):
+    import ctypes as C
+
+    import torch
+    import torch.distributed as dist
+
+    from mm_b200 import _lib, shard, synth
+    from mm_b200.engine import Engine
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (mm_b200 has no CPU fallback)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        _init_nccl(local)
+    eng = Engine(local)
+    sr, dur = SR, args.sec if args.sec != DUR else 30.0
+    total = args.tracks if args.tracks != TRACKS else 10000
+    clips = shard.local_count(total, world, rank)
+    sub = min(clips, 2500)                         # clips per device batch: 26.5 GB resident
+    n = int(round(sr * dur))
+    src = eng.empty(sub, 2, n, sr)
+    distinct = min(sub, 64)
+    with torch.cuda.stream(eng.stream):
+        src.t.zero_()
+        synth.torch_batch(list(range(distinct)), sr, dur, eng.tdev, out=src.t, row_stride=src.stride, lead=_lib.MM_LEAD)
+        for k in range(distinct, sub, distinct):   # fill the batch with copies of the 64 distinct clips
+            m = min(distinct, sub - k)
+            src.t[2 * k:2 * (k + m)].copy_(src.t[:2 * m])
+        res = {k: torch.empty(sub * w, dtype=torch.float64, device=eng.tdev) for k, w in
+               (("lufs", 1), ("tp", 1), ("corr", 1), ("peak", 1), ("bars0", 64), ("bars1", 64), ("bars2", 64))}
+    g = src.geom
+    nbatch = (clips + sub - 1) // sub
+    ptr = lambda t: C.c_void_p(t.data_ptr())   # noqa: E731
+
+    def step(i):
+        for _ in range(nbatch):
+            _lib.check(eng.lib.mm_dev_measure_lufs(eng.ctx, C.byref(g), src.ptr, ptr(res["lufs"])))
+            _lib.check(eng.lib.mm_dev_true_peak(eng.ctx, C.byref(g), src.ptr, ptr(res["tp"])))
+            _lib.check(eng.lib.mm_dev_stereo_correlation(eng.ctx, C.byref(g), src.ptr, ptr(res["corr"]), ptr(res["peak"])))
+            for v in range(3):
+                _lib.check(eng.lib.mm_dev_spectrum_bars(eng.ctx, C.byref(g), src.ptr, v, ptr(res[f"bars{v}"])))
+
+    def barrier():
+        eng.sync()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        step(i)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    eng.timing(True)
+    l0 = eng.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(eng.stream)
+    for i in range(args.steps):
+        step(i)
+    e1.record(eng.stream)
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = eng.launch_count() - l0
+    ktimes = eng.kernel_times()
+    eng.timing(False)
+    clocks = sampler.stop() if rank == 0 else None
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=eng.tdev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    done = nbatch * sub * world
+    value = done * dur * args.steps / (ms * 1e-3)
+    # end to end: one sub-batch of clips from pinned host memory, results back to the host
+    hin = torch.empty((sub, n, 2), dtype=torch.float32, pin_memory=True)
+    with torch.cuda.stream(eng.stream):
+        il = torch.empty((sub, n, 2), dtype=torch.float32, device=eng.tdev)
+        _lib.check(eng.lib.mm_dev_interleave(eng.ctx, C.byref(g), src.ptr, ptr(il)))
+        eng.sync()
+        hin.copy_(il)
+        hres = {k: torch.empty(v.shape, dtype=torch.float64, pin_memory=True) for k, v in res.items()}
+
+        def e2e_step():
+            il.copy_(hin, non_blocking=True)
+            _lib.check(eng.lib.mm_dev_deinterleave(eng.ctx, C.byref(g), ptr(il), src.ptr))
+            _lib.check(eng.lib.mm_dev_measure_lufs(eng.ctx, C.byref(g), src.ptr, ptr(res["lufs"])))
+            _lib.check(eng.lib.mm_dev_true_peak(eng.ctx, C.byref(g), src.ptr, ptr(res["tp"])))
+            _lib.check(eng.lib.mm_dev_stereo_correlation(eng.ctx, C.byref(g), src.ptr, ptr(res["corr"]), ptr(res["peak"])))
+            for v in range(3):
+                _lib.check(eng.lib.mm_dev_spectrum_bars(eng.ctx, C.byref(g), src.ptr, v, ptr(res[f"bars{v}"])))
+            for k in res:
+                hres[k].copy_(res[k], non_blocking=True)
+            eng.sync()
+
+        e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        e2e_step()
+        torch.cuda.synchronize()
+        wall = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([wall], dtype=torch.float64, device=eng.tdev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        wall = float(t.item())
+    e2e = {"value": world * sub * dur / wall, "unit": "audio-s/s", "h2d_bytes_per_step": sub * n * 8,
+           "d2h_bytes_per_step": int(sum(v.numel() for v in res.values()) * 8), "clips_per_step": sub,
+           "api": "mm_dev_measure_lufs / true_peak / stereo_correlation / spectrum_bars on clips copied from pinned host memory"}
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    peak, peak_src = measured_peak_gbs()
+    top = max(ktimes.items(), key=lambda kv: kv[1][0])
+    kname, (kms, kcnt) = top
+    alg = 4.0 * 2 * n * sub                               # one read of the batch per analyzer kernel
+    lufs_host = res["lufs"].cpu().numpy()
+    line = {
+        "metric": "analyzed audio-seconds per wall-second (integrated LUFS, 4x true peak, sample peak, correlation, 3x64 spectrum bars)",
+        "value": value, "unit": "audio-s/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic (64 distinct clips, replicated)",
+        "config": {"workload": f"configs[3]: analyzer-only path over {total} synthetic {dur:.0f} s {sr} Hz stereo clips "
+                               f"({clips} per GPU in device batches of {sub})", "clips": total, "frames_per_clip": n,
+                   "cache": f"batch ({sub * n * 8 / 1e9:.1f} GB) exceeds L2; no flush needed"},
+        "roofline": {"bound": "tensor" if False else "hbm", "kernel": kname, "achieved": alg / (kms / kcnt * 1e-3) / 1e9, "peak": peak,
+                     "unit": "GB/s", "frac": alg / (kms / kcnt * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": alg,
+                     "path": {"algorithmic_bytes_per_stereo_frame": 8.0, "achieved": 8.0 * done * n * args.steps / (ms * 1e-3) / 1e9 / world,
+                              "note": "SURVEY 8d counts ONE fused read; this round runs three reading kernels (meter, true-peak FIR, "
+                                      "correlation) -- the FIR is FP32-FMA bound (81 MAC/sample), not HBM bound"},
+                     "kernels": {k: {"ms_per_launch": v[0] / v[1], "launches_per_step": v[1] / args.steps} for k, v in
+                                 sorted(ktimes.items(), key=lambda kv: -kv[1][0])[:8]}},
+        "cpu_baseline": None, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+        "check": {"lufs_mean": float(np.mean(lufs_host)), "lufs_min": float(np.min(lufs_host)), "lufs_max": float(np.max(lufs_host))},
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -517,14 +680,17 @@ def main():
     ap.add_argument("--sec", type=float, default=DUR)
     ap.add_argument("--e2e-tracks", type=int, default=TRACKS)
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--workload", default="batch", choices=["batch", "longform"],
-                    help="batch = BASELINE configs[1] (default, what the driver times); longform = configs[4], one long file split in time")
+    ap.add_argument("--workload", default="batch", choices=["batch", "mixed", "analyze", "longform"],
+                    help="batch = BASELINE configs[1] (default, what the driver times); mixed = configs[2] (48 kHz, mixed presets); "
+                         "analyze = configs[3] (analyzer-only over 30 s clips); longform = configs[4], one long file split in time")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
         run_reference(args)
     elif args.workload == "longform":
         run_longform(args)
+    elif args.workload == "analyze":
+        run_analyze(args)
     else:
         run_ours(args)
 

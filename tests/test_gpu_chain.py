@@ -208,3 +208,22 @@ def test_master_host_pipelined_chunks_equal_one_shot(P, monkeypatch):
     dev = P.master_batch(tracks, sr, names, chain="v2")
     for i in range(len(names)):
         assert np.array_equal(one[0][i], dev["audio"][i]), i
+
+
+def test_config1_full_length_track_both_chains_vs_oracle(P):
+    """BASELINE configs[0] (doc/Pre-Master.wav is absent from the reference tree: generator track 0, 44.1 kHz, 180 s,
+    SURVEY 8d C1) through both default chains at -14 LUFS against the CPU oracle at FULL length: float32 samples
+    within 1e-4, integrated loudness within 0.01 LU, true peak within 0.01 dB."""
+    from mm_b200 import synth
+    from oracle import chain as oc
+    sr = 44100
+    x = synth.numpy_track(0, sr, 180.0)
+    for which in ("v2", "v1"):
+        ref = (oc.run_v1 if which == "v1" else oc.run_v2)(x.copy(), sr, -14.0, "standard")
+        res = P.master_batch([x], sr, ["standard"], [-14.0], chain=which, measure=True)
+        out = res["audio"][0]
+        e = _err(out, ref)
+        dl = abs(res["stats"][0]["lufs_out"] - oc.measure_lufs(ref, sr))
+        dtp = abs(P.true_peak_dbfs(out, sr) - oc.true_peak_dbfs(ref))
+        print(f"[parity] C1 {which} 180 s: max|gpu-oracle| = {e:.3e}, dLUFS = {dl:.2e}, dTP = {dtp:.2e} dB")
+        assert e <= 1e-4 and dl <= 0.01 and dtp <= 0.01
