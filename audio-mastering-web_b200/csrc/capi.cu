@@ -657,6 +657,18 @@ int mm_dev_apply_high_freq_trim(mm_ctx* c, const mm_geom* g, const float* in, fl
     return st_filtfilt_combine(c, g, p, in, out, e, none);
 }
 
+int mm_dev_apply_stereo_imager_4band(mm_ctx* c, const mm_geom* g, const float* in, float* out, const double* band_widths,
+                                     const double* crossovers_hz) {
+    MM_API_BEGIN(c);
+    MM_TRY(check_geom(g));
+    if (!band_widths) { set_error("mm_dev_apply_stereo_imager_4band: band_widths is null"); return 1; }
+    if (g->channels != 2) {   // pipeline.py:1355-1356
+        if (in != out) MM_CUDA(cudaMemcpyAsync(out, in, batch_floats(g) * sizeof(float), cudaMemcpyDeviceToDevice, c->stream));
+        return 0;
+    }
+    return st_imager4(c, g, in, out, band_widths, crossovers_hz);
+}
+
 int mm_dev_apply_stereoize(mm_ctx* c, const mm_geom* g, const float* in, float* out, double width, double delay_ms, double mix) {
     MM_API_BEGIN(c);
     MM_TRY(check_geom(g));
@@ -702,6 +714,43 @@ int mm_dev_quantize_int16(mm_ctx* c, const mm_geom* g, const float* in, int16_t*
     QuantArgs Q;
     Q.in = in; Q.n = g->n; Q.stride = g->stride; Q.tracks = g->tracks; Q.channels = g->channels;
     Q.pcm = pcm; Q.noise = noise; Q.seed = seed; Q.track_base = g->track_base;
+    Q.noise_planar = nullptr; Q.noise_scale = 1.f;
+    return run_quantize(c, Q);
+}
+
+// _dither_noise_ns_e / _dither_noise_ns_itu (pipeline.py:835-877) + the quantiser: white = 2 rand - 1 (float32), shaped by a
+// causal IIR from zero state -- ns_e: y[n] = x[n] - x[n-1] + 0.99 y[n-1]; ns_itu: lfilter([1,-2,1], [1,-1.96,0.9604]) --
+// scaled by 0.9 in float32, added to samples * 32767 in float64.  The shaping filter is one forward sweep (float64 state).
+int mm_dev_quantize_int16_shaped(mm_ctx* c, const mm_geom* g, const float* in, int16_t* pcm, const float* uniform, uint64_t seed,
+                                 int shape) {
+    MM_API_BEGIN(c);
+    MM_TRY(check_geom(g));
+    if (shape != 1 && shape != 2) { set_error("mm_dev_quantize_int16_shaped: shape must be 1 (ns_e) or 2 (ns_itu)"); return 1; }
+    if (g->n < (shape == 1 ? 4 : 8)) {      // pipeline.py:840-841 / :861-862: TPDF for very short buffers
+        set_error("mm_dev_quantize_int16_shaped: buffer too short for noise shaping (the reference falls back to TPDF: use mm_dev_quantize_int16)");
+        return 1;
+    }
+    Bufs B;
+    MM_TRY(get_bufs(c, g, &B));
+    WhiteArgs W;
+    W.uniform = uniform; W.out = B.T[0]; W.n = g->n; W.stride = g->stride; W.tracks = g->tracks; W.channels = g->channels;
+    W.seed = seed; W.track_base = g->track_base;
+    MM_TRY(run_white_noise(c, W));
+    Ba ba;
+    ba.m = 2;
+    if (shape == 1) { ba.b[0] = 1.0; ba.b[1] = -1.0; ba.b[2] = 0.0; ba.a[0] = 1.0; ba.a[1] = -0.99; ba.a[2] = 0.0; }
+    else { ba.b[0] = 1.0; ba.b[1] = -2.0; ba.b[2] = 1.0; ba.a[0] = 1.0; ba.a[1] = -1.96; ba.a[2] = 0.9604; }
+    const FilterPlan* p = get_plan_mode(c, ba, kDf2tF64);
+    if (!p) return 1;
+    const FilterPlan* pl[1] = {p};
+    const float* i1[1] = {B.T[0]};
+    float* o1[1] = {B.T[1]};
+    Pro none;
+    MM_TRY(sweep_fwd(c, g, 1, 1, pl, i1, o1, none, 0));
+    QuantArgs Q;
+    Q.in = in; Q.n = g->n; Q.stride = g->stride; Q.tracks = g->tracks; Q.channels = g->channels;
+    Q.pcm = pcm; Q.noise = nullptr; Q.seed = seed; Q.track_base = g->track_base;
+    Q.noise_planar = B.T[1]; Q.noise_scale = 0.9f;
     return run_quantize(c, Q);
 }
 

@@ -210,6 +210,7 @@ __global__ void __launch_bounds__(256) haas_kernel(const HaasArgs P) {
     const size_t r0 = (size_t)(track * 2) * (size_t)P.stride + kLead, r1 = r0 + (size_t)P.stride;
     auto widened = [&](long long k, float& l, float& r) {
         l = P.in[r0 + k]; r = P.in[r1 + k];
+        if (!P.apply_width) return;        // the pair is already the merged output of the 4-band mode
         // _imager_apply_width_stereo (pipeline.py:1329-1336)
         const float mid = __fmul_rn(__fadd_rn(l, r), 0.5f);
         const float side = __fmul_rn(__fmul_rn(__fsub_rn(l, r), 0.5f), P.width);
@@ -227,14 +228,60 @@ int st_haas_imager(mm_ctx* c, const mm_geom* g, const float* in, float* out, dou
     if (in == out) { set_error("stereoize: in-place operation is not supported (the delayed tap reads behind the writer)"); return 1; }
     HaasArgs A;
     A.in = in; A.out = out; A.n = g->n; A.stride = g->stride; A.tracks = g->tracks;
-    A.width = (float)width;
+    A.apply_width = width == width;       // NaN: skip the mid/side step
+    A.width = A.apply_width ? (float)width : 1.f;
     A.mix = (float)std::min(0.35, std::max(0.0, mix));
     long long d = std::min<long long>((long long)((double)g->sr * delay_ms / 1000.0), g->n - 1);
     A.delay = std::max<long long>(0, d);
-    A.apply_width = 1;
     dim3 grid((unsigned)((g->n + 255) / 256), (unsigned)g->tracks);
     KernelScope ks(c, "stereoize_haas");
     haas_kernel<<<grid, 256, 0, c->stream>>>(A);
+    MM_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// ---- 4-band stereo imager (pipeline.py:1360-1386): _split_bands, per-band mid/side width, sum, clip ------------------
+// The split is the dynamics stage's (same designs, same sweeps); the per-band width and the merge are one pointwise pass
+// over the four stored band pairs, in float64 like the reference's (its bands come out of filtfilt as float64; ours are
+// read back from float32 storage), accumulated into float32 band by band as numpy's in-place `out_l += ol` does.
+struct Imager4Args {
+    const float* band[4];
+    float* out;
+    long long n, stride;
+    double width[4];
+};
+__global__ void __launch_bounds__(256) imager4_kernel(const Imager4Args P) {
+    const int track = blockIdx.y;
+    const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+    if (i >= P.n) return;
+    const size_t r0 = (size_t)(track * 2) * (size_t)P.stride + kLead + (size_t)i, r1 = r0 + (size_t)P.stride;
+    float ol = 0.f, orr = 0.f;
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+        const double l = (double)P.band[b][r0], r = (double)P.band[b][r1];
+        const double mid = (l + r) * 0.5, side = (l - r) * 0.5 * P.width[b];
+        ol = (float)((double)ol + fmin(fmax(mid + side, -1.0), 1.0));
+        orr = (float)((double)orr + fmin(fmax(mid - side, -1.0), 1.0));
+    }
+    P.out[r0] = fminf(fmaxf(ol, -1.f), 1.f);
+    P.out[r1] = fminf(fmaxf(orr, -1.f), 1.f);
+}
+
+int st_imager4(mm_ctx* c, const mm_geom* g, const float* in, float* out, const double* widths, const double* crossovers_hz) {
+    double cross[3] = {214.0, 3500.0, 10000.0};                    // MULTIBAND_CROSSOVERS_HZ (pipeline.py:94)
+    if (crossovers_hz) {
+        double t[3];
+        for (int i = 0; i < 3; ++i) t[i] = std::min(std::max(crossovers_hz[i], 20.0), 20000.0);
+        if (!(t[0] >= t[1] || t[1] >= t[2])) { cross[0] = t[0]; cross[1] = t[1]; cross[2] = t[2]; }
+    }
+    float* bands[4];
+    MM_TRY(st_split_bands(c, g, in, cross, bands));
+    Imager4Args A;
+    for (int b = 0; b < 4; ++b) { A.band[b] = bands[b]; A.width[b] = widths[b]; }
+    A.out = out; A.n = g->n; A.stride = g->stride;
+    dim3 grid((unsigned)((g->n + 255) / 256), (unsigned)g->tracks);
+    KernelScope ks(c, "imager_4band_merge");
+    imager4_kernel<<<grid, 256, 0, c->stream>>>(A);
     MM_CUDA(cudaGetLastError());
     return 0;
 }

@@ -423,11 +423,27 @@ __global__ void __launch_bounds__(kPwThreads) quantize_kernel(const QuantArgs P)
     if (i >= P.n) return;
     const size_t fi = (size_t)track * (size_t)P.n + (size_t)i;
     unsigned rnd[4] = {0, 0, 0, 0};
-    if (!P.noise) dither_words((unsigned long long)i, track + P.track_base, P.seed, rnd);
+    if (!P.noise && !P.noise_planar) dither_words((unsigned long long)i, track + P.track_base, P.seed, rnd);
     for (int c = 0; c < C; ++c) {
         const float x = P.in[(size_t)(track * C + c) * (size_t)P.stride + kLead + i];
-        const double nz = P.noise ? (double)P.noise[fi * C + c] : tpdf16(rnd[(i & 1) * 2 + c]);
+        double nz;
+        if (P.noise_planar) nz = (double)__fmul_rn(P.noise_planar[(size_t)(track * C + c) * (size_t)P.stride + kLead + i], P.noise_scale);
+        else nz = P.noise ? (double)P.noise[fi * C + c] : tpdf16(rnd[(i & 1) * 2 + c]);
         P.pcm[fi * C + c] = quantize16(x, nz);
+    }
+}
+
+// white = 2 * rand - 1 in float32 (pipeline.py:843 / :864), planar, for the shaping filter
+__global__ void __launch_bounds__(kPwThreads) white_noise_kernel(const WhiteArgs P) {
+    const int track = blockIdx.y, C = P.channels;
+    const long long i = ((long long)blockIdx.x * kPwThreads + threadIdx.x);
+    if (i >= P.n) return;
+    unsigned rnd[4] = {0, 0, 0, 0};
+    if (!P.uniform) philox4x32_10((unsigned)i, (unsigned)((unsigned long long)i >> 32), (unsigned)(track + P.track_base), 1u,
+                                  (unsigned)P.seed, (unsigned)(P.seed >> 32), rnd);
+    for (int c = 0; c < C; ++c) {
+        const float u = P.uniform ? P.uniform[((size_t)track * (size_t)P.n + (size_t)i) * C + c] : (float)(rnd[c] >> 8) * 5.9604644775390625e-08f;
+        P.out[(size_t)(track * C + c) * (size_t)P.stride + kLead + i] = __fsub_rn(__fmul_rn(2.0f, u), 1.0f);
     }
 }
 

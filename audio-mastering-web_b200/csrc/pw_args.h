@@ -60,6 +60,12 @@ struct QuantArgs {
     const float* in; long long n, stride; int tracks, channels;
     int16_t* pcm; const float* noise; unsigned long long seed;
     int track_base;
+    const float* noise_planar;   // shaped dither: planar rows (batch layout), scaled by noise_scale in float32
+    float noise_scale;
+};
+struct WhiteArgs {               // white noise in [-1, 1) for the noise-shaped dithers, planar rows
+    const float* uniform;        // interleaved float32 uniforms in [0, 1) (np.random.rand(...).astype(float32)) or null -> Philox
+    float* out; long long n, stride; int tracks, channels; unsigned long long seed; int track_base;
 };
 
 }  // namespace mm

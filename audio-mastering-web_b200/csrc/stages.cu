@@ -447,6 +447,14 @@ int run_quantize(mm_ctx* c, const QuantArgs& Q) {
     return 0;
 }
 
+int run_white_noise(mm_ctx* c, const WhiteArgs& W) {
+    dim3 grid((unsigned)((W.n + kPwThreads - 1) / kPwThreads), (unsigned)W.tracks);
+    KernelScope ks(c, "dither_white_noise");
+    white_noise_kernel<<<grid, kPwThreads, 0, c->stream>>>(W);
+    MM_CUDA(cudaGetLastError());
+    return 0;
+}
+
 int run_layout(mm_ctx* c, const mm_geom* g, const float* interleaved, float* planar, int dir) {
     dim3 grid((unsigned)((g->n + kPwThreads - 1) / kPwThreads), (unsigned)g->tracks);
     KernelScope ks(c, dir ? "interleave" : "deinterleave");
@@ -610,6 +618,44 @@ int st_dynamics(mm_ctx* c, const mm_geom* g, const float* in, float* out, double
         float* o2[1] = {out};
         MM_TRY(sweep_bwd(c, g, 2, p, i2, o2, 1, e, 9));
     }
+    return 0;
+}
+
+int st_split_bands(mm_ctx* c, const mm_geom* g, const float* in, const double* cross, float** bands) {
+    const double nyq = g->sr / 2.0;
+    double f[3];
+    for (int i = 0; i < 3; ++i) f[i] = std::min(cross[i] / nyq, 0.99);
+    const FilterPlan* lp1 = plan_butter(c, 2, kLow, f[0], 0);
+    const FilterPlan* hp1 = plan_butter(c, 2, kHigh, f[0], 0);
+    const FilterPlan* lp2 = plan_butter(c, 2, kLow, f[1], 0);
+    const FilterPlan* hp2 = plan_butter(c, 2, kHigh, f[1], 0);
+    const FilterPlan* lp3 = plan_butter(c, 2, kLow, f[2], 0);
+    const FilterPlan* hp3 = plan_butter(c, 2, kHigh, f[2], 0);
+    if (!lp1 || !hp1 || !lp2 || !hp2 || !lp3 || !hp3) return 1;
+    MM_TRY(need_len(g, 9, "_split_bands"));
+    Bufs B;
+    MM_TRY(get_bufs(c, g, &B));
+    Pro none;
+    Epi store;
+    {
+        const FilterPlan* p[4] = {lp1, hp1, hp2, hp3};
+        const float* i1[1] = {in};
+        float* o1[4] = {B.E[0], B.E[1], B.E[2], B.E[3]};
+        MM_TRY(sweep_fwd(c, g, 4, 1, p, i1, o1, none, 9));
+        const float* i2[4] = {B.E[0], B.E[1], B.E[2], B.E[3]};
+        float* o2[4] = {B.T[1], B.T[2], B.T[3], B.T[4]};
+        MM_TRY(sweep_bwd(c, g, 4, p, i2, o2, 4, store, 9));
+    }
+    {
+        const FilterPlan* p[2] = {lp2, lp3};
+        const float* i1[2] = {B.T[2], B.T[3]};
+        float* o1[2] = {B.E[0], B.E[1]};
+        MM_TRY(sweep_fwd(c, g, 2, 2, p, i1, o1, none, 9));
+        const float* i2[2] = {B.E[0], B.E[1]};
+        float* o2[2] = {B.T[2], B.T[3]};
+        MM_TRY(sweep_bwd(c, g, 2, p, i2, o2, 2, store, 9));
+    }
+    bands[0] = B.T[1]; bands[1] = B.T[2]; bands[2] = B.T[3]; bands[3] = B.T[4];
     return 0;
 }
 

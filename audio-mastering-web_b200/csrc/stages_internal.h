@@ -49,6 +49,7 @@ struct FinalArgs;
 int run_finalize(mm_ctx* c, const mm_geom* g, const float* in, float* out, const double* mul, const double* width, int n_fade,
                  int16_t* pcm, const float* noise, unsigned long long seed, double* nonfinite);
 int run_quantize(mm_ctx* c, const QuantArgs& Q);
+int run_white_noise(mm_ctx* c, const WhiteArgs& W);
 // dir 0: interleaved -> planar, 1: planar -> interleaved
 int run_layout(mm_ctx* c, const mm_geom* g, const float* interleaved, float* planar, int dir);
 void fill_dyn(DynParams* d, double knee_db, const double* band_ratios, double max_upward_boost_db);
@@ -66,7 +67,10 @@ int st_style_eq(mm_ctx* c, const mm_geom* g, const float* in, float* out, const 
                 int reset_peak);
 int st_exciter(mm_ctx* c, const mm_geom* g, const float* in, float* out, double exciter_db, int mode, float* peak);
 
+// _split_bands (pipeline.py:333-364): the four zero-phase bands of every row, left in workspace buffers (bands[0..3])
+int st_split_bands(mm_ctx* c, const mm_geom* g, const float* in, const double* cross_hz, float** bands);
 // followers.cu
+int st_imager4(mm_ctx* c, const mm_geom* g, const float* in, float* out, const double* widths, const double* crossovers_hz);
 int st_transient_designer(mm_ctx* c, const mm_geom* g, const float* in, float* out, double attack_gain, double sustain_gain);
 int st_maximizer_transient_aware(mm_ctx* c, const mm_geom* g, const float* in, float* out, double sensitivity);
 int st_haas_imager(mm_ctx* c, const mm_geom* g, const float* in, float* out, double width, double delay_ms, double mix);

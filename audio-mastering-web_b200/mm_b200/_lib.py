@@ -75,6 +75,7 @@ SIGNATURES = {
     "mm_dev_apply_rumble_filter": (_i, [_vp, _gp, _vp, _vp, _d]),
     "mm_dev_iir": (_i, [_vp, _gp, _vp, _vp, _dp, _dp, _i, _i]),
     "mm_dev_quantize_int16": (_i, [_vp, _gp, _vp, _vp, _vp, _u64]),
+    "mm_dev_quantize_int16_shaped": (_i, [_vp, _gp, _vp, _vp, _vp, _u64, _i]),
     "mm_dev_true_peak": (_i, [_vp, _gp, _vp, _vp]),
     "mm_dev_spectrum_bars": (_i, [_vp, _gp, _vp, _i, _vp]),
     "mm_dev_stereo_correlation": (_i, [_vp, _gp, _vp, _vp, _vp]),
@@ -82,6 +83,7 @@ SIGNATURES = {
     "mm_dev_apply_transient_designer": (_i, [_vp, _gp, _vp, _vp, _d, _d]),
     "mm_dev_apply_maximizer_transient_aware": (_i, [_vp, _gp, _vp, _vp, _d]),
     "mm_dev_apply_high_freq_trim": (_i, [_vp, _gp, _vp, _vp, _d, _d]),
+    "mm_dev_apply_stereo_imager_4band": (_i, [_vp, _gp, _vp, _vp, _dp, _dp]),
     "mm_dev_apply_stereoize": (_i, [_vp, _gp, _vp, _vp, _d, _d, _d]),
     "mm_slice_margin": (_i64, [C.c_int32]),
     "mm_dev_master_slice": (_i, [_vp, _gp, _i, C.POINTER(Style), _vp, _vp, _vp, _vp, _u64, _vp, _u32, _vp]),

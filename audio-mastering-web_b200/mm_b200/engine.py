@@ -168,6 +168,21 @@ class Engine:
             self.sync()
             return pcm.cpu().numpy()
 
+    def quantize_int16_shaped(self, b: Batch, shape: int, uniform: np.ndarray | None = None, seed: int = 0) -> np.ndarray:
+        """Noise-shaped dither export (shape 1 = ns_e, 2 = ns_itu) -> int16 (tracks, n, channels); ``uniform`` =
+        ``np.random.rand(n, ch).astype(float32)`` per track selects the bit-exact mode."""
+        torch = _torch()
+        with torch.cuda.stream(self.stream):
+            pcm = torch.empty((b.tracks, b.n, b.channels), dtype=torch.int16, device=self.tdev)
+            un = None
+            if uniform is not None:
+                un = torch.from_numpy(np.ascontiguousarray(uniform, dtype=np.float32).reshape(b.tracks, b.n, b.channels)).to(self.tdev)
+            g = b.geom
+            _lib.check(self.lib.mm_dev_quantize_int16_shaped(self.ctx, C.byref(g), b.ptr, C.c_void_p(pcm.data_ptr()),
+                                                             C.c_void_p(un.data_ptr()) if un is not None else None, int(seed), int(shape)))
+            self.sync()
+            return pcm.cpu().numpy()
+
     # ---- whole chains -----------------------------------------------------------------------------
     def master(self, src: Batch, chain: int, styles, *, out: Batch | None = None, want_int16=False, noise=None,
                seed: int = 0, flags: int = 0, want_stats=True):

@@ -162,15 +162,22 @@ def apply_harmonic_exciter(audio: np.ndarray, sr: int, exciter_db: float = 0.0, 
 
 def apply_stereo_imager(audio: np.ndarray, width: float = 1.0, stereoize_delay_ms: float = 0.0, stereoize_mix: float = 0.12,
                         sr=None, band_widths=None, crossovers_hz=None) -> np.ndarray:
-    """backend/app/pipeline.py:1339-1398: plain width mode and the Haas "stereoize" cross-delay (the 4-band mode is
-    second-wave)."""
+    """backend/app/pipeline.py:1339-1398: plain width, 4-band width (``band_widths``) and the Haas "stereoize"
+    cross-delay."""
     a = np.asarray(audio)
     if a.ndim == 1 or a.shape[1] == 1:
         return audio
-    if band_widths is not None and len(band_widths) == 4 and sr and sr > 0:
-        raise NotImplementedError("4-band imager is second-wave scope (SURVEY 8f)")
-    if stereoize_delay_ms and stereoize_delay_ms > 0 and sr and sr > 0 and stereoize_mix > 0 and \
-            min(int(sr * stereoize_delay_ms / 1000.0), a.shape[0] - 1) > 0:
+    four = band_widths is not None and len(band_widths) == 4 and sr and sr > 0
+    haas = bool(stereoize_delay_ms and stereoize_delay_ms > 0 and sr and sr > 0 and stereoize_mix > 0 and
+                min(int(sr * stereoize_delay_ms / 1000.0), a.shape[0] - 1) > 0)
+    if four:
+        cx = _lib.darr([float(v) for v in crossovers_hz]) if crossovers_hz is not None and len(crossovers_hz) == 3 else None
+        wide = _stage("apply_stereo_imager_4band", audio, sr, _lib.darr([float(w) for w in band_widths]), cx)
+        if not haas:
+            return wide
+        eng, b, mono = _up(wide, sr)          # the cross-delay then acts on the merged pair as it is (width = NaN: no mid/side step)
+        return _down(eng, eng.stage("apply_stereoize", b, C.c_double(float("nan")), C.c_double(stereoize_delay_ms), C.c_double(stereoize_mix)), mono)
+    if haas:
         eng, b, mono = _up(audio, sr)         # the delayed tap reads behind the writer: not in place
         return _down(eng, eng.stage("apply_stereoize", b, C.c_double(width), C.c_double(stereoize_delay_ms), C.c_double(stereoize_mix)), mono)
     return _stage("apply_stereo_imager", audio, sr or 44100, C.c_double(width))
@@ -389,15 +396,19 @@ def _run_v1_stagewise(audio, sr, target_lufs, style, transient_attack, transient
 
 def export_audio(samples: np.ndarray, sr: int, channels: int, out_format: str = "wav", dither_type: str = "tpdf",
                  auto_blank_sec: float = 0.0, bitrate=None, noise: Optional[np.ndarray] = None, seed: int = 0) -> bytes:
-    """backend/app/pipeline.py:965-991, WAV/TPDF branch (``noise=`` is additive: bit-exact test hook)."""
+    """backend/app/pipeline.py:965-991, WAV branch with TPDF or noise-shaped ("ns_e", "ns_itu") dither.  ``noise=`` is
+    additive (bit-exact test hook): for TPDF the float32 dither buffer itself, for the shaped types the float32 uniforms
+    ``np.random.rand(n, ch).astype(np.float32)`` the reference would have drawn (:843 / :864)."""
     if out_format.lower() != "wav":
         raise NotImplementedError("only the WAV branch is on the hot path (codecs are host-side I/O, SURVEY L0)")
-    if dither_type not in ("tpdf", None, ""):
-        raise NotImplementedError("noise-shaped dither (ns_e / ns_itu) is second-wave scope (SURVEY 8f)")
     if auto_blank_sec:
         raise NotImplementedError("auto_blank_sec is second-wave scope")
     eng, b, _ = _up(samples, sr)
-    pcm = eng.quantize_int16(b, noise=noise, seed=seed)[0]
+    shape = {"ns_e": 1, "ns_itu": 2}.get(dither_type or "tpdf", 0)
+    if shape and b.n >= (4 if shape == 1 else 8):         # shorter buffers: the reference falls back to TPDF (:840, :861)
+        pcm = eng.quantize_int16_shaped(b, shape, uniform=noise, seed=seed)[0]
+    else:
+        pcm = eng.quantize_int16(b, noise=noise, seed=seed)[0]
     return wavio.pack_wav_pcm16(pcm, sr)
 
 

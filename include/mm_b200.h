@@ -131,8 +131,13 @@ int mm_dev_apply_transient_designer(mm_ctx*, const mm_geom*, const float* in, fl
 int mm_dev_apply_maximizer_transient_aware(mm_ctx*, const mm_geom*, const float* in, float* out, double sensitivity);
 /* apply_high_freq_trim                 backend/app/pipeline.py:1705-1733 */
 int mm_dev_apply_high_freq_trim(mm_ctx*, const mm_geom*, const float* in, float* out, double crossover_hz, double high_gain);
-/* apply_stereo_imager with stereoize_delay_ms > 0 (single-band width + Haas cross-delay), :1339-1398; in != out */
+/* apply_stereo_imager with stereoize_delay_ms > 0 (single-band width + Haas cross-delay), :1339-1398; in != out;
+ * width = NaN skips the mid/side step (the pair already went through the 4-band mode) */
 int mm_dev_apply_stereoize(mm_ctx*, const mm_geom*, const float* in, float* out, double width, double delay_ms, double mix);
+/* apply_stereo_imager with band_widths (4-band mode: _split_bands + per-band width + merge), :1360-1386;
+ * crossovers_hz NULL -> MULTIBAND_CROSSOVERS_HZ (214, 3500, 10000) */
+int mm_dev_apply_stereo_imager_4band(mm_ctx*, const mm_geom*, const float* in, float* out, const double* band_widths /*4*/,
+                                     const double* crossovers_hz /*3 or NULL*/);
 /* generic zero-phase / causal IIR on every row: scipy filtfilt / lfilter semantics of
  * _safe_filtfilt (backend/app/pipeline.py:36-52). nb == na in {3, 5}; zero_phase 0 -> lfilter. */
 int mm_dev_iir(mm_ctx*, const mm_geom*, const float* in, float* out,
@@ -145,6 +150,11 @@ int mm_dev_iir(mm_ctx*, const mm_geom*, const float* in, float* out,
  *        else device float32 [tracks][n][ch] interleaved (bit-exact mode, _dither_noise_tpdf :830). */
 int mm_dev_quantize_int16(mm_ctx*, const mm_geom*, const float* in, int16_t* out_interleaved,
                           const float* noise_interleaved, uint64_t seed);
+/* Noise-shaped dither variants of the same export (dither_type "ns_e" = 1, "ns_itu" = 2; _dither_noise_ns_e / _ns_itu,
+ * backend/app/pipeline.py:835-877): uniform_interleaved holds np.random.rand(n, ch).astype(float32) (bit-exact mode) or is
+ * NULL (Philox).  Uses the context's workspace. */
+int mm_dev_quantize_int16_shaped(mm_ctx*, const mm_geom*, const float* in, int16_t* out_interleaved,
+                                 const float* uniform_interleaved, uint64_t dither_seed, int shape);
 
 /* ---- analyzers ------------------------------------------------------------------------------*/
 /* _true_peak_dbfs                      backend/app/routers/tools.py:44-54; out: device double[tracks] (dBFS) */

@@ -540,6 +540,32 @@ def apply_stereoize(audio, sr, width=1.0, delay_ms=8.0, mix=0.12):
     return np.column_stack([out_l, out_r]).astype(np.float32)
 
 
+def apply_stereo_imager_4band(audio, sr, band_widths, crossovers_hz=None, delay_ms=0.0, mix=0.12):
+    """apply_stereo_imager in its 4-band mode (pipeline.py:1360-1398): _split_bands, per-band mid/side width, merge."""
+    if audio.ndim == 1 or audio.shape[1] == 1:
+        return audio
+    left, right = audio[:, 0].astype(np.float32), audio[:, 1].astype(np.float32)
+    cross = tuple(float(v) for v in crossovers_hz) if crossovers_hz is not None and len(crossovers_hz) == 3 else (214.0, 3500.0, 10000.0)
+    cross = tuple(np.clip(c, 20.0, 20000.0) for c in cross)
+    if cross[0] >= cross[1] or cross[1] >= cross[2]:
+        cross = (214.0, 3500.0, 10000.0)
+    bands = split_bands(np.column_stack([left, right]), float(sr), cross)
+    out_l, out_r = np.zeros_like(left), np.zeros_like(right)
+    for i in range(4):
+        bl, br = bands[i][:, 0], bands[i][:, 1]
+        mid, side = (bl + br) * 0.5, (bl - br) * 0.5 * float(band_widths[i])
+        out_l += np.clip(mid + side, -1.0, 1.0)
+        out_r += np.clip(mid - side, -1.0, 1.0)
+    out_l, out_r = np.clip(out_l, -1.0, 1.0), np.clip(out_r, -1.0, 1.0)
+    delay_n = max(0, min(int(sr * delay_ms / 1000.0), audio.shape[0] - 1))
+    m = min(0.35, max(0.0, float(mix)))
+    if delay_ms > 0 and m > 0 and delay_n > 0:
+        dr = np.concatenate([np.zeros(delay_n, dtype=out_r.dtype), out_r[:-delay_n]])
+        dl = np.concatenate([np.zeros(delay_n, dtype=out_l.dtype), out_l[:-delay_n]])
+        out_l, out_r = np.clip(out_l + m * dr, -1.0, 1.0), np.clip(out_r + m * dl, -1.0, 1.0)
+    return np.column_stack([out_l, out_r]).astype(np.float32)
+
+
 def _finalize(a):
     out = np.ascontiguousarray(np.clip(a, -1.0, 1.0).astype(np.float32))
     np.nan_to_num(out, copy=False, nan=0.0, posinf=1.0, neginf=-1.0)
@@ -616,6 +642,21 @@ def quantize_int16(samples, noise):
 
 
 # -- analyzers ----------------------------------------------------------------------------------
+def dither_noise_shaped(uniform, kind):
+    """_dither_noise_ns_e / _dither_noise_ns_itu (pipeline.py:835-877) from the float32 uniforms the reference draws."""
+    white = (2.0 * np.asarray(uniform, dtype=np.float32) - 1.0).astype(np.float32)
+    w2 = white.reshape(white.shape[0], -1)
+    out = np.empty_like(w2)
+    if kind == "ns_e":
+        out[0] = w2[0]
+        for i in range(1, w2.shape[0]):
+            out[i] = w2[i] - w2[i - 1] + 0.99 * out[i - 1]
+    else:
+        for c in range(w2.shape[1]):
+            out[:, c] = sg.lfilter(np.array([1.0, -2.0, 1.0]), np.array([1.0, -1.96, 0.9604]), w2[:, c])
+    return (out * 0.9).astype(np.float32).reshape(white.shape)
+
+
 def true_peak_dbfs(audio, sr=None):
     """routers/tools.py:44-54: 4x ``resample_poly`` then sample peak in dBFS."""
     audio = np.asarray(audio)

@@ -40,9 +40,19 @@ def main():
         "hf_trim": P.apply_high_freq_trim(loud, sr),
         "hf_trim_custom": P.apply_high_freq_trim(x, sr, crossover_hz=3000.0, high_gain=0.8),
         "haas": P.apply_stereo_imager(x, 1.2, stereoize_delay_ms=8.0, stereoize_mix=0.12, sr=sr),
+        "imager4": P.apply_stereo_imager(loud, 1.0, sr=sr, band_widths=(0.8, 1.0, 1.3, 1.6)),
+        "imager4_haas": P.apply_stereo_imager(x, 1.0, stereoize_delay_ms=6.0, stereoize_mix=0.2, sr=sr, band_widths=(1.0, 1.2, 1.4, 0.9),
+                                              crossovers_hz=(214.0, 2230.0, 10000.0)),
         "haas_loud": P.apply_stereo_imager(loud, 1.0, stereoize_delay_ms=12.0, stereoize_mix=0.3, sr=sr),
     }
     st = {k: (np.asarray(v, dtype=np.float32) if isinstance(v, np.ndarray) else v) for k, v in st.items()}
+    # noise-shaped dither export: the reference draws from the legacy global generator, so seeding it pins the uniforms
+    short = loud[:6000]
+    for kind, seed in (("ns_e", 321), ("ns_itu", 654)):
+        np.random.seed(seed)
+        wav = P.export_audio(short, sr, 2, "wav", dither_type=kind)
+        st[f"{kind}_int16"] = np.frombuffer(wav[44:], dtype="<i2").reshape(short.shape)
+        st[f"{kind}_seed"] = np.int64(seed)
     path = os.path.join(HERE, "pro_stages_48k.npz")
     np.savez_compressed(path, **st)
     print({k: np.shape(v) for k, v in st.items()}, "%.0f KB" % (os.path.getsize(path) / 1024))

@@ -140,6 +140,9 @@ def test_pro_stages_against_reference_golden(gpu_lib):
         "hf_trim_custom": P.apply_high_freq_trim(x, sr, 3000.0, 0.8),
         "haas": P.apply_stereo_imager(x, 1.2, stereoize_delay_ms=8.0, stereoize_mix=0.12, sr=sr),
         "haas_loud": P.apply_stereo_imager(loud, 1.0, stereoize_delay_ms=12.0, stereoize_mix=0.3, sr=sr),
+        "imager4": P.apply_stereo_imager(loud, 1.0, sr=sr, band_widths=(0.8, 1.0, 1.3, 1.6)),
+        "imager4_haas": P.apply_stereo_imager(x, 1.0, stereoize_delay_ms=6.0, stereoize_mix=0.2, sr=sr, band_widths=(1.0, 1.2, 1.4, 0.9),
+                                              crossovers_hz=(214.0, 2230.0, 10000.0)),
     }
     worst = {}
     for k, v in got.items():
@@ -164,3 +167,28 @@ def test_follower_chunking_is_invisible(gpu_lib):
     e2 = float(np.max(np.abs(P.apply_maximizer_transient_aware(x, sr, 0.7).astype(np.float64) - oc.apply_maximizer_transient_aware(x, sr, 0.7))))
     print(f"[parity] 12 s transient designer {e1:.3e}, transient-aware maximizer {e2:.3e}")
     assert e1 <= 2e-6 and e2 <= 2e-6
+
+
+def test_noise_shaped_dither_export(gpu_lib):
+    """export_audio(dither_type="ns_e" | "ns_itu") against the reference's own WAV bytes under the same uniforms: ns_itu is a
+    float64 lfilter on both sides (bit-exact); ns_e is a float32 recursion in the reference and a float64-state sweep here,
+    so a dithered value within ~1e-6 LSB of a rounding boundary may land on the other side (none expected in 12000 samples)."""
+    from mm_b200 import pipeline as P, wavio
+    g = load_golden("pro_stages_48k")
+    sr = int(g["sr"])
+    x = (g["input"] * np.float32(6.0)).astype(np.float32)[:6000]
+    for kind, max_diff in (("ns_itu", 0), ("ns_e", 1)):
+        np.random.seed(int(g[f"{kind}_seed"]))
+        uniform = np.random.rand(*x.shape).astype(np.float32)
+        wav = P.export_audio(x, sr, 2, "wav", dither_type=kind, noise=uniform)
+        pcm = np.frombuffer(wav[44:], dtype="<i2").reshape(x.shape)
+        bad = int(np.sum(pcm != g[f"{kind}_int16"]))
+        print(f"[parity] {kind}: {bad} of {pcm.size} int16 samples differ")
+        assert bad <= max_diff and np.max(np.abs(pcm.astype(np.int32) - g[f"{kind}_int16"].astype(np.int32))) <= 1
+    # Philox-seeded white noise: deterministic, and actually shaped (less low-frequency error power than TPDF)
+    a = np.frombuffer(P.export_audio(x, sr, 2, "wav", dither_type="ns_itu", seed=3)[44:], dtype="<i2")
+    b = np.frombuffer(P.export_audio(x, sr, 2, "wav", dither_type="ns_itu", seed=3)[44:], dtype="<i2")
+    assert np.array_equal(a, b)
+    err = a.reshape(x.shape)[:, 0].astype(np.float64) - np.clip(x[:, 0].astype(np.float64), -1, 1) * 32767.0
+    spec = np.abs(np.fft.rfft(err * np.hanning(len(err)))) ** 2
+    assert spec[: len(spec) // 8].mean() < 0.5 * spec[-len(spec) // 8:].mean()      # white rounding error (1/12 LSB^2) is the floor at low frequencies

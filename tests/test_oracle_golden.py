@@ -83,11 +83,24 @@ def test_pro_stages_match_reference_golden():
         "hf_trim_custom": oc.apply_high_freq_trim(x, sr, 3000.0, 0.8),
         "haas": oc.apply_stereoize(x, sr, 1.2, 8.0, 0.12),
         "haas_loud": oc.apply_stereoize(loud, sr, 1.0, 12.0, 0.3),
+        "imager4": oc.apply_stereo_imager_4band(loud, sr, (0.8, 1.0, 1.3, 1.6)),
+        "imager4_haas": oc.apply_stereo_imager_4band(x, sr, (1.0, 1.2, 1.4, 0.9), (214.0, 2230.0, 10000.0), 6.0, 0.2),
     }
     for k, v in got.items():
         assert np.shape(v) == g[k].shape, k
         err = np.max(np.abs(np.asarray(v, dtype=np.float64) - g[k]))
         assert err <= 1e-7, (k, err)      # measured: bit equal (numba's fastmath does not change these roundings here)
+
+
+def test_noise_shaped_dither_export_matches_reference_golden():
+    """ns_e / ns_itu (pipeline.py:835-877): the oracle's shaping of the same uniforms + quantiser == the reference's WAV."""
+    g = load_golden("pro_stages_48k")
+    x = (g["input"] * np.float32(6.0)).astype(np.float32)[:6000]
+    for kind in ("ns_e", "ns_itu"):
+        np.random.seed(int(g[f"{kind}_seed"]))
+        uniform = np.random.rand(*x.shape).astype(np.float32)
+        q = oc.quantize_int16(x, oc.dither_noise_shaped(uniform, kind))
+        assert np.array_equal(q, g[f"{kind}_int16"]), kind
 
 
 def test_analyzers_match_reference_golden():
