@@ -274,3 +274,17 @@ def test_balanced_realization_float32_pass2(lib, design, tol):
     y32 = _chunked_f32_pass2(tb, x, x[0])
     err = np.max(np.abs(y32.astype(np.float64) - ref))
     assert err <= tol, (design, err)
+
+
+def test_reference_dynamic_eq_default_bands_are_unstable():
+    """Why mm_b200 does not offer apply_dynamic_eq: the reference calls ``sg.iirpeak(w0, bw)`` with a
+    bandwidth in the Q slot (backend/app/pipeline.py:1659-1663); for all eight default bands (:1616-1625) that is an
+    unstable section at 44.1 and 48 kHz."""
+    bands = [(120, 1.0), (250, 1.2), (400, 1.0), (800, 1.2), (2500, 1.4), (5000, 1.4), (8000, 1.2), (12000, 0.8)]
+    for sr in (44100, 48000):
+        nyq = sr / 2.0
+        for freq, q in bands:
+            w0 = float(np.clip(freq / nyq, 0.001, 0.98))
+            bw = float(np.clip(w0 / max(q, 0.1), 0.001, 0.5))
+            _, a = sg.iirpeak(w0, bw)
+            assert np.max(np.abs(np.roots(a))) >= 1.0 - 1e-9, (sr, freq, q)
