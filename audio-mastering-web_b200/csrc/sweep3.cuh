@@ -81,11 +81,14 @@ struct Sweep2Cfg {
     static constexpr size_t kRing = (size_t)ST * NIN * kTileBytes;
     static constexpr size_t kExtraOff = kRing;
     static constexpr size_t kAuxOff = kExtraOff + kExtra * kTileBytes;
-    static constexpr size_t kTabOff = kAuxOff + NAUX * kTileBytes;
+    static constexpr size_t kTabOff = kAuxOff;          // the x-domain aux streams of an epilogue are read straight from
+                                                         // global memory in the (coalesced) store phase: no smem tiles
     static constexpr size_t kBytes = kTabOff + NF * sizeof(SmemTab<M>);
     // CTAs per SM the shared-memory footprint allows (227 KB usable): the register allocator is held to it
     static constexpr int kFit = (int)((227u * 1024u) / (kBytes + 1024u));
-    static constexpr int kMinBlocks = kFit < 1 ? 1 : (kFit > 6 ? 6 : kFit);
+    // the dynamics epilogues (four band chains + maximizer per sample) need ~128 registers: 4 CTAs/SM beat 6 with spills
+    static constexpr int kCap = (EPI == EPI_DYNAMICS || EPI == EPI_DYNAMICS_GEN) ? 4 : 6;
+    static constexpr int kMinBlocks = kFit < 1 ? 1 : (kFit > kCap ? kCap : kFit);
 };
 
 template <int M, int NF> struct Scratch2 {
@@ -109,7 +112,6 @@ __global__ void __launch_bounds__(kT, Sweep2Cfg<M, NF, NIN, DIR, EPI, NAUX, ST>:
     extern __shared__ __align__(128) unsigned char smraw[];
     float* ring = reinterpret_cast<float*>(smraw);
     float* extra = reinterpret_cast<float*>(smraw + Cfg::kExtraOff);
-    float* auxs = reinterpret_cast<float*>(smraw + Cfg::kAuxOff);
     SmemTab<M>* tab = reinterpret_cast<SmemTab<M>*>(smraw + Cfg::kTabOff);
     __shared__ Scratch2<M, NF> sh;
     constexpr int MM = M * M;
@@ -200,36 +202,6 @@ __global__ void __launch_bounds__(kT, Sweep2Cfg<M, NF, NIN, DIR, EPI, NAUX, ST>:
             }
         }
     };
-    auto issue_aux = [&](int row, long long lo) {
-        if (NAUX == 0) return;
-        const size_t rowoff = (size_t)row * (size_t)P.stride;
-        if (fast_out(lo)) {
-#pragma unroll
-            for (int s = 0; s < NAUX; ++s) {
-                const float* src = P.aux[s] + rowoff + lo + 4 * tid;
-                float* dst = auxs + (size_t)s * kL + 4 * swz(tid);
-#pragma unroll
-                for (int r = 0; r < kTileVecs / kT; ++r) cp_async16(dst + 4 * kT * r, src + 4 * kT * r);
-            }
-        } else {
-            // edge tile: synchronous, zeros outside the x-domain
-#pragma unroll 1
-            for (int s = 0; s < NAUX; ++s) {
-                const float* src = P.aux[s] + rowoff;
-#pragma unroll 1
-                for (int r = 0; r < kTileVecs / kT; ++r) {
-                    const int v = tid + kT * r;
-                    const long long q = lo + 4 * v;
-                    float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-                    for (int c = 0; c < 4; ++c)
-                        if (q + c >= st_lo && q + c <= st_hi) setcomp4(val, c, src[q + c]);
-                    *reinterpret_cast<float4*>(auxs + (size_t)s * kL + 4 * swz(v)) = val;
-                }
-            }
-        }
-    };
-
     long long t_ph[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     long long t_last = 0;
     const bool dbg_on = PP.dbg != nullptr && blockIdx.x == 0 && tid == 0;
@@ -257,14 +229,22 @@ __global__ void __launch_bounds__(kT, Sweep2Cfg<M, NF, NIN, DIR, EPI, NAUX, ST>:
         __syncthreads();                               // (A) previous tile fully stored; carry visible
         MM_TICK(0);
         const long long tile_lo = tile_origin(tile);
-        if (live) issue_aux(row, tile_lo);
-        cp_async_commit();                             // group: aux(tile)
+        if (EPI != EPI_STORE && live && (tid & 7) == 0) {
+            // the store phase will read this tile's aux samples: pull their lines into L2 now (one request per 128 bytes)
+#pragma unroll
+            for (int s = 0; s < NAUX; ++s) {
+                const float* ap = P.aux[s] + rowoff + tile_lo + 4 * tid;
+#pragma unroll
+                for (int r = 0; r < kTileVecs / kT; ++r)
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(ap + 4 * kT * r));
+            }
+        }
         if (ST > 1) {
             if (tile + 1 < t_end) issue_inputs(row, tile + 1, slot ^ 1);
             cp_async_commit();                         // group: inputs(tile + 1)
-            cp_async_wait<2>();                        // inputs(tile) have landed (this thread's part)
+            cp_async_wait<1>();                        // inputs(tile) have landed (this thread's part)
         } else {
-            cp_async_wait<1>();
+            cp_async_wait<0>();
         }
         __syncthreads();                               // (B) inputs(tile) visible to all threads
         MM_TICK(1);
@@ -381,10 +361,8 @@ __global__ void __launch_bounds__(kT, Sweep2Cfg<M, NF, NIN, DIR, EPI, NAUX, ST>:
 #pragma unroll
                 for (int i = 0; i < M; ++i) sh.tot[f][warp][i] = E[f][i];
         }
-        // the x-domain aux streams of a recombining epilogue are consumed inside pass 2
-        if (NAUX > 0) { if (ST > 1) cp_async_wait<1>(); else cp_async_wait<0>(); }
         MM_TICK(3);
-        __syncthreads();                               // (C) warp totals (and aux tiles) visible
+        __syncthreads();                               // (C) warp totals visible
         MM_TICK(4);
 
         double base[NF][M];
@@ -448,6 +426,7 @@ __global__ void __launch_bounds__(kT, Sweep2Cfg<M, NF, NIN, DIR, EPI, NAUX, ST>:
 
         // ---- pass 2 (+ the recombining epilogue, evaluated on the float64 section outputs) --------------------
         constexpr int NOUT = (EPI == EPI_STORE) ? NF : 1;
+        constexpr int NWR = (EPI == EPI_STORE) ? NF : ((EPI == EPI_DYNAMICS || EPI == EPI_DYNAMICS_GEN) ? 2 : 1);   // tiles pass 2 writes
         float* tout[NF];
 #pragma unroll
         for (int f = 0; f < NF; ++f) tout[f] = (f < NIN) ? (tin + (size_t)f * kL) : (extra + (size_t)(f - NIN) * kL);
@@ -467,42 +446,59 @@ __global__ void __launch_bounds__(kT, Sweep2Cfg<M, NF, NIN, DIR, EPI, NAUX, ST>:
             par_one_minus = (float)(1.0 - mixd);      // Python float (1.0 - mix), then weak-cast to float32
         }
         float pk = 0.f;
-        // one output element of a recombining epilogue; this sample's section outputs are yf[f] (float32 sections,
-        // f < NF32) and yd[f] (float64 sections)
-        auto epi_value = [&](float xa_raw, float a1c, const float (&yf)[NF], const double (&yd)[NF]) -> float {
-            const float xa = xa_raw;            // the aux prologue was applied to the whole float4 group by the caller
+        // A recombining epilogue is split in two.  Pass 2 STAGES, per sample, what depends on the section outputs
+        // (float32, into the tile buffers the inputs came from); the store phase reads the staged values back
+        // coalesced, fetches the x-domain aux samples of the same positions straight from global memory and
+        // finishes the arithmetic.  Nothing of an aux stream ever sits in shared memory.
+        //   EPI_COMBINE     stage S = sum_f w_f y_f                      finish (wc xa + S) * trim [clip]
+        //   EPI_EXCITER     stage t = (sat(hf) - hf) * gain / 4          finish xa + t
+        //   EPI_DYNAMICS*   stage chain(band 2), chain(band 3)           finish chain(b1) + . + . + chain(b4), maximize, limit
+        constexpr int NSTAGE = (EPI == EPI_DYNAMICS || EPI == EPI_DYNAMICS_GEN) ? 2 : 1;
+        auto stage_value = [&](const float (&yf)[NF], const double (&yd)[NF], float (&st)[2]) {
             auto yflt = [&](int f) -> float { return f < NF32 ? yf[f] : (float)yd[f]; };
+            st[1] = 0.f;
             if (EPI == EPI_COMBINE) {
-                // pipeline.py:273 / :603-606 / :1431: float64 recombination, one cast to float32.  The float32
-                // sections enter through their (small) weights: their weighted sum is formed in float32 and
-                // widened once
-                double acc;
-                if (NF32 > 0) {
-                    float accf = 0.f;
+                // pipeline.py:273 / :603-606 / :1431: the weighted sum of the filtered components; float32 sections in
+                // float32, float64 sections in float64, rounded to float32 once
+                float accf = 0.f;
 #pragma unroll
-                    for (int f = 0; f < NF32; ++f) accf = fmaf(P.w32[f], yf[f], accf);
-                    acc = fma(P.wc, (double)xa, (double)accf);     // wc == 1 on the chains (exact product); 0.9 in apply_high_freq_trim
-                } else {
-                    acc = P.wc * (double)xa;
+                for (int f = 0; f < NF32; ++f) accf = fmaf(P.w32[f], yf[f], accf);
+                if (NF32 < NF) {
+                    double acc = (double)accf;
+#pragma unroll
+                    for (int f = NF32; f < NF; ++f) acc = fma(P.w[f], yd[f], acc);
+                    accf = (float)acc;
                 }
-#pragma unroll
-                for (int f = NF32; f < NF; ++f) acc = fma(P.w[f], yd[f], acc);
-                const float res = (float)(acc * P.trim);
-                return P.epi_clip ? fminf(fmaxf(res, -1.f), 1.f) : res;
+                st[0] = accf;
             } else if (EPI == EPI_EXCITER) {
                 const float hf = yflt(0);
                 const float sat = exciter_sat(hf, P.exc_mode, (float)P.exc_k);
-                return (float)fma((double)(sat - hf), P.exc_gain * 0.25, (double)xa);
-            } else if (EPI == EPI_DYNAMICS) {   // aux0 = band 1, y0 = band 2, y1 = band 3, aux1 = band 4; downward knees only
+                st[0] = (float)((double)(sat - hf) * (P.exc_gain * 0.25));
+            } else if (EPI == EPI_DYNAMICS) {   // y0 = band 2, y1 = band 3; downward knees only
+                st[0] = band_chain(yflt(0), P.dyn.band[1]);
+                st[1] = band_chain(yflt(NF > 1 ? 1 : 0), P.dyn.band[2]);
+            } else if (EPI == EPI_DYNAMICS_GEN) {
+                st[0] = band_chain_gen(yflt(0), P.dyn.band[1]);
+                st[1] = band_chain_gen(yflt(NF > 1 ? 1 : 0), P.dyn.band[2]);
+            }
+        };
+        // xa = aux0 (prologue applied), a1c = aux1
+        auto final_value = [&](float s0, float s1, float xa, float a1c) -> float {
+            if (EPI == EPI_COMBINE) {
+                const float res = (float)(fma(P.wc, (double)xa, (double)s0) * P.trim);      // float64 recombination, one cast
+                return P.epi_clip ? fminf(fmaxf(res, -1.f), 1.f) : res;
+            } else if (EPI == EPI_EXCITER) {
+                return (float)((double)s0 + (double)xa);
+            } else if (EPI == EPI_DYNAMICS) {   // aux0 = band 1, aux1 = band 4 (pipeline.py:466-481, :484-492, :636)
                 float sacc = band_chain(xa, P.dyn.band[0]);
-                sacc = __fadd_rn(sacc, band_chain(yflt(0), P.dyn.band[1]));
-                sacc = __fadd_rn(sacc, band_chain(yflt(NF > 1 ? 1 : 0), P.dyn.band[2]));
+                sacc = __fadd_rn(sacc, s0);
+                sacc = __fadd_rn(sacc, s1);
                 sacc = __fadd_rn(sacc, band_chain(a1c, P.dyn.band[3]));
                 return maximize_limit(sacc, P.dyn);
             } else {                             // EPI_DYNAMICS_GEN: upward bands and/or the v1 parallel compressor
                 float sacc = band_chain_gen(xa, P.dyn.band[0]);
-                sacc = __fadd_rn(sacc, band_chain_gen(yflt(0), P.dyn.band[1]));
-                sacc = __fadd_rn(sacc, band_chain_gen(yflt(NF > 1 ? 1 : 0), P.dyn.band[2]));
+                sacc = __fadd_rn(sacc, s0);
+                sacc = __fadd_rn(sacc, s1);
                 sacc = __fadd_rn(sacc, band_chain_gen(a1c, P.dyn.band[3]));
                 float res = maximize_limit(sacc, P.dyn);
                 if (par_mix >= 0.01f) res = parallel_compress(res, par_mix, par_one_minus, P.dyn);
@@ -523,26 +519,14 @@ __global__ void __launch_bounds__(kT, Sweep2Cfg<M, NF, NIN, DIR, EPI, NAUX, ST>:
         }
         if (PP.skip & 4) {
         } else if (!inj_thread) {
-            // a recombining epilogue keeps the loop rolled (2 float4 groups in flight): fully unrolled, the
-            // hoisted aux / input loads cost ~100 extra registers and halve the occupancy
-#pragma unroll (EPI == EPI_STORE ? kS / 4 : (NF32 == NF ? 4 : 2))
+#pragma unroll (EPI == EPI_STORE ? kS / 4 : 4)
             for (int u = 0; u < kS / 4; ++u) {
                 const int uu = (DIR > 0) ? u : (kS / 4 - 1 - u);
                 const int off = cbase + ((4 * uu) ^ cx);
                 float4 xv[NIN];
 #pragma unroll
                 for (int s = 0; s < NIN; ++s) xv[s] = *reinterpret_cast<const float4*>(tin + (size_t)s * kL + off);
-                float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;
-                if (EPI != EPI_STORE && NAUX > 0) a0 = *reinterpret_cast<const float4*>(auxs + off);
-                if (EPI != EPI_STORE && NAUX > 1) a1 = *reinterpret_cast<const float4*>(auxs + kL + off);
-                if (EPI != EPI_STORE && aux_pmode == PRO_SUBMUL_F32) {
-                    a0.x = __fmul_rn(__fsub_rn(a0.x, aux_subf), aux_mulf); a0.y = __fmul_rn(__fsub_rn(a0.y, aux_subf), aux_mulf);
-                    a0.z = __fmul_rn(__fsub_rn(a0.z, aux_subf), aux_mulf); a0.w = __fmul_rn(__fsub_rn(a0.w, aux_subf), aux_mulf);
-                } else if (EPI != EPI_STORE && aux_pmode == PRO_MUL_F64) {
-                    a0.x = (float)((double)a0.x * aux_muld); a0.y = (float)((double)a0.y * aux_muld);
-                    a0.z = (float)((double)a0.z * aux_muld); a0.w = (float)((double)a0.w * aux_muld);
-                }
-                float4 yv[NOUT];
+                float4 yv[NWR];
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
                     const int cc = (DIR > 0) ? c : (3 - c);
@@ -565,22 +549,14 @@ __global__ void __launch_bounds__(kT, Sweep2Cfg<M, NF, NIN, DIR, EPI, NAUX, ST>:
 #pragma unroll
                         for (int f = 0; f < NF; ++f) setcomp4(yv[f < NOUT ? f : 0], cc, f < NF32 ? yf[f] : (float)yd[f]);
                     } else {
-                        const float res = epi_value(comp4(a0, cc), comp4(a1, cc), yf, yd);
-                        setcomp4(yv[0], cc, res);
-                    }
-                }
-                if (EPI != EPI_STORE) {     // output peak: one decision per float4 group
-                    if (pk_fast) {
-                        pk = fmaxf(fmaxf(pk, fmaxf(fabsf(yv[0].x), fabsf(yv[0].y))), fmaxf(fabsf(yv[0].z), fabsf(yv[0].w)));
-                    } else {
-                        const long long q = tile_lo + cbase + 4 * uu;
-#pragma unroll
-                        for (int c = 0; c < 4; ++c)
-                            if (q + c >= P.pk_lo && q + c <= P.pk_hi) pk = fmaxf(pk, fabsf(comp4(yv[0], c)));
+                        float st[2];
+                        stage_value(yf, yd, st);
+                        setcomp4(yv[0], cc, st[0]);
+                        if (NSTAGE > 1) setcomp4(yv[NWR > 1 ? 1 : 0], cc, st[1]);
                     }
                 }
 #pragma unroll
-                for (int f = 0; f < NOUT; ++f) *reinterpret_cast<float4*>(tout[f] + off) = yv[f];
+                for (int f = 0; f < NWR; ++f) *reinterpret_cast<float4*>(tout[f] + off) = yv[f];
             }
         } else {
             // the one thread of tile 0 that starts from zi * x_first after `d0` dead samples
@@ -612,12 +588,10 @@ __global__ void __launch_bounds__(kT, Sweep2Cfg<M, NF, NIN, DIR, EPI, NAUX, ST>:
 #pragma unroll
                     for (int f = 0; f < NF; ++f) tout[f][off] = f < NF32 ? yf[f] : (float)yd[f];
                 } else {
-                    float xa0 = NAUX > 0 ? auxs[off] : 0.f;
-                    if (aux_pmode != PRO_NONE) xa0 = pro1(aux_pmode, xa0, aux_subf, aux_mulf, aux_muld);
-                    const float res = epi_value(xa0, NAUX > 1 ? auxs[kL + off] : 0.f, yf, yd);
-                    tout[0][off] = res;
-                    const long long q = tile_lo + cbase + mi;
-                    if (q >= P.pk_lo && q <= P.pk_hi) pk = fmaxf(pk, fabsf(res));
+                    float st[2];
+                    stage_value(yf, yd, st);
+                    tout[0][off] = st[0];
+                    if (NSTAGE > 1) tout[NWR > 1 ? 1 : 0][off] = st[1];
                 }
             }
         }
@@ -625,8 +599,69 @@ __global__ void __launch_bounds__(kT, Sweep2Cfg<M, NF, NIN, DIR, EPI, NAUX, ST>:
         __syncthreads();                               // (E) results visible
         MM_TICK(6);
 
-        // ---- store: NOUT finished float32 streams, coalesced -----------------------------------------------------
+        // ---- store: coalesced.  EPI_STORE: NOUT finished float32 streams.  Recombining epilogues: finish here ------------
         if (out_fast && (PP.skip & 1)) {
+        } else if (EPI != EPI_STORE) {
+            const float* ax0 = P.aux[0] + rowoff;
+            const float* ax1 = (NAUX > 1) ? (P.aux[1] + rowoff) : ax0;
+            if (out_fast) {
+                const int so0 = 4 * swz(tid);
+                const size_t go0 = (size_t)tile_lo + 4 * tid;
+                float4 xa[kTileVecs / kT], xb[kTileVecs / kT];
+#pragma unroll
+                for (int r = 0; r < kTileVecs / kT; ++r) {     // all aux loads first: 8 (16) independent requests in flight
+                    xa[r] = __ldcs(reinterpret_cast<const float4*>(ax0 + go0 + 4 * kT * r));
+                    if (NAUX > 1) xb[r] = __ldcs(reinterpret_cast<const float4*>(ax1 + go0 + 4 * kT * r));
+                }
+#pragma unroll
+                for (int r = 0; r < kTileVecs / kT; ++r) {
+                    float4 a0 = xa[r];
+                    if (aux_pmode == PRO_SUBMUL_F32) {
+                        a0.x = __fmul_rn(__fsub_rn(a0.x, aux_subf), aux_mulf); a0.y = __fmul_rn(__fsub_rn(a0.y, aux_subf), aux_mulf);
+                        a0.z = __fmul_rn(__fsub_rn(a0.z, aux_subf), aux_mulf); a0.w = __fmul_rn(__fsub_rn(a0.w, aux_subf), aux_mulf);
+                    } else if (aux_pmode == PRO_MUL_F64) {
+                        a0.x = (float)((double)a0.x * aux_muld); a0.y = (float)((double)a0.y * aux_muld);
+                        a0.z = (float)((double)a0.z * aux_muld); a0.w = (float)((double)a0.w * aux_muld);
+                    }
+                    const float4 s0 = *reinterpret_cast<const float4*>(tout[0] + so0 + 4 * kT * r);
+                    float4 s1 = s0;
+                    if (NSTAGE > 1) s1 = *reinterpret_cast<const float4*>(tout[NWR > 1 ? 1 : 0] + so0 + 4 * kT * r);
+                    const float4 a1 = (NAUX > 1) ? xb[r] : a0;
+                    float4 o;
+                    o.x = final_value(s0.x, s1.x, a0.x, a1.x); o.y = final_value(s0.y, s1.y, a0.y, a1.y);
+                    o.z = final_value(s0.z, s1.z, a0.z, a1.z); o.w = final_value(s0.w, s1.w, a0.w, a1.w);
+                    if (pk_fast) {
+                        pk = fmaxf(fmaxf(pk, fmaxf(fabsf(o.x), fabsf(o.y))), fmaxf(fabsf(o.z), fabsf(o.w)));
+                    } else {
+                        const long long q = tile_lo + 4 * (tid + kT * r);
+#pragma unroll
+                        for (int c = 0; c < 4; ++c)
+                            if (q + c >= P.pk_lo && q + c <= P.pk_hi) pk = fmaxf(pk, fabsf(comp4(o, c)));
+                    }
+                    __stcs(reinterpret_cast<float4*>(P.out[0] + rowoff + go0 + 4 * kT * r), o);
+                }
+            } else {
+#pragma unroll 1
+                for (int r = 0; r < kTileVecs / kT; ++r) {
+                    const int v = tid + kT * r;
+                    const long long q = tile_lo + 4 * v;
+                    if (q + 3 < st_lo || q > st_hi) continue;
+                    const int so = 4 * swz(v);
+                    const float4 s0 = *reinterpret_cast<const float4*>(tout[0] + so);
+                    float4 s1 = s0;
+                    if (NSTAGE > 1) s1 = *reinterpret_cast<const float4*>(tout[NWR > 1 ? 1 : 0] + so);
+                    float* dst = P.out[0] + rowoff;
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        if (q + c < st_lo || q + c > st_hi) continue;
+                        float xa0 = ax0[q + c];
+                        if (aux_pmode != PRO_NONE) xa0 = pro1(aux_pmode, xa0, aux_subf, aux_mulf, aux_muld);
+                        const float res = final_value(comp4(s0, c), comp4(s1, c), xa0, NAUX > 1 ? ax1[q + c] : 0.f);
+                        if (q + c >= P.pk_lo && q + c <= P.pk_hi) pk = fmaxf(pk, fabsf(res));
+                        dst[q + c] = res;
+                    }
+                }
+            }
         } else if (out_fast) {
             // interior tile: every vector is complete; base + immediate addressing (swz(tid + kT r) = swz(tid) + kT r)
             const int so0 = 4 * swz(tid);
