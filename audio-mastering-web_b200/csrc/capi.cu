@@ -809,14 +809,14 @@ int mm_dev_master_slice(mm_ctx* c, const mm_geom* g, int chain, const mm_style* 
 // that on a PCIe-attached GPU the call costs about max(copy in, compute, copy out) instead of their sum.  Staging
 // buffers are double-buffered per direction; the chain's own workspace is sized for one chunk.  Results do not
 // depend on the chunking: the dither counter is keyed by the track's index in the whole call.
-int mm_master_host(mm_ctx* c, int chain, int32_t tracks, int64_t n, int32_t channels, int32_t sr, const mm_style* styles,
-                   const float* audio_in, float* audio_out, int16_t* pcm16_out, const float* noise_host, uint64_t seed,
-                   mm_track_stats* stats_host, uint32_t flags) {
-    MM_API_BEGIN(c);
+static int master_host_impl(mm_ctx* c, int chain, int32_t tracks, int64_t n, int32_t channels, int32_t sr, const mm_style* styles,
+                            const float* audio_in, const int16_t* pcm16_in, float* audio_out, int16_t* pcm16_out,
+                            const float* noise_host, uint64_t seed, mm_track_stats* stats_host, uint32_t flags) {
     mm_geom g;
     g.n = n; g.stride = mm_row_stride(n); g.tracks = tracks; g.channels = channels; g.sr = sr; g.track_base = 0;
     MM_TRY(check_geom(&g));
-    if (!audio_in) { set_error("mm_master_host: audio_in is null"); return 1; }
+    if (!audio_in && !pcm16_in) { set_error("mm_master_host: the input buffer is null"); return 1; }
+    const size_t in_elem = pcm16_in ? sizeof(int16_t) : sizeof(float);
     if (!c->h2d_stream) MM_CUDA(cudaStreamCreateWithFlags(&c->h2d_stream, cudaStreamNonBlocking));
     if (!c->d2h_stream) MM_CUDA(cudaStreamCreateWithFlags(&c->d2h_stream, cudaStreamNonBlocking));
     const size_t per_track = (size_t)n * channels;                  // interleaved samples of one track
@@ -857,7 +857,8 @@ int mm_master_host(mm_ctx* c, int chain, int32_t tracks, int64_t n, int32_t chan
         const int t0 = k * tc, tn = std::min(tc, (int)tracks - t0);
         const size_t off = (size_t)t0 * per_track, cnt = (size_t)tn * per_track;
         if (k >= 2) MM_CUDA(cudaStreamWaitEvent(c->h2d_stream, ev_deint[k - 2], 0));    // staging buffer k & 1 is free again
-        MM_CUDA(cudaMemcpyAsync(il[k & 1], audio_in + off, cnt * sizeof(float), cudaMemcpyHostToDevice, c->h2d_stream));
+        const void* hsrc = pcm16_in ? (const void*)(pcm16_in + off) : (const void*)(audio_in + off);
+        MM_CUDA(cudaMemcpyAsync(il[k & 1], hsrc, cnt * in_elem, cudaMemcpyHostToDevice, c->h2d_stream));
         if (noise_host) {
             if (k >= 2) MM_CUDA(cudaStreamWaitEvent(c->h2d_stream, ev_done[k - 2], 0));
             MM_CUDA(cudaMemcpyAsync(nz[k & 1], noise_host + off, cnt * sizeof(float), cudaMemcpyHostToDevice, c->h2d_stream));
@@ -874,7 +875,8 @@ int mm_master_host(mm_ctx* c, int chain, int32_t tracks, int64_t n, int32_t chan
         gk.tracks = tn;
         gk.track_base = t0;                                  // index of the chunk's first track in the call (dither counter)
         if ((rc = cudaStreamWaitEvent(c->stream, ev_in[k], 0) != cudaSuccess)) { set_error("cudaStreamWaitEvent failed"); break; }
-        if ((rc = mm_dev_deinterleave(c, &gk, il[k & 1], pl)) != 0) break;
+        if (pcm16_in) { if ((rc = run_layout_pcm16(c, &gk, reinterpret_cast<const int16_t*>(il[k & 1]), pl)) != 0) break; }
+        else if ((rc = mm_dev_deinterleave(c, &gk, il[k & 1], pl)) != 0) break;
         cudaEventRecord(ev_deint[k], c->stream);
         if (k >= 2) cudaStreamWaitEvent(c->stream, ev_out[k - 2], 0);     // pcm / ol staging k & 1 has left the device
         if ((rc = master_impl(c, &gk, chain, styles + t0, pl, pl, pcm16_out ? pcm[k & 1] : nullptr, noise_host ? nz[k & 1] : nullptr, seed,
@@ -900,6 +902,25 @@ int mm_master_host(mm_ctx* c, int chain, int32_t tracks, int64_t n, int32_t chan
         rc = 1;
     }
     return rc;
+}
+
+int mm_master_host(mm_ctx* c, int chain, int32_t tracks, int64_t n, int32_t channels, int32_t sr, const mm_style* styles,
+                   const float* audio_in, float* audio_out, int16_t* pcm16_out, const float* noise_host, uint64_t seed,
+                   mm_track_stats* stats_host, uint32_t flags) {
+    MM_API_BEGIN(c);
+    return master_host_impl(c, chain, tracks, n, channels, sr, styles, audio_in, nullptr, audio_out, pcm16_out, noise_host, seed,
+                            stats_host, flags);
+}
+
+// Job-level variant (what _run_mastering_job does with a PCM_16 WAV upload, routers/mastering.py:350-441): the data chunk's
+// int16 frames go to the device as they are (half the bytes of float32 over PCIe) and are widened there exactly as
+// libsndfile does for dtype="float32" (x / 32768, pipeline.py:814-817); the result comes back as PCM_16 again.
+int mm_master_host_pcm16(mm_ctx* c, int chain, int32_t tracks, int64_t n, int32_t channels, int32_t sr, const mm_style* styles,
+                         const int16_t* pcm16_in, float* audio_out, int16_t* pcm16_out, uint64_t seed, mm_track_stats* stats_host,
+                         uint32_t flags) {
+    MM_API_BEGIN(c);
+    return master_host_impl(c, chain, tracks, n, channels, sr, styles, nullptr, pcm16_in, audio_out, pcm16_out, nullptr, seed,
+                            stats_host, flags);
 }
 
 // ---- filter design ----------------------------------------------------------------------------

@@ -456,6 +456,16 @@ __global__ void __launch_bounds__(kPwThreads) deinterleave_kernel(const float* _
     const float* src = il + ((size_t)track * (size_t)n + (size_t)i) * channels;
     for (int c = 0; c < channels; ++c) pl[(size_t)(track * channels + c) * (size_t)stride + kLead + i] = src[c];
 }
+// PCM_16 frames -> planar float32, x / 32768 (libsndfile's float conversion of 16-bit PCM)
+__global__ void __launch_bounds__(kPwThreads) deinterleave_pcm16_kernel(const int16_t* __restrict__ il, float* __restrict__ pl,
+                                                                        long long n, long long stride, int channels) {
+    const int track = blockIdx.y;
+    const long long i = (long long)blockIdx.x * kPwThreads + threadIdx.x;
+    if (i >= n) return;
+    const int16_t* src = il + ((size_t)track * (size_t)n + (size_t)i) * channels;
+    for (int c = 0; c < channels; ++c)
+        pl[(size_t)(track * channels + c) * (size_t)stride + kLead + i] = (float)src[c] * (1.0f / 32768.0f);
+}
 __global__ void __launch_bounds__(kPwThreads) interleave_kernel(const float* __restrict__ pl, float* __restrict__ il,
                                                                 long long n, long long stride, int channels) {
     const int track = blockIdx.y;

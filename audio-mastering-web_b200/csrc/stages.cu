@@ -447,6 +447,14 @@ int run_quantize(mm_ctx* c, const QuantArgs& Q) {
     return 0;
 }
 
+int run_layout_pcm16(mm_ctx* c, const mm_geom* g, const int16_t* interleaved, float* planar) {
+    dim3 grid((unsigned)((g->n + kPwThreads - 1) / kPwThreads), (unsigned)g->tracks);
+    KernelScope ks(c, "deinterleave_pcm16");
+    deinterleave_pcm16_kernel<<<grid, kPwThreads, 0, c->stream>>>(interleaved, planar, g->n, g->stride, g->channels);
+    MM_CUDA(cudaGetLastError());
+    return 0;
+}
+
 int run_white_noise(mm_ctx* c, const WhiteArgs& W) {
     dim3 grid((unsigned)((W.n + kPwThreads - 1) / kPwThreads), (unsigned)W.tracks);
     KernelScope ks(c, "dither_white_noise");

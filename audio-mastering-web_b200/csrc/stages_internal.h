@@ -52,6 +52,7 @@ int run_quantize(mm_ctx* c, const QuantArgs& Q);
 int run_white_noise(mm_ctx* c, const WhiteArgs& W);
 // dir 0: interleaved -> planar, 1: planar -> interleaved
 int run_layout(mm_ctx* c, const mm_geom* g, const float* interleaved, float* planar, int dir);
+int run_layout_pcm16(mm_ctx* c, const mm_geom* g, const int16_t* interleaved, float* planar);
 void fill_dyn(DynParams* d, double knee_db, const double* band_ratios, double max_upward_boost_db);
 void fill_parallel(DynParams* d, double ratio, double threshold_db);
 

@@ -89,6 +89,8 @@ SIGNATURES = {
     "mm_dev_master_slice": (_i, [_vp, _gp, _i, C.POINTER(Style), _vp, _vp, _vp, _vp, _u64, _vp, _u32, _vp]),
     "mm_master_host": (_i, [_vp, _i, C.c_int32, _i64, C.c_int32, C.c_int32, C.POINTER(Style), _vp, _vp, _vp, _vp, _u64,
                             C.POINTER(TrackStats), _u32]),
+    "mm_master_host_pcm16": (_i, [_vp, _i, C.c_int32, _i64, C.c_int32, C.c_int32, C.POINTER(Style), _vp, _vp, _vp, _u64,
+                                  C.POINTER(TrackStats), _u32]),
     "mm_host_alloc": (_i, [C.POINTER(_vp), _i64]),
     "mm_host_free": (_i, [_vp]),
     "mm_ctx_workspace_bytes": (_i64, [_vp]),

@@ -444,3 +444,30 @@ def master_batch(tracks, sr, styles, targets=None, chain="v2", want_int16=False,
     for s in stats:
         res["stats"].append({k: (list(getattr(s, k)) if k == "mean" else getattr(s, k)) for k, _ in s._fields_})
     return res
+
+
+def master_wav_jobs(wavs, styles, targets=None, chain="v2", seed=0, eng: Optional[Engine] = None) -> list:
+    """Additive, job level: what ``_run_mastering_job(_v2)`` does per upload (routers/mastering.py:350-637) for a batch of
+    PCM_16 WAV uploads of identical shape -- decode, master, dither, encode -- with the PCM frames crossing PCIe as int16
+    in both directions (``mm_master_host_pcm16``).  Returns a list of dicts ``wav`` (bytes), ``stats``."""
+    import ctypes as C_
+    eng = eng or get_engine()
+    metas = [wavio.pcm16_view(w) for w in wavs]
+    (n, ch, sr) = metas[0][1:]
+    if any(m[1:] != (n, ch, sr) for m in metas):
+        raise ValueError("master_wav_jobs: uploads must share length, channel count and sample rate")
+    pcm_in = np.ascontiguousarray(np.stack([m[0] for m in metas]))                # (T, n, ch) int16
+    pcm_out = np.empty_like(pcm_in)
+    names = [s if s in STYLE_CONFIGS else "standard" for s in styles]
+    if targets is None:
+        targets = [STYLE_CONFIGS[s]["lufs"] for s in names]
+    arr = (_lib.Style * len(wavs))(*[style_struct(STYLE_CONFIGS[s], t) for s, t in zip(names, targets)])
+    st = (_lib.TrackStats * len(wavs))()
+    _lib.check(eng.lib.mm_master_host_pcm16(eng.ctx, _lib.CHAIN_V1 if chain == "v1" else _lib.CHAIN_V2, len(wavs), n, ch, sr, arr,
+                                            pcm_in.ctypes.data_as(C_.c_void_p), None, pcm_out.ctypes.data_as(C_.c_void_p), int(seed), st,
+                                            _lib.FLAG_MEASURE_IN | _lib.FLAG_MEASURE_OUT))
+    out = []
+    for t in range(len(wavs)):
+        rec = {k: (list(getattr(st[t], k)) if k == "mean" else getattr(st[t], k)) for k, _ in st[t]._fields_}
+        out.append({"wav": wavio.pack_wav_pcm16(pcm_out[t], sr), "stats": rec})
+    return out

@@ -69,3 +69,26 @@ def unpack_wav(data: bytes):
         raise ValueError(f"unsupported WAV format tag {tag}")
     n = x.size // ch
     return np.ascontiguousarray(x[: n * ch].reshape(n, ch)), int(sr)
+
+
+def pcm16_view(data: bytes):
+    """Canonical PCM_16 WAV bytes -> (int16 ``(n, ch)`` view of the data chunk, n, ch, sr) without widening."""
+    import struct as _st
+    if len(data) < 12 or data[:4] != b"RIFF" or data[8:12] != b"WAVE":
+        raise ValueError("not a RIFF/WAVE stream")
+    pos, fmt, body = 12, None, None
+    while pos + 8 <= len(data):
+        cid = data[pos:pos + 4]
+        (size,) = _st.unpack("<I", data[pos + 4:pos + 8])
+        start = pos + 8
+        if cid == b"fmt ":
+            tag, ch, sr, _, _, bits = _st.unpack("<HHIIHH", data[start:start + 16])
+            fmt = (tag, ch, sr, bits)
+        elif cid == b"data":
+            body = data[start:start + size]
+        pos = start + size + (size & 1)
+    if fmt is None or body is None or fmt[0] != 1 or fmt[3] != 16:
+        raise ValueError("pcm16_view: a PCM_16 WAV is required")
+    ch, sr = fmt[1], fmt[2]
+    x = np.frombuffer(body[: len(body) // (2 * ch) * 2 * ch], dtype="<i2").reshape(-1, ch)
+    return x, x.shape[0], ch, sr

@@ -322,7 +322,30 @@ def run_ours(args):
         e2e = {"value": world * e_tracks * dur * reps / wall, "unit": UNIT, "h2d_bytes_per_step": frames * 4,
                "d2h_bytes_per_step": frames * 2 + e_tracks * C.sizeof(TrackStats), "tracks_per_step": e_tracks,
                "api": "mm_master_host (C ABI, pinned host buffers in/out)"}
-        del hin, hpcm
+        # job-level variant: the upload's PCM_16 frames cross PCIe as they are (informative; the headline stays float32 in)
+        hin16 = torch.empty((e_tracks, n, 2), dtype=torch.int16, pin_memory=True)
+        hin16.copy_((hin * 32767.0).round().to(torch.int16))
+        del hin
+
+        def e2e16_step(i):
+            _lib.check(eng.lib.mm_master_host_pcm16(eng.ctx, chain, e_tracks, n, 2, sr, earr, C.c_void_p(hin16.data_ptr()), None,
+                                                    C.c_void_p(hpcm.data_ptr()), 199 + i, hstats, flags))
+
+        e2e16_step(0)
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(reps):
+            e2e16_step(1 + i)
+        torch.cuda.synchronize()
+        wall16 = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([wall16], dtype=torch.float64, device=eng.tdev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            wall16 = float(t.item())
+        e2e["pcm16_in"] = {"value": world * e_tracks * dur * reps / wall16, "unit": UNIT, "h2d_bytes_per_step": frames * 2,
+                           "d2h_bytes_per_step": frames * 2 + e_tracks * C.sizeof(TrackStats),
+                           "api": "mm_master_host_pcm16 (PCM_16 frames in and out, widened on the device)"}
+        del hin16, hpcm
 
     if rank != 0:
         if world > 1:

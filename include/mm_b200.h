@@ -213,6 +213,13 @@ int mm_master_host(mm_ctx*, int chain, int32_t tracks, int64_t n, int32_t channe
                    int16_t* pcm16_out, const float* noise_host, uint64_t dither_seed,
                    mm_track_stats* stats_host, uint32_t flags);
 
+/* Job-level variant: PCM_16 frames in (the WAV data chunk of an upload, widened on the device as libsndfile does for
+ * dtype="float32": x / 32768, backend/app/pipeline.py:814-817), PCM_16 (and/or float32) out.  Half the host->device
+ * bytes of the float32 entry point; same pipelining, same results as mm_master_host on the widened input. */
+int mm_master_host_pcm16(mm_ctx*, int chain, int32_t tracks, int64_t n, int32_t channels, int32_t sr,
+                         const mm_style* styles_host, const int16_t* pcm16_in, float* audio_out,
+                         int16_t* pcm16_out, uint64_t dither_seed, mm_track_stats* stats_host, uint32_t flags);
+
 /* Pinned host memory for the host-buffer entry point (cudaMallocHost / cudaFreeHost). */
 int mm_host_alloc(void** out, int64_t bytes);
 int mm_host_free(void* p);

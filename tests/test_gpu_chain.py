@@ -227,3 +227,27 @@ def test_config1_full_length_track_both_chains_vs_oracle(P):
         dtp = abs(P.true_peak_dbfs(out, sr) - oc.true_peak_dbfs(ref))
         print(f"[parity] C1 {which} 180 s: max|gpu-oracle| = {e:.3e}, dLUFS = {dl:.2e}, dTP = {dtp:.2e} dB")
         assert e <= 1e-4 and dl <= 0.01 and dtp <= 0.01
+
+
+def test_job_level_pcm16_entry_equals_float_entry(P):
+    """master_wav_jobs / mm_master_host_pcm16 (PCM_16 frames over PCIe, widened on the device as libsndfile does) gives
+    bit for bit the int16 of the float32 host entry fed with pcm / 32768."""
+    import ctypes as C
+    from mm_b200 import _lib, synth, wavio
+    from mm_b200.engine import get_engine, style_struct, TrackStats
+    sr, names = 48000, ["standard", "edm", "podcast"]
+    pcm = [np.round(synth.numpy_track(60 + i, sr, 0.7) * 32767.0).astype(np.int16) for i in range(len(names))]
+    wavs = [wavio.pack_wav_pcm16(p, sr) for p in pcm]
+    jobs = P.master_wav_jobs(wavs, names, chain="v2", seed=11)
+    eng = get_engine()
+    hin = np.ascontiguousarray(np.stack(pcm).astype(np.float32) / np.float32(32768.0))
+    out16 = np.zeros(hin.shape, dtype=np.int16)
+    styles = (_lib.Style * len(names))(*[style_struct(P.STYLE_CONFIGS[s], P.STYLE_CONFIGS[s]["lufs"]) for s in names])
+    st = (TrackStats * len(names))()
+    _lib.check(eng.lib.mm_master_host(eng.ctx, _lib.CHAIN_V2, len(names), hin.shape[1], 2, sr, styles, hin.ctypes.data_as(C.c_void_p),
+                                      None, out16.ctypes.data_as(C.c_void_p), None, 11, st, _lib.FLAG_MEASURE_IN | _lib.FLAG_MEASURE_OUT))
+    for i, job in enumerate(jobs):
+        assert job["wav"][:4] == b"RIFF"
+        got = np.frombuffer(job["wav"][44:], dtype="<i2").reshape(-1, 2)
+        assert np.array_equal(got, out16[i]), i
+        assert abs(job["stats"]["lufs_out"] - st[i].lufs_out) < 1e-12
