@@ -500,6 +500,31 @@ int mm_dev_apply_target_curve(mm_ctx* c, const mm_geom* g, const float* in, floa
     return st_target_curve(c, g, in, out, none);
 }
 
+int mm_dev_apply_target_curve_linear_phase(mm_ctx* c, const mm_geom* g, const float* in, float* out, int eq_ms) {
+    MM_API_BEGIN(c);
+    MM_TRY(check_geom(g));
+    Bufs B;
+    MM_TRY(get_bufs(c, g, &B));
+    if (eq_ms && g->channels == 2) {       // pipeline.py:248-255 with phase_mode="linear_phase" on mid and side
+        PwArgs A;
+        pw_base(&A, in, B.T[1], PW_MS_ENCODE);
+        MM_TRY(run_pointwise(c, g, A, "ms_encode"));
+        MM_TRY(st_target_curve_linear_phase(c, g, B.T[1], B.T[2]));
+        PwArgs D;
+        pw_base(&D, B.T[2], out, PW_MS_DECODE);
+        return run_pointwise(c, g, D, "ms_decode_clip");
+    }
+    if (in != out) return st_target_curve_linear_phase(c, g, in, out);
+    MM_TRY(st_target_curve_linear_phase(c, g, in, B.T[1]));
+    MM_CUDA(cudaMemcpyAsync(out, B.T[1], batch_floats(g) * sizeof(float), cudaMemcpyDeviceToDevice, c->stream));
+    return 0;
+}
+
+int mm_design_linear_phase_ir(int sr, int n_fft, float* ir) {
+    if (!ir || !linear_phase_target_ir(sr, n_fft, ir)) { set_error("mm_design_linear_phase_ir: bad arguments"); return 1; }
+    return 0;
+}
+
 int mm_dev_apply_deesser(mm_ctx* c, const mm_geom* g, const float* in, float* out, double threshold_db, double ratio,
                          double freq_lo, double freq_hi, double attack_ms, double release_ms) {
     MM_API_BEGIN(c);

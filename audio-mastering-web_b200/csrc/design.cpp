@@ -126,6 +126,58 @@ bool lfilter_zi(const Ba& f, double* zi) {
     return true;
 }
 
+static std::complex<long double> freq_resp(const Ba& f, long double w) {
+    std::complex<long double> num(0, 0), den(0, 0);
+    for (int i = 0; i <= f.m; ++i) {
+        const std::complex<long double> e = std::polar(1.0L, -w * (long double)i);
+        num += (long double)f.b[i] * e;
+        den += (long double)f.a[i] * e;
+    }
+    return num / den;
+}
+
+bool linear_phase_target_ir(int sr, int n_fft, float* ir) {
+    if (sr <= 0 || n_fft < 8 || (n_fft & 1)) return false;
+    const long double pi = 3.14159265358979323846264338327950288L;
+    const double nyq = sr / 2.0;
+    Ba hp, lp, pres, mud;
+    double w1[2];
+    w1[0] = std::min(40.0 / nyq, 0.99);
+    if (!butter(2, kHigh, w1, &hp)) return false;
+    w1[0] = std::min(18000.0 / nyq, 0.99);
+    if (!butter(2, kLow, w1, &lp)) return false;
+    const double fp = std::min(3000.0 / nyq, 0.99), fm = std::min(300.0 / nyq, 0.99);
+    double wb[2] = {fp * 0.7, fp * 1.3};
+    if (!butter(1, kBand, wb, &pres)) return false;
+    wb[0] = fm * 0.7; wb[1] = fm * 1.3;
+    if (!butter(1, kBand, wb, &mud)) return false;
+    const long double gp = powl(10.0L, 0.35L / 20.0L), gm = powl(10.0L, -0.25L / 20.0L);
+    const int N = n_fft, H = N / 2;
+    std::vector<long double> mag(H + 1);
+    for (int k = 0; k <= H; ++k) {
+        const long double w = pi * (long double)k / (long double)H;
+        const std::complex<long double> Hc = freq_resp(hp, w) * freq_resp(lp, w) *
+            (std::complex<long double>(1, 0) + (gp - 1.0L) * freq_resp(pres, w) + (gm - 1.0L) * freq_resp(mud, w));
+        long double m = std::abs(Hc);
+        mag[k] = fminl(fmaxl(m, 1e-8L), 1e8L);
+    }
+    // H_full[k] = mag[k] e^{i phi_k}, phi_k = -2 pi k (N-1) / (2N); H_full[N-k] = conj; H_full[N/2] = its real part.
+    // ir[n] = Re ifft = (1/N) [ mag0 + 2 sum_{k=1}^{H-1} mag_k cos(2 pi k n / N + phi_k) + mag_H cos(phi_H) cos(pi n) ]
+    for (int n = 0; n < N; ++n) {
+        long double acc = mag[0];
+        for (int k = 1; k < H; ++k) {
+            // 2 pi k n / N + phi_k = 2 pi k (n - (N-1)/2) / N = pi k (2n - N + 1) / N; reduce the integer product mod 2N
+            const long long t = ((long long)k * (long long)(2 * n - N + 1)) % (2LL * N);
+            acc += 2.0L * mag[k] * cosl(pi * (long double)t / (long double)N);
+        }
+        const long long tH = ((long long)H * (long long)(N - 1)) % (2LL * N);
+        const long double re_nyq = mag[H] * cosl(-pi * (long double)tH / (long double)N);
+        acc += re_nyq * ((n & 1) ? -1.0L : 1.0L);
+        ir[n] = (float)(double)(acc / (long double)N);
+    }
+    return true;
+}
+
 Ba k_weighting_stage(int stage, double rate) {
     const double pi = 3.14159265358979323846;
     Ba f;

@@ -24,6 +24,10 @@ enum BType { kLow = 0, kHigh = 1, kBand = 2 };
 bool butter(int order, BType bt, const double* wn, Ba* out);
 // scipy.signal.lfilter_zi(b, a): steady-state DF2T state of the unit step response.
 bool lfilter_zi(const Ba& f, double* zi);
+// _build_linear_phase_ir (backend/app/pipeline.py:187-217): the magnitude of the target curve HP*LP*(1 + (gp-1) Hpres +
+// (gm-1) Hmud) on the n_fft/2+1 grid, clipped to [1e-8, 1e8], with linear phase of (n_fft-1)/2 samples; real part of
+// the inverse DFT, cast to float32.  ir receives n_fft values.
+bool linear_phase_target_ir(int sr, int n_fft, float* ir);
 // pyloudnorm IIRfilter coefficients: stage 0 = high shelf (+4 dB, Q 1/sqrt2, 1500 Hz),
 // stage 1 = high pass (Q 0.5, 38 Hz).
 Ba k_weighting_stage(int stage, double rate);

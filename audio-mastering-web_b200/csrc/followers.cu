@@ -12,6 +12,8 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <map>
+#include <vector>
 
 #include "context.h"
 #include "pointwise.cuh"
@@ -236,6 +238,110 @@ int st_haas_imager(mm_ctx* c, const mm_geom* g, const float* in, float* out, dou
     dim3 grid((unsigned)((g->n + 255) / 256), (unsigned)g->tracks);
     KernelScope ks(c, "stereoize_haas");
     haas_kernel<<<grid, 256, 0, c->stream>>>(A);
+    MM_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// ---- apply_target_curve_linear_phase (pipeline.py:220-235): fftconvolve(x, ir, mode="same") with the 4096-tap IR of
+// design.cpp: linear_phase_target_ir, then clip.  Evaluated as a direct-form FIR: x window and the (reversed) taps in
+// shared memory, 8 outputs per thread from registers, float32 products summed per 64-tap block and carried in float64
+// (the reference's pocketfft runs in float32: both sides sit ~1e-6 from the exact convolution).  4096 MAC per sample make
+// this stage FP32-FMA bound (it is an option of the v2 target-curve module, not on the default chains); an
+// overlap-save FFT version on the spectrum kernel's Stockham passes is the next step.
+constexpr int kFirThreads = 256;
+constexpr int kFirPer = 8;
+constexpr int kFirTile = kFirThreads * kFirPer;     // 2048 outputs per CTA
+struct FirArgs {
+    const float* in;
+    float* out;
+    const float* taps;       // device, K floats
+    long long n, stride;
+    int K, center;           // out[i] = sum_k h[k] x[i + center - k]
+    int clip;
+};
+__global__ void __launch_bounds__(kFirThreads) fir_same_kernel(const FirArgs P) {
+    extern __shared__ __align__(16) float fsm[];
+    float* sh = fsm;                                  // hr[j] = h[K - 1 - j]  (so that x and taps walk the same way)
+    float* sx = fsm + P.K;                            // x[base + center - (K - 1) + j], j = 0 .. kFirTile + K - 2 (+ pad)
+    const int row = blockIdx.y;
+    const float* src = P.in + (size_t)row * (size_t)P.stride + kLead;
+    const long long base = (long long)blockIdx.x * kFirTile;
+    for (int j = threadIdx.x; j < P.K; j += kFirThreads) sh[j] = __ldg(P.taps + (P.K - 1 - j));
+    const long long x0 = base + P.center - (P.K - 1);
+    for (int j = threadIdx.x; j < kFirTile + P.K + 8; j += kFirThreads) {
+        const long long i = x0 + j;
+        sx[j] = (i >= 0 && i < P.n) ? __ldcs(src + i) : 0.f;
+    }
+    __syncthreads();
+    // output o = base + t0 + u:  sum_j hr[j] x[o + center - (K-1) + j] = sum_j sh[j] sx[t0 + u + j]
+    const int t0 = threadIdx.x * kFirPer;
+    double acc[kFirPer];
+#pragma unroll
+    for (int u = 0; u < kFirPer; ++u) acc[u] = 0.0;
+#pragma unroll 1
+    for (int jb = 0; jb < P.K; jb += 64) {
+        float part[kFirPer];
+#pragma unroll
+        for (int u = 0; u < kFirPer; ++u) part[u] = 0.f;
+#pragma unroll
+        for (int j8 = 0; j8 < 64; j8 += 8) {
+            float w[16], hv[8];
+#pragma unroll
+            for (int v = 0; v < 4; ++v) {
+                const float4 q = *reinterpret_cast<const float4*>(&sx[t0 + jb + j8 + 4 * v]);
+                w[4 * v] = q.x; w[4 * v + 1] = q.y; w[4 * v + 2] = q.z; w[4 * v + 3] = q.w;
+            }
+#pragma unroll
+            for (int v = 0; v < 2; ++v) {
+                const float4 q = *reinterpret_cast<const float4*>(&sh[jb + j8 + 4 * v]);
+                hv[4 * v] = q.x; hv[4 * v + 1] = q.y; hv[4 * v + 2] = q.z; hv[4 * v + 3] = q.w;
+            }
+#pragma unroll
+            for (int jj = 0; jj < 8; ++jj)
+#pragma unroll
+                for (int u = 0; u < kFirPer; ++u) part[u] = fmaf(hv[jj], w[u + jj], part[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < kFirPer; ++u) acc[u] += (double)part[u];
+    }
+    float* dst = P.out + (size_t)row * (size_t)P.stride + kLead;
+#pragma unroll
+    for (int u = 0; u < kFirPer; ++u) {
+        const long long o = base + t0 + u;
+        if (o < P.n) {
+            float r = (float)acc[u];
+            if (P.clip) r = fminf(fmaxf(r, -1.f), 1.f);
+            dst[o] = r;
+        }
+    }
+}
+
+int st_target_curve_linear_phase(mm_ctx* c, const mm_geom* g, const float* in, float* out) {
+    if (in == out) { set_error("linear-phase target curve: in-place operation is not supported"); return 1; }
+    const int K = 4096;
+    static std::map<int, float*> cache;               // per sample rate, device taps (one device kind per process)
+    float* taps = nullptr;
+    auto it = cache.find(g->sr);
+    if (it != cache.end()) taps = it->second;
+    else {
+        std::vector<float> ir(K);
+        if (!linear_phase_target_ir(g->sr, K, ir.data())) { set_error("linear-phase target curve: IR design failed for %d Hz", g->sr); return 1; }
+        MM_CUDA(cudaMalloc(&taps, K * sizeof(float)));
+        MM_CUDA(cudaMemcpyAsync(taps, ir.data(), K * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+        MM_CUDA(cudaStreamSynchronize(c->stream));
+        cache[g->sr] = taps;
+    }
+    FirArgs A;
+    A.in = in; A.out = out; A.taps = taps; A.n = g->n; A.stride = g->stride; A.K = K; A.center = (K - 1) / 2; A.clip = 1;
+    const size_t smem = (size_t)(K + kFirTile + K + 8 + 8) * sizeof(float);
+    static bool attr = false;
+    if (!attr) {
+        MM_CUDA(cudaFuncSetAttribute(fir_same_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr = true;
+    }
+    dim3 grid((unsigned)((g->n + kFirTile - 1) / kFirTile), (unsigned)(g->tracks * g->channels));
+    KernelScope ks(c, "target_curve_linear_phase_fir4096");
+    fir_same_kernel<<<grid, kFirThreads, smem, c->stream>>>(A);
     MM_CUDA(cudaGetLastError());
     return 0;
 }

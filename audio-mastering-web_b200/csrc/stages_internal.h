@@ -71,6 +71,7 @@ int st_exciter(mm_ctx* c, const mm_geom* g, const float* in, float* out, double 
 // _split_bands (pipeline.py:333-364): the four zero-phase bands of every row, left in workspace buffers (bands[0..3])
 int st_split_bands(mm_ctx* c, const mm_geom* g, const float* in, const double* cross_hz, float** bands);
 // followers.cu
+int st_target_curve_linear_phase(mm_ctx* c, const mm_geom* g, const float* in, float* out);
 int st_imager4(mm_ctx* c, const mm_geom* g, const float* in, float* out, const double* widths, const double* crossovers_hz);
 int st_transient_designer(mm_ctx* c, const mm_geom* g, const float* in, float* out, double attack_gain, double sustain_gain);
 int st_maximizer_transient_aware(mm_ctx* c, const mm_geom* g, const float* in, float* out, double sensitivity);

@@ -9,7 +9,7 @@ modules/equalizer.py:83-85), and the result is clipped to +-1 with nan_to_num (c
 The audio is uploaded once, every module is a CUDA stage call on the device-resident batch, and the
 result is downloaded once.  When the configuration is exactly ``default_config(target, style)`` the
 whole chain runs as the fused sweep plan (``mm_dev_master``), which is what ``bench.py`` times.
-Second-wave modules (reverb, linear-phase EQ) raise
+Second-wave modules (reverb) raise
 ``NotImplementedError`` when enabled instead of silently passing audio through.
 """
 from __future__ import annotations
@@ -97,9 +97,9 @@ class TargetCurveModule(BaseModule):
         self.phase_mode, self.eq_ms = str(phase_mode), bool(eq_ms)
 
     def _process(self, eng, b, **kw):
-        if kw.get("phase_mode", self.phase_mode) == "linear_phase":
-            raise NotImplementedError("linear-phase target curve is second-wave scope (SURVEY 8f)")
         ms = bool(kw.get("eq_ms", self.eq_ms)) and b.channels == 2
+        if kw.get("phase_mode", self.phase_mode) == "linear_phase":
+            return eng.stage("apply_target_curve_linear_phase", b, 1 if ms else 0)
         return eng.stage("apply_target_curve", b, 1 if ms else 0)
 
 

@@ -87,12 +87,19 @@ def apply_output_edge_fade_in(audio: np.ndarray, sr: int, fade_ms: float = 6.0) 
 
 
 def apply_target_curve(audio: np.ndarray, sr: int, phase_mode: str = "minimum", eq_ms: bool = False) -> np.ndarray:
-    """backend/app/pipeline.py:238-273 (IIR path; the linear-phase FFT variant :220-235 is second-wave)."""
-    if phase_mode == "linear_phase":
-        raise NotImplementedError("linear-phase target curve is second-wave scope (SURVEY 8f)")
+    """backend/app/pipeline.py:238-273: zero-phase IIR path, or ``phase_mode="linear_phase"`` (:187-235, 4096-tap FIR)."""
     a = np.asarray(audio)
     ms = bool(eq_ms) and a.ndim == 2 and a.shape[1] == 2
+    if phase_mode == "linear_phase":
+        return _stage("apply_target_curve_linear_phase", audio, sr, 1 if ms else 0)
     return _stage("apply_target_curve", audio, sr, 1 if ms else 0)
+
+
+def apply_target_curve_linear_phase(audio: np.ndarray, sr: int, n_fft: int = 4096) -> np.ndarray:
+    """backend/app/pipeline.py:220-235."""
+    if n_fft != 4096:
+        raise NotImplementedError("the linear-phase target curve is built for the reference's n_fft = 4096")
+    return _stage("apply_target_curve_linear_phase", audio, sr, 0)
 
 
 def apply_deesser(audio: np.ndarray, sr: int, threshold_db: float = -6.0, ratio: float = 3.0, freq_lo: float = 5000.0,

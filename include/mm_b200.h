@@ -96,6 +96,8 @@ int mm_dev_fade_in(mm_ctx*, const mm_geom*, const float* in, float* out, double 
 int mm_dev_blend(mm_ctx*, const mm_geom*, const float* dry, float* out, const float* processed, double amount);
 /* apply_target_curve (IIR, minimum)    backend/app/pipeline.py:238-273; eq_ms -> :248-255 */
 int mm_dev_apply_target_curve(mm_ctx*, const mm_geom*, const float* in, float* out, int eq_ms);
+/* apply_target_curve(phase_mode="linear_phase") = apply_target_curve_linear_phase, backend/app/pipeline.py:187-235 */
+int mm_dev_apply_target_curve_linear_phase(mm_ctx*, const mm_geom*, const float* in, float* out, int eq_ms);
 /* apply_deesser                        backend/app/pipeline.py:1200-1264 */
 int mm_dev_apply_deesser(mm_ctx*, const mm_geom*, const float* in, float* out,
                          double threshold_db, double ratio, double freq_lo, double freq_hi,
@@ -237,6 +239,8 @@ int64_t mm_master_workspace_bytes(const mm_geom*, int chain);
 /* wn: 1 value (low/high) or 2 (band), normalised to Nyquist. b,a receive ncoef = order+1
  * (low/high) or 2*order+1 (band) values. Returns ncoef, or <0 on error. */
 int mm_design_butter(int order, int btype, const double* wn, double* b, double* a);
+/* _build_linear_phase_ir (backend/app/pipeline.py:187-217): ir[n_fft] float32 */
+int mm_design_linear_phase_ir(int sr, int n_fft, float* ir);
 int mm_design_lfilter_zi(const double* b, const double* a, int ncoef, double* zi);
 /* pyloudnorm K-weighting stage (0 = high shelf, 1 = high pass) for a sample rate; b[3], a[3]
  * (call sites backend/app/pipeline.py:646-648). */

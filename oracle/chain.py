@@ -566,6 +566,33 @@ def apply_stereo_imager_4band(audio, sr, band_widths, crossovers_hz=None, delay_
     return np.column_stack([out_l, out_r]).astype(np.float32)
 
 
+def build_linear_phase_ir(sr, n_fft=4096):
+    """_build_linear_phase_ir (pipeline.py:187-217)."""
+    (b_hp, a_hp), (b_lp, a_lp), (b_pres, a_pres), (b_mud, a_mud), g_presence, g_mud = target_curve_designs(sr)
+    w = np.pi * np.arange(n_fft // 2 + 1) / (n_fft // 2)
+    H = sg.freqz(b_hp, a_hp, worN=w)[1] * sg.freqz(b_lp, a_lp, worN=w)[1] * (
+        1.0 + (g_presence - 1.0) * sg.freqz(b_pres, a_pres, worN=w)[1] + (g_mud - 1.0) * sg.freqz(b_mud, a_mud, worN=w)[1])
+    mag = np.clip(np.abs(H), 1e-8, 1e8)
+    N = n_fft
+    phase = -2.0 * np.pi * np.arange(N // 2 + 1, dtype=np.float64) * (N - 1) / (2.0 * N)
+    full = np.zeros(N, dtype=np.complex128)
+    full[: N // 2 + 1] = mag * np.exp(1j * phase)
+    for k in range(1, N // 2):
+        full[N - k] = np.conj(full[k])
+    full[N // 2] = np.real(full[N // 2])
+    return np.ascontiguousarray(np.fft.ifft(full).real.astype(np.float32))
+
+
+def apply_target_curve_linear_phase(audio, sr, n_fft=4096):
+    """pipeline.py:220-235: fftconvolve(x, ir, mode="same") per channel, clip."""
+    a, mono = _cols(audio)
+    ir = build_linear_phase_ir(sr, n_fft)
+    out = np.zeros_like(a, dtype=np.float32)
+    for ch in range(a.shape[1]):
+        out[:, ch] = sg.fftconvolve(a[:, ch], ir, mode="same")
+    return _uncols(np.clip(out, -1.0, 1.0).astype(np.float32), mono)
+
+
 def _finalize(a):
     out = np.ascontiguousarray(np.clip(a, -1.0, 1.0).astype(np.float32))
     np.nan_to_num(out, copy=False, nan=0.0, posinf=1.0, neginf=-1.0)

@@ -43,6 +43,9 @@ def main():
         "imager4": P.apply_stereo_imager(loud, 1.0, sr=sr, band_widths=(0.8, 1.0, 1.3, 1.6)),
         "imager4_haas": P.apply_stereo_imager(x, 1.0, stereoize_delay_ms=6.0, stereoize_mix=0.2, sr=sr, band_widths=(1.0, 1.2, 1.4, 0.9),
                                               crossovers_hz=(214.0, 2230.0, 10000.0)),
+        "linear_phase": P.apply_target_curve(loud, sr, phase_mode="linear_phase"),
+        "linear_phase_ms": P.apply_target_curve(x, sr, phase_mode="linear_phase", eq_ms=True),
+        "linear_phase_mono_short": P.apply_target_curve_linear_phase(np.ascontiguousarray(loud[:3000, 0]), sr),
         "haas_loud": P.apply_stereo_imager(loud, 1.0, stereoize_delay_ms=12.0, stereoize_mix=0.3, sr=sr),
     }
     st = {k: (np.asarray(v, dtype=np.float32) if isinstance(v, np.ndarray) else v) for k, v in st.items()}

@@ -83,6 +83,8 @@ def test_pro_stages_match_reference_golden():
         "hf_trim_custom": oc.apply_high_freq_trim(x, sr, 3000.0, 0.8),
         "haas": oc.apply_stereoize(x, sr, 1.2, 8.0, 0.12),
         "haas_loud": oc.apply_stereoize(loud, sr, 1.0, 12.0, 0.3),
+        "linear_phase": oc.apply_target_curve_linear_phase(loud, sr),
+        "linear_phase_mono_short": oc.apply_target_curve_linear_phase(np.ascontiguousarray(loud[:3000, 0]), sr),
         "imager4": oc.apply_stereo_imager_4band(loud, sr, (0.8, 1.0, 1.3, 1.6)),
         "imager4_haas": oc.apply_stereo_imager_4band(x, sr, (1.0, 1.2, 1.4, 0.9), (214.0, 2230.0, 10000.0), 6.0, 0.2),
     }
