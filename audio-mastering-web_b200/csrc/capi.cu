@@ -796,6 +796,14 @@ int mm_dev_stereo_correlation(mm_ctx* c, const mm_geom* g, const float* in, doub
     return st_correlation(c, g, in, corr, peak);
 }
 
+// mastering_trace.signal_metrics on the device (trace hook): out[tracks][3] = peak over finite samples,
+// non-finite count, infinity count
+int mm_dev_signal_metrics(mm_ctx* c, const mm_geom* g, const float* in, double* out3) {
+    MM_API_BEGIN(c);
+    MM_TRY(check_geom(g));
+    return run_signal_metrics(c, g, in, out3);
+}
+
 // ---- chains ---------------------------------------------------------------------------------------
 int mm_dev_master(mm_ctx* c, const mm_geom* g, int chain, const mm_style* styles, const float* in, float* out,
                   int16_t* pcm, const float* noise, uint64_t seed, mm_track_stats* stats_dev, uint32_t flags) {

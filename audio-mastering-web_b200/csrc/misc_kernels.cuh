@@ -447,6 +447,35 @@ __global__ void __launch_bounds__(kPwThreads) white_noise_kernel(const WhiteArgs
     }
 }
 
+// mastering_trace.signal_metrics (backend/app/mastering_trace.py:115-149): per track, max |x| over the finite samples,
+// count of non-finite samples, count of infinities.  out[track * 3 + {0, 1, 2}] (doubles, zeroed by the host).
+__global__ void __launch_bounds__(kPwThreads) signal_metrics_kernel(const float* __restrict__ in, long long n, long long stride,
+                                                                    int channels, double* __restrict__ out) {
+    const int row = blockIdx.y;
+    const float* src = in + (size_t)row * (size_t)stride + kLead;
+    float pk = 0.f;
+    double bad = 0.0, inf = 0.0;
+    for (long long i = (long long)blockIdx.x * kPwThreads + threadIdx.x; i < n; i += (long long)gridDim.x * kPwThreads) {
+        const float v = src[i];
+        const float a = fabsf(v);
+        if (a <= 3.4028235e38f) pk = fmaxf(pk, a);
+        else { bad += 1.0; if (a == a) inf += 1.0; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        pk = fmaxf(pk, __shfl_xor_sync(0xffffffffu, pk, o));
+        bad += shfl_xor_d(bad, o);
+        inf += shfl_xor_d(inf, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        double* o = out + (size_t)(row / channels) * 3;
+        // |x| max as double bits is monotone for non-negative values: 64-bit atomicMax on the bit pattern
+        atomicMax(reinterpret_cast<unsigned long long*>(o), (unsigned long long)__double_as_longlong((double)pk));
+        if (bad > 0.0) atomicAdd(o + 1, bad);
+        if (inf > 0.0) atomicAdd(o + 2, inf);
+    }
+}
+
 // ---- layout conversion ------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kPwThreads) deinterleave_kernel(const float* __restrict__ il, float* __restrict__ pl,
                                                                   long long n, long long stride, int channels) {

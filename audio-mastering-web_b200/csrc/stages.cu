@@ -455,6 +455,16 @@ int run_layout_pcm16(mm_ctx* c, const mm_geom* g, const int16_t* interleaved, fl
     return 0;
 }
 
+int run_signal_metrics(mm_ctx* c, const mm_geom* g, const float* in, double* out3) {
+    MM_CUDA(cudaMemsetAsync(out3, 0, (size_t)g->tracks * 3 * sizeof(double), c->stream));
+    const unsigned gx = (unsigned)std::min<long long>((g->n + kPwThreads - 1) / kPwThreads, 1024);
+    dim3 grid(gx, (unsigned)(g->tracks * g->channels));
+    KernelScope ks(c, "trace_signal_metrics");
+    signal_metrics_kernel<<<grid, kPwThreads, 0, c->stream>>>(in, g->n, g->stride, g->channels, out3);
+    MM_CUDA(cudaGetLastError());
+    return 0;
+}
+
 int run_white_noise(mm_ctx* c, const WhiteArgs& W) {
     dim3 grid((unsigned)((W.n + kPwThreads - 1) / kPwThreads), (unsigned)W.tracks);
     KernelScope ks(c, "dither_white_noise");

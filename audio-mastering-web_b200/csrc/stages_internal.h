@@ -49,6 +49,7 @@ struct FinalArgs;
 int run_finalize(mm_ctx* c, const mm_geom* g, const float* in, float* out, const double* mul, const double* width, int n_fade,
                  int16_t* pcm, const float* noise, unsigned long long seed, double* nonfinite);
 int run_quantize(mm_ctx* c, const QuantArgs& Q);
+int run_signal_metrics(mm_ctx* c, const mm_geom* g, const float* in, double* out3);
 int run_white_noise(mm_ctx* c, const WhiteArgs& W);
 // dir 0: interleaved -> planar, 1: planar -> interleaved
 int run_layout(mm_ctx* c, const mm_geom* g, const float* interleaved, float* planar, int dir);

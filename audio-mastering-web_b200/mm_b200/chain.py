@@ -275,7 +275,9 @@ class MasteringChain:
     def process(self, audio: np.ndarray, sr: int, *, target_lufs: Optional[float] = None, style: Optional[str] = None,
                 progress_callback: Optional[Callable[[int, str], None]] = None, trace_ctx=None, **kwargs: Any) -> np.ndarray:
         total = len(self.modules)
-        plan = self._fused_plan(target_lufs, style) if not kwargs else None
+        from . import mastering_trace as _mt
+        tracing = trace_ctx is not None and _mt.trace_enabled()      # the trace needs the module boundaries: no fusion
+        plan = self._fused_plan(target_lufs, style) if (not kwargs and not tracing) else None
         if plan is not None:
             # the reference reports one progress tick per module (chain.py:80-82); same ticks, fused execution
             if progress_callback:
@@ -293,9 +295,13 @@ class MasteringChain:
                 if style is not None:
                     kw["style"] = style
                 b = mod.process_batch(eng, b, **kw)
+                if tracing:       # chain.py:92: device reduction over the resident batch, no copy
+                    _mt.trace_stage(trace_ctx, getattr(mod, "module_id", "module"), b, sr, eng=eng)
             out = P._down(eng, b, mono)
             out = np.ascontiguousarray(np.clip(out, -1.0, 1.0).astype(np.float32))
             np.nan_to_num(out, copy=False, nan=0.0, posinf=1.0, neginf=-1.0)
+            if tracing:
+                _mt.trace_stage(trace_ctx, "chain_finalize_clip", out, sr)
         if progress_callback:
             progress_callback(98, "Готово")
         return out

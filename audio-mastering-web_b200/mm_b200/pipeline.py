@@ -367,8 +367,11 @@ def run_mastering_pipeline(audio: np.ndarray, sr: int, target_lufs: float = -14.
     if denoise_strength > 0 or reference_audio is not None:
         raise NotImplementedError("spectral denoise / reference match are second-wave scope (SURVEY 8f)")
     style = style if style in STYLE_CONFIGS else "standard"
-    if abs(transient_attack - 1.0) > 0.02 or abs(transient_sustain - 1.0) > 0.02:
-        out = _run_v1_stagewise(audio, sr, target_lufs, style, transient_attack, transient_sustain)
+    from . import mastering_trace as _mt
+    tracing = trace_ctx is not None and _mt.trace_enabled()
+    if tracing or abs(transient_attack - 1.0) > 0.02 or abs(transient_sustain - 1.0) > 0.02:
+        out = _run_v1_stagewise(audio, sr, target_lufs, style, transient_attack, transient_sustain,
+                                trace_ctx=trace_ctx if tracing else None)
     else:
         out = master_batch([audio], sr, [style], [target_lufs], chain="v1")["audio"][0]
     if progress_callback is not None:      # stage boundaries are fused on the device; report them in order
@@ -377,28 +380,38 @@ def run_mastering_pipeline(audio: np.ndarray, sr: int, target_lufs: float = -14.
     return out
 
 
-def _run_v1_stagewise(audio, sr, target_lufs, style, transient_attack, transient_sustain):
-    """run_mastering_pipeline stage by stage (pipeline.py:1833-1909), for the options the fused chain does not carry."""
+def _run_v1_stagewise(audio, sr, target_lufs, style, transient_attack, transient_sustain, trace_ctx=None):
+    """run_mastering_pipeline stage by stage (pipeline.py:1833-1909), for the options the fused chain does not carry:
+    the transient designer, and the per-stage trace (mastering_trace.trace_stage after every stage, same stage names)."""
+    from .mastering_trace import trace_stage
     cfg = STYLE_CONFIGS[style]
-    a = remove_dc_offset(audio)
-    a = remove_intersample_peaks(a, headroom_db=0.5)
-    a = apply_target_curve(a, sr)
-    a = apply_deesser(a, sr)
-    a = apply_dynamics(a, sr)
+
+    def tr(name, a, **extra):
+        trace_stage(trace_ctx, name, a, sr, **extra)
+        return a
+
+    a = tr("dc_offset", remove_dc_offset(audio))
+    a = tr("peak_guard_in", remove_intersample_peaks(a, headroom_db=0.5))
+    a = tr("target_eq", apply_target_curve(a, sr))
+    a = tr("deesser", apply_deesser(a, sr))
+    a = tr("dynamics", apply_dynamics(a, sr))
     if cfg.get("parallel_mix", 0.0) > 0.01:
-        a = apply_parallel_compression(a, sr, mix=cfg["parallel_mix"])
-    a = normalize_lufs(a, sr, target_lufs)
-    a = apply_final_spectral_balance(a, sr)
-    a = apply_style_eq(a, sr, style)
-    a = apply_transient_designer(a, sr, attack_gain=transient_attack, sustain_gain=transient_sustain)
+        a = tr("parallel_compress", apply_parallel_compression(a, sr, mix=cfg["parallel_mix"]), parallel_mix=cfg["parallel_mix"])
+    a = tr("normalize_lufs", normalize_lufs(a, sr, target_lufs), target_lufs=target_lufs)
+    a = tr("final_spectral_balance", apply_final_spectral_balance(a, sr))
+    a = tr("style_eq", apply_style_eq(a, sr, style), style=style)
+    if abs(transient_attack - 1.0) > 0.02 or abs(transient_sustain - 1.0) > 0.02:
+        a = tr("transient_designer", apply_transient_designer(a, sr, attack_gain=transient_attack, sustain_gain=transient_sustain),
+               transient_attack=transient_attack, transient_sustain=transient_sustain)
     if cfg.get("exciter_db", 0.0) > 0.05:
-        a = apply_harmonic_exciter(a, sr, cfg["exciter_db"])
+        a = tr("harmonic_exciter", apply_harmonic_exciter(a, sr, cfg["exciter_db"]), exciter_db=cfg["exciter_db"])
     if abs(cfg.get("imager_width", 1.0) - 1.0) > 0.01:
-        a = apply_stereo_imager(a, cfg["imager_width"])
-    a = remove_intersample_peaks(a, headroom_db=0.5)
-    a = apply_output_edge_fade_in(a, sr, fade_ms=6.0)
+        a = tr("stereo_imager", apply_stereo_imager(a, cfg["imager_width"]), imager_width=cfg["imager_width"])
+    a = tr("peak_guard_out", remove_intersample_peaks(a, headroom_db=0.5))
+    a = tr("output_fade_in", apply_output_edge_fade_in(a, sr, fade_ms=6.0))
     a = np.clip(a, -1.0, 1.0).astype(np.float32)
-    return np.nan_to_num(a, nan=0.0, posinf=1.0, neginf=-1.0)
+    a = np.nan_to_num(a, nan=0.0, posinf=1.0, neginf=-1.0)
+    return tr("finalize_clip", a)
 
 
 def export_audio(samples: np.ndarray, sr: int, channels: int, out_format: str = "wav", dither_type: str = "tpdf",

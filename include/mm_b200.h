@@ -168,6 +168,10 @@ int mm_dev_spectrum_bars(mm_ctx*, const mm_geom*, const float* in, int view, dou
  * (NaN encodes the reference's None), plus sample peak per track (double[tracks], may be NULL) */
 int mm_dev_stereo_correlation(mm_ctx*, const mm_geom*, const float* in, double* corr_dev, double* sample_peak_dev);
 
+/* mastering_trace.signal_metrics (backend/app/mastering_trace.py:115-149) as a device reduction: out3_dev[tracks][3] =
+ * max |x| over the finite samples, count of non-finite samples, count of infinities. */
+int mm_dev_signal_metrics(mm_ctx*, const mm_geom*, const float* in, double* out3_dev);
+
 /* ---- whole chains (fused sweep plan; what bench.py times) ------------------------------------*/
 #define MM_CHAIN_V1 1   /* run_mastering_pipeline            backend/app/pipeline.py:1800-1909 */
 #define MM_CHAIN_V2 2   /* MasteringChain.default_chain(...).process + job fade-in

@@ -166,3 +166,36 @@ def test_v2_chain_on_seeded_noise_is_finite_with_moderate_highs(gpu_lib):   # te
         hf_out = np.sqrt(np.mean(sg.lfilter(b, a, out[s].astype(np.float64)) ** 2))
         assert hf_out / (hf_in + 1e-12) < 80.0
         assert np.max(np.abs(np.diff(out[s].astype(np.float64)))) < 1.5
+
+
+def test_mastering_trace_lines(P, stereo, monkeypatch, caplog):              # test_mastering_trace.py:17-52
+    """With MAGIC_MASTER_MASTERING_TRACE on, every stage logs a `mastering_trace` line carrying the job id, the stage name
+    and the device-computed metrics; without it nothing is logged and the fused path runs."""
+    import logging
+    from mm_b200.chain import MasteringChain
+    from mm_b200.mastering_trace import TraceContext, batch_metrics
+    ctx = TraceContext(job_id="job-42", filename="../some dir/My Song (final).wav", path="v1")
+    caplog.set_level(logging.INFO, logger="magic_master.mastering_trace")
+    monkeypatch.delenv("MAGIC_MASTER_MASTERING_TRACE", raising=False)
+    quiet = P.run_mastering_pipeline(stereo, SR, trace_ctx=ctx)
+    assert not [r for r in caplog.records if "mastering_trace" in r.getMessage()]
+    monkeypatch.setenv("MAGIC_MASTER_MASTERING_TRACE", "1")
+    monkeypatch.setenv("MAGIC_MASTER_MASTERING_TRACE_LUFS_STAGES", "1")
+    traced = P.run_mastering_pipeline(stereo, SR, trace_ctx=ctx)
+    lines = [r.getMessage() for r in caplog.records if "mastering_trace" in r.getMessage()]
+    stages = [ln.split("stage=")[1].split()[0] for ln in lines]
+    assert stages[:3] == ["dc_offset", "peak_guard_in", "target_eq"] and stages[-1] == "finalize_clip" and "normalize_lufs" in stages
+    assert all("job_id=job-42" in ln and "filename=My_Song_final_.wav" in ln and "peak_db=" in ln and "nan_count=0" in ln for ln in lines)
+    assert any("lufs=" in ln for ln in lines)
+    assert np.max(np.abs(traced.astype(np.float64) - quiet)) <= 2e-6        # stage-by-stage == fused (float32 hand-offs aside)
+    caplog.clear()
+    MasteringChain.default_chain(target_lufs=-14.0, style="standard").process(stereo, SR, target_lufs=-14.0, style="standard",
+                                                                            trace_ctx=TraceContext("job-43", "a.wav", "v2"))
+    v2 = [r.getMessage().split("stage=")[1].split()[0] for r in caplog.records if "mastering_trace" in r.getMessage()]
+    assert v2[0] == "dc_offset" and v2[-1] == "chain_finalize_clip" and "dynamics" in v2
+    # the metrics kernel itself: NaN / Inf are counted, the peak ignores them
+    bad = stereo.copy()
+    bad[10, 0], bad[11, 1], bad[12, 0] = np.nan, np.inf, -np.inf
+    eng, b, _ = P._up(bad, SR)
+    m = batch_metrics(eng, b)[0]
+    assert m["nan_count"] == 3 and m["inf_count"] == 2 and abs(m["peak_linear"] - round(float(np.max(np.abs(stereo))), 6)) < 2e-6
