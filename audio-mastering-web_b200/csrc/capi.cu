@@ -682,6 +682,13 @@ int mm_dev_apply_high_freq_trim(mm_ctx* c, const mm_geom* g, const float* in, fl
     return st_filtfilt_combine(c, g, p, in, out, e, none);
 }
 
+int mm_dev_apply_reverb(mm_ctx* c, const mm_geom* g, const float* in, float* out, int reverb_type, double decay_sec, double mix,
+                        int use_ms, double mix_mid, double mix_side) {
+    MM_API_BEGIN(c);
+    MM_TRY(check_geom(g));
+    return st_reverb(c, g, in, out, reverb_type, decay_sec, mix, use_ms, mix_mid, mix_side);
+}
+
 int mm_dev_apply_stereo_imager_4band(mm_ctx* c, const mm_geom* g, const float* in, float* out, const double* band_widths,
                                      const double* crossovers_hz) {
     MM_API_BEGIN(c);

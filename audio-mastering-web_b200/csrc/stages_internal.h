@@ -71,6 +71,9 @@ int st_exciter(mm_ctx* c, const mm_geom* g, const float* in, float* out, double 
 
 // _split_bands (pipeline.py:333-364): the four zero-phase bands of every row, left in workspace buffers (bands[0..3])
 int st_split_bands(mm_ctx* c, const mm_geom* g, const float* in, const double* cross_hz, float** bands);
+// reverb.cu: type 0 plate, 1 room, 2 hall, 3 theater, 4 cathedral (in == out allowed)
+int st_reverb(mm_ctx* c, const mm_geom* g, const float* in, float* out, int type, double decay_sec, double mix, int use_ms,
+              double mix_mid, double mix_side);
 // followers.cu
 int st_target_curve_linear_phase(mm_ctx* c, const mm_geom* g, const float* in, float* out);
 int st_imager4(mm_ctx* c, const mm_geom* g, const float* in, float* out, const double* widths, const double* crossovers_hz);

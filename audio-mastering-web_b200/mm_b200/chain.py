@@ -9,7 +9,7 @@ modules/equalizer.py:83-85), and the result is clipped to +-1 with nan_to_num (c
 The audio is uploaded once, every module is a CUDA stage call on the device-resident batch, and the
 result is downloaded once.  When the configuration is exactly ``default_config(target, style)`` the
 whole chain runs as the fused sweep plan (``mm_dev_master``), which is what ``bench.py`` times.
-Second-wave modules (reverb) raise
+Second-wave options without a kernel yet (oversampled exciter) raise
 ``NotImplementedError`` when enabled instead of silently passing audio through.
 """
 from __future__ import annotations
@@ -197,11 +197,16 @@ class ImagerModule(BaseModule):
 class ReverbModule(BaseModule):
     module_id = "reverb"
 
-    def __init__(self, enabled=False, amount=1.0, **kwargs):
+    def __init__(self, enabled=False, amount=1.0, reverb_type="plate", decay_sec=1.2, mix=0.15, mix_mid=None, mix_side=None, **kwargs):
         super().__init__(enabled=enabled, amount=amount, **kwargs)
+        self.reverb_type, self.decay_sec, self.mix = str(reverb_type), float(decay_sec), float(mix)
+        self.mix_mid = float(mix_mid) if mix_mid is not None else None
+        self.mix_side = float(mix_side) if mix_side is not None else None
 
-    def _process(self, eng, b, **kw):
-        raise NotImplementedError("apply_reverb is second-wave scope (SURVEY 8f); it is disabled in the default chain")
+    def _process(self, eng, b, **kw):      # modules/reverb.py -> pipeline.py:1119-1176
+        use_ms = b.channels == 2 and (self.mix_mid is not None or self.mix_side is not None)
+        return eng.stage("apply_reverb", b, P._REVERB_TYPES.get(self.reverb_type, 0), _d(self.decay_sec), _d(self.mix), 1 if use_ms else 0,
+                         _d(self.mix_mid if self.mix_mid is not None else self.mix), _d(self.mix_side if self.mix_side is not None else self.mix))
 
 
 MODULE_REGISTRY = {m.module_id: m for m in (

@@ -215,6 +215,20 @@ def apply_high_freq_trim(audio: np.ndarray, sr: int, crossover_hz: float = HIGH_
     return _stage("apply_high_freq_trim", audio, sr, C.c_double(crossover_hz), C.c_double(high_gain))
 
 
+_REVERB_TYPES = {"plate": 0, "room": 1, "hall": 2, "theater": 3, "cathedral": 4}
+
+
+def apply_reverb(audio: np.ndarray, sr: int, reverb_type: str = "plate", decay_sec: float = 1.2, mix: float = 0.15,
+                 mix_mid: Optional[float] = None, mix_side: Optional[float] = None) -> np.ndarray:
+    """backend/app/pipeline.py:1119-1176 (Schroeder comb + allpass; optional separate mid / side mixes)."""
+    a = np.asarray(audio)
+    use_ms = a.ndim == 2 and a.shape[1] == 2 and (mix_mid is not None or mix_side is not None)
+    m_mid = float(mix_mid) if mix_mid is not None else float(mix)
+    m_side = float(mix_side) if mix_side is not None else float(mix)
+    return _stage("apply_reverb", audio, sr, _REVERB_TYPES.get(reverb_type, 0), C.c_double(float(decay_sec)), C.c_double(float(mix)),
+                  1 if use_ms else 0, C.c_double(m_mid), C.c_double(m_side))
+
+
 def apply_rumble_filter(audio: np.ndarray, sr: int, cutoff_hz: float = 80.0) -> np.ndarray:
     """backend/app/pipeline.py:1449-1469."""
     return _stage("apply_rumble_filter", audio, sr, C.c_double(cutoff_hz))

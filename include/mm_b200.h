@@ -140,6 +140,10 @@ int mm_dev_apply_stereoize(mm_ctx*, const mm_geom*, const float* in, float* out,
  * crossovers_hz NULL -> MULTIBAND_CROSSOVERS_HZ (214, 3500, 10000) */
 int mm_dev_apply_stereo_imager_4band(mm_ctx*, const mm_geom*, const float* in, float* out, const double* band_widths /*4*/,
                                      const double* crossovers_hz /*3 or NULL*/);
+/* apply_reverb (Schroeder comb + allpass), backend/app/pipeline.py:1055-1176.  reverb_type: 0 plate, 1 room, 2 hall,
+ * 3 theater, 4 cathedral; decay_sec <= 0 -> the preset's; use_ms != 0 (stereo only): separate mixes on mid and side. */
+int mm_dev_apply_reverb(mm_ctx*, const mm_geom*, const float* in, float* out, int reverb_type, double decay_sec, double mix,
+                        int use_ms, double mix_mid, double mix_side);
 /* generic zero-phase / causal IIR on every row: scipy filtfilt / lfilter semantics of
  * _safe_filtfilt (backend/app/pipeline.py:36-52). nb == na in {3, 5}; zero_phase 0 -> lfilter. */
 int mm_dev_iir(mm_ctx*, const mm_geom*, const float* in, float* out,

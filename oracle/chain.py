@@ -593,6 +593,75 @@ def apply_target_curve_linear_phase(audio, sr, n_fft=4096):
     return _uncols(np.clip(out, -1.0, 1.0).astype(np.float32), mono)
 
 
+_REVERB_PRESETS = {
+    "plate": (1.2, [29, 37, 41, 53], [0.7, 0.65, 0.6, 0.55], [5, 7], [0.5, 0.4]),
+    "room": (0.6, [23, 31, 43, 47], [0.5, 0.45, 0.4, 0.35], [3, 5], [0.4, 0.3]),
+    "hall": (2.2, [47, 53, 61, 71], [0.75, 0.7, 0.65, 0.6], [8, 11], [0.5, 0.45]),
+    "theater": (3.5, [59, 67, 73, 83], [0.78, 0.73, 0.68, 0.63], [10, 14], [0.52, 0.45]),
+    "cathedral": (5.0, [97, 103, 109, 127], [0.82, 0.78, 0.74, 0.7], [15, 19], [0.55, 0.48]),
+}
+
+
+def _comb(x, d, g):
+    """y[n] = x[n] + g y[n - d] (pipeline.py:1065-1078) = lfilter([1], [1, 0, ..., -g])."""
+    if d <= 0 or d >= len(x):
+        return x
+    a = np.zeros(d + 1)
+    a[0], a[d] = 1.0, -g
+    return sg.lfilter([1.0], a, x)
+
+
+def _allpass(x, d, g):
+    """y[n] = -g x[n] + x[n - d] + g y[n - d] (pipeline.py:1082-1094)."""
+    if d <= 0 or d >= len(x):
+        return x
+    b = np.zeros(d + 1)
+    a = np.zeros(d + 1)
+    b[0], b[d] = -g, 1.0
+    a[0], a[d] = 1.0, -g
+    return sg.lfilter(b, a, x)
+
+
+def _reverb_mono(x, sr, reverb_type, decay_sec, mix):
+    preset = _REVERB_PRESETS.get(reverb_type, _REVERB_PRESETS["plate"])
+    decay = decay_sec if decay_sec > 0 else preset[0]
+    dps = 0.001 ** (1.0 / max(0.1, decay))
+    n = len(x)
+    x = np.asarray(x, dtype=np.float64)
+    wet = np.zeros(n)
+    for d_ms, g in zip(preset[1], preset[2]):
+        d = min(int(sr * d_ms / 1000.0), n - 1)
+        if d < 1:
+            continue
+        wet += _comb(x, d, g * (dps ** (d_ms / 1000.0)))
+    wet /= max(len(preset[1]), 1)
+    for d_ms, g in zip(preset[3], preset[4]):
+        d = min(int(sr * d_ms / 1000.0), n - 1)
+        if d < 1:
+            continue
+        wet = _allpass(wet, d, g)
+    peak = np.max(np.abs(wet))
+    if peak > 1e-6:
+        wet = wet / min(peak, 2.0)
+    return (x * (1.0 - mix) + wet * mix).astype(np.float32)
+
+
+def apply_reverb(audio, sr, reverb_type="plate", decay_sec=1.2, mix=0.15, mix_mid=None, mix_side=None):
+    """pipeline.py:1119-1176."""
+    a, mono = _cols(audio)
+    if a.shape[1] == 2 and (mix_mid is not None or mix_side is not None):
+        mid = ((a[:, 0] + a[:, 1]) * 0.5).astype(np.float64)
+        side = ((a[:, 0] - a[:, 1]) * 0.5).astype(np.float64)
+        mm = max(0.0, min(1.0, float(mix_mid) if mix_mid is not None else mix))
+        ms = max(0.0, min(1.0, float(mix_side) if mix_side is not None else mix))
+        mo, so = _reverb_mono(mid, sr, reverb_type, decay_sec, mm), _reverb_mono(side, sr, reverb_type, decay_sec, ms)
+        return np.stack([np.clip(mo + so, -1.0, 1.0).astype(np.float32), np.clip(mo - so, -1.0, 1.0).astype(np.float32)], axis=1)
+    out = np.zeros_like(a)
+    for ch in range(a.shape[1]):
+        out[:, ch] = _reverb_mono(a[:, ch].astype(np.float64), sr, reverb_type, decay_sec, mix)
+    return _uncols(np.clip(out, -1.0, 1.0).astype(np.float32), mono)
+
+
 def _finalize(a):
     out = np.ascontiguousarray(np.clip(a, -1.0, 1.0).astype(np.float32))
     np.nan_to_num(out, copy=False, nan=0.0, posinf=1.0, neginf=-1.0)

@@ -46,6 +46,9 @@ def main():
         "linear_phase": P.apply_target_curve(loud, sr, phase_mode="linear_phase"),
         "linear_phase_ms": P.apply_target_curve(x, sr, phase_mode="linear_phase", eq_ms=True),
         "linear_phase_mono_short": P.apply_target_curve_linear_phase(np.ascontiguousarray(loud[:3000, 0]), sr),
+        "reverb_plate": P.apply_reverb(loud, sr, "plate", 1.2, 0.15),
+        "reverb_hall_ms": P.apply_reverb(perc, sr, "hall", 0.0, 0.2, mix_mid=0.1, mix_side=0.35),
+        "reverb_room_mono": P.apply_reverb(np.ascontiguousarray(perc[:, 0]), sr, "room", 0.6, 0.3),
         "haas_loud": P.apply_stereo_imager(loud, 1.0, stereoize_delay_ms=12.0, stereoize_mix=0.3, sr=sr),
     }
     st = {k: (np.asarray(v, dtype=np.float32) if isinstance(v, np.ndarray) else v) for k, v in st.items()}

@@ -221,3 +221,34 @@ def test_linear_phase_target_curve(gpu_lib):
             m["phase_mode"] = "linear_phase"
     out = MasteringChain.from_config(cfg).process(loud, sr, target_lufs=-14.0, style="standard")
     assert out.shape == loud.shape and np.all(np.isfinite(out))
+
+
+def test_reverb_against_reference_golden(gpu_lib):
+    """apply_reverb (pipeline.py:1055-1176): plate on L/R, hall with separate mid / side mixes, room on a mono track, against
+    the reference's own outputs; plus a long row (many steps per phase thread) against the oracle."""
+    from mm_b200 import pipeline as P, synth
+    from mm_b200.chain import MasteringChain
+    from oracle import chain as oc
+    g = load_golden("pro_stages_48k")
+    sr, x, perc = int(g["sr"]), g["input"], g["perc"]
+    loud = (x * np.float32(6.0)).astype(np.float32)
+    got = {
+        "reverb_plate": P.apply_reverb(loud, sr, "plate", 1.2, 0.15),
+        "reverb_hall_ms": P.apply_reverb(perc, sr, "hall", 0.0, 0.2, mix_mid=0.1, mix_side=0.35),
+        "reverb_room_mono": P.apply_reverb(np.ascontiguousarray(perc[:, 0]), sr, "room", 0.6, 0.3),
+    }
+    for k, v in got.items():
+        assert np.shape(v) == g[k].shape and np.asarray(v).dtype == np.float32, k
+        e = float(np.max(np.abs(np.asarray(v, dtype=np.float64) - g[k])))
+        print(f"[parity] {k}: {e:.3e}")
+        assert e <= 2e-6, (k, e)
+    y = synth.numpy_track(5, 44100, 8.0)
+    e = float(np.max(np.abs(P.apply_reverb(y, 44100, "cathedral", 5.0, 0.25).astype(np.float64) - oc.apply_reverb(y, 44100, "cathedral", 5.0, 0.25))))
+    print(f"[parity] reverb cathedral 8 s: {e:.3e}")
+    assert e <= 2e-6
+    cfg = MasteringChain.default_config(target_lufs=-14.0, style="standard")
+    for m in cfg["modules"]:
+        if m["id"] == "reverb":
+            m.update({"enabled": True, "reverb_type": "room", "mix": 0.1})
+    out = MasteringChain.from_config(cfg).process(loud, sr, target_lufs=-14.0, style="standard")
+    assert out.shape == loud.shape and np.all(np.isfinite(out))

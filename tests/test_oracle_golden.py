@@ -85,6 +85,9 @@ def test_pro_stages_match_reference_golden():
         "haas_loud": oc.apply_stereoize(loud, sr, 1.0, 12.0, 0.3),
         "linear_phase": oc.apply_target_curve_linear_phase(loud, sr),
         "linear_phase_mono_short": oc.apply_target_curve_linear_phase(np.ascontiguousarray(loud[:3000, 0]), sr),
+        "reverb_plate": oc.apply_reverb(loud, sr, "plate", 1.2, 0.15),
+        "reverb_hall_ms": oc.apply_reverb(perc, sr, "hall", 0.0, 0.2, mix_mid=0.1, mix_side=0.35),
+        "reverb_room_mono": oc.apply_reverb(np.ascontiguousarray(perc[:, 0]), sr, "room", 0.6, 0.3),
         "imager4": oc.apply_stereo_imager_4band(loud, sr, (0.8, 1.0, 1.3, 1.6)),
         "imager4_haas": oc.apply_stereo_imager_4band(x, sr, (1.0, 1.2, 1.4, 0.9), (214.0, 2230.0, 10000.0), 6.0, 0.2),
     }
