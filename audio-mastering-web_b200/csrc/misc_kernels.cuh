@@ -305,7 +305,7 @@ constexpr int kFinVec = 4;                                   // float4 per threa
 constexpr int kFinFrames = kFinThreads * kFinVec * 4;        // frames per block
 
 template <int C, bool PCM, bool NOISE>
-__global__ void __launch_bounds__(kFinThreads) finalize_kernel(const FinalArgs P) {
+__global__ void __launch_bounds__(kFinThreads, 3) finalize_kernel(const FinalArgs P) {
     const int track = blockIdx.y;
     const long long base = (long long)blockIdx.x * kFinFrames;
     const size_t r0 = (size_t)(track * C) * (size_t)P.stride + kLead;

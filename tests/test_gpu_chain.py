@@ -171,9 +171,13 @@ def test_mastering_chain_api_default_and_custom(P):
     a = oc.remove_intersample_peaks(a, 1.0)
     ref = np.clip(a, -1, 1).astype(np.float32)
     assert _err(got, ref) <= 5e-6
-    # second-wave modules fail loudly instead of passing audio through
+    # options without a kernel fail loudly instead of passing audio through (the reference would swallow the error)
     with pytest.raises(NotImplementedError):
-        mc.MasteringChain.from_config({"modules": [{"id": "reverb", "enabled": True}]}).process(x.copy(), sr)
+        mc.MasteringChain.from_config({"modules": [{"id": "exciter", "enabled": True, "exciter_db": 0.8, "oversample": 2}]}).process(x.copy(), sr)
+    # the reverb module now runs (second wave): enabled, it changes the signal; disabled (the default), it does not
+    wet = mc.MasteringChain.from_config({"modules": [{"id": "reverb", "enabled": True, "mix": 0.2}]}).process(x.copy(), sr)
+    dry = mc.MasteringChain.from_config({"modules": [{"id": "reverb", "enabled": False}]}).process(x.copy(), sr)
+    assert _err(wet, x) > 1e-3 and _err(dry, np.clip(x, -1, 1)) == 0.0
 
 
 def test_master_host_pipelined_chunks_equal_one_shot(P, monkeypatch):
