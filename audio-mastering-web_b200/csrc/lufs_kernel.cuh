@@ -63,13 +63,15 @@ __device__ __forceinline__ void mv4(const float2 (&M)[4][2], const float (&v)[4]
     }
 }
 
-constexpr int kLufsSmem = kL * (int)sizeof(float) + (int)sizeof(LufsTab);
+constexpr int kLufsSmem = 2 * kL * (int)sizeof(float) + (int)sizeof(LufsTab);
 
 __global__ void __launch_bounds__(kT, 6) lufs_kernel(const __grid_constant__ LufsArgs P) {
-    // a float32 staging tile receives the NEXT tile (cp.async) while the current one is scanned
+    // two float32 staging tiles: the NEXT tile lands (cp.async) while the current one is scanned.  Both passes read their
+    // samples from shared memory in rolled loops over float4 groups: the whole kernel stays small enough for the
+    // instruction cache (the fully unrolled register version spent 30 % of its issue slots waiting for instructions)
     extern __shared__ __align__(128) unsigned char lufs_smem[];
-    float* tile_s = reinterpret_cast<float*>(lufs_smem);
-    LufsTab* tab = reinterpret_cast<LufsTab*>(lufs_smem + kL * sizeof(float));
+    float* tiles = reinterpret_cast<float*>(lufs_smem);
+    LufsTab* tab = reinterpret_cast<LufsTab*>(lufs_smem + 2 * kL * sizeof(float));
     __shared__ LufsScratch sh;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (int i = tid; i < 32 * 16; i += kT) tab->PlaneT[i % 16][i / 16] = (float)__ldg(P.tab + Tab<4>::Plane + i);
@@ -82,16 +84,11 @@ __global__ void __launch_bounds__(kT, 6) lufs_kernel(const __grid_constant__ Luf
         const int t_end = min(P.ntiles, t_live + P.seglen);
         const int t_first = max(0, t_live - P.whalo);
         const float* src = P.in + (size_t)row * (size_t)P.stride;
-        float subf = 0.f, mulf = 1.f;
-        double muld = 1.0;
-        if (P.pro_mode != PRO_NONE) {
-            if (P.pro_sub) subf = (float)__ldg(P.pro_sub + row);
-            if (P.pro_mul) { muld = __ldg(P.pro_mul + row); mulf = (float)muld; }
-        }
         __syncthreads();
         if (tid == 0) sh.carry[t_first & 1] = make_float4(0.f, 0.f, 0.f, 0.f);
         unsigned long long* dst = P.segsum + (size_t)row * (size_t)P.nhop;
-        auto load_tile = [&](int t) {
+        auto load_tile = [&](int t, int slot) {
+            float* tile_s = tiles + (size_t)slot * kL;
             const long long lo = (long long)t * kL;
             if (lo >= kLead && lo + kL <= kLead + P.n) {
                 const float* s4 = src + lo + 4 * tid;
@@ -112,40 +109,29 @@ __global__ void __launch_bounds__(kT, 6) lufs_kernel(const __grid_constant__ Luf
             }
             cp_async_commit();
         };
-        load_tile(t_first);
+        load_tile(t_first, 0);
 #pragma unroll 1
         for (int tile = t_first; tile < t_end; ++tile) {
             const bool live = tile >= t_live;
             const long long tile_lo = (long long)tile * kL;
-            const bool interior = tile_lo >= kLead && tile_lo + kL <= kLead + P.n;
+            const int slot = (tile - t_first) & 1;
             cp_async_wait<0>();
-            __syncthreads();                               // staged floats of this tile visible; previous tile done
-
-            // this thread's 32 input samples leave shared memory here
-            float xin[32];
-#pragma unroll
-            for (int u = 0; u < kS / 4; ++u) {
-                float4 xv = *reinterpret_cast<const float4*>(tile_s + cbase + ((4 * u) ^ cx));
-                if (P.pro_mode != PRO_NONE) {
-                    const long long q0 = tile_lo + cbase + 4 * u;      // dead positions of edge tiles stay exactly zero
-#pragma unroll
-                    for (int c = 0; c < 4; ++c) {
-                        const bool in_range = interior || (q0 + c >= kLead && q0 + c < kLead + P.n);
-                        if (in_range) setcomp4(xv, c, pro1(P.pro_mode, comp4(xv, c), subf, mulf, muld));
-                    }
-                }
-                xin[4 * u] = xv.x; xin[4 * u + 1] = xv.y; xin[4 * u + 2] = xv.z; xin[4 * u + 3] = xv.w;
-            }
-            __syncthreads();                               // every thread holds its inputs: the staging tile is free
-            if (tile + 1 < t_end) load_tile(tile + 1);     // lands while this tile is scanned
+            __syncthreads();                               // this tile's floats visible; everybody is done with the other slot
+            if (tile + 1 < t_end) load_tile(tile + 1, slot ^ 1);     // lands while this tile is scanned
+            const float* mine = tiles + (size_t)slot * kL + cbase;  // this thread's 32 samples: float4 group u at ((4 u) ^ cx)
 
             // ---- pass 1 (packed float32): zero-state end state of the 4-state cascade over this chunk ----
             float2 E01 = make_float2(0.f, 0.f), E23 = E01;
+#pragma unroll 2
+            for (int u = 0; u < kS / 4; ++u) {
+                const float4 xv = *reinterpret_cast<const float4*>(mine + ((4 * u) ^ cx));
 #pragma unroll
-            for (int j = 0; j < kS; ++j) {
-                const float2 X = make_float2(xin[j], xin[j]);
-                E01 = ffma2(P.k.g[j][0], X, E01);
-                E23 = ffma2(P.k.g[j][1], X, E23);
+                for (int c = 0; c < 4; ++c) {
+                    const float x = comp4(xv, c);
+                    const float2 X = make_float2(x, x);
+                    E01 = ffma2(P.k.g[4 * u + c][0], X, E01);
+                    E23 = ffma2(P.k.g[4 * u + c][1], X, E23);
+                }
             }
             // ---- warp scan, tile Horner, carry update (float32, packed) ----
 #pragma unroll
@@ -211,49 +197,57 @@ __global__ void __launch_bounds__(kT, 6) lufs_kernel(const __grid_constant__ Luf
             const bool whole = (i0 >= P.own_lo) && (i0 + kS <= P.own_hi) && (i0 + kS <= nb1);   // chunk inside the counted range and one hop
             float2 S0 = make_float2(z[0], z[2]);
             float2 S1 = make_float2(z[1], z[3]);
-            // step 0: the shelf alone (lane .y idles on a zero-weight copy of itself)
-            float u_prev;
-            {
-                const float u = fmaf(P.k.C[0].x, S0.x, fmaf(P.k.C[1].x, S1.x, P.k.D.x * xin[0]));
-                const float n0 = fmaf(P.k.A[0][0].x, S0.x, fmaf(P.k.A[0][1].x, S1.x, P.k.B[0].x * xin[0]));
-                const float n1 = fmaf(P.k.A[1][0].x, S0.x, fmaf(P.k.A[1][1].x, S1.x, P.k.B[1].x * xin[0]));
+            // the high-pass lane runs one sample behind the shelf lane: step 0 is the shelf alone, the last output comes
+            // from the high-pass state after the loop
+            float u_prev = 0.f;
+            float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f;
+            auto first_step = [&](float x0) {
+                const float u = fmaf(P.k.C[0].x, S0.x, fmaf(P.k.C[1].x, S1.x, P.k.D.x * x0));
+                const float n0 = fmaf(P.k.A[0][0].x, S0.x, fmaf(P.k.A[0][1].x, S1.x, P.k.B[0].x * x0));
+                const float n1 = fmaf(P.k.A[1][0].x, S0.x, fmaf(P.k.A[1][1].x, S1.x, P.k.B[1].x * x0));
                 S0.x = n0; S1.x = n1;
                 u_prev = u;
-            }
-            float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f;
+            };
             if (__all_sync(0xffffffffu, whole)) {
+#pragma unroll 2
+                for (int u = 0; u < kS / 4; ++u) {
+                    const float4 xv = *reinterpret_cast<const float4*>(mine + ((4 * u) ^ cx));
 #pragma unroll
-                for (int j = 1; j < kS; ++j) {
-                    const float2 Y = pair_step(P.k, make_float2(xin[j], u_prev), S0, S1);   // Y.x = shelf(j), Y.y = K-weighted(j-1)
-                    u_prev = Y.x;
-                    if (j & 1) acc0 = fmaf(Y.y, Y.y, acc0); else acc1 = fmaf(Y.y, Y.y, acc1);
+                    for (int c = 0; c < 4; ++c) {
+                        if (c == 0 && u == 0) { first_step(xv.x); continue; }
+                        const float2 Y = pair_step(P.k, make_float2(comp4(xv, c), u_prev), S0, S1);   // Y.x = shelf(j), Y.y = K-weighted(j-1)
+                        u_prev = Y.x;
+                        if (c & 1) acc0 = fmaf(Y.y, Y.y, acc0); else acc1 = fmaf(Y.y, Y.y, acc1);
+                    }
                 }
                 const float yl = fmaf(P.k.C[0].y, S0.y, fmaf(P.k.C[1].y, S1.y, P.k.D.y * u_prev));
                 acc1 = fmaf(yl, yl, acc1);
                 acc0 += acc1; acc1 = 0.f;
             } else {
-                // chunks cut by hop boundaries (at most two: the host plan guarantees it) or by the row's end:
+                // chunks cut by hop boundaries (at most two: the host plan guarantees it) or by the ends of the counted range:
                 // samples [jlo, j1) -> hop s, [j1, j2) -> hop s+1, [j2, jv) -> hop s+2; the rest is not counted
                 const int jv = (int)max(0LL, min((long long)kS, P.own_hi - i0));
-                const int jlo = (int)max(0LL, min((long long)kS, P.own_lo - i0));       // samples before it are not counted
+                const int jlo = (int)max(0LL, min((long long)kS, P.own_lo - i0));
                 const int j1 = (int)max(0LL, min((long long)jv, nb1 - i0));
                 const int j2 = (int)max((long long)j1, min((long long)jv, nb2 - i0));
-#pragma unroll
-                for (int j = 1; j <= kS; ++j) {
-                    float yk;
-                    if (j < kS) {
-                        const float2 Y = pair_step(P.k, make_float2(xin[j], u_prev), S0, S1);
-                        u_prev = Y.x;
-                        yk = Y.y;
-                    } else {
-                        yk = fmaf(P.k.C[0].y, S0.y, fmaf(P.k.C[1].y, S1.y, P.k.D.y * u_prev));
-                    }
+                auto count = [&](float yk, int js) {       // js: the sample this K-weighted output belongs to
                     const float t = yk * yk;
-                    const int js = j - 1;                  // sample this output belongs to
                     acc0 += (js >= jlo && js < j1) ? t : 0.f;
                     acc1 += (js >= jlo && js >= j1 && js < j2) ? t : 0.f;
                     acc2 += (js >= jlo && js >= j2 && js < jv) ? t : 0.f;
+                };
+#pragma unroll 1
+                for (int u = 0; u < kS / 4; ++u) {
+                    const float4 xv = *reinterpret_cast<const float4*>(mine + ((4 * u) ^ cx));
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        if (c == 0 && u == 0) { first_step(xv.x); continue; }
+                        const float2 Y = pair_step(P.k, make_float2(comp4(xv, c), u_prev), S0, S1);
+                        u_prev = Y.x;
+                        count(Y.y, 4 * u + c - 1);
+                    }
                 }
+                count(fmaf(P.k.C[0].y, S0.y, fmaf(P.k.C[1].y, S1.y, P.k.D.y * u_prev)), kS - 1);
             }
             double accA = 0.0, accB = 0.0;
             auto flush = [&](int hop, float v) {

@@ -681,6 +681,7 @@ int st_split_bands(mm_ctx* c, const mm_geom* g, const float* in, const double* c
 // backend/app/pipeline.py:644-664)
 int st_lufs(mm_ctx* c, const mm_geom* g, const float* in, const Pro& pro, double* lufs_dev, const double* target_dev,
             double* gain_row, double* gain_db) {
+    if (pro.mode != PRO_NONE) { set_error("the loudness kernel takes its input as it is (no fused prologue)"); return 1; }
     const LufsPlan* lp;
     const mm_slice* sl = c->slice;
     if (sl) MM_TRY(get_lufs_plan(c, sl->global_n, g->sr, &lp, sl->global_off, g->n));

@@ -385,14 +385,14 @@ def run_ours(args):
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f64", "data": "synthetic",
+        "dtype": "f64/f32", "data": "synthetic",
         "config": {"workload": (f"configs[2]: {tracks} synthetic {dur:.0f} s {sr} Hz stereo tracks per GPU, genre presets cycling over the "
                                 f"global track index (STYLE_CONFIGS order) at their own LUFS targets, {args.chain} chain + TPDF int16 + after-LUFS"
                                 if mixed else
                                 f"configs[1]: {tracks} synthetic {dur:.0f} s {sr} Hz stereo tracks per GPU, {args.chain} default chain "
                                 f"(style standard, -14 LUFS) + TPDF dither to int16 + after-LUFS"),
                    "chain": args.chain, "tracks_per_gpu": tracks, "frames_per_track": n,
-                   "cache": f"inputs ({tracks * n * 8 / 1e9:.2f} GB per GPU) exceed L2; no flush needed", "storage": "float32 streams, float64 recurrence state"},
+                   "cache": f"inputs ({tracks * n * 8 / 1e9:.2f} GB per GPU) exceed L2; no flush needed", "storage": "float32 streams; float64 chunk scan everywhere; in-chunk recurrences float64 (full-path low cut-offs) or float32 FFMA2 on balanced realizations (DESIGN.md precision policy)"},
         "roofline": roofline, "cpu_baseline": cb, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
         "check": {"lufs_out_mean": float(np.mean(lufs_out)), "lufs_out_min": float(np.min(lufs_out)),
                   "lufs_out_max": float(np.max(lufs_out)), "nonfinite": nonfinite},
