@@ -534,7 +534,7 @@ def run_longform(args):
                    "sample": "20 s of 96 kHz stereo through the oracle (numpy/scipy), v2 chain + TPDF int16"}
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64/f32",
         "data": "synthetic",
         "config": {"workload": f"configs[4]: one {dur:.0f} s {sr} Hz stereo file, {args.chain} default chain + TPDF int16 + after-LUFS, "
                                f"split in time over {world} GPU(s) ({longform.slice_margin(sr)} margin frames per cut side)",
