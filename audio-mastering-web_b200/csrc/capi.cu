@@ -689,6 +689,28 @@ int mm_dev_apply_reverb(mm_ctx* c, const mm_geom* g, const float* in, float* out
     return st_reverb(c, g, in, out, reverb_type, decay_sec, mix, use_ms, mix_mid, mix_side);
 }
 
+int mm_dev_spectral_envelope(mm_ctx* c, const mm_geom* g, const float* in, float* env_dev) {
+    MM_API_BEGIN(c);
+    MM_TRY(check_geom(g));
+    return st_spectral_envelope(c, g, in, env_dev);
+}
+
+int mm_dev_fir_same(mm_ctx* c, const mm_geom* g, const float* in, float* out, const float* taps_host, int ntaps, int clip) {
+    MM_API_BEGIN(c);
+    MM_TRY(check_geom(g));
+    if (!taps_host) { set_error("mm_dev_fir_same: taps is null"); return 1; }
+    float* taps;
+    MM_TRY(arena(c, SL_ROWMAP, (size_t)ntaps, &taps));
+    MM_CUDA(cudaMemcpyAsync(taps, taps_host, (size_t)ntaps * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    MM_CUDA(cudaStreamSynchronize(c->stream));
+    Bufs B;
+    MM_TRY(get_bufs(c, g, &B));
+    if (in != out) return st_fir_same(c, g, in, out, taps, ntaps, clip);
+    MM_TRY(st_fir_same(c, g, in, B.T[1], taps, ntaps, clip));
+    MM_CUDA(cudaMemcpyAsync(out, B.T[1], batch_floats(g) * sizeof(float), cudaMemcpyDeviceToDevice, c->stream));
+    return 0;
+}
+
 int mm_dev_apply_stereo_imager_4band(mm_ctx* c, const mm_geom* g, const float* in, float* out, const double* band_widths,
                                      const double* crossovers_hz) {
     MM_API_BEGIN(c);

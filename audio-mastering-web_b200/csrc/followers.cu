@@ -346,6 +346,20 @@ int st_target_curve_linear_phase(mm_ctx* c, const mm_geom* g, const float* in, f
     return 0;
 }
 
+int st_fir_same(mm_ctx* c, const mm_geom* g, const float* in, float* out, const float* taps_dev, int K, int clip) {
+    if (in == out) { set_error("FIR: in-place operation is not supported"); return 1; }
+    if (K < 64 || (K % 64) != 0 || K > 16384) { set_error("FIR: the tap count must be a multiple of 64 in [64, 16384]"); return 1; }
+    FirArgs A;
+    A.in = in; A.out = out; A.taps = taps_dev; A.n = g->n; A.stride = g->stride; A.K = K; A.center = (K - 1) / 2; A.clip = clip;
+    const size_t smem = (size_t)(K + kFirTile + K + 8 + 8) * sizeof(float);
+    MM_CUDA(cudaFuncSetAttribute(fir_same_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 98304)));
+    dim3 grid((unsigned)((g->n + kFirTile - 1) / kFirTile), (unsigned)(g->tracks * g->channels));
+    KernelScope ks(c, "fir_same");
+    fir_same_kernel<<<grid, kFirThreads, smem, c->stream>>>(A);
+    MM_CUDA(cudaGetLastError());
+    return 0;
+}
+
 // ---- 4-band stereo imager (pipeline.py:1360-1386): _split_bands, per-band mid/side width, sum, clip ------------------
 // The split is the dynamics stage's (same designs, same sweeps); the per-band width and the merge are one pointwise pass
 // over the four stored band pairs, in float64 like the reference's (its bands come out of filtfilt as float64; ours are

@@ -74,6 +74,10 @@ int st_split_bands(mm_ctx* c, const mm_geom* g, const float* in, const double* c
 // reverb.cu: type 0 plate, 1 room, 2 hall, 3 theater, 4 cathedral (in == out allowed)
 int st_reverb(mm_ctx* c, const mm_geom* g, const float* in, float* out, int type, double decay_sec, double mix, int use_ms,
               double mix_mid, double mix_side);
+// spectral.cu: compute_spectral_envelope (pipeline.py:1527-1551): env_dev[tracks][4097] float32
+int st_spectral_envelope(mm_ctx* c, const mm_geom* g, const float* in, float* env_dev);
+// followers.cu: out[i] = sum_k taps[k] x[i + (K-1)/2 - k] (fftconvolve mode="same"), K a multiple of 64, taps on the device
+int st_fir_same(mm_ctx* c, const mm_geom* g, const float* in, float* out, const float* taps_dev, int K, int clip);
 // followers.cu
 int st_target_curve_linear_phase(mm_ctx* c, const mm_geom* g, const float* in, float* out);
 int st_imager4(mm_ctx* c, const mm_geom* g, const float* in, float* out, const double* widths, const double* crossovers_hz);

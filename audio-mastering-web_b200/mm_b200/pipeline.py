@@ -215,6 +215,56 @@ def apply_high_freq_trim(audio: np.ndarray, sr: int, crossover_hz: float = HIGH_
     return _stage("apply_high_freq_trim", audio, sr, C.c_double(crossover_hz), C.c_double(high_gain))
 
 
+def compute_spectral_envelope(audio: np.ndarray, sr: int, n_fft: int = 8192) -> np.ndarray:
+    """backend/app/pipeline.py:1527-1551: averaged RMS spectrum (8192-sample Hann frames, hop 2048) -> float32 (4097,)."""
+    if n_fft != 8192:
+        raise NotImplementedError("the spectral-envelope kernel is built for the reference's n_fft = 8192")
+    a = np.asarray(audio)
+    if a.shape[0] < n_fft:
+        return np.ones(n_fft // 2 + 1, dtype=np.float32)
+    import torch
+    eng, b, _ = _up(audio, sr)
+    with torch.cuda.stream(eng.stream):
+        env = torch.empty(b.tracks * (n_fft // 2 + 1), dtype=torch.float32, device=eng.tdev)
+        g = b.geom
+        _lib.check(eng.lib.mm_dev_spectral_envelope(eng.ctx, C.byref(g), b.ptr, C.c_void_p(env.data_ptr())))
+        eng.sync()
+        return env.cpu().numpy()[: n_fft // 2 + 1].copy()
+
+
+def reference_match_ir(src_env: np.ndarray, ref_env: np.ndarray, strength: float, n_fft: int = 8192) -> np.ndarray:
+    """The design half of apply_reference_match (backend/app/pipeline.py:1590-1604): ratio curve, Savitzky-Golay smoothing,
+    strength, clipping, Hann-windowed impulse response.  4097 numbers on the host, exactly the reference's numpy/scipy calls."""
+    from scipy.signal import savgol_filter
+    eps = 1e-8
+    ratio = (ref_env.astype(np.float64) + eps) / (src_env.astype(np.float64) + eps)
+    win_len = min(51, (len(ratio) // 4) * 2 + 1)
+    win_len = max(5, win_len if win_len % 2 == 1 else win_len + 1)
+    ratio_smooth = np.clip(savgol_filter(ratio, win_len, 3), 0.1, 10.0)
+    ratio_applied = np.clip(1.0 + (ratio_smooth - 1.0) * strength, 0.1, 10.0)
+    n_bins = n_fft // 2 + 1
+    H = np.zeros(n_fft, dtype=np.complex128)
+    H[:n_bins] = ratio_applied
+    H[n_bins:] = ratio_applied[1: n_fft // 2][::-1]
+    return (np.fft.ifft(H).real * np.hanning(n_fft)).astype(np.float32)
+
+
+def apply_reference_match(audio: np.ndarray, sr: int, reference_audio: np.ndarray, ref_sr: int, strength: float = 1.0,
+                          n_fft: int = 8192) -> np.ndarray:
+    """backend/app/pipeline.py:1554-1612: both spectral envelopes and the 8192-tap convolution run on the device, the filter
+    design on the host.  A reference at another sample rate would need scipy.signal.resample of the whole reference track
+    (FFT-class, second wave): not offered."""
+    strength = float(np.clip(strength, 0.0, 1.0))
+    if strength < 0.01:
+        return audio
+    if int(ref_sr) != int(sr):
+        raise NotImplementedError("reference track at a different sample rate: whole-signal FFT resampling is second-wave scope")
+    src_env = compute_spectral_envelope(audio, sr, n_fft)
+    ref_env = compute_spectral_envelope(reference_audio, sr, n_fft)
+    ir = np.ascontiguousarray(reference_match_ir(src_env, ref_env, strength, n_fft))
+    return _stage("fir_same", audio, sr, ir.ctypes.data_as(C.c_void_p), int(ir.shape[0]), 1)
+
+
 _REVERB_TYPES = {"plate": 0, "room": 1, "hall": 2, "theater": 3, "cathedral": 4}
 
 
@@ -378,14 +428,16 @@ def run_mastering_pipeline(audio: np.ndarray, sr: int, target_lufs: float = -14.
     """backend/app/pipeline.py:1800-1909.  The default path is one fused device call; a transient-designer request
     (which sits between the style EQ and the exciter, :1879-1889) takes the stage-by-stage path.  Denoise and
     reference match are second-wave (FFT-class stages)."""
-    if denoise_strength > 0 or reference_audio is not None:
-        raise NotImplementedError("spectral denoise / reference match are second-wave scope (SURVEY 8f)")
+    if denoise_strength > 0:
+        raise NotImplementedError("spectral denoise is second-wave scope (SURVEY 8f)")
     style = style if style in STYLE_CONFIGS else "standard"
     from . import mastering_trace as _mt
     tracing = trace_ctx is not None and _mt.trace_enabled()
-    if tracing or abs(transient_attack - 1.0) > 0.02 or abs(transient_sustain - 1.0) > 0.02:
+    refm = reference_audio is not None and reference_sr is not None
+    if tracing or refm or abs(transient_attack - 1.0) > 0.02 or abs(transient_sustain - 1.0) > 0.02:
         out = _run_v1_stagewise(audio, sr, target_lufs, style, transient_attack, transient_sustain,
-                                trace_ctx=trace_ctx if tracing else None)
+                                trace_ctx=trace_ctx if tracing else None,
+                                reference=(reference_audio, reference_sr, reference_strength) if refm else None)
     else:
         out = master_batch([audio], sr, [style], [target_lufs], chain="v1")["audio"][0]
     if progress_callback is not None:      # stage boundaries are fused on the device; report them in order
@@ -394,7 +446,7 @@ def run_mastering_pipeline(audio: np.ndarray, sr: int, target_lufs: float = -14.
     return out
 
 
-def _run_v1_stagewise(audio, sr, target_lufs, style, transient_attack, transient_sustain, trace_ctx=None):
+def _run_v1_stagewise(audio, sr, target_lufs, style, transient_attack, transient_sustain, trace_ctx=None, reference=None):
     """run_mastering_pipeline stage by stage (pipeline.py:1833-1909), for the options the fused chain does not carry:
     the transient designer, and the per-stage trace (mastering_trace.trace_stage after every stage, same stage names)."""
     from .mastering_trace import trace_stage
@@ -413,6 +465,9 @@ def _run_v1_stagewise(audio, sr, target_lufs, style, transient_attack, transient
         a = tr("parallel_compress", apply_parallel_compression(a, sr, mix=cfg["parallel_mix"]), parallel_mix=cfg["parallel_mix"])
     a = tr("normalize_lufs", normalize_lufs(a, sr, target_lufs), target_lufs=target_lufs)
     a = tr("final_spectral_balance", apply_final_spectral_balance(a, sr))
+    if reference is not None:                                            # pipeline.py:1868-1871
+        a = tr("reference_match", apply_reference_match(a, sr, reference[0], reference[1], strength=reference[2]),
+               reference_strength=reference[2])
     a = tr("style_eq", apply_style_eq(a, sr, style), style=style)
     if abs(transient_attack - 1.0) > 0.02 or abs(transient_sustain - 1.0) > 0.02:
         a = tr("transient_designer", apply_transient_designer(a, sr, attack_gain=transient_attack, sustain_gain=transient_sustain),

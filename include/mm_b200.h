@@ -144,6 +144,12 @@ int mm_dev_apply_stereo_imager_4band(mm_ctx*, const mm_geom*, const float* in, f
  * 3 theater, 4 cathedral; decay_sec <= 0 -> the preset's; use_ms != 0 (stereo only): separate mixes on mid and side. */
 int mm_dev_apply_reverb(mm_ctx*, const mm_geom*, const float* in, float* out, int reverb_type, double decay_sec, double mix,
                         int use_ms, double mix_mid, double mix_side);
+/* compute_spectral_envelope (backend/app/pipeline.py:1527-1551): per track, RMS over 8192-sample Hann frames (hop 2048) of
+ * |rfft| of the channel mean -> env_dev[tracks][4097] float32 (device). */
+int mm_dev_spectral_envelope(mm_ctx*, const mm_geom*, const float* in, float* env_dev);
+/* scipy.signal.fftconvolve(x, taps, mode="same") on every row as a direct FIR (float32 products, float64 carries);
+ * ntaps a multiple of 64; taps on the HOST; clip != 0 clips to +-1 (apply_reference_match, :1600-1606) */
+int mm_dev_fir_same(mm_ctx*, const mm_geom*, const float* in, float* out, const float* taps_host, int ntaps, int clip);
 /* generic zero-phase / causal IIR on every row: scipy filtfilt / lfilter semantics of
  * _safe_filtfilt (backend/app/pipeline.py:36-52). nb == na in {3, 5}; zero_phase 0 -> lfilter. */
 int mm_dev_iir(mm_ctx*, const mm_geom*, const float* in, float* out,

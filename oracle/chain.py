@@ -662,6 +662,47 @@ def apply_reverb(audio, sr, reverb_type="plate", decay_sec=1.2, mix=0.15, mix_mi
     return _uncols(np.clip(out, -1.0, 1.0).astype(np.float32), mono)
 
 
+def compute_spectral_envelope(audio, sr, n_fft=8192):
+    """pipeline.py:1527-1551."""
+    mono = np.mean(audio, axis=1).astype(np.float32) if audio.ndim > 1 else np.asarray(audio, dtype=np.float32)
+    hop = n_fft // 4
+    window = np.hanning(n_fft).astype(np.float32)
+    accum = np.zeros(n_fft // 2 + 1, dtype=np.float64)
+    count = 0
+    for i in range((len(mono) - n_fft) // hop + 1):
+        frame = mono[i * hop: i * hop + n_fft]
+        if len(frame) < n_fft:
+            break
+        accum += np.abs(np.fft.rfft(frame * window)) ** 2
+        count += 1
+    if count == 0:
+        return np.ones(n_fft // 2 + 1, dtype=np.float32)
+    return np.sqrt(accum / count).astype(np.float32)
+
+
+def apply_reference_match(audio, sr, reference_audio, ref_sr, strength=1.0, n_fft=8192):
+    """pipeline.py:1554-1612 (same sample rate)."""
+    from scipy.signal import savgol_filter
+    strength = float(np.clip(strength, 0.0, 1.0))
+    if strength < 0.01:
+        return audio
+    a, mono = _cols(audio)
+    src_env, ref_env = compute_spectral_envelope(a, sr, n_fft), compute_spectral_envelope(reference_audio, sr, n_fft)
+    ratio = (ref_env.astype(np.float64) + 1e-8) / (src_env.astype(np.float64) + 1e-8)
+    win_len = min(51, (len(ratio) // 4) * 2 + 1)
+    win_len = max(5, win_len if win_len % 2 == 1 else win_len + 1)
+    rs = np.clip(savgol_filter(ratio, win_len, 3), 0.1, 10.0)
+    ra = np.clip(1.0 + (rs - 1.0) * strength, 0.1, 10.0)
+    H = np.zeros(n_fft, dtype=np.complex128)
+    H[: n_fft // 2 + 1] = ra
+    H[n_fft // 2 + 1:] = ra[1: n_fft // 2][::-1]
+    ir = (np.fft.ifft(H).real * np.hanning(n_fft)).astype(np.float32)
+    out = np.zeros_like(a, dtype=np.float32)
+    for ch in range(a.shape[1]):
+        out[:, ch] = sg.fftconvolve(a[:, ch].astype(np.float64), ir.astype(np.float64), mode="same")
+    return _uncols(np.clip(out, -1.0, 1.0).astype(np.float32), mono)
+
+
 def _finalize(a):
     out = np.ascontiguousarray(np.clip(a, -1.0, 1.0).astype(np.float32))
     np.nan_to_num(out, copy=False, nan=0.0, posinf=1.0, neginf=-1.0)

@@ -51,6 +51,15 @@ def main():
         "reverb_room_mono": P.apply_reverb(np.ascontiguousarray(perc[:, 0]), sr, "room", 0.6, 0.3),
         "haas_loud": P.apply_stereo_imager(loud, 1.0, stereoize_delay_ms=12.0, stereoize_mix=0.3, sr=sr),
     }
+    # reference mastering: a brighter, bass-lighter "reference" for the same material
+    from scipy import signal as _sg
+    bb, aa = _sg.butter(1, 2000 / (sr / 2), "high")
+    refsig = (loud + 0.8 * _sg.lfilter(bb, aa, loud, axis=0)).astype(np.float32)
+    st["refmatch_reference"] = refsig
+    st["refmatch_env_src"] = P.compute_spectral_envelope(loud, sr)
+    st["refmatch_env_ref"] = P.compute_spectral_envelope(refsig, sr)
+    st["refmatch_out"] = P.apply_reference_match(loud, sr, refsig, sr, strength=0.8)
+    st["refmatch_out_mono"] = P.apply_reference_match(np.ascontiguousarray(loud[:, 0]), sr, refsig, sr, strength=1.0)
     st = {k: (np.asarray(v, dtype=np.float32) if isinstance(v, np.ndarray) else v) for k, v in st.items()}
     # noise-shaped dither export: the reference draws from the legacy global generator, so seeding it pins the uniforms
     short = loud[:6000]

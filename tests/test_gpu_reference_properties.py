@@ -199,3 +199,32 @@ def test_mastering_trace_lines(P, stereo, monkeypatch, caplog):              # t
     eng, b, _ = P._up(bad, SR)
     m = batch_metrics(eng, b)[0]
     assert m["nan_count"] == 3 and m["inf_count"] == 2 and abs(m["peak_linear"] - round(float(np.max(np.abs(stereo))), 6)) < 2e-6
+
+
+def test_error_conventions_at_the_boundary(P, stereo):
+    """SURVEY 8b "error conventions": what degrades quietly in the reference and what fails loudly here.
+    * measure_lufs -> NaN and normalize_lufs -> input unchanged for clips shorter than one 400 ms block (pipeline.py:647-664);
+    * a missing GPU / library or an option without a kernel raises instead of passing audio through;
+    * the C ABI rejects bad geometry with a message instead of reading out of bounds."""
+    import ctypes as C
+    from mm_b200 import _lib
+    from mm_b200.engine import get_engine
+    short = stereo[:4000]
+    assert np.isnan(P.measure_lufs(short, SR))
+    assert np.array_equal(P.normalize_lufs(short, SR, -14.0), short)
+    with pytest.raises(NotImplementedError):
+        P.apply_harmonic_exciter(stereo, SR, 0.8, oversample=2)
+    with pytest.raises(NotImplementedError):
+        P.export_audio(stereo, SR, 2, "mp3")
+    with pytest.raises(NotImplementedError):
+        P.run_mastering_pipeline(stereo, SR, denoise_strength=0.5)
+    eng = get_engine()
+    b = eng.upload([stereo], SR)
+    for bad in (_lib.Geom(b.n, b.stride, 1, 3, SR, 0), _lib.Geom(0, b.stride, 1, 2, SR, 0), _lib.Geom(b.n, b.n, 1, 2, SR, 0),
+                _lib.Geom(b.n, b.stride, 0, 2, SR, 0)):
+        rc = eng.lib.mm_dev_remove_dc_offset(eng.ctx, C.byref(bad), b.ptr, b.ptr)
+        assert rc != 0 and _lib.last_error()
+    tiny = eng.upload([stereo[:8]], SR)                  # shorter than filtfilt's padlen: the reference would degrade to lfilter
+    g = tiny.geom
+    assert eng.lib.mm_dev_apply_target_curve(eng.ctx, C.byref(g), tiny.ptr, tiny.ptr, 0) != 0 and "padlen" in _lib.last_error()
+    assert eng.lib.mm_dev_master(eng.ctx, C.byref(g), 7, None, tiny.ptr, tiny.ptr, None, None, 0, None, 0) != 0

@@ -252,3 +252,27 @@ def test_reverb_against_reference_golden(gpu_lib):
             m.update({"enabled": True, "reverb_type": "room", "mix": 0.1})
     out = MasteringChain.from_config(cfg).process(loud, sr, target_lufs=-14.0, style="standard")
     assert out.shape == loud.shape and np.all(np.isfinite(out))
+
+
+def test_reference_match_against_reference_golden(gpu_lib):
+    """compute_spectral_envelope + apply_reference_match (pipeline.py:1527-1612) against the reference's outputs: the envelope
+    (float32 FFTs on both sides) to 1e-5 relative, the matched audio to 1e-5 absolute."""
+    from mm_b200 import pipeline as P
+    g = load_golden("pro_stages_48k")
+    sr = int(g["sr"])
+    loud = (g["input"] * np.float32(6.0)).astype(np.float32)
+    ref = g["refmatch_reference"]
+    for name, sig in (("refmatch_env_src", loud), ("refmatch_env_ref", ref)):
+        env = P.compute_spectral_envelope(sig, sr)
+        rel = float(np.max(np.abs(env.astype(np.float64) - g[name]) / (np.abs(g[name]) + 1e-3 * np.max(g[name]))))
+        print(f"[parity] {name}: max relative {rel:.3e}")
+        assert env.shape == (4097,) and rel <= 1e-4
+    for name, sig, st in (("refmatch_out", loud, 0.8), ("refmatch_out_mono", np.ascontiguousarray(loud[:, 0]), 1.0)):
+        out = P.apply_reference_match(sig, sr, ref, sr, strength=st)
+        e = float(np.max(np.abs(out.astype(np.float64) - g[name])))
+        print(f"[parity] {name}: {e:.3e}")
+        assert out.shape == g[name].shape and e <= 2e-5
+    assert P.apply_reference_match(loud, sr, ref, sr, strength=0.0) is loud
+    assert np.array_equal(P.compute_spectral_envelope(loud[:1000], sr), np.ones(4097, dtype=np.float32))
+    out = P.run_mastering_pipeline(loud, sr, reference_audio=ref, reference_sr=sr, reference_strength=0.5)
+    assert out.shape == loud.shape and np.all(np.isfinite(out))

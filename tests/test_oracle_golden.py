@@ -97,6 +97,16 @@ def test_pro_stages_match_reference_golden():
         assert err <= 1e-7, (k, err)      # measured: bit equal (numba's fastmath does not change these roundings here)
 
 
+def test_reference_match_matches_reference_golden():
+    g = load_golden("pro_stages_48k")
+    sr = int(g["sr"])
+    loud = (g["input"] * np.float32(6.0)).astype(np.float32)
+    ref = g["refmatch_reference"]
+    assert np.max(np.abs(oc.compute_spectral_envelope(loud, sr) - g["refmatch_env_src"])) <= 1e-6
+    assert np.max(np.abs(oc.apply_reference_match(loud, sr, ref, sr, 0.8).astype(np.float64) - g["refmatch_out"])) <= 1e-6
+    assert np.max(np.abs(oc.apply_reference_match(np.ascontiguousarray(loud[:, 0]), sr, ref, sr, 1.0).astype(np.float64) - g["refmatch_out_mono"])) <= 1e-6
+
+
 def test_noise_shaped_dither_export_matches_reference_golden():
     """ns_e / ns_itu (pipeline.py:835-877): the oracle's shaping of the same uniforms + quantiser == the reference's WAV."""
     g = load_golden("pro_stages_48k")
