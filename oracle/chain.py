@@ -438,23 +438,96 @@ def exciter_saturate(x, mode, k=2.0):
     return np.tanh(k * x) / (k + 1e-8)
 
 
+def fft_resample(x, num):
+    """scipy.signal.resample(x, num) for real 1-D ``x`` (scipy 1.18 ``_signaltools.resample``, time domain, no window), which
+    pipeline.py:920-936 and :1294-1320 call: one-sided spectrum, the first min(n, num)//2 + 1 bins kept, the unpaired bin
+    at m/2 doubled (down-sampling) or halved (up-sampling), inverse real FFT of length ``num`` scaled by num / n."""
+    x = np.asarray(x, dtype=np.float64)
+    n = x.shape[0]
+    m = min(num, n)
+    X = np.fft.rfft(x)[: m // 2 + 1].copy()
+    if m % 2 == 0 and num != n:
+        X[m // 2] *= 2.0 if num < n else 0.5
+    return np.fft.irfft(X * (num / n), n=num)
+
+
+def resample_audio(audio, sr, target_sr):
+    """pipeline.py:920-936."""
+    if target_sr <= 0 or sr <= 0:
+        raise ValueError("Invalid sample rate")
+    if target_sr == sr:
+        return np.asarray(audio, dtype=np.float32)
+    a, mono = _cols(np.asarray(audio, dtype=np.float64))
+    n_out = int(round(a.shape[0] * target_sr / sr))
+    out = np.empty((n_out, a.shape[1]), dtype=np.float32)
+    for c in range(a.shape[1]):
+        out[:, c] = fft_resample(a[:, c], n_out).astype(np.float32)
+    return _uncols(out, mono)
+
+
 def apply_harmonic_exciter(audio, sr, exciter_db=0.0, mode="warm", oversample=1):
-    """pipeline.py:1267-1326 with ``oversample == 1`` (FFT resampling is second-wave)."""
+    """pipeline.py:1267-1326; ``oversample`` 2..4 runs the side chain on an FFT-up-sampled float32 copy and
+    FFT-down-samples the sum (:1294-1320)."""
     if abs(exciter_db) < 0.05:
         return audio
-    if max(1, min(4, int(oversample))) > 1:
-        raise NotImplementedError("oversampled exciter is second-wave scope (SURVEY 8f)")
+    os_ = max(1, min(4, int(oversample)))
     x, mono = _cols(audio)
-    nyq = sr / 2.0
+    n = x.shape[0]
+    if os_ > 1:
+        work = np.stack([fft_resample(x[:, c].astype(np.float64), n * os_).astype(np.float32) for c in range(x.shape[1])], axis=1)
+    else:
+        work = x
+    nyq = sr * os_ / 2.0
     b, a = sg.butter(2, min(6000.0 / nyq, 0.97), "high")
     gain = 10 ** (exciter_db / 20.0) - 1.0
     m = mode if mode in ("warm", "tape", "tube", "transistor", "digital") else "warm"
     k = 2.5 if m == "warm" else 2.0
-    out = x.copy()
-    for c in range(x.shape[1]):
-        hf = zero_phase(b, a, x[:, c])
-        out[:, c] = x[:, c] + (exciter_saturate(hf, m, k) - hf) * gain * 0.25
+    out = work.copy()
+    for c in range(work.shape[1]):
+        hf = zero_phase(b, a, work[:, c])
+        out[:, c] = work[:, c] + (exciter_saturate(hf, m, k) - hf) * gain * 0.25
+    if os_ > 1:
+        out = np.stack([fft_resample(out[:, c].astype(np.float64), n).astype(np.float32) for c in range(out.shape[1])], axis=1)
     return _uncols(out.astype(np.float32), mono)
+
+
+def apply_spectral_denoise(audio, sr, strength=0.5, noise_percentile=15.0):
+    """pipeline.py:1472-1524, with scipy's stft / istft (legacy ``_spectral_helper``: boundary='zeros', padded=True, periodic
+    Hann, scaling='spectrum') written out: 1024 zeros either side, the tail padded to a whole hop, frames of 2048 every 512,
+    rfft(window * frame) / sum(window); per bin the ``noise_percentile`` percentile over the frames capped by 0.85 x the
+    median; gain clip(1 - strength (noise / (|Z| + 1e-10))^2, 0.25, 1); inverse: irfft * sum(window), windowed overlap-add
+    divided by the overlap-added squared window, the 1024-sample boundary removed."""
+    strength = float(np.clip(strength, 0.0, 1.0))
+    if strength < 0.01:
+        return audio
+    a, mono = _cols(audio)
+    n = a.shape[0]
+    nfft, hop = 2048, 512
+    if n < nfft:
+        raise ValueError("noverlap must be less than nperseg.")          # what scipy raises once nperseg is cut to n <= 1536
+    win = sg.get_window("hann", nfft)
+    nadd = (-n) % hop
+    F = (n + nadd) // hop + 1
+    out = np.zeros_like(a, dtype=np.float32)
+    idx = hop * np.arange(F)[:, None] + np.arange(nfft)[None, :]
+    for ch in range(a.shape[1]):
+        ext = np.concatenate([np.zeros(nfft // 2), a[:, ch].astype(np.float64), np.zeros(nfft // 2 + nadd)])
+        Z = np.fft.rfft(ext[idx] * win, axis=1).T / win.sum()               # (1025, F)
+        mag = np.abs(Z)
+        noise = np.percentile(mag, noise_percentile, axis=1, keepdims=True)
+        med = np.median(mag, axis=1, keepdims=True)
+        cap = np.minimum(np.maximum(noise, 1e-12), 0.85 * np.maximum(med, 1e-12))
+        gain = np.clip(1.0 - strength * (cap / (mag + 1e-10)) ** 2, 0.25, 1.0)
+        y = np.fft.irfft((mag * gain * np.exp(1j * np.angle(Z))).T, n=nfft, axis=1) * win.sum()
+        acc = np.zeros(ext.shape[0])
+        norm = np.zeros(ext.shape[0])
+        for f in range(F):
+            acc[f * hop: f * hop + nfft] += y[f] * win
+            norm[f * hop: f * hop + nfft] += win ** 2
+        acc, norm = acc[nfft // 2: -(nfft // 2)], norm[nfft // 2: -(nfft // 2)]
+        xo = acc / np.where(norm > 1e-10, norm, 1.0)
+        out[:, ch] = np.clip(xo[:n], -1.0, 1.0).astype(np.float32)
+    return _uncols(out, mono)
 
 
 def apply_stereo_imager(audio, width=1.0):

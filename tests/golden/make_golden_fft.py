@@ -1,0 +1,63 @@
+#!/usr/bin/env python
+"""Golden vectors of the FFT-class stages, produced by the UNMODIFIED reference (build container only):
+
+    python tests/golden/make_golden_fft.py      ->  tests/golden/fft_stages.npz
+
+* apply_spectral_denoise (backend/app/pipeline.py:1472-1524): 2048/512 STFT Wiener gain with a per-bin percentile noise floor
+* resample_audio (pipeline.py:920-936): scipy.signal.resample, whole-signal FFT
+* apply_harmonic_exciter(oversample=2|4) (pipeline.py:1267-1326): FFT up-sampling, side chain at the high rate, FFT down-sampling
+
+Input: tones + a noise floor + bursts (so the percentile floor, the median cap and the gain clip all engage), seeded.
+"""
+from __future__ import annotations
+
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REPO = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, REPO)
+sys.path.insert(0, os.path.join(REPO, "audio-mastering-web_b200"))
+
+from oracle import ref_harness  # noqa: E402
+
+
+def material(n, sr, seed):
+    rng = np.random.default_rng(seed)
+    t = np.arange(n) / sr
+    tone = 0.25 * np.sin(2 * np.pi * 220.0 * t) + 0.12 * np.sin(2 * np.pi * 1760.0 * t + 0.3) + 0.05 * np.sin(2 * np.pi * 7040.0 * t)
+    gate = ((np.arange(n) % 9000) < 5000).astype(np.float64)          # the tones pause: frames of pure noise floor
+    hiss = 0.01 * rng.standard_normal((n, 2))
+    x = np.stack([tone * gate, 0.8 * tone * gate], axis=1) + hiss
+    return x.astype(np.float32)
+
+
+def main():
+    P = ref_harness.load().pipeline
+    sr, n = 48000, 30000
+    x = material(n, sr, 7)
+    odd = np.ascontiguousarray(x[:20011])                              # not a multiple of the hop: scipy pads the tail
+    st = {
+        "input": x, "sr": np.int64(sr),
+        "denoise_medium": P.apply_spectral_denoise(x, sr, strength=0.5, noise_percentile=15.0),
+        "denoise_strong_odd": P.apply_spectral_denoise(odd, sr, strength=0.9, noise_percentile=20.0),
+        "denoise_mono_short": P.apply_spectral_denoise(np.ascontiguousarray(x[:2500, 0]), sr, strength=0.35, noise_percentile=10.0),
+        "denoise_p37": P.apply_spectral_denoise(np.ascontiguousarray(x[:12345, 1]), sr, strength=1.0, noise_percentile=37.5),
+        "resample_48_44": P.resample_audio(x, 48000, 44100),
+        "resample_44_48": P.resample_audio(odd, 44100, 48000),
+        "resample_mono_96": P.resample_audio(np.ascontiguousarray(x[:9999, 0]), 48000, 96000),
+        "resample_down_even": P.resample_audio(np.ascontiguousarray(x[:20000]), 48000, 24000),
+        "exciter_os2": P.apply_harmonic_exciter(x * np.float32(2.0), sr, exciter_db=2.0, mode="tape", oversample=2),
+        "exciter_os4_mono": P.apply_harmonic_exciter(np.ascontiguousarray(x[:15001, 0]) * np.float32(3.0), sr, exciter_db=1.5,
+                                                     mode="warm", oversample=4),
+    }
+    st = {k: (np.asarray(v, dtype=np.float32) if isinstance(v, np.ndarray) else v) for k, v in st.items()}
+    path = os.path.join(HERE, "fft_stages.npz")
+    np.savez_compressed(path, **st)
+    print({k: np.shape(v) for k, v in st.items()}, "%.0f KB" % (os.path.getsize(path) / 1024))
+
+
+if __name__ == "__main__":
+    main()

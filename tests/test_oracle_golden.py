@@ -107,6 +107,41 @@ def test_reference_match_matches_reference_golden():
     assert np.max(np.abs(oc.apply_reference_match(np.ascontiguousarray(loud[:, 0]), sr, ref, sr, 1.0).astype(np.float64) - g["refmatch_out_mono"])) <= 1e-6
 
 
+def fft_stage_cases(mod, g):
+    """The calls behind tests/golden/fft_stages.npz (make_golden_fft.py), against any module with the reference's names."""
+    x, sr = g["input"], int(g["sr"])
+    odd = np.ascontiguousarray(x[:20011])
+    return {
+        "denoise_medium": lambda: mod.apply_spectral_denoise(x, sr, strength=0.5, noise_percentile=15.0),
+        "denoise_strong_odd": lambda: mod.apply_spectral_denoise(odd, sr, strength=0.9, noise_percentile=20.0),
+        "denoise_mono_short": lambda: mod.apply_spectral_denoise(np.ascontiguousarray(x[:2500, 0]), sr, strength=0.35, noise_percentile=10.0),
+        "denoise_p37": lambda: mod.apply_spectral_denoise(np.ascontiguousarray(x[:12345, 1]), sr, strength=1.0, noise_percentile=37.5),
+        "resample_48_44": lambda: mod.resample_audio(x, 48000, 44100),
+        "resample_44_48": lambda: mod.resample_audio(odd, 44100, 48000),
+        "resample_mono_96": lambda: mod.resample_audio(np.ascontiguousarray(x[:9999, 0]), 48000, 96000),
+        "resample_down_even": lambda: mod.resample_audio(np.ascontiguousarray(x[:20000]), 48000, 24000),
+        "exciter_os2": lambda: mod.apply_harmonic_exciter(x * np.float32(2.0), sr, exciter_db=2.0, mode="tape", oversample=2),
+        "exciter_os4_mono": lambda: mod.apply_harmonic_exciter(np.ascontiguousarray(x[:15001, 0]) * np.float32(3.0), sr, exciter_db=1.5,
+                                                               mode="warm", oversample=4),
+    }
+
+
+def test_fft_class_stages_match_reference_golden():
+    """apply_spectral_denoise / resample_audio / oversampled exciter (pipeline.py:1472-1524, :920-936, :1294-1320): the
+    written-out stft/istft and rfft-resample restatements reproduce the reference's outputs (measured: bit equal)."""
+    g = load_golden("fft_stages")
+    for k, call in fft_stage_cases(oc, g).items():
+        v = call()
+        assert np.shape(v) == g[k].shape and v.dtype == np.float32, k
+        err = np.max(np.abs(np.asarray(v, dtype=np.float64) - g[k]))
+        assert err <= 1e-7, (k, err)
+    with pytest.raises(ValueError):
+        oc.apply_spectral_denoise(g["input"][:1500], 48000, 0.5)
+    x = g["input"]
+    assert oc.apply_spectral_denoise(x, 48000, 0.005) is x
+    assert oc.resample_audio(x, 48000, 48000).dtype == np.float32
+
+
 def test_noise_shaped_dither_export_matches_reference_golden():
     """ns_e / ns_itu (pipeline.py:835-877): the oracle's shaping of the same uniforms + quantiser == the reference's WAV."""
     g = load_golden("pro_stages_48k")
