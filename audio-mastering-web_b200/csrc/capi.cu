@@ -695,6 +695,23 @@ int mm_dev_spectral_envelope(mm_ctx* c, const mm_geom* g, const float* in, float
     return st_spectral_envelope(c, g, in, env_dev);
 }
 
+int mm_dev_apply_spectral_denoise(mm_ctx* c, const mm_geom* g, const float* in, float* out, double strength, double noise_percentile) {
+    MM_API_BEGIN(c);
+    MM_TRY(check_geom(g));
+    if (!(noise_percentile >= 0.0 && noise_percentile <= 100.0)) { set_error("Percentiles must be in the range [0, 100]"); return 2; }
+    strength = std::min(1.0, std::max(0.0, strength));
+    if (strength < 0.01) {                       // bypass (pipeline.py:1489-1490)
+        if (in != out) MM_CUDA(cudaMemcpyAsync(out, in, batch_floats(g) * sizeof(float), cudaMemcpyDeviceToDevice, c->stream));
+        return 0;
+    }
+    if (in != out) return st_spectral_denoise(c, g, in, out, strength, noise_percentile);
+    Bufs B;
+    MM_TRY(get_bufs(c, g, &B));
+    MM_TRY(st_spectral_denoise(c, g, in, B.T[1], strength, noise_percentile));
+    MM_CUDA(cudaMemcpyAsync(out, B.T[1], batch_floats(g) * sizeof(float), cudaMemcpyDeviceToDevice, c->stream));
+    return 0;
+}
+
 int mm_dev_fir_same(mm_ctx* c, const mm_geom* g, const float* in, float* out, const float* taps_host, int ntaps, int clip) {
     MM_API_BEGIN(c);
     MM_TRY(check_geom(g));

@@ -42,7 +42,9 @@ STYLE_CONFIGS = {
 TRUE_PEAK_LIMIT_DB = -1.5
 MULTIBAND_CROSSOVERS_HZ = (214.0, 3500.0, 10000.0)
 MULTIBAND_CONFIG = [(-7.2, 1.0, -7.2, 1.5), (-18.5, 2.2, -18.5, 1.8), (-17.0, 1.55, -17.0, 1.65), (-15.0, 1.35, -15.0, 1.2)]
-DENOISE_PRESETS = {"light": 0.25, "medium": 0.5, "aggressive": 0.8}
+# (strength, noise_percentile) -- backend/app/pipeline.py:1439-1446
+DENOISE_PRESETS = {"vocal": (0.15, 25.0), "light": (0.20, 22.0), "medium": (0.5, 15.0), "aggressive": (0.75, 10.0),
+                   "tape_hiss": (0.25, 22.0), "room_tone": (0.40, 18.0)}
 
 _EXCITER_MODES = {"warm": 0, "tape": 1, "tube": 2, "transistor": 3, "digital": 4}
 
@@ -213,6 +215,20 @@ def apply_high_freq_trim(audio: np.ndarray, sr: int, crossover_hz: float = HIGH_
     if abs(high_gain - 1.0) < 0.001:
         return audio
     return _stage("apply_high_freq_trim", audio, sr, C.c_double(crossover_hz), C.c_double(high_gain))
+
+
+def apply_spectral_denoise(audio: np.ndarray, sr: int, strength: float = 0.5, noise_percentile: float = 15.0) -> np.ndarray:
+    """backend/app/pipeline.py:1472-1524: STFT (2048 / 512, scipy.signal.stft conventions) Wiener gain against a per-bin
+    percentile noise floor, all on the device (csrc/denoise.cu).  Inputs shorter than one 2048-sample segment raise
+    ``ValueError`` as the reference's scipy call does."""
+    strength = float(np.clip(strength, 0.0, 1.0))
+    if strength < 0.01:
+        return audio
+    if not 0.0 <= float(noise_percentile) <= 100.0:
+        raise ValueError("Percentiles must be in the range [0, 100]")
+    if np.asarray(audio).shape[0] < 2048:
+        raise ValueError("noverlap must be less than nperseg.")
+    return _stage("apply_spectral_denoise", audio, sr, C.c_double(strength), C.c_double(float(noise_percentile)))
 
 
 def compute_spectral_envelope(audio: np.ndarray, sr: int, n_fft: int = 8192) -> np.ndarray:
@@ -426,17 +442,15 @@ def run_mastering_pipeline(audio: np.ndarray, sr: int, target_lufs: float = -14.
                            transient_attack: float = 1.0, transient_sustain: float = 1.0, reference_audio=None,
                            reference_sr=None, reference_strength: float = 0.8, trace_ctx=None) -> np.ndarray:
     """backend/app/pipeline.py:1800-1909.  The default path is one fused device call; a transient-designer request
-    (which sits between the style EQ and the exciter, :1879-1889) takes the stage-by-stage path.  Denoise and
-    reference match are second-wave (FFT-class stages)."""
-    if denoise_strength > 0:
-        raise NotImplementedError("spectral denoise is second-wave scope (SURVEY 8f)")
+    (which sits between the style EQ and the exciter, :1879-1889), spectral denoise (:1841-1844) or a reference track
+    (:1868-1871) takes the stage-by-stage path."""
     style = style if style in STYLE_CONFIGS else "standard"
     from . import mastering_trace as _mt
     tracing = trace_ctx is not None and _mt.trace_enabled()
     refm = reference_audio is not None and reference_sr is not None
-    if tracing or refm or abs(transient_attack - 1.0) > 0.02 or abs(transient_sustain - 1.0) > 0.02:
+    if tracing or refm or denoise_strength > 0.01 or abs(transient_attack - 1.0) > 0.02 or abs(transient_sustain - 1.0) > 0.02:
         out = _run_v1_stagewise(audio, sr, target_lufs, style, transient_attack, transient_sustain,
-                                trace_ctx=trace_ctx if tracing else None,
+                                trace_ctx=trace_ctx if tracing else None, denoise_strength=denoise_strength,
                                 reference=(reference_audio, reference_sr, reference_strength) if refm else None)
     else:
         out = master_batch([audio], sr, [style], [target_lufs], chain="v1")["audio"][0]
@@ -446,7 +460,8 @@ def run_mastering_pipeline(audio: np.ndarray, sr: int, target_lufs: float = -14.
     return out
 
 
-def _run_v1_stagewise(audio, sr, target_lufs, style, transient_attack, transient_sustain, trace_ctx=None, reference=None):
+def _run_v1_stagewise(audio, sr, target_lufs, style, transient_attack, transient_sustain, trace_ctx=None, reference=None,
+                      denoise_strength=0.0):
     """run_mastering_pipeline stage by stage (pipeline.py:1833-1909), for the options the fused chain does not carry:
     the transient designer, and the per-stage trace (mastering_trace.trace_stage after every stage, same stage names)."""
     from .mastering_trace import trace_stage
@@ -458,6 +473,8 @@ def _run_v1_stagewise(audio, sr, target_lufs, style, transient_attack, transient
 
     a = tr("dc_offset", remove_dc_offset(audio))
     a = tr("peak_guard_in", remove_intersample_peaks(a, headroom_db=0.5))
+    if denoise_strength > 0.01:                                          # pipeline.py:1841-1844
+        a = tr("spectral_denoise", apply_spectral_denoise(a, sr, strength=denoise_strength), denoise_strength=denoise_strength)
     a = tr("target_eq", apply_target_curve(a, sr))
     a = tr("deesser", apply_deesser(a, sr))
     a = tr("dynamics", apply_dynamics(a, sr))

@@ -144,6 +144,10 @@ int mm_dev_apply_stereo_imager_4band(mm_ctx*, const mm_geom*, const float* in, f
  * 3 theater, 4 cathedral; decay_sec <= 0 -> the preset's; use_ms != 0 (stereo only): separate mixes on mid and side. */
 int mm_dev_apply_reverb(mm_ctx*, const mm_geom*, const float* in, float* out, int reverb_type, double decay_sec, double mix,
                         int use_ms, double mix_mid, double mix_side);
+/* apply_spectral_denoise (backend/app/pipeline.py:1472-1524): 2048/512 STFT (scipy.signal.stft conventions), per-bin
+ * percentile noise floor over the frames capped by 0.85 x the median, Wiener gain clipped to [0.25, 1], inverse STFT, clip.
+ * n >= 2048 (the reference's scipy call raises below that); strength < 0.01 is a bypass */
+int mm_dev_apply_spectral_denoise(mm_ctx*, const mm_geom*, const float* in, float* out, double strength, double noise_percentile);
 /* compute_spectral_envelope (backend/app/pipeline.py:1527-1551): per track, RMS over 8192-sample Hann frames (hop 2048) of
  * |rfft| of the channel mean -> env_dev[tracks][4097] float32 (device). */
 int mm_dev_spectral_envelope(mm_ctx*, const mm_geom*, const float* in, float* env_dev);

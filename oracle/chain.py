@@ -782,8 +782,9 @@ def _finalize(a):
     return out
 
 
-def run_v1(audio, sr, target_lufs=-14.0, style="standard", stages=None):
-    """``run_mastering_pipeline`` default path (pipeline.py:1800-1909; no denoise/reference/transient).
+def run_v1(audio, sr, target_lufs=-14.0, style="standard", stages=None, denoise_strength=0.0):
+    """``run_mastering_pipeline`` default path (pipeline.py:1800-1909; optional spectral denoise :1841-1844; no
+    reference/transient).
 
     ``stages``: optional dict that receives a copy of the buffer after each stage.
     """
@@ -796,6 +797,8 @@ def run_v1(audio, sr, target_lufs=-14.0, style="standard", stages=None):
 
     a = keep("dc_offset", remove_dc_offset(audio))
     a = keep("peak_guard_in", remove_intersample_peaks(a, 0.5))
+    if denoise_strength > 0.01:
+        a = keep("spectral_denoise", apply_spectral_denoise(a, sr, strength=denoise_strength))
     a = keep("target_eq", apply_target_curve(a, sr))
     a = keep("deesser", apply_deesser(a, sr))
     a = keep("dynamics", apply_dynamics(a, sr))

@@ -3,7 +3,7 @@ tests/golden/make_golden.py produced by running the unmodified reference."""
 import numpy as np
 import pytest
 
-from conftest import load_golden, tpdf_noise
+from conftest import fft_stage_cases, load_golden, tpdf_noise
 from oracle import chain as oc
 from mm_b200 import synth
 
@@ -105,25 +105,6 @@ def test_reference_match_matches_reference_golden():
     assert np.max(np.abs(oc.compute_spectral_envelope(loud, sr) - g["refmatch_env_src"])) <= 1e-6
     assert np.max(np.abs(oc.apply_reference_match(loud, sr, ref, sr, 0.8).astype(np.float64) - g["refmatch_out"])) <= 1e-6
     assert np.max(np.abs(oc.apply_reference_match(np.ascontiguousarray(loud[:, 0]), sr, ref, sr, 1.0).astype(np.float64) - g["refmatch_out_mono"])) <= 1e-6
-
-
-def fft_stage_cases(mod, g):
-    """The calls behind tests/golden/fft_stages.npz (make_golden_fft.py), against any module with the reference's names."""
-    x, sr = g["input"], int(g["sr"])
-    odd = np.ascontiguousarray(x[:20011])
-    return {
-        "denoise_medium": lambda: mod.apply_spectral_denoise(x, sr, strength=0.5, noise_percentile=15.0),
-        "denoise_strong_odd": lambda: mod.apply_spectral_denoise(odd, sr, strength=0.9, noise_percentile=20.0),
-        "denoise_mono_short": lambda: mod.apply_spectral_denoise(np.ascontiguousarray(x[:2500, 0]), sr, strength=0.35, noise_percentile=10.0),
-        "denoise_p37": lambda: mod.apply_spectral_denoise(np.ascontiguousarray(x[:12345, 1]), sr, strength=1.0, noise_percentile=37.5),
-        "resample_48_44": lambda: mod.resample_audio(x, 48000, 44100),
-        "resample_44_48": lambda: mod.resample_audio(odd, 44100, 48000),
-        "resample_mono_96": lambda: mod.resample_audio(np.ascontiguousarray(x[:9999, 0]), 48000, 96000),
-        "resample_down_even": lambda: mod.resample_audio(np.ascontiguousarray(x[:20000]), 48000, 24000),
-        "exciter_os2": lambda: mod.apply_harmonic_exciter(x * np.float32(2.0), sr, exciter_db=2.0, mode="tape", oversample=2),
-        "exciter_os4_mono": lambda: mod.apply_harmonic_exciter(np.ascontiguousarray(x[:15001, 0]) * np.float32(3.0), sr, exciter_db=1.5,
-                                                               mode="warm", oversample=4),
-    }
 
 
 def test_fft_class_stages_match_reference_golden():
