@@ -332,6 +332,7 @@ void mm_ctx_destroy(mm_ctx* c) {
     if (!c) return;
     DeviceGuard guard(c->device);
     cudaStreamSynchronize(c->stream);
+    bigfft_release(c);
     for (int i = 0; i < SL_COUNT; ++i) if (c->slots[i].p) cudaFree(c->slots[i].p);
     for (auto& kv : c->plans) if (kv.second.dev) cudaFree(kv.second.dev);
     for (auto& kv : c->kw_plans) if (kv.second.dev) cudaFree(kv.second.dev);
@@ -693,6 +694,14 @@ int mm_dev_spectral_envelope(mm_ctx* c, const mm_geom* g, const float* in, float
     MM_API_BEGIN(c);
     MM_TRY(check_geom(g));
     return st_spectral_envelope(c, g, in, env_dev);
+}
+
+int mm_dev_fft_resample(mm_ctx* c, const mm_geom* gin, const float* in, const mm_geom* gout, float* out) {
+    MM_API_BEGIN(c);
+    MM_TRY(check_geom(gin));
+    MM_TRY(check_geom(gout));
+    if (in == out) { set_error("mm_dev_fft_resample: not in place"); return 2; }
+    return st_fft_resample(c, gin, in, gout, out);
 }
 
 int mm_dev_apply_spectral_denoise(mm_ctx* c, const mm_geom* g, const float* in, float* out, double strength, double noise_percentile) {

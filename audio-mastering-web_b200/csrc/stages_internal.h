@@ -76,6 +76,9 @@ int st_reverb(mm_ctx* c, const mm_geom* g, const float* in, float* out, int type
               double mix_mid, double mix_side);
 // spectral.cu: compute_spectral_envelope (pipeline.py:1527-1551): env_dev[tracks][4097] float32
 int st_spectral_envelope(mm_ctx* c, const mm_geom* g, const float* in, float* env_dev);
+// bigfft.cu: scipy.signal.resample of every row (gi->n -> go->n frames; same tracks / channels); plan cache per context
+int st_fft_resample(mm_ctx* c, const mm_geom* gi, const float* in, const mm_geom* go, float* out);
+void bigfft_release(mm_ctx* c);
 // denoise.cu: apply_spectral_denoise (pipeline.py:1472-1524); not in place
 int st_spectral_denoise(mm_ctx* c, const mm_geom* g, const float* in, float* out, double strength, double noise_percentile);
 // followers.cu: out[i] = sum_k taps[k] x[i + (K-1)/2 - k] (fftconvolve mode="same"), K a multiple of 64, taps on the device

@@ -9,8 +9,7 @@ modules/equalizer.py:83-85), and the result is clipped to +-1 with nan_to_num (c
 The audio is uploaded once, every module is a CUDA stage call on the device-resident batch, and the
 result is downloaded once.  When the configuration is exactly ``default_config(target, style)`` the
 whole chain runs as the fused sweep plan (``mm_dev_master``), which is what ``bench.py`` times.
-Second-wave options without a kernel yet (oversampled exciter) raise
-``NotImplementedError`` when enabled instead of silently passing audio through.
+Every module option of the reference has a device stage (oversampled exciter, 4-band / Haas imager, reverb included).
 """
 from __future__ import annotations
 
@@ -171,11 +170,7 @@ class ExciterModule(BaseModule):
         self.exciter_db, self.mode, self.oversample = float(exciter_db), str(mode), int(oversample)
 
     def _process(self, eng, b, **kw):
-        if abs(self.exciter_db) < 0.05:
-            return b
-        if max(1, min(4, self.oversample)) > 1:
-            raise NotImplementedError("oversampled exciter is second-wave scope (SURVEY 8f)")
-        return eng.stage("apply_harmonic_exciter", b, _d(self.exciter_db), P._EXCITER_MODES.get(self.mode, 0))
+        return P._exciter_dev(eng, b, self.exciter_db, self.mode, self.oversample)     # modules/exciter.py -> pipeline.py:1267-1326
 
 
 class ImagerModule(BaseModule):
@@ -184,14 +179,12 @@ class ImagerModule(BaseModule):
     def __init__(self, enabled=True, amount=1.0, width=1.0, stereoize_delay_ms=0.0, stereoize_mix=0.12, band_widths=None,
                  crossovers_hz=None, **kwargs):
         super().__init__(enabled=enabled, amount=amount, **kwargs)
-        self.width, self.stereoize_delay_ms, self.band_widths = float(width), float(stereoize_delay_ms or 0.0), band_widths
+        self.width, self.stereoize_delay_ms, self.stereoize_mix = float(width), float(stereoize_delay_ms or 0.0), float(stereoize_mix)
+        self.band_widths = list(band_widths) if band_widths else None
+        self.crossovers_hz = tuple(float(x) for x in crossovers_hz) if crossovers_hz else None
 
-    def _process(self, eng, b, **kw):
-        if b.channels != 2:
-            return b
-        if self.band_widths is not None or self.stereoize_delay_ms > 0:
-            raise NotImplementedError("multiband / Haas imager is second-wave scope (SURVEY 8f)")
-        return eng.stage("apply_stereo_imager", b, _d(self.width))
+    def _process(self, eng, b, **kw):      # modules/imaging.py:44-53 -> pipeline.py:1339-1398
+        return P._imager_dev(eng, b, self.width, self.stereoize_delay_ms, self.stereoize_mix, self.band_widths, self.crossovers_hz)
 
 
 class ReverbModule(BaseModule):

@@ -118,6 +118,16 @@ class Engine:
         _lib.check(fn(self.ctx, C.byref(g), src.ptr, dst.ptr, *args))
         return dst
 
+    def fft_resample(self, src: Batch, num: int, sr: int | None = None) -> Batch:
+        """scipy.signal.resample(row, num) of every row (csrc/bigfft.cu); ``sr`` labels the new batch."""
+        num = int(num)
+        if num == src.n:
+            return src
+        dst = self.empty(src.tracks, src.channels, num, sr if sr is not None else src.sr)
+        gi, go = src.geom, dst.geom
+        _lib.check(self.lib.mm_dev_fft_resample(self.ctx, C.byref(gi), src.ptr, C.byref(go), dst.ptr))
+        return dst
+
     # ---- reductions / analyzers -------------------------------------------------------------------
     def _doubles(self, count):
         torch = _torch()

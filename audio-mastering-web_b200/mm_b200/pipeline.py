@@ -160,13 +160,63 @@ def apply_style_eq(audio: np.ndarray, sr: int, style: str = "standard") -> np.nd
     return _stage("apply_style_eq", audio, sr, _lib.darr([cfg[k] for k in ("sub", "bass", "mids", "presence", "air")]))
 
 
+def _exciter_dev(eng, b, exciter_db, mode, oversample):
+    """apply_harmonic_exciter on a device batch (returns a batch; may be ``b`` itself when bypassed)."""
+    if abs(exciter_db) < 0.05:
+        return b
+    os_ = max(1, min(4, int(oversample)))
+    if os_ == 1:
+        return eng.stage("apply_harmonic_exciter", b, C.c_double(exciter_db), _EXCITER_MODES.get(mode, 0))
+    work = eng.fft_resample(b, b.n * os_, b.sr * os_)
+    work = eng.stage("apply_harmonic_exciter", work, C.c_double(exciter_db), _EXCITER_MODES.get(mode, 0), out=work)
+    return eng.fft_resample(work, b.n, b.sr)
+
+
 def apply_harmonic_exciter(audio: np.ndarray, sr: int, exciter_db: float = 0.0, mode: str = "warm", oversample: int = 1) -> np.ndarray:
-    """backend/app/pipeline.py:1267-1326 (oversample == 1; FFT-resampled variant is second-wave)."""
+    """backend/app/pipeline.py:1267-1326.  ``oversample`` 2..4: whole-signal FFT up-sampling (scipy.signal.resample
+    semantics, csrc/bigfft.cu), the side chain at the high rate, FFT down-sampling -- three device calls, no host trip."""
     if abs(exciter_db) < 0.05:
         return audio
-    if max(1, min(4, int(oversample))) > 1:
-        raise NotImplementedError("oversampled exciter is second-wave scope (SURVEY 8f)")
-    return _stage("apply_harmonic_exciter", audio, sr, C.c_double(exciter_db), _EXCITER_MODES.get(mode, 0))
+    eng, b, mono = _up(audio, sr)
+    return _down(eng, _exciter_dev(eng, b, exciter_db, mode, oversample), mono)
+
+
+def fft_resample(audio: np.ndarray, num: int) -> np.ndarray:
+    """``scipy.signal.resample(audio, num, axis=0).astype(float32)`` on the device."""
+    eng, b, mono = _up(audio, 44100)
+    if int(num) == b.n:
+        return _down(eng, b, mono)
+    return _down(eng, eng.fft_resample(b, int(num)), mono)
+
+
+def resample_audio(audio: np.ndarray, sr: int, target_sr: int) -> np.ndarray:
+    """backend/app/pipeline.py:920-936."""
+    if target_sr <= 0 or sr <= 0:
+        raise ValueError("Invalid sample rate")
+    if target_sr == sr:
+        return np.asarray(audio, dtype=np.float32)
+    a = np.asarray(audio)
+    return fft_resample(a, int(round(a.shape[0] * target_sr / sr)))
+
+
+def _imager_dev(eng, b, width=1.0, stereoize_delay_ms=0.0, stereoize_mix=0.12, band_widths=None, crossovers_hz=None):
+    """apply_stereo_imager on a device batch (backend/app/pipeline.py:1339-1398); returns a batch."""
+    if b.channels != 2:
+        return b
+    sr = b.sr
+    four = band_widths is not None and len(band_widths) == 4 and sr and sr > 0
+    haas = bool(stereoize_delay_ms and stereoize_delay_ms > 0 and sr and sr > 0 and stereoize_mix > 0 and
+                min(int(sr * stereoize_delay_ms / 1000.0), b.n - 1) > 0)
+    if four:
+        cx = _lib.darr([float(v) for v in crossovers_hz]) if crossovers_hz is not None and len(crossovers_hz) == 3 else None
+        wide = eng.stage("apply_stereo_imager_4band", b, _lib.darr([float(w) for w in band_widths]), cx)
+        if not haas:
+            return wide
+        # the cross-delay then acts on the merged pair as it is (width = NaN: no mid/side step)
+        return eng.stage("apply_stereoize", wide, C.c_double(float("nan")), C.c_double(stereoize_delay_ms), C.c_double(stereoize_mix))
+    if haas:                                  # the delayed tap reads behind the writer: not in place
+        return eng.stage("apply_stereoize", b, C.c_double(width), C.c_double(stereoize_delay_ms), C.c_double(stereoize_mix))
+    return eng.stage("apply_stereo_imager", b, C.c_double(width))
 
 
 def apply_stereo_imager(audio: np.ndarray, width: float = 1.0, stereoize_delay_ms: float = 0.0, stereoize_mix: float = 0.12,
@@ -176,20 +226,10 @@ def apply_stereo_imager(audio: np.ndarray, width: float = 1.0, stereoize_delay_m
     a = np.asarray(audio)
     if a.ndim == 1 or a.shape[1] == 1:
         return audio
-    four = band_widths is not None and len(band_widths) == 4 and sr and sr > 0
-    haas = bool(stereoize_delay_ms and stereoize_delay_ms > 0 and sr and sr > 0 and stereoize_mix > 0 and
-                min(int(sr * stereoize_delay_ms / 1000.0), a.shape[0] - 1) > 0)
-    if four:
-        cx = _lib.darr([float(v) for v in crossovers_hz]) if crossovers_hz is not None and len(crossovers_hz) == 3 else None
-        wide = _stage("apply_stereo_imager_4band", audio, sr, _lib.darr([float(w) for w in band_widths]), cx)
-        if not haas:
-            return wide
-        eng, b, mono = _up(wide, sr)          # the cross-delay then acts on the merged pair as it is (width = NaN: no mid/side step)
-        return _down(eng, eng.stage("apply_stereoize", b, C.c_double(float("nan")), C.c_double(stereoize_delay_ms), C.c_double(stereoize_mix)), mono)
-    if haas:
-        eng, b, mono = _up(audio, sr)         # the delayed tap reads behind the writer: not in place
-        return _down(eng, eng.stage("apply_stereoize", b, C.c_double(width), C.c_double(stereoize_delay_ms), C.c_double(stereoize_mix)), mono)
-    return _stage("apply_stereo_imager", audio, sr or 44100, C.c_double(width))
+    if not (sr and sr > 0):                   # without a rate only the plain width mode exists (:1360, :1385)
+        return _stage("apply_stereo_imager", audio, 44100, C.c_double(width))
+    eng, b, mono = _up(audio, sr)
+    return _down(eng, _imager_dev(eng, b, width, stereoize_delay_ms, stereoize_mix, band_widths, crossovers_hz), mono)
 
 
 def apply_transient_designer(audio: np.ndarray, sr: int, attack_gain: float = 1.0, sustain_gain: float = 1.0) -> np.ndarray:
@@ -268,13 +308,14 @@ def reference_match_ir(src_env: np.ndarray, ref_env: np.ndarray, strength: float
 def apply_reference_match(audio: np.ndarray, sr: int, reference_audio: np.ndarray, ref_sr: int, strength: float = 1.0,
                           n_fft: int = 8192) -> np.ndarray:
     """backend/app/pipeline.py:1554-1612: both spectral envelopes and the 8192-tap convolution run on the device, the filter
-    design on the host.  A reference at another sample rate would need scipy.signal.resample of the whole reference track
-    (FFT-class, second wave): not offered."""
+    design on the host.  A reference at another sample rate is mixed to mono and FFT-resampled first (:1581-1584)."""
     strength = float(np.clip(strength, 0.0, 1.0))
     if strength < 0.01:
         return audio
-    if int(ref_sr) != int(sr):
-        raise NotImplementedError("reference track at a different sample rate: whole-signal FFT resampling is second-wave scope")
+    if ref_sr != sr:
+        ref = np.asarray(reference_audio)
+        ref_mono = np.mean(ref, axis=1) if ref.ndim > 1 else ref
+        reference_audio = fft_resample(ref_mono, int(len(ref_mono) * sr / ref_sr))
     src_env = compute_spectral_envelope(audio, sr, n_fft)
     ref_env = compute_spectral_envelope(reference_audio, sr, n_fft)
     ir = np.ascontiguousarray(reference_match_ir(src_env, ref_env, strength, n_fft))

@@ -144,6 +144,10 @@ int mm_dev_apply_stereo_imager_4band(mm_ctx*, const mm_geom*, const float* in, f
  * 3 theater, 4 cathedral; decay_sec <= 0 -> the preset's; use_ms != 0 (stereo only): separate mixes on mid and side. */
 int mm_dev_apply_reverb(mm_ctx*, const mm_geom*, const float* in, float* out, int reverb_type, double decay_sec, double mix,
                         int use_ms, double mix_mid, double mix_side);
+/* scipy.signal.resample(x, gout->n) of every row of the input batch (whole-signal FFT resampling, any pair of lengths up
+ * to 2^27 combined points): resample_audio (backend/app/pipeline.py:920-936), the oversampled exciter (:1294-1320), a
+ * reference track at another rate (:1581-1584).  gout has the same tracks / channels; gin->n != gout->n; not in place */
+int mm_dev_fft_resample(mm_ctx*, const mm_geom* gin, const float* in, const mm_geom* gout, float* out);
 /* apply_spectral_denoise (backend/app/pipeline.py:1472-1524): 2048/512 STFT (scipy.signal.stft conventions), per-bin
  * percentile noise floor over the frames capped by 0.85 x the median, Wiener gain clipped to [0.25, 1], inverse STFT, clip.
  * n >= 2048 (the reference's scipy call raises below that); strength < 0.01 is a bypass */

@@ -171,9 +171,9 @@ def test_mastering_chain_api_default_and_custom(P):
     a = oc.remove_intersample_peaks(a, 1.0)
     ref = np.clip(a, -1, 1).astype(np.float32)
     assert _err(got, ref) <= 5e-6
-    # options without a kernel fail loudly instead of passing audio through (the reference would swallow the error)
-    with pytest.raises(NotImplementedError):
-        mc.MasteringChain.from_config({"modules": [{"id": "exciter", "enabled": True, "exciter_db": 0.8, "oversample": 2}]}).process(x.copy(), sr)
+    # the oversampled exciter runs on the device too (FFT resampling either side of the side chain)
+    os2 = mc.MasteringChain.from_config({"modules": [{"id": "exciter", "enabled": True, "exciter_db": 0.8, "oversample": 2}]}).process(x.copy(), sr)
+    assert _err(os2, np.clip(oc.apply_harmonic_exciter(x, sr, 0.8, "warm", 2), -1, 1)) <= 2e-5
     # the reverb module now runs (second wave): enabled, it changes the signal; disabled (the default), it does not
     wet = mc.MasteringChain.from_config({"modules": [{"id": "reverb", "enabled": True, "mix": 0.2}]}).process(x.copy(), sr)
     dry = mc.MasteringChain.from_config({"modules": [{"id": "reverb", "enabled": False}]}).process(x.copy(), sr)

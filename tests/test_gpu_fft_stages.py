@@ -87,3 +87,99 @@ def test_v1_chain_with_denoise_against_oracle(P):
     e = _err(out, ref)
     print(f"[parity] v1 chain with denoise: {e:.3e}")
     assert out.shape == x.shape and e <= TOL
+
+
+RS_TOL = 2e-5       # float32 Bluestein (four 2^18..2^25-point FFTs per row); measured ~1e-6
+
+
+def test_fft_resample_against_reference_golden(P):
+    g = load_golden("fft_stages")
+    for k, call in fft_stage_cases(P, g).items():
+        if not k.startswith("resample"):
+            continue
+        out = call()
+        e = _err(out, g[k])
+        print(f"[parity] {k}: {e:.3e}")
+        assert out.shape == g[k].shape and out.dtype == np.float32 and e <= RS_TOL, (k, e)
+
+
+def test_oversampled_exciter_against_reference_golden(P):
+    g = load_golden("fft_stages")
+    for k, call in fft_stage_cases(P, g).items():
+        if not k.startswith("exciter"):
+            continue
+        out = call()
+        e = _err(out, g[k])
+        print(f"[parity] {k}: {e:.3e}")
+        assert out.shape == g[k].shape and out.dtype == np.float32 and e <= RS_TOL, (k, e)
+
+
+def test_fft_resample_lengths_against_oracle(P):
+    """Odd / even / prime lengths either way (the unpaired-bin rule of scipy.signal.resample), identity, errors."""
+    from oracle import chain as oc
+    rng = np.random.default_rng(3)
+    for n, num in ((1000, 1500), (1001, 1500), (1000, 1501), (1500, 1000), (1501, 1000), (1500, 1001), (7919, 7907), (2, 3),
+                   (3, 2), (1, 5), (5, 1), (262144, 262145), (300000, 100000)):
+        x = (0.5 * rng.standard_normal(n)).astype(np.float32)
+        out = P.fft_resample(x, num)
+        ref = oc.fft_resample(x, num).astype(np.float32)
+        e = _err(out, ref)
+        print(f"[parity] resample {n} -> {num}: {e:.3e}")
+        assert out.shape == (num,) and e <= RS_TOL * max(1.0, float(np.max(np.abs(ref)))), (n, num, e)
+    x = (0.1 * rng.standard_normal((500, 2))).astype(np.float32)
+    assert np.array_equal(P.resample_audio(x, 48000, 48000), x)
+    with pytest.raises(ValueError):
+        P.resample_audio(x, 0, 48000)
+
+
+def test_fft_resample_three_minute_track(P):
+    """BASELINE size: one 180 s stereo track 44.1 -> 48 kHz (7,938,000 -> 8,640,000 frames, two 2^24-point chirp
+    convolutions per row) against scipy on the host, and back again (band-limited material survives the round trip)."""
+    from oracle import chain as oc
+    sr, n = 44100, 180 * 44100
+    t = np.arange(n, dtype=np.float64) / sr
+    rng = np.random.default_rng(11)
+    x = np.stack([0.3 * np.sin(2 * np.pi * 440.0 * t) + 0.2 * np.sin(2 * np.pi * 9000.0 * t * (1 + 1e-3 * t)),
+                  0.25 * np.sin(2 * np.pi * 55.0 * t) + 0.02 * rng.standard_normal(n)], axis=1).astype(np.float32)
+    up = P.resample_audio(x, 44100, 48000)
+    ref = oc.resample_audio(x, 44100, 48000)
+    e = _err(up, ref)
+    print(f"[parity] resample 180 s 44.1k -> 48k: {e:.3e}")
+    assert up.shape == ref.shape and e <= RS_TOL
+    back = P.resample_audio(up, 48000, 44100)
+    e2 = _err(back, x)
+    print(f"[parity] resample round trip 180 s: {e2:.3e}")
+    assert back.shape == x.shape and e2 <= 5e-5
+
+
+def test_reference_match_with_reference_at_another_rate(P):
+    """apply_reference_match, ref_sr != sr (pipeline.py:1581-1584): mono mix, truncating length, FFT resample."""
+    from oracle import chain as oc
+    g = load_golden("pro_stages_48k")
+    sr = int(g["sr"])
+    loud = (g["input"] * np.float32(6.0)).astype(np.float32)
+    ref441 = oc.resample_audio(g["refmatch_reference"], 48000, 44100)
+    out = P.apply_reference_match(loud, sr, ref441, 44100, strength=0.8)
+    ref_mono = np.mean(ref441, axis=1)
+    ref48 = oc.fft_resample(ref_mono.astype(np.float64), int(len(ref_mono) * sr / 44100)).astype(np.float32)
+    want = oc.apply_reference_match(loud, sr, ref48, sr, 0.8)
+    e = _err(out, want)
+    print(f"[parity] reference match, reference at 44.1 kHz: {e:.3e}")
+    assert e <= 2e-5
+
+
+def test_chain_modules_oversampled_exciter_and_multiband_imager(P):
+    """v2 chain with ExciterModule(oversample=2) and ImagerModule(band_widths=...) (modules/exciter.py, modules/imaging.py)
+    == the same stage functions applied in order."""
+    from mm_b200.chain import MasteringChain
+    g = load_golden("fft_stages")
+    x, sr = (g["input"] * np.float32(2.0)).astype(np.float32), int(g["sr"])
+    cfg = {"modules": [{"id": "exciter", "enabled": True, "exciter_db": 2.0, "mode": "tape", "oversample": 2},
+                       {"id": "imager", "enabled": True, "width": 1.0, "band_widths": [0.8, 1.0, 1.3, 1.6]}]}
+    out = MasteringChain.from_config(cfg).process(x, sr)
+    want = P.apply_stereo_imager(P.apply_harmonic_exciter(x, sr, 2.0, "tape", 2), 1.0, sr=sr, band_widths=[0.8, 1.0, 1.3, 1.6])
+    want = np.nan_to_num(np.clip(want, -1.0, 1.0))
+    e = _err(out, want)
+    print(f"[parity] chain exciter(os=2) + imager(4 band): {e:.3e}")
+    assert e <= 1e-6
+    assert _err(P.apply_harmonic_exciter(x, sr, 2.0, "tape", 2), g["exciter_os2"]) <= RS_TOL
