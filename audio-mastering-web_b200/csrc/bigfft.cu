@@ -8,15 +8,16 @@
 // which is scipy's "rfft -> keep m/2 + 1 bins -> x2 / x0.5 on the unpaired bin -> irfft(n = num) * num / n" written as one
 // one-sided sum.  n and num are arbitrary (7,938,000 -> 8,640,000 for a 180 s track), so both DFTs are evaluated as
 // Bluestein chirp convolutions, e^{s 2 pi i j k / N} = u[j] u[k] conj(u[k - j]) with u[j] = e^{s i pi j^2 / N} (phase from
-// j^2 mod 2N in 64-bit integers, float64 sincospi), over power-of-two circular lengths L >= n_in + n_out - 1.
+// j^2 mod 2N in 64-bit integers, reduced in float64), over power-of-two circular lengths L >= n_in + n_out - 1.
 //
-// The length-L complex FFT (float32, L = 2^18 .. 2^27) is three in-place passes over the row viewed as [N1][N2][N3]:
-// pass 1 and 2 transform a strided axis for a tile of adjacent columns (coalesced 32..128-byte runs, transposed into
-// shared memory), pass 3 the contiguous axis; every pass is a shared-memory Stockham FFT (radix 4 + one radix-2 step for
-// odd log2) of up to 4096 points per CTA, with the inter-pass twiddles W_L^e read from two L2-resident tables
+// The length-L complex FFT (float32, L = 2^18 .. 2^27) is three (four above 2^24) in-place passes over the row viewed as
+// [N1][N2][N3]([N4]) with axes of 64, 128 or 256 points: the strided axes are transformed for a tile of adjacent columns
+// (coalesced 128..512-byte runs), the last pass the contiguous axis.  A CTA owns 4096 points, 16 per thread: a radix-16
+// (radix-8) step in registers straight from global memory, one exchange through padded shared memory, a second in-register
+// step straight back to global memory; the inter-pass twiddles W_L^e come from two L2-resident tables
 // (W_L^e = lo[e & 4095] * hi[e >> 12], both rounded from float64).  The spectrum stays in the digit-scrambled order
-// [k1][k2][k3]; the chirp filter's spectrum is computed by the same passes, its product rides the store of pass 3, and the
-// inverse runs the passes backwards -- no transposes, no bit reversal.
+// [k1][k2][k3]; the chirp filter's spectrum is computed by the same passes, its product rides the load of the inverse's
+// first pass, and the inverse runs the passes backwards -- no transposes, no bit reversal.
 #include <algorithm>
 #include <cmath>
 #include <map>
@@ -35,8 +36,9 @@ constexpr int kBfLoBits = 12;
 struct BigFft {
     int p = 0;
     long long L = 0;
-    int lg[3] = {0, 0, 0};              // log2 of N1, N2, N3
-    float2* twR[3] = {nullptr, nullptr, nullptr};
+    int np = 3;                         // passes (axes)
+    int lg[4] = {0, 0, 0, 0};           // log2 of the axis lengths, outermost first
+    float2* twR[4] = {nullptr, nullptr, nullptr, nullptr};
     float2* tlo = nullptr;
     float2* thi = nullptr;
 };
@@ -63,7 +65,7 @@ void bigfft_release(mm_ctx* c) {
     auto it = caches().find(c);
     if (it == caches().end()) return;
     for (auto& kv : it->second.ffts) {
-        for (int i = 0; i < 3; ++i) cudaFree(kv.second->twR[i]);
+        for (int i = 0; i < 4; ++i) cudaFree(kv.second->twR[i]);
         cudaFree(kv.second->tlo);
         cudaFree(kv.second->thi);
     }
@@ -71,12 +73,32 @@ void bigfft_release(mm_ctx* c) {
     caches().erase(it);
 }
 
-// e^{sign i pi j^2 / N}
-__device__ __forceinline__ double2 chirp(long long j, long long N, int sign) {
-    const unsigned long long q = ((unsigned long long)j * (unsigned long long)j) % (unsigned long long)(2 * N);
-    double s, c;
-    sincospi((double)q / (double)N, &s, &c);
-    return make_double2(c, sign > 0 ? s : -s);
+// e^{sign i pi j^2 / N} to float32 accuracy: j^2 mod 2N exactly (Barrett reduction with m = floor(2^64 / 2N)), the phase
+// reduced in float64 to [-1/4, 1/4] half-turns around the nearest quadrant, float32 sincospi there, quadrant rotation
+struct ChirpMod {
+    unsigned long long twoN, m;
+    double invN;
+};
+static ChirpMod chirp_mod(long long N) {
+    ChirpMod c;
+    c.twoN = 2ULL * (unsigned long long)N;
+    c.m = (unsigned long long)((((unsigned __int128)1) << 64) / c.twoN);
+    c.invN = 1.0 / (double)N;
+    return c;
+}
+__device__ __forceinline__ float2 chirp(unsigned long long j, const ChirpMod& M, int sign) {
+    const unsigned long long q = j * j;
+    unsigned long long rem = q - __umul64hi(q, M.m) * M.twoN;
+    while (rem >= M.twoN) rem -= M.twoN;
+    const double t = (double)(long long)rem * M.invN;          // half-turns in [0, 2)
+    const double kq = rint(t * 2.0);
+    const float a = (float)(t - 0.5 * kq);
+    float s, c;
+    sincospif(a, &s, &c);
+    const int k = (int)kq & 3;
+    const float cr = k == 0 ? c : k == 1 ? -s : k == 2 ? -c : s;
+    const float sr = k == 0 ? s : k == 1 ? c : k == 2 ? -s : -c;
+    return make_float2(cr, sign > 0 ? sr : -sr);
 }
 
 __global__ void bf_table_kernel(float2* t, long long count, long long mul, long long L) {
@@ -90,137 +112,179 @@ __global__ void bf_table_kernel(float2* t, long long count, long long mul, long 
 struct BfPass {
     float2* data;
     long long pitch;        // float2 per row
-    int R, lgR;             // FFT length of this pass
-    int G, lgG;             // FFTs per CTA
     long long S;            // element stride of the transformed axis (1: contiguous pass)
-    long long tmul;         // twiddle exponent = inner * k * tmul (0: no twiddle)
-    const float2* twR;
+    unsigned tmul;          // twiddle exponent = inner * k * tmul (0: no twiddle)
+    const float2* twR;      // [R] e^{-2 pi i t / R}
     const float2* tlo;
     const float2* thi;
-    const float2* mul;      // forward only: pointwise multiplier applied on store
+    const float2* mul;      // pointwise multiplier applied on load (the inverse's first pass)
     int inverse;
 };
 
-__global__ void __launch_bounds__(kBfThreads) bf_pass_kernel(const BfPass P) {
-    extern __shared__ __align__(16) unsigned char bsm[];
-    const int R = P.R, G = P.G, Rp = R + 1;
-    float2* A = reinterpret_cast<float2*>(bsm);
-    float2* B = A + (size_t)G * Rp;
-    float2* tw = B + (size_t)G * Rp;
-    for (int t = threadIdx.x; t < R; t += kBfThreads) tw[t] = P.twR[t];
-    float2* row = P.data + (size_t)blockIdx.y * (size_t)P.pitch;
-    const bool strided = P.S > 1;
-    long long base, inner0 = 0;
-    if (strided) {
-        const long long tiles_per_outer = P.S >> P.lgG;
-        const long long outer = blockIdx.x / tiles_per_outer, it = blockIdx.x % tiles_per_outer;
-        base = outer * (long long)R * P.S + it * G;
-        inner0 = it * G;
-    } else {
-        base = (long long)blockIdx.x * kBfTile;
+// ---- in-register DFTs (forward sign); dft_pos<N>(k) is where output k ends up --------------------------------------
+__device__ __forceinline__ void dft4(float2& a, float2& b, float2& c, float2& d) {
+    const float2 a02 = make_float2(a.x + c.x, a.y + c.y), s02 = make_float2(a.x - c.x, a.y - c.y);
+    const float2 a13 = make_float2(b.x + d.x, b.y + d.y), s13 = make_float2(b.x - d.x, b.y - d.y);
+    a = make_float2(a02.x + a13.x, a02.y + a13.y);
+    b = make_float2(s02.x + s13.y, s02.y - s13.x);
+    c = make_float2(a02.x - a13.x, a02.y - a13.y);
+    d = make_float2(s02.x - s13.y, s02.y + s13.x);
+}
+__device__ __forceinline__ float2 w16(int m) {          // e^{-2 pi i m / 16}, m folded at compile time
+    constexpr float c1 = 0.92387953251128674f, s1 = 0.38268343236508977f, h = 0.70710678118654752f;
+    switch (m) {
+        case 0: return make_float2(1.0f, 0.0f);
+        case 1: return make_float2(c1, -s1);
+        case 2: return make_float2(h, -h);
+        case 3: return make_float2(s1, -c1);
+        case 4: return make_float2(0.0f, -1.0f);
+        case 6: return make_float2(-h, -h);
+        default: return make_float2(-c1, s1);           // m == 9
     }
-    // ---- load (inverse: conj(x) * W^e, so that the forward transform below inverts) ----
-    for (int i = threadIdx.x; i < kBfTile; i += kBfThreads) {
-        int g, r;
-        long long off;
-        if (strided) { r = i >> P.lgG; g = i & (G - 1); off = base + (long long)r * P.S + g; }
-        else { g = i >> P.lgR; r = i & (R - 1); off = base + i; }
-        float2 v = row[off];
-        if (P.inverse) {
-            v = cconj(v);
-            if (P.tmul) {
-                const long long e = (inner0 + g) * (long long)r * P.tmul;
-                v = cmulf(v, cmulf(P.tlo[e & ((1 << kBfLoBits) - 1)], P.thi[e >> kBfLoBits]));
-            }
-        }
-        A[g * Rp + r] = v;
+}
+template <int N> __device__ __forceinline__ void dft_reg(float2* v);
+template <> __device__ __forceinline__ void dft_reg<16>(float2* v) {
+#pragma unroll
+    for (int n0 = 0; n0 < 4; ++n0) dft4(v[n0], v[4 + n0], v[8 + n0], v[12 + n0]);
+#pragma unroll
+    for (int k1 = 1; k1 < 4; ++k1)
+#pragma unroll
+        for (int n0 = 1; n0 < 4; ++n0) v[4 * k1 + n0] = cmulf(v[4 * k1 + n0], w16(n0 * k1));
+#pragma unroll
+    for (int k1 = 0; k1 < 4; ++k1) dft4(v[4 * k1], v[4 * k1 + 1], v[4 * k1 + 2], v[4 * k1 + 3]);
+}
+template <> __device__ __forceinline__ void dft_reg<8>(float2* v) {
+#pragma unroll
+    for (int n0 = 0; n0 < 2; ++n0) dft4(v[n0], v[2 + n0], v[4 + n0], v[6 + n0]);
+#pragma unroll
+    for (int k1 = 1; k1 < 4; ++k1) v[2 * k1 + 1] = cmulf(v[2 * k1 + 1], w16(2 * k1));
+#pragma unroll
+    for (int k1 = 0; k1 < 4; ++k1) {
+        const float2 a = v[2 * k1], b = v[2 * k1 + 1];
+        v[2 * k1] = make_float2(a.x + b.x, a.y + b.y);
+        v[2 * k1 + 1] = make_float2(a.x - b.x, a.y - b.y);
     }
-    __syncthreads();
-    // ---- G Stockham FFTs of length R ----
-    float2* src = A;
-    float2* dst = B;
-    const int quarter = R >> 2, lgQ = P.lgR - 2;
-    int Ns = 1;
-    for (; Ns * 4 <= R; Ns <<= 2) {
-        const int tstep = R / (4 * Ns);
-        for (int b = threadIdx.x; b < kBfTile / 4; b += kBfThreads) {
-            const int g = b >> lgQ, j = b & (quarter - 1);
-            const int k = j & (Ns - 1);
-            const float2* s = src + g * Rp;
-            float2* d = dst + g * Rp;
-            float2 v0 = s[j], v1 = s[j + quarter], v2 = s[j + 2 * quarter], v3 = s[j + 3 * quarter];
-            if (Ns > 1) {
-                v1 = cmulf(v1, tw[k * tstep]);
-                v2 = cmulf(v2, tw[2 * k * tstep]);
-                v3 = cmulf(v3, tw[3 * k * tstep]);
-            }
-            const float2 a02 = make_float2(v0.x + v2.x, v0.y + v2.y), s02 = make_float2(v0.x - v2.x, v0.y - v2.y);
-            const float2 a13 = make_float2(v1.x + v3.x, v1.y + v3.y), s13 = make_float2(v1.x - v3.x, v1.y - v3.y);
-            const int j0 = ((j - k) << 2) + k;
-            d[j0] = make_float2(a02.x + a13.x, a02.y + a13.y);
-            d[j0 + Ns] = make_float2(s02.x + s13.y, s02.y - s13.x);
-            d[j0 + 2 * Ns] = make_float2(a02.x - a13.x, a02.y - a13.y);
-            d[j0 + 3 * Ns] = make_float2(s02.x - s13.y, s02.y + s13.x);
-        }
-        __syncthreads();
-        float2* t = src; src = dst; dst = t;
-    }
-    if (Ns < R) {                                   // odd log2(R): one radix-2 step with Ns = R / 2
-        const int half = R >> 1, lgH = P.lgR - 1;
-        for (int b = threadIdx.x; b < kBfTile / 2; b += kBfThreads) {
-            const int g = b >> lgH, k = b & (half - 1);
-            const float2* s = src + g * Rp;
-            float2* d = dst + g * Rp;
-            const float2 v0 = s[k], v1 = cmulf(s[k + half], tw[k]);
-            d[k] = make_float2(v0.x + v1.x, v0.y + v1.y);
-            d[k + half] = make_float2(v0.x - v1.x, v0.y - v1.y);
-        }
-        __syncthreads();
-        float2* t = src; src = dst; dst = t;
-    }
-    // ---- store (forward: * W^e, * multiplier; inverse: conj) ----
-    for (int i = threadIdx.x; i < kBfTile; i += kBfThreads) {
-        int g, r;
-        long long off;
-        if (strided) { r = i >> P.lgG; g = i & (G - 1); off = base + (long long)r * P.S + g; }
-        else { g = i >> P.lgR; r = i & (R - 1); off = base + i; }
-        float2 v = src[g * Rp + r];
-        if (P.inverse) {
-            v = cconj(v);
-        } else {
-            if (P.tmul) {
-                const long long e = (inner0 + g) * (long long)r * P.tmul;
-                v = cmulf(v, cmulf(P.tlo[e & ((1 << kBfLoBits) - 1)], P.thi[e >> kBfLoBits]));
-            }
-            if (P.mul) v = cmulf(v, P.mul[off]);
-        }
-        row[off] = v;
+}
+template <int N> __device__ __forceinline__ constexpr int dft_pos(int k) { return N == 16 ? 4 * (k & 3) + (k >> 2) : 2 * (k & 3) + (k >> 2); }
+
+// W_L^{c (j + q STEP)}, q = 0 .. N-1, from four table reads: base W^{c j}, step D = W^{c STEP}, D^2, D^4, D^8 by squaring and
+// every power as a product of at most five factors (error <= 5 float32 roundings, instead of 2 N dependent L2 reads)
+template <int N> __device__ __forceinline__ void twiddle_run(const BfPass& P, unsigned c, unsigned j, unsigned step, float2* w) {
+    const unsigned lomask = (1u << kBfLoBits) - 1u;
+    const unsigned e0 = c * j, e1 = c * step;
+    w[0] = cmulf(P.tlo[e0 & lomask], P.thi[e0 >> kBfLoBits]);
+    float2 d = cmulf(P.tlo[e1 & lomask], P.thi[e1 >> kBfLoBits]);
+#pragma unroll
+    for (int h = 1; h < N; h <<= 1) {
+#pragma unroll
+        for (int q = 0; q < h; ++q) w[h + q] = cmulf(w[q], d);
+        d = cmulf(d, d);
     }
 }
 
-static int bf_run(mm_ctx* c, const BigFft* F, float2* data, long long pitch, int rows, int inverse, const float2* mul) {
-    static bool attr = false;
-    const size_t smem_max = (2 * (size_t)(kBfTile + 256) + 1024) * sizeof(float2);
-    if (!attr) {
-        MM_CUDA(cudaFuncSetAttribute(bf_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
-        attr = true;
+// One pass = G = 4096 / R transforms of length R = RA * RB per CTA, 16 points per thread: a radix-RA step straight from
+// global memory into registers, one exchange through shared memory, a radix-RB step straight back to global memory.
+template <int RA, int RB, bool STRIDED> __global__ void __launch_bounds__(kBfThreads, 3) bf_pass_kernel(const BfPass P) {
+    constexpr int R = RA * RB, G = kBfTile / R, Rp = R + RB + 1;          // index i of a transform lives at i + i / RA
+    constexpr int NA = 16 / RA, NB = 16 / RB;
+    __shared__ float2 Y[G * Rp];
+    __shared__ float2 tw[R];
+    for (int t = threadIdx.x; t < R; t += kBfThreads) tw[t] = P.twR[t];
+    float2* row = P.data + (size_t)blockIdx.y * (size_t)P.pitch;
+    const unsigned S = (unsigned)P.S;                 // offsets inside a row fit 32 bits (L <= 2^27)
+    unsigned base, inner0 = 0;
+    if (STRIDED) {
+        const unsigned tiles_per_outer = S / G;
+        const unsigned outer = blockIdx.x / tiles_per_outer, it = blockIdx.x % tiles_per_outer;
+        base = outer * (unsigned)R * S + it * G;
+        inner0 = it * G;
+    } else {
+        base = blockIdx.x * (unsigned)kBfTile;
     }
-    const long long N1 = 1LL << F->lg[0], N2 = 1LL << F->lg[1], N3 = 1LL << F->lg[2];
-    for (int step = 0; step < 3; ++step) {
-        const int ps = inverse ? 2 - step : step;
+    float2 v[16];
+    // ---- radix RA (Stockham step with Ns = 1) ----
+#pragma unroll
+    for (int i = 0; i < NA; ++i) {
+        const int b = threadIdx.x + kBfThreads * i;
+        const int g = STRIDED ? b % G : b / RB, j = STRIDED ? b / G : b % RB;
+#pragma unroll
+        for (int q = 0; q < RA; ++q) {
+            const int r = j + q * RB;
+            const unsigned off = STRIDED ? base + (unsigned)r * S + g : base + g * R + r;
+            float2 x = row[off];
+            if (P.mul) x = cmulf(x, P.mul[off]);    // inverse, first pass: the chirp filter's spectrum
+            v[i * RA + q] = x;
+        }
+        if (P.inverse) {                            // conj(x) W^e: the forward transform below then inverts
+            if (STRIDED && P.tmul) {
+                float2 w[RA];
+                twiddle_run<RA>(P, (inner0 + g) * P.tmul, j, RB, w);
+#pragma unroll
+                for (int q = 0; q < RA; ++q) v[i * RA + q] = cmulf(cconj(v[i * RA + q]), w[q]);
+            } else {
+#pragma unroll
+                for (int q = 0; q < RA; ++q) v[i * RA + q] = cconj(v[i * RA + q]);
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < NA; ++i) {
+        const int b = threadIdx.x + kBfThreads * i;
+        const int g = STRIDED ? b % G : b / RB, j = STRIDED ? b / G : b % RB;
+        dft_reg<RA>(v + i * RA);
+#pragma unroll
+        for (int k = 0; k < RA; ++k) Y[g * Rp + j * (RA + 1) + k] = v[i * RA + dft_pos<RA>(k)];
+    }
+    __syncthreads();
+    // ---- radix RB (Ns = RA): inputs j' + q RA, twiddle W_R^{j' q}, outputs j' + q' RA ----
+#pragma unroll
+    for (int i = 0; i < NB; ++i) {
+        const int b = threadIdx.x + kBfThreads * i;
+        const int g = STRIDED ? b % G : b / RA, j = STRIDED ? b / G : b % RA;
+#pragma unroll
+        for (int q = 0; q < RB; ++q) {
+            float2 x = Y[g * Rp + j + q * (RA + 1)];
+            if (q) x = cmulf(x, tw[j * q]);
+            v[i * RB + q] = x;
+        }
+        dft_reg<RB>(v + i * RB);
+        float2 w[RB];
+        const bool twid = STRIDED && !P.inverse && P.tmul;
+        if (twid) twiddle_run<RB>(P, (inner0 + g) * P.tmul, j, RA, w);
+#pragma unroll
+        for (int k = 0; k < RB; ++k) {
+            const int r = j + k * RA;
+            const unsigned off = STRIDED ? base + (unsigned)r * S + g : base + g * R + r;
+            float2 x = v[i * RB + dft_pos<RB>(k)];
+            if (P.inverse) x = cconj(x);
+            else if (twid) x = cmulf(x, w[k]);
+            row[off] = x;
+        }
+    }
+}
+
+template <bool STRIDED> static void bf_launch(int lgR, dim3 grid, cudaStream_t st, const BfPass& P) {
+    if (lgR == 6) bf_pass_kernel<8, 8, STRIDED><<<grid, kBfThreads, 0, st>>>(P);
+    else if (lgR == 7) bf_pass_kernel<16, 8, STRIDED><<<grid, kBfThreads, 0, st>>>(P);
+    else bf_pass_kernel<16, 16, STRIDED><<<grid, kBfThreads, 0, st>>>(P);
+}
+
+static int bf_run(mm_ctx* c, const BigFft* F, float2* data, long long pitch, int rows, int inverse, const float2* mul) {
+    for (int step = 0; step < F->np; ++step) {
+        const int ps = inverse ? F->np - 1 - step : step;
         BfPass P;
         P.data = data; P.pitch = pitch; P.inverse = inverse;
-        P.lgR = F->lg[ps]; P.R = 1 << P.lgR;
-        P.lgG = 12 - P.lgR; P.G = 1 << P.lgG;
         P.twR = F->twR[ps]; P.tlo = F->tlo; P.thi = F->thi;
-        P.mul = (!inverse && ps == 2) ? mul : nullptr;
-        if (ps == 0) { P.S = N2 * N3; P.tmul = 1; }
-        else if (ps == 1) { P.S = N3; P.tmul = N1; }
-        else { P.S = 1; P.tmul = 0; }
-        const size_t smem = (2 * (size_t)P.G * (P.R + 1) + P.R) * sizeof(float2);
+        P.mul = (inverse && ps == F->np - 1) ? mul : nullptr;
+        int below = 0, above = 0;                   // log2 of the product of the axes after / before this one
+        for (int m = ps + 1; m < F->np; ++m) below += F->lg[m];
+        for (int m = 0; m < ps; ++m) above += F->lg[m];
+        P.S = 1LL << below;
+        P.tmul = ps == F->np - 1 ? 0u : 1u << above;
         dim3 grid((unsigned)(F->L / kBfTile), (unsigned)rows);
         KernelScope ks(c, inverse ? "bigfft_pass_inverse" : "bigfft_pass_forward");
-        bf_pass_kernel<<<grid, kBfThreads, smem, c->stream>>>(P);
+        if (P.S > 1) bf_launch<true>(F->lg[ps], grid, c->stream, P);
+        else bf_launch<false>(F->lg[ps], grid, c->stream, P);
         MM_CUDA(cudaGetLastError());
     }
     return 0;
@@ -233,9 +297,10 @@ static int bf_get_fft(mm_ctx* c, int p, BigFft** out) {
     std::unique_ptr<BigFft> F(new BigFft);
     F->p = p;
     F->L = 1LL << p;
-    // three factors, each between 2^4 and 2^9, the contiguous one the largest
-    F->lg[0] = p / 3; F->lg[1] = (p - F->lg[0]) / 2; F->lg[2] = p - F->lg[0] - F->lg[1];
-    for (int i = 0; i < 3; ++i) {
+    // three (L <= 2^24) or four axes of 64, 128 or 256 points, the longer ones last
+    F->np = p <= 24 ? 3 : 4;
+    for (int i = 0; i < F->np; ++i) F->lg[i] = p / F->np + (i >= F->np - p % F->np ? 1 : 0);
+    for (int i = 0; i < F->np; ++i) {
         const long long R = 1LL << F->lg[i];
         MM_CUDA(cudaMalloc(&F->twR[i], R * sizeof(float2)));
         bf_table_kernel<<<(unsigned)((R + 255) / 256), 256, 0, c->stream>>>(F->twR[i], R, 1, R);
@@ -252,17 +317,14 @@ static int bf_get_fft(mm_ctx* c, int p, BigFft** out) {
 }
 
 // filter sequence conj(u) laid out circularly: index j for 0 <= j < nout, index L - j for 1 <= j < nin
-__global__ void bf_chirp_filter_kernel(float2* w, long long L, long long N, long long nin, long long nout, int sign) {
+__global__ void bf_chirp_filter_kernel(float2* w, long long L, const ChirpMod M, long long nin, long long nout, int sign) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= L) return;
     long long j = -1;
     if (i < nout) j = i;
     else if (L - i < nin) j = L - i;
     float2 v = make_float2(0.0f, 0.0f);
-    if (j >= 0) {
-        const double2 u = chirp(j, N, -sign);
-        v = make_float2((float)u.x, (float)u.y);
-    }
+    if (j >= 0) v = chirp((unsigned long long)j, M, -sign);
     w[i] = v;
 }
 
@@ -291,7 +353,7 @@ static int bf_get_chirp(mm_ctx* c, long long N, long long nin, long long nout, i
     MM_TRY(bf_get_fft(c, p, &P.fft));
     const long long L = P.fft->L;
     MM_CUDA(cudaMalloc(&P.FW, L * sizeof(float2)));
-    bf_chirp_filter_kernel<<<(unsigned)((L + 255) / 256), 256, 0, c->stream>>>(P.FW, L, N, nin, nout, sign);
+    bf_chirp_filter_kernel<<<(unsigned)((L + 255) / 256), 256, 0, c->stream>>>(P.FW, L, chirp_mod(N), nin, nout, sign);
     MM_CUDA(cudaGetLastError());
     MM_TRY(bf_run(c, P.fft, P.FW, L, 1, 0, nullptr));
     bf_scale_kernel<<<(unsigned)((L + 255) / 256), 256, 0, c->stream>>>(P.FW, L, (float)(1.0 / (double)L));
@@ -308,6 +370,7 @@ struct RsArgs {
     long long n, num, m2, in_stride, out_stride, pitch, L1, L2;
     int up, m_even;
     float2* work;
+    ChirpMod Mn, Mnum;
 };
 
 // A1[j] = x[j] u1[j]   (u1[j] = e^{-i pi j^2 / n}), zero up to L1
@@ -316,9 +379,9 @@ __global__ void rs_pre_kernel(const RsArgs P) {
     if (j >= P.L1) return;
     float2 v = make_float2(0.0f, 0.0f);
     if (j < P.n) {
-        const double x = (double)P.in[(size_t)blockIdx.y * (size_t)P.in_stride + kLead + j];
-        const double2 u = chirp(j, P.n, -1);
-        v = make_float2((float)(x * u.x), (float)(x * u.y));
+        const float x = P.in[(size_t)blockIdx.y * (size_t)P.in_stride + kLead + j];
+        const float2 u = chirp((unsigned long long)j, P.Mn, -1);
+        v = make_float2(x * u.x, x * u.y);
     }
     P.work[(size_t)blockIdx.y * (size_t)P.pitch + j] = v;
 }
@@ -331,12 +394,13 @@ __global__ void rs_mid_kernel(const RsArgs P) {
     float2 v = make_float2(0.0f, 0.0f);
     if (k < P.m2) {
         const float2 cv = *w;
-        const double2 u1 = chirp(k, P.n, -1), u2 = chirp(k, P.num, +1);
-        const double xr = (double)cv.x * u1.x - (double)cv.y * u1.y, xi = (double)cv.x * u1.y + (double)cv.y * u1.x;
+        const float2 u1 = chirp((unsigned long long)k, P.Mn, -1), u2 = chirp((unsigned long long)k, P.Mnum, +1);
         double g = k == 0 ? 1.0 : 2.0;
         if (P.m_even && k == P.m2 - 1) g = P.up ? 1.0 : 2.0;
-        g /= (double)P.n;
-        v = make_float2((float)(g * (xr * u2.x - xi * u2.y)), (float)(g * (xr * u2.y + xi * u2.x)));
+        const float gf = (float)(g / (double)P.n);
+        const float2 x = cmulf(cv, u1);
+        const float2 y = cmulf(x, u2);
+        v = make_float2(gf * y.x, gf * y.y);
     }
     *w = v;
 }
@@ -346,8 +410,8 @@ __global__ void rs_post_kernel(const RsArgs P) {
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= P.num) return;
     const float2 cv = P.work[(size_t)blockIdx.y * (size_t)P.pitch + t];
-    const double2 u = chirp(t, P.num, +1);
-    P.out[(size_t)blockIdx.y * (size_t)P.out_stride + kLead + t] = (float)((double)cv.x * u.x - (double)cv.y * u.y);
+    const float2 u = chirp((unsigned long long)t, P.Mnum, +1);
+    P.out[(size_t)blockIdx.y * (size_t)P.out_stride + kLead + t] = fmaf(cv.x, u.x, -cv.y * u.y);
 }
 
 int st_fft_resample(mm_ctx* c, const mm_geom* gi, const float* in, const mm_geom* go, float* out) {
@@ -364,6 +428,7 @@ int st_fft_resample(mm_ctx* c, const mm_geom* gi, const float* in, const mm_geom
     A.n = n; A.num = num; A.m2 = m2; A.in_stride = gi->stride; A.out_stride = go->stride;
     A.L1 = F1->fft->L; A.L2 = F2->fft->L; A.pitch = std::max(A.L1, A.L2);
     A.up = num > n; A.m_even = (m % 2 == 0);
+    A.Mn = chirp_mod(n); A.Mnum = chirp_mod(num);
     // rows per sub-batch: keep the complex work area near 4 GB
     const int chunk = (int)std::max<long long>(1, std::min<long long>(rows, (4LL << 30) / (A.pitch * (long long)sizeof(float2))));
     MM_TRY(arena(c, SL_BIGFFT, (size_t)chunk * (size_t)A.pitch, &A.work));
@@ -376,15 +441,15 @@ int st_fft_resample(mm_ctx* c, const mm_geom* gi, const float* in, const mm_geom
             rs_pre_kernel<<<dim3((unsigned)((A.L1 + 255) / 256), (unsigned)nr), 256, 0, c->stream>>>(A);
             MM_CUDA(cudaGetLastError());
         }
-        MM_TRY(bf_run(c, F1->fft, A.work, A.pitch, nr, 0, F1->FW));
-        MM_TRY(bf_run(c, F1->fft, A.work, A.pitch, nr, 1, nullptr));
+        MM_TRY(bf_run(c, F1->fft, A.work, A.pitch, nr, 0, nullptr));
+        MM_TRY(bf_run(c, F1->fft, A.work, A.pitch, nr, 1, F1->FW));
         {
             KernelScope ks(c, "resample_chirp_mid");
             rs_mid_kernel<<<dim3((unsigned)((A.L2 + 255) / 256), (unsigned)nr), 256, 0, c->stream>>>(A);
             MM_CUDA(cudaGetLastError());
         }
-        MM_TRY(bf_run(c, F2->fft, A.work, A.pitch, nr, 0, F2->FW));
-        MM_TRY(bf_run(c, F2->fft, A.work, A.pitch, nr, 1, nullptr));
+        MM_TRY(bf_run(c, F2->fft, A.work, A.pitch, nr, 0, nullptr));
+        MM_TRY(bf_run(c, F2->fft, A.work, A.pitch, nr, 1, F2->FW));
         {
             KernelScope ks(c, "resample_chirp_post");
             rs_post_kernel<<<dim3((unsigned)((num + 255) / 256), (unsigned)nr), 256, 0, c->stream>>>(A);
