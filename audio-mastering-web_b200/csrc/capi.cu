@@ -788,6 +788,18 @@ int mm_dev_iir(mm_ctx* c, const mm_geom* g, const float* in, float* out, const d
 }
 
 // ---- export -------------------------------------------------------------------------------------
+int mm_dev_last_above(mm_ctx* c, const mm_geom* g, const float* in, double threshold_lin, int64_t* idx_dev) {
+    MM_API_BEGIN(c);
+    MM_TRY(check_geom(g));
+    return st_last_above(c, g, in, threshold_lin, reinterpret_cast<long long*>(idx_dev));
+}
+
+int mm_dev_quantize_pcm24(mm_ctx* c, const mm_geom* g, const float* in, int32_t* out_interleaved) {
+    MM_API_BEGIN(c);
+    MM_TRY(check_geom(g));
+    return st_quantize_pcm24(c, g, in, out_interleaved);
+}
+
 int mm_dev_quantize_int16(mm_ctx* c, const mm_geom* g, const float* in, int16_t* pcm, const float* noise, uint64_t seed) {
     MM_API_BEGIN(c);
     MM_TRY(check_geom(g));

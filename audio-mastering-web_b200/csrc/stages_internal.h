@@ -79,6 +79,9 @@ int st_spectral_envelope(mm_ctx* c, const mm_geom* g, const float* in, float* en
 // bigfft.cu: scipy.signal.resample of every row (gi->n -> go->n frames; same tracks / channels); plan cache per context
 int st_fft_resample(mm_ctx* c, const mm_geom* gi, const float* in, const mm_geom* go, float* out);
 void bigfft_release(mm_ctx* c);
+// export.cu: _auto_blank_end's scan (idx_dev[tracks]: last frame above the threshold, -1 if none) and the PCM_24 conversion
+int st_last_above(mm_ctx* c, const mm_geom* g, const float* in, double threshold, long long* idx_dev);
+int st_quantize_pcm24(mm_ctx* c, const mm_geom* g, const float* in, int32_t* out);
 // denoise.cu: apply_spectral_denoise (pipeline.py:1472-1524); not in place
 int st_spectral_denoise(mm_ctx* c, const mm_geom* g, const float* in, float* out, double strength, double noise_percentile);
 // followers.cu: out[i] = sum_k taps[k] x[i + (K-1)/2 - k] (fftconvolve mode="same"), K a multiple of 64, taps on the device

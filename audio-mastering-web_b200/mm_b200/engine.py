@@ -164,6 +164,32 @@ class Engine:
                                                       C.c_void_p(peak.data_ptr())))
         return self._to_host(corr), self._to_host(peak)
 
+    def auto_blank_end(self, b: Batch, threshold_dbfs: float, min_silence_sec: float) -> Batch:
+        """_auto_blank_end (pipeline.py:900-918) for a one-track batch: a view of ``b`` cut after the last frame above the
+        threshold plus ``min_silence_sec`` (the scan runs on the device; the cut is a shorter geometry over the same rows)."""
+        torch = _torch()
+        n_silence = int(b.sr * min_silence_sec)
+        if b.n == 0 or min_silence_sec <= 0 or n_silence <= 0 or b.tracks != 1:
+            return b
+        with torch.cuda.stream(self.stream):
+            idx = torch.empty(b.tracks, dtype=torch.int64, device=self.tdev)
+            g = b.geom
+            _lib.check(self.lib.mm_dev_last_above(self.ctx, C.byref(g), b.ptr, float(10 ** (threshold_dbfs / 20.0)), C.c_void_p(idx.data_ptr())))
+            self.sync()
+            last = int(idx.cpu()[0])
+        keep = b.n if last < 0 else min(b.n, last + 1 + n_silence)
+        return Batch(b.t, b.tracks, b.channels, keep, b.sr)
+
+    def quantize_pcm24(self, b: Batch) -> np.ndarray:
+        """-> int32 (tracks, n, channels) holding 24-bit samples (libsndfile's float -> PCM_24 conversion)."""
+        torch = _torch()
+        with torch.cuda.stream(self.stream):
+            pcm = torch.empty((b.tracks, b.n, b.channels), dtype=torch.int32, device=self.tdev)
+            g = b.geom
+            _lib.check(self.lib.mm_dev_quantize_pcm24(self.ctx, C.byref(g), b.ptr, C.c_void_p(pcm.data_ptr())))
+            self.sync()
+            return pcm.cpu().numpy()
+
     def quantize_int16(self, b: Batch, noise: np.ndarray | None = None, seed: int = 0) -> np.ndarray:
         """-> int16 (tracks, n, channels); ``noise`` float32 of that shape selects the bit-exact mode."""
         torch = _torch()

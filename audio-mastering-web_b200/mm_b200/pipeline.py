@@ -547,16 +547,26 @@ def export_audio(samples: np.ndarray, sr: int, channels: int, out_format: str = 
     additive (bit-exact test hook): for TPDF the float32 dither buffer itself, for the shaped types the float32 uniforms
     ``np.random.rand(n, ch).astype(np.float32)`` the reference would have drawn (:843 / :864)."""
     if out_format.lower() != "wav":
-        raise NotImplementedError("only the WAV branch is on the hot path (codecs are host-side I/O, SURVEY L0)")
-    if auto_blank_sec:
-        raise NotImplementedError("auto_blank_sec is second-wave scope")
+        raise NotImplementedError("only the WAV branch is on the hot path (codecs are host-side I/O, SURVEY L0); "
+                                  "export_pcm24 hands 24-bit samples to a host FLAC encoder")
     eng, b, _ = _up(samples, sr)
+    if auto_blank_sec > 0:                                 # pipeline.py:976-977
+        b = eng.auto_blank_end(b, -50.0, auto_blank_sec)
     shape = {"ns_e": 1, "ns_itu": 2}.get(dither_type or "tpdf", 0)
     if shape and b.n >= (4 if shape == 1 else 8):         # shorter buffers: the reference falls back to TPDF (:840, :861)
         pcm = eng.quantize_int16_shaped(b, shape, uniform=noise, seed=seed)[0]
     else:
         pcm = eng.quantize_int16(b, noise=noise, seed=seed)[0]
     return wavio.pack_wav_pcm16(pcm, sr)
+
+
+def export_pcm24(samples: np.ndarray, sr: int, auto_blank_sec: float = 0.0) -> np.ndarray:
+    """The sample conversion of export_audio's FLAC branch (backend/app/pipeline.py:981-985: libsndfile PCM_24 from
+    float32 = clip, lrintf(x * 0x7FFFFF)) on the device -> int32 (n, channels) for a host-side FLAC encoder."""
+    eng, b, _ = _up(samples, sr)
+    if auto_blank_sec > 0:
+        b = eng.auto_blank_end(b, -50.0, auto_blank_sec)
+    return eng.quantize_pcm24(b)[0]
 
 
 def load_audio_from_bytes(data: bytes, fmt: str = "wav"):

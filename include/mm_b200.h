@@ -164,6 +164,12 @@ int mm_dev_iir(mm_ctx*, const mm_geom*, const float* in, float* out,
                const double* b, const double* a, int ncoef, int zero_phase);
 
 /* ---- export ---------------------------------------------------------------------------------*/
+/* _auto_blank_end (backend/app/pipeline.py:900-918): idx_dev[tracks] <- the last frame whose peak over the channels (after
+ * the +-1 clip of export_audio) exceeds threshold_lin, -1 if none; the caller keeps min(n, idx + 1 + int(sr * min_silence)) */
+int mm_dev_last_above(mm_ctx*, const mm_geom*, const float* in, double threshold_lin, int64_t* idx_dev);
+/* export_audio's FLAC branch (pipeline.py:981-985) hands float32 to libsndfile as PCM_24: clip, lrintf(x * 0x7FFFFF);
+ * interleaved int32 [tracks][n][ch] for a host-side encoder (parity unpinned: libsndfile is not available to compare) */
+int mm_dev_quantize_pcm24(mm_ctx*, const mm_geom*, const float* in, int32_t* out_interleaved);
 /* _write_wav_16bit_dithered quantiser  backend/app/pipeline.py:880-898
  * planar float rows -> interleaved int16 [tracks][n][ch].
  * noise: NULL -> TPDF from counter-based Philox4x32-10 keyed by (seed, track);

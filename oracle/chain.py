@@ -870,6 +870,38 @@ def dither_noise_shaped(uniform, kind):
     return (out * 0.9).astype(np.float32).reshape(white.shape)
 
 
+def auto_blank_end(samples, sr, threshold_dbfs=-60.0, min_silence_sec=0.5):
+    """pipeline.py:900-918: cut after the last frame whose peak over the channels exceeds the threshold, keeping
+    ``min_silence_sec`` of tail."""
+    if samples.size == 0 or min_silence_sec <= 0:
+        return samples
+    thr = 10 ** (threshold_dbfs / 20.0)
+    n_silence = int(sr * min_silence_sec)
+    if n_silence <= 0:
+        return samples
+    peak = np.max(np.abs(samples), axis=1) if samples.ndim > 1 else np.abs(samples)
+    above = np.nonzero(peak > thr)[0]
+    if above.size == 0:
+        return samples
+    return samples[: min(samples.shape[0], int(above[-1]) + 1 + n_silence)]
+
+
+def export_prepare(samples, sr, auto_blank_sec=0.0):
+    """Head of export_audio (pipeline.py:972-977): float32, 2-D, clip, optional trailing-silence cut at -50 dBFS."""
+    a = np.asarray(samples, dtype=np.float32)
+    if a.ndim == 1:
+        a = a.reshape(-1, 1)
+    a = np.clip(a, -1.0, 1.0)
+    return auto_blank_end(a, sr, -50.0, auto_blank_sec) if auto_blank_sec > 0 else a
+
+
+def quantize_pcm24(samples):
+    """What libsndfile does with float32 written as PCM_24 (FLAC branch, pipeline.py:981-985; flac.c f2flac24_array with
+    normalisation on): lrintf(x * 0x7FFFFF) in float32.  PARITY UNPINNED: libsndfile itself is not available here."""
+    a = np.clip(np.nan_to_num(np.asarray(samples, dtype=np.float32), nan=0.0), -1.0, 1.0)
+    return np.rint(a * np.float32(8388607.0)).astype(np.int32)
+
+
 def true_peak_dbfs(audio, sr=None):
     """routers/tools.py:44-54: 4x ``resample_poly`` then sample peak in dBFS."""
     audio = np.asarray(audio)

@@ -54,6 +54,14 @@ def main():
                                                      mode="warm", oversample=4),
     }
     st = {k: (np.asarray(v, dtype=np.float32) if isinstance(v, np.ndarray) else v) for k, v in st.items()}
+    # export_audio(auto_blank_sec=...) (pipeline.py:900-918, :976-977): trailing silence cut; kept lengths from the reference
+    tail = x.copy()
+    tail[17000:] *= np.float32(1e-4)                                     # below -50 dBFS after frame 17000
+    st["blank_input"] = tail
+    for name, sig, sec in (("blank_len_03", tail, 0.3), ("blank_len_mono_01", np.ascontiguousarray(tail[:, 0]), 0.1),
+                           ("blank_len_none", x, 0.2), ("blank_len_all_quiet", tail[17100:], 0.05)):
+        wav = P.export_audio(sig, sr, sig.ndim, "wav", auto_blank_sec=sec)
+        st[name] = np.int64((len(wav) - 44) // (2 * (sig.shape[1] if sig.ndim > 1 else 1)))
     path = os.path.join(HERE, "fft_stages.npz")
     np.savez_compressed(path, **st)
     print({k: np.shape(v) for k, v in st.items()}, "%.0f KB" % (os.path.getsize(path) / 1024))

@@ -183,3 +183,26 @@ def test_chain_modules_oversampled_exciter_and_multiband_imager(P):
     print(f"[parity] chain exciter(os=2) + imager(4 band): {e:.3e}")
     assert e <= 1e-6
     assert _err(P.apply_harmonic_exciter(x, sr, 2.0, "tape", 2), g["exciter_os2"]) <= RS_TOL
+
+
+def test_export_auto_blank_and_pcm24(P):
+    """export_audio(auto_blank_sec=...) cuts where the reference cuts (golden WAV sizes), the kept int16 frames equal the
+    uncut export's under the same dither buffer, and the PCM_24 hand-off equals lrintf(x * 0x7FFFFF)."""
+    from oracle import chain as oc
+    g = load_golden("fft_stages")
+    tail, x, sr = g["blank_input"], g["input"], int(g["sr"])
+    for name, sig, sec in (("blank_len_03", tail, 0.3), ("blank_len_mono_01", np.ascontiguousarray(tail[:, 0]), 0.1),
+                           ("blank_len_none", x, 0.2), ("blank_len_all_quiet", tail[17100:], 0.05)):
+        ch = 1 if sig.ndim == 1 else sig.shape[1]
+        wav = P.export_audio(sig, sr, ch, "wav", auto_blank_sec=sec)
+        assert (len(wav) - 44) // (2 * ch) == int(g[name]), name
+    keep = int(g["blank_len_mono_01"])
+    mono = np.ascontiguousarray(tail[:, 0])
+    noise = (np.random.default_rng(5).random((len(mono), 1)) + np.random.default_rng(6).random((len(mono), 1)) - 1.0).astype(np.float32)
+    cut = P.export_audio(mono, sr, 1, "wav", auto_blank_sec=0.1, noise=noise[:keep])
+    full = P.export_audio(mono, sr, 1, "wav", noise=noise)
+    assert cut[44:] == full[44:44 + 2 * keep]
+    loud = np.concatenate([x * np.float32(40.0), np.array([[np.nan, 1.0], [-1.0, 0.5]], dtype=np.float32)])
+    pcm = P.export_pcm24(loud, sr)
+    assert pcm.dtype == np.int32 and np.array_equal(pcm, oc.quantize_pcm24(loud))
+    assert P.export_pcm24(tail, sr, auto_blank_sec=0.1).shape[0] == keep

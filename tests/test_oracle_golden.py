@@ -123,6 +123,15 @@ def test_fft_class_stages_match_reference_golden():
     assert oc.resample_audio(x, 48000, 48000).dtype == np.float32
 
 
+def test_auto_blank_end_matches_reference_golden():
+    """export_audio(auto_blank_sec=...) (pipeline.py:900-918, :976-977): kept lengths from the reference's WAV sizes."""
+    g = load_golden("fft_stages")
+    tail, x, sr = g["blank_input"], g["input"], int(g["sr"])
+    for name, sig, sec in (("blank_len_03", tail, 0.3), ("blank_len_mono_01", np.ascontiguousarray(tail[:, 0]), 0.1),
+                           ("blank_len_none", x, 0.2), ("blank_len_all_quiet", tail[17100:], 0.05)):
+        assert oc.export_prepare(sig, sr, sec).shape[0] == int(g[name]), name
+
+
 def test_noise_shaped_dither_export_matches_reference_golden():
     """ns_e / ns_itu (pipeline.py:835-877): the oracle's shaping of the same uniforms + quantiser == the reference's WAV."""
     g = load_golden("pro_stages_48k")
