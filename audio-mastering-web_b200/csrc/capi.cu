@@ -644,6 +644,13 @@ int mm_dev_apply_rumble_filter(mm_ctx* c, const mm_geom* g, const float* in, flo
     return st_filtfilt_combine(c, g, p, in, out, e, none);
 }
 
+int mm_dev_apply_dynamic_eq(mm_ctx* c, const mm_geom* g, const float* in, float* out, int nbands, const double* params) {
+    MM_API_BEGIN(c);
+    MM_TRY(check_geom(g));
+    if (nbands < 0 || nbands > 64 || (nbands > 0 && !params)) { set_error("mm_dev_apply_dynamic_eq: 0..64 bands with 7 parameters each"); return 2; }
+    return st_dynamic_eq(c, g, in, out, nbands, params);
+}
+
 int mm_dev_apply_transient_designer(mm_ctx* c, const mm_geom* g, const float* in, float* out, double attack_gain, double sustain_gain) {
     MM_API_BEGIN(c);
     MM_TRY(check_geom(g));

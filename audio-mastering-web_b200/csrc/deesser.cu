@@ -17,6 +17,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <vector>
 
 #include "context.h"
 #include "stages_internal.h"
@@ -36,7 +37,13 @@ struct EnvArgs {
     long long chunk, halo; // multiples of 32 samples (one 128-byte line)
     int nchunks;           // per row
     float atk, one_m_atk, rel, one_m_rel;
+    float atk_lo, rel_lo;  // float64 coefficient = (atk + atk_lo): without the low part a float32-rounded release coefficient
+                           // biases a 4000-sample decay by up to 1e-4 of the envelope
     float thr, inv_ratio;
+    int mode;              // 0: de-esser gain, 1: dynamic-EQ band gain
+    float ratio, max_cut;
+    double d_atk, d_1matk, d_rel, d_1mrel;   // mode 1: float64 coefficients and products, float32 state (numba's arithmetic,
+                                             // pipeline.py:495-507): a float32 coefficient biases long release tails by ~1e-4
 };
 
 __device__ __forceinline__ float deess_gain(float env, float thr, float inv_ratio) {
@@ -46,10 +53,25 @@ __device__ __forceinline__ float deess_gain(float env, float thr, float inv_rati
     return fminf(fmaxf(g, 0.35f), 1.0f);
 }
 
+// apply_dynamic_eq (pipeline.py:1680-1689), float32 as numpy evaluates it: where(env > thr, clip((thr + (env - thr) / ratio)
+// / (env + 1e-12), max_cut, 1), 1), then clip(., 0.3, 1)
+__device__ __forceinline__ float dyneq_gain(float env, float thr, float ratio, float max_cut) {
+    float g = 1.0f;
+    if (env > thr) {
+        const float red = __fadd_rn(thr, __fdiv_rn(__fsub_rn(env, thr), ratio));
+        g = fminf(fmaxf(__fdiv_rn(red, __fadd_rn(env, 1e-12f)), max_cut), 1.0f);
+    }
+    return fminf(fmaxf(g, 0.3f), 1.0f);
+}
+
 __device__ __forceinline__ float env_step(float e, float v, const EnvArgs& P) {
     // max of the attack and the release update == the reference's branch on v > e (atk < rel)
-    const float a = fmaf(P.atk, e, P.one_m_atk * v);
-    const float r = fmaf(P.rel, e, P.one_m_rel * v);
+    if (P.mode) {
+        const double ed = (double)e, vd = (double)v;
+        return v > e ? (float)(P.d_atk * ed + P.d_1matk * vd) : (float)(P.d_rel * ed + P.d_1mrel * vd);
+    }
+    const float a = fmaf(P.atk, e, fmaf(P.atk_lo, e, P.one_m_atk * v));
+    const float r = fmaf(P.rel, e, fmaf(P.rel_lo, e, P.one_m_rel * v));
     return fmaxf(a, r);
 }
 
@@ -114,10 +136,10 @@ __global__ void __launch_bounds__(kEnvThreads) envelope_gain_kernel(const EnvArg
         for (int u = 0; u < 8; ++u) {
             const float4 v = *reinterpret_cast<const float4*>(s + 4 * (u ^ sx));
             float4 g;
-            e = env_step(e, fabsf(v.x), P); g.x = deess_gain(e, P.thr, P.inv_ratio);
-            e = env_step(e, fabsf(v.y), P); g.y = deess_gain(e, P.thr, P.inv_ratio);
-            e = env_step(e, fabsf(v.z), P); g.z = deess_gain(e, P.thr, P.inv_ratio);
-            e = env_step(e, fabsf(v.w), P); g.w = deess_gain(e, P.thr, P.inv_ratio);
+            e = env_step(e, fabsf(v.x), P); g.x = P.mode ? dyneq_gain(e, P.thr, P.ratio, P.max_cut) : deess_gain(e, P.thr, P.inv_ratio);
+            e = env_step(e, fabsf(v.y), P); g.y = P.mode ? dyneq_gain(e, P.thr, P.ratio, P.max_cut) : deess_gain(e, P.thr, P.inv_ratio);
+            e = env_step(e, fabsf(v.z), P); g.z = P.mode ? dyneq_gain(e, P.thr, P.ratio, P.max_cut) : deess_gain(e, P.thr, P.inv_ratio);
+            e = env_step(e, fabsf(v.w), P); g.w = P.mode ? dyneq_gain(e, P.thr, P.ratio, P.max_cut) : deess_gain(e, P.thr, P.inv_ratio);
             const long long i = i0 + 4 * u;
             if (i + 3 < P.n) *reinterpret_cast<float4*>(dst + i) = g;
             else {
@@ -205,6 +227,134 @@ __global__ void __launch_bounds__(kApplyThreads) deesser_apply_kernel(const Appl
     }
 }
 
+// follower launch shared by the de-esser and the dynamic EQ: chunking from the slower of the two time constants
+static int launch_envelope(mm_ctx* c, const mm_geom* g, EnvArgs& A, double attack_ms, double release_ms, const char* name) {
+    const int rows = g->tracks * g->channels;
+    A.n = g->n; A.stride = g->stride; A.rows = rows;
+    // pipeline.py:509-518: coef = exp(-1 / max(1e-6, sr * t)); Python floats, float32 state
+    const double atk = std::exp(-1.0 / std::max(1e-6, (double)g->sr * (attack_ms / 1000.0)));
+    const double rel = std::exp(-1.0 / std::max(1e-6, (double)g->sr * (release_ms / 1000.0)));
+    A.atk = (float)atk; A.one_m_atk = (float)(1.0 - atk);
+    A.rel = (float)rel; A.one_m_rel = (float)(1.0 - rel);
+    A.atk_lo = (float)(atk - (double)A.atk); A.rel_lo = (float)(rel - (double)A.rel);
+    A.d_atk = atk; A.d_1matk = 1.0 - atk; A.d_rel = rel; A.d_1mrel = 1.0 - rel;
+    const double slow = std::max(atk, rel);
+    const long long nceil = ((g->n + 31) / 32) * 32;
+    long long halo = slow < 1.0 ? (long long)std::ceil(17.5 / -std::log(slow)) : nceil;
+    halo = std::min<long long>(((halo + 31) / 32) * 32, nceil);
+    A.halo = halo;
+    // chunk = halo / 2 (three times the work, short critical path) until the grid exceeds ~8 warps per SM
+    long long chunk = std::max<long long>(((halo / 2 + 31) / 32) * 32, 4096);
+    while ((long long)rows * ((g->n + chunk - 1) / chunk) > 148LL * 8 * 32 && chunk < nceil) chunk *= 2;
+    A.chunk = chunk;
+    A.nchunks = (int)((g->n + A.chunk - 1) / A.chunk);
+    const long long total = (long long)rows * A.nchunks;
+    KernelScope ks(c, name);
+    envelope_gain_kernel<<<(unsigned)((total + kEnvThreads - 1) / kEnvThreads), kEnvThreads, 0, c->stream>>>(A);
+    MM_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// out = x - band + band * gain (float32, numpy's order), optional final clip (pipeline.py:1690, :1696)
+__global__ void __launch_bounds__(256) dyneq_apply_kernel(const float* x, const float* band, const float* gain, float* out, long long n,
+                                                         long long stride, int clip) {
+    const size_t ro = (size_t)blockIdx.y * (size_t)stride + kLead;
+    const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (i >= n) return;
+    if (i + 3 < n) {
+        const float4 xv = *reinterpret_cast<const float4*>(x + ro + i), bv = *reinterpret_cast<const float4*>(band + ro + i);
+        const float4 gv = *reinterpret_cast<const float4*>(gain + ro + i);
+        float4 r;
+        r.x = __fadd_rn(__fsub_rn(xv.x, bv.x), __fmul_rn(bv.x, gv.x));
+        r.y = __fadd_rn(__fsub_rn(xv.y, bv.y), __fmul_rn(bv.y, gv.y));
+        r.z = __fadd_rn(__fsub_rn(xv.z, bv.z), __fmul_rn(bv.z, gv.z));
+        r.w = __fadd_rn(__fsub_rn(xv.w, bv.w), __fmul_rn(bv.w, gv.w));
+        if (clip) {
+            r.x = fminf(fmaxf(r.x, -1.f), 1.f); r.y = fminf(fmaxf(r.y, -1.f), 1.f);
+            r.z = fminf(fmaxf(r.z, -1.f), 1.f); r.w = fminf(fmaxf(r.w, -1.f), 1.f);
+        }
+        *reinterpret_cast<float4*>(out + ro + i) = r;
+    } else {
+        for (int c = 0; c < 4 && i + c < n; ++c) {
+            const float xs = x[ro + i + c], b = band[ro + i + c];
+            float r = __fadd_rn(__fsub_rn(xs, b), __fmul_rn(b, gain[ro + i + c]));
+            if (clip) r = fminf(fmaxf(r, -1.f), 1.f);
+            out[ro + i + c] = r;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) clip_rows_kernel(const float* in, float* out, long long n, long long stride) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        const size_t o = (size_t)blockIdx.y * (size_t)stride + kLead + i;
+        out[o] = fminf(fmaxf(in[o], -1.f), 1.f);
+    }
+}
+
+// apply_dynamic_eq (backend/app/pipeline.py:1628-1700): per band a zero-phase peaking section (scipy.signal.iirpeak with the
+// reference's arguments), the attack/release follower of |band|, a downward gain above the threshold, x - band + band * g;
+// bands run one after the other on the running signal.  params[b] = {w0, bw, threshold_db, ratio, attack_ms, release_ms,
+// max_cut_db} with w0, bw already clipped as the reference does (:1657-1658).  A band whose section is unstable -- which is
+// what the reference's bandwidth-in-the-Q-slot call yields for every default band -- is refused: its exponentially growing
+// filtfilt output (zeroed / patched by the reference) is not a parity target.
+int st_dynamic_eq(mm_ctx* c, const mm_geom* g, const float* in, float* out, int nbands, const double* params) {
+    const int rows = g->tracks * g->channels;
+    const size_t bytes = (size_t)rows * (size_t)g->stride * sizeof(float);
+    std::vector<const FilterPlan*> plans;
+    for (int b = 0; b < nbands; ++b) {
+        const double* q = params + 7 * b;
+        Ba ba;
+        if (!iirpeak(q[0], q[1], &ba)) { set_error("apply_dynamic_eq: band %d: iirpeak(%g, %g) is not a valid design", b, q[0], q[1]); return 3; }
+        const double a1 = ba.a[1], a2 = ba.a[2];
+        if (!(std::fabs(a2) < 1.0 && std::fabs(a1) < 1.0 + a2)) {
+            set_error("apply_dynamic_eq: band %d: iirpeak(w0=%g, Q=%g) is an unstable section (a = [1, %g, %g]); the reference passes "
+                      "a bandwidth where scipy expects Q (pipeline.py:1661-1663)", b, q[0], q[1], a1, a2);
+            return 3;
+        }
+        const FilterPlan* p = get_plan(c, ba, PREC_F64);
+        if (!p) return 1;
+        if (g->n <= p->pad) { set_error("apply_dynamic_eq: %lld frames is not longer than filtfilt's padlen %d", (long long)g->n, p->pad); return 1; }
+        plans.push_back(p);
+    }
+    Bufs B;
+    MM_TRY(get_bufs(c, g, &B));
+    float* sc = B.T[1];
+    float* gain = B.T[2];
+    const float* cur = in;
+    for (int b = 0; b < nbands; ++b) {
+        const double* q = params + 7 * b;
+        const FilterPlan* p[1] = {plans[b]};
+        const float* i1[1] = {cur};
+        float* o1[1] = {B.E[0]};
+        Pro none;
+        MM_TRY(sweep_fwd(c, g, 1, 1, p, i1, o1, none, plans[b]->pad));
+        const float* i2[1] = {B.E[0]};
+        float* o2[1] = {sc};
+        Epi store;
+        MM_TRY(sweep_bwd(c, g, 1, p, i2, o2, 1, store, plans[b]->pad));
+        EnvArgs A;
+        memset(&A, 0, sizeof(A));
+        A.sc = sc; A.gain = gain; A.mode = 1;
+        A.thr = (float)std::pow(10.0, q[2] / 20.0);
+        A.ratio = (float)q[3];
+        A.max_cut = (float)std::pow(10.0, q[6] / 20.0);
+        MM_TRY(launch_envelope(c, g, A, q[4], q[5], "dyneq_envelope_gain"));
+        KernelScope ks(c, "dyneq_apply");
+        dyneq_apply_kernel<<<dim3((unsigned)((g->n + 1023) / 1024), (unsigned)rows), 256, 0, c->stream>>>(cur, sc, gain, out, g->n, g->stride,
+                                                                                                         b == nbands - 1);
+        MM_CUDA(cudaGetLastError());
+        cur = out;
+    }
+    if (nbands == 0) {                               // every band skipped: clip(input) (pipeline.py:1696)
+        (void)bytes;
+        KernelScope ks(c, "dyneq_clip");
+        clip_rows_kernel<<<dim3((unsigned)((g->n + 255) / 256), (unsigned)rows), 256, 0, c->stream>>>(in, out, g->n, g->stride);
+        MM_CUDA(cudaGetLastError());
+    }
+    return 0;
+}
+
 int st_deesser(mm_ctx* c, const mm_geom* g, const float* in, float* out, double threshold_db, double ratio, double freq_lo,
                double freq_hi, double attack_ms, double release_ms) {
     const double nyq = g->sr / 2.0;
@@ -236,28 +386,10 @@ int st_deesser(mm_ctx* c, const mm_geom* g, const float* in, float* out, double 
     {
         EnvArgs A;
         memset(&A, 0, sizeof(A));
-        A.sc = sc; A.gain = gain; A.n = g->n; A.stride = g->stride; A.rows = rows;
-        // pipeline.py:509-518: coef = exp(-1 / max(1e-6, sr * t)); Python floats, float32 state
-        const double atk = std::exp(-1.0 / std::max(1e-6, (double)g->sr * (attack_ms / 1000.0)));
-        const double rel = std::exp(-1.0 / std::max(1e-6, (double)g->sr * (release_ms / 1000.0)));
-        A.atk = (float)atk; A.one_m_atk = (float)(1.0 - atk);
-        A.rel = (float)rel; A.one_m_rel = (float)(1.0 - rel);
+        A.sc = sc; A.gain = gain;
         A.thr = (float)std::pow(10.0, threshold_db / 20.0);
         A.inv_ratio = (float)(1.0 / ratio);
-        const double slow = std::max(atk, rel);
-        const long long nceil = ((g->n + 31) / 32) * 32;
-        long long halo = slow < 1.0 ? (long long)std::ceil(17.5 / -std::log(slow)) : nceil;
-        halo = std::min<long long>(((halo + 31) / 32) * 32, nceil);
-        A.halo = halo;
-        // chunk = halo / 2 (three times the work, short critical path) until the grid exceeds ~8 warps per SM
-        long long chunk = std::max<long long>(((halo / 2 + 31) / 32) * 32, 4096);
-        while ((long long)rows * ((g->n + chunk - 1) / chunk) > 148LL * 8 * 32 && chunk < nceil) chunk *= 2;
-        A.chunk = chunk;
-        A.nchunks = (int)((g->n + A.chunk - 1) / A.chunk);
-        const long long total = (long long)rows * A.nchunks;
-        KernelScope ks(c, "envelope_gain");
-        envelope_gain_kernel<<<(unsigned)((total + kEnvThreads - 1) / kEnvThreads), kEnvThreads, 0, c->stream>>>(A);
-        MM_CUDA(cudaGetLastError());
+        MM_TRY(launch_envelope(c, g, A, attack_ms, release_ms, "envelope_gain"));
     }
     {
         ApplyArgs A;

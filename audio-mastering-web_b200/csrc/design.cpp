@@ -115,6 +115,21 @@ static void state_matrices(const Ba& f, long double* A, long double* B) {
     }
 }
 
+bool iirpeak(double w0, double Q, Ba* out) {
+    if (!(w0 > 0.0 && w0 < 1.0) || !(Q > 0.0)) return false;
+    const double pi = 3.14159265358979323846;
+    const double bw = (w0 / Q) * pi, w = w0 * pi;
+    const double gb = 1.0 / std::sqrt(2.0);
+    const double beta = (std::sqrt(1.0 - gb * gb) / gb) * std::tan(bw / 2.0);
+    const double gain = 1.0 / (1.0 + beta);
+    Ba f;
+    f.m = 2;
+    f.b[0] = 1.0 - gain; f.b[1] = 0.0; f.b[2] = -(1.0 - gain);
+    f.a[0] = 1.0; f.a[1] = -2.0 * gain * std::cos(w); f.a[2] = 2.0 * gain - 1.0;
+    *out = f;
+    return true;
+}
+
 bool lfilter_zi(const Ba& f, double* zi) {
     const int m = f.m;
     long double A[kMaxOrder * kMaxOrder], B[kMaxOrder], I_A[kMaxOrder * kMaxOrder];

@@ -22,6 +22,9 @@ enum BType { kLow = 0, kHigh = 1, kBand = 2 };
 
 // scipy.signal.butter(order, wn, btype, analog=False, output="ba"); wn normalised to Nyquist.
 bool butter(int order, BType bt, const double* wn, Ba* out);
+// scipy.signal.iirpeak(w0, Q) (fs = 2): bandwidth w0 / Q, -3 dB gain; b = (1 - g) [1, 0, -1], a = [1, -2 g cos(pi w0), 2 g - 1]
+// with g = 1 / (1 + tan(pi w0 / (2 Q))).  Returns false outside 0 < w0 < 1.
+bool iirpeak(double w0, double Q, Ba* out);
 // scipy.signal.lfilter_zi(b, a): steady-state DF2T state of the unit step response.
 bool lfilter_zi(const Ba& f, double* zi);
 // _build_linear_phase_ir (backend/app/pipeline.py:187-217): the magnitude of the target curve HP*LP*(1 + (gp-1) Hpres +

@@ -96,6 +96,8 @@ int st_haas_imager(mm_ctx* c, const mm_geom* g, const float* in, float* out, dou
 // analyzers.cu / deesser.cu
 int st_deesser(mm_ctx* c, const mm_geom* g, const float* in, float* out, double threshold_db, double ratio, double freq_lo,
                double freq_hi, double attack_ms, double release_ms);
+// deesser.cu: apply_dynamic_eq over nbands x {w0, bw, threshold_db, ratio, attack_ms, release_ms, max_cut_db}; in == out allowed
+int st_dynamic_eq(mm_ctx* c, const mm_geom* g, const float* in, float* out, int nbands, const double* params);
 int st_true_peak(mm_ctx* c, const mm_geom* g, const float* in, double* tp_dev);
 int st_spectrum_bars(mm_ctx* c, const mm_geom* g, const float* in, int view, double* bars_dev);
 int st_correlation(mm_ctx* c, const mm_geom* g, const float* in, double* corr_dev, double* peak_dev);

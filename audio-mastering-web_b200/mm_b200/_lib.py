@@ -85,6 +85,7 @@ SIGNATURES = {
     "mm_dev_master": (_i, [_vp, _gp, _i, C.POINTER(Style), _vp, _vp, _vp, _vp, _u64, _vp, _u32]),
     "mm_dev_apply_target_curve_linear_phase": (_i, [_vp, _gp, _vp, _vp, _i]),
     "mm_design_linear_phase_ir": (_i, [_i, _i, _vp]),
+    "mm_dev_apply_dynamic_eq": (_i, [_vp, _gp, _vp, _vp, _i, _vp]),
     "mm_dev_fft_resample": (_i, [_vp, _gp, _vp, _gp, _vp]),
     "mm_dev_apply_spectral_denoise": (_i, [_vp, _gp, _vp, _vp, _d, _d]),
     "mm_dev_spectral_envelope": (_i, [_vp, _gp, _vp, _vp]),

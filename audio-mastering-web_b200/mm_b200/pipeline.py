@@ -245,6 +245,44 @@ def apply_maximizer_transient_aware(audio: np.ndarray, sr: int, sensitivity: flo
     return _stage("apply_maximizer_transient_aware", audio, sr, C.c_double(float(sensitivity)))
 
 
+# backend/app/pipeline.py:1616-1625
+DYNAMIC_EQ_MASTERING_BANDS = [
+    {"freq": 120, "q": 1.0, "threshold_db": -14, "ratio": 2.0, "attack_ms": 10, "release_ms": 100, "max_cut_db": -4},
+    {"freq": 250, "q": 1.2, "threshold_db": -12, "ratio": 2.5, "attack_ms": 8, "release_ms": 80, "max_cut_db": -5},
+    {"freq": 400, "q": 1.0, "threshold_db": -12, "ratio": 2.0, "attack_ms": 8, "release_ms": 80, "max_cut_db": -4},
+    {"freq": 800, "q": 1.2, "threshold_db": -12, "ratio": 2.0, "attack_ms": 5, "release_ms": 60, "max_cut_db": -4},
+    {"freq": 2500, "q": 1.4, "threshold_db": -12, "ratio": 2.5, "attack_ms": 5, "release_ms": 60, "max_cut_db": -5},
+    {"freq": 5000, "q": 1.4, "threshold_db": -14, "ratio": 3.0, "attack_ms": 3, "release_ms": 50, "max_cut_db": -6},
+    {"freq": 8000, "q": 1.2, "threshold_db": -16, "ratio": 4.0, "attack_ms": 2, "release_ms": 40, "max_cut_db": -8},
+    {"freq": 12000, "q": 0.8, "threshold_db": -18, "ratio": 2.0, "attack_ms": 5, "release_ms": 60, "max_cut_db": -4},
+]
+
+
+def apply_dynamic_eq(audio: np.ndarray, sr: int, bands=None) -> np.ndarray:
+    """backend/app/pipeline.py:1628-1700: per band a zero-phase ``iirpeak`` section, the attack/release follower of the band,
+    a downward gain above the threshold, ``x - band + band * g``; bands act one after the other.
+
+    The reference hands ``scipy.signal.iirpeak`` a *bandwidth* in its ``Q`` slot (:1661-1663), so a band is a stable section
+    only for ``q < 1`` (roughly); every band of ``DYNAMIC_EQ_MASTERING_BANDS`` is UNSTABLE and the reference's output for
+    them is overflow debris that it zeroes or patches with its input.  Stable bands run on the device with the reference's
+    arithmetic; an unstable band raises ``MMError`` naming it instead of reproducing garbage."""
+    if bands is None:
+        bands = DYNAMIC_EQ_MASTERING_BANDS
+    nyq = sr / 2.0
+    rows = []
+    for band in bands:
+        freq = float(band.get("freq", 1000))
+        q = float(band.get("q", 1.4))
+        if freq <= 0 or freq >= nyq * 0.98:
+            continue
+        w0 = float(np.clip(freq / nyq, 0.001, 0.98))
+        bw = float(np.clip(w0 / max(q, 0.1), 0.001, 0.5))
+        rows.append([w0, bw, float(band.get("threshold_db", -12)), float(band.get("ratio", 3.0)), float(band.get("attack_ms", 5)),
+                     float(band.get("release_ms", 80)), float(band.get("max_cut_db", -6))])
+    flat = _lib.darr([v for r in rows for v in r]) if rows else None
+    return _stage("apply_dynamic_eq", audio, sr, len(rows), flat)
+
+
 HIGH_FREQ_TRIM_CROSSOVER_HZ = 5000.0
 HIGH_FREQ_TRIM_GAIN = 0.9
 

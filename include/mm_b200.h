@@ -148,6 +148,10 @@ int mm_dev_apply_reverb(mm_ctx*, const mm_geom*, const float* in, float* out, in
  * to 2^27 combined points): resample_audio (backend/app/pipeline.py:920-936), the oversampled exciter (:1294-1320), a
  * reference track at another rate (:1581-1584).  gout has the same tracks / channels; gin->n != gout->n; not in place */
 int mm_dev_fft_resample(mm_ctx*, const mm_geom* gin, const float* in, const mm_geom* gout, float* out);
+/* apply_dynamic_eq (backend/app/pipeline.py:1628-1700): params[nbands][7] = {w0, bw, threshold_db, ratio, attack_ms,
+ * release_ms, max_cut_db}, w0 / bw as the reference clips them (:1657-1658) and hands them to scipy.signal.iirpeak(w0, bw).
+ * Returns 3 when a band's section is unstable (every default band of the reference is: it passes a bandwidth as Q) */
+int mm_dev_apply_dynamic_eq(mm_ctx*, const mm_geom*, const float* in, float* out, int nbands, const double* params);
 /* apply_spectral_denoise (backend/app/pipeline.py:1472-1524): 2048/512 STFT (scipy.signal.stft conventions), per-bin
  * percentile noise floor over the frames capped by 0.85 x the median, Wiener gain clipped to [0.25, 1], inverse STFT, clip.
  * n >= 2048 (the reference's scipy call raises below that); strength < 0.01 is a bypass */

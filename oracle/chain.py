@@ -579,6 +579,36 @@ def apply_maximizer_transient_aware(audio, sr, sensitivity=0.5):
     return _uncols(np.clip(limited, -1.0, 1.0).astype(np.float32), mono)
 
 
+def apply_dynamic_eq(audio, sr, bands):
+    """pipeline.py:1628-1700 for explicitly given bands (the reference's default bands are unstable sections: see
+    tests/test_host_design.py).  ``sg.iirpeak(w0, bw)`` is called with the reference's own (bandwidth-as-Q) arguments."""
+    a, mono = _cols(audio)
+    nyq = sr / 2.0
+    out = a.copy().astype(np.float32)
+    for band in bands:
+        freq, q = float(band.get("freq", 1000)), float(band.get("q", 1.4))
+        thr = 10 ** (float(band.get("threshold_db", -12)) / 20.0)
+        ratio = float(band.get("ratio", 3.0))
+        atk, rel = float(band.get("attack_ms", 5)) / 1000.0, float(band.get("release_ms", 80)) / 1000.0
+        max_cut = 10 ** (float(band.get("max_cut_db", -6)) / 20.0)
+        if freq <= 0 or freq >= nyq * 0.98:
+            continue
+        w0 = float(np.clip(freq / nyq, 0.001, 0.98))
+        bw = float(np.clip(w0 / max(q, 0.1), 0.001, 0.5))
+        bb, aa = sg.iirpeak(w0, bw)
+        for ch in range(a.shape[1]):
+            x = out[:, ch].copy()
+            bs = np.nan_to_num(zero_phase(bb, aa, x.astype(np.float64)).astype(np.float32), nan=0.0, posinf=0.0, neginf=0.0)
+            env = np.nan_to_num(envelope_follower(np.abs(bs), float(sr), atk, rel), nan=0.0, posinf=0.0, neginf=0.0)
+            g = np.where(env > thr, np.clip((thr + (env - thr) / ratio) / (env + 1e-12), max_cut, 1.0), 1.0).astype(np.float32)
+            g = np.clip(np.nan_to_num(g, nan=1.0, posinf=1.0, neginf=1.0), 0.3, 1.0)
+            out[:, ch] = x - bs + bs * g
+    bad = ~np.isfinite(out)
+    if np.any(bad):
+        out = np.where(bad, a.astype(np.float32), out)
+    return _uncols(np.clip(out, -1.0, 1.0).astype(np.float32), mono)
+
+
 def apply_high_freq_trim(audio, sr, crossover_hz=5000.0, high_gain=0.9):
     """pipeline.py:1705-1733: low = filtfilt(butter(2, fc)), out = low + high_gain * (x - low), clip."""
     if abs(high_gain - 1.0) < 0.001:

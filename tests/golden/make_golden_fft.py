@@ -54,6 +54,15 @@ def main():
                                                      mode="warm", oversample=4),
     }
     st = {k: (np.asarray(v, dtype=np.float32) if isinstance(v, np.ndarray) else v) for k, v in st.items()}
+    # apply_dynamic_eq (pipeline.py:1628-1700) with STABLE bands (q < 1: the reference's iirpeak(w0, bw) call is a stable
+    # section only then; its default bands are not -- tests/test_host_design.py)
+    st["dyneq_bands"] = np.array([[3000, 0.5, -30, 3.0, 5, 60, -6], [6000, 0.7, -34, 4.0, 2, 40, -8], [200, 0.3, -28, 2.0, 10, 100, -4],
+                                  [23900, 0.5, -20, 2.0, 5, 50, -3]], dtype=np.float64)      # the last one is skipped (>= 0.98 nyq)
+    keys = ("freq", "q", "threshold_db", "ratio", "attack_ms", "release_ms", "max_cut_db")
+    bands = [dict(zip(keys, row)) for row in st["dyneq_bands"]]
+    st["dyneq_stereo"] = P.apply_dynamic_eq(x * np.float32(3.0), sr, bands)
+    st["dyneq_mono"] = P.apply_dynamic_eq(np.ascontiguousarray(x[:9001, 0]) * np.float32(2.0), sr, bands[:2])
+    st["dyneq_skipped"] = P.apply_dynamic_eq(x * np.float32(30.0), sr, bands[3:])
     # export_audio(auto_blank_sec=...) (pipeline.py:900-918, :976-977): trailing silence cut; kept lengths from the reference
     tail = x.copy()
     tail[17000:] *= np.float32(1e-4)                                     # below -50 dBFS after frame 17000

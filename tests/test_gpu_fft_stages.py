@@ -206,3 +206,32 @@ def test_export_auto_blank_and_pcm24(P):
     pcm = P.export_pcm24(loud, sr)
     assert pcm.dtype == np.int32 and np.array_equal(pcm, oc.quantize_pcm24(loud))
     assert P.export_pcm24(tail, sr, auto_blank_sec=0.1).shape[0] == keep
+
+
+def test_dynamic_eq_stable_bands_against_reference_golden(P):
+    """apply_dynamic_eq (pipeline.py:1628-1700): float64 zero-phase peaking sections + the float32 follower / gain arithmetic
+    of numpy; an unstable band (all of the reference's defaults) is refused by name."""
+    from test_oracle_golden import dyneq_cases
+    from mm_b200._lib import MMError
+    g = load_golden("fft_stages")
+    for k, call in dyneq_cases(P, g).items():
+        out = call()
+        e = _err(out, g[k])
+        print(f"[parity] {k}: {e:.3e}")
+        assert out.shape == g[k].shape and out.dtype == np.float32 and e <= 1e-5, (k, e)   # |x| up to 3.8: a few float32 ulps over three bands
+    with pytest.raises(MMError, match="unstable"):
+        P.apply_dynamic_eq(g["input"], int(g["sr"]))
+    assert len(P.DYNAMIC_EQ_MASTERING_BANDS) == 8
+
+
+def test_dynamic_eq_long_against_oracle(P):
+    from oracle import chain as oc
+    sr, n = 44100, 20 * 44100
+    x = (_material(n, sr, 21) * np.float32(1.5)).astype(np.float32)
+    bands = [{"freq": 150, "q": 0.4, "threshold_db": -30, "ratio": 3.0, "attack_ms": 10, "release_ms": 120, "max_cut_db": -6},
+             {"freq": 4000, "q": 0.6, "threshold_db": -36, "ratio": 4.0, "attack_ms": 2, "release_ms": 40, "max_cut_db": -9}]
+    out = P.apply_dynamic_eq(x, sr, bands)
+    ref = oc.apply_dynamic_eq(x, sr, bands)
+    e = _err(out, ref)
+    print(f"[parity] dynamic eq 20 s: {e:.3e}")
+    assert e <= 5e-6 and _err(ref, np.clip(x, -1, 1)) > 1e-2

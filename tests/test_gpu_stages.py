@@ -276,3 +276,20 @@ def test_reference_match_against_reference_golden(gpu_lib):
     assert np.array_equal(P.compute_spectral_envelope(loud[:1000], sr), np.ones(4097, dtype=np.float32))
     out = P.run_mastering_pipeline(loud, sr, reference_audio=ref, reference_sr=sr, reference_strength=0.5)
     assert out.shape == loud.shape and np.all(np.isfinite(out))
+
+
+def test_deesser_long_release_tails_against_oracle(P):
+    """Sibilant bursts followed by 85 ms release tails above the threshold: the follower's release coefficient must not be
+    rounded to float32 on its own (a 4000-sample decay would drift by 1e-4 of the envelope)."""
+    from oracle import chain as oc
+    sr, n = 48000, 96000
+    t = np.arange(n) / sr
+    rng = np.random.default_rng(8)
+    burst = ((np.arange(n) % 12000) < 1500).astype(np.float64)
+    x = (0.9 * burst * np.sin(2 * np.pi * 7000.0 * t) + 0.2 * np.sin(2 * np.pi * 6500.0 * t) + 0.01 * rng.standard_normal(n))
+    x = np.stack([x, 0.8 * x], axis=1).astype(np.float32)
+    out = P.apply_deesser(x, sr, threshold_db=-24.0)
+    ref = oc.apply_deesser(x, sr, threshold_db=-24.0)
+    e = _err(out, ref)
+    print(f"[parity] deesser bursts + tails: {e:.3e}")
+    assert e <= TIGHT and _err(ref, x) > 1e-2

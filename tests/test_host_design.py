@@ -277,7 +277,7 @@ def test_balanced_realization_float32_pass2(lib, design, tol):
 
 
 def test_reference_dynamic_eq_default_bands_are_unstable():
-    """Why mm_b200 does not offer apply_dynamic_eq: the reference calls ``sg.iirpeak(w0, bw)`` with a
+    """Why mm_b200 refuses the DEFAULT bands of apply_dynamic_eq: the reference calls ``sg.iirpeak(w0, bw)`` with a
     bandwidth in the Q slot (backend/app/pipeline.py:1659-1663); for all eight default bands (:1616-1625) that is an
     unstable section at 44.1 and 48 kHz."""
     bands = [(120, 1.0), (250, 1.2), (400, 1.0), (800, 1.2), (2500, 1.4), (5000, 1.4), (8000, 1.2), (12000, 0.8)]

@@ -123,6 +123,26 @@ def test_fft_class_stages_match_reference_golden():
     assert oc.resample_audio(x, 48000, 48000).dtype == np.float32
 
 
+def dyneq_cases(mod, g):
+    x, sr = g["input"], int(g["sr"])
+    keys = ("freq", "q", "threshold_db", "ratio", "attack_ms", "release_ms", "max_cut_db")
+    bands = [dict(zip(keys, row)) for row in g["dyneq_bands"]]
+    return {"dyneq_stereo": lambda: mod.apply_dynamic_eq(x * np.float32(3.0), sr, bands),
+            "dyneq_mono": lambda: mod.apply_dynamic_eq(np.ascontiguousarray(x[:9001, 0]) * np.float32(2.0), sr, bands[:2]),
+            "dyneq_skipped": lambda: mod.apply_dynamic_eq(x * np.float32(30.0), sr, bands[3:])}
+
+
+def test_dynamic_eq_stable_bands_match_reference_golden():
+    """apply_dynamic_eq (pipeline.py:1628-1700) with bands whose iirpeak(w0, bw) section is stable (q < 1)."""
+    g = load_golden("fft_stages")
+    for k, call in dyneq_cases(oc, g).items():
+        v = call()
+        assert v.shape == g[k].shape and v.dtype == np.float32, k
+        assert np.max(np.abs(v.astype(np.float64) - g[k])) <= 1e-7, k
+    # the gain engages: the result differs from the merely clipped input
+    assert np.max(np.abs(g["dyneq_stereo"] - np.clip(g["input"] * np.float32(3.0), -1, 1))) > 1e-2
+
+
 def test_auto_blank_end_matches_reference_golden():
     """export_audio(auto_blank_sec=...) (pipeline.py:900-918, :976-977): kept lengths from the reference's WAV sizes."""
     g = load_golden("fft_stages")
