@@ -56,21 +56,22 @@ struct BigFftCache {
     std::vector<std::string> order;
 };
 
-static std::map<mm_ctx*, BigFftCache>& caches() {
-    static std::map<mm_ctx*, BigFftCache> m;
-    return m;
+static BigFftCache& cache_of(mm_ctx* c) {
+    if (!c->bigfft) c->bigfft = new BigFftCache;
+    return *static_cast<BigFftCache*>(c->bigfft);
 }
 
 void bigfft_release(mm_ctx* c) {
-    auto it = caches().find(c);
-    if (it == caches().end()) return;
-    for (auto& kv : it->second.ffts) {
+    if (!c->bigfft) return;
+    BigFftCache* cache = static_cast<BigFftCache*>(c->bigfft);
+    for (auto& kv : cache->ffts) {
         for (int i = 0; i < 4; ++i) cudaFree(kv.second->twR[i]);
         cudaFree(kv.second->tlo);
         cudaFree(kv.second->thi);
     }
-    for (auto& kv : it->second.chirps) cudaFree(kv.second.FW);
-    caches().erase(it);
+    for (auto& kv : cache->chirps) cudaFree(kv.second.FW);
+    delete cache;
+    c->bigfft = nullptr;
 }
 
 // e^{sign i pi j^2 / N} to float32 accuracy: j^2 mod 2N exactly (Barrett reduction with m = floor(2^64 / 2N)), the phase
@@ -291,7 +292,7 @@ static int bf_run(mm_ctx* c, const BigFft* F, float2* data, long long pitch, int
 }
 
 static int bf_get_fft(mm_ctx* c, int p, BigFft** out) {
-    auto& cache = caches()[c];
+    auto& cache = cache_of(c);
     auto it = cache.ffts.find(p);
     if (it != cache.ffts.end()) { *out = it->second.get(); return 0; }
     std::unique_ptr<BigFft> F(new BigFft);
@@ -334,7 +335,7 @@ __global__ void bf_scale_kernel(float2* w, long long L, float s) {
 }
 
 static int bf_get_chirp(mm_ctx* c, long long N, long long nin, long long nout, int sign, const ChirpPlan** out) {
-    auto& cache = caches()[c];
+    auto& cache = cache_of(c);
     char key[96];
     snprintf(key, sizeof key, "%lld/%lld/%lld/%d", N, nin, nout, sign);
     auto it = cache.chirps.find(key);

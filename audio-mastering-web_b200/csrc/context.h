@@ -94,6 +94,7 @@ struct mm_ctx {
     std::vector<mm::KTime> ktimes;
     std::map<std::string, std::pair<double, int64_t>> kacc;
     int64_t workspace_bytes = 0;
+    void* bigfft = nullptr;             // bigfft.cu's plan cache (FFT tables, chirp-filter spectra); owned by the context: contexts are per thread
 };
 
 namespace mm {
