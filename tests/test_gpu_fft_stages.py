@@ -235,3 +235,34 @@ def test_dynamic_eq_long_against_oracle(P):
     e = _err(out, ref)
     print(f"[parity] dynamic eq 20 s: {e:.3e}")
     assert e <= 5e-6 and _err(ref, np.clip(x, -1, 1)) > 1e-2
+
+
+def test_fft_stages_from_concurrent_threads(P):
+    """SURVEY 8b threading: the job functions run in up to three asyncio.to_thread workers.  Every thread has its own engine
+    (stream, workspace, FFT plan cache); concurrent calls return bit for bit what a lone call returns."""
+    import threading
+    x = load_golden("fft_stages")["input"]
+    sr = 48000
+    jobs = [lambda: P.resample_audio(x, 48000, 44100),
+            lambda: P.apply_spectral_denoise(x, sr, 0.5, 15.0),
+            lambda: P.apply_harmonic_exciter(x * np.float32(2.0), sr, 2.0, "tape", 2)]
+    alone = [j() for j in jobs]
+    got = [[None] * 4 for _ in jobs]
+    errs = []
+
+    def work(i):
+        try:
+            for rep in range(4):
+                got[i][rep] = jobs[i]()
+        except Exception as e:      # pragma: no cover
+            errs.append(e)
+
+    th = [threading.Thread(target=work, args=(i,)) for i in range(len(jobs))]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    assert not errs, errs
+    for i in range(len(jobs)):
+        for rep in range(4):
+            assert np.array_equal(got[i][rep], alone[i]), (i, rep)
