@@ -64,16 +64,19 @@ __device__ __forceinline__ float dyneq_gain(float env, float thr, float ratio, f
     return fminf(fmaxf(g, 0.3f), 1.0f);
 }
 
-__device__ __forceinline__ float env_step(float e, float v, const EnvArgs& P) {
-    // max of the attack and the release update == the reference's branch on v > e (atk < rel)
-    if (P.mode) {
+// One follower step; `ep` is the envelope one sample earlier.  The low parts of the coefficients multiply `ep` instead of `e`
+// (the difference, lo * (e - ep), is far below float32 resolution), which keeps them off the e -> e' dependency chain.
+template <int MODE> __device__ __forceinline__ float env_step(float e, float ep, float v, const EnvArgs& P) {
+    if (MODE) {
         const double ed = (double)e, vd = (double)v;
         return v > e ? (float)(P.d_atk * ed + P.d_1matk * vd) : (float)(P.d_rel * ed + P.d_1mrel * vd);
     }
-    const float a = fmaf(P.atk, e, fmaf(P.atk_lo, e, P.one_m_atk * v));
-    const float r = fmaf(P.rel, e, fmaf(P.rel_lo, e, P.one_m_rel * v));
+    // max of the attack and the release update == the reference's branch on v > e (atk < rel)
+    const float a = fmaf(P.atk, e, fmaf(P.atk_lo, ep, P.one_m_atk * v));
+    const float r = fmaf(P.rel, e, fmaf(P.rel_lo, ep, P.one_m_rel * v));
     return fmaxf(a, r);
 }
+#define MM_ENV_STEP(val) do { const float _en = env_step<MODE>(e, ep, fabsf(val), P); ep = e; e = _en; } while (0)
 
 // One thread = one chunk (+ its halo) of one row: a strictly sequential recurrence, so the kernel is
 // latency bound by design; each thread streams its samples through a private ring of 128-byte lines in
@@ -81,7 +84,7 @@ __device__ __forceinline__ float env_step(float e, float v, const EnvArgs& P) {
 constexpr int kEnvDepth = 8;
 constexpr int kEnvThreads = 32;
 
-__global__ void __launch_bounds__(kEnvThreads) envelope_gain_kernel(const EnvArgs P) {
+template <int MODE> __global__ void __launch_bounds__(kEnvThreads) envelope_gain_kernel(const EnvArgs P) {
     __shared__ __align__(128) float ring[kEnvDepth][kEnvThreads][32];
     const int lane = threadIdx.x;
     const long long gid = (long long)blockIdx.x * kEnvThreads + lane;
@@ -110,6 +113,7 @@ __global__ void __launch_bounds__(kEnvThreads) envelope_gain_kernel(const EnvArg
     // env[0] = |v0|: starting from e = |v0| the first update returns |v0| again (to within one ulp), so the
     // recurrence below needs no special case for the chunk's first sample
     float e = active ? fabsf(__ldg(src + start)) : 0.f;
+    float ep = e;
     const int halo_lines = active ? (int)((live0 - start) / 32) : 0;
     // halo: only the state matters -- 5 instructions per sample, all but two of them off the dependency chain
 #pragma unroll 1
@@ -120,10 +124,10 @@ __global__ void __launch_bounds__(kEnvThreads) envelope_gain_kernel(const EnvArg
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
             const float4 v = *reinterpret_cast<const float4*>(s + 4 * (u ^ sx));
-            e = env_step(e, fabsf(v.x), P);
-            e = env_step(e, fabsf(v.y), P);
-            e = env_step(e, fabsf(v.z), P);
-            e = env_step(e, fabsf(v.w), P);
+            MM_ENV_STEP(v.x);
+            MM_ENV_STEP(v.y);
+            MM_ENV_STEP(v.z);
+            MM_ENV_STEP(v.w);
         }
     }
 #pragma unroll 1
@@ -136,10 +140,10 @@ __global__ void __launch_bounds__(kEnvThreads) envelope_gain_kernel(const EnvArg
         for (int u = 0; u < 8; ++u) {
             const float4 v = *reinterpret_cast<const float4*>(s + 4 * (u ^ sx));
             float4 g;
-            e = env_step(e, fabsf(v.x), P); g.x = P.mode ? dyneq_gain(e, P.thr, P.ratio, P.max_cut) : deess_gain(e, P.thr, P.inv_ratio);
-            e = env_step(e, fabsf(v.y), P); g.y = P.mode ? dyneq_gain(e, P.thr, P.ratio, P.max_cut) : deess_gain(e, P.thr, P.inv_ratio);
-            e = env_step(e, fabsf(v.z), P); g.z = P.mode ? dyneq_gain(e, P.thr, P.ratio, P.max_cut) : deess_gain(e, P.thr, P.inv_ratio);
-            e = env_step(e, fabsf(v.w), P); g.w = P.mode ? dyneq_gain(e, P.thr, P.ratio, P.max_cut) : deess_gain(e, P.thr, P.inv_ratio);
+            MM_ENV_STEP(v.x); g.x = MODE ? dyneq_gain(e, P.thr, P.ratio, P.max_cut) : deess_gain(e, P.thr, P.inv_ratio);
+            MM_ENV_STEP(v.y); g.y = MODE ? dyneq_gain(e, P.thr, P.ratio, P.max_cut) : deess_gain(e, P.thr, P.inv_ratio);
+            MM_ENV_STEP(v.z); g.z = MODE ? dyneq_gain(e, P.thr, P.ratio, P.max_cut) : deess_gain(e, P.thr, P.inv_ratio);
+            MM_ENV_STEP(v.w); g.w = MODE ? dyneq_gain(e, P.thr, P.ratio, P.max_cut) : deess_gain(e, P.thr, P.inv_ratio);
             const long long i = i0 + 4 * u;
             if (i + 3 < P.n) *reinterpret_cast<float4*>(dst + i) = g;
             else {
@@ -250,7 +254,9 @@ static int launch_envelope(mm_ctx* c, const mm_geom* g, EnvArgs& A, double attac
     A.nchunks = (int)((g->n + A.chunk - 1) / A.chunk);
     const long long total = (long long)rows * A.nchunks;
     KernelScope ks(c, name);
-    envelope_gain_kernel<<<(unsigned)((total + kEnvThreads - 1) / kEnvThreads), kEnvThreads, 0, c->stream>>>(A);
+    const unsigned nblk = (unsigned)((total + kEnvThreads - 1) / kEnvThreads);
+    if (A.mode) envelope_gain_kernel<1><<<nblk, kEnvThreads, 0, c->stream>>>(A);
+    else envelope_gain_kernel<0><<<nblk, kEnvThreads, 0, c->stream>>>(A);
     MM_CUDA(cudaGetLastError());
     return 0;
 }
