@@ -26,47 +26,116 @@ constexpr int kDnN = 2048;              // nperseg
 constexpr int kDnM = kDnN / 2;          // packed complex FFT size
 constexpr int kDnHop = 512;
 constexpr int kDnBins = kDnN / 2 + 1;
-constexpr int kDnThreads = 256;
-constexpr int kDnMagFrames = 16;        // frames per CTA of the magnitude pass (64-byte runs per bin)
+constexpr int kDnThreads = 256;         // four groups of 64 threads, one frame per group at a time
+constexpr int kDnGroups = kDnThreads / 64;
+constexpr int kDnBuf = kDnM + kDnM / 16;    // padded FFT buffer: index i lives at i + i / 16
+constexpr int kDnMagFrames = 8;         // frames per CTA of the magnitude pass (32-byte runs per bin)
 constexpr int kDnHops = 13;             // hops of output per CTA of the apply pass
 constexpr int kDnApplyFrames = kDnHops + 3;
 constexpr int kDnAccLen = (kDnHops + 6) * kDnHop;
 
-struct DnTables {
-    float2* tw;        // [kDnM]  e^{-2 pi i k / 1024}
+struct DnSmem {                          // carved from dynamic shared memory, in this order
+    float* win;        // [kDnN]   periodic Hann rounded to float32 (the same values window, synthesise and normalise)
+    float2* tw;        // [kDnM]   e^{-2 pi i k / 1024}
     float2* twh;       // [kDnM/2 + 1]  e^{-2 pi i k / 2048}
-    double* win;       // [kDnN]  periodic Hann
+    float2* buf;       // [kDnGroups][kDnBuf]
+    unsigned char* rest;
 };
+constexpr size_t kDnSmemHead = kDnN * sizeof(float) + (kDnM + kDnM / 2 + 1 + 1 + kDnGroups * kDnBuf) * sizeof(float2);
 
-__device__ __forceinline__ void dn_fill_tables(const DnTables& T) {
-    fft_fill_twiddles<kDnM, kDnThreads>(T.tw);
+__device__ __forceinline__ DnSmem dn_carve(unsigned char* base) {
+    DnSmem S;
+    S.win = reinterpret_cast<float*>(base);
+    S.tw = reinterpret_cast<float2*>(S.win + kDnN);
+    S.twh = S.tw + kDnM;
+    S.buf = S.twh + kDnM / 2 + 2;
+    S.rest = reinterpret_cast<unsigned char*>(S.buf + kDnGroups * kDnBuf);
+    return S;
+}
+
+__device__ __forceinline__ void dn_fill_tables(const DnSmem& S) {
+    fft_fill_twiddles<kDnM, kDnThreads>(S.tw);
     for (int k = threadIdx.x; k <= kDnM / 2; k += kDnThreads) {
         double s, c;
         sincospi(-2.0 * (double)k / (double)kDnN, &s, &c);
-        T.twh[k] = make_float2((float)c, (float)s);
+        S.twh[k] = make_float2((float)c, (float)s);
     }
-    for (int j = threadIdx.x; j < kDnN; j += kDnThreads) T.win[j] = 0.5 - 0.5 * cospi(2.0 * (double)j / (double)kDnN);
+    for (int j = threadIdx.x; j < kDnN; j += kDnThreads) S.win[j] = (float)(0.5 - 0.5 * cospi(2.0 * (double)j / (double)kDnN));
 }
 
-// windowed frame f of one row, packed even/odd into A (zeros outside [0, n))
-__device__ __forceinline__ void dn_load_frame(const float* row, long long n, long long f, const double* win, float2* A) {
+__device__ __forceinline__ void gbar(int group) { asm volatile("bar.sync %0, 64;" ::"r"(group + 1) : "memory"); }
+__device__ __forceinline__ int padx(int i) { return i + (i >> 4); }
+
+// 1024-point forward FFT by one 64-thread group, 16 points per thread: radix 16 (inputs v[q] = z[gt + 64 q]), exchange,
+// radix 16, exchange, radix 4.  On return v[m] = Z[gt + 64 m] (natural order).  `buf` is free to be overwritten on return
+// only after a further gbar().
+__device__ __forceinline__ void fft1024_group(float2 (&v)[16], float2* buf, const float2* tw, int gt, int group) {
+    dft_reg<16>(v);
+#pragma unroll
+    for (int k = 0; k < 16; ++k) buf[gt * 17 + k] = v[dft_pos<16>(k)];                 // padx(16 gt + k)
+    gbar(group);
+    const int kk = gt & 15;
+#pragma unroll
+    for (int q = 0; q < 16; ++q) {
+        float2 x = buf[padx(gt + 64 * q)];
+        if (q) x = cmulf(x, tw[4 * kk * q]);
+        v[q] = x;
+    }
+    gbar(group);
+    dft_reg<16>(v);
+    const int o = (gt - kk) * 16 + kk;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) buf[padx(o + 16 * k)] = v[dft_pos<16>(k)];
+    gbar(group);
+    float2 w[16];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int jj = gt + 64 * i;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            float2 x = buf[padx(jj + 256 * q)];
+            if (q) x = cmulf(x, tw[jj * q]);
+            w[4 * i + q] = x;
+        }
+        dft4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) v[i + 4 * q] = w[4 * i + q];                        // Z[gt + 64 (i + 4 q)]
+}
+
+// windowed frame f of one row, packed even / odd: v[q] = z[gt + 64 q] (zeros outside [0, n))
+__device__ __forceinline__ void dn_load_frame(const float* row, long long n, long long f, const float* win, int gt, float2 (&v)[16]) {
     const long long t0 = f * kDnHop - kDnN / 2;
-    for (int k = threadIdx.x; k < kDnM; k += kDnThreads) {
-        const long long t = t0 + 2 * k;
-        const float x0 = (t >= 0 && t < n) ? row[t] : 0.0f;
-        const float x1 = (t + 1 >= 0 && t + 1 < n) ? row[t + 1] : 0.0f;
-        A[k] = make_float2((float)((double)x0 * win[2 * k]), (float)((double)x1 * win[2 * k + 1]));
+    if (t0 >= 0 && t0 + kDnN <= n) {
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+            const int m = gt + 64 * q;
+            const float2 x = *reinterpret_cast<const float2*>(row + t0 + 2 * m);
+            const float2 w = *reinterpret_cast<const float2*>(win + 2 * m);
+            v[q] = make_float2(x.x * w.x, x.y * w.y);
+        }
+    } else {
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+            const int m = gt + 64 * q;
+            const long long t = t0 + 2 * m;
+            const float x0 = (t >= 0 && t < n) ? row[t] : 0.0f;
+            const float x1 = (t + 1 >= 0 && t + 1 < n) ? row[t + 1] : 0.0f;
+            v[q] = make_float2(x0 * win[2 * m], x1 * win[2 * m + 1]);
+        }
     }
 }
 
-// X[k] and X[M - k] of the 2M-point real FFT from the packed transform Z (k = 0 .. M/2; k = 0 yields X[0] and X[M])
+// X[k] and X[M - k] of the 2M-point real FFT from the packed transform Z (k = 0 .. M/2; k = 0 yields X[0] and X[M]); Z padded
 __device__ __forceinline__ void dn_untangle(const float2* Z, const float2* twh, int k, float2& xk, float2& xm) {
     if (k == 0) {
         xk = make_float2(Z[0].x + Z[0].y, 0.0f);
         xm = make_float2(Z[0].x - Z[0].y, 0.0f);
         return;
     }
-    const float2 zk = Z[k], zm = Z[kDnM - k];
+    const float2 zk = Z[padx(k)], zm = Z[padx(kDnM - k)];
     const float2 e = make_float2(0.5f * (zk.x + zm.x), 0.5f * (zk.y - zm.y));
     const float2 d = make_float2(0.5f * (zk.x - zm.x), 0.5f * (zk.y + zm.y));        // (Z[k] - conj Z[M-k]) / 2
     const float2 wo = cmulf(make_float2(d.y, -d.x), twh[k]);                          // W^k * (-i d)
@@ -82,26 +151,28 @@ struct DnMagArgs {
 
 __global__ void __launch_bounds__(kDnThreads) dn_mag_kernel(const DnMagArgs P) {
     extern __shared__ __align__(16) unsigned char dsm[];
-    DnTables T;
-    T.win = reinterpret_cast<double*>(dsm);
-    float2* A = reinterpret_cast<float2*>(T.win + kDnN);
-    float2* B = A + kDnM;
-    T.tw = B + kDnM;
-    T.twh = T.tw + kDnM;
-    float* stage = reinterpret_cast<float*>(T.twh + kDnM / 2 + 1);                    // [kDnMagFrames][kDnBins]
-    dn_fill_tables(T);
+    const DnSmem S = dn_carve(dsm);
+    float* stage = reinterpret_cast<float*>(S.rest);                                  // [kDnMagFrames][kDnBins]
+    dn_fill_tables(S);
+    __syncthreads();
+    const int group = threadIdx.x >> 6, gt = threadIdx.x & 63;
+    float2* buf = S.buf + group * kDnBuf;
     const int rowi = blockIdx.y;
     const float* row = P.in + (size_t)rowi * (size_t)P.stride + kLead;
     const long long f0 = (long long)blockIdx.x * kDnMagFrames;
     const int nf = (int)min((long long)kDnMagFrames, P.frames - f0);
-    for (int fl = 0; fl < nf; ++fl) {
-        __syncthreads();
-        dn_load_frame(row, P.n, f0 + fl, T.win, A);
-        __syncthreads();
-        const float2* Z = fft_r4_smem<kDnM, kDnThreads>(A, B, T.tw);
-        for (int k = threadIdx.x; k <= kDnM / 2; k += kDnThreads) {
+    for (int fl = group; fl < nf; fl += kDnGroups) {                                  // group-uniform trip count
+        float2 v[16];
+        dn_load_frame(row, P.n, f0 + fl, S.win, gt, v);
+        gbar(group);                                                                  // the previous frame's readers are done
+        fft1024_group(v, buf, S.tw, gt, group);
+        gbar(group);
+#pragma unroll
+        for (int m = 0; m < 16; ++m) buf[padx(gt + 64 * m)] = v[m];
+        gbar(group);
+        for (int k = gt; k <= kDnM / 2; k += 64) {
             float2 xk, xm;
-            dn_untangle(Z, T.twh, k, xk, xm);
+            dn_untangle(buf, S.twh, k, xk, xm);
             stage[fl * kDnBins + k] = sqrtf(xk.x * xk.x + xk.y * xk.y) * (1.0f / 1024.0f);
             stage[fl * kDnBins + kDnM - k] = sqrtf(xm.x * xm.x + xm.y * xm.y) * (1.0f / 1024.0f);
         }
@@ -190,63 +261,81 @@ struct DnApplyArgs {
 
 __global__ void __launch_bounds__(kDnThreads) dn_apply_kernel(const DnApplyArgs P) {
     extern __shared__ __align__(16) unsigned char dsm[];
-    DnTables T;
-    T.win = reinterpret_cast<double*>(dsm);
-    float2* A = reinterpret_cast<float2*>(T.win + kDnN);
-    float2* B = A + kDnM;
-    T.tw = B + kDnM;
-    T.twh = T.tw + kDnM;
-    float* noise = reinterpret_cast<float*>(T.twh + kDnM / 2 + 1);                    // [kDnBins]
+    const DnSmem S = dn_carve(dsm);
+    float* noise = reinterpret_cast<float*>(S.rest);                                  // [kDnBins]
     float* acc = noise + kDnBins + 3;                                                 // [kDnAccLen]
-    dn_fill_tables(T);
+    dn_fill_tables(S);
+    const int group = threadIdx.x >> 6, gt = threadIdx.x & 63;
+    float2* buf = S.buf + group * kDnBuf;
     const int rowi = blockIdx.y;
     const float* row = P.in + (size_t)rowi * (size_t)P.stride + kLead;
     float* orow = P.out + (size_t)rowi * (size_t)P.stride + kLead;
     for (int k = threadIdx.x; k < kDnBins; k += kDnThreads) noise[k] = P.noise[(size_t)rowi * kDnBins + k];
     for (int i = threadIdx.x; i < kDnAccLen; i += kDnThreads) acc[i] = 0.0f;
+    __syncthreads();
     const long long hb = (long long)blockIdx.x * kDnHops;          // first hop owned: output samples [512 hb, 512 (hb + 13))
     const long long fa = hb - 1;                                    // frames fa .. fa + 15 touch them
     const long long acc0 = fa * kDnHop - kDnN / 2;                  // sample index of acc[0]
-    for (int fl = 0; fl < kDnApplyFrames; ++fl) {
+    for (int round = 0; round < kDnApplyFrames / kDnGroups; ++round) {
+        const int fl = round * kDnGroups + group;
         const long long f = fa + fl;
-        if (f < 0 || f >= P.frames) continue;                       // uniform over the CTA
-        __syncthreads();
-        dn_load_frame(row, P.n, f, T.win, A);
-        __syncthreads();
-        float2* Z = fft_r4_smem<kDnM, kDnThreads>(A, B, T.tw);
-        float2* Y = Z == A ? B : A;
-        for (int k = threadIdx.x; k <= kDnM / 2; k += kDnThreads) {
-            float2 xk, xm;
-            dn_untangle(Z, T.twh, k, xk, xm);
-            // Wiener gain on |Zxx| = |X| / 1024 (pipeline.py:1504-1510)
-            const float mk = sqrtf(xk.x * xk.x + xk.y * xk.y) * (1.0f / 1024.0f);
-            const float mm_ = sqrtf(xm.x * xm.x + xm.y * xm.y) * (1.0f / 1024.0f);
-            const float rk = noise[k] / (mk + 1e-10f), rm = noise[kDnM - k] / (mm_ + 1e-10f);
-            const float gk = fminf(fmaxf(1.0f - P.strength * (rk * rk), 0.25f), 1.0f);
-            const float gm = fminf(fmaxf(1.0f - P.strength * (rm * rm), 0.25f), 1.0f);
-            const float2 yk = make_float2(gk * xk.x, gk * xk.y), ym = make_float2(gm * xm.x, gm * xm.y);
-            // inverse packing: E' = (Y[k] + conj Y[M-k]) / 2, O' = (Y[k] - conj Y[M-k]) / 2 * conj(W^k), Z'[k] = E' + i O',
-            // Z'[M-k] = conj(E') + i conj(O'); stored conjugated so that the forward transform inverts
-            if (k == 0) {
-                Y[0] = make_float2(0.5f * (yk.x + ym.x), -0.5f * (yk.x - ym.x));
-            } else {
-                const float2 e = make_float2(0.5f * (yk.x + ym.x), 0.5f * (yk.y - ym.y));
-                const float2 d = make_float2(0.5f * (yk.x - ym.x), 0.5f * (yk.y + ym.y));
-                const float2 o = cmulf(d, cconj(T.twh[k]));
-                Y[k] = cconj(make_float2(e.x - o.y, e.y + o.x));
-                Y[kDnM - k] = cconj(make_float2(e.x + o.y, -e.y + o.x));
+        const bool valid = f >= 0 && f < P.frames;                  // uniform over the group
+        float2 v[16];
+        if (valid) {
+            dn_load_frame(row, P.n, f, S.win, gt, v);
+            fft1024_group(v, buf, S.tw, gt, group);
+            gbar(group);
+#pragma unroll
+            for (int m = 0; m < 16; ++m) buf[padx(gt + 64 * m)] = v[m];
+            gbar(group);
+            // gain between the forward and the inverse untangling; the pair {k, M - k} belongs to this thread alone, so the
+            // conjugated inverse-packed spectrum overwrites Z in place
+            for (int k = gt; k <= kDnM / 2; k += 64) {
+                float2 xk, xm;
+                dn_untangle(buf, S.twh, k, xk, xm);
+                // Wiener gain on |Zxx| = |X| / 1024 (pipeline.py:1504-1510)
+                const float mk = sqrtf(xk.x * xk.x + xk.y * xk.y) * (1.0f / 1024.0f);
+                const float mm_ = sqrtf(xm.x * xm.x + xm.y * xm.y) * (1.0f / 1024.0f);
+                const float rk = noise[k] / (mk + 1e-10f), rm = noise[kDnM - k] / (mm_ + 1e-10f);
+                const float gk = fminf(fmaxf(1.0f - P.strength * (rk * rk), 0.25f), 1.0f);
+                const float gm = fminf(fmaxf(1.0f - P.strength * (rm * rm), 0.25f), 1.0f);
+                const float2 yk = make_float2(gk * xk.x, gk * xk.y), ym = make_float2(gm * xm.x, gm * xm.y);
+                // inverse packing: E' = (Y[k] + conj Y[M-k]) / 2, O' = (Y[k] - conj Y[M-k]) / 2 * conj(W^k), Z'[k] = E' + i O',
+                // Z'[M-k] = conj(E') + i conj(O'); stored conjugated so that the forward transform inverts
+                if (k == 0) {
+                    buf[0] = make_float2(0.5f * (yk.x + ym.x), -0.5f * (yk.x - ym.x));
+                } else {
+                    const float2 e = make_float2(0.5f * (yk.x + ym.x), 0.5f * (yk.y - ym.y));
+                    const float2 d = make_float2(0.5f * (yk.x - ym.x), 0.5f * (yk.y + ym.y));
+                    const float2 o = cmulf(d, cconj(S.twh[k]));
+                    buf[padx(k)] = cconj(make_float2(e.x - o.y, e.y + o.x));
+                    buf[padx(kDnM - k)] = cconj(make_float2(e.x + o.y, -e.y + o.x));
+                }
             }
+            gbar(group);
+#pragma unroll
+            for (int q = 0; q < 16; ++q) v[q] = buf[padx(gt + 64 * q)];
+            gbar(group);
+            fft1024_group(v, buf, S.tw, gt, group);
         }
-        __syncthreads();
-        const float2* z = fft_r4_smem<kDnM, kDnThreads>(Y, Y == A ? B : A, T.tw);
-        float* dst = acc + fl * kDnHop;
-        for (int j = threadIdx.x; j < kDnM; j += kDnThreads) {
-            const float2 v = z[j];
-            dst[2 * j] += (float)((double)(v.x * (1.0f / kDnM)) * T.win[2 * j]);
-            dst[2 * j + 1] += (float)((double)(-v.y * (1.0f / kDnM)) * T.win[2 * j + 1]);
+        // overlap-add in frame order (the reference's order): the four frames of a round overlap one another
+#pragma unroll 1
+        for (int g = 0; g < kDnGroups; ++g) {
+            if (g == group && valid) {
+                float* dst = acc + fl * kDnHop;
+#pragma unroll
+                for (int m = 0; m < 16; ++m) {
+                    const int j = gt + 64 * m;                      // y[2j] = Re z[j] / M, y[2j+1] = -Im conj-trick
+                    const float2 w = *reinterpret_cast<const float2*>(S.win + 2 * j);
+                    float2 a = *reinterpret_cast<float2*>(dst + 2 * j);
+                    a.x += (v[m].x * (1.0f / kDnM)) * w.x;
+                    a.y += (-v[m].y * (1.0f / kDnM)) * w.y;
+                    *reinterpret_cast<float2*>(dst + 2 * j) = a;
+                }
+            }
+            __syncthreads();
         }
     }
-    __syncthreads();
     const long long s0 = hb * kDnHop;
     for (int i = threadIdx.x; i < kDnHops * kDnHop; i += kDnThreads) {
         const long long t = s0 + i;
@@ -258,7 +347,7 @@ __global__ void __launch_bounds__(kDnThreads) dn_apply_kernel(const DnApplyArgs 
         const long long fhi = min(P.frames - 1, p / kDnHop);
         double norm = 0.0;
         for (long long f = flo; f <= fhi; ++f) {
-            const double w = T.win[p - f * kDnHop];
+            const double w = (double)S.win[p - f * kDnHop];
             norm += w * w;
         }
         const float v = (float)((double)acc[t - acc0] / (norm > 1e-10 ? norm : 1.0));
@@ -276,7 +365,7 @@ int st_spectral_denoise(mm_ctx* c, const mm_geom* g, const float* in, float* out
     float* noise;
     MM_TRY(arena(c, SL_DN_MAG, (size_t)rows * kDnBins * (size_t)fpad, &mag));
     MM_TRY(arena(c, SL_DN_NOISE, (size_t)rows * kDnBins, &noise));
-    const size_t tables = kDnN * sizeof(double) + (2 * kDnM + kDnM + kDnM / 2 + 1) * sizeof(float2);
+    const size_t tables = kDnSmemHead;
     {
         const size_t smem = tables + (size_t)kDnMagFrames * kDnBins * sizeof(float);
         static bool attr = false;

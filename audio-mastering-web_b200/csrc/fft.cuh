@@ -49,4 +49,50 @@ template <int M, int THREADS> __device__ __forceinline__ float2* fft_r4_smem(flo
     return src;
 }
 
+// ---- in-register DFTs (forward sign); dft_pos<N>(k) is where output k ends up --------------------------------------
+__device__ __forceinline__ void dft4(float2& a, float2& b, float2& c, float2& d) {
+    const float2 a02 = make_float2(a.x + c.x, a.y + c.y), s02 = make_float2(a.x - c.x, a.y - c.y);
+    const float2 a13 = make_float2(b.x + d.x, b.y + d.y), s13 = make_float2(b.x - d.x, b.y - d.y);
+    a = make_float2(a02.x + a13.x, a02.y + a13.y);
+    b = make_float2(s02.x + s13.y, s02.y - s13.x);
+    c = make_float2(a02.x - a13.x, a02.y - a13.y);
+    d = make_float2(s02.x - s13.y, s02.y + s13.x);
+}
+__device__ __forceinline__ float2 w16(int m) {          // e^{-2 pi i m / 16}, m folded at compile time
+    constexpr float c1 = 0.92387953251128674f, s1 = 0.38268343236508977f, h = 0.70710678118654752f;
+    switch (m) {
+        case 0: return make_float2(1.0f, 0.0f);
+        case 1: return make_float2(c1, -s1);
+        case 2: return make_float2(h, -h);
+        case 3: return make_float2(s1, -c1);
+        case 4: return make_float2(0.0f, -1.0f);
+        case 6: return make_float2(-h, -h);
+        default: return make_float2(-c1, s1);           // m == 9
+    }
+}
+template <int N> __device__ __forceinline__ void dft_reg(float2* v);
+template <> __device__ __forceinline__ void dft_reg<16>(float2* v) {
+#pragma unroll
+    for (int n0 = 0; n0 < 4; ++n0) dft4(v[n0], v[4 + n0], v[8 + n0], v[12 + n0]);
+#pragma unroll
+    for (int k1 = 1; k1 < 4; ++k1)
+#pragma unroll
+        for (int n0 = 1; n0 < 4; ++n0) v[4 * k1 + n0] = cmulf(v[4 * k1 + n0], w16(n0 * k1));
+#pragma unroll
+    for (int k1 = 0; k1 < 4; ++k1) dft4(v[4 * k1], v[4 * k1 + 1], v[4 * k1 + 2], v[4 * k1 + 3]);
+}
+template <> __device__ __forceinline__ void dft_reg<8>(float2* v) {
+#pragma unroll
+    for (int n0 = 0; n0 < 2; ++n0) dft4(v[n0], v[2 + n0], v[4 + n0], v[6 + n0]);
+#pragma unroll
+    for (int k1 = 1; k1 < 4; ++k1) v[2 * k1 + 1] = cmulf(v[2 * k1 + 1], w16(2 * k1));
+#pragma unroll
+    for (int k1 = 0; k1 < 4; ++k1) {
+        const float2 a = v[2 * k1], b = v[2 * k1 + 1];
+        v[2 * k1] = make_float2(a.x + b.x, a.y + b.y);
+        v[2 * k1 + 1] = make_float2(a.x - b.x, a.y - b.y);
+    }
+}
+template <int N> __device__ __forceinline__ constexpr int dft_pos(int k) { return N == 16 ? 4 * (k & 3) + (k >> 2) : 2 * (k & 3) + (k >> 2); }
+
 }  // namespace mm
