@@ -414,4 +414,88 @@ int st_fft_resample(mm_ctx* c, const mm_geom* gi, const float* in, const mm_geom
     return 0;
 }
 
+
+// ---- long FIR as one circular convolution per row -----------------------------------------------------------------------
+// out[i] = sum_k taps[k] x[i + (K-1)/2 - k]  (scipy.signal.fftconvolve(x, taps, mode="same"): the 4096-tap linear-phase
+// target curve, pipeline.py:220-235, and the 8192-tap reference match, :1600-1606).  The two channels of a track ride one
+// complex transform -- z = L + i R convolved with real taps is (L * h) + i (R * h), no untangling -- of length
+// L >= n + K - 1 (a power of two), so a 180 s stereo track costs two 2^24-point FFTs instead of 2 x 4096 MACs per sample.
+struct CvArgs {
+    const float* in;
+    float* out;
+    long long n, stride, L;
+    int channels, K, center, clip;
+    float2* work;
+    const float* taps;
+};
+
+__global__ void cv_taps_kernel(float2* h, long long L, const float* taps, int K) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < L) h[i] = make_float2(i < K ? taps[i] : 0.0f, 0.0f);
+}
+
+__global__ void cv_pre_kernel(const CvArgs P) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P.L) return;
+    float2 v = make_float2(0.0f, 0.0f);
+    if (i < P.n) {
+        const float* r0 = P.in + (size_t)(blockIdx.y * P.channels) * (size_t)P.stride + kLead;
+        v.x = r0[i];
+        if (P.channels > 1) v.y = r0[P.stride + i];
+    }
+    P.work[(size_t)blockIdx.y * (size_t)P.L + i] = v;
+}
+
+__global__ void cv_post_kernel(const CvArgs P) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P.n) return;
+    float2 v = P.work[(size_t)blockIdx.y * (size_t)P.L + i + P.center];
+    if (P.clip) { v.x = fminf(fmaxf(v.x, -1.f), 1.f); v.y = fminf(fmaxf(v.y, -1.f), 1.f); }
+    float* r0 = P.out + (size_t)(blockIdx.y * P.channels) * (size_t)P.stride + kLead;
+    r0[i] = v.x;
+    if (P.channels > 1) r0[P.stride + i] = v.y;
+}
+
+bool fft_convolve_fits(const mm_geom* g, int K) { return g->n + K - 1 <= (1LL << 27); }
+
+int st_fft_convolve_same(mm_ctx* c, const mm_geom* g, const float* in, float* out, const float* taps_dev, int K, int clip) {
+    int p = 18;
+    while ((1LL << p) < g->n + K - 1) ++p;
+    if (p > 27) { set_error("FFT convolution: %lld + %d points exceed the 2^27-point transform", (long long)g->n, K); return 2; }
+    BigFft* F;
+    MM_TRY(bf_get_fft(c, p, &F));
+    const long long L = F->L;
+    float2* H;
+    MM_TRY(arena(c, SL_BIGFFT_H, (size_t)L, &H));
+    cv_taps_kernel<<<(unsigned)((L + 255) / 256), 256, 0, c->stream>>>(H, L, taps_dev, K);
+    MM_CUDA(cudaGetLastError());
+    MM_TRY(bf_run(c, F, H, L, 1, 0, nullptr));
+    bf_scale_kernel<<<(unsigned)((L + 255) / 256), 256, 0, c->stream>>>(H, L, (float)(1.0 / (double)L));
+    MM_CUDA(cudaGetLastError());
+    CvArgs A;
+    A.n = g->n; A.stride = g->stride; A.L = L; A.channels = g->channels; A.K = K; A.center = (K - 1) / 2; A.clip = clip;
+    A.taps = taps_dev;
+    const int tracks = g->tracks;
+    const int chunk = (int)std::max<long long>(1, std::min<long long>(tracks, (4LL << 30) / (L * (long long)sizeof(float2))));
+    MM_TRY(arena(c, SL_BIGFFT, (size_t)chunk * (size_t)L, &A.work));
+    for (int t0 = 0; t0 < tracks; t0 += chunk) {
+        const int nt = std::min(chunk, tracks - t0);
+        A.in = in + (size_t)(t0 * g->channels) * (size_t)g->stride;
+        A.out = out + (size_t)(t0 * g->channels) * (size_t)g->stride;
+        {
+            KernelScope ks(c, "fftconv_pack");
+            cv_pre_kernel<<<dim3((unsigned)((L + 255) / 256), (unsigned)nt), 256, 0, c->stream>>>(A);
+            MM_CUDA(cudaGetLastError());
+        }
+        MM_TRY(bf_run(c, F, A.work, L, nt, 0, nullptr));
+        MM_TRY(bf_run(c, F, A.work, L, nt, 1, H));
+        {
+            KernelScope ks(c, "fftconv_unpack");
+            cv_post_kernel<<<dim3((unsigned)((g->n + 255) / 256), (unsigned)nt), 256, 0, c->stream>>>(A);
+            MM_CUDA(cudaGetLastError());
+        }
+    }
+    return 0;
+}
+
 }  // namespace mm

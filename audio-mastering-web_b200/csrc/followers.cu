@@ -13,6 +13,7 @@
 #include <cmath>
 #include <cstring>
 #include <map>
+#include <mutex>
 #include <vector>
 
 #include "context.h"
@@ -316,10 +317,20 @@ __global__ void __launch_bounds__(kFirThreads) fir_same_kernel(const FirArgs P) 
     }
 }
 
+// Long filters run as one FFT convolution per track (bigfft.cu: 2 x 2^24-point transforms for a 180 s stereo track instead of
+// K multiply-adds per sample); the direct kernel keeps short filters, rows beyond the 2^27-point transform (a 2-hour 96 kHz
+// file) and MM_FIR=direct.
+static bool fir_use_fft(const mm_geom* g, int K) {
+    static const bool direct = [] { const char* e = getenv("MM_FIR"); return e && !strcmp(e, "direct"); }();
+    return !direct && K >= 1024 && g->n >= 4 * (long long)K && fft_convolve_fits(g, K);
+}
+
 int st_target_curve_linear_phase(mm_ctx* c, const mm_geom* g, const float* in, float* out) {
     if (in == out) { set_error("linear-phase target curve: in-place operation is not supported"); return 1; }
     const int K = 4096;
     static std::map<int, float*> cache;               // per sample rate, device taps (one device kind per process)
+    static std::mutex cache_mu;                       // contexts are per thread; this cache is per process
+    std::lock_guard<std::mutex> lock(cache_mu);
     float* taps = nullptr;
     auto it = cache.find(g->sr);
     if (it != cache.end()) taps = it->second;
@@ -331,6 +342,7 @@ int st_target_curve_linear_phase(mm_ctx* c, const mm_geom* g, const float* in, f
         MM_CUDA(cudaStreamSynchronize(c->stream));
         cache[g->sr] = taps;
     }
+    if (fir_use_fft(g, K)) return st_fft_convolve_same(c, g, in, out, taps, K, 1);
     FirArgs A;
     A.in = in; A.out = out; A.taps = taps; A.n = g->n; A.stride = g->stride; A.K = K; A.center = (K - 1) / 2; A.clip = 1;
     const size_t smem = (size_t)(K + kFirTile + K + 8 + 8) * sizeof(float);
@@ -349,6 +361,7 @@ int st_target_curve_linear_phase(mm_ctx* c, const mm_geom* g, const float* in, f
 int st_fir_same(mm_ctx* c, const mm_geom* g, const float* in, float* out, const float* taps_dev, int K, int clip) {
     if (in == out) { set_error("FIR: in-place operation is not supported"); return 1; }
     if (K < 64 || (K % 64) != 0 || K > 16384) { set_error("FIR: the tap count must be a multiple of 64 in [64, 16384]"); return 1; }
+    if (fir_use_fft(g, K)) return st_fft_convolve_same(c, g, in, out, taps_dev, K, clip);
     FirArgs A;
     A.in = in; A.out = out; A.taps = taps_dev; A.n = g->n; A.stride = g->stride; A.K = K; A.center = (K - 1) / 2; A.clip = clip;
     const size_t smem = (size_t)(K + kFirTile + K + 8 + 8) * sizeof(float);

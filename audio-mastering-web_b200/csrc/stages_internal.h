@@ -79,6 +79,10 @@ int st_spectral_envelope(mm_ctx* c, const mm_geom* g, const float* in, float* en
 // bigfft.cu: scipy.signal.resample of every row (gi->n -> go->n frames; same tracks / channels); plan cache per context
 int st_fft_resample(mm_ctx* c, const mm_geom* gi, const float* in, const mm_geom* go, float* out);
 void bigfft_release(mm_ctx* c);
+// bigfft.cu: the same "same"-mode FIR as st_fir_same, evaluated as one circular FFT convolution per track (both channels in one
+// complex transform); usable while n + K - 1 <= 2^27
+bool fft_convolve_fits(const mm_geom* g, int K);
+int st_fft_convolve_same(mm_ctx* c, const mm_geom* g, const float* in, float* out, const float* taps_dev, int K, int clip);
 // export.cu: _auto_blank_end's scan (idx_dev[tracks]: last frame above the threshold, -1 if none) and the PCM_24 conversion
 int st_last_above(mm_ctx* c, const mm_geom* g, const float* in, double threshold, long long* idx_dev);
 int st_quantize_pcm24(mm_ctx* c, const mm_geom* g, const float* in, int32_t* out);

@@ -266,3 +266,25 @@ def test_fft_stages_from_concurrent_threads(P):
     for i in range(len(jobs)):
         for rep in range(4):
             assert np.array_equal(got[i][rep], alone[i]), (i, rep)
+
+
+def test_long_fir_as_fft_convolution_against_oracle(P):
+    """Rows long enough for the FFT-convolution path (n >= 4 K): the 4096-tap linear-phase target curve on a 60 s stereo and
+    a mono track, and an 8192-tap reference match, against the oracle's scipy.signal.fftconvolve."""
+    from oracle import chain as oc
+    sr, n = 44100, 60 * 44100
+    x = (_material(n, sr, 31) * np.float32(1.5)).astype(np.float32)
+    for name, sig in (("stereo", x), ("mono", np.ascontiguousarray(x[:, 1]))):
+        out = P.apply_target_curve(sig, sr, phase_mode="linear_phase")
+        ref = oc.apply_target_curve_linear_phase(sig, sr)
+        e = _err(out, ref)
+        print(f"[parity] linear phase 60 s {name} (FFT convolution): {e:.3e}")
+        assert out.shape == ref.shape and e <= FFT_TOL
+    from scipy import signal as sg
+    bb, aa = sg.butter(1, 2500 / (sr / 2), "high")
+    refsig = (x + 0.7 * sg.lfilter(bb, aa, x, axis=0)).astype(np.float32)
+    out = P.apply_reference_match(x, sr, refsig, sr, strength=0.8)
+    ref = oc.apply_reference_match(x, sr, refsig, sr, 0.8)
+    e = _err(out, ref)
+    print(f"[parity] reference match 60 s (8192 taps, FFT convolution): {e:.3e}")
+    assert e <= 2e-5

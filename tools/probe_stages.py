@@ -65,6 +65,13 @@ def main():
         timed(eng, f"fft_resample {n} -> {num}", lambda: eng.fft_resample(b, num, 48000), cs, a.reps, 4 * 2)
     if on("exciter2"):
         timed(eng, "apply_harmonic_exciter oversample=2", lambda: P._exciter_dev(eng, b, 2.0, "tape", 2), cs, a.reps, 4 * 2)
+    if on("linphase"):
+        timed(eng, "apply_target_curve_linear_phase (4096 taps)", lambda: eng.stage("apply_target_curve_linear_phase", b, 4096, out=out), cs, a.reps, 4 * 2)
+    if on("fir8192"):
+        import numpy as np
+        ir = np.ascontiguousarray((np.hanning(8192) / 4096.0).astype(np.float32))
+        timed(eng, "fir_same (8192 taps, reference match)", lambda: eng.stage("fir_same", b, ir.ctypes.data_as(C.c_void_p), 8192, 1, out=out),
+              cs, a.reps, 4 * 2)
     if on("refenv"):
         env = torch.empty(a.tracks * 4097, dtype=torch.float32, device=eng.tdev)
         g = b.geom
