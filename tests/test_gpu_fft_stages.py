@@ -288,3 +288,28 @@ def test_long_fir_as_fft_convolution_against_oracle(P):
     e = _err(out, ref)
     print(f"[parity] reference match 60 s (8192 taps, FFT convolution): {e:.3e}")
     assert e <= 2e-5
+
+
+def test_big_fft_row_chunking(P):
+    """More rows than one 4 GB work area holds (2048 rows of the smallest, 2^18-point transform): FFT resampling of 4200 rows and
+    FFT convolution of 2100 stereo tracks are processed in sub-batches; every track must equal its lone result."""
+    import ctypes as C
+    from mm_b200.engine import get_engine
+    from oracle import chain as oc
+    eng = get_engine()
+    rng = np.random.default_rng(17)
+    tracks, n = 2100, 4200
+    base = (0.2 * rng.standard_normal((8, n, 2))).astype(np.float32)
+    batch = [base[t % 8] * np.float32(1.0 + 0.001 * (t // 8)) for t in range(tracks)]
+    b = eng.upload(batch, 48000)
+    up = eng.download(eng.fft_resample(b, 6300, 72000))
+    for t in (0, 1, 2047, 2048, 2099):
+        ref = oc.fft_resample(batch[t][:, 0], 6300).astype(np.float32)
+        assert _err(up[t][:, 0], ref) <= RS_TOL, t
+    taps = np.ascontiguousarray((np.hanning(1024) * rng.standard_normal(1024) / 64.0).astype(np.float32))
+    out = eng.download(eng.stage("fir_same", b, taps.ctypes.data_as(C.c_void_p), 1024, 0))
+    from scipy import signal as sg
+    for t in (0, 1023, 1024, 2047, 2048, 2099):
+        for ch in (0, 1):
+            ref = sg.fftconvolve(batch[t][:, ch].astype(np.float64), taps.astype(np.float64), mode="same")
+            assert _err(out[t][:, ch], ref) <= RS_TOL, (t, ch)
