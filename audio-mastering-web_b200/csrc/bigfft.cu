@@ -2,11 +2,10 @@
 // (backend/app/pipeline.py:920-936), the oversampled exciter (:1294-1320) and apply_reference_match for a reference track
 // at another rate (:1581-1584).
 //
-//   x_r[t] = (1/n) Re sum_{k < m/2 + 1} g_k X[k] e^{+2 pi i k t / num},   X = DFT_n(x),  m = min(n, num),
-//   g_0 = 1, g_k = 2, and for even m the unpaired bin g_{m/2} = 1 (up-sampling) or 2 (down-sampling)
+//   x_r[t] = (1/n) sum_{|k| <= m/2} w_k X[k mod n] e^{+2 pi i k t / num},   X = DFT_n(x),  m = min(n, num)
 //
-// which is scipy's "rfft -> keep m/2 + 1 bins -> x2 / x0.5 on the unpaired bin -> irfft(n = num) * num / n" written as one
-// one-sided sum.  n and num are arbitrary (7,938,000 -> 8,640,000 for a 180 s track), so both DFTs are evaluated as
+// which is scipy's "fft -> keep the m lowest bins -> split / fold the unpaired bin -> ifft(n = num) * num / n" written as one
+// sum (its rfft path for real input is the same thing); a track's two channels go through as ONE complex signal L + i R.  n and num are arbitrary (7,938,000 -> 8,640,000 for a 180 s track), so both DFTs are evaluated as
 // Bluestein chirp convolutions, e^{s 2 pi i j k / N} = u[j] u[k] conj(u[k - j]) with u[j] = e^{s i pi j^2 / N} (phase from
 // j^2 mod 2N in 64-bit integers, reduced in float64), over power-of-two circular lengths L >= n_in + n_out - 1.
 //
@@ -319,78 +318,108 @@ static int bf_get_chirp(mm_ctx* c, long long N, long long nin, long long nout, i
     return 0;
 }
 
+// Both channels of a track ride ONE complex signal z = L + i R (resampling is linear with real coefficients, so the real
+// and imaginary parts of the resampled z are the resampled channels; mono: R = 0).  For a complex signal scipy's rule is
+// the two-sided one:
+//   y[t] = (1/n) sum_{k = -Kn}^{Kn} w_k X[k mod n] e^{2 pi i k t / num},   Kn = m / 2 (m even) or (m - 1) / 2 (m odd),
+//   w = 1, except w_{+-m/2} = 1/2 when up-sampling an even n (the unpaired bin split in two); when down-sampling to an
+//   even num both +-num/2 terms fold onto the new Nyquist bin with weight 1 -- which is the same sum.
+// The window of bins starts at -Kn, so both chirps carry a linear phase: the forward one e^{-i pi (j^2 - 2 Kn j) / n}
+// yields X'[k'] = X[k' - Kn] for k' = 0 .. nk - 1 directly, the inverse one e^{+i pi (t^2 - 2 Kn t) / num} undoes the shift.
 struct RsArgs {
     const float* in;
     float* out;
-    long long n, num, m2, in_stride, out_stride, pitch, L1, L2;
-    int up, m_even;
+    long long n, num, nk, in_stride, out_stride, pitch, L1, L2;
+    int channels;
+    float w_end;            // weight of the first and the last bin of the window
     float2* work;
     ChirpMod Mn, Mnum;
+    unsigned long long lin_n, lin_num;   // (-2 Kn) mod 2n, (-2 Kn) mod 2 num
 };
 
-// A1[j] = x[j] u1[j]   (u1[j] = e^{-i pi j^2 / n}), zero up to L1
+// e^{sign i pi (j^2 + lin j) / N},  lin given mod 2N
+__device__ __forceinline__ float2 chirp_lin(unsigned long long j, unsigned long long lin, const ChirpMod& M, int sign) {
+    const unsigned long long q = j * (j + lin);                        // < 2^27 * 2^29
+    unsigned long long rem = q - __umul64hi(q, M.m) * M.twoN;
+    while (rem >= M.twoN) rem -= M.twoN;
+    const double t = (double)(long long)rem * M.invN;
+    const double kq = rint(t * 2.0);
+    const float a = (float)(t - 0.5 * kq);
+    float s, c;
+    sincospif(a, &s, &c);
+    const int k = (int)kq & 3;
+    const float cr = k == 0 ? c : k == 1 ? -s : k == 2 ? -c : s;
+    const float sr = k == 0 ? s : k == 1 ? c : k == 2 ? -s : -c;
+    return make_float2(cr, sign > 0 ? sr : -sr);
+}
+
+// A1[j] = z[j] e^{-i pi (j^2 - 2 Kn j) / n}, zero up to L1
 __global__ void rs_pre_kernel(const RsArgs P) {
     const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= P.L1) return;
     float2 v = make_float2(0.0f, 0.0f);
     if (j < P.n) {
-        const float x = P.in[(size_t)blockIdx.y * (size_t)P.in_stride + kLead + j];
-        const float2 u = chirp((unsigned long long)j, P.Mn, -1);
-        v = make_float2(x * u.x, x * u.y);
+        const float* r0 = P.in + (size_t)(blockIdx.y * P.channels) * (size_t)P.in_stride + kLead;
+        const float2 z = make_float2(r0[j], P.channels > 1 ? r0[P.in_stride + j] : 0.0f);
+        v = cmulf(z, chirp_lin((unsigned long long)j, P.lin_n, P.Mn, -1));
     }
     P.work[(size_t)blockIdx.y * (size_t)P.pitch + j] = v;
 }
 
-// X[k] = u1[k] conv1[k];  A2[k] = (g_k / n) X[k] u2[k]   (u2[k] = e^{+i pi k^2 / num}), zero up to L2
+// X'[k'] = u1[k'] conv1[k'];  A2[k'] = (w / n) X'[k'] v[k']   (u1 = e^{-i pi k'^2 / n}, v = e^{+i pi k'^2 / num}), zero up to L2
 __global__ void rs_mid_kernel(const RsArgs P) {
     const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= P.L2) return;
     float2* w = P.work + (size_t)blockIdx.y * (size_t)P.pitch + k;
     float2 v = make_float2(0.0f, 0.0f);
-    if (k < P.m2) {
+    if (k < P.nk) {
         const float2 cv = *w;
         const float2 u1 = chirp((unsigned long long)k, P.Mn, -1), u2 = chirp((unsigned long long)k, P.Mnum, +1);
-        double g = k == 0 ? 1.0 : 2.0;
-        if (P.m_even && k == P.m2 - 1) g = P.up ? 1.0 : 2.0;
-        const float gf = (float)(g / (double)P.n);
-        const float2 x = cmulf(cv, u1);
-        const float2 y = cmulf(x, u2);
+        const float wk = (k == 0 || k == P.nk - 1) ? P.w_end : 1.0f;
+        const float gf = (float)((double)wk / (double)P.n);
+        const float2 y = cmulf(cmulf(cv, u1), u2);
         v = make_float2(gf * y.x, gf * y.y);
     }
     *w = v;
 }
 
-// out[t] = Re(u2[t] conv2[t])
+// (L, R)[t] = e^{+i pi (t^2 - 2 Kn t) / num} conv2[t]
 __global__ void rs_post_kernel(const RsArgs P) {
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= P.num) return;
     const float2 cv = P.work[(size_t)blockIdx.y * (size_t)P.pitch + t];
-    const float2 u = chirp((unsigned long long)t, P.Mnum, +1);
-    P.out[(size_t)blockIdx.y * (size_t)P.out_stride + kLead + t] = fmaf(cv.x, u.x, -cv.y * u.y);
+    const float2 y = cmulf(cv, chirp_lin((unsigned long long)t, P.lin_num, P.Mnum, +1));
+    float* r0 = P.out + (size_t)(blockIdx.y * P.channels) * (size_t)P.out_stride + kLead;
+    r0[t] = y.x;
+    if (P.channels > 1) r0[P.out_stride + t] = y.y;
 }
 
 int st_fft_resample(mm_ctx* c, const mm_geom* gi, const float* in, const mm_geom* go, float* out) {
     const long long n = gi->n, num = go->n;
-    const int rows = gi->tracks * gi->channels;
-    if (rows != go->tracks * go->channels) { set_error("fft resample: input and output batches differ in rows"); return 2; }
+    if (gi->tracks != go->tracks || gi->channels != go->channels) { set_error("fft resample: input and output batches differ in tracks / channels"); return 2; }
     if (n < 1 || num < 1) { set_error("fft resample: empty signal"); return 2; }
     if (n == num) { set_error("fft resample: equal lengths (copy instead)"); return 2; }
-    const long long m = std::min(n, num), m2 = m / 2 + 1;
+    const long long m = std::min(n, num);
+    const long long Kn = (m % 2 == 0) ? m / 2 : (m - 1) / 2;
+    const long long nk = 2 * Kn + 1;
     const ChirpPlan *F1, *F2;
-    MM_TRY(bf_get_chirp(c, n, n, m2, -1, &F1));
-    MM_TRY(bf_get_chirp(c, num, m2, num, +1, &F2));
+    MM_TRY(bf_get_chirp(c, n, n, nk, -1, &F1));
+    MM_TRY(bf_get_chirp(c, num, nk, num, +1, &F2));
     RsArgs A;
-    A.n = n; A.num = num; A.m2 = m2; A.in_stride = gi->stride; A.out_stride = go->stride;
+    A.n = n; A.num = num; A.nk = nk; A.in_stride = gi->stride; A.out_stride = go->stride; A.channels = gi->channels;
     A.L1 = F1->fft->L; A.L2 = F2->fft->L; A.pitch = std::max(A.L1, A.L2);
-    A.up = num > n; A.m_even = (m % 2 == 0);
+    A.w_end = (m % 2 == 0 && num > n) ? 0.5f : 1.0f;
     A.Mn = chirp_mod(n); A.Mnum = chirp_mod(num);
-    // rows per sub-batch: keep the complex work area near 4 GB
-    const int chunk = (int)std::max<long long>(1, std::min<long long>(rows, (4LL << 30) / (A.pitch * (long long)sizeof(float2))));
+    A.lin_n = (unsigned long long)((2 * n - (2 * Kn) % (2 * n)) % (2 * n));
+    A.lin_num = (unsigned long long)((2 * num - (2 * Kn) % (2 * num)) % (2 * num));
+    const int tracks = gi->tracks;
+    // tracks per sub-batch: keep the complex work area near 4 GB
+    const int chunk = (int)std::max<long long>(1, std::min<long long>(tracks, (4LL << 30) / (A.pitch * (long long)sizeof(float2))));
     MM_TRY(arena(c, SL_BIGFFT, (size_t)chunk * (size_t)A.pitch, &A.work));
-    for (int r0 = 0; r0 < rows; r0 += chunk) {
-        const int nr = std::min(chunk, rows - r0);
-        A.in = in + (size_t)r0 * (size_t)gi->stride;
-        A.out = out + (size_t)r0 * (size_t)go->stride;
+    for (int t0 = 0; t0 < tracks; t0 += chunk) {
+        const int nr = std::min(chunk, tracks - t0);
+        A.in = in + (size_t)(t0 * gi->channels) * (size_t)gi->stride;
+        A.out = out + (size_t)(t0 * go->channels) * (size_t)go->stride;
         {
             KernelScope ks(c, "resample_chirp_pre");
             rs_pre_kernel<<<dim3((unsigned)((A.L1 + 255) / 256), (unsigned)nr), 256, 0, c->stream>>>(A);
