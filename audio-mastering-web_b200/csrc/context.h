@@ -69,7 +69,7 @@ enum SlotId {
     SL_PEAKBITS, SL_WIDTH, SL_PARMIX, SL_PEAKIN, SL_MEAN, SL_NONFINITE, SL_LUFS2, SL_LUFS3,
     SL_STAGE_IL, SL_STAGE_PCM, SL_STAGE_NOISE, SL_STAGE_PL, SL_STATS, SL_ENV0, SL_ENV1, SL_MISC,
     SL_STAGE_IL1, SL_STAGE_PCM1, SL_STAGE_NOISE1, SL_STAGE_OL, SL_STAGE_OL1, SL_XCHG, SL_ROWMAP, SL_REV0, SL_REV1,
-    SL_DN_MAG, SL_DN_NOISE, SL_BIGFFT, SL_BIGFFT_H,
+    SL_DN_MAG, SL_DN_NOISE, SL_BIGFFT, SL_BIGFFT_H, SL_ENV_WIN, SL_ENV_TW,
     SL_COUNT
 };
 
