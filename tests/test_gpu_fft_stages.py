@@ -313,3 +313,23 @@ def test_big_fft_row_chunking(P):
         for ch in (0, 1):
             ref = sg.fftconvolve(batch[t][:, ch].astype(np.float64), taps.astype(np.float64), mode="same")
             assert _err(out[t][:, ch], ref) <= RS_TOL, (t, ch)
+
+
+def test_fft_resample_four_pass_transforms(P):
+    """Transforms above 2^24 points run as four passes (64 / 128-point axes): x2 of a 180 s mono track needs 2^25, x4 needs 2^26
+    (what the oversampled exciter does at the bench length).  Against scipy on the host."""
+    from oracle import chain as oc
+    sr, n = 44100, 170 * 44100
+    t = np.arange(n, dtype=np.float64) / sr
+    rng = np.random.default_rng(23)
+    x = (0.3 * np.sin(2 * np.pi * 523.25 * t) + 0.15 * np.sin(2 * np.pi * 11000.0 * t) + 0.02 * rng.standard_normal(n)).astype(np.float32)
+    for os_ in (2, 4):
+        up = P.fft_resample(x, n * os_)
+        ref = oc.fft_resample(x, n * os_).astype(np.float32)
+        e = _err(up, ref)
+        print(f"[parity] resample 170 s x{os_} (2^{25 if os_ == 2 else 26}-point chirp convolution): {e:.3e}")
+        assert up.shape == ref.shape and e <= RS_TOL
+        back = P.fft_resample(up, n)
+        e2 = _err(back, x)
+        print(f"[parity] resample x{os_} and back: {e2:.3e}")
+        assert e2 <= 5e-5
