@@ -540,6 +540,25 @@ int mm_dev_apply_dynamics(mm_ctx* c, const mm_geom* g, const float* in, float* o
     return st_dynamics(c, g, in, out, knee_db, crossovers_hz, band_ratios, max_upward_boost_db, nullptr, nullptr);
 }
 
+int mm_dev_apply_maximizer(mm_ctx* c, const mm_geom* g, const float* in, float* out);
+
+int mm_dev_apply_multiband_dynamics(mm_ctx* c, const mm_geom* g, const float* in, float* out, double knee_db, const double* crossovers_hz,
+                                    const double* band_ratios, double max_upward_boost_db) {
+    MM_API_BEGIN(c);
+    MM_TRY(check_geom(g));
+    return st_dynamics(c, g, in, out, knee_db, crossovers_hz, band_ratios, max_upward_boost_db, nullptr, nullptr, 1);
+}
+
+int mm_dev_apply_maximizer_lookahead(mm_ctx* c, const mm_geom* g, const float* in, float* out, double lookahead_ms) {
+    MM_API_BEGIN(c);
+    MM_TRY(check_geom(g));
+    if (in == out) { set_error("mm_dev_apply_maximizer_lookahead: not in place"); return 2; }
+    const long long delay_n = (long long)((double)g->sr * (lookahead_ms / 1000.0));
+    if (delay_n <= 0 || delay_n >= g->n) return mm_dev_apply_maximizer(c, g, in, out);       // pipeline.py:554-555
+    const int cf = (int)std::min<long long>(delay_n, std::max(2, (int)((double)g->sr * 0.002)));
+    return st_maximizer_lookahead(c, g, in, out, delay_n, cf);
+}
+
 int mm_dev_apply_maximizer(mm_ctx* c, const mm_geom* g, const float* in, float* out) {
     MM_API_BEGIN(c);
     MM_TRY(check_geom(g));

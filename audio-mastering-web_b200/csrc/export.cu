@@ -4,6 +4,7 @@
 //                       int32 for a host-side encoder.  libsndfile is absent here and in the oracle: PARITY UNPINNED against
 //                       the library itself; the formula is the one its f2flac24_array applies with normalisation on.
 #include <algorithm>
+#include <cmath>
 
 #include "context.h"
 #include "stages_internal.h"
@@ -34,6 +35,39 @@ __global__ void __launch_bounds__(256) pcm24_kernel(const float* in, long long n
         x = x != x ? 0.0f : fminf(fmaxf(x, -1.0f), 1.0f);
         out[((size_t)track * (size_t)n + (size_t)i) * channels + c] = __float2int_rn(__fmul_rn(x, 8388607.0f));
     }
+}
+
+// apply_maximizer_lookahead (pipeline.py:548-573): the first delay_n frames pass unlimited, the rest is the soft-knee maximizer
+// of the signal delay_n frames EARLIER (that is what the reference's splice of `limited[delay_n:]` returns), with a cf-frame
+// cross-fade before the seam against limited = maximizer(0) = 0.
+__global__ void __launch_bounds__(256) lookahead_kernel(const float* in, float* out, long long n, long long stride, long long delay_n,
+                                                       int cf, float max_k, float max_c, float max_top) {
+    const size_t ro = (size_t)blockIdx.y * (size_t)stride + kLead;
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float r;
+    if (i >= delay_n) {
+        const float s = in[ro + i - delay_n];
+        const float ax = fabsf(s);
+        r = copysignf(fminf(fminf(ax, fmaf(ax, max_k, max_c)), max_top), s);
+    } else if (i >= delay_n - cf) {
+        const double a = (double)(i - (delay_n - cf) + 1) / (double)cf;
+        r = __fadd_rn(__fmul_rn((float)(1.0 - a), in[ro + i]), __fmul_rn((float)a, 0.0f));
+    } else {
+        r = in[ro + i];
+    }
+    out[ro + i] = r;
+}
+
+int st_maximizer_lookahead(mm_ctx* c, const mm_geom* g, const float* in, float* out, long long delay_n, int cf) {
+    DynParams d;
+    fill_dyn(&d, 6.0, nullptr, 12.0);
+    d.max_top = (float)std::pow(10.0, -0.3 / 20.0);       // the maximizer alone: its ceiling, no limiter behind it
+    KernelScope ks(c, "maximizer_lookahead");
+    lookahead_kernel<<<dim3((unsigned)((g->n + 255) / 256), (unsigned)(g->tracks * g->channels)), 256, 0, c->stream>>>(
+        in, out, g->n, g->stride, delay_n, cf, d.max_k, d.max_c, d.max_top);
+    MM_CUDA(cudaGetLastError());
+    return 0;
 }
 
 int st_last_above(mm_ctx* c, const mm_geom* g, const float* in, double threshold, long long* idx_dev) {

@@ -585,7 +585,7 @@ int st_target_curve(mm_ctx* c, const mm_geom* g, const float* in, float* out, co
 // apply_dynamics = apply_multiband_dynamics (numpy branch) + apply_maximizer + hard limiter
 // (backend/app/pipeline.py:610-641, :414-481, :333-364)
 int st_dynamics(mm_ctx* c, const mm_geom* g, const float* in, float* out, double knee_db, const double* crossovers_hz,
-                const double* band_ratios, double max_upward_boost_db, const double* par_mix_rows, float* peak) {
+                const double* band_ratios, double max_upward_boost_db, const double* par_mix_rows, float* peak, int bands_only) {
     double cross[3] = {214.0, 3500.0, 10000.0};
     if (crossovers_hz) {
         double t[3];
@@ -624,6 +624,9 @@ int st_dynamics(mm_ctx* c, const mm_geom* g, const float* in, float* out, double
         DynParams d;
         fill_dyn(&d, knee_db, band_ratios, max_upward_boost_db);
         d.par_mix = par_mix_rows;
+        if (bands_only) {                            // min(|s|, |s| + inf, inf) = |s|: the maximizer / limiter step is the identity
+            d.max_k = 1.0f; d.max_c = INFINITY; d.max_top = INFINITY;
+        }
         bool general = par_mix_rows != nullptr;
         for (int i = 0; i < 4; ++i) general |= d.band[i].mode == 3;
         Epi e;

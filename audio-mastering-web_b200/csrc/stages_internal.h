@@ -59,7 +59,8 @@ void fill_parallel(DynParams* d, double ratio, double threshold_db);
 
 int st_target_curve(mm_ctx* c, const mm_geom* g, const float* in, float* out, const Pro& pro);
 int st_dynamics(mm_ctx* c, const mm_geom* g, const float* in, float* out, double knee_db, const double* crossovers_hz,
-                const double* band_ratios, double max_upward_boost_db, const double* par_mix_rows, float* peak);
+                const double* band_ratios, double max_upward_boost_db, const double* par_mix_rows, float* peak,
+                int bands_only = 0);     // bands_only: apply_multiband_dynamics alone (no maximizer, no limiter)
 int st_lufs(mm_ctx* c, const mm_geom* g, const float* in, const Pro& pro, double* lufs_dev, const double* target_dev,
             double* gain_row, double* gain_db);
 int st_final_balance(mm_ctx* c, const mm_geom* g, const float* in, float* out, const Pro& pro, float* peak);
@@ -100,6 +101,8 @@ int st_haas_imager(mm_ctx* c, const mm_geom* g, const float* in, float* out, dou
 // analyzers.cu / deesser.cu
 int st_deesser(mm_ctx* c, const mm_geom* g, const float* in, float* out, double threshold_db, double ratio, double freq_lo,
                double freq_hi, double attack_ms, double release_ms);
+// export.cu: apply_maximizer_lookahead (pipeline.py:548-573); not in place
+int st_maximizer_lookahead(mm_ctx* c, const mm_geom* g, const float* in, float* out, long long delay_n, int cf);
 // deesser.cu: apply_dynamic_eq over nbands x {w0, bw, threshold_db, ratio, attack_ms, release_ms, max_cut_db}; in == out allowed
 int st_dynamic_eq(mm_ctx* c, const mm_geom* g, const float* in, float* out, int nbands, const double* params);
 int st_true_peak(mm_ctx* c, const mm_geom* g, const float* in, double* tp_dev);

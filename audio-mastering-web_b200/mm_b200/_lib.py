@@ -64,6 +64,8 @@ SIGNATURES = {
     "mm_dev_apply_target_curve": (_i, [_vp, _gp, _vp, _vp, _i]),
     "mm_dev_apply_deesser": (_i, [_vp, _gp, _vp, _vp, _d, _d, _d, _d, _d, _d]),
     "mm_dev_apply_dynamics": (_i, [_vp, _gp, _vp, _vp, _d, _dp, _dp, _d]),
+    "mm_dev_apply_multiband_dynamics": (_i, [_vp, _gp, _vp, _vp, _d, _dp, _dp, _d]),
+    "mm_dev_apply_maximizer_lookahead": (_i, [_vp, _gp, _vp, _vp, _d]),
     "mm_dev_apply_maximizer": (_i, [_vp, _gp, _vp, _vp]),
     "mm_dev_apply_parallel_compression": (_i, [_vp, _gp, _vp, _vp, _d, _d, _d]),
     "mm_dev_measure_lufs": (_i, [_vp, _gp, _vp, _vp]),

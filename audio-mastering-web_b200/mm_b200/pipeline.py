@@ -41,6 +41,9 @@ STYLE_CONFIGS = {
 
 TRUE_PEAK_LIMIT_DB = -1.5
 MULTIBAND_CROSSOVERS_HZ = (214.0, 3500.0, 10000.0)
+MAXIMIZER_THRESHOLD_DB = -2.5
+MAXIMIZER_MARGIN_DB = -0.3
+FINAL_TRIM_DB = 0.5
 MULTIBAND_CONFIG = [(-7.2, 1.0, -7.2, 1.5), (-18.5, 2.2, -18.5, 1.8), (-17.0, 1.55, -17.0, 1.65), (-15.0, 1.35, -15.0, 1.2)]
 # (strength, noise_percentile) -- backend/app/pipeline.py:1439-1446
 DENOISE_PRESETS = {"vocal": (0.15, 25.0), "light": (0.20, 22.0), "medium": (0.5, 15.0), "aggressive": (0.75, 10.0),
@@ -119,9 +122,25 @@ def apply_dynamics(samples: np.ndarray, sr: int, knee_db: float = 6.0, crossover
     return _stage("apply_dynamics", samples, sr, C.c_double(knee_db), cx, br, C.c_double(max_upward_boost_db))
 
 
+def apply_multiband_dynamics(samples: np.ndarray, sr: int, knee_db: float = 6.0, crossovers_hz=None, band_ratios=None,
+                             max_upward_boost_db: float = 12.0) -> np.ndarray:
+    """backend/app/pipeline.py:414-481 (numpy compressor branch): the four-band split / compress / limit / gain / sum on its
+    own -- apply_dynamics without the maximizer and limiter behind it."""
+    cx = _lib.darr(crossovers_hz) if crossovers_hz is not None and len(crossovers_hz) == 3 else None
+    br = _lib.darr(band_ratios) if band_ratios is not None and len(band_ratios) == 4 else None
+    return _stage("apply_multiband_dynamics", samples, sr, C.c_double(knee_db), cx, br, C.c_double(max_upward_boost_db))
+
+
 def apply_maximizer(audio: np.ndarray) -> np.ndarray:
     """backend/app/pipeline.py:484-492 (module constants -2.5 / -0.3 dB)."""
     return _stage("apply_maximizer", audio, 44100)
+
+
+def apply_maximizer_lookahead(audio: np.ndarray, sr: int, lookahead_ms: float = 6.0) -> np.ndarray:
+    """backend/app/pipeline.py:548-573: the first ``lookahead_ms`` pass unlimited, the rest is the maximizer of the delayed
+    signal, with a 2 ms cross-fade before the seam."""
+    eng, b, mono = _up(audio, sr)
+    return _down(eng, eng.stage("apply_maximizer_lookahead", b, C.c_double(float(lookahead_ms))), mono)
 
 
 def apply_parallel_compression(audio: np.ndarray, sr: int, mix: float = 0.3, ratio: float = 8.0,

@@ -106,6 +106,12 @@ int mm_dev_apply_deesser(mm_ctx*, const mm_geom*, const float* in, float* out,
 int mm_dev_apply_dynamics(mm_ctx*, const mm_geom*, const float* in, float* out, double knee_db,
                           const double* crossovers_hz /*3 or NULL*/, const double* band_ratios /*4 or NULL*/,
                           double max_upward_boost_db);
+/* apply_multiband_dynamics alone (backend/app/pipeline.py:414-481, numpy branch): split, per-band soft knee + limiter + gain,
+ * sum -- apply_dynamics without its maximizer / limiter tail.  Arguments as mm_dev_apply_dynamics */
+int mm_dev_apply_multiband_dynamics(mm_ctx*, const mm_geom*, const float* in, float* out, double knee_db,
+                                    const double* crossovers_hz, const double* band_ratios, double max_upward_boost_db);
+/* apply_maximizer_lookahead (pipeline.py:548-573); not in place */
+int mm_dev_apply_maximizer_lookahead(mm_ctx*, const mm_geom*, const float* in, float* out, double lookahead_ms);
 /* apply_maximizer                      backend/app/pipeline.py:484-492 */
 int mm_dev_apply_maximizer(mm_ctx*, const mm_geom*, const float* in, float* out);
 /* apply_parallel_compression           backend/app/pipeline.py:1771-1797 */

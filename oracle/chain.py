@@ -311,6 +311,24 @@ def apply_maximizer(audio):
     return (np.sign(audio) * np.minimum(y, ceil_)).astype(np.float32)
 
 
+def apply_maximizer_lookahead(audio, sr, lookahead_ms=6.0):
+    """pipeline.py:548-573."""
+    delay_n = int(sr * (lookahead_ms / 1000.0))
+    if delay_n <= 0 or delay_n >= audio.shape[0]:
+        return apply_maximizer(audio)
+    a, mono = _cols(audio)
+    delayed = np.concatenate([np.zeros((delay_n, a.shape[1]), dtype=a.dtype), a[:-delay_n]], axis=0)
+    limited = apply_maximizer(delayed)
+    out = np.concatenate([a[:delay_n], limited[delay_n:]], axis=0).astype(np.float32)
+    cf = min(delay_n, max(2, int(sr * 0.002)))
+    for i in range(cf):
+        idx = delay_n - cf + i
+        if 0 <= idx < out.shape[0]:
+            w = (i + 1) / float(cf)
+            out[idx, :] = (1.0 - w) * a[idx, :] + w * limited[idx, :]
+    return _uncols(out, mono)
+
+
 def apply_dynamics(samples, sr, knee_db=6.0, crossovers_hz=None, band_ratios=None, max_upward_boost_db=12.0):
     """pipeline.py:610-641."""
     samples = np.asarray(samples)

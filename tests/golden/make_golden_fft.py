@@ -63,6 +63,14 @@ def main():
     st["dyneq_stereo"] = P.apply_dynamic_eq(x * np.float32(3.0), sr, bands)
     st["dyneq_mono"] = P.apply_dynamic_eq(np.ascontiguousarray(x[:9001, 0]) * np.float32(2.0), sr, bands[:2])
     st["dyneq_skipped"] = P.apply_dynamic_eq(x * np.float32(30.0), sr, bands[3:])
+    # the two remaining public stage functions of pipeline.py: the multiband stage on its own (:414-481) and the lookahead
+    # maximizer (:548-573)
+    st["multiband_only"] = P.apply_multiband_dynamics(x * np.float32(3.0), sr)
+    st["multiband_only_custom"] = P.apply_multiband_dynamics(np.ascontiguousarray(x[:, 0]) * np.float32(2.0), sr, knee_db=4.0,
+                                                              crossovers_hz=(214.0, 2230.0, 10000.0), band_ratios=(0.8, 2.0, 1.0, 3.0))
+    st["lookahead"] = P.apply_maximizer_lookahead(x * np.float32(3.0), sr, lookahead_ms=6.0)
+    st["lookahead_mono_3ms"] = P.apply_maximizer_lookahead(np.ascontiguousarray(x[:5000, 1]) * np.float32(4.0), sr, lookahead_ms=3.0)
+    st["lookahead_bypass"] = P.apply_maximizer_lookahead(x[:100] * np.float32(4.0), sr, lookahead_ms=6.0)
     # export_audio(auto_blank_sec=...) (pipeline.py:900-918, :976-977): trailing silence cut; kept lengths from the reference
     tail = x.copy()
     tail[17000:] *= np.float32(1e-4)                                     # below -50 dBFS after frame 17000

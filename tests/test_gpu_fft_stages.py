@@ -333,3 +333,16 @@ def test_fft_resample_four_pass_transforms(P):
         e2 = _err(back, x)
         print(f"[parity] resample x{os_} and back: {e2:.3e}")
         assert e2 <= 5e-5
+
+
+def test_multiband_only_and_lookahead_maximizer(P):
+    """The last two public stage functions of pipeline.py: apply_multiband_dynamics on its own (:414-481) and
+    apply_maximizer_lookahead (:548-573), against the reference's outputs."""
+    from test_oracle_golden import tail_stage_cases
+    g = load_golden("fft_stages")
+    for k, call in tail_stage_cases(P, g).items():
+        out = call()
+        e = _err(out, g[k])
+        print(f"[parity] {k}: {e:.3e}")
+        assert out.shape == g[k].shape and out.dtype == np.float32 and e <= 2e-6, (k, e)
+    assert (P.MAXIMIZER_THRESHOLD_DB, P.MAXIMIZER_MARGIN_DB, P.FINAL_TRIM_DB) == (-2.5, -0.3, 0.5)

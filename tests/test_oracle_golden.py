@@ -143,6 +143,25 @@ def test_dynamic_eq_stable_bands_match_reference_golden():
     assert np.max(np.abs(g["dyneq_stereo"] - np.clip(g["input"] * np.float32(3.0), -1, 1))) > 1e-2
 
 
+def tail_stage_cases(mod, g):
+    x, sr = g["input"], int(g["sr"])
+    return {"multiband_only": lambda: mod.apply_multiband_dynamics(x * np.float32(3.0), sr),
+            "multiband_only_custom": lambda: mod.apply_multiband_dynamics(np.ascontiguousarray(x[:, 0]) * np.float32(2.0), sr, knee_db=4.0,
+                                                                          crossovers_hz=(214.0, 2230.0, 10000.0), band_ratios=(0.8, 2.0, 1.0, 3.0)),
+            "lookahead": lambda: mod.apply_maximizer_lookahead(x * np.float32(3.0), sr, lookahead_ms=6.0),
+            "lookahead_mono_3ms": lambda: mod.apply_maximizer_lookahead(np.ascontiguousarray(x[:5000, 1]) * np.float32(4.0), sr, lookahead_ms=3.0),
+            "lookahead_bypass": lambda: mod.apply_maximizer_lookahead(x[:100] * np.float32(4.0), sr, lookahead_ms=6.0)}
+
+
+def test_multiband_only_and_lookahead_maximizer_match_reference_golden():
+    """apply_multiband_dynamics (pipeline.py:414-481) and apply_maximizer_lookahead (:548-573)."""
+    g = load_golden("fft_stages")
+    for k, call in tail_stage_cases(oc, g).items():
+        v = call()
+        assert v.shape == g[k].shape, k
+        assert np.max(np.abs(np.asarray(v, dtype=np.float64) - g[k])) <= 1e-7, k
+
+
 def test_auto_blank_end_matches_reference_golden():
     """export_audio(auto_blank_sec=...) (pipeline.py:900-918, :976-977): kept lengths from the reference's WAV sizes."""
     g = load_golden("fft_stages")
