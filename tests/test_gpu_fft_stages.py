@@ -346,3 +346,34 @@ def test_multiband_only_and_lookahead_maximizer(P):
         print(f"[parity] {k}: {e:.3e}")
         assert out.shape == g[k].shape and out.dtype == np.float32 and e <= 2e-6, (k, e)
     assert (P.MAXIMIZER_THRESHOLD_DB, P.MAXIMIZER_MARGIN_DB, P.FINAL_TRIM_DB) == (-2.5, -0.3, 0.5)
+
+
+def test_second_wave_stages_batch_equals_single_track(P):
+    """Tracks are independent: a batch of different tracks through the STFT denoiser, the dynamic EQ, the spectral envelope and
+    the lookahead maximizer returns, bit for bit, what each track returns alone."""
+    import ctypes as C
+    import torch
+    from mm_b200 import _lib
+    from mm_b200.engine import get_engine
+    eng = get_engine()
+    sr, n = 48000, 50000
+    tracks = [_material(n, sr, 100 + t) * np.float32(0.5 + 0.4 * t) for t in range(3)]
+    b = eng.upload(tracks, sr)
+    bands = [{"freq": 3000, "q": 0.5, "threshold_db": -30, "ratio": 3.0, "attack_ms": 5, "release_ms": 60, "max_cut_db": -6}]
+    row = _lib.darr([3000 / 24000, (3000 / 24000) / 0.5, -30, 3.0, 5, 60, -6])
+    outs = {
+        "denoise": eng.download(eng.stage("apply_spectral_denoise", b, C.c_double(0.6), C.c_double(20.0))),
+        "dyneq": eng.download(eng.stage("apply_dynamic_eq", b, 1, row)),
+        "lookahead": eng.download(eng.stage("apply_maximizer_lookahead", b, C.c_double(6.0))),
+    }
+    with torch.cuda.stream(eng.stream):
+        env = torch.empty(3 * 4097, dtype=torch.float32, device=eng.tdev)
+        g = b.geom
+        _lib.check(eng.lib.mm_dev_spectral_envelope(eng.ctx, C.byref(g), b.ptr, C.c_void_p(env.data_ptr())))
+        eng.sync()
+        env = env.cpu().numpy().reshape(3, 4097)
+    for t in range(3):
+        assert np.array_equal(outs["denoise"][t], P.apply_spectral_denoise(tracks[t], sr, 0.6, 20.0)), t
+        assert np.array_equal(outs["dyneq"][t], P.apply_dynamic_eq(tracks[t], sr, bands)), t
+        assert np.array_equal(outs["lookahead"][t], P.apply_maximizer_lookahead(tracks[t], sr, 6.0)), t
+        assert np.array_equal(env[t], P.compute_spectral_envelope(tracks[t], sr)), t
