@@ -81,7 +81,7 @@ template <int MODE> __device__ __forceinline__ float env_step(float e, float ep,
 // One thread = one chunk (+ its halo) of one row: a strictly sequential recurrence, so the kernel is
 // latency bound by design; each thread streams its samples through a private ring of 128-byte lines in
 // shared memory (cp.async, kEnvDepth lines in flight) so that HBM latency never sits on the chain.
-constexpr int kEnvDepth = 8;
+constexpr int kEnvDepth = 4;
 constexpr int kEnvThreads = 32;
 
 template <int MODE> __global__ void __launch_bounds__(kEnvThreads) envelope_gain_kernel(const EnvArgs P) {
@@ -247,9 +247,11 @@ static int launch_envelope(mm_ctx* c, const mm_geom* g, EnvArgs& A, double attac
     long long halo = slow < 1.0 ? (long long)std::ceil(17.5 / -std::log(slow)) : nceil;
     halo = std::min<long long>(((halo + 31) / 32) * 32, nceil);
     A.halo = halo;
-    // chunk = halo / 2 (three times the work, short critical path) until the grid exceeds ~8 warps per SM
+    // chunk = halo / 2 (three times the work, short critical path) until the grid exceeds ~14 warps per SM.  Measured at the
+    // bench size (972 one-warp CTAs): ring depth 8 (32 KB per CTA, 6 CTAs/SM = 888 slots) left a tail wave, 6.5 ms; depth 4
+    // (12 CTAs/SM, one wave) 4.85 ms; chunk = halo / 4 (five times the work, twice the warps) 7.9 ms
     long long chunk = std::max<long long>(((halo / 2 + 31) / 32) * 32, 4096);
-    while ((long long)rows * ((g->n + chunk - 1) / chunk) > 148LL * 8 * 32 && chunk < nceil) chunk *= 2;
+    while ((long long)rows * ((g->n + chunk - 1) / chunk) > 148LL * 14 * 32 && chunk < nceil) chunk *= 2;
     A.chunk = chunk;
     A.nchunks = (int)((g->n + A.chunk - 1) / A.chunk);
     const long long total = (long long)rows * A.nchunks;
