@@ -295,6 +295,7 @@ static int bf_get_chirp(mm_ctx* c, long long N, long long nin, long long nout, i
     if (it != cache.chirps.end()) { *out = &it->second; return 0; }
     if (cache.order.size() >= 6) {                  // a handful of (n, num) pairs is all a service sees; bound the filters kept
         MM_CUDA(cudaStreamSynchronize(c->stream));
+        c->workspace_bytes -= (int64_t)(cache.chirps[cache.order.front()].fft->L * sizeof(float2));
         cudaFree(cache.chirps[cache.order.front()].FW);
         cache.chirps.erase(cache.order.front());
         cache.order.erase(cache.order.begin());
@@ -307,6 +308,7 @@ static int bf_get_chirp(mm_ctx* c, long long N, long long nin, long long nout, i
     MM_TRY(bf_get_fft(c, p, &P.fft));
     const long long L = P.fft->L;
     MM_CUDA(cudaMalloc(&P.FW, L * sizeof(float2)));
+    c->workspace_bytes += (int64_t)(L * sizeof(float2));
     bf_chirp_filter_kernel<<<(unsigned)((L + 255) / 256), 256, 0, c->stream>>>(P.FW, L, chirp_mod(N), nin, nout, sign);
     MM_CUDA(cudaGetLastError());
     MM_TRY(bf_run(c, P.fft, P.FW, L, 1, 0, nullptr));

@@ -346,6 +346,16 @@ void mm_ctx_destroy(mm_ctx* c) {
     delete c;
 }
 
+int mm_ctx_release_workspace(mm_ctx* c) {
+    MM_API_BEGIN(c);
+    MM_CUDA(cudaStreamSynchronize(c->stream));
+    bigfft_release(c);
+    for (int i = 0; i < SL_COUNT; ++i)
+        if (c->slots[i].p) { cudaFree(c->slots[i].p); c->slots[i].p = nullptr; c->slots[i].cap = 0; }
+    c->workspace_bytes = 0;
+    return 0;
+}
+
 int mm_ctx_sync(mm_ctx* c) {
     MM_API_BEGIN(c);
     MM_CUDA(cudaStreamSynchronize(c->stream));

@@ -52,6 +52,7 @@ SIGNATURES = {
     "mm_ctx_create": (_i, [_i, _vp, C.POINTER(_vp)]),
     "mm_ctx_destroy": (None, [_vp]),
     "mm_ctx_sync": (_i, [_vp]),
+    "mm_ctx_release_workspace": (_i, [_vp]),
     "mm_ctx_launch_count": (_i64, [_vp]),
     "mm_ctx_timing": (_i, [_vp, _i]),
     "mm_ctx_kernel_times": (_i, [_vp, C.POINTER(KTime), _i, C.POINTER(_i)]),

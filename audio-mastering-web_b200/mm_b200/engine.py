@@ -106,6 +106,10 @@ class Engine:
             self.sync()
             return il.cpu().numpy()
 
+    def release_workspace(self):
+        """Give the device scratch back (it grows on demand and stays at its high-water mark otherwise)."""
+        _lib.check(self.lib.mm_ctx_release_workspace(self.ctx))
+
     def sync(self):
         _lib.check(self.lib.mm_ctx_sync(self.ctx))
 

@@ -72,6 +72,9 @@ int64_t     mm_row_stride(int64_t n);
 int  mm_ctx_create(int device, void* stream, mm_ctx** out);
 void mm_ctx_destroy(mm_ctx* ctx);
 int  mm_ctx_sync(mm_ctx* ctx);
+/* Free the context's device scratch (arena slots, FFT plan spectra); they grow on demand and otherwise stay at their high-water
+ * mark -- a service calls this after an unusually large job (a 2-hour file, a 64-track denoise).  Filter tables are kept. */
+int  mm_ctx_release_workspace(mm_ctx* ctx);
 /* Number of kernels this context has launched so far (bench.py's gpu_launches). */
 int64_t mm_ctx_launch_count(mm_ctx* ctx);
 /* Device-time accounting: when enabled, every kernel is bracketed by CUDA events on the

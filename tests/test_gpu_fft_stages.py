@@ -377,3 +377,16 @@ def test_second_wave_stages_batch_equals_single_track(P):
         assert np.array_equal(outs["dyneq"][t], P.apply_dynamic_eq(tracks[t], sr, bands)), t
         assert np.array_equal(outs["lookahead"][t], P.apply_maximizer_lookahead(tracks[t], sr, 6.0)), t
         assert np.array_equal(env[t], P.compute_spectral_envelope(tracks[t], sr)), t
+
+
+def test_release_workspace(P):
+    """mm_ctx_release_workspace: scratch returns to zero and the next call simply allocates again, same result."""
+    from mm_b200.engine import get_engine
+    x = load_golden("fft_stages")["input"]
+    a = P.resample_audio(x, 48000, 44100)
+    eng = get_engine()
+    assert eng.lib.mm_ctx_workspace_bytes(eng.ctx) > 0
+    eng.release_workspace()
+    assert eng.lib.mm_ctx_workspace_bytes(eng.ctx) == 0
+    assert np.array_equal(P.resample_audio(x, 48000, 44100), a)
+    assert np.array_equal(P.apply_spectral_denoise(x, 48000, 0.5), P.apply_spectral_denoise(x, 48000, 0.5))
