@@ -2,6 +2,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <mutex>
 #include <vector>
 
 #include "context.h"
@@ -23,7 +24,8 @@ constexpr int kTpTile = kTpThreads * kTpPer;      // 2048 input samples per CTA
 constexpr int kTpHalo = 10;
 constexpr int kTpTaps = 21;
 
-struct TpCoef { float h[4][kTpTaps]; };           // h[p][d] = h81[4 d + p] (0 where 4 d + p > 80)
+struct TpCoef { float h[4][kTpTaps]; };
+struct CorrAcc { double sl, sr, slr, sll, srr; unsigned pk; unsigned pad; };           // h[p][d] = h81[4 d + p] (0 where 4 d + p > 80)
 
 __global__ void __launch_bounds__(kTpThreads) true_peak_kernel(const float* __restrict__ in, long long n, long long stride,
                                                                int channels, const __grid_constant__ TpCoef K,
@@ -150,6 +152,104 @@ __global__ void __launch_bounds__(kTpThreads) true_peak_kernel8(const float* __r
     }
 }
 
+// True peak and the stereo-correlation sums of a stereo track in ONE pass over its samples: the FIR is FP32 bound and leaves the
+// memory system idle, the five float64 sums + sample peak ride on the centre samples the register windows already hold.
+__global__ void __launch_bounds__(kTpThreads) true_peak_corr_kernel(const float* __restrict__ in, long long n, long long stride,
+                                                                    const __grid_constant__ TpCoef K, float* __restrict__ peak_bits,
+                                                                    CorrAcc* __restrict__ acc) {
+    __shared__ float sx[2][2][kTp8Buf];
+    const int track = blockIdx.y;
+    const float* src0 = in + (size_t)(track * 2) * (size_t)stride + kLead;
+    const float* src1 = src0 + stride;
+    const long long tile0 = (long long)blockIdx.x * kTp8Tiles;
+    const long long ntiles = (n + kTpTile - 1) / kTpTile;
+    const int T = (int)min((long long)kTp8Tiles, ntiles - tile0);
+    float pre[2][kTp8Loads];
+    auto fetch = [&](long long tile) {
+        const long long base = tile * kTpTile - kTp8Lead;
+#pragma unroll
+        for (int r = 0; r < kTp8Loads; ++r) {
+            const int m = threadIdx.x + kTpThreads * r;
+            const long long i = base + m;
+            const bool ok = m < kTp8Span && i >= 0 && i < n;
+            pre[0][r] = ok ? __ldcs(src0 + i) : 0.f;
+            pre[1][r] = ok ? __ldcs(src1 + i) : 0.f;
+        }
+    };
+    fetch(tile0);
+    float pk = 0.f, spk = 0.f;
+    double v[5] = {0, 0, 0, 0, 0};
+    const float h0 = K.h[0][10];
+#pragma unroll 1
+    for (int k = 0; k < T; ++k) {
+#pragma unroll
+        for (int r = 0; r < kTp8Loads; ++r) {
+            const int m = threadIdx.x + kTpThreads * r;
+            if (m < kTp8Span) { sx[k & 1][0][m + (m >> 3)] = pre[0][r]; sx[k & 1][1][m + (m >> 3)] = pre[1][r]; }
+        }
+        __syncthreads();
+        if (k + 1 < T) fetch(tile0 + k + 1);
+        const long long base = (tile0 + k) * kTpTile;
+        float xc[2][kTpPer];
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+            float xw[27];
+            const float* wp0 = sx[k & 1][c] + 9 * threadIdx.x;
+#pragma unroll
+            for (int j = 0; j < 27; ++j) xw[j] = wp0[((7 + j) >> 3) * 9 + ((7 + j) & 7)];
+            float a1[kTpPer], a2[kTpPer], a3[kTpPer];
+#pragma unroll
+            for (int u = 0; u < kTpPer; ++u) a1[u] = a2[u] = a3[u] = 0.f;
+#pragma unroll
+            for (int d = 0; d < kTpTaps - 1; ++d) {
+                const float h1 = K.h[1][d], h2 = K.h[2][d], h3 = K.h[3][d];
+#pragma unroll
+                for (int u = 0; u < kTpPer; ++u) {
+                    const float xv = xw[u + 19 - d];
+                    a1[u] = fmaf(h1, xv, a1[u]);
+                    a2[u] = fmaf(h2, xv, a2[u]);
+                    a3[u] = fmaf(h3, xv, a3[u]);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < kTpPer; ++u) {
+                xc[c][u] = xw[u + 9];
+                const float a0 = h0 * xw[u + 9];
+                if (base + 8 * (long long)threadIdx.x + u < n)
+                    pk = fmaxf(pk, fmaxf(fmaxf(fabsf(a0), fabsf(a1[u])), fmaxf(fabsf(a2[u]), fabsf(a3[u]))));
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < kTpPer; ++u) {                   // samples past n were staged as zeros: they add nothing
+            const double l = (double)xc[0][u], rr = (double)xc[1][u];
+            v[0] += l; v[1] += rr; v[2] = fma(l, rr, v[2]); v[3] = fma(l, l, v[3]); v[4] = fma(rr, rr, v[4]);
+            spk = fmaxf(spk, fmaxf(fabsf(xc[0][u]), fabsf(xc[1][u])));
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        pk = fmaxf(pk, __shfl_xor_sync(0xffffffffu, pk, o));
+        spk = fmaxf(spk, __shfl_xor_sync(0xffffffffu, spk, o));
+#pragma unroll
+        for (int q = 0; q < 5; ++q) v[q] += shfl_xor_d(v[q], o);
+    }
+    __shared__ float wp[kTpThreads / 32], ws[kTpThreads / 32];
+    __shared__ double sv[kTpThreads / 32][5];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) { wp[warp] = pk; ws[warp] = spk; for (int q = 0; q < 5; ++q) sv[warp][q] = v[q]; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < kTpThreads / 32; ++w) {
+            pk = fmaxf(pk, wp[w]); spk = fmaxf(spk, ws[w]);
+            for (int q = 0; q < 5; ++q) v[q] += sv[w][q];
+        }
+        if (pk > 0.f) atomicMax(reinterpret_cast<int*>(peak_bits + track), __float_as_int(pk));
+        CorrAcc* a = acc + track;
+        atomicAdd(&a->sl, v[0]); atomicAdd(&a->sr, v[1]); atomicAdd(&a->slr, v[2]); atomicAdd(&a->sll, v[3]); atomicAdd(&a->srr, v[4]);
+        atomicMax(&a->pk, __float_as_uint(spk));
+    }
+}
+
 __global__ void peak_to_db_kernel(const float* peak_bits, int tracks, double* db) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t < tracks) db[t] = 20.0 * log10(fmax((double)peak_bits[t], 1e-12));
@@ -185,10 +285,16 @@ static void true_peak_fir(double* h81) {
     for (int j = 0; j < N; ++j) h81[j] = h81[j] / sum * 4.0;
 }
 
-int st_true_peak(mm_ctx* c, const mm_geom* g, const float* in, double* tp_dev) {
-    static TpCoef K;
-    static bool built = false, delay0 = false;
-    if (!built) {
+static TpCoef g_tp_coef;
+static bool g_tp_delay0 = false;
+static const TpCoef* tp_coef() { return &g_tp_coef; }
+// builds the polyphase coefficients once; returns whether branch 0 is the pure delay the register-tiled kernels assume
+static bool tp_build_coef() {
+    static std::once_flag once;
+    std::call_once(once, [] {
+        TpCoef& K = g_tp_coef;
+        bool& delay0 = g_tp_delay0;
+        {
         double h[81];
         true_peak_fir(h);
         memset(&K, 0, sizeof(K));
@@ -198,8 +304,14 @@ int st_true_peak(mm_ctx* c, const mm_geom* g, const float* in, double* tp_dev) {
         delay0 = true;                                  // branch 0 is a pure delay (all other taps are sinc zeros)?
         for (int d = 0; d < kTpTaps; ++d)
             if (d != 10 && std::fabs(h[4 * d]) > 1e-12) delay0 = false;
-        built = true;
-    }
+        }
+    });
+    return g_tp_delay0;
+}
+
+int st_true_peak(mm_ctx* c, const mm_geom* g, const float* in, double* tp_dev) {
+    const bool delay0 = tp_build_coef();
+    const TpCoef& K = g_tp_coef;
     float* bits;
     MM_TRY(arena(c, SL_PEAKBITS, (size_t)g->tracks, &bits));
     MM_CUDA(cudaMemsetAsync(bits, 0, (size_t)g->tracks * sizeof(float), c->stream));
@@ -348,7 +460,6 @@ int st_spectrum_bars(mm_ctx* c, const mm_geom* g, const float* in, int view, dou
 // ---------------------------------------------------------------------------------------------------
 // measure_stereo_correlation (backend/app/pipeline.py:766-791) + sample peak: five float64 sums
 // ---------------------------------------------------------------------------------------------------
-struct CorrAcc { double sl, sr, slr, sll, srr; unsigned pk; unsigned pad; };
 
 constexpr int kCorrThreads = 256;
 constexpr int kCorrPerBlock = kCorrThreads * 4 * 4;
@@ -427,6 +538,37 @@ int st_correlation(mm_ctx* c, const mm_geom* g, const float* in, double* corr_de
         corr_kernel<<<grid, kCorrThreads, 0, c->stream>>>(in, g->n, g->stride, g->channels, acc);
     }
     MM_CUDA(cudaGetLastError());
+    {
+        KernelScope ks(c, "stereo_corr_final");
+        corr_final_kernel<<<(g->tracks + 127) / 128, 128, 0, c->stream>>>(acc, g->tracks, g->channels, g->n, corr_dev, peak_dev);
+    }
+    MM_CUDA(cudaGetLastError());
+    return 0;
+}
+
+
+// true peak + correlation + sample peak of stereo tracks in one pass (mono: the two separate kernels; no correlation there)
+int st_true_peak_corr(mm_ctx* c, const mm_geom* g, const float* in, double* tp_dev, double* corr_dev, double* peak_dev) {
+    if (g->channels != 2 || !tp_build_coef()) {
+        MM_TRY(st_true_peak(c, g, in, tp_dev));
+        return st_correlation(c, g, in, corr_dev, peak_dev);
+    }
+    float* bits;
+    CorrAcc* acc;
+    MM_TRY(arena(c, SL_PEAKBITS, (size_t)g->tracks, &bits));
+    MM_TRY(arena(c, SL_ENV0, (size_t)g->tracks, &acc));
+    MM_CUDA(cudaMemsetAsync(bits, 0, (size_t)g->tracks * sizeof(float), c->stream));
+    MM_CUDA(cudaMemsetAsync(acc, 0, (size_t)g->tracks * sizeof(CorrAcc), c->stream));
+    const dim3 grid((unsigned)((g->n + (long long)kTpTile * kTp8Tiles - 1) / ((long long)kTpTile * kTp8Tiles)), (unsigned)g->tracks);
+    {
+        KernelScope ks(c, "true_peak_fir4x_corr");
+        true_peak_corr_kernel<<<grid, kTpThreads, 0, c->stream>>>(in, g->n, g->stride, *tp_coef(), bits, acc);
+    }
+    MM_CUDA(cudaGetLastError());
+    {
+        KernelScope ks(c, "peak_to_db");
+        peak_to_db_kernel<<<(g->tracks + 127) / 128, 128, 0, c->stream>>>(bits, g->tracks, tp_dev);
+    }
     {
         KernelScope ks(c, "stereo_corr_final");
         corr_final_kernel<<<(g->tracks + 127) / 128, 128, 0, c->stream>>>(acc, g->tracks, g->channels, g->n, corr_dev, peak_dev);

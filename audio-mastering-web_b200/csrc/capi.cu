@@ -888,6 +888,11 @@ int mm_dev_true_peak(mm_ctx* c, const mm_geom* g, const float* in, double* tp) {
     MM_TRY(check_geom(g));
     return st_true_peak(c, g, in, tp);
 }
+int mm_dev_true_peak_correlation(mm_ctx* c, const mm_geom* g, const float* in, double* tp, double* corr, double* peak) {
+    MM_API_BEGIN(c);
+    MM_TRY(check_geom(g));
+    return st_true_peak_corr(c, g, in, tp, corr, peak);
+}
 int mm_dev_spectrum_bars(mm_ctx* c, const mm_geom* g, const float* in, int view, double* bars) {
     MM_API_BEGIN(c);
     MM_TRY(check_geom(g));

@@ -106,6 +106,8 @@ int st_maximizer_lookahead(mm_ctx* c, const mm_geom* g, const float* in, float* 
 // deesser.cu: apply_dynamic_eq over nbands x {w0, bw, threshold_db, ratio, attack_ms, release_ms, max_cut_db}; in == out allowed
 int st_dynamic_eq(mm_ctx* c, const mm_geom* g, const float* in, float* out, int nbands, const double* params);
 int st_true_peak(mm_ctx* c, const mm_geom* g, const float* in, double* tp_dev);
+// true peak + stereo correlation + sample peak in one pass over the samples (stereo); mono falls back to the two kernels
+int st_true_peak_corr(mm_ctx* c, const mm_geom* g, const float* in, double* tp_dev, double* corr_dev, double* peak_dev);
 int st_spectrum_bars(mm_ctx* c, const mm_geom* g, const float* in, int view, double* bars_dev);
 int st_correlation(mm_ctx* c, const mm_geom* g, const float* in, double* corr_dev, double* peak_dev);
 

@@ -84,6 +84,7 @@ SIGNATURES = {
     "mm_dev_true_peak": (_i, [_vp, _gp, _vp, _vp]),
     "mm_dev_spectrum_bars": (_i, [_vp, _gp, _vp, _i, _vp]),
     "mm_dev_stereo_correlation": (_i, [_vp, _gp, _vp, _vp, _vp]),
+    "mm_dev_true_peak_correlation": (_i, [_vp, _gp, _vp, _vp, _vp, _vp]),
     "mm_dev_signal_metrics": (_i, [_vp, _gp, _vp, _vp]),
     "mm_dev_master": (_i, [_vp, _gp, _i, C.POINTER(Style), _vp, _vp, _vp, _vp, _u64, _vp, _u32]),
     "mm_dev_apply_target_curve_linear_phase": (_i, [_vp, _gp, _vp, _vp, _i]),

@@ -184,6 +184,14 @@ class Engine:
         keep = b.n if last < 0 else min(b.n, last + 1 + n_silence)
         return Batch(b.t, b.tracks, b.channels, keep, b.sr)
 
+    def true_peak_correlation(self, b: Batch):
+        """true peak (dBTP), stereo correlation and sample peak per track from one pass over the samples."""
+        tp, corr, peak = self._doubles(b.tracks), self._doubles(b.tracks), self._doubles(b.tracks)
+        g = b.geom
+        _lib.check(self.lib.mm_dev_true_peak_correlation(self.ctx, C.byref(g), b.ptr, C.c_void_p(tp.data_ptr()), C.c_void_p(corr.data_ptr()),
+                                                         C.c_void_p(peak.data_ptr())))
+        return self._to_host(tp), self._to_host(corr), self._to_host(peak)
+
     def quantize_pcm24(self, b: Batch) -> np.ndarray:
         """-> int32 (tracks, n, channels) holding 24-bit samples (libsndfile's float -> PCM_24 conversion)."""
         torch = _torch()

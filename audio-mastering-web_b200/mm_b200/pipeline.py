@@ -512,8 +512,7 @@ def analyze_batch(tracks, sr, spectrum=True, eng: Optional[Engine] = None) -> li
     eng = eng or get_engine()
     b = eng.upload(tracks, int(sr))
     lufs = eng.measure_lufs(b)
-    tp = eng.true_peak(b)
-    corr, peak = eng.stereo_correlation(b)
+    tp, corr, peak = eng.true_peak_correlation(b)
     bars = [eng.spectrum_bars(b, v) for v in ((0, 1, 2) if (spectrum and b.channels == 2) else ((0,) if spectrum else ()))]
     out = []
     for t in range(b.tracks):

@@ -590,8 +590,7 @@ def run_analyze(args):
     def step(i):
         for _ in range(nbatch):
             _lib.check(eng.lib.mm_dev_measure_lufs(eng.ctx, C.byref(g), src.ptr, ptr(res["lufs"])))
-            _lib.check(eng.lib.mm_dev_true_peak(eng.ctx, C.byref(g), src.ptr, ptr(res["tp"])))
-            _lib.check(eng.lib.mm_dev_stereo_correlation(eng.ctx, C.byref(g), src.ptr, ptr(res["corr"]), ptr(res["peak"])))
+            _lib.check(eng.lib.mm_dev_true_peak_correlation(eng.ctx, C.byref(g), src.ptr, ptr(res["tp"]), ptr(res["corr"]), ptr(res["peak"])))
             for v in range(3):
                 _lib.check(eng.lib.mm_dev_spectrum_bars(eng.ctx, C.byref(g), src.ptr, v, ptr(res[f"bars{v}"])))
 
@@ -639,8 +638,7 @@ def run_analyze(args):
             il.copy_(hin, non_blocking=True)
             _lib.check(eng.lib.mm_dev_deinterleave(eng.ctx, C.byref(g), ptr(il), src.ptr))
             _lib.check(eng.lib.mm_dev_measure_lufs(eng.ctx, C.byref(g), src.ptr, ptr(res["lufs"])))
-            _lib.check(eng.lib.mm_dev_true_peak(eng.ctx, C.byref(g), src.ptr, ptr(res["tp"])))
-            _lib.check(eng.lib.mm_dev_stereo_correlation(eng.ctx, C.byref(g), src.ptr, ptr(res["corr"]), ptr(res["peak"])))
+            _lib.check(eng.lib.mm_dev_true_peak_correlation(eng.ctx, C.byref(g), src.ptr, ptr(res["tp"]), ptr(res["corr"]), ptr(res["peak"])))
             for v in range(3):
                 _lib.check(eng.lib.mm_dev_spectrum_bars(eng.ctx, C.byref(g), src.ptr, v, ptr(res[f"bars{v}"])))
             for k in res:
@@ -659,7 +657,7 @@ def run_analyze(args):
         wall = float(t.item())
     e2e = {"value": world * sub * dur / wall, "unit": "audio-s/s", "h2d_bytes_per_step": sub * n * 8,
            "d2h_bytes_per_step": int(sum(v.numel() for v in res.values()) * 8), "clips_per_step": sub,
-           "api": "mm_dev_measure_lufs / true_peak / stereo_correlation / spectrum_bars on clips copied from pinned host memory"}
+           "api": "mm_dev_measure_lufs / true_peak_correlation / spectrum_bars on clips copied from pinned host memory"}
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -680,8 +678,8 @@ def run_analyze(args):
                      "unit": "GB/s", "frac": alg / (kms / kcnt * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": alg,
                      "path": {"algorithmic_bytes_per_stereo_frame": 8.0, "achieved": 8.0 * done * n * args.steps / (ms * 1e-3) / 1e9 / world,
-                              "note": "SURVEY 8d counts ONE fused read; this round runs three reading kernels (meter, true-peak FIR, "
-                                      "correlation) -- the FIR is FP32-FMA bound (81 MAC/sample), not HBM bound"},
+                              "note": "SURVEY 8d counts ONE fused read; this build runs two reading kernels (the meter, and the true-peak FIR "
+                                      "with the correlation sums riding on it) -- the FIR is FP32-FMA bound (61 MAC/sample), not HBM bound"},
                      "kernels": {k: {"ms_per_launch": v[0] / v[1], "launches_per_step": v[1] / args.steps} for k, v in
                                  sorted(ktimes.items(), key=lambda kv: -kv[1][0])[:8]}},
         "cpu_baseline": None, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,

@@ -204,6 +204,9 @@ int mm_dev_spectrum_bars(mm_ctx*, const mm_geom*, const float* in, int view, dou
 /* measure_stereo_correlation           backend/app/pipeline.py:766-791; out: device double[tracks]
  * (NaN encodes the reference's None), plus sample peak per track (double[tracks], may be NULL) */
 int mm_dev_stereo_correlation(mm_ctx*, const mm_geom*, const float* in, double* corr_dev, double* sample_peak_dev);
+/* mm_dev_true_peak and mm_dev_stereo_correlation in ONE pass over the samples (the FIR is FP32 bound: the correlation sums ride
+ * on the samples its register windows hold); tp / corr / peak as in the two separate calls */
+int mm_dev_true_peak_correlation(mm_ctx*, const mm_geom*, const float* in, double* tp_db, double* corr, double* peak);
 
 /* mastering_trace.signal_metrics (backend/app/mastering_trace.py:115-149) as a device reduction: out3_dev[tracks][3] =
  * max |x| over the finite samples, count of non-finite samples, count of infinities. */

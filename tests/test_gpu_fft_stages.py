@@ -390,3 +390,24 @@ def test_release_workspace(P):
     assert eng.lib.mm_ctx_workspace_bytes(eng.ctx) == 0
     assert np.array_equal(P.resample_audio(x, 48000, 44100), a)
     assert np.array_equal(P.apply_spectral_denoise(x, 48000, 0.5), P.apply_spectral_denoise(x, 48000, 0.5))
+
+
+def test_fused_true_peak_correlation_equals_separate_kernels(P):
+    """mm_dev_true_peak_correlation (one pass) == mm_dev_true_peak + mm_dev_stereo_correlation: true peak and sample peak bit for
+    bit, correlation to float64 summation order; mono batches take the separate kernels."""
+    from mm_b200.engine import get_engine
+    eng = get_engine()
+    sr = 44100
+    for n in (30 * 44100, 16384 * 3 + 5, 1000):
+        tracks = [_material(n, sr, 40 + t) * np.float32(0.7 + 0.3 * t) for t in range(3)]
+        b = eng.upload(tracks, sr)
+        tp, corr, peak = eng.true_peak_correlation(b)
+        tp0 = eng.true_peak(b)
+        corr0, peak0 = eng.stereo_correlation(b)
+        assert np.array_equal(tp, tp0) and np.array_equal(peak, peak0), n
+        assert np.max(np.abs(corr - corr0)) <= 1e-12, (n, corr, corr0)
+    mono = eng.upload([_material(5000, sr, 3)[:, 0]], sr)
+    tp, corr, peak = eng.true_peak_correlation(mono)
+    assert np.array_equal(tp, eng.true_peak(mono)) and np.isnan(corr[0])
+    rec = P.analyze_batch([_material(60000, sr, 9)], sr)[0]
+    assert set(rec) >= {"lufs", "true_peak_dbfs", "sample_peak", "correlation", "spectrum_bars"}
