@@ -961,9 +961,11 @@ static int master_host_impl(mm_ctx* c, int chain, int32_t tracks, int64_t n, int
     if (!c->h2d_stream) MM_CUDA(cudaStreamCreateWithFlags(&c->h2d_stream, cudaStreamNonBlocking));
     if (!c->d2h_stream) MM_CUDA(cudaStreamCreateWithFlags(&c->d2h_stream, cudaStreamNonBlocking));
     const size_t per_track = (size_t)n * channels;                  // interleaved samples of one track
-    int tc = 0;                                                     // tracks per chunk: ~512 MB of float32 input
+    int tc = 0;                                                     // tracks per chunk: ~256 MB of float32 input.  Measured (64 x 180 s,
+                                                                    // float32 / PCM_16 in): 2 tracks 140 / 173 k audio-s/s, 4: 138 / 189 k,
+                                                                    // 8: 131 / 188 k, 16: 118 / 168 k -- short pipeline fill against small grids
     if (const char* e = getenv("MM_HOST_CHUNK")) tc = atoi(e);
-    if (tc <= 0) tc = (int)std::max<size_t>(1, ((size_t)512 << 20) / std::max<size_t>(per_track * sizeof(float), 1));
+    if (tc <= 0) tc = (int)std::max<size_t>(1, ((size_t)256 << 20) / std::max<size_t>(per_track * sizeof(float), 1));
     tc = std::min(tc, (int)tracks);
     const int nchunks = (tracks + tc - 1) / tc;
     const size_t cframes = (size_t)tc * per_track;
