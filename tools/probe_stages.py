@@ -72,6 +72,8 @@ def main():
         ir = np.ascontiguousarray((np.hanning(8192) / 4096.0).astype(np.float32))
         timed(eng, "fir_same (8192 taps, reference match)", lambda: eng.stage("fir_same", b, ir.ctypes.data_as(C.c_void_p), 8192, 1, out=out),
               cs, a.reps, 4 * 2)
+    if on("truepeak"):
+        timed(eng, "true peak + correlation (fused)", lambda: eng.true_peak_correlation(b), cs, a.reps, 4)
     if on("refenv"):
         env = torch.empty(a.tracks * 4097, dtype=torch.float32, device=eng.tdev)
         g = b.geom
