@@ -292,7 +292,14 @@ static int bf_get_chirp(mm_ctx* c, long long N, long long nin, long long nout, i
     char key[96];
     snprintf(key, sizeof key, "%lld/%lld/%lld/%d", N, nin, nout, sign);
     auto it = cache.chirps.find(key);
-    if (it != cache.chirps.end()) { *out = &it->second; return 0; }
+    if (it != cache.chirps.end()) {
+        // least recently used goes first: a plan handed out a moment ago (the forward half of a resample) must not be the one
+        // the next miss evicts
+        auto pos = std::find(cache.order.begin(), cache.order.end(), std::string(key));
+        if (pos != cache.order.end()) { cache.order.erase(pos); cache.order.push_back(key); }
+        *out = &it->second;
+        return 0;
+    }
     if (cache.order.size() >= 6) {                  // a handful of (n, num) pairs is all a service sees; bound the filters kept
         MM_CUDA(cudaStreamSynchronize(c->stream));
         c->workspace_bytes -= (int64_t)(cache.chirps[cache.order.front()].fft->L * sizeof(float2));

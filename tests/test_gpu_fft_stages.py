@@ -411,3 +411,16 @@ def test_fused_true_peak_correlation_equals_separate_kernels(P):
     assert np.array_equal(tp, eng.true_peak(mono)) and np.isnan(corr[0])
     rec = P.analyze_batch([_material(60000, sr, 9)], sr)[0]
     assert set(rec) >= {"lufs", "true_peak_dbfs", "sample_peak", "correlation", "spectrum_bars"}
+
+
+def test_chirp_plan_cache_eviction(P):
+    """More (n, num) pairs than the plan cache keeps (6 chirp filters = 3 pairs): old plans are evicted least-recently-used
+    first and every result still matches scipy -- including a pair whose forward plan is the oldest entry when its inverse
+    plan is created."""
+    from oracle import chain as oc
+    rng = np.random.default_rng(29)
+    x = (0.3 * rng.standard_normal(5000)).astype(np.float32)
+    pairs = [(5000, 5100), (5000, 5200), (5000, 5300), (5000, 5400), (5000, 5100), (5000, 5500), (5000, 5200)]
+    for n, num in pairs:
+        out = P.fft_resample(x[:n], num)
+        assert _err(out, oc.fft_resample(x[:n], num).astype(np.float32)) <= RS_TOL, (n, num)
