@@ -370,9 +370,10 @@ def apply_reference_match(audio: np.ndarray, sr: int, reference_audio: np.ndarra
     if strength < 0.01:
         return audio
     if ref_sr != sr:
+        # the reference mixes to mono, then resamples; resampling is linear, so both channels are resampled on the device (one
+        # complex transform, the cost of a mono row) and the envelope kernel forms the channel mean itself -- no host arithmetic
         ref = np.asarray(reference_audio)
-        ref_mono = np.mean(ref, axis=1) if ref.ndim > 1 else ref
-        reference_audio = fft_resample(ref_mono, int(len(ref_mono) * sr / ref_sr))
+        reference_audio = fft_resample(ref, int(ref.shape[0] * sr / ref_sr))
     src_env = compute_spectral_envelope(audio, sr, n_fft)
     ref_env = compute_spectral_envelope(reference_audio, sr, n_fft)
     ir = np.ascontiguousarray(reference_match_ir(src_env, ref_env, strength, n_fft))
