@@ -824,6 +824,12 @@ int mm_dev_iir(mm_ctx* c, const mm_geom* g, const float* in, float* out, const d
 }
 
 // ---- export -------------------------------------------------------------------------------------
+int mm_dev_finalize_clip(mm_ctx* c, const mm_geom* g, const float* in, float* out) {
+    MM_API_BEGIN(c);
+    MM_TRY(check_geom(g));
+    return st_finalize_clip(c, g, in, out);
+}
+
 int mm_dev_last_above(mm_ctx* c, const mm_geom* g, const float* in, double threshold_lin, int64_t* idx_dev) {
     MM_API_BEGIN(c);
     MM_TRY(check_geom(g));

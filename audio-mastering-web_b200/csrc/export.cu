@@ -70,6 +70,23 @@ int st_maximizer_lookahead(mm_ctx* c, const mm_geom* g, const float* in, float* 
     return 0;
 }
 
+// np.clip(x, -1, 1) followed by nan_to_num(nan=0, posinf=1, neginf=-1): the last two lines of run_mastering_pipeline (pipeline.py:
+// 1904-1906) and of MasteringChain.process (chain.py:93-94)
+__global__ void __launch_bounds__(256) finalize_clip_kernel(const float* in, float* out, long long n, long long stride) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const size_t o = (size_t)blockIdx.y * (size_t)stride + kLead + i;
+    const float x = in[o];
+    out[o] = (x != x) ? 0.0f : fminf(fmaxf(x, -1.0f), 1.0f);
+}
+
+int st_finalize_clip(mm_ctx* c, const mm_geom* g, const float* in, float* out) {
+    KernelScope ks(c, "finalize_clip");
+    finalize_clip_kernel<<<dim3((unsigned)((g->n + 255) / 256), (unsigned)(g->tracks * g->channels)), 256, 0, c->stream>>>(in, out, g->n, g->stride);
+    MM_CUDA(cudaGetLastError());
+    return 0;
+}
+
 int st_last_above(mm_ctx* c, const mm_geom* g, const float* in, double threshold, long long* idx_dev) {
     MM_CUDA(cudaMemsetAsync(idx_dev, 0xff, (size_t)g->tracks * sizeof(long long), c->stream));      // -1
     const unsigned bx = (unsigned)std::max<long long>(1, std::min<long long>((g->n + 255) / 256, 148LL * 8 / std::max(1, std::min(g->tracks, 148 * 8)) + 1));

@@ -85,6 +85,7 @@ void bigfft_release(mm_ctx* c);
 bool fft_convolve_fits(const mm_geom* g, int K);
 int st_fft_convolve_same(mm_ctx* c, const mm_geom* g, const float* in, float* out, const float* taps_dev, int K, int clip);
 // export.cu: _auto_blank_end's scan (idx_dev[tracks]: last frame above the threshold, -1 if none) and the PCM_24 conversion
+int st_finalize_clip(mm_ctx* c, const mm_geom* g, const float* in, float* out);
 int st_last_above(mm_ctx* c, const mm_geom* g, const float* in, double threshold, long long* idx_dev);
 int st_quantize_pcm24(mm_ctx* c, const mm_geom* g, const float* in, int32_t* out);
 // denoise.cu: apply_spectral_denoise (pipeline.py:1472-1524); not in place

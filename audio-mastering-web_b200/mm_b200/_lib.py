@@ -77,6 +77,7 @@ SIGNATURES = {
     "mm_dev_apply_stereo_imager": (_i, [_vp, _gp, _vp, _vp, _d]),
     "mm_dev_apply_rumble_filter": (_i, [_vp, _gp, _vp, _vp, _d]),
     "mm_dev_iir": (_i, [_vp, _gp, _vp, _vp, _dp, _dp, _i, _i]),
+    "mm_dev_finalize_clip": (_i, [_vp, _gp, _vp, _vp]),
     "mm_dev_last_above": (_i, [_vp, _gp, _vp, _d, _vp]),
     "mm_dev_quantize_pcm24": (_i, [_vp, _gp, _vp, _vp]),
     "mm_dev_quantize_int16": (_i, [_vp, _gp, _vp, _vp, _vp, _u64]),

@@ -295,9 +295,8 @@ class MasteringChain:
                 b = mod.process_batch(eng, b, **kw)
                 if tracing:       # chain.py:92: device reduction over the resident batch, no copy
                     _mt.trace_stage(trace_ctx, getattr(mod, "module_id", "module"), b, sr, eng=eng)
+            b = eng.stage("finalize_clip", b, out=b)            # chain.py:93-94: clip + nan_to_num, on the device
             out = P._down(eng, b, mono)
-            out = np.ascontiguousarray(np.clip(out, -1.0, 1.0).astype(np.float32))
-            np.nan_to_num(out, copy=False, nan=0.0, posinf=1.0, neginf=-1.0)
             if tracing:
                 _mt.trace_stage(trace_ctx, "chain_finalize_clip", out, sr)
         if progress_callback:

@@ -593,9 +593,7 @@ def _run_v1_stagewise(audio, sr, target_lufs, style, transient_attack, transient
         a = tr("stereo_imager", apply_stereo_imager(a, cfg["imager_width"]), imager_width=cfg["imager_width"])
     a = tr("peak_guard_out", remove_intersample_peaks(a, headroom_db=0.5))
     a = tr("output_fade_in", apply_output_edge_fade_in(a, sr, fade_ms=6.0))
-    a = np.clip(a, -1.0, 1.0).astype(np.float32)
-    a = np.nan_to_num(a, nan=0.0, posinf=1.0, neginf=-1.0)
-    return tr("finalize_clip", a)
+    return tr("finalize_clip", _stage("finalize_clip", a, sr))         # clip + nan_to_num (pipeline.py:1904-1906), on the device
 
 
 def export_audio(samples: np.ndarray, sr: int, channels: int, out_format: str = "wav", dither_type: str = "tpdf",

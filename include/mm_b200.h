@@ -177,6 +177,9 @@ int mm_dev_iir(mm_ctx*, const mm_geom*, const float* in, float* out,
                const double* b, const double* a, int ncoef, int zero_phase);
 
 /* ---- export ---------------------------------------------------------------------------------*/
+/* clip to +-1, then nan_to_num(nan=0, posinf=1, neginf=-1): the closing lines of run_mastering_pipeline (backend/app/pipeline.py:
+ * 1904-1906) and MasteringChain.process (backend/app/chain.py:93-94); in == out allowed */
+int mm_dev_finalize_clip(mm_ctx*, const mm_geom*, const float* in, float* out);
 /* _auto_blank_end (backend/app/pipeline.py:900-918): idx_dev[tracks] <- the last frame whose peak over the channels (after
  * the +-1 clip of export_audio) exceeds threshold_lin, -1 if none; the caller keeps min(n, idx + 1 + int(sr * min_silence)) */
 int mm_dev_last_above(mm_ctx*, const mm_geom*, const float* in, double threshold_lin, int64_t* idx_dev);
