@@ -74,7 +74,7 @@ def batch_metrics(eng, b) -> list:
         peak = float(v[t, 0])
         res.append({"channels": b.channels, "samples": b.n, "duration_sec": round(b.n / float(b.sr), 4) if b.sr else 0.0,
                     "peak_linear": round(peak, 6), "peak_db": round(float(20.0 * np.log10(max(peak, 1e-12))), 2),
-                    "nan_count": int(v[t, 1]), "inf_count": int(v[t, 2])})
+                    "nan_count": int(v[t, 1]), "inf_count": int(v[t, 2]), "peak_raw": peak})
     return res
 
 
@@ -91,7 +91,8 @@ def trace_stage(ctx: Optional[TraceContext], stage: str, audio, sr: int, *, eng=
         if np.asarray(audio).size == 0:
             return
         eng, b, _ = P._up(audio, sr)
-    m = batch_metrics(eng, b)[0]
+    m = dict(batch_metrics(eng, b)[0])
+    m.pop("peak_raw", None)                 # the unrounded peak is for validate_mastered_not_silent, not for the log line
     payload = {"job_id": ctx.job_id, "path": ctx.path, "filename": ctx.filename, "stage": stage, **m,
                **{k: v for k, v in extra.items() if v is not None}}
     if _on(_ENV_LUFS):

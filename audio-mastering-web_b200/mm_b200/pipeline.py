@@ -409,12 +409,12 @@ def validate_mastered_not_silent(mastered: np.ndarray, *, trace_ctx=None, trace_
     m = np.asarray(mastered)
     if m.size == 0:
         raise ValueError(_SILENT_MSG)
+    from .mastering_trace import batch_metrics
     eng, b, _ = _up(m, trace_sr)
-    _, peak = eng.stereo_correlation(b)       # device reduction: max |x| (NaN/Inf propagate into it)
-    pk = float(peak[0])
-    if not np.isfinite(pk) or not np.all(np.isfinite(m)):
+    met = batch_metrics(eng, b)[0]            # one device reduction: peak over the finite samples, NaN and Inf counts
+    if met["nan_count"] or met["inf_count"]:
         raise ValueError(_NONFINITE_MSG)
-    if pk < 1e-5:
+    if met["peak_raw"] < 1e-5:
         raise ValueError(_SILENT_MSG)
 
 
