@@ -443,12 +443,8 @@ __global__ void __launch_bounds__(kFftThreads) spectrum_kernel(const SpecArgs P)
 
 int st_spectrum_bars(mm_ctx* c, const mm_geom* g, const float* in, int view, double* bars_dev) {
     if (view < 0 || view > 2) { set_error("spectrum view must be 0 (mean), 1 (mid) or 2 (side)"); return 1; }
-    static bool attr = false;
     const size_t smem = 2 * kFftN * sizeof(float2);
-    if (!attr) {
-        MM_CUDA(cudaFuncSetAttribute(spectrum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr = true;
-    }
+    MM_TRY(kernel_setup(c, (const void*)spectrum_kernel, kFftThreads, smem, false, nullptr));
     SpecArgs A;
     A.in = in; A.n = g->n; A.stride = g->stride; A.channels = g->channels; A.view = view; A.sr = g->sr; A.bars = bars_dev;
     KernelScope ks(c, "spectrum_fft4096_bars");

@@ -140,9 +140,7 @@ static int master_impl(mm_ctx* c, const mm_geom* g, int chain, const mm_style* s
     MM_TRY(run_row_stats(c, g, in, &st));
     const mm_slice* sl = c->slice;
     auto reduce = [&](void* ptr, int64_t count, int dtype, int op, const char* what) -> int {
-        if (!sl || !sl->allreduce) return 0;
-        if (sl->allreduce(sl->user, ptr, count, dtype, op) != 0) { set_error("allreduce of %s failed", what); return 1; }
-        return 0;
+        return slice_allreduce(c, ptr, count, dtype, op, what);
     };
     MM_TRY(exchange_row_stats(c, st, rows));     // time slices: sums / minima / maxima over every rank's own frames
     MM_TRY(run_in_scalars(c, g, st, 1, 1, 0.5, d_sub, d_mul, d_peakin, d_mean));
@@ -289,7 +287,8 @@ using namespace mm;
 
 #define MM_API_BEGIN(ctx)                                   \
     if (!(ctx)) { mm::set_error("null context"); return 1; } \
-    mm::DeviceGuard _guard((ctx)->device);
+    mm::DeviceGuard _guard((ctx)->device);                   \
+    mm::plan_gc(ctx);
 
 extern "C" {
 
@@ -314,7 +313,7 @@ int mm_ctx_create(int device, void* stream, mm_ctx** out) {
     MM_CUDA(cudaSetDevice(device));
     cudaDeviceProp prop;
     MM_CUDA(cudaGetDeviceProperties(&prop, device));
-    if (prop.major < 10) { set_error("device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor); return 1; }
+    if (prop.major != 10) { set_error("device %d is sm_%d%d; this library holds sm_100a code only", device, prop.major, prop.minor); return 1; }
     mm_ctx* c = new mm_ctx();
     c->device = device;
     if (stream) {
@@ -336,6 +335,7 @@ void mm_ctx_destroy(mm_ctx* c) {
     for (int i = 0; i < SL_COUNT; ++i) if (c->slots[i].p) cudaFree(c->slots[i].p);
     for (auto& kv : c->plans) if (kv.second.dev) cudaFree(kv.second.dev);
     for (auto& kv : c->kw_plans) if (kv.second.dev) cudaFree(kv.second.dev);
+    for (auto& kv : c->lp_taps) if (kv.second) cudaFree(kv.second);
     for (auto& kv : c->lufs_plans) {
         cudaFree(kv.second.bnd); cudaFree(kv.second.tile_seg); cudaFree(kv.second.blk_lo); cudaFree(kv.second.blk_hi);
     }
@@ -353,6 +353,8 @@ int mm_ctx_release_workspace(mm_ctx* c) {
     for (int i = 0; i < SL_COUNT; ++i)
         if (c->slots[i].p) { cudaFree(c->slots[i].p); c->slots[i].p = nullptr; c->slots[i].cap = 0; }
     c->workspace_bytes = 0;
+    for (auto& kv : c->lufs_plans) { cudaFree(kv.second.bnd); cudaFree(kv.second.tile_seg); cudaFree(kv.second.blk_lo); cudaFree(kv.second.blk_hi); }
+    c->lufs_plans.clear();
     return 0;
 }
 
@@ -381,8 +383,9 @@ int mm_ctx_kernel_times(mm_ctx* c, mm_ktime* out, int cap, int* count) {
         float ms = 0.f;
         if (cudaEventElapsedTime(&ms, k.a, k.b) == cudaSuccess) {
             auto& acc = c->kacc[k.name];
-            acc.first += (double)ms;
-            acc.second += 1;
+            acc.ms += (double)ms;
+            acc.launches += 1;
+            acc.samples += k.samples;
         }
         cudaEventDestroy(k.a);
         cudaEventDestroy(k.b);
@@ -393,8 +396,9 @@ int mm_ctx_kernel_times(mm_ctx* c, mm_ktime* out, int cap, int* count) {
         if (i < cap && out) {
             memset(&out[i], 0, sizeof(mm_ktime));
             strncpy(out[i].name, kv.first.c_str(), sizeof(out[i].name) - 1);
-            out[i].ms = kv.second.first;
-            out[i].launches = kv.second.second;
+            out[i].ms = kv.second.ms;
+            out[i].launches = kv.second.launches;
+            out[i].samples = kv.second.samples;
         }
         ++i;
     }
@@ -663,9 +667,9 @@ int mm_dev_apply_stereo_imager(mm_ctx* c, const mm_geom* g, const float* in, flo
 int mm_dev_apply_rumble_filter(mm_ctx* c, const mm_geom* g, const float* in, float* out, double cutoff_hz) {
     MM_API_BEGIN(c);
     MM_TRY(check_geom(g));
-    // pipeline.py:1449-1469: butter(2, clip(cutoff,20,300)/nyq <= 0.99, 'high') through filtfilt
+    // pipeline.py:1449-1469: butter(2, clip(cutoff, 20, 200) / nyq <= 0.99, 'high') through filtfilt
     const double nyq = g->sr / 2.0;
-    const double fc = std::min(std::max(cutoff_hz, 20.0), 300.0);
+    const double fc = std::min(std::max(cutoff_hz, 20.0), 200.0);
     const FilterPlan* p = plan_butter(c, 2, kHigh, std::min(fc / nyq, 0.99), 0);
     if (!p) return 1;
     Epi e;
@@ -677,7 +681,15 @@ int mm_dev_apply_dynamic_eq(mm_ctx* c, const mm_geom* g, const float* in, float*
     MM_API_BEGIN(c);
     MM_TRY(check_geom(g));
     if (nbands < 0 || nbands > 64 || (nbands > 0 && !params)) { set_error("mm_dev_apply_dynamic_eq: 0..64 bands with 7 parameters each"); return 2; }
-    return st_dynamic_eq(c, g, in, out, nbands, params);
+    return st_dynamic_eq(c, g, in, out, nbands, params, 0, nullptr);
+}
+
+int mm_dev_apply_dynamic_eq2(mm_ctx* c, const mm_geom* g, const float* in, float* out, int nbands, const double* params, uint32_t flags,
+                             int32_t* classes) {
+    MM_API_BEGIN(c);
+    MM_TRY(check_geom(g));
+    if (nbands < 0 || nbands > 64 || (nbands > 0 && !params)) { set_error("mm_dev_apply_dynamic_eq2: 0..64 bands with 7 parameters each"); return 2; }
+    return st_dynamic_eq(c, g, in, out, nbands, params, flags, classes);
 }
 
 int mm_dev_apply_transient_designer(mm_ctx* c, const mm_geom* g, const float* in, float* out, double attack_gain, double sustain_gain) {
@@ -973,7 +985,23 @@ static int master_host_impl(mm_ctx* c, int chain, int32_t tracks, int64_t n, int
     if (const char* e = getenv("MM_HOST_CHUNK")) tc = atoi(e);
     if (tc <= 0) tc = (int)std::max<size_t>(1, ((size_t)256 << 20) / std::max<size_t>(per_track * sizeof(float), 1));
     tc = std::min(tc, (int)tracks);
-    const int nchunks = (tracks + tc - 1) / tc;
+    // chunk plan: full chunks of tc tracks, with short chunks at both ends (1, 2, ... tracks) so that the pipeline's fill (the
+    // first copy-in before any compute) and drain (the last chunk's chain + copy-out after the last copy-in) cost one track
+    // instead of one full chunk.  MM_HOST_RAMP=0 switches the ramps off.
+    std::vector<int> c0, cn;
+    {
+        std::vector<int> head, tail;
+        int rem = tracks;
+        const char* er = getenv("MM_HOST_RAMP");
+        const bool ramp = !(er && atoi(er) == 0);
+        for (int s = 1; ramp && s < tc && rem >= 2 * s + tc; s *= 2) { head.push_back(s); tail.push_back(s); rem -= 2 * s; }
+        std::vector<int> sizes(head);
+        while (rem > 0) { const int s = std::min(tc, rem); sizes.push_back(s); rem -= s; }
+        for (size_t i = tail.size(); i-- > 0;) sizes.push_back(tail[i]);
+        int t0 = 0;
+        for (int s : sizes) { c0.push_back(t0); cn.push_back(s); t0 += s; }
+    }
+    const int nchunks = (int)c0.size();
     const size_t cframes = (size_t)tc * per_track;
     float *il[2] = {nullptr, nullptr}, *ol[2] = {nullptr, nullptr}, *nz[2] = {nullptr, nullptr}, *pl = nullptr;
     int16_t* pcm[2] = {nullptr, nullptr};
@@ -1003,7 +1031,7 @@ static int master_host_impl(mm_ctx* c, int chain, int32_t tracks, int64_t n, int
     MM_CUDA(cudaStreamWaitEvent(c->h2d_stream, ev_start, 0));
     MM_CUDA(cudaStreamWaitEvent(c->d2h_stream, ev_start, 0));
     auto copy_in = [&](int k) -> int {
-        const int t0 = k * tc, tn = std::min(tc, (int)tracks - t0);
+        const int t0 = c0[k], tn = cn[k];
         const size_t off = (size_t)t0 * per_track, cnt = (size_t)tn * per_track;
         if (k >= 2) MM_CUDA(cudaStreamWaitEvent(c->h2d_stream, ev_deint[k - 2], 0));    // staging buffer k & 1 is free again
         const void* hsrc = pcm16_in ? (const void*)(pcm16_in + off) : (const void*)(audio_in + off);
@@ -1017,7 +1045,7 @@ static int master_host_impl(mm_ctx* c, int chain, int32_t tracks, int64_t n, int
     };
     rc = copy_in(0);
     for (int k = 0; k < nchunks && rc == 0; ++k) {
-        const int t0 = k * tc, tn = std::min(tc, (int)tracks - t0);
+        const int t0 = c0[k], tn = cn[k];
         const size_t off = (size_t)t0 * per_track, cnt = (size_t)tn * per_track;
         if (k + 1 < nchunks && (rc = copy_in(k + 1)) != 0) break;
         mm_geom gk = g;
@@ -1080,6 +1108,16 @@ int mm_design_butter(int order, int btype, const double* wn, double* b, double* 
     if (!butter(order, (BType)btype, wn, &f)) { set_error("mm_design_butter: unsupported order or critical frequencies"); return -1; }
     for (int i = 0; i <= f.m; ++i) { b[i] = f.b[i]; a[i] = f.a[i]; }
     return f.m + 1;
+}
+
+int mm_design_iirpeak(double w0, double q, double* b, double* a, int* kind, double* rmax) {
+    Ba f;
+    memset(&f, 0, sizeof(f));
+    if (!b || !a || !iirpeak(w0, q, &f)) { set_error("mm_design_iirpeak: bad arguments"); return 1; }
+    for (int i = 0; i < 3; ++i) { b[i] = f.b[i]; a[i] = f.a[i]; }
+    const int k = dyneq_band_kind(f, rmax);
+    if (kind) *kind = k;
+    return 0;
 }
 
 int mm_design_lfilter_zi(const double* b, const double* a, int ncoef, double* zi) {

@@ -40,6 +40,25 @@ int arena_get(mm_ctx* c, int slot, size_t bytes, void** out) {
     return 0;
 }
 
+int kernel_setup(mm_ctx* c, const void* kern, int threads, size_t smem, bool max_carveout, int* blocks_per_sm) {
+    auto it = c->occupancy.find(kern);
+    if (it == c->occupancy.end()) {
+        if (c->num_sms == 0) {
+            cudaDeviceProp prop;
+            MM_CUDA(cudaGetDeviceProperties(&prop, c->device));
+            c->num_sms = prop.multiProcessorCount;
+        }
+        if (smem > 48 * 1024) MM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        if (max_carveout) MM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        int bps = 0;
+        MM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, threads, smem));
+        if (bps < 1) { set_error("kernel does not fit on an SM (%zu bytes of shared memory, %d threads)", smem, threads); return 1; }
+        it = c->occupancy.emplace(kern, bps).first;
+    }
+    if (blocks_per_sm) *blocks_per_sm = it->second;
+    return 0;
+}
+
 template <int M> static void pack_tables(const ScanTables& t, std::vector<double>& h) {
     typedef Tab<M> TB;
     h.assign((size_t)TB::Mpow + (size_t)t.W * TB::MM, 0.0);
@@ -81,7 +100,7 @@ const FilterPlan* get_plan_mode(mm_ctx* c, const Ba& ba, int mode) {
     std::string key((const char*)&ba, sizeof(Ba));
     key.push_back((char)('0' + mode));
     auto it = c->plans.find(key);
-    if (it != c->plans.end()) return &it->second;
+    if (it != c->plans.end()) { it->second.last_use = ++c->tick; return &it->second; }
     FilterPlan p;
     p.ba = ba;
     bool ok = false;
@@ -105,6 +124,7 @@ const FilterPlan* get_plan_mode(mm_ctx* c, const Ba& ba, int mode) {
         set_error("upload of filter tables failed");
         return nullptr;
     }
+    p.last_use = ++c->tick;
     auto res = c->plans.emplace(key, p);
     return &res.first->second;
 }
@@ -152,7 +172,7 @@ int get_lufs_plan(mm_ctx* c, long long n, int sr, const LufsPlan** out, long lon
     if (n_local < 0) n_local = n;
     snprintf(keyb, sizeof(keyb), "%lld:%d:%lld:%lld", n, sr, goff, n_local);
     auto it = c->lufs_plans.find(keyb);
-    if (it != c->lufs_plans.end()) { *out = &it->second; return 0; }
+    if (it != c->lufs_plans.end()) { it->second.last_use = ++c->tick; *out = &it->second; return 0; }
     LufsPlan p;
     const double rate = (double)sr, T_g = 0.4, step = 1.0 - 0.75;
     p.valid = !((double)n < T_g * rate);
@@ -195,9 +215,33 @@ int get_lufs_plan(mm_ctx* c, long long n, int sr, const LufsPlan** out, long lon
     MM_TRY(upload_vec(c, tseg, &p.tile_seg));
     MM_TRY(upload_vec(c, blo, &p.blk_lo));
     MM_TRY(upload_vec(c, bhi, &p.blk_hi));
+    p.last_use = ++c->tick;
     auto res = c->lufs_plans.emplace(keyb, p);
     *out = &res.first->second;
     return 0;
+}
+
+// Filter plans are keyed by coefficients the caller controls (crossovers, cut-offs, dynamic-EQ bands), loudness plans by the
+// exact frame count of an upload: a service would grow both without bound.  Beyond the caps the least-recently-used half is
+// dropped -- only here, at API entry, when no stage holds a plan pointer -- after the stream has drained (kernels may still be
+// reading the device tables).
+constexpr size_t kMaxFilterPlans = 192, kMaxLufsPlans = 24;
+template <class Map, class Free> static void evict_lru(mm_ctx* c, Map& m, size_t cap, Free free_one, bool* synced) {
+    if (m.size() <= cap) return;
+    std::vector<uint64_t> uses;
+    for (auto& kv : m) uses.push_back(kv.second.last_use);
+    std::nth_element(uses.begin(), uses.begin() + uses.size() / 2, uses.end());
+    const uint64_t cut = uses[uses.size() / 2];
+    if (!*synced) { cudaStreamSynchronize(c->stream); *synced = true; }
+    for (auto it = m.begin(); it != m.end();) {
+        if (it->second.last_use < cut) { free_one(it->second); it = m.erase(it); }
+        else ++it;
+    }
+}
+void plan_gc(mm_ctx* c) {
+    bool synced = false;
+    evict_lru(c, c->plans, kMaxFilterPlans, [](FilterPlan& p) { if (p.dev) cudaFree(p.dev); }, &synced);
+    evict_lru(c, c->lufs_plans, kMaxLufsPlans, [](LufsPlan& p) { cudaFree(p.bnd); cudaFree(p.tile_seg); cudaFree(p.blk_lo); cudaFree(p.blk_hi); }, &synced);
 }
 
 KernelScope::KernelScope(mm_ctx* ctx, const char* nm) : c(ctx), name(nm) {
@@ -212,7 +256,7 @@ KernelScope::~KernelScope() {
     if (c->timing && a) {
         cudaEventRecord(b, c->stream);
         KTime k;
-        k.name = name; k.a = a; k.b = b;
+        k.name = name; k.a = a; k.b = b; k.samples = samples;
         c->ktimes.push_back(k);
     }
 }

@@ -44,6 +44,7 @@ struct FilterPlan {
     ScanTables tabs;
     double* dev = nullptr;      // device copy laid out as common.cuh Tab<M>
     int pad = 0;                // filtfilt padlen = 3 * max(len(a), len(b))
+    uint64_t last_use = 0;
 };
 
 struct KwPlan {                 // K-weighting cascade (shelf -> high-pass) of one sample rate as a 4-state system
@@ -59,6 +60,7 @@ struct LufsPlan {               // per (n, sr): gating blocks expressed over mer
     int* tile_seg = nullptr;
     int* blk_lo = nullptr;
     int* blk_hi = nullptr;
+    uint64_t last_use = 0;
 };
 
 struct Slot { void* p = nullptr; size_t cap = 0; };
@@ -73,7 +75,8 @@ enum SlotId {
     SL_COUNT
 };
 
-struct KTime { std::string name; cudaEvent_t a, b; };
+struct KTime { std::string name; cudaEvent_t a, b; double samples; };
+struct KAcc { double ms = 0; int64_t launches = 0; double samples = 0; };
 
 }  // namespace mm
 
@@ -92,8 +95,12 @@ struct mm_ctx {
     int64_t launches = 0;
     bool timing = false;
     std::vector<mm::KTime> ktimes;
-    std::map<std::string, std::pair<double, int64_t>> kacc;
+    std::map<std::string, mm::KAcc> kacc;
     int64_t workspace_bytes = 0;
+    std::map<const void*, int> occupancy;   // kernel -> resident CTAs per SM on THIS device (attributes set when the entry is made)
+    int num_sms = 0;
+    std::map<int, float*> lp_taps;          // linear-phase target-curve IR per sample rate (device)
+    uint64_t tick = 0;                      // use counter of the plan caches (least-recently-used eviction at API entry)
     void* bigfft = nullptr;             // bigfft.cu's plan cache (FFT tables, chirp-filter spectra); owned by the context: contexts are per thread
 };
 
@@ -112,8 +119,16 @@ const FilterPlan* get_plan_mode(mm_ctx* c, const Ba& ba, int mode);   // mode: d
 int get_lufs_plan(mm_ctx* c, long long n, int sr, const LufsPlan** out, long long goff = 0, long long n_local = -1);
 const KwPlan* get_kw_plan(mm_ctx* c, int sr);
 
+// Per-context (= per device, per thread) launch configuration of a kernel that needs more than 48 KB of dynamic shared memory:
+// sets cudaFuncAttributeMaxDynamicSharedMemorySize (a per-device attribute) the first time this context sees the kernel and
+// caches the resident CTAs per SM.  Nothing here is process-global: contexts on different devices do not share state.
+int kernel_setup(mm_ctx* c, const void* kern, int threads, size_t smem, bool max_carveout, int* blocks_per_sm);
+// drop least-recently-used filter / loudness plans beyond the caps (called at API entry, when no plan pointer is held)
+void plan_gc(mm_ctx* c);
+
 struct KernelScope {            // brackets a launch with events when timing is on
     mm_ctx* c; const char* name; cudaEvent_t a = nullptr, b = nullptr;
+    double samples = 0;         // channel-samples this launch visits (per-kernel GB/s of launches over row lists / track runs)
     KernelScope(mm_ctx* ctx, const char* nm);
     ~KernelScope();
 };

@@ -300,47 +300,157 @@ __global__ void __launch_bounds__(256) clip_rows_kernel(const float* in, float* 
     }
 }
 
+// band = (float)(kk * ((double)x - sub[row])): what the reference's filter call returns for a band whose iirpeak section
+// degenerates to b = k [1, 0, -1], a = [1, ~0, ~-1] (H(z) = k; see st_dynamic_eq)
+__global__ void __launch_bounds__(256) dyneq_affine_band_kernel(const float* x, float* band, long long n, long long stride, double kk,
+                                                               const double* sub) {
+    const size_t ro = (size_t)blockIdx.y * (size_t)stride + kLead;
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) band[ro + i] = (float)(kk * ((double)x[ro + i] - (sub ? sub[blockIdx.y] : 0.0)));
+}
+// last sample of scipy's odd extension (padlen 9): 2 x[n-1] - x[n-10], per row, float64
+__global__ void dyneq_right_end_kernel(const float* x, long long n, long long stride, int rows, double* sub) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < rows) {
+        const float* p = x + (size_t)r * (size_t)stride + kLead;
+        sub[r] = 2.0 * (double)p[n - 1] - (double)p[n - 10];
+    }
+}
+// flag[row] = 1 when the row's first `cnt` samples are not all equal (a constant row never excites an unstable section)
+__global__ void __launch_bounds__(256) dyneq_activity_kernel(const float* x, long long cnt, long long stride, int* flag) {
+    const float* p = x + (size_t)blockIdx.y * (size_t)stride + kLead;
+    const float x0 = p[0];
+    bool any = false;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < cnt; i += (long long)gridDim.x * blockDim.x) any |= p[i] != x0;
+    if (__syncthreads_or(any) && threadIdx.x == 0) atomicOr(flag + blockIdx.y, 1);
+}
+
 // apply_dynamic_eq (backend/app/pipeline.py:1628-1700): per band a zero-phase peaking section (scipy.signal.iirpeak with the
 // reference's arguments), the attack/release follower of |band|, a downward gain above the threshold, x - band + band * g;
 // bands run one after the other on the running signal.  params[b] = {w0, bw, threshold_db, ratio, attack_ms, release_ms,
-// max_cut_db} with w0, bw already clipped as the reference does (:1657-1658).  A band whose section is unstable -- which is
-// what the reference's bandwidth-in-the-Q-slot call yields for every default band -- is refused: its exponentially growing
-// filtfilt output (zeroed / patched by the reference) is not a parity target.
-int st_dynamic_eq(mm_ctx* c, const mm_geom* g, const float* in, float* out, int nbands, const double* params) {
+// max_cut_db} with w0, bw already clipped as the reference does (:1657-1658).
+//
+// The reference hands iirpeak a *bandwidth* in its Q slot (:1661-1663), so the section's -3 dB width is pi * q radians whatever
+// the frequency, and what `_safe_filtfilt` (:36-52) returns falls into one of five classes, decided here from (b, a) exactly as
+// scipy 1.18 computes them (double arithmetic, libm tan / cos) and reported through `classes`:
+//   MM_DYNEQ_STABLE (0)    poles inside the unit circle: the device path (float64 zero-phase section + follower)
+//   MM_DYNEQ_OVERFLOW (1)  a pole outside the unit circle and a signal long / lively enough that the forward lfilter pass must
+//                          leave float32 range long before the end: every sample of filtfilt's output is NaN, +-Inf, or beyond
+//                          float32 -> nan_to_num zeroes the whole band (:1677) -> x - 0 + 0 * g = x: the band is the identity
+//                          (every default band at 44.1 kHz, six of eight at 48 kHz)
+//   MM_DYNEQ_LFILTER (2)   q = 1 below ~0.35 nyq: a = [1, -1.2e-16 cos, -(1 - 1.1e-16)] sums to 0.0 in float64, lfilter_zi
+//                          raises ValueError, the reference falls back to the causal lfilter whose transfer function is
+//                          b0 (1 - z^-2) / (1 - z^-2) = b0: band = b0 x (the 1e-16 feedback term moves it by < 1e-12)
+//   MM_DYNEQ_MARGINAL (3)  same degenerate section but sum(a) != 0 (bw clipped to 0.5 at w0 = 0.5, or q = 1 above 0.35 nyq):
+//                          filtfilt runs with poles at +-(1 - 5.5e-17); started from zi * ext[0] = -b0 ext[0] [1, 1] the forward
+//                          pass returns b0 (ext - ext[0]), the backward pass b0^2 (ext - ext[last]):
+//                          band = b0^2 (x - (2 x[n-1] - x[n-10]))
+//   MM_DYNEQ_SKIPPED (4)   unstable but overflow is not certain (short or constant signal, pole barely outside): the reference's
+//                          output is rounding-noise-seeded garbage and cannot be a parity target; the band is passed through
+//                          (flags & MM_DYNEQ_STRICT: refused by name with return code 3)
+int dyneq_band_kind(const Ba& ba, double* rmax_out) {
+    const double a1 = ba.a[1], a2 = ba.a[2];
+    const bool stable = std::fabs(a2) < 1.0 && std::fabs(a1) < 1.0 + a2;
+    const bool degenerate = std::fabs(a1) <= 1e-12 && std::fabs(a2 + 1.0) <= 1e-12;     // H(z) = b0
+    volatile double sum_a = 1.0 + a1;            // numpy's left-to-right float64 sum of [1, a1, a2] (lfilter_zi's pole-at-1 test)
+    sum_a = sum_a + a2;
+    const double disc = a1 * a1 - 4.0 * a2;
+    if (rmax_out)
+        *rmax_out = disc >= 0.0 ? std::max(std::fabs((-a1 + std::sqrt(disc)) / 2.0), std::fabs((-a1 - std::sqrt(disc)) / 2.0))
+                                : std::sqrt(std::fabs(a2));
+    if (degenerate) return sum_a == 0.0 ? MM_DYNEQ_LFILTER : MM_DYNEQ_MARGINAL;
+    if (stable && sum_a != 0.0) return MM_DYNEQ_STABLE;
+    return -1;
+}
+
+int st_dynamic_eq(mm_ctx* c, const mm_geom* g, const float* in, float* out, int nbands, const double* params, unsigned flags,
+                  int* classes) {
     const int rows = g->tracks * g->channels;
-    const size_t bytes = (size_t)rows * (size_t)g->stride * sizeof(float);
-    std::vector<const FilterPlan*> plans;
+    std::vector<const FilterPlan*> plans((size_t)nbands, nullptr);
+    std::vector<int> cls((size_t)nbands, MM_DYNEQ_STABLE);
+    std::vector<double> kk((size_t)nbands, 1.0);
+    int activity_known = 0;                      // 0 unknown, 1 every row lively, -1 some row constant
     for (int b = 0; b < nbands; ++b) {
         const double* q = params + 7 * b;
         Ba ba;
         if (!iirpeak(q[0], q[1], &ba)) { set_error("apply_dynamic_eq: band %d: iirpeak(%g, %g) is not a valid design", b, q[0], q[1]); return 3; }
         const double a1 = ba.a[1], a2 = ba.a[2];
-        if (!(std::fabs(a2) < 1.0 && std::fabs(a1) < 1.0 + a2)) {
-            set_error("apply_dynamic_eq: band %d: iirpeak(w0=%g, Q=%g) is an unstable section (a = [1, %g, %g]); the reference passes "
-                      "a bandwidth where scipy expects Q (pipeline.py:1661-1663)", b, q[0], q[1], a1, a2);
-            return 3;
+        double rmax = 0.0;
+        const int kind = dyneq_band_kind(ba, &rmax);
+        if (kind == MM_DYNEQ_LFILTER || kind == MM_DYNEQ_MARGINAL) {
+            if (g->n <= 9 && kind == MM_DYNEQ_MARGINAL) { set_error("apply_dynamic_eq: %lld frames is not longer than filtfilt's padlen 9", (long long)g->n); return 1; }
+            cls[b] = kind;
+            kk[b] = kind == MM_DYNEQ_LFILTER ? ba.b[0] : ba.b[0] * ba.b[0];
+        } else if (kind == MM_DYNEQ_STABLE) {
+            const FilterPlan* p = get_plan(c, ba, PREC_F64);
+            if (!p) return 1;
+            if (g->n <= p->pad) { set_error("apply_dynamic_eq: %lld frames is not longer than filtfilt's padlen %d", (long long)g->n, p->pad); return 1; }
+            plans[b] = p;
+        } else {
+            // largest pole radius; the unstable mode excited by the first change of the signal (>= one float32 denormal, 1e-45)
+            // must pass 1e48 (float32 range times 1e10 for the zero crossings of a complex pair) before the forward pass ends
+            bool certain = false;
+            if (rmax > 1.0 + 1e-9) {
+                const double need = std::ceil((48.0 + 45.0 + 12.0) * std::log(10.0) / std::log(rmax)) + 64.0;   // + 1e12 of residue / margin
+                if ((double)g->n > 2.0 * need) {
+                    if (activity_known == 0) {
+                        int* flag;
+                        MM_TRY(arena(c, SL_MISC, (size_t)rows, &flag));
+                        MM_CUDA(cudaMemsetAsync(flag, 0, (size_t)rows * sizeof(int), c->stream));
+                        // lively within the first half of the signal covers every band that passes the 2 * need test
+                        const long long cnt = g->n / 2;
+                        dyneq_activity_kernel<<<dim3((unsigned)std::min<long long>((cnt + 255) / 256, 512), (unsigned)rows), 256, 0, c->stream>>>(in, cnt, g->stride, flag);
+                        MM_CUDA(cudaGetLastError());
+                        std::vector<int> h((size_t)rows);
+                        MM_CUDA(cudaMemcpyAsync(h.data(), flag, (size_t)rows * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+                        MM_CUDA(cudaStreamSynchronize(c->stream));
+                        activity_known = 1;
+                        for (int r = 0; r < rows; ++r) if (!h[r]) activity_known = -1;
+                    }
+                    certain = activity_known == 1;
+                }
+            }
+            if (certain) cls[b] = MM_DYNEQ_OVERFLOW;
+            else if (flags & MM_DYNEQ_STRICT) {
+                set_error("apply_dynamic_eq: band %d: iirpeak(w0=%g, Q=%g) is an unstable section (a = [1, %g, %g], pole radius %g) whose "
+                          "overflow over %lld frames is not certain; the reference passes a bandwidth where scipy expects Q "
+                          "(pipeline.py:1661-1663)", b, q[0], q[1], a1, a2, rmax, (long long)g->n);
+                return 3;
+            } else cls[b] = MM_DYNEQ_SKIPPED;
         }
-        const FilterPlan* p = get_plan(c, ba, PREC_F64);
-        if (!p) return 1;
-        if (g->n <= p->pad) { set_error("apply_dynamic_eq: %lld frames is not longer than filtfilt's padlen %d", (long long)g->n, p->pad); return 1; }
-        plans.push_back(p);
     }
+    if (classes) for (int b = 0; b < nbands; ++b) classes[b] = cls[b];
     Bufs B;
     MM_TRY(get_bufs(c, g, &B));
     float* sc = B.T[1];
     float* gain = B.T[2];
     const float* cur = in;
+    int last = -1;                                   // the last band that touches the samples carries the closing clip
+    for (int b = 0; b < nbands; ++b) if (cls[b] != MM_DYNEQ_OVERFLOW && cls[b] != MM_DYNEQ_SKIPPED) last = b;
     for (int b = 0; b < nbands; ++b) {
+        if (cls[b] == MM_DYNEQ_OVERFLOW || cls[b] == MM_DYNEQ_SKIPPED) continue;
         const double* q = params + 7 * b;
-        const FilterPlan* p[1] = {plans[b]};
-        const float* i1[1] = {cur};
-        float* o1[1] = {B.E[0]};
-        Pro none;
-        MM_TRY(sweep_fwd(c, g, 1, 1, p, i1, o1, none, plans[b]->pad));
-        const float* i2[1] = {B.E[0]};
-        float* o2[1] = {sc};
-        Epi store;
-        MM_TRY(sweep_bwd(c, g, 1, p, i2, o2, 1, store, plans[b]->pad));
+        if (cls[b] == MM_DYNEQ_STABLE) {
+            const FilterPlan* p[1] = {plans[b]};
+            const float* i1[1] = {cur};
+            float* o1[1] = {B.E[0]};
+            Pro none;
+            MM_TRY(sweep_fwd(c, g, 1, 1, p, i1, o1, none, plans[b]->pad));
+            const float* i2[1] = {B.E[0]};
+            float* o2[1] = {sc};
+            Epi store;
+            MM_TRY(sweep_bwd(c, g, 1, p, i2, o2, 1, store, plans[b]->pad));
+        } else {
+            double* sub = nullptr;
+            if (cls[b] == MM_DYNEQ_MARGINAL) {
+                MM_TRY(arena(c, SL_XCHG, (size_t)rows, &sub));
+                dyneq_right_end_kernel<<<(rows + 127) / 128, 128, 0, c->stream>>>(cur, g->n, g->stride, rows, sub);
+                MM_CUDA(cudaGetLastError());
+            }
+            KernelScope ks(c, "dyneq_degenerate_band");
+            dyneq_affine_band_kernel<<<dim3((unsigned)((g->n + 255) / 256), (unsigned)rows), 256, 0, c->stream>>>(cur, sc, g->n, g->stride, kk[b], sub);
+            MM_CUDA(cudaGetLastError());
+        }
         EnvArgs A;
         memset(&A, 0, sizeof(A));
         A.sc = sc; A.gain = gain; A.mode = 1;
@@ -350,12 +460,11 @@ int st_dynamic_eq(mm_ctx* c, const mm_geom* g, const float* in, float* out, int 
         MM_TRY(launch_envelope(c, g, A, q[4], q[5], "dyneq_envelope_gain"));
         KernelScope ks(c, "dyneq_apply");
         dyneq_apply_kernel<<<dim3((unsigned)((g->n + 1023) / 1024), (unsigned)rows), 256, 0, c->stream>>>(cur, sc, gain, out, g->n, g->stride,
-                                                                                                         b == nbands - 1);
+                                                                                                         b == last);
         MM_CUDA(cudaGetLastError());
         cur = out;
     }
-    if (nbands == 0) {                               // every band skipped: clip(input) (pipeline.py:1696)
-        (void)bytes;
+    if (last < 0) {                                  // no band touched the samples: clip(input) (pipeline.py:1696)
         KernelScope ks(c, "dyneq_clip");
         clip_rows_kernel<<<dim3((unsigned)((g->n + 255) / 256), (unsigned)rows), 256, 0, c->stream>>>(in, out, g->n, g->stride);
         MM_CUDA(cudaGetLastError());

@@ -368,11 +368,7 @@ int st_spectral_denoise(mm_ctx* c, const mm_geom* g, const float* in, float* out
     const size_t tables = kDnSmemHead;
     {
         const size_t smem = tables + (size_t)kDnMagFrames * kDnBins * sizeof(float);
-        static bool attr = false;
-        if (!attr) {
-            MM_CUDA(cudaFuncSetAttribute(dn_mag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            attr = true;
-        }
+        MM_CUDA(cudaFuncSetAttribute(dn_mag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   // per device; cheap
         DnMagArgs A;
         A.in = in; A.n = n; A.stride = g->stride; A.frames = frames; A.fpad = fpad; A.mag = mag;
         dim3 grid((unsigned)(fpad / kDnMagFrames), (unsigned)rows);
@@ -400,11 +396,7 @@ int st_spectral_denoise(mm_ctx* c, const mm_geom* g, const float* in, float* out
     }
     {
         const size_t smem = tables + (size_t)(kDnBins + 3 + kDnAccLen) * sizeof(float);
-        static bool attr = false;
-        if (!attr) {
-            MM_CUDA(cudaFuncSetAttribute(dn_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            attr = true;
-        }
+        MM_CUDA(cudaFuncSetAttribute(dn_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         DnApplyArgs A;
         A.in = in; A.out = out; A.n = n; A.stride = g->stride; A.frames = frames; A.noise = noise; A.strength = (float)strength;
         const long long hops = (n + kDnHop - 1) / kDnHop;

@@ -119,8 +119,10 @@ bool iirpeak(double w0, double Q, Ba* out) {
     if (!(w0 > 0.0 && w0 < 1.0) || !(Q > 0.0)) return false;
     const double pi = 3.14159265358979323846;
     const double bw = (w0 / Q) * pi, w = w0 * pi;
-    const double gb = 1.0 / std::sqrt(2.0);
-    const double beta = (std::sqrt(1.0 - gb * gb) / gb) * std::tan(bw / 2.0);
+    // scipy 1.18 (_design_notch_peak_filter): beta = math.tan(bw / 2) -- the -3 dB factor sqrt(1 - gb^2) / gb is taken as exactly 1
+    // (older releases multiplied by its float64 value 1.0000000000000002); plain double arithmetic and libm tan / cos, so that
+    // the degenerate cases st_dynamic_eq classifies (a summing to 0.0 in float64) fall where scipy's own do
+    const double beta = std::tan(bw / 2.0);
     const double gain = 1.0 / (1.0 + beta);
     Ba f;
     f.m = 2;

@@ -328,9 +328,7 @@ static bool fir_use_fft(const mm_geom* g, int K) {
 int st_target_curve_linear_phase(mm_ctx* c, const mm_geom* g, const float* in, float* out) {
     if (in == out) { set_error("linear-phase target curve: in-place operation is not supported"); return 1; }
     const int K = 4096;
-    static std::map<int, float*> cache;               // per sample rate, device taps (one device kind per process)
-    static std::mutex cache_mu;                       // contexts are per thread; this cache is per process
-    std::lock_guard<std::mutex> lock(cache_mu);
+    std::map<int, float*>& cache = c->lp_taps;        // per context: device pointers never cross devices or threads
     float* taps = nullptr;
     auto it = cache.find(g->sr);
     if (it != cache.end()) taps = it->second;
@@ -346,11 +344,7 @@ int st_target_curve_linear_phase(mm_ctx* c, const mm_geom* g, const float* in, f
     FirArgs A;
     A.in = in; A.out = out; A.taps = taps; A.n = g->n; A.stride = g->stride; A.K = K; A.center = (K - 1) / 2; A.clip = 1;
     const size_t smem = (size_t)(K + kFirTile + K + 8 + 8) * sizeof(float);
-    static bool attr = false;
-    if (!attr) {
-        MM_CUDA(cudaFuncSetAttribute(fir_same_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr = true;
-    }
+    MM_CUDA(cudaFuncSetAttribute(fir_same_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid((unsigned)((g->n + kFirTile - 1) / kFirTile), (unsigned)(g->tracks * g->channels));
     KernelScope ks(c, "target_curve_linear_phase_fir4096");
     fir_same_kernel<<<grid, kFirThreads, smem, c->stream>>>(A);

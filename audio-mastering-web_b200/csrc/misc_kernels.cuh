@@ -51,11 +51,12 @@ __global__ void __launch_bounds__(kPwThreads) row_stats_kernel(const float* __re
 // RowStats <-> three float64 vectors [sum | min | max] for the cross-rank reduction of a time-sliced file
 __global__ void row_stats_pack_kernel(const RowStats* st, int rows, double* buf) {
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r < rows) { buf[r] = st[r].sum; buf[rows + r] = (double)ord2f(st[r].mn); buf[2 * rows + r] = (double)ord2f(st[r].mx); }
+    // [sums | negated minima | maxima]: one SUM and one MAX all-reduce (min x = -max(-x))
+    if (r < rows) { buf[r] = st[r].sum; buf[rows + r] = -(double)ord2f(st[r].mn); buf[2 * rows + r] = (double)ord2f(st[r].mx); }
 }
 __global__ void row_stats_unpack_kernel(RowStats* st, int rows, const double* buf) {
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r < rows) { st[r].sum = buf[r]; st[r].mn = f2ord((float)buf[rows + r]); st[r].mx = f2ord((float)buf[2 * rows + r]); }
+    if (r < rows) { st[r].sum = buf[r]; st[r].mn = f2ord((float)-buf[rows + r]); st[r].mx = f2ord((float)buf[2 * rows + r]); }
 }
 
 __global__ void row_stats_init_kernel(RowStats* st, int rows) {

@@ -141,11 +141,7 @@ int st_spectral_envelope(mm_ctx* c, const mm_geom* g, const float* in, float* en
         MM_TRY(arena(c, SL_ENV_TW, (size_t)kEnvM, &twd));
         envelope_tables_kernel<<<kEnvN / 256, 256, 0, c->stream>>>(window, twd);
         MM_CUDA(cudaGetLastError());
-        static bool attr = false;
-        if (!attr) {
-            MM_CUDA(cudaFuncSetAttribute(envelope_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            attr = true;
-        }
+        MM_CUDA(cudaFuncSetAttribute(envelope_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));      // per device; cheap
         EnvArgs2 A;
         A.in = in; A.n = g->n; A.stride = g->stride; A.channels = g->channels; A.frames = frames;
         // enough CTAs to fill the machine, few enough flushes: ~8 frames per CTA unless the batch is small

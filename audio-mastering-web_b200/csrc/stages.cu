@@ -57,23 +57,16 @@ static void choose_segments(int rows, int ntiles, int whalo, int capacity, int* 
 template <int M, int NF, int NIN, int DIR, int EPI, int NAUX, int ST, int NF32, int NSET = 1>
 static int launch_sweep2(mm_ctx* c, SweepArgs<M, NF>* As, int whalo, const char* name) {
     typedef Sweep2Cfg<M, NF, NIN, DIR, EPI, NAUX, ST> Cfg;
-    static int blocks_per_sm = 0;          // per instantiation; one device kind per process
-    static int num_sms = 0;
     auto kern = sweep2_kernel<M, NF, NIN, DIR, EPI, NAUX, ST, NF32, NSET>;
     SweepArgs<M, NF>& A = As[0];
     const size_t smem = Cfg::kBytes;
-    if (blocks_per_sm == 0) {
-        MM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        MM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-        int bps = 0;
-        MM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, kT, smem));
-        if (bps < 1) { set_error("sweep kernel %s does not fit on an SM (%zu bytes of shared memory)", name, smem); return 1; }
-        cudaDeviceProp prop;
-        MM_CUDA(cudaGetDeviceProperties(&prop, c->device));
-        num_sms = prop.multiProcessorCount;
-        blocks_per_sm = bps;
-        if (getenv("MM_DEBUG")) fprintf(stderr, "[mm] %s (%d float32 sections): %zu B smem, %d CTAs/SM x %d SMs\n", name, NF32, smem, bps, num_sms);
+    int blocks_per_sm = 0;
+    {
+        const bool first = c->occupancy.find((const void*)kern) == c->occupancy.end();
+        MM_TRY(kernel_setup(c, (const void*)kern, kT, smem, true, &blocks_per_sm));
+        if (first && getenv("MM_DEBUG")) fprintf(stderr, "[mm] %s (%d float32 sections): %zu B smem, %d CTAs/SM x %d SMs\n", name, NF32, smem, blocks_per_sm, c->num_sms);
     }
+    const int num_sms = c->num_sms;
     for (int k = 0; k < NSET; ++k) As[k].ntiles = DIR > 0 ? tiles_fwd(A.n, A.pad) : tiles_bwd(A.n, A.pad);
     if ((size_t)A.rows * (size_t)A.ntiles == 0) return 0;
     const int capacity = std::max(1, num_sms * blocks_per_sm / NSET);      // work items in flight (NSET CTAs each)
@@ -98,6 +91,7 @@ static int launch_sweep2(mm_ctx* c, SweepArgs<M, NF>* As, int whalo, const char*
     }
     {
         KernelScope ks(c, name);
+        ks.samples = (double)A.rows * (double)A.n;
         kern<<<grid, kT, smem, c->stream>>>(PP);
     }
     MM_CUDA(cudaGetLastError());
@@ -373,18 +367,29 @@ int run_row_stats(mm_ctx* c, const mm_geom* g, const float* in, RowStats** st_ou
     return 0;
 }
 
-int exchange_row_stats(mm_ctx* c, RowStats* st, int rows) {
+// One all-reduce of a time slice's exchange step, in stream order: NCCL enqueued from C on the context's stream when the slice
+// carries a communicator (nccl_shim.cu), else the caller's callback (tests: threads sharing a GPU, gloo on the CPU).
+int slice_allreduce(mm_ctx* c, void* ptr, int64_t count, int dtype, int op, const char* what) {
     const mm_slice* sl = c->slice;
-    if (!sl || !sl->allreduce) return 0;
+    if (!sl) return 0;
+    if (sl->nccl_comm) {
+        c->launches += 1;            // NCCL's kernel, not ours -- counted so that the launch total covers everything on the stream
+        return nccl_allreduce(c, sl->nccl_comm, ptr, count, dtype, op);
+    }
+    if (!sl->allreduce) return 0;
+    if (sl->allreduce(sl->user, ptr, count, dtype, op) != 0) { set_error("allreduce of %s failed", what); return 1; }
+    return 0;
+}
+static inline bool slice_exchanges(const mm_ctx* c) { return c->slice && (c->slice->nccl_comm || c->slice->allreduce); }
+
+int exchange_row_stats(mm_ctx* c, RowStats* st, int rows) {
+    if (!slice_exchanges(c)) return 0;
     double* xb;
     MM_TRY(arena(c, SL_XCHG, (size_t)rows * 3, &xb));
     row_stats_pack_kernel<<<(rows + 127) / 128, 128, 0, c->stream>>>(st, rows, xb);
     MM_CUDA(cudaGetLastError());
-    if (sl->allreduce(sl->user, xb, rows, 0, 0) != 0 || sl->allreduce(sl->user, xb + rows, rows, 0, 1) != 0 ||
-        sl->allreduce(sl->user, xb + 2 * rows, rows, 0, 2) != 0) {
-        set_error("allreduce of the channel statistics failed");
-        return 1;
-    }
+    MM_TRY(slice_allreduce(c, xb, rows, 0, 0, "the channel sums"));
+    MM_TRY(slice_allreduce(c, xb + rows, 2 * (int64_t)rows, 0, 2, "the channel minima / maxima"));
     row_stats_unpack_kernel<<<(rows + 127) / 128, 128, 0, c->stream>>>(st, rows, xb);
     MM_CUDA(cudaGetLastError());
     return 0;
@@ -407,6 +412,7 @@ int run_pointwise(mm_ctx* c, const mm_geom* g, PwArgs& A, const char* name) {
     A.n = g->n; A.stride = g->stride; A.tracks = g->tracks; A.channels = g->channels; A.track_base = g->track_base;
     dim3 grid((unsigned)((g->n + kPwFramesPerBlock - 1) / kPwFramesPerBlock), (unsigned)g->tracks);
     KernelScope ks(c, name);
+    ks.samples = (double)g->n * g->tracks * g->channels;
     pointwise_kernel<<<grid, kPwThreads, 0, c->stream>>>(A);
     MM_CUDA(cudaGetLastError());
     return 0;
@@ -696,17 +702,9 @@ int st_lufs(mm_ctx* c, const mm_geom* g, const float* in, const Pro& pro, double
         const KwPlan* kw = get_kw_plan(c, g->sr);
         if (!kw) return 1;
         MM_CUDA(cudaMemsetAsync(segsum, 0, (size_t)rows * lp->nseg * sizeof(unsigned long long), c->stream));
-        static int capacity = 0;
-        if (capacity == 0) {
-            int bps = 0;
-            MM_CUDA(cudaFuncSetAttribute(lufs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kLufsSmem));
-            MM_CUDA(cudaFuncSetAttribute(lufs_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-            MM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, lufs_kernel, kT, kLufsSmem));
-            cudaDeviceProp prop;
-            MM_CUDA(cudaGetDeviceProperties(&prop, c->device));
-            capacity = std::max(1, bps) * prop.multiProcessorCount;
-            if (getenv("MM_DEBUG")) fprintf(stderr, "[mm] lufs_kernel: %d B smem, %d CTAs/SM\n", kLufsSmem, bps);
-        }
+        int bps = 0;
+        MM_TRY(kernel_setup(c, (const void*)lufs_kernel, kT, kLufsSmem, true, &bps));
+        const int capacity = std::max(1, bps) * c->num_sms;
         LufsArgs A;
         memset(&A, 0, sizeof(A));
         for (int i = 0; i < 2; ++i) {
@@ -743,9 +741,8 @@ int st_lufs(mm_ctx* c, const mm_geom* g, const float* in, const Pro& pro, double
         }
         MM_CUDA(cudaGetLastError());
     }
-    if (sl && sl->allreduce && lp->valid) {      // block sums of the other ranks' frames (exact: 64-bit fixed point)
-        if (sl->allreduce(sl->user, segsum, (int64_t)rows * lp->nseg, 1, 0) != 0) { set_error("allreduce of the loudness block sums failed"); return 1; }
-    }
+    if (slice_exchanges(c) && lp->valid)         // block sums of the other ranks' frames (exact: 64-bit fixed point)
+        MM_TRY(slice_allreduce(c, segsum, (int64_t)rows * lp->nseg, 1, 0, "the loudness block sums"));
     GateArgs G;
     memset(&G, 0, sizeof(G));
     G.segsum = segsum; G.nseg = std::max(lp->nseg, 1); G.nblocks = lp->nblocks; G.channels = g->channels; G.tracks = g->tracks;

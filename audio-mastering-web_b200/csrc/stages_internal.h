@@ -41,6 +41,9 @@ int sweep_bwd(mm_ctx* c, const mm_geom* g, int nf, const FilterPlan* const* plan
 
 int run_row_stats(mm_ctx* c, const mm_geom* g, const float* in, RowStats** st_out);
 int exchange_row_stats(mm_ctx* c, RowStats* st, int rows);
+int slice_allreduce(mm_ctx* c, void* ptr, int64_t count, int dtype, int op, const char* what);
+// nccl_shim.cu
+int nccl_allreduce(mm_ctx* c, void* comm, void* ptr, int64_t count, int dtype, int op);
 int run_in_scalars(mm_ctx* c, const mm_geom* g, const RowStats* st, int use_dc, int use_guard, double headroom_db,
                    double* sub, double* mul, double* peak_track, double* mean_row);
 int run_pointwise(mm_ctx* c, const mm_geom* g, PwArgs& A, const char* name);
@@ -105,7 +108,10 @@ int st_deesser(mm_ctx* c, const mm_geom* g, const float* in, float* out, double 
 // export.cu: apply_maximizer_lookahead (pipeline.py:548-573); not in place
 int st_maximizer_lookahead(mm_ctx* c, const mm_geom* g, const float* in, float* out, long long delay_n, int cf);
 // deesser.cu: apply_dynamic_eq over nbands x {w0, bw, threshold_db, ratio, attack_ms, release_ms, max_cut_db}; in == out allowed
-int st_dynamic_eq(mm_ctx* c, const mm_geom* g, const float* in, float* out, int nbands, const double* params);
+// class of a dynamic-EQ section before the signal is looked at: MM_DYNEQ_STABLE / _LFILTER / _MARGINAL, or -1 (unstable)
+int dyneq_band_kind(const Ba& ba, double* rmax_out);
+int st_dynamic_eq(mm_ctx* c, const mm_geom* g, const float* in, float* out, int nbands, const double* params, unsigned flags = 0,
+                  int* classes = nullptr);
 int st_true_peak(mm_ctx* c, const mm_geom* g, const float* in, double* tp_dev);
 // true peak + stereo correlation + sample peak in one pass over the samples (stereo); mono falls back to the two kernels
 int st_true_peak_corr(mm_ctx* c, const mm_geom* g, const float* in, double* tp_dev, double* corr_dev, double* peak_dev);

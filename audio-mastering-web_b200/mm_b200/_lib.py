@@ -32,13 +32,14 @@ class TrackStats(C.Structure):
 
 
 class KTime(C.Structure):
-    _fields_ = [("name", C.c_char * 48), ("ms", C.c_double), ("launches", C.c_int64)]
+    _fields_ = [("name", C.c_char * 48), ("ms", C.c_double), ("launches", C.c_int64), ("samples", C.c_double)]
 
 
 MM_LEAD = 32
 CHAIN_V1, CHAIN_V2 = 1, 2
 FLAG_MEASURE_IN, FLAG_MEASURE_OUT, FLAG_NO_JOB_FADE = 1, 2, 4
 LOWPASS, HIGHPASS, BANDPASS = 0, 1, 2
+DYNEQ_STRICT = 1
 
 _vp, _i, _i64, _u64, _u32, _d = C.c_void_p, C.c_int, C.c_int64, C.c_uint64, C.c_uint32, C.c_double
 _dp = C.POINTER(C.c_double)
@@ -91,6 +92,7 @@ SIGNATURES = {
     "mm_dev_apply_target_curve_linear_phase": (_i, [_vp, _gp, _vp, _vp, _i]),
     "mm_design_linear_phase_ir": (_i, [_i, _i, _vp]),
     "mm_dev_apply_dynamic_eq": (_i, [_vp, _gp, _vp, _vp, _i, _vp]),
+    "mm_dev_apply_dynamic_eq2": (_i, [_vp, _gp, _vp, _vp, _i, _vp, _u32, C.POINTER(C.c_int32)]),
     "mm_dev_fft_resample": (_i, [_vp, _gp, _vp, _gp, _vp]),
     "mm_dev_apply_spectral_denoise": (_i, [_vp, _gp, _vp, _vp, _d, _d]),
     "mm_dev_spectral_envelope": (_i, [_vp, _gp, _vp, _vp]),
@@ -103,6 +105,10 @@ SIGNATURES = {
     "mm_dev_apply_stereoize": (_i, [_vp, _gp, _vp, _vp, _d, _d, _d]),
     "mm_slice_margin": (_i64, [C.c_int32]),
     "mm_dev_master_slice": (_i, [_vp, _gp, _i, C.POINTER(Style), _vp, _vp, _vp, _vp, _u64, _vp, _u32, _vp]),
+    "mm_nccl_unique_id": (_i, [_vp]),
+    "mm_nccl_comm_create": (_i, [_vp, _vp, _i, _i, C.POINTER(_vp)]),
+    "mm_nccl_comm_destroy": (_i, [_vp]),
+    "mm_nccl_version": (_i, []),
     "mm_master_host": (_i, [_vp, _i, C.c_int32, _i64, C.c_int32, C.c_int32, C.POINTER(Style), _vp, _vp, _vp, _vp, _u64,
                             C.POINTER(TrackStats), _u32]),
     "mm_master_host_pcm16": (_i, [_vp, _i, C.c_int32, _i64, C.c_int32, C.c_int32, C.POINTER(Style), _vp, _vp, _vp, _u64,
@@ -112,6 +118,7 @@ SIGNATURES = {
     "mm_ctx_workspace_bytes": (_i64, [_vp]),
     "mm_master_workspace_bytes": (_i64, [_gp, _i]),
     "mm_design_butter": (_i, [_i, _i, _dp, _dp, _dp]),
+    "mm_design_iirpeak": (_i, [_d, _d, _dp, _dp, C.POINTER(_i), _dp]),
     "mm_design_lfilter_zi": (_i, [_dp, _dp, _i, _dp]),
     "mm_design_k_weighting": (_i, [_i, _d, _dp, _dp]),
     "mm_design_scan_tables": (_i, [_dp, _dp, _i, _dp, _dp, _dp, _dp, _dp, _i, _dp, _dp, C.POINTER(_i), C.POINTER(_i)]),

@@ -17,7 +17,7 @@ INCLUDE = os.path.normpath(os.path.join(HERE, "..", "..", "include"))
 BUILD = os.path.join(CSRC, "build")
 LIB = os.path.join(HERE, "libmm_b200.so")
 
-SOURCES = ["stages.cu", "capi.cu", "deesser.cu", "followers.cu", "reverb.cu", "spectral.cu", "denoise.cu", "bigfft.cu", "export.cu", "analyzers.cu", "context.cu", "design.cpp"]
+SOURCES = ["stages.cu", "capi.cu", "nccl_shim.cu", "deesser.cu", "followers.cu", "reverb.cu", "spectral.cu", "denoise.cu", "bigfft.cu", "export.cu", "analyzers.cu", "context.cu", "design.cpp"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "--fmad=false",            # every rounding is the one written (numpy float32 steps are reproduced)
@@ -73,7 +73,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         with ThreadPoolExecutor(max_workers=min(len(jobs), os.cpu_count() or 4)) as ex:
             list(ex.map(run, jobs))
     if jobs or not os.path.exists(LIB):
-        cmd = [_nvcc(), "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-lcudart"]
+        cmd = [_nvcc(), "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-lcudart", "-ldl"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")

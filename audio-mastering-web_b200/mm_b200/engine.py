@@ -264,7 +264,7 @@ class Engine:
         buf = (_lib.KTime * cap)()
         cnt = C.c_int(0)
         _lib.check(self.lib.mm_ctx_kernel_times(self.ctx, buf, cap, C.byref(cnt)))
-        return {buf[i].name.decode(): (buf[i].ms, buf[i].launches) for i in range(min(cnt.value, cap))}
+        return {buf[i].name.decode(): (buf[i].ms, buf[i].launches, buf[i].samples) for i in range(min(cnt.value, cap))}
 
     def timing(self, on: bool):
         _lib.check(self.lib.mm_ctx_timing(self.ctx, 1 if on else 0))

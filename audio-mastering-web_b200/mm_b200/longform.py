@@ -10,9 +10,12 @@ couples the ranks are only the chain's global scalars:
 * BS.1770 100 ms block square sums -> gated loudness, gain          (pipeline.py:644-664)   rows x hops int64
 * output peak                      -> final -0.5 dB guard           (pipeline.py:1899)      1 float32
 
-each reduced over the ranks' OWN frames with an all-reduce (NCCL over NVLink on GPUs) that the C side requests
-through a callback, in stream order.  Block sums are 64-bit fixed point, so the loudness -- and with it every
-output sample's gain -- does not depend on the number of ranks.  With one rank this is ``mm_dev_master``.
+each reduced over the ranks' OWN frames with an all-reduce in stream order: four per file (sums; negated minima and
+maxima together; block sums; peak).  In production these are ``ncclAllReduce`` calls the C side enqueues itself on
+the context's stream (``make_exchange``: a communicator created from C, ``csrc/nccl_shim.cu``) -- no Python, no
+stream hand-over between two kernels; a callback (``make_allreduce``) serves the tests, where ranks are threads
+sharing one GPU or gloo processes on the CPU.  Block sums are 64-bit fixed point, so the loudness -- and with it
+every output sample's gain -- does not depend on the number of ranks.  With one rank this is ``mm_dev_master``.
 """
 from __future__ import annotations
 
@@ -29,7 +32,7 @@ _ALLREDUCE_T = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, 
 
 class Slice(C.Structure):
     _fields_ = [("global_n", C.c_int64), ("global_off", C.c_int64), ("own_lo", C.c_int64), ("own_hi", C.c_int64),
-                ("allreduce", _ALLREDUCE_T), ("user", C.c_void_p)]
+                ("allreduce", _ALLREDUCE_T), ("user", C.c_void_p), ("nccl_comm", C.c_void_p)]
 
 
 def slice_margin(sr: int) -> int:
@@ -102,8 +105,51 @@ def torch_allreduce(stream, device, group=None):
     return make_allreduce(red, wrap)
 
 
+class Exchange:
+    """The exchange step of one rank: an NCCL communicator owned by the C library (``mm_nccl_comm_create``), or -- ``comm``
+    None -- a Python all-reduce callback.  ``slice_struct`` fills the ``mm_slice`` either way."""
+
+    def __init__(self, comm=None, callback=None, note=""):
+        self.comm, self.callback, self.note = comm, callback, note
+
+    def slice_struct(self, global_n, plan):
+        return Slice(int(global_n), int(plan["start"]), int(plan["own_lo"]), int(plan["own_hi"]),
+                     self.callback if (self.callback is not None and not self.comm) else _ALLREDUCE_T(), None,
+                     self.comm if self.comm else None)
+
+    def describe(self):
+        return self.note
+
+    def close(self):
+        if self.comm:
+            _lib.load().mm_nccl_comm_destroy(self.comm)
+            self.comm = None
+
+
+def make_exchange(eng, world: int, rank: int, group=None, direct: bool = True) -> Exchange:
+    """Production exchange under torch.distributed (one process per GPU).  ``direct``: the C library opens its own NCCL
+    communicator (rank 0's unique id travels by a torch.distributed broadcast, once) and issues the all-reduces itself;
+    otherwise (or when libnccl cannot be loaded) torch.distributed's all-reduce through the callback."""
+    import torch
+    import torch.distributed as dist
+    lib = _lib.load()
+    if world <= 1:
+        return Exchange(note="single rank: none")
+    if direct and lib.mm_nccl_version() > 0:
+        buf = (C.c_ubyte * 128)()
+        if rank == 0:
+            _lib.check(lib.mm_nccl_unique_id(buf))
+        t = torch.tensor(list(buf), dtype=torch.uint8, device=eng.tdev)
+        dist.broadcast(t, src=0, group=group)
+        raw = bytes(t.cpu().tolist())
+        comm = C.c_void_p()
+        _lib.check(lib.mm_nccl_comm_create(eng.ctx, raw, int(world), int(rank), C.byref(comm)))
+        return Exchange(comm=comm, note=f"4 ncclAllReduce per file enqueued from C on the chain's stream (NCCL {lib.mm_nccl_version()})")
+    return Exchange(callback=torch_allreduce(eng.stream, eng.tdev, group), note="torch.distributed all_reduce through the mm_slice callback")
+
+
 def master_slice(eng, x_slice: np.ndarray, sr: int, plan: dict, global_n: int, style: dict, target_lufs: float, chain: str = "v2",
-                 *, allreduce=None, want_int16: bool = False, seed: int = 0, measure: bool = False, src=None):
+                 *, allreduce=None, exchange: Exchange = None, want_int16: bool = False, seed: int = 0, measure: bool = False, src=None):
     """Master one rank's slice.  ``x_slice``: (slice_frames, ch) float32 host array (or None with a device
     ``src`` Batch already holding it).  Returns dict(audio=(own, ch) float32, pcm=int16 or None, stats=record)."""
     import torch
@@ -112,8 +158,9 @@ def master_slice(eng, x_slice: np.ndarray, sr: int, plan: dict, global_n: int, s
     b = src if src is not None else eng.upload([np.asarray(x_slice, dtype=np.float32)], sr)
     dst = eng.like(b)
     g = b.geom
-    sl = Slice(int(global_n), int(plan["start"]), int(plan["own_lo"]), int(plan["own_hi"]),
-               allreduce if allreduce is not None else _ALLREDUCE_T(), None)
+    if exchange is None:
+        exchange = Exchange(callback=allreduce)
+    sl = exchange.slice_struct(global_n, plan)
     st_arr = (_lib.Style * 1)(style_struct(style, target_lufs))
     flags = (_lib.FLAG_MEASURE_IN | _lib.FLAG_MEASURE_OUT) if measure else 0
     with torch.cuda.stream(eng.stream):
@@ -143,8 +190,11 @@ def master_long_file(x: np.ndarray, sr: int, style: dict, target_lufs: float, ch
     plan = plan_slices(n, world, margin)[rank]
     if plan is None:
         raise ValueError(f"rank {rank} of {world} owns no frames of a {n}-frame file")
-    cb = torch_allreduce(eng.stream, eng.tdev, group) if world > 1 else None
-    res = master_slice(eng, x[plan["start"]:plan["stop"]], sr, plan, n, style, target_lufs, chain, allreduce=cb,
-                       want_int16=want_int16, seed=seed, measure=measure)
+    xch = make_exchange(eng, world, rank, group)
+    try:
+        res = master_slice(eng, x[plan["start"]:plan["stop"]], sr, plan, n, style, target_lufs, chain, exchange=xch,
+                           want_int16=want_int16, seed=seed, measure=measure)
+    finally:
+        xch.close()
     res["own_start"], res["own_stop"] = plan["own_start"], plan["own_stop"]
     return res

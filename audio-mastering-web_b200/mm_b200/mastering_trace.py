@@ -74,7 +74,7 @@ def batch_metrics(eng, b) -> list:
         peak = float(v[t, 0])
         res.append({"channels": b.channels, "samples": b.n, "duration_sec": round(b.n / float(b.sr), 4) if b.sr else 0.0,
                     "peak_linear": round(peak, 6), "peak_db": round(float(20.0 * np.log10(max(peak, 1e-12))), 2),
-                    "nan_count": int(v[t, 1]), "inf_count": int(v[t, 2]), "peak_raw": peak})
+                    "nan_count": int(v[t, 1]) - int(v[t, 2]), "inf_count": int(v[t, 2]), "peak_raw": peak})      # kernel: non-finite, Inf
     return res
 
 

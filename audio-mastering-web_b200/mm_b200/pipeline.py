@@ -53,10 +53,15 @@ _EXCITER_MODES = {"warm": 0, "tape": 1, "tube": 2, "transistor": 3, "digital": 4
 
 
 # ---- host <-> device edge -------------------------------------------------------------------------
-def _up(audio, sr, eng: Optional[Engine] = None):
+# elementwise reference functions return their input's shape; the filter stages squeeze an (n, 1) input to (n,) ("[:, 0]")
+_SHAPE_PRESERVING = {"remove_dc_offset", "remove_intersample_peaks", "fade_in", "apply_maximizer", "apply_parallel_compression",
+                     "normalize_lufs", "finalize_clip", "apply_rumble_filter"}
+
+
+def _up(audio, sr, eng: Optional[Engine] = None, squeeze: bool = True):
     eng = eng or get_engine()
     a = np.asarray(audio)
-    mono = a.ndim == 1
+    mono = a.ndim == 1 or (squeeze and a.shape[1] == 1)
     a2 = np.ascontiguousarray(a.reshape(a.shape[0], -1), dtype=np.float32)
     if a2.shape[1] not in (1, 2):
         raise ValueError("mm_b200 supports mono or stereo audio")
@@ -69,7 +74,7 @@ def _down(eng: Engine, b: Batch, mono: bool) -> np.ndarray:
 
 
 def _stage(name, audio, sr, *args):
-    eng, b, mono = _up(audio, sr)
+    eng, b, mono = _up(audio, sr, squeeze=name not in _SHAPE_PRESERVING)
     return _down(eng, eng.stage(name, b, *args, out=b), mono)
 
 
@@ -202,7 +207,7 @@ def apply_harmonic_exciter(audio: np.ndarray, sr: int, exciter_db: float = 0.0, 
 
 def fft_resample(audio: np.ndarray, num: int) -> np.ndarray:
     """``scipy.signal.resample(audio, num, axis=0).astype(float32)`` on the device."""
-    eng, b, mono = _up(audio, 44100)
+    eng, b, mono = _up(audio, 44100, squeeze=False)
     if int(num) == b.n:
         return _down(eng, b, mono)
     return _down(eng, eng.fft_resample(b, int(num)), mono)
@@ -277,14 +282,21 @@ DYNAMIC_EQ_MASTERING_BANDS = [
 ]
 
 
-def apply_dynamic_eq(audio: np.ndarray, sr: int, bands=None) -> np.ndarray:
+DYNEQ_CLASS_NAMES = ("stable", "overflow->identity", "lfilter-fallback", "marginal-filtfilt", "skipped")
+
+
+def apply_dynamic_eq(audio: np.ndarray, sr: int, bands=None, strict: bool = False, report: Optional[list] = None) -> np.ndarray:
     """backend/app/pipeline.py:1628-1700: per band a zero-phase ``iirpeak`` section, the attack/release follower of the band,
     a downward gain above the threshold, ``x - band + band * g``; bands act one after the other.
 
     The reference hands ``scipy.signal.iirpeak`` a *bandwidth* in its ``Q`` slot (:1661-1663), so a band is a stable section
-    only for ``q < 1`` (roughly); every band of ``DYNAMIC_EQ_MASTERING_BANDS`` is UNSTABLE and the reference's output for
-    them is overflow debris that it zeroes or patches with its input.  Stable bands run on the device with the reference's
-    arithmetic; an unstable band raises ``MMError`` naming it instead of reproducing garbage."""
+    only for ``q < 1`` (roughly), and most bands of ``DYNAMIC_EQ_MASTERING_BANDS`` are unstable or degenerate.  What the
+    reference then returns is reproduced per band class (``csrc/deesser.cu`` ``st_dynamic_eq``): an unstable section whose
+    forward pass must overflow is zeroed by the reference's ``nan_to_num`` and is therefore the identity; the degenerate
+    ``[1, 0, -1] / [1, ~0, ~-1]`` sections (q = 1, or the bandwidth clipped at w0 = 0.5) come back as ``x`` (``lfilter``
+    fallback) or ``x - const`` (``filtfilt`` with poles at +-1).  An unstable band whose overflow is not certain (a few
+    hundred samples, a constant signal) is passed through with a warning -- ``strict=True`` raises ``MMError`` instead.
+    ``report`` (additive): a list that receives one class name per band handed to the device."""
     if bands is None:
         bands = DYNAMIC_EQ_MASTERING_BANDS
     nyq = sr / 2.0
@@ -299,7 +311,17 @@ def apply_dynamic_eq(audio: np.ndarray, sr: int, bands=None) -> np.ndarray:
         rows.append([w0, bw, float(band.get("threshold_db", -12)), float(band.get("ratio", 3.0)), float(band.get("attack_ms", 5)),
                      float(band.get("release_ms", 80)), float(band.get("max_cut_db", -6))])
     flat = _lib.darr([v for r in rows for v in r]) if rows else None
-    return _stage("apply_dynamic_eq", audio, sr, len(rows), flat)
+    classes = (C.c_int32 * max(len(rows), 1))()
+    out = _stage("apply_dynamic_eq2", audio, sr, len(rows), flat, _lib.DYNEQ_STRICT if strict else 0, classes)
+    kinds = [DYNEQ_CLASS_NAMES[classes[i]] for i in range(len(rows))]
+    if report is not None:
+        report.extend(kinds)
+    if "skipped" in kinds:
+        import logging
+        logging.getLogger(__name__).warning(
+            "apply_dynamic_eq: %d unstable band(s) passed through (overflow of the reference's filter not certain for %d frames)",
+            kinds.count("skipped"), int(np.asarray(audio).shape[0]))
+    return out
 
 
 HIGH_FREQ_TRIM_CROSSOVER_HZ = 5000.0
@@ -399,8 +421,10 @@ def apply_rumble_filter(audio: np.ndarray, sr: int, cutoff_hz: float = 80.0) -> 
     return _stage("apply_rumble_filter", audio, sr, C.c_double(cutoff_hz))
 
 
-_SILENT_MSG = ("Обработка дала тишину. Отключите часть доп. настроек и попробуйте снова.")
-_NONFINITE_MSG = ("Обработка дала недопустимые значения (NaN/Inf). Отключите доп. модули и попробуйте снова.")
+# user-facing texts of the reference (pipeline.py:948-961); its tests match "тишину" / "Отключите"
+_SILENT_MSG = ("Обработка дала тишину. Отключите часть доп. настроек (Spectral Denoiser, De-esser, "
+               "Transient Designer, Parallel Compression, Dynamic EQ) и попробуйте снова.")
+_NONFINITE_MSG = "Обработка дала недопустимые значения (NaN/Inf). Отключите Dynamic EQ или другие доп. модули и попробуйте снова."
 
 
 def validate_mastered_not_silent(mastered: np.ndarray, *, trace_ctx=None, trace_sr: int = 44100) -> None:
@@ -530,9 +554,29 @@ def analyze_batch(tracks, sr, spectrum=True, eng: Optional[Engine] = None) -> li
 
 
 # ---- chains -----------------------------------------------------------------------------------------
-_V1_PROGRESS = [(5, "dc_offset"), (10, "peak_guard"), (15, "target_curve"), (32, "deesser"), (38, "dynamics"),
-                (52, "normalize_lufs"), (65, "final_spectral_balance"), (72, "style_eq"), (82, "peak_guard"),
-                (95, "fade_in"), (97, "done")]
+def _v1_progress_ticks(style, cfg, denoise_strength, transient_attack, transient_sustain, reference, reference_strength):
+    """The (percent, message) pairs run_mastering_pipeline reports, in order, with its conditional ticks 22 / 57 / 78 / 86 /
+    89 / 92 (backend/app/pipeline.py:1833-1907).  The router copies the message into the job record shown to the user
+    (routers/mastering.py:379-381), so the texts are the reference's, keyed by the stage that has just finished."""
+    t = [("start", 5, "Подготовка…"), ("dc_offset", 10, "Удаление DC-смещения"), ("peak_guard_in", 15, "Защита от пиков")]
+    if denoise_strength > 0.01:
+        t.append(("spectral_denoise", 22, f"Шумоподавление · strength={denoise_strength:.2f}"))
+    t += [("target_eq", 32, "Студийный EQ"), ("deesser", 38, "De-esser (5–9 kHz)"),
+          ("dynamics", 52, "Многополосная динамика и максимайзер")]
+    if cfg.get("parallel_mix", 0.0) > 0.01:
+        t.append(("parallel_compress", 57, f"Параллельная компрессия · mix={cfg['parallel_mix']:.2f}"))
+    t += [("normalize_lufs", 65, "Нормализация LUFS"), ("final_spectral_balance", 72, "Финальная частотная коррекция")]
+    if reference:
+        t.append(("reference_match", 78, f"Reference mastering · strength={reference_strength:.2f}"))
+    t.append(("style_eq", 82, f"Жанровый EQ · {style}"))
+    if abs(transient_attack - 1.0) > 0.02 or abs(transient_sustain - 1.0) > 0.02:
+        t.append(("transient_designer", 86, f"Транзиентный дизайнер · punch={transient_attack:.2f} sustain={transient_sustain:.2f}"))
+    if cfg.get("exciter_db", 0.0) > 0.05:
+        t.append(("harmonic_exciter", 89, f"Гармонический эксайтер · +{cfg['exciter_db']:.1f} dB"))
+    if abs(cfg.get("imager_width", 1.0) - 1.0) > 0.01:
+        t.append(("stereo_imager", 92, f"Стерео-расширение · width={cfg['imager_width']:.2f}"))
+    t += [("peak_guard_out", 95, "Финальная защита пиков"), ("finalize_clip", 97, "Готово")]
+    return t
 
 
 def run_mastering_pipeline(audio: np.ndarray, sr: int, target_lufs: float = -14.0, style: str = "standard",
@@ -541,25 +585,50 @@ def run_mastering_pipeline(audio: np.ndarray, sr: int, target_lufs: float = -14.
                            reference_sr=None, reference_strength: float = 0.8, trace_ctx=None) -> np.ndarray:
     """backend/app/pipeline.py:1800-1909.  The default path is one fused device call; a transient-designer request
     (which sits between the style EQ and the exciter, :1879-1889), spectral denoise (:1841-1844) or a reference track
-    (:1868-1871) takes the stage-by-stage path."""
+    (:1868-1871) takes the stage-by-stage path.
+
+    ``progress_callback(percent, message)``: the reference's percentages and messages in its order, conditional ticks
+    included.  On the stage-by-stage path each fires when its stage has finished, as in the reference; on the fused path the
+    first ("Подготовка…", 5) fires before the device call and the rest right after it (the stages have no host-visible
+    boundaries inside one launch sequence -- a 3-minute track is ~10 ms of device time)."""
+    name = style                                               # the reference's "Жанровый EQ" message shows the caller's string
     style = style if style in STYLE_CONFIGS else "standard"
     from . import mastering_trace as _mt
     tracing = trace_ctx is not None and _mt.trace_enabled()
     refm = reference_audio is not None and reference_sr is not None
+    ticks = _v1_progress_ticks(name, STYLE_CONFIGS[style], denoise_strength, transient_attack, transient_sustain, refm, reference_strength)
+
+    def report(stage):
+        if progress_callback is not None:
+            for key, pct, msg in ticks:
+                if key == stage:
+                    progress_callback(pct, msg)
+
+    report("start")
     if tracing or refm or denoise_strength > 0.01 or abs(transient_attack - 1.0) > 0.02 or abs(transient_sustain - 1.0) > 0.02:
         out = _run_v1_stagewise(audio, sr, target_lufs, style, transient_attack, transient_sustain,
                                 trace_ctx=trace_ctx if tracing else None, denoise_strength=denoise_strength,
-                                reference=(reference_audio, reference_sr, reference_strength) if refm else None)
+                                reference=(reference_audio, reference_sr, reference_strength) if refm else None, report=report)
     else:
         out = master_batch([audio], sr, [style], [target_lufs], chain="v1")["audio"][0]
-    if progress_callback is not None:      # stage boundaries are fused on the device; report them in order
-        for pct, msg in _V1_PROGRESS:
-            progress_callback(pct, msg)
+        for key, _, _ in ticks[1:]:
+            report(key)
+    _trim_engine()
     return out
 
 
+def _trim_engine():
+    """Give the calling thread's device scratch back when it exceeds ``MM_WORKSPACE_KEEP_MB`` (default 2048): worker threads
+    of a web service (asyncio.to_thread: up to min(32, cpu + 4) of them) would otherwise each keep their high-water mark."""
+    import os
+    eng = get_engine()
+    keep = float(os.environ.get("MM_WORKSPACE_KEEP_MB", "2048")) * (1 << 20)
+    if eng.lib.mm_ctx_workspace_bytes(eng.ctx) > keep:
+        eng.release_workspace()
+
+
 def _run_v1_stagewise(audio, sr, target_lufs, style, transient_attack, transient_sustain, trace_ctx=None, reference=None,
-                      denoise_strength=0.0):
+                      denoise_strength=0.0, report=None):
     """run_mastering_pipeline stage by stage (pipeline.py:1833-1909), for the options the fused chain does not carry:
     the transient designer, and the per-stage trace (mastering_trace.trace_stage after every stage, same stage names)."""
     from .mastering_trace import trace_stage
@@ -567,6 +636,8 @@ def _run_v1_stagewise(audio, sr, target_lufs, style, transient_attack, transient
 
     def tr(name, a, **extra):
         trace_stage(trace_ctx, name, a, sr, **extra)
+        if report is not None:
+            report(name)
         return a
 
     a = tr("dc_offset", remove_dc_offset(audio))
@@ -592,7 +663,8 @@ def _run_v1_stagewise(audio, sr, target_lufs, style, transient_attack, transient
     if abs(cfg.get("imager_width", 1.0) - 1.0) > 0.01:
         a = tr("stereo_imager", apply_stereo_imager(a, cfg["imager_width"]), imager_width=cfg["imager_width"])
     a = tr("peak_guard_out", remove_intersample_peaks(a, headroom_db=0.5))
-    a = tr("output_fade_in", apply_output_edge_fade_in(a, sr, fade_ms=6.0))
+    a = apply_output_edge_fade_in(a, sr, fade_ms=6.0)
+    trace_stage(trace_ctx, "output_fade_in", a, sr)
     return tr("finalize_clip", _stage("finalize_clip", a, sr))         # clip + nan_to_num (pipeline.py:1904-1906), on the device
 
 

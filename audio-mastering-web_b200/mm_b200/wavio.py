@@ -90,5 +90,7 @@ def pcm16_view(data: bytes):
     if fmt is None or body is None or fmt[0] != 1 or fmt[3] != 16:
         raise ValueError("pcm16_view: a PCM_16 WAV is required")
     ch, sr = fmt[1], fmt[2]
+    if ch not in (1, 2) or sr <= 0:
+        raise ValueError(f"pcm16_view: {ch} channels at {sr} Hz (mono or stereo PCM_16 required)")
     x = np.frombuffer(body[: len(body) // (2 * ch) * 2 * ch], dtype="<i2").reshape(-1, ch)
     return x, x.shape[0], ch, sr

@@ -78,9 +78,10 @@ int  mm_ctx_release_workspace(mm_ctx* ctx);
 /* Number of kernels this context has launched so far (bench.py's gpu_launches). */
 int64_t mm_ctx_launch_count(mm_ctx* ctx);
 /* Device-time accounting: when enabled, every kernel is bracketed by CUDA events on the
- * context's stream; mm_ctx_kernel_times fills up to `cap` entries (name, total ms, launches). */
+ * context's stream; mm_ctx_kernel_times fills up to `cap` entries (name, total ms, launches, channel-samples the launches
+ * visited where the launcher knows it -- row lists and track runs of a mixed batch -- else 0). */
 int  mm_ctx_timing(mm_ctx* ctx, int enable);
-typedef struct mm_ktime { char name[48]; double ms; int64_t launches; } mm_ktime;
+typedef struct mm_ktime { char name[48]; double ms; int64_t launches; double samples; } mm_ktime;
 int  mm_ctx_kernel_times(mm_ctx* ctx, mm_ktime* out, int cap, int* count);
 
 /* ---- layout helpers -------------------------------------------------------------------------*/
@@ -159,8 +160,18 @@ int mm_dev_apply_reverb(mm_ctx*, const mm_geom*, const float* in, float* out, in
 int mm_dev_fft_resample(mm_ctx*, const mm_geom* gin, const float* in, const mm_geom* gout, float* out);
 /* apply_dynamic_eq (backend/app/pipeline.py:1628-1700): params[nbands][7] = {w0, bw, threshold_db, ratio, attack_ms,
  * release_ms, max_cut_db}, w0 / bw as the reference clips them (:1657-1658) and hands them to scipy.signal.iirpeak(w0, bw).
- * Returns 3 when a band's section is unstable (every default band of the reference is: it passes a bandwidth as Q) */
+ * The reference passes a bandwidth where scipy expects Q, so most of its DEFAULT bands (DYNAMIC_EQ_MASTERING_BANDS,
+ * :1616-1625) are unstable or degenerate sections; what `_safe_filtfilt` + nan_to_num (:36-52, :1677) make of them is
+ * reproduced per band class (csrc/deesser.cu st_dynamic_eq): an unstable band whose forward pass must overflow is zeroed by
+ * the reference and therefore the identity; a degenerate b0 [1,0,-1] / [1,~0,~-1] section returns b0 x (lfilter fallback) or
+ * b0^2 (x - last sample of the odd extension) (filtfilt with poles at +-1). */
 int mm_dev_apply_dynamic_eq(mm_ctx*, const mm_geom*, const float* in, float* out, int nbands, const double* params);
+/* Same, reporting each band's class into classes[nbands] (host, may be NULL).  flags & MM_DYNEQ_STRICT: an unstable band
+ * whose overflow is not certain (class MM_DYNEQ_SKIPPED: passed through by default) is refused with return code 3. */
+#define MM_DYNEQ_STRICT 1u
+enum { MM_DYNEQ_STABLE = 0, MM_DYNEQ_OVERFLOW = 1, MM_DYNEQ_LFILTER = 2, MM_DYNEQ_MARGINAL = 3, MM_DYNEQ_SKIPPED = 4 };
+int mm_dev_apply_dynamic_eq2(mm_ctx*, const mm_geom*, const float* in, float* out, int nbands, const double* params,
+                             uint32_t flags, int32_t* classes);
 /* apply_spectral_denoise (backend/app/pipeline.py:1472-1524): 2048/512 STFT (scipy.signal.stft conventions), per-bin
  * percentile noise floor over the frames capped by 0.85 x the median, Wiener gain clipped to [0.25, 1], inverse STFT, clip.
  * n >= 2048 (the reference's scipy call raises below that); strength < 0.01 is a bypass */
@@ -246,7 +257,16 @@ typedef struct mm_slice {
     int64_t own_lo, own_hi; /* frames of the slice this rank owns (multiples of 4 except at the file's end) */
     mm_allreduce_fn allreduce;
     void* user;
+    void* nccl_comm;      /* ncclComm_t from mm_nccl_comm_create, or NULL: when set, the exchanges are ncclAllReduce calls enqueued
+                             from C on the context's stream and `allreduce` is not used */
 } mm_slice;
+/* NCCL communicator for the exchange step, created from C (libnccl.so.2 resolved with dlopen at first use).  Rank 0 makes a
+ * 128-byte id with mm_nccl_unique_id and hands it to the other ranks (any transport: torch.distributed broadcast in
+ * mm_b200/longform.py); every rank then calls mm_nccl_comm_create.  mm_nccl_version: NCCL_VERSION_CODE, 0 if unavailable. */
+int mm_nccl_unique_id(void* id128);
+int mm_nccl_comm_create(mm_ctx*, const void* id128, int world, int rank, void** comm_out);
+int mm_nccl_comm_destroy(void* comm);
+int mm_nccl_version(void);
 /* Margin (frames, multiple of 4096) a cut side needs at this sample rate. */
 int64_t mm_slice_margin(int32_t sr);
 int mm_dev_master_slice(mm_ctx*, const mm_geom*, int chain, const mm_style* style_host,
@@ -286,6 +306,10 @@ int64_t mm_master_workspace_bytes(const mm_geom*, int chain);
 /* wn: 1 value (low/high) or 2 (band), normalised to Nyquist. b,a receive ncoef = order+1
  * (low/high) or 2*order+1 (band) values. Returns ncoef, or <0 on error. */
 int mm_design_butter(int order, int btype, const double* wn, double* b, double* a);
+/* scipy.signal.iirpeak(w0, Q) as scipy 1.18 evaluates it (b[3], a[3]) and the class apply_dynamic_eq's band falls into
+ * before the signal is looked at: MM_DYNEQ_STABLE / MM_DYNEQ_LFILTER / MM_DYNEQ_MARGINAL, or -1 for an unstable section
+ * (rmax: its largest pole radius).  kind / rmax may be NULL. */
+int mm_design_iirpeak(double w0, double q, double* b, double* a, int* kind, double* rmax);
 /* _build_linear_phase_ir (backend/app/pipeline.py:187-217): ir[n_fft] float32 */
 int mm_design_linear_phase_ir(int sr, int n_fft, float* ir);
 int mm_design_lfilter_zi(const double* b, const double* a, int ncoef, double* zi);

@@ -597,9 +597,25 @@ def apply_maximizer_transient_aware(audio, sr, sensitivity=0.5):
     return _uncols(np.clip(limited, -1.0, 1.0).astype(np.float32), mono)
 
 
-def apply_dynamic_eq(audio, sr, bands):
-    """pipeline.py:1628-1700 for explicitly given bands (the reference's default bands are unstable sections: see
-    tests/test_host_design.py).  ``sg.iirpeak(w0, bw)`` is called with the reference's own (bandwidth-as-Q) arguments."""
+# pipeline.py:1616-1625
+DYNAMIC_EQ_MASTERING_BANDS = [
+    {"freq": 120, "q": 1.0, "threshold_db": -14, "ratio": 2.0, "attack_ms": 10, "release_ms": 100, "max_cut_db": -4},
+    {"freq": 250, "q": 1.2, "threshold_db": -12, "ratio": 2.5, "attack_ms": 8, "release_ms": 80, "max_cut_db": -5},
+    {"freq": 400, "q": 1.0, "threshold_db": -12, "ratio": 2.0, "attack_ms": 8, "release_ms": 80, "max_cut_db": -4},
+    {"freq": 800, "q": 1.2, "threshold_db": -12, "ratio": 2.0, "attack_ms": 5, "release_ms": 60, "max_cut_db": -4},
+    {"freq": 2500, "q": 1.4, "threshold_db": -12, "ratio": 2.5, "attack_ms": 5, "release_ms": 60, "max_cut_db": -5},
+    {"freq": 5000, "q": 1.4, "threshold_db": -14, "ratio": 3.0, "attack_ms": 3, "release_ms": 50, "max_cut_db": -6},
+    {"freq": 8000, "q": 1.2, "threshold_db": -16, "ratio": 4.0, "attack_ms": 2, "release_ms": 40, "max_cut_db": -8},
+    {"freq": 12000, "q": 0.8, "threshold_db": -18, "ratio": 2.0, "attack_ms": 5, "release_ms": 60, "max_cut_db": -4},
+]
+
+
+def apply_dynamic_eq(audio, sr, bands=None):
+    """pipeline.py:1628-1700.  ``sg.iirpeak(w0, bw)`` is called with the reference's own (bandwidth-as-Q) arguments, so the
+    default bands are unstable / degenerate sections (tests/test_host_design.py); the same scipy calls overflow, raise and
+    fall back exactly as they do in the reference."""
+    if bands is None:
+        bands = DYNAMIC_EQ_MASTERING_BANDS
     a, mono = _cols(audio)
     nyq = sr / 2.0
     out = a.copy().astype(np.float32)

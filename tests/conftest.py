@@ -40,6 +40,16 @@ def fft_stage_cases(mod, g):
     }
 
 
+def dyneq_default_cases():
+    """(name, input, sr, decimation) of tests/golden/dyneq_default.npz (make_golden_dyneq.py): inputs are regenerated from the
+    deterministic track recipe, only the reference's outputs are stored."""
+    sys.path.insert(0, GOLDEN)
+    import make_golden_dyneq as mg
+    for name, spec in mg.CASES.items():
+        x, sr = mg.case_input(name)
+        yield name, x, sr, spec[5]
+
+
 def tpdf_noise(seed, shape2d):
     """Recipe of tests/golden/make_golden.py for the dither buffer of a chain case."""
     rng = np.random.default_rng(int(seed))

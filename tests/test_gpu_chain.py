@@ -114,6 +114,32 @@ def test_chain_vs_oracle_longer_track(P):
         assert abs(res["stats"][0]["lufs_in"] - oc.measure_lufs(x, sr)) <= 0.01
 
 
+ALL_STYLES = ["standard", "edm", "hiphop", "classical", "podcast", "lofi", "house_basic", "dry_vocal"]
+
+
+@pytest.mark.parametrize("which", ["v1", "v2"])
+def test_all_presets_48k_against_oracle(P, which):
+    """BASELINE configs[2] in miniature: the eight presets (STYLE_CONFIGS order, each at its own target) as ONE mixed batch of
+    10 s 48 kHz stereo tracks, every track against the CPU oracle: samples 1e-4, LUFS 0.01 LU, true peak 0.01 dB."""
+    from mm_b200 import synth
+    from oracle import chain as oc
+    sr, dur = 48000, 10.0
+    tracks = [synth.numpy_track(60 + i, sr, dur) for i in range(len(ALL_STYLES))]
+    targets = [P.STYLE_CONFIGS[s]["lufs"] for s in ALL_STYLES]
+    res = P.master_batch(tracks, sr, ALL_STYLES, targets, chain=which, measure=True)
+    worst = 0.0
+    for i, style in enumerate(ALL_STYLES):
+        ref = (oc.run_v1 if which == "v1" else oc.run_v2)(tracks[i].copy(), sr, targets[i], style)
+        out = res["audio"][i]
+        e = _err(out, ref)
+        d_l = abs(res["stats"][i]["lufs_out"] - oc.measure_lufs(ref, sr))
+        d_tp = abs(P.true_peak_dbfs(out, sr) - oc.true_peak_dbfs(ref, sr))
+        print(f"[parity] {which}/{style} 48 kHz 10 s: max|gpu-oracle| = {e:.3e}  dLUFS {d_l:.2e}  dTP {d_tp:.2e}")
+        assert e <= 1e-4 and d_l <= 0.01 and d_tp <= 0.01, (which, style, e, d_l, d_tp)
+        worst = max(worst, e)
+    assert worst <= 5e-6          # what the chains are expected to hold (measured ~5e-7)
+
+
 def test_run_mastering_pipeline_contract(P):
     """The reference's own property tests (backend/tests/test_pipeline.py:204-223, :480-487)."""
     sr = 44100

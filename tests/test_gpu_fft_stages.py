@@ -219,9 +219,31 @@ def test_dynamic_eq_stable_bands_against_reference_golden(P):
         e = _err(out, g[k])
         print(f"[parity] {k}: {e:.3e}")
         assert out.shape == g[k].shape and out.dtype == np.float32 and e <= 1e-5, (k, e)   # |x| up to 3.8: a few float32 ulps over three bands
-    with pytest.raises(MMError, match="unstable"):
-        P.apply_dynamic_eq(g["input"], int(g["sr"]))
     assert len(P.DYNAMIC_EQ_MASTERING_BANDS) == 8
+
+
+def test_dynamic_eq_default_bands_against_reference_golden(P):
+    """apply_dynamic_eq(audio, sr) with the reference's DEFAULT bands (pipeline.py:1616-1625): unstable sections the reference
+    zeroes (identity), q = 1 sections its lfilter fallback turns into ``x * g``, the 12 kHz band at 48 kHz that filtfilt
+    returns as ``x - const`` -- against outputs of the unmodified reference at 44.1 / 48 / 96 kHz, 1 to 20 s."""
+    from conftest import dyneq_default_cases
+    from mm_b200._lib import MMError
+    g = load_golden("dyneq_default")
+    for name, x, sr, dec in dyneq_default_cases():
+        rep = []
+        out = P.apply_dynamic_eq(x, sr, report=rep)
+        e = _err(out[::dec], g[name])
+        print(f"[parity] dynamic eq defaults {name}: {e:.3e}  {rep}")
+        assert out.shape == x.shape and out.dtype == np.float32 and e <= 2e-6, (name, e)
+        assert "skipped" not in rep and rep.count("overflow->identity") >= 4
+    # an unstable band on a signal too short for its overflow to be certain: passed through (warning), refused under strict
+    x, sr, _ = next((x, sr, d) for n_, x, sr, d in dyneq_default_cases() if n_ == "d44_2s")
+    short = np.ascontiguousarray(x[:600])
+    rep = []
+    out = P.apply_dynamic_eq(short, sr, [P.DYNAMIC_EQ_MASTERING_BANDS[1]], report=rep)
+    assert rep == ["skipped"] and np.array_equal(out, np.clip(short, -1, 1))
+    with pytest.raises(MMError, match="unstable"):
+        P.apply_dynamic_eq(short, sr, [P.DYNAMIC_EQ_MASTERING_BANDS[1]], strict=True)
 
 
 def test_dynamic_eq_long_against_oracle(P):

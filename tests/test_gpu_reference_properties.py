@@ -122,8 +122,10 @@ def test_validate_mastered_not_silent(P, stereo):                     # test_pip
     P.validate_mastered_not_silent(stereo)
 
 
-def test_pro_modules_not_silent(P, stereo):                           # test_pipeline.py:387-421 (without the unstable dynamic EQ)
-    a = P.apply_transient_designer(stereo, SR, attack_gain=1.3, sustain_gain=0.9)
+def test_pro_modules_not_silent(P, stereo):                           # test_pipeline.py:387-421
+    a = P.apply_dynamic_eq(stereo, SR)
+    assert a.shape == stereo.shape and a.dtype == np.float32 and np.all(np.isfinite(a)) and np.max(np.abs(a)) > 1e-4
+    a = P.apply_transient_designer(a, SR, attack_gain=1.3, sustain_gain=0.9)
     a = P.apply_parallel_compression(a, SR, mix=0.25)
     assert a.shape == stereo.shape and np.all(np.isfinite(a)) and np.max(np.abs(a)) > 1e-4
 

@@ -276,11 +276,55 @@ def test_balanced_realization_float32_pass2(lib, design, tol):
     assert err <= tol, (design, err)
 
 
+_DYNEQ_DEFAULT = [(120, 1.0), (250, 1.2), (400, 1.0), (800, 1.2), (2500, 1.4), (5000, 1.4), (8000, 1.2), (12000, 0.8)]
+
+
+def _scipy_band_kind(w0, bw):
+    """What _safe_filtfilt (backend/app/pipeline.py:36-52) does with sg.iirpeak(w0, bw): 0 stable filtfilt, 2 ValueError ->
+    lfilter of an H(z) = b0 section, 3 filtfilt with poles at +-1, -1 unstable filtfilt."""
+    b, a = sg.iirpeak(w0, bw)
+    degenerate = abs(a[1]) <= 1e-12 and abs(a[2] + 1.0) <= 1e-12
+    try:
+        sg.lfilter_zi(b, a)
+    except ValueError:
+        assert degenerate, (w0, bw, a)          # the only way an iirpeak section gets a pole at exactly z = 1
+        return 2, b, a
+    if degenerate:
+        return 3, b, a
+    return (0 if np.max(np.abs(np.roots(a))) < 1.0 else -1), b, a
+
+
+def test_dynamic_eq_band_classes_match_scipy(lib):
+    """mm_design_iirpeak reproduces scipy 1.18's iirpeak coefficients bit for bit and sorts the reference's bandwidth-as-Q
+    sections (backend/app/pipeline.py:1657-1663) into the classes scipy's own filtfilt / lfilter_zi calls fall into: default
+    bands (:1616-1625) at every common rate plus a sweep of q = 1 bands across the sum(a) == 0 boundary."""
+    cases = []
+    for sr in (22050, 32000, 44100, 48000, 88200, 96000, 192000):
+        nyq = sr / 2.0
+        for freq, q in _DYNEQ_DEFAULT + [(f, 1.0) for f in (1000, 3000, 6000, 7000, 8000, 9000, 15000)] + [(1000, 0.7), (3000, 0.5)]:
+            if freq >= nyq * 0.98:
+                continue
+            w0 = float(np.clip(freq / nyq, 0.001, 0.98))
+            cases.append((sr, freq, q, w0, float(np.clip(w0 / max(q, 0.1), 0.001, 0.5))))
+    seen = set()
+    for sr, freq, q, w0, bw in cases:
+        kind_ref, b_ref, a_ref = _scipy_band_kind(w0, bw)
+        b, a = (C.c_double * 3)(), (C.c_double * 3)()
+        kind, rmax = C.c_int(99), C.c_double(0)
+        assert lib.mm_design_iirpeak(w0, bw, b, a, C.byref(kind), C.byref(rmax)) == 0
+        assert list(b) == list(b_ref) and list(a) == list(a_ref), (sr, freq, q)
+        assert kind.value == kind_ref, (sr, freq, q, kind.value, kind_ref, list(a_ref))
+        if kind_ref == -1:
+            assert abs(rmax.value - np.max(np.abs(np.roots(a_ref)))) < 1e-9 * rmax.value and rmax.value > 1.0
+        seen.add(kind_ref)
+    assert seen == {0, 2, 3, -1}
+
+
 def test_reference_dynamic_eq_default_bands_are_unstable():
-    """Why mm_b200 refuses the DEFAULT bands of apply_dynamic_eq: the reference calls ``sg.iirpeak(w0, bw)`` with a
-    bandwidth in the Q slot (backend/app/pipeline.py:1659-1663); for all eight default bands (:1616-1625) that is an
-    unstable section at 44.1 and 48 kHz."""
-    bands = [(120, 1.0), (250, 1.2), (400, 1.0), (800, 1.2), (2500, 1.4), (5000, 1.4), (8000, 1.2), (12000, 0.8)]
+    """The reference calls ``sg.iirpeak(w0, bw)`` with a bandwidth in the Q slot (backend/app/pipeline.py:1659-1663); for all
+    eight default bands (:1616-1625) that is an unstable or marginal section at 44.1 and 48 kHz (how each
+    class is reproduced)."""
+    bands = _DYNEQ_DEFAULT
     for sr in (44100, 48000):
         nyq = sr / 2.0
         for freq, q in bands:

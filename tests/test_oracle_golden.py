@@ -132,6 +132,21 @@ def dyneq_cases(mod, g):
             "dyneq_skipped": lambda: mod.apply_dynamic_eq(x * np.float32(30.0), sr, bands[3:])}
 
 
+def test_dynamic_eq_default_bands_match_reference_golden():
+    """apply_dynamic_eq(audio, sr) with the reference's default bands: the oracle makes the same scipy calls as the reference
+    (overflowing / degenerate sections included) and must return its outputs bit for bit."""
+    import warnings
+    from conftest import dyneq_default_cases
+    g = load_golden("dyneq_default")
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for name, x, sr, dec in dyneq_default_cases():
+            if len(x) > 200000:
+                continue                                  # the 20 s cases: GPU test / tests/test_oracle_vs_reference.py
+            out = oc.apply_dynamic_eq(x, sr, oc.DYNAMIC_EQ_MASTERING_BANDS)
+            assert np.array_equal(out[::dec], g[name]), name
+
+
 def test_dynamic_eq_stable_bands_match_reference_golden():
     """apply_dynamic_eq (pipeline.py:1628-1700) with bands whose iirpeak(w0, bw) section is stable (q < 1)."""
     g = load_golden("fft_stages")

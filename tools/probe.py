@@ -44,7 +44,7 @@ def main():
         tot = sum(v[0] for v in kt.values())
         print(f"rep {rep}: wall {wall*1e3:.1f} ms, kernels {tot:.1f} ms, audio-s/s {a.tracks*a.sec/wall:.0f}")
     frames = a.tracks * n
-    for k, (ms, cnt) in sorted(kt.items(), key=lambda kv: -kv[1][0]):
+    for k, (ms, cnt, _smp) in sorted(kt.items(), key=lambda kv: -kv[1][0]):
         print(f"  {k:32s} {ms:9.3f} ms  x{cnt:<3d}  {ms/tot*100:5.1f}%   {frames*2*4/ (ms/cnt*1e-3)/1e9:8.1f} GB/s per 1R-stream-equivalent")
     print("workspace GB", eng.lib.mm_ctx_workspace_bytes(eng.ctx) / 1e9, "launches", eng.launch_count())
 

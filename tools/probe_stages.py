@@ -31,7 +31,7 @@ def timed(eng, name, fn, frames_in, reps, bytes_per_frame):
     tot, kt = best
     print(f"{name}: {tot:.2f} ms of kernels, {frames_in / tot / 1e6:.1f} G channel-samples/s, "
           f"{frames_in * bytes_per_frame / tot / 1e6:.0f} GB/s of algorithmic traffic ({bytes_per_frame} B per channel-sample)")
-    for k, (ms, cnt) in sorted(kt.items(), key=lambda kv: -kv[1][0]):
+    for k, (ms, cnt, _smp) in sorted(kt.items(), key=lambda kv: -kv[1][0]):
         print(f"    {k:32s} {ms:9.3f} ms  x{cnt:<4d} {ms / tot * 100:5.1f}%")
     return tot
 
