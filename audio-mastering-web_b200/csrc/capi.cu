@@ -133,6 +133,14 @@ static int master_impl(mm_ctx* c, const mm_geom* g, int chain, const mm_style* s
     MM_TRY(arena(c, SL_NONFINITE, (size_t)T, &d_nonfinite));
     MM_TRY(arena(c, SL_PEAKBITS, (size_t)T, &d_peakbits));
     MM_CUDA(cudaMemsetAsync(d_nonfinite, 0, (size_t)T * sizeof(double), c->stream));
+    c->track_ids_dev = nullptr;
+    if (c->track_ids_host) {
+        int* d_ids;
+        MM_TRY(arena(c, SL_TRACKIDS, (size_t)T, &d_ids));
+        MM_CUDA(cudaMemcpyAsync(d_ids, c->track_ids_host + g->track_base, (size_t)T * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+        MM_CUDA(cudaStreamSynchronize(c->stream));
+        c->track_ids_dev = d_ids;
+    }
 
     // 1. remove_dc_offset + remove_intersample_peaks(0.5): one statistics read; the affine map rides
     //    as the prologue of the first sweeps (pipeline.py:134-149, :1833-1837; chain.py:112-113)
@@ -160,7 +168,8 @@ static int master_impl(mm_ctx* c, const mm_geom* g, int chain, const mm_style* s
     // 4. apply_dynamics (+ style-driven parallel compression in v1, pipeline.py:1850-1858)
     {
         const double v2x[3] = {214.0, 2230.0, 10000.0};   // chain.py:116
-        MM_TRY(st_dynamics(c, g, out, out, 6.0, v1 ? nullptr : v2x, nullptr, 12.0, any_par ? d_parmix : nullptr, nullptr));
+        MM_TRY(st_dynamics(c, g, out, out, 6.0, v1 ? nullptr : v2x, nullptr, 12.0, any_par ? d_parmix : nullptr, nullptr, 0,
+                           (flags & MM_FLAG_ENVELOPE_COMPRESSOR) ? MM_COMPRESSOR_ENVELOPE : MM_COMPRESSOR_SOFT_KNEE));
     }
     // 5. normalize_lufs: measure, derive the gain; the multiply rides as the next prologue
     Pro none;
@@ -555,6 +564,14 @@ int mm_dev_apply_dynamics(mm_ctx* c, const mm_geom* g, const float* in, float* o
 }
 
 int mm_dev_apply_maximizer(mm_ctx* c, const mm_geom* g, const float* in, float* out);
+
+int mm_dev_apply_dynamics_mode(mm_ctx* c, const mm_geom* g, const float* in, float* out, double knee_db, const double* crossovers_hz,
+                               const double* band_ratios, double max_upward_boost_db, int bands_only, int compressor) {
+    MM_API_BEGIN(c);
+    MM_TRY(check_geom(g));
+    if (compressor != MM_COMPRESSOR_SOFT_KNEE && compressor != MM_COMPRESSOR_ENVELOPE) { set_error("unknown compressor mode %d", compressor); return 2; }
+    return st_dynamics(c, g, in, out, knee_db, crossovers_hz, band_ratios, max_upward_boost_db, nullptr, nullptr, bands_only ? 1 : 0, compressor);
+}
 
 int mm_dev_apply_multiband_dynamics(mm_ctx* c, const mm_geom* g, const float* in, float* out, double knee_db, const double* crossovers_hz,
                                     const double* band_ratios, double max_upward_boost_db) {
@@ -1087,6 +1104,18 @@ int mm_master_host(mm_ctx* c, int chain, int32_t tracks, int64_t n, int32_t chan
     MM_API_BEGIN(c);
     return master_host_impl(c, chain, tracks, n, channels, sr, styles, audio_in, nullptr, audio_out, pcm16_out, noise_host, seed,
                             stats_host, flags);
+}
+
+int mm_master_host_ids(mm_ctx* c, int chain, int32_t tracks, int64_t n, int32_t channels, int32_t sr, const mm_style* styles,
+                       const float* audio_in, const int16_t* pcm16_in, float* audio_out, int16_t* pcm16_out, uint64_t seed,
+                       mm_track_stats* stats_host, uint32_t flags, const int32_t* track_ids) {
+    MM_API_BEGIN(c);
+    c->track_ids_host = track_ids;
+    const int rc = master_host_impl(c, chain, tracks, n, channels, sr, styles, audio_in, pcm16_in, audio_out, pcm16_out, nullptr, seed,
+                                    stats_host, flags);
+    c->track_ids_host = nullptr;
+    c->track_ids_dev = nullptr;
+    return rc;
 }
 
 // Job-level variant (what _run_mastering_job does with a PCM_16 WAV upload, routers/mastering.py:350-441): the data chunk's

@@ -71,7 +71,7 @@ enum SlotId {
     SL_PEAKBITS, SL_WIDTH, SL_PARMIX, SL_PEAKIN, SL_MEAN, SL_NONFINITE, SL_LUFS2, SL_LUFS3,
     SL_STAGE_IL, SL_STAGE_PCM, SL_STAGE_NOISE, SL_STAGE_PL, SL_STATS, SL_ENV0, SL_ENV1, SL_MISC,
     SL_STAGE_IL1, SL_STAGE_PCM1, SL_STAGE_NOISE1, SL_STAGE_OL, SL_STAGE_OL1, SL_XCHG, SL_ROWMAP, SL_REV0, SL_REV1,
-    SL_DN_MAG, SL_DN_NOISE, SL_BIGFFT, SL_BIGFFT_H, SL_ENV_WIN, SL_ENV_TW,
+    SL_DN_MAG, SL_DN_NOISE, SL_BIGFFT, SL_BIGFFT_H, SL_ENV_WIN, SL_ENV_TW, SL_TRACKIDS,
     SL_COUNT
 };
 
@@ -87,6 +87,8 @@ struct mm_ctx {
     cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
     const int* row_map = nullptr;       // set around the per-style stages of a mixed batch: device list of the rows to visit
     int row_map_rows = 0;
+    const int32_t* track_ids_host = nullptr;   // set for the duration of mm_master_host_ids: dither-stream index of every track of the call
+    const int* track_ids_dev = nullptr;        // ... and the current chunk's slice of it on the device
     const mm_slice* slice = nullptr;    // set for the duration of mm_dev_master_slice: the batch is a time slice of one file   // copy streams of the host-buffer entry point (lazy)
     mm::Slot slots[mm::SL_COUNT];
     std::map<std::string, mm::FilterPlan> plans;

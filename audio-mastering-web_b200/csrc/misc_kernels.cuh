@@ -299,6 +299,8 @@ struct FinalArgs {
     double* nonfinite;          // per track or null
     int track_base;             // mm_geom::track_base: keeps the dither stream independent of host-side chunking
     long long frame_base;       // index of frame 0 in the whole file (time slices): dither counter
+    const int* track_ids;       // optional: the dither stream of track t is keyed by track_ids[t] (uploads of different shapes are
+                                // mastered in groups; every track keeps the stream of its index in the caller's list)
 };
 
 constexpr int kFinThreads = 256;
@@ -380,7 +382,7 @@ __global__ void __launch_bounds__(kFinThreads, 3) finalize_kernel(const FinalArg
                 } else {
                     // i and frame_base are even: frames (c, c + 1) of an even c share one Philox call
                     const unsigned long long fr = (unsigned long long)(i + c + P.frame_base);
-                    if ((c & 1) == 0) dither_words(fr, track + P.track_base, P.seed, rnd);
+                    if ((c & 1) == 0) dither_words(fr, P.track_ids ? __ldg(P.track_ids + track) : track + P.track_base, P.seed, rnd);
                     n0 = tpdf16(rnd[(c & 1) * 2]);
                     n1 = tpdf16(rnd[(c & 1) * 2 + 1]);
                 }

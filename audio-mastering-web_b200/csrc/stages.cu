@@ -432,6 +432,7 @@ int run_finalize(mm_ctx* c, const mm_geom* g, const float* in, float* out, const
     A.n_fade = n_fade; A.fade_step = n_fade > 1 ? 1.0 / (double)(n_fade - 1) : 0.0;
     A.pcm = pcm; A.noise = noise; A.seed = seed; A.nonfinite = nonfinite; A.track_base = g->track_base;
     A.frame_base = c->slice ? c->slice->global_off : 0;
+    A.track_ids = c->track_ids_dev;
     dim3 grid((unsigned)((g->n + kFinFrames - 1) / kFinFrames), (unsigned)g->tracks);
     KernelScope ks(c, pcm ? "finalize_dither_int16" : "finalize");
 #define MM_FIN(C_, PCM_, NZ_) finalize_kernel<C_, PCM_, NZ_><<<grid, kFinThreads, 0, c->stream>>>(A)
@@ -591,7 +592,8 @@ int st_target_curve(mm_ctx* c, const mm_geom* g, const float* in, float* out, co
 // apply_dynamics = apply_multiband_dynamics (numpy branch) + apply_maximizer + hard limiter
 // (backend/app/pipeline.py:610-641, :414-481, :333-364)
 int st_dynamics(mm_ctx* c, const mm_geom* g, const float* in, float* out, double knee_db, const double* crossovers_hz,
-                const double* band_ratios, double max_upward_boost_db, const double* par_mix_rows, float* peak, int bands_only) {
+                const double* band_ratios, double max_upward_boost_db, const double* par_mix_rows, float* peak, int bands_only,
+                int compressor) {
     double cross[3] = {214.0, 3500.0, 10000.0};
     if (crossovers_hz) {
         double t[3];
@@ -632,6 +634,16 @@ int st_dynamics(mm_ctx* c, const mm_geom* g, const float* in, float* out, double
         d.par_mix = par_mix_rows;
         if (bands_only) {                            // min(|s|, |s| + inf, inf) = |s|: the maximizer / limiter step is the identity
             d.max_k = 1.0f; d.max_c = INFINITY; d.max_top = INFINITY;
+        }
+        if (compressor == MM_COMPRESSOR_ENVELOPE) {
+            // envelope-compressor mode (pipeline.py:373-411): the two middle bands are materialised (2 R / 2 W), then one pass over
+            // the four bands runs the followers, limiters, sum, maximizer and limiter (4 R / 1 W) -- bandcomp.cu
+            if (peak) { set_error("apply_dynamics (envelope compressor): output-peak tracking is not fused into this mode"); return 1; }
+            const float* i2[2] = {B.E[0], B.E[1]};
+            float* o2[2] = {B.T[2], B.T[3]};
+            MM_TRY(sweep_bwd(c, g, 2, p, i2, o2, 2, store, 9));
+            const float* bands[4] = {B.T[1], B.T[2], B.T[3], B.T[4]};
+            return launch_band_compress(c, g, bands, out, d);
         }
         bool general = par_mix_rows != nullptr;
         for (int i = 0; i < 4; ++i) general |= d.band[i].mode == 3;

@@ -63,7 +63,10 @@ void fill_parallel(DynParams* d, double ratio, double threshold_db);
 int st_target_curve(mm_ctx* c, const mm_geom* g, const float* in, float* out, const Pro& pro);
 int st_dynamics(mm_ctx* c, const mm_geom* g, const float* in, float* out, double knee_db, const double* crossovers_hz,
                 const double* band_ratios, double max_upward_boost_db, const double* par_mix_rows, float* peak,
-                int bands_only = 0);     // bands_only: apply_multiband_dynamics alone (no maximizer, no limiter)
+                int bands_only = 0,      // bands_only: apply_multiband_dynamics alone (no maximizer, no limiter)
+                int compressor = 0);     // MM_COMPRESSOR_SOFT_KNEE (numpy branch) or MM_COMPRESSOR_ENVELOPE (pedalboard-style branch)
+// bandcomp.cu: followers + limiters + sum + maximizer + limiter over the four float32 bands
+int launch_band_compress(mm_ctx* c, const mm_geom* g, const float* const* bands, float* out, const DynParams& d);
 int st_lufs(mm_ctx* c, const mm_geom* g, const float* in, const Pro& pro, double* lufs_dev, const double* target_dev,
             double* gain_row, double* gain_db);
 int st_final_balance(mm_ctx* c, const mm_geom* g, const float* in, float* out, const Pro& pro, float* peak);

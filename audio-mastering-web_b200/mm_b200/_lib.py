@@ -37,7 +37,8 @@ class KTime(C.Structure):
 
 MM_LEAD = 32
 CHAIN_V1, CHAIN_V2 = 1, 2
-FLAG_MEASURE_IN, FLAG_MEASURE_OUT, FLAG_NO_JOB_FADE = 1, 2, 4
+FLAG_MEASURE_IN, FLAG_MEASURE_OUT, FLAG_NO_JOB_FADE, FLAG_ENVELOPE_COMPRESSOR = 1, 2, 4, 8
+COMPRESSOR_SOFT_KNEE, COMPRESSOR_ENVELOPE = 0, 1
 LOWPASS, HIGHPASS, BANDPASS = 0, 1, 2
 DYNEQ_STRICT = 1
 
@@ -66,6 +67,7 @@ SIGNATURES = {
     "mm_dev_apply_target_curve": (_i, [_vp, _gp, _vp, _vp, _i]),
     "mm_dev_apply_deesser": (_i, [_vp, _gp, _vp, _vp, _d, _d, _d, _d, _d, _d]),
     "mm_dev_apply_dynamics": (_i, [_vp, _gp, _vp, _vp, _d, _dp, _dp, _d]),
+    "mm_dev_apply_dynamics_mode": (_i, [_vp, _gp, _vp, _vp, _d, _dp, _dp, _d, _i, _i]),
     "mm_dev_apply_multiband_dynamics": (_i, [_vp, _gp, _vp, _vp, _d, _dp, _dp, _d]),
     "mm_dev_apply_maximizer_lookahead": (_i, [_vp, _gp, _vp, _vp, _d]),
     "mm_dev_apply_maximizer": (_i, [_vp, _gp, _vp, _vp]),
@@ -113,6 +115,8 @@ SIGNATURES = {
                             C.POINTER(TrackStats), _u32]),
     "mm_master_host_pcm16": (_i, [_vp, _i, C.c_int32, _i64, C.c_int32, C.c_int32, C.POINTER(Style), _vp, _vp, _vp, _u64,
                                   C.POINTER(TrackStats), _u32]),
+    "mm_master_host_ids": (_i, [_vp, _i, C.c_int32, _i64, C.c_int32, C.c_int32, C.POINTER(Style), _vp, _vp, _vp, _vp, _u64,
+                                C.POINTER(TrackStats), _u32, C.POINTER(C.c_int32)]),
     "mm_host_alloc": (_i, [C.POINTER(_vp), _i64]),
     "mm_host_free": (_i, [_vp]),
     "mm_ctx_workspace_bytes": (_i64, [_vp]),

@@ -17,7 +17,7 @@ INCLUDE = os.path.normpath(os.path.join(HERE, "..", "..", "include"))
 BUILD = os.path.join(CSRC, "build")
 LIB = os.path.join(HERE, "libmm_b200.so")
 
-SOURCES = ["stages.cu", "capi.cu", "nccl_shim.cu", "deesser.cu", "followers.cu", "reverb.cu", "spectral.cu", "denoise.cu", "bigfft.cu", "export.cu", "analyzers.cu", "context.cu", "design.cpp"]
+SOURCES = ["stages.cu", "capi.cu", "nccl_shim.cu", "bandcomp.cu", "deesser.cu", "followers.cu", "reverb.cu", "spectral.cu", "denoise.cu", "bigfft.cu", "export.cu", "analyzers.cu", "context.cu", "design.cpp"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "--fmad=false",            # every rounding is the one written (numpy float32 steps are reproduced)

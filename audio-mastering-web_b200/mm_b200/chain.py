@@ -115,7 +115,7 @@ class DynamicsModule(BaseModule):
     def _process(self, eng, b, **kw):
         cx = _lib.darr(self.crossovers_hz) if self.crossovers_hz and len(self.crossovers_hz) == 3 else None
         br = _lib.darr(self.band_ratios) if self.band_ratios and len(self.band_ratios) == 4 else None
-        return eng.stage("apply_dynamics", b, _d(self.knee_db), cx, br, _d(self.max_upward_boost_db))
+        return eng.stage("apply_dynamics_mode", b, _d(self.knee_db), cx, br, _d(self.max_upward_boost_db), 0, P._compressor_id())
 
 
 class MaximizerModule(BaseModule):

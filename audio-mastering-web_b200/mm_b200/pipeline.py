@@ -51,6 +51,23 @@ DENOISE_PRESETS = {"vocal": (0.15, 25.0), "light": (0.20, 22.0), "medium": (0.5,
 
 _EXCITER_MODES = {"warm": 0, "tape": 1, "tube": 2, "transistor": 3, "digital": 4}
 
+# Which compressor apply_multiband_dynamics runs per band.  The reference decides by whether ``pedalboard`` imports
+# (backend/app/pipeline.py:442-446): with it, the envelope compressor (:373-411); without it, the memoryless soft-knee branch
+# (:466-474).  "soft_knee" is the default here because it is the branch pinned against the unmodified reference; "envelope"
+# (PARITY UNPINNED: restated JUCE arithmetic, csrc/bandcomp.cu) is what a production install of the reference runs.  Set
+# ``MM_COMPRESSOR=envelope`` (or assign COMPRESSOR_MODE) to make it the default of every entry point, or pass ``compressor=``.
+import os as _os
+COMPRESSOR_MODE = _os.environ.get("MM_COMPRESSOR", "soft_knee")
+
+
+def _compressor_id(compressor=None) -> int:
+    mode = COMPRESSOR_MODE if compressor is None else compressor
+    if mode in ("soft_knee", "numpy", 0):
+        return _lib.COMPRESSOR_SOFT_KNEE
+    if mode in ("envelope", "pedalboard", 1):
+        return _lib.COMPRESSOR_ENVELOPE
+    raise ValueError(f"unknown compressor mode {mode!r} (soft_knee | envelope)")
+
 
 # ---- host <-> device edge -------------------------------------------------------------------------
 # elementwise reference functions return their input's shape; the filter stages squeeze an (n, 1) input to (n,) ("[:, 0]")
@@ -119,21 +136,23 @@ def apply_deesser(audio: np.ndarray, sr: int, threshold_db: float = -6.0, ratio:
 
 
 def apply_dynamics(samples: np.ndarray, sr: int, knee_db: float = 6.0, crossovers_hz=None, band_ratios=None,
-                   max_upward_boost_db: float = 12.0) -> np.ndarray:
-    """backend/app/pipeline.py:610-641 (numpy compressor branch :466-474; the pedalboard/JUCE branch is
-    parity-unpinned and not offered)."""
+                   max_upward_boost_db: float = 12.0, compressor: Optional[str] = None) -> np.ndarray:
+    """backend/app/pipeline.py:610-641.  ``compressor`` (additive): "soft_knee" = the numpy branch (:466-474), "envelope" = the
+    pedalboard-style envelope compressor (:373-411, parity unpinned); default ``COMPRESSOR_MODE``."""
     cx = _lib.darr(crossovers_hz) if crossovers_hz is not None and len(crossovers_hz) == 3 else None
     br = _lib.darr(band_ratios) if band_ratios is not None and len(band_ratios) == 4 else None
-    return _stage("apply_dynamics", samples, sr, C.c_double(knee_db), cx, br, C.c_double(max_upward_boost_db))
+    return _stage("apply_dynamics_mode", samples, sr, C.c_double(knee_db), cx, br, C.c_double(max_upward_boost_db), 0,
+                  _compressor_id(compressor))
 
 
 def apply_multiband_dynamics(samples: np.ndarray, sr: int, knee_db: float = 6.0, crossovers_hz=None, band_ratios=None,
-                             max_upward_boost_db: float = 12.0) -> np.ndarray:
-    """backend/app/pipeline.py:414-481 (numpy compressor branch): the four-band split / compress / limit / gain / sum on its
-    own -- apply_dynamics without the maximizer and limiter behind it."""
+                             max_upward_boost_db: float = 12.0, compressor: Optional[str] = None) -> np.ndarray:
+    """backend/app/pipeline.py:414-481: the four-band split / compress / limit / gain / sum on its own -- apply_dynamics without
+    the maximizer and limiter behind it.  ``compressor`` as in apply_dynamics."""
     cx = _lib.darr(crossovers_hz) if crossovers_hz is not None and len(crossovers_hz) == 3 else None
     br = _lib.darr(band_ratios) if band_ratios is not None and len(band_ratios) == 4 else None
-    return _stage("apply_multiband_dynamics", samples, sr, C.c_double(knee_db), cx, br, C.c_double(max_upward_boost_db))
+    return _stage("apply_dynamics_mode", samples, sr, C.c_double(knee_db), cx, br, C.c_double(max_upward_boost_db), 1,
+                  _compressor_id(compressor))
 
 
 def apply_maximizer(audio: np.ndarray) -> np.ndarray:
@@ -705,7 +724,7 @@ def load_audio_from_bytes(data: bytes, fmt: str = "wav"):
 
 # ---- additive: batched entry point ------------------------------------------------------------------
 def master_batch(tracks, sr, styles, targets=None, chain="v2", want_int16=False, noise=None, seed=0, job_fade=True,
-                 measure=False, eng: Optional[Engine] = None):
+                 measure=False, eng: Optional[Engine] = None, compressor: Optional[str] = None):
     """Master equally-shaped tracks as one device batch.
 
     tracks: list of (n,) / (n, ch) float32 arrays; styles: list of style names; targets: list of LUFS
@@ -718,6 +737,8 @@ def master_batch(tracks, sr, styles, targets=None, chain="v2", want_int16=False,
         targets = [STYLE_CONFIGS[s]["lufs"] for s in names]
     sts = [style_struct(STYLE_CONFIGS[s], t) for s, t in zip(names, targets)]
     flags = (0 if job_fade else _lib.FLAG_NO_JOB_FADE) | ((_lib.FLAG_MEASURE_IN | _lib.FLAG_MEASURE_OUT) if measure else 0)
+    if _compressor_id(compressor) == _lib.COMPRESSOR_ENVELOPE:
+        flags |= _lib.FLAG_ENVELOPE_COMPRESSOR
     out, pcm, stats = eng.master(b, _lib.CHAIN_V1 if chain == "v1" else _lib.CHAIN_V2, sts, out=b, want_int16=want_int16,
                                  noise=noise, seed=seed, flags=flags)
     audio = eng.download(out)
@@ -730,28 +751,43 @@ def master_batch(tracks, sr, styles, targets=None, chain="v2", want_int16=False,
     return res
 
 
+def _shape_groups(shapes):
+    """Indices of equally-shaped items, groups in order of first appearance."""
+    groups = {}
+    for i, sh in enumerate(shapes):
+        groups.setdefault(sh, []).append(i)
+    return list(groups.items())
+
+
 def master_wav_jobs(wavs, styles, targets=None, chain="v2", seed=0, eng: Optional[Engine] = None) -> list:
-    """Additive, job level: what ``_run_mastering_job(_v2)`` does per upload (routers/mastering.py:350-637) for a batch of
-    PCM_16 WAV uploads of identical shape -- decode, master, dither, encode -- with the PCM frames crossing PCIe as int16
-    in both directions (``mm_master_host_pcm16``).  Returns a list of dicts ``wav`` (bytes), ``stats``."""
+    """Additive, job level: what ``_run_mastering_job(_v2)`` does per upload (routers/mastering.py:350-637) -- and what
+    ``/api/v2/batch`` (routers/mastering.py:855-1037) does for up to ten uploads one after the other -- for a whole list of PCM_16
+    WAV uploads: decode, master, dither, encode, with the PCM frames crossing PCIe as int16 in both directions
+    (``mm_master_host_ids``).  Uploads may differ in length, channel count and sample rate: they are mastered group by group of
+    equal shape (one pipelined device batch per group), and every track's result -- dither stream included, keyed by the track's
+    index in ``wavs`` -- equals what the same upload gives alone at that index.  Returns a list of dicts ``wav`` (bytes), ``stats``."""
     import ctypes as C_
     eng = eng or get_engine()
     metas = [wavio.pcm16_view(w) for w in wavs]
-    (n, ch, sr) = metas[0][1:]
-    if any(m[1:] != (n, ch, sr) for m in metas):
-        raise ValueError("master_wav_jobs: uploads must share length, channel count and sample rate")
-    pcm_in = np.ascontiguousarray(np.stack([m[0] for m in metas]))                # (T, n, ch) int16
-    pcm_out = np.empty_like(pcm_in)
     names = [s if s in STYLE_CONFIGS else "standard" for s in styles]
     if targets is None:
         targets = [STYLE_CONFIGS[s]["lufs"] for s in names]
-    arr = (_lib.Style * len(wavs))(*[style_struct(STYLE_CONFIGS[s], t) for s, t in zip(names, targets)])
-    st = (_lib.TrackStats * len(wavs))()
-    _lib.check(eng.lib.mm_master_host_pcm16(eng.ctx, _lib.CHAIN_V1 if chain == "v1" else _lib.CHAIN_V2, len(wavs), n, ch, sr, arr,
-                                            pcm_in.ctypes.data_as(C_.c_void_p), None, pcm_out.ctypes.data_as(C_.c_void_p), int(seed), st,
-                                            _lib.FLAG_MEASURE_IN | _lib.FLAG_MEASURE_OUT))
-    out = []
-    for t in range(len(wavs)):
-        rec = {k: (list(getattr(st[t], k)) if k == "mean" else getattr(st[t], k)) for k, _ in st[t]._fields_}
-        out.append({"wav": wavio.pack_wav_pcm16(pcm_out[t], sr), "stats": rec})
+    flags = (_lib.FLAG_MEASURE_IN | _lib.FLAG_MEASURE_OUT |
+             (_lib.FLAG_ENVELOPE_COMPRESSOR if _compressor_id() == _lib.COMPRESSOR_ENVELOPE else 0))
+    out = [None] * len(wavs)
+    for (n, ch, sr), idx in _shape_groups([m[1:] for m in metas]):
+        if n == 0:
+            raise ValueError("master_wav_jobs: an upload holds no frames")
+        pcm_in = np.ascontiguousarray(np.stack([metas[i][0] for i in idx]))                # (T, n, ch) int16
+        pcm_out = np.empty_like(pcm_in)
+        arr = (_lib.Style * len(idx))(*[style_struct(STYLE_CONFIGS[names[i]], targets[i]) for i in idx])
+        st = (_lib.TrackStats * len(idx))()
+        ids = (C_.c_int32 * len(idx))(*idx)
+        _lib.check(eng.lib.mm_master_host_ids(eng.ctx, _lib.CHAIN_V1 if chain == "v1" else _lib.CHAIN_V2, len(idx), n, ch, sr, arr, None,
+                                              pcm_in.ctypes.data_as(C_.c_void_p), None, pcm_out.ctypes.data_as(C_.c_void_p), int(seed), st,
+                                              flags, ids))
+        for k, i in enumerate(idx):
+            rec = {f: (list(getattr(st[k], f)) if f == "mean" else getattr(st[k], f)) for f, _ in st[k]._fields_}
+            out[i] = {"wav": wavio.pack_wav_pcm16(pcm_out[k], sr), "stats": rec}
+    _trim_engine()
     return out

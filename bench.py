@@ -2,7 +2,7 @@
 """Benchmark of the mastering hot path (BASELINE.json metric: mastered audio-seconds per wall-second).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--chain v2|v1]
-                    [--workload batch|mixed|analyze|longform] [--extras v1,mixed,analyze,longform|none]
+                    [--workload batch|mixed|analyze|longform] [--extras v1,envelope,mixed,analyze,longform|none]
 
 One step = one pass of the full mastering chain (+ TPDF dither to int16) over a batch of synthetic
 tracks that is already resident in HBM.  At N = 1 the workload is BASELINE.json configs[1]:
@@ -11,7 +11,7 @@ masters its own 64 tracks (sharded by track, weak scaling) and the per-track lou
 all-gathered over NCCL inside the timed region.  Prints ONE JSON line on rank 0.
 
 The default line also carries, under "extra", bounded runs of the other BASELINE configurations in the same
-process (same command the driver runs): the v1 chain on configs[1], configs[2] (mixed presets at 48 kHz),
+process (same command the driver runs): the v1 chain and the envelope-compressor mode on configs[1], configs[2] (mixed presets at 48 kHz),
 configs[3] (analyzer-only path) and configs[4] (one 2-hour 96 kHz file split in time over the N ranks).
 
 Accuracy gate ("check"): track 0 of the timed batch is the synthetic track the CPU oracle masters in the
@@ -52,7 +52,7 @@ STREAMS = {
     "sweep_bwd_m2_f2_dynamics": 5, "sweep_bwd_m2_f2_dynamics_gen": 5, "sweep_fwd_m2_f4_i1": 5, "sweep_bwd_m2_f4_combine": 6,
     "sweep_fwd_m4_f1_i1": 2, "sweep_bwd_m4_f1_store": 2, "envelope_gain": 2, "deesser_smooth_apply": 4,
     "lufs_kweight_blocks": 1, "row_stats": 1, "finalize_dither_int16": 2.5, "finalize": 2, "peak_after_imager": 1,
-    "sweep_bwd_m2_f2_dynamics_env": 5, "band_envelope_gain": 2,
+    "band_envelope_compress": 5,
 }
 FP32_PEAK_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12       # 148 SMs x 128 FP32 lanes x 2 flop x 1.965 GHz = 74.4 (B200_PROFILING.md)
 
@@ -134,12 +134,13 @@ def _cpu_one(args, keep=False):
     t, dur, chain = args[:3]
     sr = args[3] if len(args) > 3 else SR
     style = args[4] if len(args) > 4 else "standard"
+    compressor = args[5] if len(args) > 5 else "soft_knee"
     from oracle import chain as oc
     from mm_b200 import synth
     x = synth.numpy_track(t, sr, dur)
     target = oc.STYLE_CONFIGS[style]["lufs"]
     t0 = time.time()
-    out = (oc.run_v1 if chain == "v1" else oc.run_v2)(x, sr, target, style)
+    out = (oc.run_v1 if chain == "v1" else oc.run_v2)(x, sr, target, style, compressor=compressor)
     rng = np.random.default_rng(t)
     noise = (rng.random(out.shape) + rng.random(out.shape) - 1.0).astype(np.float32)
     pcm = oc.quantize_int16(out, noise)
@@ -316,26 +317,28 @@ def gate_record(max_abs, d_lufs, d_tp, int16_same_input, int16_chain_maxdiff, wh
             "pass": bool(ok)}
 
 
-def side_gate(rt, chain, style, sr, dur=10.0, track=1001):
+def side_gate(rt, chain, style, sr, dur=10.0, track=1001, compressor="soft_knee"):
     """Short-track gate for the bounded extras: one synthetic track through P.master_batch (same library, same precision policy)
     against the oracle."""
     from mm_b200 import pipeline as P
     from oracle import chain as oc
-    _, kept = _cpu_one((track, dur, chain, sr, style), keep=True)
+    _, kept = _cpu_one((track, dur, chain, sr, style, compressor), keep=True)
     target = P.STYLE_CONFIGS[style]["lufs"]
-    res = P.master_batch([kept["x"]], sr, [style], [target], chain=chain, want_int16=True, noise=kept["noise"][None], measure=True, eng=rt.eng)
+    res = P.master_batch([kept["x"]], sr, [style], [target], chain=chain, want_int16=True, noise=kept["noise"][None], measure=True, eng=rt.eng,
+                         compressor=compressor)
     out = res["audio"][0]
     max_abs = float(np.max(np.abs(out.astype(np.float64) - kept["out"])))
     q = rt.eng.quantize_int16(rt.eng.upload([kept["out"]], sr), noise=kept["noise"][None])[0]
     return gate_record(max_abs, abs(res["stats"][0]["lufs_out"] - kept["lufs"]), abs(P.true_peak_dbfs(out, sr) - kept["tp"]),
                        int(np.count_nonzero(q != kept["pcm"])), int(np.max(np.abs(res["int16"][0].astype(np.int32) - kept["pcm"].astype(np.int32)))),
-                       f"{dur:.0f} s synthetic track {track}, {sr} Hz, {chain}/{style} through master_batch vs the oracle")
+                       f"{dur:.0f} s synthetic track {track}, {sr} Hz, {chain}/{style}" + (" (envelope compressor)" if compressor != "soft_knee" else "") +
+                       " through master_batch vs the oracle")
 
 
 # -------------------------------------------------------------------------------------------------------
 # configs[1] / configs[2]: a batch of tracks through the full chain
 # -------------------------------------------------------------------------------------------------------
-def bench_batch(rt, args, *, chain, mixed, steps, warmup, main):
+def bench_batch(rt, args, *, chain, mixed, steps, warmup, main, envelope=False):
     torch, eng, world, rank = rt.torch, rt.eng, rt.world, rt.rank
     from mm_b200 import _lib, pipeline as P, shard, synth
     from mm_b200.engine import style_struct, TrackStats
@@ -368,7 +371,7 @@ def bench_batch(rt, args, *, chain, mixed, steps, warmup, main):
     style_names = [names[t % len(names)] if mixed else "standard" for t in ids]
     styles = [style_struct(P.STYLE_CONFIGS[s], P.STYLE_CONFIGS[s]["lufs"] if mixed else -14.0) for s in style_names]
     # algorithmic bytes per stereo frame of each track: 8 (W_base + 5 n_style_bands + 5 [exciter fires])
-    wbase = 64.5 if chain == "v1" else 54.5
+    wbase = (64.5 if chain == "v1" else 54.5) + (4.0 if envelope else 0.0)      # envelope-compressor mode: +4 words
 
     def _alg_bytes(sn):
         cfg = P.STYLE_CONFIGS[sn]
@@ -381,7 +384,7 @@ def bench_batch(rt, args, *, chain, mixed, steps, warmup, main):
         pcm = torch.empty((tracks, n, 2), dtype=torch.int16, device=eng.tdev)
         stats = torch.empty((tracks, shard.STATS_DOUBLES), dtype=torch.float64, device=eng.tdev)
     g = src.geom
-    flags = _lib.FLAG_MEASURE_OUT
+    flags = _lib.FLAG_MEASURE_OUT | (_lib.FLAG_ENVELOPE_COMPRESSOR if envelope else 0)
 
     def step(i):
         _lib.check(eng.lib.mm_dev_master(eng.ctx, C.byref(g), chain_id, arr, src.ptr, out.ptr, C.c_void_p(pcm.data_ptr()), None,
@@ -415,7 +418,7 @@ def bench_batch(rt, args, *, chain, mixed, steps, warmup, main):
         check["gate"]["philox_int16_vs_oracle_float_lsb"] = float(np.max(np.abs(got_pcm.astype(np.float64) - kept["out"].astype(np.float64) * 32767.0)))
         del kept
     elif not args.no_cpu and rank == 0:
-        check["gate"] = side_gate(rt, chain, "edm" if mixed else "standard", sr)
+        check["gate"] = side_gate(rt, chain, "edm" if mixed else "standard", sr, compressor="envelope" if envelope else "soft_knee")
 
     # ---- end-to-end through the host-buffer C-ABI call (pinned host memory, copies inside the timing) ----
     e2e = None
@@ -518,7 +521,8 @@ def bench_batch(rt, args, *, chain, mixed, steps, warmup, main):
                         if mixed else
                         f"configs[1]: {tracks} synthetic {dur:.0f} s {sr} Hz stereo tracks per GPU, {chain} default chain "
                         f"(style standard, -14 LUFS) + TPDF dither to int16 + after-LUFS"),
-           "chain": chain, "tracks_per_gpu": tracks, "frames_per_track": n,
+           "chain": chain, "compressor": "envelope (pedalboard-style, parity unpinned)" if envelope else "soft_knee (pinned)",
+           "tracks_per_gpu": tracks, "frames_per_track": n,
            "cache": f"inputs ({tracks * n * 8 / 1e9:.2f} GB per GPU) exceed L2; no flush needed",
            "precision_policy": "MM_PASS2=" + os.environ.get("MM_PASS2", "auto") + ": float32 streams; float64 chunk scan everywhere; in-chunk "
                                "recurrences float64 (full-path low cut-offs) or float32 FFMA2 on balanced realizations (DESIGN.md)"}
@@ -768,6 +772,8 @@ def run_ours(args):
         try:
             if name == "v1":
                 extra["v1_chain"] = compact(bench_batch(rt, args, chain="v1", mixed=False, steps=xs, warmup=xw, main=False))
+            elif name == "envelope":
+                extra["v2_envelope"] = compact(bench_batch(rt, args, chain=args.chain, mixed=False, steps=xs, warmup=xw, main=False, envelope=True))
             elif name == "mixed":
                 extra["mixed"] = compact(bench_batch(rt, args, chain=args.chain, mixed=True, steps=xs, warmup=xw, main=False))
             elif name == "analyze":
@@ -813,7 +819,7 @@ def main():
     ap.add_argument("--workload", default="batch", choices=["batch", "mixed", "analyze", "longform"],
                     help="batch = BASELINE configs[1] (default, what the driver times); mixed = configs[2] (48 kHz, mixed presets); "
                          "analyze = configs[3] (analyzer-only over 30 s clips); longform = configs[4], one long file split in time")
-    ap.add_argument("--extras", default="v1,mixed,analyze,longform",
+    ap.add_argument("--extras", default="v1,envelope,mixed,analyze,longform",
                     help="bounded runs of the other configurations appended to the default line under 'extra' ('none' to skip)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

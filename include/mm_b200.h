@@ -146,6 +146,9 @@ int mm_dev_apply_high_freq_trim(mm_ctx*, const mm_geom*, const float* in, float*
 /* apply_stereo_imager with stereoize_delay_ms > 0 (single-band width + Haas cross-delay), :1339-1398; in != out;
  * width = NaN skips the mid/side step (the pair already went through the 4-band mode) */
 int mm_dev_apply_stereoize(mm_ctx*, const mm_geom*, const float* in, float* out, double width, double delay_ms, double mix);
+/* apply_dynamics / apply_multiband_dynamics (bands_only != 0) with an explicit compressor mode (MM_COMPRESSOR_*) */
+int mm_dev_apply_dynamics_mode(mm_ctx*, const mm_geom*, const float* in, float* out, double knee_db, const double* crossovers_hz /*3 or NULL*/,
+                               const double* band_ratios /*4 or NULL*/, double max_upward_boost_db, int bands_only, int compressor);
 /* apply_stereo_imager with band_widths (4-band mode: _split_bands + per-band width + merge), :1360-1386;
  * crossovers_hz NULL -> MULTIBAND_CROSSOVERS_HZ (214, 3500, 10000) */
 int mm_dev_apply_stereo_imager_4band(mm_ctx*, const mm_geom*, const float* in, float* out, const double* band_widths /*4*/,
@@ -233,6 +236,14 @@ int mm_dev_signal_metrics(mm_ctx*, const mm_geom*, const float* in, double* out3
 #define MM_FLAG_MEASURE_IN   1u  /* also measure_lufs(input)  */
 #define MM_FLAG_MEASURE_OUT  2u  /* also measure_lufs(output) */
 #define MM_FLAG_NO_JOB_FADE  4u  /* v2: return chain.process output without the job's fade-in */
+#define MM_FLAG_ENVELOPE_COMPRESSOR 8u  /* multiband dynamics with the envelope (pedalboard-style) compressor, see below */
+/* Which compressor apply_multiband_dynamics runs per band (backend/app/pipeline.py:442-474).  The reference takes the
+ * envelope branch (_compress_band_pedalboard, :373-411: JUCE ballistics follower, attack / release 10/80, 10/80, 12/130,
+ * 18/180 ms per band, gain (env / thr)^(1/ratio - 1)) whenever `pedalboard` imports and the memoryless soft-knee branch
+ * otherwise.  SOFT_KNEE is pinned against the unmodified reference; ENVELOPE is PARITY UNPINNED (pedalboard is absent from the
+ * build image and from the reference's tests): it restates the published JUCE arithmetic and is checked against its own CPU
+ * restatement only (csrc/bandcomp.cu, oracle/chain.py). */
+enum { MM_COMPRESSOR_SOFT_KNEE = 0, MM_COMPRESSOR_ENVELOPE = 1 };
 /* styles: host array, one per track.  out_f32 planar (may alias in); out_i16 interleaved int16 or
  * NULL; noise as in mm_dev_quantize_int16; stats_dev: device mm_track_stats[tracks] or NULL. */
 int mm_dev_master(mm_ctx*, const mm_geom*, int chain, const mm_style* styles_host,
@@ -288,6 +299,14 @@ int mm_master_host(mm_ctx*, int chain, int32_t tracks, int64_t n, int32_t channe
 int mm_master_host_pcm16(mm_ctx*, int chain, int32_t tracks, int64_t n, int32_t channels, int32_t sr,
                          const mm_style* styles_host, const int16_t* pcm16_in, float* audio_out,
                          int16_t* pcm16_out, uint64_t dither_seed, mm_track_stats* stats_host, uint32_t flags);
+
+/* One group of a batch of uploads (backend/app/routers/mastering.py:855-1037, /api/v2/batch): `tracks` equally-shaped tracks stored
+ * back to back, float32 (audio_in) or PCM_16 (pcm16_in) -- exactly one of the two non-NULL.  track_ids[t] (NULL: t) keys track t's
+ * dither stream, so that uploads of different shapes, which mm_b200.pipeline.master_wav_jobs masters group by group, each keep
+ * the stream of their index in the caller's list: a track's result does not depend on what else was uploaded with it. */
+int mm_master_host_ids(mm_ctx*, int chain, int32_t tracks, int64_t n, int32_t channels, int32_t sr, const mm_style* styles_host,
+                       const float* audio_in, const int16_t* pcm16_in, float* audio_out, int16_t* pcm16_out, uint64_t dither_seed,
+                       mm_track_stats* stats_host, uint32_t flags, const int32_t* track_ids);
 
 /* Pinned host memory for the host-buffer entry point (cudaMallocHost / cudaFreeHost). */
 int mm_host_alloc(void** out, int64_t bytes);

@@ -282,8 +282,74 @@ def split_bands(audio, sr, crossovers_hz):
     return [_uncols(bd, mono) for bd in bands]
 
 
-def apply_multiband_dynamics(samples, sr, knee_db=6.0, crossovers_hz=None, band_ratios=None, max_upward_boost_db=12.0):
-    """pipeline.py:414-481, numpy branch (:466-474)."""
+# -- envelope-compressor branch (pedalboard / JUCE) ---------------------------------------------------------------
+# PARITY UNPINNED: pedalboard is not installed here and nothing in the reference's tests touches this branch
+# (pipeline.py:373-411, :442-465).  What follows restates the published JUCE sources that pedalboard.Compressor wraps --
+# juce::dsp::Compressor<float>::processSample over juce::dsp::BallisticsFilter<float> (peak level type):
+#     a = |x|;  cte = a > y_prev ? cteAT : cteRL;  y = a + cte * (y_prev - a)        cte = exp(-2 pi 1000 / (sr * t_ms)), y(-1) = 0
+#     gain = y < thr ? 1 : pow(y * (1 / thr), 1 / ratio - 1);   out = gain * x       thr = 10^(dB / 20), all float32
+# JUCE's per-block snap-to-zero of states below 1e-8 is not modelled.
+def _ballistics(x32, cat, crl):
+    env = np.empty(x32.shape[0], dtype=np.float32)
+    y = np.float32(0.0)
+    for i in range(x32.shape[0]):
+        a = np.float32(abs(x32[i]))
+        d = np.float32(y - a)
+        m = np.float32(cat * d) if d < 0 else np.float32(crl * d)
+        y = np.float32(a + m)
+        env[i] = y
+    return env
+
+
+try:
+    @_nb.njit(cache=False)
+    def _ballistics_nb(x32, cat, crl):
+        n = x32.shape[0]
+        env = np.empty(n, dtype=np.float32)
+        y = np.float32(0.0)
+        for i in range(n):
+            a = np.float32(abs(x32[i]))
+            d = np.float32(y - a)
+            if d < np.float32(0.0):
+                m = np.float32(cat * d)
+            else:
+                m = np.float32(crl * d)
+            y = np.float32(a + m)
+            env[i] = y
+        return env
+except Exception:  # pragma: no cover
+    _ballistics_nb = None
+
+
+BAND_TIMES_MS = ((10.0, 80.0), (10.0, 80.0), (12.0, 130.0), (18.0, 180.0))      # pipeline.py:451-456
+
+
+def compress_band_envelope(band, sr, threshold_db, ratio, lim_db, gain, attack_ms=10.0, release_ms=80.0):
+    """_compress_band_pedalboard (pipeline.py:373-411) with the JUCE compressor restated (parity unpinned, see above):
+    compressor -> hard clip at lim_db -> x gain, float32."""
+    b, mono = _cols(np.asarray(band))
+    x = np.ascontiguousarray(b, dtype=np.float32)
+    cat = np.float32(np.exp(-2.0 * np.pi * 1000.0 / (float(sr) * attack_ms)))
+    crl = np.float32(np.exp(-2.0 * np.pi * 1000.0 / (float(sr) * release_ms)))
+    thr = np.float32(10.0 ** (threshold_db / 20.0))
+    thr_inv = np.float32(1.0) / thr
+    pw = np.float32(1.0) / np.float32(max(ratio, 1.0)) - np.float32(1.0)
+    out = np.empty_like(x)
+    for c in range(x.shape[1]):
+        col = np.ascontiguousarray(x[:, c])
+        env = (_ballistics_nb or _ballistics)(col, cat, crl)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            g = np.where(env < thr, np.float32(1.0), np.power(env * thr_inv, pw, dtype=np.float32)).astype(np.float32)
+        out[:, c] = g * col
+    lim = 10 ** (lim_db / 20.0)
+    out = (np.clip(out, -lim, lim).astype(np.float32) * gain).astype(np.float32)
+    return _uncols(out, mono)
+
+
+def apply_multiband_dynamics(samples, sr, knee_db=6.0, crossovers_hz=None, band_ratios=None, max_upward_boost_db=12.0,
+                             compressor="soft_knee"):
+    """pipeline.py:414-481: ``compressor="soft_knee"`` is the numpy branch (:466-474, what the reference runs without
+    pedalboard -- pinned); ``"envelope"`` the pedalboard branch (:457-465) on the restated JUCE compressor (unpinned)."""
     samples = np.asarray(samples)
     x = samples.reshape(-1, 1) if samples.ndim == 1 else samples
     cross = crossovers_hz if crossovers_hz and len(crossovers_hz) == 3 else MULTIBAND_CROSSOVERS_HZ
@@ -295,8 +361,11 @@ def apply_multiband_dynamics(samples, sr, knee_db=6.0, crossovers_hz=None, band_
     acc = None
     for i, (lim_db, ratio, thr_db, gain) in enumerate(MULTIBAND_CONFIG):
         r = over[i] if over else ratio
-        bd = compress_soft_knee(bands[i], thr_db, r, knee_db, max_upward_boost_db)
-        bd = hard_limit(bd, lim_db) * gain
+        if compressor == "envelope" and r >= 1.0:
+            bd = compress_band_envelope(bands[i], sr, thr_db, r, lim_db, gain, *BAND_TIMES_MS[i])
+        else:
+            bd = compress_soft_knee(bands[i], thr_db, r, knee_db, max_upward_boost_db)
+            bd = hard_limit(bd, lim_db) * gain
         acc = bd if acc is None else acc + bd
     out = acc.astype(np.float32)
     return out[:, 0] if x.shape[1] == 1 else out
@@ -329,12 +398,12 @@ def apply_maximizer_lookahead(audio, sr, lookahead_ms=6.0):
     return _uncols(out, mono)
 
 
-def apply_dynamics(samples, sr, knee_db=6.0, crossovers_hz=None, band_ratios=None, max_upward_boost_db=12.0):
+def apply_dynamics(samples, sr, knee_db=6.0, crossovers_hz=None, band_ratios=None, max_upward_boost_db=12.0, compressor="soft_knee"):
     """pipeline.py:610-641."""
     samples = np.asarray(samples)
     x = samples.reshape(-1, 1) if samples.ndim == 1 else samples
     x = np.ascontiguousarray(x, dtype=np.float32)
-    y = apply_multiband_dynamics(x, sr, knee_db, crossovers_hz, band_ratios, max_upward_boost_db)
+    y = apply_multiband_dynamics(x, sr, knee_db, crossovers_hz, band_ratios, max_upward_boost_db, compressor=compressor)
     if y.ndim == 1:
         y = y.reshape(-1, 1)
     y = hard_limit(apply_maximizer(y), TRUE_PEAK_LIMIT_DB)
@@ -846,7 +915,7 @@ def _finalize(a):
     return out
 
 
-def run_v1(audio, sr, target_lufs=-14.0, style="standard", stages=None, denoise_strength=0.0):
+def run_v1(audio, sr, target_lufs=-14.0, style="standard", stages=None, denoise_strength=0.0, compressor="soft_knee"):
     """``run_mastering_pipeline`` default path (pipeline.py:1800-1909; optional spectral denoise :1841-1844; no
     reference/transient).
 
@@ -865,7 +934,7 @@ def run_v1(audio, sr, target_lufs=-14.0, style="standard", stages=None, denoise_
         a = keep("spectral_denoise", apply_spectral_denoise(a, sr, strength=denoise_strength))
     a = keep("target_eq", apply_target_curve(a, sr))
     a = keep("deesser", apply_deesser(a, sr))
-    a = keep("dynamics", apply_dynamics(a, sr))
+    a = keep("dynamics", apply_dynamics(a, sr, compressor=compressor))
     if cfg["parallel_mix"] > 0.01:
         a = keep("parallel_compress", apply_parallel_compression(a, sr, mix=cfg["parallel_mix"]))
     a = keep("normalize_lufs", normalize_lufs(a, sr, target_lufs))
@@ -880,7 +949,7 @@ def run_v1(audio, sr, target_lufs=-14.0, style="standard", stages=None, denoise_
     return keep("finalize_clip", _finalize(a))
 
 
-def run_v2(audio, sr, target_lufs=-14.0, style="standard", stages=None, job_fade=True):
+def run_v2(audio, sr, target_lufs=-14.0, style="standard", stages=None, job_fade=True, compressor="soft_knee"):
     """``MasteringChain.default_chain(...).process`` (chain.py:66-98, :101-134) followed, when
     ``job_fade``, by the job function's 6 ms fade-in (routers/mastering.py:583)."""
     cfg = STYLE_CONFIGS.get(style, STYLE_CONFIGS["standard"])
@@ -893,7 +962,7 @@ def run_v2(audio, sr, target_lufs=-14.0, style="standard", stages=None, job_fade
     a = keep("dc_offset", remove_dc_offset(audio))
     a = keep("peak_guard", remove_intersample_peaks(a, 0.5))
     a = keep("target_curve", apply_target_curve(a, sr))
-    a = keep("dynamics", apply_dynamics(a, sr, knee_db=6.0, crossovers_hz=V2_CROSSOVERS_HZ))
+    a = keep("dynamics", apply_dynamics(a, sr, knee_db=6.0, crossovers_hz=V2_CROSSOVERS_HZ, compressor=compressor))
     a = keep("normalize_lufs", normalize_lufs(a, sr, float(target_lufs)))
     a = keep("final_spectral_balance", apply_final_spectral_balance(a, sr))
     a = keep("style_eq", apply_style_eq(a, sr, style))

@@ -140,6 +140,39 @@ def test_all_presets_48k_against_oracle(P, which):
     assert worst <= 5e-6          # what the chains are expected to hold (measured ~5e-7)
 
 
+def test_envelope_compressor_mode_against_oracle(P):
+    """The pedalboard-style envelope compressor of apply_multiband_dynamics (pipeline.py:373-411, :442-465) as an explicit mode.
+    PARITY UNPINNED against pedalboard itself (absent); the device path is held to the CPU restatement of the JUCE arithmetic
+    (oracle/chain.py compress_band_envelope): stage, bands-only, an upward band (stays memoryless), mono, and both chains."""
+    from mm_b200 import synth
+    from oracle import chain as oc
+    for sr, dur, t in ((44100, 12.0, 70), (48000, 6.0, 71), (96000, 3.0, 72)):
+        x = synth.numpy_track(t, sr, dur) * np.float32(1.6)              # hot enough for every band's threshold
+        for kw in ({}, {"band_ratios": (2.0, 0.7, 1.0, 4.0), "crossovers_hz": (214.0, 2230.0, 10000.0)}):
+            out = P.apply_dynamics(x, sr, compressor="envelope", **kw)
+            ref = oc.apply_dynamics(x, sr, compressor="envelope", **kw)
+            soft = oc.apply_dynamics(x, sr, **kw)
+            e = _err(out, ref)
+            print(f"[parity] envelope compressor {sr} Hz {kw and 'custom' or 'default'}: max|gpu-oracle| = {e:.3e} (mode differs from soft knee by {_err(ref, soft):.3f})")
+            assert out.dtype == np.float32 and e <= 2e-6 and _err(ref, soft) > 1e-3
+        mb = P.apply_multiband_dynamics(x[:, 0].copy(), sr, compressor="envelope")
+        assert mb.shape == (x.shape[0],) and _err(mb, oc.apply_multiband_dynamics(x[:, 0].copy(), sr, compressor="envelope")) <= 2e-6
+    # chunking is invisible: one track alone and the same track inside a batch (different chunk plan) agree to float32 resolution
+    sr = 44100
+    tracks = [synth.numpy_track(80 + i, sr, 30.0) for i in range(6)]
+    for which, style in (("v2", "standard"), ("v1", "edm")):
+        target = P.STYLE_CONFIGS[style]["lufs"]
+        batch = P.master_batch(tracks, sr, [style] * 6, chain=which, compressor="envelope", measure=True)
+        single = P.master_batch([tracks[3]], sr, [style], chain=which, compressor="envelope")
+        assert _err(batch["audio"][3], single["audio"][0]) <= 1e-6
+        ref = (oc.run_v1 if which == "v1" else oc.run_v2)(tracks[3].copy(), sr, target, style, compressor="envelope")
+        e = _err(batch["audio"][3], ref)
+        print(f"[parity] {which}/{style} envelope-compressor chain 30 s: max|gpu-oracle| = {e:.3e}")
+        assert e <= 5e-6 and abs(batch["stats"][3]["lufs_out"] - oc.measure_lufs(ref, sr)) <= 0.01
+    # the default stays the pinned soft-knee branch
+    assert P.COMPRESSOR_MODE == "soft_knee"
+
+
 def test_run_mastering_pipeline_contract(P):
     """The reference's own property tests (backend/tests/test_pipeline.py:204-223, :480-487)."""
     sr = 44100
@@ -281,3 +314,33 @@ def test_job_level_pcm16_entry_equals_float_entry(P):
         got = np.frombuffer(job["wav"][44:], dtype="<i2").reshape(-1, 2)
         assert np.array_equal(got, out16[i]), i
         assert abs(job["stats"]["lufs_out"] - st[i].lufs_out) < 1e-12
+
+
+def test_wav_jobs_of_different_lengths_rates_and_channel_counts(P):
+    """/api/v2/batch takes arbitrary uploads (routers/mastering.py:855-1037): master_wav_jobs accepts a list whose members differ
+    in length, sample rate and channel count, masters them in groups of equal shape, and every member's WAV -- dither included --
+    is byte for byte what the same upload gives alone at that position of the list."""
+    from mm_b200 import synth, wavio
+    specs = [(44100, 1.3, 2), (48000, 0.9, 2), (44100, 1.3, 2), (44100, 2.1, 1), (48000, 0.9, 2), (44100, 0.8, 2), (96000, 0.6, 2),
+             (44100, 1.3, 2), (44100, 2.1, 1), (44100, 1.7, 2)]
+    styles = ["standard", "edm", "lofi", "podcast", "hiphop", "classical", "house_basic", "dry_vocal", "edm", "standard"]
+    wavs = []
+    for i, (sr, dur, ch) in enumerate(specs):
+        x = synth.numpy_track(90 + i, sr, dur, channels=ch)
+        wavs.append(wavio.pack_wav_pcm16(np.round(x * 32767.0).astype(np.int16), sr))
+    for chain in ("v2", "v1"):
+        jobs = P.master_wav_jobs(wavs, styles, chain=chain, seed=5)
+        assert len(jobs) == len(wavs)
+        for i in (0, 3, 4, 6, 7, 9):
+            # the same upload at the same list position in a shorter list (other groups, other group sizes)
+            alone = P.master_wav_jobs(wavs[:i + 1], styles[:i + 1], chain=chain, seed=5)[i]
+            assert jobs[i]["wav"] == alone["wav"], (chain, i)
+            got, sr_i = wavio.unpack_wav(jobs[i]["wav"])
+            assert sr_i == specs[i][0] and got.shape == (int(round(specs[i][0] * specs[i][1])), specs[i][2])
+            assert abs(jobs[i]["stats"]["lufs_out"] - alone["stats"]["lufs_out"]) < 1e-12
+        assert P.master_wav_jobs([wavs[0]], [styles[0]], chain=chain, seed=5)[0]["wav"] == jobs[0]["wav"]      # truly alone
+        # a track's audio does not depend on its group either: position 0 and position 2 / 7 hold different uploads of one shape
+        lone = P.master_wav_jobs([wavs[2]], [styles[2]], chain=chain, seed=5)[0]
+        a, _ = wavio.unpack_wav(jobs[2]["wav"])
+        b, _ = wavio.unpack_wav(lone["wav"])
+        assert np.max(np.abs(a - b)) <= 2.0 / 32768.0            # same float32 master, different dither stream (index 2 vs 0)
