@@ -181,86 +181,120 @@ static int master_impl(mm_ctx* c, const mm_geom* g, int chain, const mm_style* s
     //    a track's samples
     MM_CUDA(cudaMemsetAsync(d_peakbits, 0, (size_t)T * sizeof(float), c->stream));
     MM_TRY(st_final_balance(c, g, out, out, pgain, d_peakbits));
-    // 7./8. apply_style_eq, apply_harmonic_exciter per GROUP of tracks that share a style signature (wherever they sit
-    //       in the batch: the sweeps visit a group's rows through a device row list, one launch per sweep and group)
+    // 7./8. apply_style_eq, apply_harmonic_exciter (pipeline.py:1401-1434, :1267-1326).  The five band designs and the exciter's
+    //       high-pass are the same for every style; only the recombination weight differs.  So a mixed batch costs ONE forward
+    //       and ONE backward sweep per stage (band 0..4, exciter) over the rows whose style fires that stage -- a device row
+    //       list -- with the weight read per row, instead of one pair of launches per stage and style group (round 1: ~60
+    //       launches for the eight presets, now <= 12).  Each row's last firing stage tracks the track's output peak.
     {
-        std::vector<int> group(T, -1);
-        int ngroups = 0;
-        std::vector<int> rep;
-        for (int t = 0; t < T; ++t) {
-            for (int k = 0; k < ngroups && group[t] < 0; ++k)
-                if (sig[rep[k]] == sig[t]) group[t] = k;
-            if (group[t] < 0) { group[t] = ngroups++; rep.push_back(t); }
-        }
-        std::vector<int> rowlist;
-        std::vector<int> off(ngroups + 1, 0);
-        for (int k = 0; k < ngroups; ++k) {
-            for (int t = 0; t < T; ++t)
-                if (group[t] == k) for (int ch = 0; ch < C; ++ch) rowlist.push_back(t * C + ch);
-            off[k + 1] = (int)rowlist.size();
-        }
-        int* d_rows = nullptr;
+        const double nyq = g->sr / 2.0;
+        const double lo[5] = {30.0, 90.0, 700.0, 2800.0, 10000.0};
+        const double hi[5] = {90.0, 280.0, 2800.0, 9000.0, std::min(g->sr * 0.46, 18000.0)};
+        constexpr int kStages = 6;                                 // 5 style-EQ bands + exciter
+        std::vector<double> h_w((size_t)kStages * rows, 0.0);      // per stage and row: band weight / exciter gain (0 = does not fire)
+        std::vector<unsigned char> h_last((size_t)kStages * rows, 0);
+        std::vector<int> last_stage(T, -1);
         bool any_fires = false;
-        for (int k = 0; k < ngroups; ++k) {
-            for (int b = 0; b < 5; ++b) any_fires |= std::fabs(sig[rep[k]].eq[b]) >= 0.05;
-            any_fires |= sig[rep[k]].exciter_db != 0.0;
-        }
-        if (any_fires && ngroups > 1) {
-            MM_TRY(arena(c, SL_ROWMAP, rowlist.size(), &d_rows));
-            MM_CUDA(cudaMemcpyAsync(d_rows, rowlist.data(), rowlist.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
-            MM_CUDA(cudaStreamSynchronize(c->stream));      // rowlist is a host temporary
-        }
-        for (int k = 0; k < ngroups; ++k) {
-            const StyleSig& sg_ = sig[rep[k]];
-            bool fires = false;
-            for (int b = 0; b < 5; ++b) fires |= std::fabs(sg_.eq[b]) >= 0.05;
-            fires |= sg_.exciter_db != 0.0;
-            if (!fires) continue;
-            if (d_rows) { c->row_map = d_rows + off[k]; c->row_map_rows = off[k + 1] - off[k]; }
-            // the group's tracks re-track their output peak from scratch in the last stage that touches them
-            std::vector<int> members;
-            for (int t = 0; t < T; ++t) if (group[t] == k) members.push_back(t);
-            auto reset_peaks = [&]() -> int {
-                for (size_t a0 = 0; a0 < members.size();) {
-                    size_t a1 = a0 + 1;
-                    while (a1 < members.size() && members[a1] == members[a1 - 1] + 1) ++a1;
-                    MM_CUDA(cudaMemsetAsync(d_peakbits + members[a0], 0, (a1 - a0) * sizeof(float), c->stream));
-                    a0 = a1;
-                }
-                return 0;
-            };
-            int rc = reset_peaks();
-            int fired = 0;
-            if (rc == 0) rc = st_style_eq(c, g, out, out, sg_.eq, d_peakbits, &fired, /*reset_peak=*/0);
-            if (rc == 0 && sg_.exciter_db != 0.0) {
-                rc = reset_peaks();
-                if (rc == 0) rc = st_exciter(c, g, out, out, sg_.exciter_db, 0, d_peakbits);
+        for (int t = 0; t < T; ++t) {
+            for (int b = 0; b < 5; ++b) {
+                const double l = std::min(lo[b] / nyq, 0.98), h = std::min(hi[b] / nyq, 0.98);
+                if (std::fabs(sig[t].eq[b]) < 0.05 || l >= h) continue;                    // pipeline.py:1421-1426
+                const double wb = std::pow(10.0, sig[t].eq[b] / 20.0) - 1.0;
+                for (int ch = 0; ch < C; ++ch) h_w[(size_t)b * rows + t * C + ch] = wb;
+                last_stage[t] = b;
             }
-            c->row_map = nullptr;
-            c->row_map_rows = 0;
-            if (rc != 0) return rc;
+            if (sig[t].exciter_db != 0.0) {
+                for (int ch = 0; ch < C; ++ch) h_w[(size_t)5 * rows + t * C + ch] = std::pow(10.0, sig[t].exciter_db / 20.0) - 1.0;
+                last_stage[t] = 5;
+            }
+            if (last_stage[t] >= 0) {
+                any_fires = true;
+                for (int ch = 0; ch < C; ++ch) h_last[(size_t)last_stage[t] * rows + t * C + ch] = 1;
+            }
+        }
+        if (any_fires) {
+            // launch lists: per stage, the firing rows split by the precision class of their weight (style_eq: float32 pass 2 behind
+            // weights <= 0.3, the automatic policy otherwise -- the choice a single-track run makes, so batch == single bit for bit)
+            struct Launch { int stage, cls, off, cnt; bool uniform; double w; };
+            std::vector<Launch> launches;
+            std::vector<int> rowlist;
+            for (int st_ = 0; st_ < kStages; ++st_)
+                for (int cls = 0; cls < (st_ < 5 ? 2 : 1); ++cls) {
+                    Launch L{st_, cls, (int)rowlist.size(), 0, true, 0.0};
+                    for (int r = 0; r < rows; ++r) {
+                        const double w = h_w[(size_t)st_ * rows + r];
+                        if (w == 0.0) continue;
+                        if (st_ < 5 && (std::fabs(w) <= 0.3 ? 0 : 1) != cls) continue;
+                        if (L.cnt == 0) L.w = w; else if (w != L.w) L.uniform = false;
+                        rowlist.push_back(r);
+                        ++L.cnt;
+                    }
+                    if (L.cnt) launches.push_back(L);
+                }
+            int* d_rows = nullptr;
+            double* d_w = nullptr;
+            unsigned char* d_last = nullptr;
+            MM_TRY(arena(c, SL_ROWMAP, rowlist.size(), &d_rows));
+            MM_TRY(arena(c, SL_ROWW, h_w.size(), &d_w));
+            MM_TRY(arena(c, SL_ROWFLAG, h_last.size(), &d_last));
+            MM_CUDA(cudaMemcpyAsync(d_rows, rowlist.data(), rowlist.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+            MM_CUDA(cudaMemcpyAsync(d_w, h_w.data(), h_w.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+            MM_CUDA(cudaMemcpyAsync(d_last, h_last.data(), h_last.size(), cudaMemcpyHostToDevice, c->stream));
+            // tracks with a firing stage re-track their output peak from scratch in their last stage
+            for (int t0 = 0; t0 < T;) {
+                int t1 = t0 + 1;
+                const bool on = last_stage[t0] >= 0;
+                while (t1 < T && (last_stage[t1] >= 0) == on) ++t1;
+                if (on) MM_CUDA(cudaMemsetAsync(d_peakbits + t0, 0, (size_t)(t1 - t0) * sizeof(float), c->stream));
+                t0 = t1;
+            }
+            MM_CUDA(cudaStreamSynchronize(c->stream));           // the host vectors above are temporaries
+            for (const Launch& L : launches) {
+                const bool all_rows = L.cnt == rows;             // rows come out in increasing order: the list is the identity
+                c->row_map = all_rows ? nullptr : d_rows + L.off;
+                c->row_map_rows = all_rows ? 0 : L.cnt;
+                Epi e;
+                e.aux0 = out;
+                e.peak = d_peakbits;
+                e.peak_row = d_last + (size_t)L.stage * rows;
+                const FilterPlan* p;
+                if (L.stage < 5) {
+                    const int bnd = L.stage;
+                    p = plan_butter(c, 1, kBand, std::min(lo[bnd] / nyq, 0.98), std::min(hi[bnd] / nyq, 0.98), L.cls == 0 ? PREC_F32 : PREC_AUTO);
+                    e.mode = EPI_COMBINE;
+                    e.w[0] = L.w;
+                    if (!L.uniform) e.w_row = d_w + (size_t)L.stage * rows;
+                } else {
+                    p = plan_butter(c, 2, kHigh, std::min(6000.0 / nyq, 0.97), 0, PREC_F32);      // as st_exciter
+                    e.mode = EPI_EXCITER;
+                    e.exc_gain = L.w;
+                    e.exc_mode = 0;
+                    e.exc_k = 2.5;
+                    if (!L.uniform) e.exc_row = d_w + (size_t)L.stage * rows;
+                }
+                int rc = p ? 0 : 1;
+                Pro none2;
+                if (rc == 0) rc = st_filtfilt_combine(c, g, p, out, out, e, none2);
+                c->row_map = nullptr;
+                c->row_map_rows = 0;
+                if (rc != 0) return rc;
+            }
         }
     }
     // 9. apply_stereo_imager: folded into the final pass; tracks with an active imager need their
     //    post-imager peak first (read-only pass over those runs)
     if (any_img) {
-        for (int t0 = 0; t0 < T;) {
-            int t1 = t0 + 1;
-            const bool on = sig[t0].width != 1.0;
-            while (t1 < T && (sig[t1].width != 1.0) == on) ++t1;
-            if (on) {
-                mm_geom sub = *g;
-                sub.tracks = t1 - t0;
-                MM_CUDA(cudaMemsetAsync(d_peakbits + t0, 0, (size_t)sub.tracks * sizeof(float), c->stream));
-                PwArgs A;
-                pw_base(&A, out + (size_t)t0 * C * (size_t)g->stride + (sl ? sl->own_lo : 0), nullptr, PW_PEAK);
-                if (sl) sub.n = sl->own_hi - sl->own_lo;
-                A.width = d_width + t0;
-                A.peak = d_peakbits + t0;
-                MM_TRY(run_pointwise(c, &sub, A, "peak_after_imager"));
-            }
-            t0 = t1;
-        }
+        // one launch over the whole batch: CTAs of tracks without an active imager return immediately (round 1 launched once per
+        // run of consecutive imager tracks -- 32 small launches for the eight presets cycling over 128 tracks)
+        MM_TRY(reset_imager_peaks(c, d_peakbits, d_width, T));
+        mm_geom sub = *g;
+        PwArgs A;
+        pw_base(&A, out + (sl ? sl->own_lo : 0), nullptr, PW_PEAK);
+        if (sl) sub.n = sl->own_hi - sl->own_lo;
+        A.width = d_width;
+        A.peak = d_peakbits;
+        A.skip_unity = 1;
+        MM_TRY(run_pointwise(c, &sub, A, "peak_after_imager"));
     }
     // 10. remove_intersample_peaks(0.5) + clip/nan_to_num + 6 ms fade-in (+ TPDF dither to int16)
     {
@@ -343,7 +377,7 @@ void mm_ctx_destroy(mm_ctx* c) {
     bigfft_release(c);
     for (int i = 0; i < SL_COUNT; ++i) if (c->slots[i].p) cudaFree(c->slots[i].p);
     for (auto& kv : c->plans) if (kv.second.dev) cudaFree(kv.second.dev);
-    for (auto& kv : c->kw_plans) if (kv.second.dev) cudaFree(kv.second.dev);
+    for (auto& kv : c->kw_plans) { if (kv.second.dev) cudaFree(kv.second.dev); if (kv.second.plane64) cudaFree(kv.second.plane64); }
     for (auto& kv : c->lp_taps) if (kv.second) cudaFree(kv.second);
     for (auto& kv : c->lufs_plans) {
         cudaFree(kv.second.bnd); cudaFree(kv.second.tile_seg); cudaFree(kv.second.blk_lo); cudaFree(kv.second.blk_hi);

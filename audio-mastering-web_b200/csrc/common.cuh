@@ -53,6 +53,22 @@ __device__ __forceinline__ float2 pair_step(const PairK& k, float2 x, float2& s0
     return y;
 }
 
+// The same step with the two lanes' inputs given as scalars: the input-dependent products (D x, B x) are scalar FMULs written
+// straight into the halves of the accumulator pairs, so no register moves are needed to pack (xa, xb) -- 6 FMUL + 6 FFMA2 where
+// packing cost 9 packed instructions plus ~10 moves per step (SASS of the round-1 loudness kernel).  Same association, same bits.
+__device__ __forceinline__ float2 pair_step_xy(const PairK& k, float xa, float xb, float2& s0, float2& s1) {
+    float2 t, m0, m1;
+    t.x = __fmul_rn(k.D.x, xa);     t.y = __fmul_rn(k.D.y, xb);
+    m0.x = __fmul_rn(k.B[0].x, xa); m0.y = __fmul_rn(k.B[0].y, xb);
+    m1.x = __fmul_rn(k.B[1].x, xa); m1.y = __fmul_rn(k.B[1].y, xb);
+    const float2 y = ffma2(k.C[0], s0, ffma2(k.C[1], s1, t));
+    const float2 n0 = ffma2(k.A[0][0], s0, ffma2(k.A[0][1], s1, m0));
+    const float2 n1 = ffma2(k.A[1][0], s0, ffma2(k.A[1][1], s1, m1));
+    s0 = n0;
+    s1 = n1;
+    return y;
+}
+
 // prologue applied to samples as they are loaded
 enum { PRO_NONE = 0, PRO_SUBMUL_F32 = 1, PRO_MUL_F64 = 2 };
 // epilogue of a sweep
@@ -94,7 +110,11 @@ template <int M, int NF> struct SweepArgs {
     double exc_gain, exc_k;
     int exc_mode;
     float* peak;             // per track |out| max (float bits, atomicMax) or null
-    const int* row_map;      // optional: the sweep visits rows row_map[0 .. rows) of the batch (tracks that share a style)
+    const int* row_map;      // optional: the sweep visits rows row_map[0 .. rows) of the batch (tracks whose style fires this stage)
+    // per-row parameters of a mixed-preset batch (indexed by the row's position in the batch; null = the scalars above)
+    const double* w_row;     // EPI_COMBINE with one section: recombination weight (a style-EQ band's 10^(dB/20) - 1)
+    const double* exc_row;   // EPI_EXCITER: 10^(dB/20) - 1
+    const unsigned char* peak_row;   // the row's output counts towards its track's peak (this is the last stage that touches it)
     long long pk_lo, pk_hi;  // row positions (inclusive) whose outputs count towards the peak (a time slice's own frames)
 };
 

@@ -140,8 +140,8 @@ const KwPlan* get_kw_plan(mm_ctx* c, int sr) {
         return nullptr;
     }
     cascade_realization(s0, s1, &cas);
-    if (!build_scan_tables_ss(cas, kS, kT, &p.tabs) || !build_scan_tables_ss(s0, kS, kT, &p.sec[0]) ||
-        !build_scan_tables_ss(s1, kS, kT, &p.sec[1])) {
+    if (!build_scan_tables_ss(cas, kS, kT, &p.tabs) || !build_scan_tables_ss(cas, 2 * kS, kT, &p.tabs64) ||
+        !build_scan_tables_ss(s0, kS, kT, &p.sec[0]) || !build_scan_tables_ss(s1, kS, kT, &p.sec[1])) {
         set_error("K-weighting at %d Hz: pole too close to the unit circle for the %d-sample tile", sr, kL);
         return nullptr;
     }
@@ -149,6 +149,12 @@ const KwPlan* get_kw_plan(mm_ctx* c, int sr) {
     pack_tables<4>(p.tabs, h);
     if (cudaMalloc(&p.dev, h.size() * sizeof(double)) != cudaSuccess) { set_error("cudaMalloc(K-weighting tables) failed"); return nullptr; }
     if (cudaMemcpyAsync(p.dev, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream) != cudaSuccess ||
+        cudaStreamSynchronize(c->stream) != cudaSuccess) {
+        set_error("upload of K-weighting tables failed");
+        return nullptr;
+    }
+    if (cudaMalloc(&p.plane64, p.tabs64.Plane.size() * sizeof(double)) != cudaSuccess ||
+        cudaMemcpyAsync(p.plane64, p.tabs64.Plane.data(), p.tabs64.Plane.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream) != cudaSuccess ||
         cudaStreamSynchronize(c->stream) != cudaSuccess) {
         set_error("upload of K-weighting tables failed");
         return nullptr;
@@ -197,9 +203,13 @@ int get_lufs_plan(mm_ctx* c, long long n, int sr, const LufsPlan** out, long lon
     if (bnd.size() < 2) { bnd.clear(); bnd.push_back(0); bnd.push_back(0); p.valid = p.valid && false; }
     p.nseg = (int)bnd.size() - 1;
     p.nblocks = (int)lo.size();
-    // the loudness kernel splits a 32-sample chunk over at most three hops (lufs_kernel.cuh)
-    for (size_t s2 = 0; p.valid && s2 + 2 < bnd.size(); ++s2)
-        if (bnd[s2 + 2] - bnd[s2] < kS) { set_error("loudness: %d Hz is too low a sample rate for the block partition of this kernel", sr); return 1; }
+    // the loudness kernel splits a warp-tile (2048 or 1024 samples) over at most three hops (lufs_kernel.cuh)
+    p.min_span2 = 1LL << 40;
+    for (size_t s2 = 0; p.valid && s2 + 3 < bnd.size(); ++s2) p.min_span2 = std::min(p.min_span2, bnd[s2 + 2] - bnd[s2]);
+    if (p.valid && p.min_span2 < 1024) {
+        set_error("loudness: %d Hz is too low a sample rate for the block partition of this kernel (100 ms hops of at least 512 samples)", sr);
+        return 1;
+    }
     std::vector<int> blo(lo.size()), bhi(lo.size());
     for (size_t j = 0; j < lo.size(); ++j) {
         blo[j] = (int)(std::lower_bound(bnd.begin(), bnd.end(), lo[j]) - bnd.begin());

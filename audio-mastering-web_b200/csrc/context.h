@@ -48,13 +48,16 @@ struct FilterPlan {
 };
 
 struct KwPlan {                 // K-weighting cascade (shelf -> high-pass) of one sample rate as a 4-state system
-    ScanTables tabs;            // tables of the cascade in [balanced shelf; balanced high-pass] coordinates
+    ScanTables tabs;            // tables of the cascade in [balanced shelf; balanced high-pass] coordinates, 32-sample chunks
+    ScanTables tabs64;          // the same for 64-sample chunks (the loudness kernel's default)
     ScanTables sec[2];          // the two sections' balanced realizations (A, B, C, D used)
-    double* dev = nullptr;
+    double* dev = nullptr;      // Tab<4> of `tabs`
+    double* plane64 = nullptr;  // tabs64.Plane ([32][16]) on the device
 };
 
 struct LufsPlan {               // per (n, sr): gating blocks expressed over merged segments
     int nseg = 0, nblocks = 0, valid = 0, ntiles = 0;
+    long long min_span2 = 0;    // min over s of bnd[s + 2] - bnd[s] (interior): a warp-tile no longer than this holds <= 2 hop ends
     double scale = 0;
     long long* bnd = nullptr;
     int* tile_seg = nullptr;
@@ -71,7 +74,7 @@ enum SlotId {
     SL_PEAKBITS, SL_WIDTH, SL_PARMIX, SL_PEAKIN, SL_MEAN, SL_NONFINITE, SL_LUFS2, SL_LUFS3,
     SL_STAGE_IL, SL_STAGE_PCM, SL_STAGE_NOISE, SL_STAGE_PL, SL_STATS, SL_ENV0, SL_ENV1, SL_MISC,
     SL_STAGE_IL1, SL_STAGE_PCM1, SL_STAGE_NOISE1, SL_STAGE_OL, SL_STAGE_OL1, SL_XCHG, SL_ROWMAP, SL_REV0, SL_REV1,
-    SL_DN_MAG, SL_DN_NOISE, SL_BIGFFT, SL_BIGFFT_H, SL_ENV_WIN, SL_ENV_TW, SL_TRACKIDS,
+    SL_DN_MAG, SL_DN_NOISE, SL_BIGFFT, SL_BIGFFT_H, SL_ENV_WIN, SL_ENV_TW, SL_TRACKIDS, SL_ROWW, SL_ROWFLAG,
     SL_COUNT
 };
 

@@ -26,7 +26,8 @@ namespace mm {
 
 __device__ __forceinline__ void cp_async16_env(void* smem_dst, const void* gsrc) {
     const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gsrc) : "memory");
+    // L2::256B: one DRAM row activation per 256-byte block of a thread's private sequential stream instead of two
+    asm volatile("cp.async.cg.shared.global.L2::256B [%0], [%1], 16;\n" ::"r"(d), "l"(gsrc) : "memory");
 }
 
 struct EnvArgs {

@@ -14,22 +14,29 @@
 // accumulators (integer atomics are associative, so the loudness -- and the gain derived from it -- is
 // bit-reproducible).
 #pragma once
-#include "sweep3.cuh"
+#include "sweep4.cuh"
 
 namespace mm {
 
 constexpr double kSqScale = 1099511627776.0;        // 2^40: fixed-point scale of the square sums
 
+constexpr int kLufsMaxS = 64;
 struct LufsArgs {
-    PairK k;                 // .x = shelf, .y = high-pass (balanced realizations); g[j] = cascade pass-1 weights:
-                             // g[j][0] = states (0, 1) of the shelf, g[j][1] = states (2, 3) of the high-pass
-    const double* tab;       // Tab<4> of the cascade (device): Plane[lane] is read from here
+    // pass-1 weights of the cascade for a lane's chunk of S samples: g[j][0] = states (0, 1) of the shelf, g[j][1] = states (2, 3) of
+    // the high-pass (balanced coordinates)
+    float2 g[kLufsMaxS][2];
+    const double* plane;     // [32][16] (device): (A^S)^lane of the cascade
     // float32 scan tables, column pairs: M[k][0] = rows (0, 1) of column k, M[k][1] = rows (2, 3)
-    float2 Pw2[5][4][2];     // (A^32)^(2^d)
-    float2 Qw2[kNW + 1][4][2];   // (A^1024)^w; [kNW] carries a state across one tile
+    float2 Pw2[5][4][2];     // (A^S)^(2^d)
+    float2 Q1[4][2];         // A^(32 S): carries a state across one warp-tile
+    // pass 2.  The shelf as a float32 DF2T section: b, negated a1 / a2, and the map from the balanced state to the DF2T state.
+    // The high-pass in its balanced realization with the states rescaled so that B = (1, 1) (floating-point round-off is scale
+    // invariant): y = C s + D u, s' = A s + (u, u) -- 7 operations; hp_d maps the balanced state into the rescaled one.
+    float sh_b[3], sh_na[2], shT[2][2];
+    float hpA[2][2], hpC[2], hpD, hp_d[2];
     const float* in;
     long long n, stride;
-    int rows, ntiles, channels;
+    int rows, ntiles, channels;   // ntiles, seglen, whalo: in WARP-tiles of 1024 samples
     int seglen, nseg, whalo;
     int pro_mode;
     const double* pro_sub;
@@ -37,7 +44,7 @@ struct LufsArgs {
     // hop bookkeeping: sample i belongs to hop s iff bnd[s] <= i < bnd[s+1]
     const long long* bnd;    // [nhop + 1]
     int nhop;
-    const int* tile_seg;     // [ntiles] hop of max(first sample of tile, 0), clamped to nhop
+    const int* tile_seg;     // [4096-sample tiles] hop of max(first sample of tile, 0), clamped to nhop
     long long goff;          // index of the row's sample 0 in the signal the hops are laid over (time slices; else 0)
     long long own_lo, own_hi;   // samples of the row that are counted (time slices; else 0, n)
     unsigned long long* segsum;   // [rows][nhop] fixed-point sums of squares
@@ -45,13 +52,18 @@ struct LufsArgs {
 
 // The scan runs in float32 as well: in the balanced coordinates every combine is well conditioned, a state error of
 // 6e-8 dies with the filters' own memory (A^4096 is ~1e-10 for the 38 Hz high-pass at 44.1 kHz), and the meter only
-// needs the block powers to ~1e-6 relative (0.01 LU = 2.3e-3).  No float64 instruction is left in this kernel.
-struct LufsTab {             // per-lane scan table of the 4-state cascade in shared memory
-    float PlaneT[16][32];    // Plane[lane][k] transposed: lane-contiguous, conflict free
-};
-struct LufsScratch {
-    float4 tot[kNW];
-    float4 carry[2];         // [tile parity]
+// needs the block powers to ~1e-6 relative (0.01 LU = 2.3e-3).  No float64 instruction is left in the sample loops.
+//
+// Round 2: every WARP is autonomous.  A warp owns a segment of 1024-sample warp-tiles of one row (32 lanes x 32 samples), keeps
+// the state entering its next warp-tile in registers (identical in all lanes), double-buffers its own 4 KB staging slots with
+// cp.async and never meets a block barrier: the round-1 kernel spent 2.5 stall cycles per issued instruction at its two
+// __syncthreads per tile.  The hop bookkeeping (which 100 ms hop a sample's square belongs to) is done once per warp-tile in
+// 32-bit offsets relative to the warp-tile -- a warp-tile holds at most two hop boundaries (host check: bnd[s+2] - bnd[s] >= 1024)
+// -- instead of per chunk in 64-bit arithmetic, and the per-hop partial sums are reduced with float32 shuffles (fixed order:
+// bit-reproducible) before one fixed-point atomic per warp-tile and hop.  A lane's chunk is S = 64 samples (one warp scan per
+// 2048 samples; S = 32 for sample rates whose 100 ms hops are shorter than 1024 samples).
+struct LufsTab {                                 // per-lane scan table of the 4-state cascade in shared memory
+    float PlaneT[16][32];                        // Plane[lane][k] transposed: lane-contiguous, conflict free
 };
 // acc (rows 0,1 | rows 2,3) += M v
 __device__ __forceinline__ void mv4(const float2 (&M)[4][2], const float (&v)[4], float2& a01, float2& a23) {
@@ -63,77 +75,87 @@ __device__ __forceinline__ void mv4(const float2 (&M)[4][2], const float (&v)[4]
     }
 }
 
-constexpr int kLufsSmem = 2 * kL * (int)sizeof(float) + (int)sizeof(LufsTab);
+template <int S> struct LufsCfg {
+    static constexpr int kWT = 32 * S;             // samples per warp-tile
+    static constexpr int kSmem = kNW * 2 * kWT * (int)sizeof(float) + (int)sizeof(LufsTab);
+    static constexpr int kMinBlocks = S == 32 ? 6 : 3;
+};
 
-__global__ void __launch_bounds__(kT, 6) lufs_kernel(const __grid_constant__ LufsArgs P) {
-    // two float32 staging tiles: the NEXT tile lands (cp.async) while the current one is scanned.  Both passes read their
-    // samples from shared memory in rolled loops over float4 groups: the whole kernel stays small enough for the
-    // instruction cache (the fully unrolled register version spent 30 % of its issue slots waiting for instructions)
+template <int S>
+__global__ void __launch_bounds__(kT, LufsCfg<S>::kMinBlocks) lufs_kernel(const __grid_constant__ LufsArgs P) {
+    constexpr int kWT = LufsCfg<S>::kWT;
+    constexpr int kU = S / 4;                      // float4 groups per chunk; group u of lane l sits at vector l * kU + u
     extern __shared__ __align__(128) unsigned char lufs_smem[];
-    float* tiles = reinterpret_cast<float*>(lufs_smem);
-    LufsTab* tab = reinterpret_cast<LufsTab*>(lufs_smem + 2 * kL * sizeof(float));
-    __shared__ LufsScratch sh;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (int i = tid; i < 32 * 16; i += kT) tab->PlaneT[i % 16][i / 16] = (float)__ldg(P.tab + Tab<4>::Plane + i);
-    const int cbase = tid * 32, cx = (tid & 7) << 2;
+    float* slots = reinterpret_cast<float*>(lufs_smem) + (size_t)warp * 2 * kWT;      // this warp's two staging slots
+    LufsTab* tab = reinterpret_cast<LufsTab*>(lufs_smem + (size_t)kNW * 2 * kWT * sizeof(float));
+    for (int i = tid; i < 32 * 16; i += kT) tab->PlaneT[i % 16][i / 16] = (float)__ldg(P.plane + i);
+    __syncthreads();                                         // the only block barrier: the table is read-only from here on
+    float pl[16];                                            // this lane's Plane rows (A^(32 lane)): registers for the whole kernel
+#pragma unroll
+    for (int i = 0; i < 16; ++i) pl[i] = tab->PlaneT[i][lane];
+    // a chunk is kU consecutive 16-byte vectors; vector v of the warp-tile is stored at sw(v): the low three bits XORed with the
+    // chunk index (v / kU) & 7, so that eight neighbouring lanes walking their chunks, and eight neighbouring vectors of the
+    // coalesced copy, both touch eight different 16-byte bank groups
+    auto sw = [](int v) -> int { return (v & ~7) | ((v ^ (v >> (S == 64 ? 4 : 3))) & 7); };
     const int items = P.rows * P.nseg;
+    const int wstride = gridDim.x * kNW;
 #pragma unroll 1
-    for (int item = blockIdx.x; item < items; item += gridDim.x) {
+    for (int item = blockIdx.x * kNW + warp; item < items; item += wstride) {
         const int row = item % P.rows, seg = item / P.rows;
         const int t_live = seg * P.seglen;
         const int t_end = min(P.ntiles, t_live + P.seglen);
         const int t_first = max(0, t_live - P.whalo);
         const float* src = P.in + (size_t)row * (size_t)P.stride;
-        __syncthreads();
-        if (tid == 0) sh.carry[t_first & 1] = make_float4(0.f, 0.f, 0.f, 0.f);
         unsigned long long* dst = P.segsum + (size_t)row * (size_t)P.nhop;
         auto load_tile = [&](int t, int slot) {
-            float* tile_s = tiles + (size_t)slot * kL;
-            const long long lo = (long long)t * kL;
-            if (lo >= kLead && lo + kL <= kLead + P.n) {
-                const float* s4 = src + lo + 4 * tid;
-                float* d4 = tile_s + 4 * swz(tid);
+            float* tile_s = slots + (size_t)slot * kWT;
+            const long long lo = (long long)t * kWT;
+            if (lo >= kLead && lo + kWT <= kLead + P.n) {
+                const float* s4 = src + lo + 4 * lane;
 #pragma unroll
-                for (int r = 0; r < kTileVecs / kT; ++r) cp_async16(d4 + 4 * kT * r, s4 + 4 * kT * r);
+                for (int r = 0; r < kWT / 128; ++r) cp_async16(tile_s + 4 * sw(lane + 32 * r), s4 + 128 * r);
             } else {
 #pragma unroll 1
-                for (int r = 0; r < kTileVecs / kT; ++r) {
-                    const int v = tid + kT * r;
+                for (int r = 0; r < kWT / 128; ++r) {
+                    const int v = lane + 32 * r;
                     const long long q = lo + 4 * v;
                     float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
                     for (int c = 0; c < 4; ++c)
                         if (q + c >= kLead && q + c < kLead + P.n) setcomp4(val, c, src[q + c]);
-                    *reinterpret_cast<float4*>(tile_s + 4 * swz(v)) = val;
+                    *reinterpret_cast<float4*>(tile_s + 4 * sw(v)) = val;
                 }
             }
             cp_async_commit();
         };
+        float cin[4] = {0.f, 0.f, 0.f, 0.f};                 // state entering the next warp-tile (same in every lane)
+        __syncwarp();                                        // the previous item's last reads of slot 0 are done
         load_tile(t_first, 0);
 #pragma unroll 1
         for (int tile = t_first; tile < t_end; ++tile) {
             const bool live = tile >= t_live;
-            const long long tile_lo = (long long)tile * kL;
             const int slot = (tile - t_first) & 1;
             cp_async_wait<0>();
-            __syncthreads();                               // this tile's floats visible; everybody is done with the other slot
-            if (tile + 1 < t_end) load_tile(tile + 1, slot ^ 1);     // lands while this tile is scanned
-            const float* mine = tiles + (size_t)slot * kL + cbase;  // this thread's 32 samples: float4 group u at ((4 u) ^ cx)
+            __syncwarp();                                    // this warp-tile's floats visible; the other slot is free
+            if (tile + 1 < t_end) load_tile(tile + 1, slot ^ 1);     // lands while this warp-tile is scanned
+            const float* tile_s = slots + (size_t)slot * kWT;
+            auto group = [&](int u) -> float4 { return *reinterpret_cast<const float4*>(tile_s + 4 * sw(lane * kU + u)); };
 
-            // ---- pass 1 (packed float32): zero-state end state of the 4-state cascade over this chunk ----
+            // ---- pass 1 (packed float32): zero-state end state of the 4-state cascade over this lane's chunk ----
             float2 E01 = make_float2(0.f, 0.f), E23 = E01;
-#pragma unroll 2
-            for (int u = 0; u < kS / 4; ++u) {
-                const float4 xv = *reinterpret_cast<const float4*>(mine + ((4 * u) ^ cx));
+#pragma unroll
+            for (int u = 0; u < kU; ++u) {                       // fully unrolled: g[j] are immediate constant-bank operands
+                const float4 xv = group(u);
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
                     const float x = comp4(xv, c);
                     const float2 X = make_float2(x, x);
-                    E01 = ffma2(P.k.g[4 * u + c][0], X, E01);
-                    E23 = ffma2(P.k.g[4 * u + c][1], X, E23);
+                    E01 = ffma2(P.g[4 * u + c][0], X, E01);
+                    E23 = ffma2(P.g[4 * u + c][1], X, E23);
                 }
             }
-            // ---- warp scan, tile Horner, carry update (float32, packed) ----
+            // ---- warp scan (float32, packed): inclusive prefix of the chunk end states ----
 #pragma unroll
             for (int d = 0; d < 5; ++d) {
                 float pe[4];
@@ -144,128 +166,108 @@ __global__ void __launch_bounds__(kT, 6) lufs_kernel(const __grid_constant__ Luf
                 if (lane < (1 << d)) { pe[0] = 0.f; pe[1] = 0.f; pe[2] = 0.f; pe[3] = 0.f; }
                 mv4(P.Pw2[d], pe, E01, E23);
             }
-            if (lane == 31) sh.tot[warp] = make_float4(E01.x, E01.y, E23.x, E23.y);
-            __syncthreads();
-            float2 b01 = make_float2(0.f, 0.f), b23 = b01;        // state contributed by the warps before this one
-#pragma unroll
-            for (int v = 0; v < kNW - 1; ++v) {
-                if (v < warp) {
-                    const float4 t4 = sh.tot[v];
-                    const float bv[4] = {b01.x, b01.y, b23.x, b23.y};
-                    float2 n01 = make_float2(t4.x, t4.y), n23 = make_float2(t4.z, t4.w);
-                    mv4(P.Qw2[1], bv, n01, n23);
-                    b01 = n01; b23 = n23;
-                }
-            }
-            const float4 c4 = sh.carry[tile & 1];
-            const float cin[4] = {c4.x, c4.y, c4.z, c4.w};
-            if (tid == kT - 1) {
-                const float bv[4] = {b01.x, b01.y, b23.x, b23.y};
-                float2 a01 = E01, a23 = E23;
-                mv4(P.Qw2[1], bv, a01, a23);
-                mv4(P.Qw2[kNW], cin, a01, a23);
-                sh.carry[(tile + 1) & 1] = make_float4(a01.x, a01.y, a23.x, a23.y);
-            }
-            if (!live) continue;                           // halo: only the carried state was needed
-            mv4(P.Qw2[warp], cin, b01, b23);               // + the state entering the tile, carried to this warp
+            // state entering this lane's chunk = zero-state prefix of the lanes before it + A^(32 lane) * (state entering the tile)
             float z[4];
             {
                 const float u0 = __shfl_up_sync(0xffffffffu, E01.x, 1), u1 = __shfl_up_sync(0xffffffffu, E01.y, 1);
                 const float u2 = __shfl_up_sync(0xffffffffu, E23.x, 1), u3 = __shfl_up_sync(0xffffffffu, E23.y, 1);
                 z[0] = lane > 0 ? u0 : 0.f; z[1] = lane > 0 ? u1 : 0.f; z[2] = lane > 0 ? u2 : 0.f; z[3] = lane > 0 ? u3 : 0.f;
             }
-            const float bs[4] = {b01.x, b01.y, b23.x, b23.y};
+            // state leaving the warp-tile = lane 31's inclusive prefix + A^1024 * (state entering it)
+            float2 n01 = make_float2(__shfl_sync(0xffffffffu, E01.x, 31), __shfl_sync(0xffffffffu, E01.y, 31));
+            float2 n23 = make_float2(__shfl_sync(0xffffffffu, E23.x, 31), __shfl_sync(0xffffffffu, E23.y, 31));
+            mv4(P.Q1, cin, n01, n23);
+            if (live) {
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                float acc = z[i];
+                for (int i = 0; i < 4; ++i) {
+                    float acc = z[i];
 #pragma unroll
-                for (int k = 0; k < 4; ++k) acc = fmaf(tab->PlaneT[i * 4 + k][lane], bs[k], acc);
-                z[i] = acc;
+                    for (int k = 0; k < 4; ++k) acc = fmaf(pl[i * 4 + k], cin[k], acc);
+                    z[i] = acc;
+                }
             }
+            cin[0] = n01.x; cin[1] = n01.y; cin[2] = n23.x; cin[3] = n23.y;
+            if (!live) continue;                             // halo: only the carried state was needed
 
-            // ---- pass 2 (packed float32, the high-pass runs one sample behind the shelf) + squared sums per hop ----
-            const long long i0 = tile_lo + (long long)tid * kS - kLead;          // first sample index of this thread
-            const long long iw = tile_lo + (long long)(tid & ~31) * kS - kLead;   // first sample of this warp
-            const long long ig0 = i0 + P.goff, igw = iw + P.goff;                    // the same in hop coordinates
-            int sw = __ldg(P.tile_seg + tile);
-            while (sw < P.nhop && __ldg(P.bnd + sw + 1) <= igw) ++sw;
-            int s = sw;
-            while (s < P.nhop && __ldg(P.bnd + s + 1) <= ig0) ++s;
-            const long long kBig = 0x3fffffffffffffffLL;
-            const long long nb1 = (s < P.nhop) ? __ldg(P.bnd + s + 1) - P.goff : kBig;     // row-local hop ends
-            const long long nb2 = (s + 1 < P.nhop) ? __ldg(P.bnd + s + 2) - P.goff : kBig;
-            const bool whole = (i0 >= P.own_lo) && (i0 + kS <= P.own_hi) && (i0 + kS <= nb1);   // chunk inside the counted range and one hop
-            float2 S0 = make_float2(z[0], z[2]);
-            float2 S1 = make_float2(z[1], z[3]);
-            // the high-pass lane runs one sample behind the shelf lane: step 0 is the shelf alone, the last output comes
-            // from the high-pass state after the loop
-            float u_prev = 0.f;
-            float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f;
-            auto first_step = [&](float x0) {
-                const float u = fmaf(P.k.C[0].x, S0.x, fmaf(P.k.C[1].x, S1.x, P.k.D.x * x0));
-                const float n0 = fmaf(P.k.A[0][0].x, S0.x, fmaf(P.k.A[0][1].x, S1.x, P.k.B[0].x * x0));
-                const float n1 = fmaf(P.k.A[1][0].x, S0.x, fmaf(P.k.A[1][1].x, S1.x, P.k.B[1].x * x0));
-                S0.x = n0; S1.x = n1;
-                u_prev = u;
+            // ---- hop bookkeeping, once per warp-tile, in offsets relative to its first sample ----
+            const long long iw = (long long)tile * kWT - kLead;          // sample index of the warp-tile's first position
+            const long long igw = iw + P.goff;                            // the same in hop coordinates
+            int hs = __ldg(P.tile_seg + (int)(((long long)tile * kWT) / kL));   // hop of the enclosing 4096-tile's first sample
+            while (hs < P.nhop && __ldg(P.bnd + hs + 1) <= igw) ++hs;
+            const long long kFar = 1 << 20;
+            const int b1 = (int)min(kFar, max(0LL, (hs < P.nhop ? __ldg(P.bnd + hs + 1) : igw + kFar) - igw));      // first hop end, relative
+            const int b2 = (int)min(kFar, max(0LL, (hs + 1 < P.nhop ? __ldg(P.bnd + hs + 2) : igw + kFar) - igw));  // second hop end
+            const int lo_rel = (int)min(kFar, max(-kFar, P.own_lo - iw));      // counted range of the row, relative
+            const int hi_rel = (int)min(kFar, max(-kFar, P.own_hi - iw));
+            const bool fast = lo_rel <= 0 && hi_rel >= kWT && b1 >= kWT;       // whole warp-tile counted, one hop (warp-uniform)
+
+            // ---- pass 2 (scalar float32) + squared sums per hop ----
+            // Packing (x_j, shelf_{j-1}) into register pairs for FFMA2 costs more moves than the packed arithmetic saves (SASS: 26
+            // instructions per sample packed, 15 here).  The shelf (poles at radius ~0.9) runs as a float32 DF2T section -- 5
+            // operations -- from the scan's state mapped into DF2T coordinates; the 38 Hz high-pass (poles at 0.995) keeps its
+            // balanced realization (9 operations).  Every chunk restarts from the scan-resolved state, so round-off lives 32 samples.
+            float zs0 = fmaf(P.shT[0][0], z[0], P.shT[0][1] * z[1]), zs1 = fmaf(P.shT[1][0], z[0], P.shT[1][1] * z[1]);
+            float sb0 = P.hp_d[0] * z[2], sb1 = P.hp_d[1] * z[3];
+            auto kweight = [&](float x) -> float {
+                const float u = fmaf(P.sh_b[0], x, zs0);                                   // shelf, DF2T
+                zs0 = fmaf(P.sh_b[1], x, fmaf(P.sh_na[0], u, zs1));
+                zs1 = fmaf(P.sh_b[2], x, P.sh_na[1] * u);
+                const float y = fmaf(P.hpC[0], sb0, fmaf(P.hpC[1], sb1, P.hpD * u));       // high-pass, balanced states rescaled to B = (1, 1)
+                const float m0 = fmaf(P.hpA[0][0], sb0, fmaf(P.hpA[0][1], sb1, u));
+                const float m1 = fmaf(P.hpA[1][0], sb0, fmaf(P.hpA[1][1], sb1, u));
+                sb0 = m0; sb1 = m1;
+                return y;
             };
-            if (__all_sync(0xffffffffu, whole)) {
+            float a0 = 0.f, a1 = 0.f, a2 = 0.f;                // sums of this lane's squares in hops hs, hs + 1, hs + 2
+            if (fast) {
+                float acc1 = 0.f;
 #pragma unroll 2
-                for (int u = 0; u < kS / 4; ++u) {
-                    const float4 xv = *reinterpret_cast<const float4*>(mine + ((4 * u) ^ cx));
+                for (int u = 0; u < kU; ++u) {
+                    const float4 xv = group(u);
 #pragma unroll
                     for (int c = 0; c < 4; ++c) {
-                        if (c == 0 && u == 0) { first_step(xv.x); continue; }
-                        const float2 Y = pair_step(P.k, make_float2(comp4(xv, c), u_prev), S0, S1);   // Y.x = shelf(j), Y.y = K-weighted(j-1)
-                        u_prev = Y.x;
-                        if (c & 1) acc0 = fmaf(Y.y, Y.y, acc0); else acc1 = fmaf(Y.y, Y.y, acc1);
+                        const float y = kweight(comp4(xv, c));
+                        if (c & 1) a0 = fmaf(y, y, a0); else acc1 = fmaf(y, y, acc1);
                     }
                 }
-                const float yl = fmaf(P.k.C[0].y, S0.y, fmaf(P.k.C[1].y, S1.y, P.k.D.y * u_prev));
-                acc1 = fmaf(yl, yl, acc1);
-                acc0 += acc1; acc1 = 0.f;
+                a0 += acc1;
             } else {
-                // chunks cut by hop boundaries (at most two: the host plan guarantees it) or by the ends of the counted range:
-                // samples [jlo, j1) -> hop s, [j1, j2) -> hop s+1, [j2, jv) -> hop s+2; the rest is not counted
-                const int jv = (int)max(0LL, min((long long)kS, P.own_hi - i0));
-                const int jlo = (int)max(0LL, min((long long)kS, P.own_lo - i0));
-                const int j1 = (int)max(0LL, min((long long)jv, nb1 - i0));
-                const int j2 = (int)max((long long)j1, min((long long)jv, nb2 - i0));
-                auto count = [&](float yk, int js) {       // js: the sample this K-weighted output belongs to
-                    const float t = yk * yk;
-                    acc0 += (js >= jlo && js < j1) ? t : 0.f;
-                    acc1 += (js >= jlo && js >= j1 && js < j2) ? t : 0.f;
-                    acc2 += (js >= jlo && js >= j2 && js < jv) ? t : 0.f;
-                };
+                // this lane's samples [jlo, j1) belong to hop hs, [j1, j2) to hs + 1, [j2, jv) to hs + 2; the rest is not counted
+                const int j0 = S * lane;
+                const int jv = max(0, min(S, hi_rel - j0));
+                const int jlo = max(0, min(S, lo_rel - j0));
+                const int j1 = max(0, min(jv, b1 - j0));
+                const int j2 = max(j1, min(jv, b2 - j0));
 #pragma unroll 1
-                for (int u = 0; u < kS / 4; ++u) {
-                    const float4 xv = *reinterpret_cast<const float4*>(mine + ((4 * u) ^ cx));
+                for (int u = 0; u < kU; ++u) {
+                    const float4 xv = group(u);
 #pragma unroll
                     for (int c = 0; c < 4; ++c) {
-                        if (c == 0 && u == 0) { first_step(xv.x); continue; }
-                        const float2 Y = pair_step(P.k, make_float2(comp4(xv, c), u_prev), S0, S1);
-                        u_prev = Y.x;
-                        count(Y.y, 4 * u + c - 1);
+                        const float y = kweight(comp4(xv, c));
+                        const float t = y * y;
+                        const int js = 4 * u + c;
+                        a0 += (js >= jlo && js < j1) ? t : 0.f;
+                        a1 += (js >= jlo && js >= j1 && js < j2) ? t : 0.f;
+                        a2 += (js >= jlo && js >= j2 && js < jv) ? t : 0.f;
                     }
                 }
-                count(fmaf(P.k.C[0].y, S0.y, fmaf(P.k.C[1].y, S1.y, P.k.D.y * u_prev)), kS - 1);
             }
-            double accA = 0.0, accB = 0.0;
-            auto flush = [&](int hop, float v) {
-                if (v == 0.f) return;
-                if (hop == sw) accA += (double)v;
-                else if (hop == sw + 1) accB += (double)v;
-                else if (hop < P.nhop) atomicAdd(dst + hop, (unsigned long long)__double2ll_rn((double)v * kSqScale));
-            };
-            flush(s, acc0);
-            flush(s + 1, acc1);
-            flush(s + 2, acc2);
+            // ---- per-hop sums of the warp-tile: fixed-order float32 butterfly, one fixed-point atomic per hop ----
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) { accA += shfl_xor_d(accA, o); accB += shfl_xor_d(accB, o); }
+            for (int o = 16; o > 0; o >>= 1) a0 += __shfl_xor_sync(0xffffffffu, a0, o);
+            if (!fast) {
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) { a1 += __shfl_xor_sync(0xffffffffu, a1, o); a2 += __shfl_xor_sync(0xffffffffu, a2, o); }
+            }
             if (lane == 0) {
-                if (sw < P.nhop && accA != 0.0) atomicAdd(dst + sw, (unsigned long long)__double2ll_rn(accA * kSqScale));
-                if (sw + 1 < P.nhop && accB != 0.0) atomicAdd(dst + sw + 1, (unsigned long long)__double2ll_rn(accB * kSqScale));
+                if (hs < P.nhop && a0 != 0.f) atomicAdd(dst + hs, (unsigned long long)__double2ll_rn((double)a0 * kSqScale));
+                if (!fast) {
+                    if (hs + 1 < P.nhop && a1 != 0.f) atomicAdd(dst + hs + 1, (unsigned long long)__double2ll_rn((double)a1 * kSqScale));
+                    if (hs + 2 < P.nhop && a2 != 0.f) atomicAdd(dst + hs + 2, (unsigned long long)__double2ll_rn((double)a2 * kSqScale));
+                }
             }
         }
+        cp_async_wait<0>();
     }
 }
 

@@ -59,6 +59,12 @@ __global__ void row_stats_unpack_kernel(RowStats* st, int rows, const double* bu
     if (r < rows) { st[r].sum = buf[r]; st[r].mn = f2ord((float)-buf[rows + r]); st[r].mx = f2ord((float)buf[2 * rows + r]); }
 }
 
+// the tracks with an active imager re-track their output peak after the imager (peak_after_imager): zero those entries first
+__global__ void reset_imager_peaks_kernel(float* peak, const double* width, int tracks) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < tracks && width[t] != 1.0) peak[t] = 0.f;
+}
+
 __global__ void row_stats_init_kernel(RowStats* st, int rows) {
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r < rows) { st[r].sum = 0.0; st[r].mn = 0xffffffffu; st[r].mx = 0u; st[r].pad = 0; }
@@ -152,6 +158,7 @@ __global__ void __launch_bounds__(kPwThreads) pointwise_kernel(const PwArgs P) {
     if (P.sub) { sub0 = (float)P.sub[track * C]; sub1 = (float)P.sub[track * C + (C > 1)]; }
     if (P.mul) { mul0 = (float)P.mul[track * C]; mul1 = (float)P.mul[track * C + (C > 1)]; }
     const bool imager = (P.width != nullptr) && C == 2 && (P.force_imager || fabs(P.width[track] - 1.0) > 0.0);
+    if (P.mode == PW_PEAK && P.skip_unity && !imager) return;      // mixed batch: only the tracks with an active imager are re-scanned
     const double muld0 = (P.mode == PW_GAIN_F64 && P.mul) ? P.mul[track * C] : 1.0;
     const double muld1 = (P.mode == PW_GAIN_F64 && P.mul) ? P.mul[track * C + (C > 1)] : 1.0;
     const float wf = imager ? (float)P.width[track] : 1.f;

@@ -43,6 +43,7 @@ struct PwArgs {
     int clip;                   // clip to +-1 after the affine map
     const double* width;        // per track imager width (null = none)
     int force_imager;           // run the mid/side arithmetic even for width == 1 (standalone apply_stereo_imager)
+    int skip_unity;             // PW_PEAK over a mixed batch: CTAs of tracks whose width is 1 return at once
     DynParams dyn;              // maximizer / parallel constants
     double par_mix;             // PW_PARALLEL uniform mix
     int n_fade;                 // fade-in length (0 = none)

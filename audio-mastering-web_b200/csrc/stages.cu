@@ -6,7 +6,7 @@
 #include <cstring>
 
 #include "context.h"
-#include "sweep3.cuh"
+#include "sweep4.cuh"
 #include "lufs_kernel.cuh"
 #include "misc_kernels.cuh"
 #include "stages_internal.h"
@@ -16,11 +16,12 @@ namespace mm {
 // ---------------------------------------------------------------------------------------------------
 // launch helpers
 // ---------------------------------------------------------------------------------------------------
-static inline int tiles_fwd(long long n, int pad) { return (int)((kLead + n + pad - 1 + kL) / kL); }
+// warp-tiles (kWT samples) of a sweep
+static inline int tiles_fwd(long long n, int pad) { return (int)((kLead + n + pad - 1 + kWT) / kWT); }
 static inline int tiles_bwd(long long n, int pad) {
     const long long q_last = kLead + n + pad - 1, q_first = kLead - pad;
     const long long qend = (q_last + 4) & ~3LL;
-    return (int)((qend - q_first + kL - 1) / kL);
+    return (int)((qend - q_first + kWT - 1) / kWT);
 }
 
 template <int M> static void fill_filter(FiltK<M>& fk, const FilterPlan* p) {
@@ -54,56 +55,35 @@ static void choose_segments(int rows, int ntiles, int whalo, int capacity, int* 
     *seglen_out = (ntiles + best - 1) / best;
 }
 
-template <int M, int NF, int NIN, int DIR, int EPI, int NAUX, int ST, int NF32, int NSET = 1>
+template <int M, int NF, int NIN, int DIR, int EPI, int NAUX, int NF32>
 static int launch_sweep2(mm_ctx* c, SweepArgs<M, NF>* As, int whalo, const char* name) {
+    constexpr int ST = SweepStages<NF, NIN>::value;
     typedef Sweep2Cfg<M, NF, NIN, DIR, EPI, NAUX, ST> Cfg;
-    auto kern = sweep2_kernel<M, NF, NIN, DIR, EPI, NAUX, ST, NF32, NSET>;
+    auto kern = sweep2_kernel<M, NF, NIN, DIR, EPI, NAUX, ST, NF32, 1>;
     SweepArgs<M, NF>& A = As[0];
     const size_t smem = Cfg::kBytes;
     int blocks_per_sm = 0;
     {
         const bool first = c->occupancy.find((const void*)kern) == c->occupancy.end();
-        MM_TRY(kernel_setup(c, (const void*)kern, kT, smem, true, &blocks_per_sm));
-        if (first && getenv("MM_DEBUG")) fprintf(stderr, "[mm] %s (%d float32 sections): %zu B smem, %d CTAs/SM x %d SMs\n", name, NF32, smem, blocks_per_sm, c->num_sms);
+        MM_TRY(kernel_setup(c, (const void*)kern, Cfg::kThreads, smem, true, &blocks_per_sm));
+        if (first && getenv("MM_DEBUG")) fprintf(stderr, "[mm] %s (%d float32 sections, %d-stage ring): %zu B smem, %d CTAs x %d warps per SM x %d SMs\n", name, NF32, ST, smem, blocks_per_sm, Cfg::kSW, c->num_sms);
     }
-    const int num_sms = c->num_sms;
-    for (int k = 0; k < NSET; ++k) As[k].ntiles = DIR > 0 ? tiles_fwd(A.n, A.pad) : tiles_bwd(A.n, A.pad);
+    A.ntiles = DIR > 0 ? tiles_fwd(A.n, A.pad) : tiles_bwd(A.n, A.pad);
     if ((size_t)A.rows * (size_t)A.ntiles == 0) return 0;
-    const int capacity = std::max(1, num_sms * blocks_per_sm / NSET);      // work items in flight (NSET CTAs each)
-    Sweep2Args<M, NF, NSET> PP;
-    PP.whalo = whalo;
-    choose_segments(A.rows, A.ntiles, whalo, capacity, &PP.nseg, &PP.seglen);
+    constexpr int kSW = Cfg::kSW, kSweepThreads = Cfg::kThreads;
+    const int capacity = std::max(1, c->num_sms * blocks_per_sm * kSW);      // warps in flight = independent workers
+    Sweep2Args<M, NF, 1> PP;
+    PP.whalo = whalo * (kL / kWT);                   // the tables count look-back windows in 4096-sample tiles
+    choose_segments(A.rows, A.ntiles, PP.whalo, capacity, &PP.nseg, &PP.seglen);
     const long long items = (long long)A.rows * PP.nseg;
-    const unsigned grid = (unsigned)std::min<long long>(items, capacity) * NSET;
-    for (int k = 0; k < NSET; ++k) PP.a[k] = As[k];
-    PP.dbg = nullptr;
-    {
-        static int skip = -1;
-        if (skip < 0) { const char* e = getenv("MM_SKIP"); skip = e ? atoi(e) : 0; }
-        PP.skip = skip;
-    }
-    static long long* dbg_dev = nullptr;
-    const bool dbg = getenv("MM_PHASES") != nullptr;
-    if (dbg) {
-        if (!dbg_dev) MM_CUDA(cudaMalloc(&dbg_dev, 8 * sizeof(long long)));
-        MM_CUDA(cudaMemsetAsync(dbg_dev, 0, 8 * sizeof(long long), c->stream));
-        PP.dbg = dbg_dev;
-    }
+    const unsigned grid = (unsigned)std::min<long long>((items + kSW - 1) / kSW, capacity / kSW);
+    PP.a[0] = A;
     {
         KernelScope ks(c, name);
         ks.samples = (double)A.rows * (double)A.n;
-        kern<<<grid, kT, smem, c->stream>>>(PP);
+        kern<<<grid, kSweepThreads, smem, c->stream>>>(PP);
     }
     MM_CUDA(cudaGetLastError());
-    if (dbg) {
-        long long h[8];
-        MM_CUDA(cudaMemcpyAsync(h, dbg_dev, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
-        MM_CUDA(cudaStreamSynchronize(c->stream));
-        const int tiles = PP.seglen + whalo;
-        fprintf(stderr, "[phases] %-28s seg %d tiles(+%d halo) x%d items/cta~%lld | wait(A) %lld load+B %lld pass1 %lld scan %lld barC %lld horner+pass2 %lld barE %lld epilogue %lld (cycles per tile, CTA 0)\n",
-                name, PP.seglen, whalo, PP.nseg, (long long)((items + grid - 1) / grid), h[0] / tiles, h[1] / tiles, h[2] / tiles, h[3] / tiles, h[4] / tiles,
-                h[5] / tiles, h[6] / tiles, h[7] / tiles);
-    }
     return 0;
 }
 
@@ -162,6 +142,9 @@ static void fill_common(const mm_ctx* c, SweepArgs<M, NF>& A, const mm_geom* g, 
     A.exc_k = epi.exc_k;
     A.exc_mode = epi.exc_mode;
     A.peak = epi.peak;
+    A.w_row = epi.w_row;
+    A.exc_row = epi.exc_row;
+    A.peak_row = epi.peak_row;
 }
 
 // One sweep's sections put in launch order: the float32-pass-2 sections first (the kernel's NF32 counts a
@@ -211,25 +194,7 @@ template <int M, int NF, int NIN, int DIR, int EPI, int NAUX, int NF32>
 static int run_sweep(mm_ctx* c, const mm_geom* g, const Arranged& R, int nout, const Pro& pro, int pad, const char* name) {
     SweepArgs<M, NF> A;
     fill_common<M, NF>(c, A, g, R.plans, R.in, NIN, R.out, nout, pro, R.epi, pad);
-    return launch_sweep2<M, NF, NIN, DIR, EPI, NAUX, 1, NF32>(c, &A, halo_tiles(R.plans, NF), name);
-}
-
-// Four sections of one input (forward, EPI_STORE) as two sets of two: arranged sections (0, 2) and (1, 3), so that both
-// sets hold the same number of float32 sections (n32 / 2 each).
-template <int N32SET>
-static int run_fwd4_split(mm_ctx* c, const mm_geom* g, const Arranged& R, const Pro& pro, int pad, const char* name) {
-    SweepArgs<2, 2> A[2];
-    for (int k = 0; k < 2; ++k) {
-        Arranged S;
-        S.epi = R.epi;
-        for (int j = 0; j < 2; ++j) {
-            S.plans[j] = R.plans[k + 2 * j];
-            S.in[j] = R.in[0];
-            S.out[j] = R.out[k + 2 * j];
-        }
-        fill_common<2, 2>(c, A[k], g, S.plans, S.in, 1, S.out, 2, pro, S.epi, pad);
-    }
-    return launch_sweep2<2, 2, 1, +1, EPI_STORE, 0, 1, N32SET, 2>(c, A, halo_tiles(R.plans, 4), name);
+    return launch_sweep2<M, NF, NIN, DIR, EPI, NAUX, NF32>(c, &A, halo_tiles(R.plans, NF), name);
 }
 
 int sweep_fwd(mm_ctx* c, const mm_geom* g, int nf, int nin, const FilterPlan* const* plans, const float* const* in,
@@ -251,21 +216,6 @@ int sweep_fwd(mm_ctx* c, const mm_geom* g, int nf, int nin, const FilterPlan* co
     MM_FWD(2, 1, 1, 0) MM_FWD(2, 1, 1, 1)
     MM_FWD(2, 2, 1, 0) MM_FWD(2, 2, 1, 1) MM_FWD(2, 2, 1, 2)
     MM_FWD(2, 2, 2, 0) MM_FWD(2, 2, 2, 1) MM_FWD(2, 2, 2, 2)
-    if (m == 2 && nf == 4 && nin == 1 && getenv("MM_SPLIT4") && atoi(getenv("MM_SPLIT4")) == 2) {   // experiment: co-scheduled half-section CTAs, measured slower
-        if (R.n32 == 0) return run_fwd4_split<0>(c, g, R, pro, pad, "sweep_fwd_m2_f4_i1");
-        if (R.n32 == 2) return run_fwd4_split<1>(c, g, R, pro, pad, "sweep_fwd_m2_f4_i1");
-        if (R.n32 == 4) return run_fwd4_split<2>(c, g, R, pro, pad, "sweep_fwd_m2_f4_i1");
-    }
-    if (m == 2 && nf == 4 && nin == 1 && getenv("MM_SPLIT4") && atoi(getenv("MM_SPLIT4")) == 1) {
-        // two 2-section sweeps over the same input (6 streams instead of 5, but 6 CTAs per SM instead of 3)
-        const FilterPlan* pa[2] = {R.plans[0], R.plans[2]};
-        const FilterPlan* pb[2] = {R.plans[1], R.plans[3]};
-        float* oa[2] = {R.out[0], R.out[2]};
-        float* ob[2] = {R.out[1], R.out[3]};
-        const float* i1[1] = {R.in[0]};
-        MM_TRY(sweep_fwd(c, g, 2, 1, pa, i1, oa, pro, pad));
-        return sweep_fwd(c, g, 2, 1, pb, i1, ob, pro, pad);
-    }
     MM_FWD(2, 4, 1, 0) MM_FWD(2, 4, 1, 2) MM_FWD(2, 4, 1, 4)
     MM_FWD(4, 1, 1, 0)
 #undef MM_FWD
@@ -414,6 +364,12 @@ int run_pointwise(mm_ctx* c, const mm_geom* g, PwArgs& A, const char* name) {
     KernelScope ks(c, name);
     ks.samples = (double)g->n * g->tracks * g->channels;
     pointwise_kernel<<<grid, kPwThreads, 0, c->stream>>>(A);
+    MM_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int reset_imager_peaks(mm_ctx* c, float* peak, const double* width, int tracks) {
+    reset_imager_peaks_kernel<<<(tracks + 127) / 128, 128, 0, c->stream>>>(peak, width, tracks);
     MM_CUDA(cudaGetLastError());
     return 0;
 }
@@ -714,42 +670,70 @@ int st_lufs(mm_ctx* c, const mm_geom* g, const float* in, const Pro& pro, double
         const KwPlan* kw = get_kw_plan(c, g->sr);
         if (!kw) return 1;
         MM_CUDA(cudaMemsetAsync(segsum, 0, (size_t)rows * lp->nseg * sizeof(unsigned long long), c->stream));
+        const int S = lp->min_span2 >= 2048 ? 64 : 32;            // samples per lane and warp scan (64 unless the hops are too short)
+        const ScanTables& tb = S == 64 ? kw->tabs64 : kw->tabs;
+        const int wt = 32 * S;                                      // samples per warp-tile
+        auto kern = S == 64 ? lufs_kernel<64> : lufs_kernel<32>;
+        const int smem = S == 64 ? LufsCfg<64>::kSmem : LufsCfg<32>::kSmem;
         int bps = 0;
-        MM_TRY(kernel_setup(c, (const void*)lufs_kernel, kT, kLufsSmem, true, &bps));
+        MM_TRY(kernel_setup(c, (const void*)kern, kT, smem, true, &bps));
         const int capacity = std::max(1, bps) * c->num_sms;
         LufsArgs A;
         memset(&A, 0, sizeof(A));
-        for (int i = 0; i < 2; ++i) {
-            for (int k = 0; k < 2; ++k) A.k.A[i][k] = make_float2((float)kw->sec[0].A[i * 2 + k], (float)kw->sec[1].A[i * 2 + k]);
-            A.k.B[i] = make_float2((float)kw->sec[0].B[i], (float)kw->sec[1].B[i]);
-            A.k.C[i] = make_float2((float)kw->sec[0].C[i], (float)kw->sec[1].C[i]);
-        }
-        A.k.D = make_float2((float)kw->sec[0].D, (float)kw->sec[1].D);
-        for (int j = 0; j < kS; ++j) {
-            A.k.g[j][0] = make_float2((float)kw->tabs.g[(size_t)j * 4 + 0], (float)kw->tabs.g[(size_t)j * 4 + 1]);
-            A.k.g[j][1] = make_float2((float)kw->tabs.g[(size_t)j * 4 + 2], (float)kw->tabs.g[(size_t)j * 4 + 3]);
+        for (int j = 0; j < S; ++j) {
+            A.g[j][0] = make_float2((float)tb.g[(size_t)j * 4 + 0], (float)tb.g[(size_t)j * 4 + 1]);
+            A.g[j][1] = make_float2((float)tb.g[(size_t)j * 4 + 2], (float)tb.g[(size_t)j * 4 + 3]);
         }
         for (int k = 0; k < 4; ++k)
             for (int h = 0; h < 2; ++h) {
                 for (int d = 0; d < 5; ++d)
-                    A.Pw2[d][k][h] = make_float2((float)kw->tabs.Pw[(size_t)d * 16 + (2 * h) * 4 + k], (float)kw->tabs.Pw[(size_t)d * 16 + (2 * h + 1) * 4 + k]);
-                for (int w = 0; w <= kNW; ++w)
-                    A.Qw2[w][k][h] = make_float2((float)kw->tabs.Qpow[(size_t)w * 16 + (2 * h) * 4 + k], (float)kw->tabs.Qpow[(size_t)w * 16 + (2 * h + 1) * 4 + k]);
+                    A.Pw2[d][k][h] = make_float2((float)tb.Pw[(size_t)d * 16 + (2 * h) * 4 + k], (float)tb.Pw[(size_t)d * 16 + (2 * h + 1) * 4 + k]);
+                A.Q1[k][h] = make_float2((float)tb.Qpow[(size_t)16 + (2 * h) * 4 + k], (float)tb.Qpow[(size_t)16 + (2 * h + 1) * 4 + k]);
             }
-        A.tab = kw->dev;
-        A.in = in; A.n = g->n; A.stride = g->stride; A.rows = rows; A.ntiles = lp->ntiles; A.channels = g->channels;
+        {
+            // shelf in DF2T coordinates: z = T s with T = O_d^-1 O_b (observability matrices of the DF2T and the balanced realization)
+            const Ba sh = k_weighting_stage(0, (double)g->sr);
+            const double* Ab = kw->sec[0].A;
+            const double* Cb = kw->sec[0].C;
+            const double a1 = sh.a[1], a2 = sh.a[2];
+            const double ob[2][2] = {{Cb[0], Cb[1]}, {Cb[0] * Ab[0] + Cb[1] * Ab[2], Cb[0] * Ab[1] + Cb[1] * Ab[3]}};     // [C; C A]
+            for (int j = 0; j < 2; ++j) {
+                A.shT[0][j] = (float)ob[0][j];                       // O_d^-1 = [[1, 0], [a1, 1]]
+                A.shT[1][j] = (float)(a1 * ob[0][j] + ob[1][j]);
+            }
+            for (int i = 0; i < 3; ++i) A.sh_b[i] = (float)sh.b[i];
+            A.sh_na[0] = (float)-a1;
+            A.sh_na[1] = (float)-a2;
+            // high-pass: balanced states rescaled by d_i = 1 / B_i, so that B' = (1, 1): A'_ij = d_i A_ij / d_j, C'_j = C_j / d_j
+            const double* Ah = kw->sec[1].A;
+            const double* Bh = kw->sec[1].B;
+            const double* Ch = kw->sec[1].C;
+            if (std::fabs(Bh[0]) < 1e-12 || std::fabs(Bh[1]) < 1e-12) { set_error("K-weighting at %d Hz: degenerate high-pass realization", g->sr); return 1; }
+            const double d[2] = {1.0 / Bh[0], 1.0 / Bh[1]};
+            for (int i = 0; i < 2; ++i) {
+                for (int j = 0; j < 2; ++j) A.hpA[i][j] = (float)(d[i] * Ah[i * 2 + j] / d[j]);
+                A.hpC[i] = (float)(Ch[i] / d[i]);
+                A.hp_d[i] = (float)d[i];
+            }
+            A.hpD = (float)kw->sec[1].D;
+        }
+        A.plane = S == 64 ? kw->plane64 : kw->dev + Tab<4>::Plane;
+        A.in = in; A.n = g->n; A.stride = g->stride; A.rows = rows; A.channels = g->channels;
+        A.ntiles = (int)((kLead + g->n + wt - 1) / wt);             // warp-tiles (the plan counts 4096-sample tiles)
         A.pro_mode = pro.mode; A.pro_sub = pro.sub; A.pro_mul = pro.mul;
         A.bnd = lp->bnd; A.nhop = lp->nseg; A.tile_seg = lp->tile_seg; A.segsum = segsum;
         A.goff = sl ? sl->global_off : 0;
         A.own_lo = sl ? sl->own_lo : 0;
         A.own_hi = sl ? sl->own_hi : g->n;
-        A.whalo = kw->tabs.W;
-        choose_segments(rows, lp->ntiles, A.whalo, capacity, &A.nseg, &A.seglen);
+        A.whalo = tb.W * (S * kT / wt);                            // the tables count tiles of S * kT samples
+        // every warp is an independent worker: capacity and segments are counted in warps / warp-tiles
+        choose_segments(rows, A.ntiles, A.whalo, capacity * kNW, &A.nseg, &A.seglen);
         const long long items = (long long)rows * A.nseg;
-        const unsigned grid = (unsigned)std::min<long long>(items, capacity);
+        const unsigned grid = (unsigned)std::min<long long>((items + kNW - 1) / kNW, capacity);
         {
             KernelScope ks(c, "lufs_kweight_blocks");
-            lufs_kernel<<<grid, kT, kLufsSmem, c->stream>>>(A);
+            ks.samples = (double)rows * (double)g->n;
+            kern<<<grid, kT, smem, c->stream>>>(A);
         }
         MM_CUDA(cudaGetLastError());
     }

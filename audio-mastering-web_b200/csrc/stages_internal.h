@@ -26,6 +26,10 @@ struct Epi {                     // epilogue of a backward sweep
     int exc_mode = 0;
     float* peak = nullptr;
     int clip = 0;                // clip the recombined output to +-1 (apply_high_freq_trim)
+    // mixed-preset batches: per-row overrides (device arrays indexed by batch row; see SweepArgs)
+    const double* w_row = nullptr;
+    const double* exc_row = nullptr;
+    const unsigned char* peak_row = nullptr;
 };
 
 struct Bufs { float* E[4]; float* T[5]; };
@@ -48,6 +52,7 @@ int run_in_scalars(mm_ctx* c, const mm_geom* g, const RowStats* st, int use_dc, 
                    double* sub, double* mul, double* peak_track, double* mean_row);
 int run_pointwise(mm_ctx* c, const mm_geom* g, PwArgs& A, const char* name);
 int run_out_scalars(mm_ctx* c, const OutScalarArgs& O);
+int reset_imager_peaks(mm_ctx* c, float* peak, const double* width, int tracks);
 struct FinalArgs;
 int run_finalize(mm_ctx* c, const mm_geom* g, const float* in, float* out, const double* mul, const double* width, int n_fade,
                  int16_t* pcm, const float* noise, unsigned long long seed, double* nonfinite);

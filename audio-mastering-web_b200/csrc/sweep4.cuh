@@ -1,41 +1,66 @@
-// Persistent, software-pipelined zero-phase / causal IIR sweep kernel ("kernel (1)" of the north star).
+// Persistent, software-pipelined zero-phase / causal IIR sweep kernel ("kernel (1)" of the north star), round 2: every WARP is
+// an autonomous worker.
 //
-// A row is cut into SEGMENTS of `seglen` tiles (kL = 4096 samples each, in sweep order).  One CTA owns
-// one segment at a time and walks its tiles in order, so the state entering a tile is simply the state
-// that left the previous one (kept in shared memory): no flags, no spinning, no inter-CTA traffic.
-// The state entering a segment is rebuilt from a HALO: the `whalo` tiles before the segment are read
+// A row is cut into SEGMENTS of `seglen` warp-tiles (kWT = 1024 samples each, in sweep order: 32 lanes x 32 consecutive
+// samples).  One warp owns one segment at a time and walks its warp-tiles in order, so the state entering a warp-tile is simply
+// the state that left the previous one (kept in the warp's slice of shared memory): no flags, no spinning, no inter-warp
+// traffic, and -- new in round 2 -- no block barrier anywhere in the tile loop.  Round 1 ran 128-thread CTAs over 4096-sample
+// tiles with four __syncthreads per tile and a single-stage input ring: every CTA exposed the full DRAM latency of its next
+// tile's input once per tile, all four warps sat in the same phase, and the 4-section sweeps reached 0.36 issue slots per cycle
+// at 12 warps per SM (ncu, profiles/r01_ncu_full_fwd_f4_dynamics.md).  Now a warp double-buffers its own 4 KB input slots
+// (cp.async for tile t + 1 is in flight while tile t is scanned), warps drift apart freely, and loads, arithmetic and stores of
+// different warps overlap on their own.
+// The state entering a segment is rebuilt from a HALO: the `whalo` warp-tiles before the segment are read
 // once more and only their zero-state end states are formed (pass 1) and chained,
-//       s <- A^kL s + aggregate(tile),
-// which after whalo tiles differs from the true state by A^(kL*whalo) times the unknown older state --
-// whalo is chosen on the host so that every entry of that matrix is below 1e-13 (the filters are
-// stable: 1..3 tiles for most sections, more for the lowest cut-offs at high sample rates).
+//       s <- A^kWT s + aggregate(tile),
+// which after the halo differs from the true state by A^(kWT*whalo) times the unknown older state --
+// whalo is chosen on the host so that every entry of that matrix is below 1e-18 (the filters are
+// stable: 4..12 warp-tiles for most sections, more for the lowest cut-offs at high sample rates).
 //
-// Per tile:
-//   cp.async ring (ST stages)   : the NIN input streams of the NEXT tile land in shared memory while the
-//                                  current tile is being scanned; the x-domain aux streams an epilogue needs
-//                                  are fetched asynchronously at tile start and waited for only before use
-//   pass 1   (per thread)        : zero-state end state of its 32 samples, E = sum_j g[j] x_j   (2 DFMA/sample)
-//   warp scan / tile Horner      : 2x2 (4x4) state-transfer powers composed with warp shuffles, tables in smem
-//   pass 2   (per thread)        : the DF2T recurrence from the resolved state, float32 results into smem
+// Per warp-tile:
+//   cp.async ring (ST stages)   : the NIN input streams of the NEXT warp-tile land in shared memory while the
+//                                  current one is being scanned; the x-domain aux streams an epilogue needs
+//                                  are prefetched into L2 at tile start and read in the store phase
+//   pass 1   (per lane)          : zero-state end state of its 32 samples, E = sum_j g[j] x_j   (2 DFMA/sample)
+//   warp scan                    : 2x2 (4x4) state-transfer powers composed with warp shuffles, tables in smem
+//   pass 2   (per lane)          : the DF2T recurrence from the resolved state, float32 results into smem
 //   epilogue                     : coalesced float4 stores / recombination / dynamics / exciter, peak tracking
 //
-// Shared-memory tiles are stored as 1024 16-byte vectors with the 128-byte XOR swizzle
+// Shared-memory warp-tiles are stored as 256 16-byte vectors with the 128-byte XOR swizzle
 //   phys(chunk, u) = chunk * 8 + (u ^ (chunk & 7))
-// so that both access patterns are bank-conflict free: the coalesced one (8 consecutive threads touch one
-// chunk) and the scan one (thread t walks chunk t).
+// so that both access patterns are bank-conflict free: the coalesced one (8 consecutive lanes touch one
+// chunk) and the scan one (lane l walks chunk l).
 #pragma once
 #include "pointwise.cuh"
 #include "common.cuh"
 
 namespace mm {
 
-constexpr int kTileVecs = kL / 4;  // float4 per stream tile
+constexpr int kWT = 1024;            // samples per warp-tile (32 lanes x kS)
+// Warps per sweep CTA.  The warps of a CTA share nothing but the read-only scan tables, so the CTA size only sets the granularity
+// at which an SM's 228 KB of shared memory is handed out: the count that fits the most warps on an SM wins (ties: the smaller
+// CTA).  `slice` = bytes of one warp's tiles, `tables` = bytes of the CTA's scan tables; 1.25 KB per CTA is reserved / static.
+constexpr int sweep_warps_on_sm(int k, size_t slice, size_t tables) {
+    const size_t cta = (size_t)k * slice + tables + 1280;
+    if (cta > 232448) return 0;
+    const int ctas = (int)(232448 / cta) > 32 ? 32 : (int)(232448 / cta);
+    return k * ctas > 16 ? 16 : k * ctas;      // beyond ~16 warps the register file (90 to 200 registers per thread) is the limit anyway
+}
+// the smallest CTA that reaches the best warp count
+constexpr int sweep_warps_per_cta(size_t slice, size_t tables) {
+    int best_warps = 0;
+    for (int k = 1; k <= 12; ++k) { const int w = sweep_warps_on_sm(k, slice, tables); if (w > best_warps) best_warps = w; }
+    for (int k = 1; k <= 12; ++k) if (sweep_warps_on_sm(k, slice, tables) >= best_warps) return k;
+    return 1;
+}
+
+constexpr int kTileVecs = kWT / 4;  // float4 per stream warp-tile
+constexpr int kVecsPerLane = kTileVecs / 32;
 
 // float -> double widening.  Measured on B200 (tools/microbench.cu): F2F runs at ~15 lanes/clk/SM, an
 // integer-pipe emulation (shift/add/select, 6-7 instructions) is slower at saturation and costs issue
 // slots this kernel does not have, so the conversion unit it is.
 __device__ __forceinline__ double f2d_bits(float x) { return (double)x; }
-
 
 template <int M> struct SmemTab {
     double Pw[5][M * M];
@@ -62,38 +87,40 @@ template <int M> __device__ __forceinline__ void matvec_acc_s(const double* p, c
     }
 }
 
-// NSET > 1: the sections of one sweep are dealt out to NSET CTAs per tile range (a[0], a[1], ... differ only in their
-// sections and output streams).  CTA b serves set b % NSET, so the CTAs that share an input tile run side by side
-// and the second read of it hits L2; each CTA stages only its own NF outputs in shared memory.
 template <int M, int NF, int NSET = 1> struct Sweep2Args {
-    SweepArgs<M, NF> a[NSET];
-    int seglen;           // live tiles per segment
+    SweepArgs<M, NF> a[NSET];   // NSET is always 1 (the split-section experiment of round 1 is gone)
+    int seglen;           // live warp-tiles per segment
     int nseg;             // segments per row
-    int whalo;            // halo tiles read before a segment (max over the sweep's sections)
-    long long* dbg;       // phase clocks of CTA 0 / thread 0 (tuning; null in production)
-    int skip;             // tuning only (MM_SKIP): 1 no global stores, 2 no interior loads, 4 no pass 2, 8 no warp scan
+    int whalo;            // halo warp-tiles read before a segment (max over the sweep's sections)
 };
 
 template <int M, int NF, int NIN, int DIR, int EPI, int NAUX, int ST>
 struct Sweep2Cfg {
     static constexpr int kExtra = NF > NIN ? NF - NIN : 0;
-    static constexpr size_t kTileBytes = (size_t)kL * sizeof(float);
-    static constexpr size_t kRing = (size_t)ST * NIN * kTileBytes;
-    static constexpr size_t kExtraOff = kRing;
-    static constexpr size_t kAuxOff = kExtraOff + kExtra * kTileBytes;
-    static constexpr size_t kTabOff = kAuxOff;          // the x-domain aux streams of an epilogue are read straight from
+    static constexpr size_t kTileBytes = (size_t)kWT * sizeof(float);
+    // per warp: ST input slots of NIN streams, then the staging tiles of the outputs that do not fit the input slots
+    static constexpr size_t kWarpBytes = ((size_t)ST * NIN + kExtra) * kTileBytes;
+    static constexpr size_t kExtraOff = (size_t)ST * NIN * kTileBytes;     // inside a warp's slice
+    static constexpr int kSW = sweep_warps_per_cta(kWarpBytes, NF * sizeof(SmemTab<M>));   // warps per CTA
+    static constexpr int kThreads = 32 * kSW;
+    static constexpr size_t kTabOff = kSW * kWarpBytes;  // the x-domain aux streams of an epilogue are read straight from
                                                          // global memory in the (coalesced) store phase: no smem tiles
     static constexpr size_t kBytes = kTabOff + NF * sizeof(SmemTab<M>);
-    // CTAs per SM the shared-memory footprint allows (227 KB usable): the register allocator is held to it
+    // CTAs (of kSW warps) per SM the shared-memory footprint allows (227 KB usable): the register allocator is held to it
     static constexpr int kFit = (int)((227u * 1024u) / (kBytes + 1024u));
-    // the dynamics epilogues (four band chains + maximizer per sample) need ~128 registers: 4 CTAs/SM beat 6 with spills
-    static constexpr int kCap = (EPI == EPI_DYNAMICS || EPI == EPI_DYNAMICS_GEN) ? 4 : 6;
+    // the dynamics epilogues (four band chains + maximizer per sample) need ~128 registers: 16 warps/SM beat 24 with spills
+    static constexpr int kCapW = ((EPI == EPI_DYNAMICS || EPI == EPI_DYNAMICS_GEN) ? 16 : 24) / kSW;
+    static constexpr int kCap = kCapW < 1 ? 1 : kCapW;
     static constexpr int kMinBlocks = kFit < 1 ? 1 : (kFit > kCap ? kCap : kFit);
 };
+// input ring depth per instantiation: double-buffered while a warp's slice stays within 20 KB (11+ warps per SM by shared memory)
+template <int NF, int NIN> struct SweepStages {
+    static constexpr int kExtra = NF > NIN ? NF - NIN : 0;
+    static constexpr int value = (2 * NIN + kExtra) * 4 <= 32 ? 2 : 1;
+};
 
-template <int M, int NF> struct Scratch2 {
-    double tot[NF][kNW][M];
-    double carry[2][NF][M];      // state entering tile t lives in carry[t & 1]
+template <int M, int NF, int SW> struct Scratch2 {
+    double carry[SW][2][NF][M];      // per warp: the state entering warp-tile t lives in carry[warp][t & 1]
 };
 
 // prologue helpers (see common.cuh PRO_*)
@@ -106,25 +133,26 @@ __device__ __forceinline__ float pro1(int mode, float x, float subf, float mulf,
 // NF32: the first NF32 sections run pass 2 in float32 on their balanced realization (tables and g in those
 // coordinates), the others in float64 DF2T.  Pass 1 and the scan are float64 for both.
 template <int M, int NF, int NIN, int DIR, int EPI, int NAUX, int ST, int NF32, int NSET = 1>
-__global__ void __launch_bounds__(kT, Sweep2Cfg<M, NF, NIN, DIR, EPI, NAUX, ST>::kMinBlocks) sweep2_kernel(const __grid_constant__ Sweep2Args<M, NF, NSET> PP) {
+__global__ void __launch_bounds__(Sweep2Cfg<M, NF, NIN, DIR, EPI, NAUX, ST>::kThreads, Sweep2Cfg<M, NF, NIN, DIR, EPI, NAUX, ST>::kMinBlocks) sweep2_kernel(const __grid_constant__ Sweep2Args<M, NF, NSET> PP) {
     typedef Sweep2Cfg<M, NF, NIN, DIR, EPI, NAUX, ST> Cfg;
-    const SweepArgs<M, NF>& P = PP.a[NSET > 1 ? (blockIdx.x % NSET) : 0];
+    constexpr int kSW = Cfg::kSW, kSweepThreads = Cfg::kThreads;
+    const SweepArgs<M, NF>& P = PP.a[0];
     extern __shared__ __align__(128) unsigned char smraw[];
-    float* ring = reinterpret_cast<float*>(smraw);
-    float* extra = reinterpret_cast<float*>(smraw + Cfg::kExtraOff);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    float* ring = reinterpret_cast<float*>(smraw + (size_t)warp * Cfg::kWarpBytes);            // this warp's input slots
+    float* extra = reinterpret_cast<float*>(smraw + (size_t)warp * Cfg::kWarpBytes + Cfg::kExtraOff);
     SmemTab<M>* tab = reinterpret_cast<SmemTab<M>*>(smraw + Cfg::kTabOff);
-    __shared__ Scratch2<M, NF> sh;
+    __shared__ Scratch2<M, NF, kSW> sh;
     constexpr int MM = M * M;
 
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-
-    // ---- one-time: scan tables into shared memory -------------------------------------------------
+    // ---- one-time: scan tables into shared memory (shared by the CTA's warps, read-only afterwards) ----
 #pragma unroll 1
     for (int f = 0; f < NF; ++f) {
         const double* g = P.tab[f];
         double* d = reinterpret_cast<double*>(&tab[f]);
-        for (int i = tid; i < (5 + 32 + kNW + 1) * MM; i += kT) d[i] = __ldg(g + i);   // Pw, Plane, Qpow are contiguous
+        for (int i = tid; i < (5 + 32 + kNW + 1) * MM; i += kSweepThreads) d[i] = __ldg(g + i);   // Pw, Plane, Qpow are contiguous
     }
+    __syncthreads();                                        // the only block barrier of the kernel
 
     const long long q_first = kLead - P.pad;
     const long long q_last = kLead + P.n + P.pad - 1;
@@ -135,27 +163,25 @@ __global__ void __launch_bounds__(kT, Sweep2Cfg<M, NF, NIN, DIR, EPI, NAUX, ST>:
     const long long st_hi = (DIR > 0) ? q_last : (long long)(kLead + P.n - 1);
 
     auto tile_origin = [&](int tile) -> long long {
-        return (DIR > 0) ? (long long)tile * kL : qend - (long long)(tile + 1) * kL;
+        return (DIR > 0) ? (long long)tile * kWT : qend - (long long)(tile + 1) * kWT;
     };
     // can the tile's inputs be fetched with unconditional 16-byte async copies?
     auto fast_in = [&](long long lo) -> bool {
-        return (DIR > 0) ? (lo >= kLead && lo + kL <= kLead + P.n) : (lo >= q_first && lo + kL - 1 <= q_last);
+        return (DIR > 0) ? (lo >= kLead && lo + kWT <= kLead + P.n) : (lo >= q_first && lo + kWT - 1 <= q_last);
     };
-    auto fast_out = [&](long long lo) -> bool { return lo >= st_lo && lo + kL - 1 <= st_hi; };
+    auto fast_out = [&](long long lo) -> bool { return lo >= st_lo && lo + kWT - 1 <= st_hi; };
 
     // ---- loaders ------------------------------------------------------------------------------------
     auto issue_inputs = [&](int row, int tile, int slot) {
         const long long lo = tile_origin(tile);
         const size_t rowoff = (size_t)row * (size_t)P.stride;
         if (fast_in(lo)) {
-            if (PP.skip & 2) return;
 #pragma unroll
             for (int s = 0; s < NIN; ++s) {
-                // swz(tid + kT r) = swz(tid) + kT r (kT is a multiple of 8): base + immediate addressing
-                const float* src = P.in[s] + rowoff + lo + 4 * tid;
-                float* dst = ring + ((size_t)slot * NIN + s) * kL + 4 * swz(tid);
+                const float* src = P.in[s] + rowoff + lo + 4 * lane;
+                float* dst = ring + ((size_t)slot * NIN + s) * kWT;
 #pragma unroll
-                for (int r = 0; r < kTileVecs / kT; ++r) cp_async16(dst + 4 * kT * r, src + 4 * kT * r);
+                for (int r = 0; r < kVecsPerLane; ++r) cp_async16(dst + 4 * swz(lane + 32 * r), src + 128 * r);
             }
         } else {
             // edge tile: synchronous, with prologue, scipy's odd extension and dead zeros applied here
@@ -168,10 +194,10 @@ __global__ void __launch_bounds__(kT, Sweep2Cfg<M, NF, NIN, DIR, EPI, NAUX, ST>:
 #pragma unroll 1
             for (int s = 0; s < NIN; ++s) {
                 const float* src = P.in[s] + rowoff;
-                float* dst = ring + ((size_t)slot * NIN + s) * kL;
+                float* dst = ring + ((size_t)slot * NIN + s) * kWT;
 #pragma unroll 1
-                for (int r = 0; r < kTileVecs / kT; ++r) {
-                    const int v = tid + kT * r;
+                for (int r = 0; r < kVecsPerLane; ++r) {
+                    const int v = lane + 32 * r;
                     const long long q = lo + 4 * v;
                     float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
                     if (q + 3 >= q_first && q <= q_last) {
@@ -202,23 +228,25 @@ __global__ void __launch_bounds__(kT, Sweep2Cfg<M, NF, NIN, DIR, EPI, NAUX, ST>:
             }
         }
     };
-    long long t_ph[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    long long t_last = 0;
-    const bool dbg_on = PP.dbg != nullptr && blockIdx.x == 0 && tid == 0;
-#define MM_TICK(k) do { if (dbg_on) { const long long _t = clock64(); t_ph[k] += _t - t_last; t_last = _t; } } while (0)
-    if (dbg_on) t_last = clock64();
-    // ---- segment loop --------------------------------------------------------------------------------
+    // ---- segment loop: every warp is its own worker ------------------------------------------------------
     const int items = P.rows * PP.nseg;
 #pragma unroll 1
-    for (int item = blockIdx.x / NSET; item < items; item += gridDim.x / NSET) {
+    for (int item = blockIdx.x * kSW + warp; item < items; item += gridDim.x * kSW) {
     const int row = P.row_map ? __ldg(P.row_map + item % P.rows) : item % P.rows;
     const int seg = item / P.rows;
     const int t_live = seg * PP.seglen;
     const int t_end = min(P.ntiles, t_live + PP.seglen);
     const int t_first = max(0, t_live - PP.whalo);
     const size_t rowoff = (size_t)row * (size_t)P.stride;
-    __syncthreads();                                   // previous item completely done (smem, carry)
-    if (tid < NF * M) sh.carry[t_first & 1][tid / M][tid % M] = 0.0;
+    // per-row parameters of a mixed-preset batch (one launch per stage over the rows whose style fires it)
+    double w0d = P.w[0], excg = P.exc_gain;
+    float w0f = P.w32[0];
+    bool pk_on = P.peak != nullptr;
+    if (EPI == EPI_COMBINE && NF == 1 && P.w_row) { w0d = __ldg(P.w_row + row); w0f = (float)w0d; }
+    if (EPI == EPI_EXCITER && P.exc_row) excg = __ldg(P.exc_row + row);
+    if (EPI != EPI_STORE && pk_on && P.peak_row) pk_on = P.peak_row[row] != 0;
+    __syncwarp();                                      // the previous item is completely done (this warp's smem, carry)
+    if (lane < NF * M) sh.carry[warp][t_first & 1][lane / M][lane % M] = 0.0;
     int slot = 0;
     issue_inputs(row, t_first, 0);
     cp_async_commit();
@@ -226,35 +254,33 @@ __global__ void __launch_bounds__(kT, Sweep2Cfg<M, NF, NIN, DIR, EPI, NAUX, ST>:
 #pragma unroll 1
     for (int tile = t_first; tile < t_end; ++tile) {
         const bool live = tile >= t_live;
-        __syncthreads();                               // (A) previous tile fully stored; carry visible
-        MM_TICK(0);
         const long long tile_lo = tile_origin(tile);
-        if (EPI != EPI_STORE && live && (tid & 7) == 0) {
-            // the store phase will read this tile's aux samples: pull their lines into L2 now (one request per 128 bytes)
-#pragma unroll
-            for (int s = 0; s < NAUX; ++s) {
-                const float* ap = P.aux[s] + rowoff + tile_lo + 4 * tid;
-#pragma unroll
-                for (int r = 0; r < kTileVecs / kT; ++r)
-                    asm volatile("prefetch.global.L2 [%0];" ::"l"(ap + 4 * kT * r));
-            }
-        }
         if (ST > 1) {
+            __syncwarp();                              // every lane is done with the other slot (stored from it last tile)
             if (tile + 1 < t_end) issue_inputs(row, tile + 1, slot ^ 1);
             cp_async_commit();                         // group: inputs(tile + 1)
-            cp_async_wait<1>();                        // inputs(tile) have landed (this thread's part)
+            cp_async_wait<1>();                        // inputs(tile) have landed (this lane's part)
         } else {
             cp_async_wait<0>();
         }
-        __syncthreads();                               // (B) inputs(tile) visible to all threads
-        MM_TICK(1);
+        __syncwarp();                                  // inputs(tile) and the carried state visible to all lanes
+        if (EPI != EPI_STORE && live && (lane & 7) == 0) {
+            // the store phase will read this tile's aux samples: pull their lines into L2 now (one request per 128 bytes)
+#pragma unroll
+            for (int s = 0; s < NAUX; ++s) {
+                const float* ap = P.aux[s] + rowoff + tile_lo + 4 * lane;
+#pragma unroll
+                for (int r = 0; r < kVecsPerLane; ++r)
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(ap + 128 * r));
+            }
+        }
 
-        float* tin = ring + (size_t)slot * NIN * kL;
+        float* tin = ring + (size_t)slot * NIN * kWT;
         const bool in_fast = fast_in(tile_lo);
         const bool inject = (tile == 0) && (P.pad > 0);
         const int dead = (tile == 0) ? dead0 : 0;
         const int d0 = dead;                           // dead < kS always (pad <= 15, lead 32)
-        const bool inj_thread = inject && tid == 0;
+        const bool inj_thread = inject && lane == 0;
 
         // prologue constants: edge tiles were transformed by their loader already
         int pmode = PRO_NONE;
@@ -266,8 +292,8 @@ __global__ void __launch_bounds__(kT, Sweep2Cfg<M, NF, NIN, DIR, EPI, NAUX, ST>:
             if (P.pro_mul) { muld = __ldg(P.pro_mul + row); mulf = (float)muld; }
         }
 
-        const int chunk = (DIR > 0) ? tid : (kT - 1 - tid);
-        const int cbase = chunk * 32;                  // float index of this thread's chunk
+        const int chunk = (DIR > 0) ? lane : (31 - lane);
+        const int cbase = chunk * 32;                  // float index of this lane's chunk
         const int cx = (chunk & 7) << 2;               // float-index XOR of the swizzle
         // address of logical vec u of this chunk in stream buffer b: b + cbase + ((4u) ^ cx)
 
@@ -289,7 +315,7 @@ __global__ void __launch_bounds__(kT, Sweep2Cfg<M, NF, NIN, DIR, EPI, NAUX, ST>:
             float4 xv[NIN];
 #pragma unroll
             for (int s = 0; s < NIN; ++s) {
-                float* p = tin + (size_t)s * kL + cbase + ((4 * uu) ^ cx);
+                float* p = tin + (size_t)s * kWT + cbase + ((4 * uu) ^ cx);
                 xv[s] = *reinterpret_cast<const float4*>(p);
                 if (pmode == PRO_SUBMUL_F32) {
                     xv[s].x = __fmul_rn(__fsub_rn(xv[s].x, subf), mulf); xv[s].y = __fmul_rn(__fsub_rn(xv[s].y, subf), mulf);
@@ -330,7 +356,7 @@ __global__ void __launch_bounds__(kT, Sweep2Cfg<M, NF, NIN, DIR, EPI, NAUX, ST>:
             const int off = cbase + (((mi >> 2) << 2) ^ cx) + (mi & 3);
 #pragma unroll
             for (int f = 0; f < NF; ++f) {
-                const float x0 = tin[(size_t)(NIN == 1 ? 0 : f) * kL + off];
+                const float x0 = tin[(size_t)(NIN == 1 ? 0 : f) * kWT + off];
                 double si[M];
 #pragma unroll
                 for (int i = 0; i < M; ++i) si[i] = __ldg(P.tab[f] + Tab<M>::Zi + i) * (double)x0;
@@ -338,11 +364,9 @@ __global__ void __launch_bounds__(kT, Sweep2Cfg<M, NF, NIN, DIR, EPI, NAUX, ST>:
             }
         }
 
-        MM_TICK(2);
         // ---- warp scan: branch-free (lanes below the stride shuffle in zeros), sections interleaved --------
 #pragma unroll
         for (int d = 0; d < 5; ++d) {
-            if (PP.skip & 8) break;
             const bool act = lane >= (1 << d);
             double pe[NF][M];
 #pragma unroll
@@ -355,73 +379,42 @@ __global__ void __launch_bounds__(kT, Sweep2Cfg<M, NF, NIN, DIR, EPI, NAUX, ST>:
 #pragma unroll
             for (int f = 0; f < NF; ++f) matvec_acc_s<M>(tab[f].Pw[d], pe[f], E[f]);
         }
+
+        // ---- state leaving this warp-tile = zero-state aggregate + A^kWT * state entering it -------------------
         if (lane == 31) {
-#pragma unroll
-            for (int f = 0; f < NF; ++f)
-#pragma unroll
-                for (int i = 0; i < M; ++i) sh.tot[f][warp][i] = E[f][i];
-        }
-        MM_TICK(3);
-        __syncthreads();                               // (C) warp totals visible
-        MM_TICK(4);
-
-        double base[NF][M];
-#pragma unroll
-        for (int f = 0; f < NF; ++f)
-#pragma unroll
-            for (int i = 0; i < M; ++i) base[f][i] = 0.0;
-#pragma unroll
-        for (int v = 0; v < kNW - 1; ++v) {
-            if (v < warp) {                            // warp-uniform
-#pragma unroll
-                for (int f = 0; f < NF; ++f) {
-                    double nb[M];
-#pragma unroll
-                    for (int i = 0; i < M; ++i) nb[i] = sh.tot[f][v][i];
-                    matvec_acc_s<M>(tab[f].Qpow[1], base[f], nb);
-#pragma unroll
-                    for (int i = 0; i < M; ++i) base[f][i] = nb[i];
-                }
-            }
-        }
-
-        // ---- state leaving this tile = zero-state aggregate + A^kL * state entering it ------------------------
-        if (tid == kT - 1) {
 #pragma unroll
             for (int f = 0; f < NF; ++f) {
                 double ag[M], cin[M];
 #pragma unroll
-                for (int i = 0; i < M; ++i) { ag[i] = E[f][i]; cin[i] = sh.carry[tile & 1][f][i]; }
-                matvec_acc_s<M>(tab[f].Qpow[1], base[f], ag);
-                matvec_acc_s<M>(tab[f].Qpow[kNW], cin, ag);
+                for (int i = 0; i < M; ++i) { ag[i] = E[f][i]; cin[i] = sh.carry[warp][tile & 1][f][i]; }
+                matvec_acc_s<M>(tab[f].Qpow[1], cin, ag);
 #pragma unroll
-                for (int i = 0; i < M; ++i) sh.carry[(tile + 1) & 1][f][i] = ag[i];
+                for (int i = 0; i < M; ++i) sh.carry[warp][(tile + 1) & 1][f][i] = ag[i];
             }
         }
         if (!live) {   // halo tile: only its contribution to the state was needed
             if (ST > 1) slot ^= 1;
             else {
-                __syncthreads();
+                __syncwarp();
                 if (tile + 1 < t_end) issue_inputs(row, tile + 1, 0);
                 cp_async_commit();
             }
             continue;
         }
 
-        // ---- incoming state of this thread -------------------------------------------------------------------
+        // ---- incoming state of this lane ------------------------------------------------------------------------
         double z[NF][M];
 #pragma unroll
         for (int f = 0; f < NF; ++f) {
             double C[M];
 #pragma unroll
-            for (int i = 0; i < M; ++i) C[i] = sh.carry[tile & 1][f][i];
-            matvec_acc_s<M>(tab[f].Qpow[warp], C, base[f]);
+            for (int i = 0; i < M; ++i) C[i] = sh.carry[warp][tile & 1][f][i];
 #pragma unroll
             for (int i = 0; i < M; ++i) {
                 const double up = shfl_up_d(E[f][i], 1);
                 z[f][i] = (lane > 0) ? up : 0.0;
             }
-            matvec_acc_s<M>(tab[f].Plane[lane], base[f], z[f]);
+            matvec_acc_s<M>(tab[f].Plane[lane], C, z[f]);
         }
 
         // ---- pass 2 (+ the recombining epilogue, evaluated on the float64 section outputs) --------------------
@@ -429,9 +422,9 @@ __global__ void __launch_bounds__(kT, Sweep2Cfg<M, NF, NIN, DIR, EPI, NAUX, ST>:
         constexpr int NWR = (EPI == EPI_STORE) ? NF : ((EPI == EPI_DYNAMICS || EPI == EPI_DYNAMICS_GEN) ? 2 : 1);   // tiles pass 2 writes
         float* tout[NF];
 #pragma unroll
-        for (int f = 0; f < NF; ++f) tout[f] = (f < NIN) ? (tin + (size_t)f * kL) : (extra + (size_t)(f - NIN) * kL);
+        for (int f = 0; f < NF; ++f) tout[f] = (f < NIN) ? (tin + (size_t)f * kWT) : (extra + (size_t)(f - NIN) * kWT);
         const bool out_fast = fast_out(tile_lo);
-        const bool pk_fast = tile_lo >= P.pk_lo && tile_lo + kL - 1 <= P.pk_hi;
+        const bool pk_fast = tile_lo >= P.pk_lo && tile_lo + kWT - 1 <= P.pk_hi;
         float aux_subf = 0.f, aux_mulf = 1.f;
         double aux_muld = 1.0;
         const int aux_pmode = (EPI != EPI_STORE && P.aux_pro) ? P.pro_mode : PRO_NONE;
@@ -462,18 +455,18 @@ __global__ void __launch_bounds__(kT, Sweep2Cfg<M, NF, NIN, DIR, EPI, NAUX, ST>:
                 // float32, float64 sections in float64, rounded to float32 once
                 float accf = 0.f;
 #pragma unroll
-                for (int f = 0; f < NF32; ++f) accf = fmaf(P.w32[f], yf[f], accf);
+                for (int f = 0; f < NF32; ++f) accf = fmaf(NF == 1 ? w0f : P.w32[f], yf[f], accf);
                 if (NF32 < NF) {
                     double acc = (double)accf;
 #pragma unroll
-                    for (int f = NF32; f < NF; ++f) acc = fma(P.w[f], yd[f], acc);
+                    for (int f = NF32; f < NF; ++f) acc = fma(NF == 1 ? w0d : P.w[f], yd[f], acc);
                     accf = (float)acc;
                 }
                 st[0] = accf;
             } else if (EPI == EPI_EXCITER) {
                 const float hf = yflt(0);
                 const float sat = exciter_sat(hf, P.exc_mode, (float)P.exc_k);
-                st[0] = (float)((double)(sat - hf) * (P.exc_gain * 0.25));
+                st[0] = (float)((double)(sat - hf) * (excg * 0.25));
             } else if (EPI == EPI_DYNAMICS) {   // y0 = band 2, y1 = band 3; downward knees only
                 st[0] = band_chain(yflt(0), P.dyn.band[1]);
                 st[1] = band_chain(yflt(NF > 1 ? 1 : 0), P.dyn.band[2]);
@@ -517,15 +510,14 @@ __global__ void __launch_bounds__(kT, Sweep2Cfg<M, NF, NIN, DIR, EPI, NAUX, ST>:
             S0[p] = make_float2(sf[2 * p][0], sf[2 * p + 1][0]);
             S1[p] = make_float2(sf[2 * p][M > 1 ? 1 : 0], sf[2 * p + 1][M > 1 ? 1 : 0]);
         }
-        if (PP.skip & 4) {
-        } else if (!inj_thread) {
+        if (!inj_thread) {
 #pragma unroll (EPI == EPI_STORE ? kS / 4 : 4)
             for (int u = 0; u < kS / 4; ++u) {
                 const int uu = (DIR > 0) ? u : (kS / 4 - 1 - u);
                 const int off = cbase + ((4 * uu) ^ cx);
                 float4 xv[NIN];
 #pragma unroll
-                for (int s = 0; s < NIN; ++s) xv[s] = *reinterpret_cast<const float4*>(tin + (size_t)s * kL + off);
+                for (int s = 0; s < NIN; ++s) xv[s] = *reinterpret_cast<const float4*>(tin + (size_t)s * kWT + off);
                 float4 yv[NWR];
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
@@ -559,14 +551,14 @@ __global__ void __launch_bounds__(kT, Sweep2Cfg<M, NF, NIN, DIR, EPI, NAUX, ST>:
                 for (int f = 0; f < NWR; ++f) *reinterpret_cast<float4*>(tout[f] + off) = yv[f];
             }
         } else {
-            // the one thread of tile 0 that starts from zi * x_first after `d0` dead samples
+            // the one lane of tile 0 that starts from zi * x_first after `d0` dead samples
 #pragma unroll 1
             for (int j = 0; j < kS; ++j) {
                 const int mi = (DIR > 0) ? j : (kS - 1 - j);
                 const int off = cbase + (((mi >> 2) << 2) ^ cx) + (mi & 3);
                 float xs[NIN];
 #pragma unroll
-                for (int s = 0; s < NIN; ++s) xs[s] = tin[(size_t)s * kL + off];
+                for (int s = 0; s < NIN; ++s) xs[s] = tin[(size_t)s * kWT + off];
                 if (j == d0) {
 #pragma unroll
                     for (int f = 0; f < NF; ++f)
@@ -595,26 +587,22 @@ __global__ void __launch_bounds__(kT, Sweep2Cfg<M, NF, NIN, DIR, EPI, NAUX, ST>:
                 }
             }
         }
-        MM_TICK(5);
-        __syncthreads();                               // (E) results visible
-        MM_TICK(6);
+        __syncwarp();                                  // results visible to the whole warp
 
         // ---- store: coalesced.  EPI_STORE: NOUT finished float32 streams.  Recombining epilogues: finish here ------------
-        if (out_fast && (PP.skip & 1)) {
-        } else if (EPI != EPI_STORE) {
+        if (EPI != EPI_STORE) {
             const float* ax0 = P.aux[0] + rowoff;
             const float* ax1 = (NAUX > 1) ? (P.aux[1] + rowoff) : ax0;
             if (out_fast) {
-                const int so0 = 4 * swz(tid);
-                const size_t go0 = (size_t)tile_lo + 4 * tid;
-                float4 xa[kTileVecs / kT], xb[kTileVecs / kT];
+                const size_t go0 = (size_t)tile_lo + 4 * lane;
+                float4 xa[kVecsPerLane], xb[kVecsPerLane];
 #pragma unroll
-                for (int r = 0; r < kTileVecs / kT; ++r) {     // all aux loads first: 8 (16) independent requests in flight
-                    xa[r] = __ldcs(reinterpret_cast<const float4*>(ax0 + go0 + 4 * kT * r));
-                    if (NAUX > 1) xb[r] = __ldcs(reinterpret_cast<const float4*>(ax1 + go0 + 4 * kT * r));
+                for (int r = 0; r < kVecsPerLane; ++r) {       // all aux loads first: 8 (16) independent requests in flight
+                    xa[r] = __ldcs(reinterpret_cast<const float4*>(ax0 + go0 + 128 * r));
+                    if (NAUX > 1) xb[r] = __ldcs(reinterpret_cast<const float4*>(ax1 + go0 + 128 * r));
                 }
 #pragma unroll
-                for (int r = 0; r < kTileVecs / kT; ++r) {
+                for (int r = 0; r < kVecsPerLane; ++r) {
                     float4 a0 = xa[r];
                     if (aux_pmode == PRO_SUBMUL_F32) {
                         a0.x = __fmul_rn(__fsub_rn(a0.x, aux_subf), aux_mulf); a0.y = __fmul_rn(__fsub_rn(a0.y, aux_subf), aux_mulf);
@@ -623,9 +611,10 @@ __global__ void __launch_bounds__(kT, Sweep2Cfg<M, NF, NIN, DIR, EPI, NAUX, ST>:
                         a0.x = (float)((double)a0.x * aux_muld); a0.y = (float)((double)a0.y * aux_muld);
                         a0.z = (float)((double)a0.z * aux_muld); a0.w = (float)((double)a0.w * aux_muld);
                     }
-                    const float4 s0 = *reinterpret_cast<const float4*>(tout[0] + so0 + 4 * kT * r);
+                    const int so = 4 * swz(lane + 32 * r);
+                    const float4 s0 = *reinterpret_cast<const float4*>(tout[0] + so);
                     float4 s1 = s0;
-                    if (NSTAGE > 1) s1 = *reinterpret_cast<const float4*>(tout[NWR > 1 ? 1 : 0] + so0 + 4 * kT * r);
+                    if (NSTAGE > 1) s1 = *reinterpret_cast<const float4*>(tout[NWR > 1 ? 1 : 0] + so);
                     const float4 a1 = (NAUX > 1) ? xb[r] : a0;
                     float4 o;
                     o.x = final_value(s0.x, s1.x, a0.x, a1.x); o.y = final_value(s0.y, s1.y, a0.y, a1.y);
@@ -633,17 +622,17 @@ __global__ void __launch_bounds__(kT, Sweep2Cfg<M, NF, NIN, DIR, EPI, NAUX, ST>:
                     if (pk_fast) {
                         pk = fmaxf(fmaxf(pk, fmaxf(fabsf(o.x), fabsf(o.y))), fmaxf(fabsf(o.z), fabsf(o.w)));
                     } else {
-                        const long long q = tile_lo + 4 * (tid + kT * r);
+                        const long long q = tile_lo + 4 * (lane + 32 * r);
 #pragma unroll
                         for (int c = 0; c < 4; ++c)
                             if (q + c >= P.pk_lo && q + c <= P.pk_hi) pk = fmaxf(pk, fabsf(comp4(o, c)));
                     }
-                    __stcs(reinterpret_cast<float4*>(P.out[0] + rowoff + go0 + 4 * kT * r), o);
+                    __stcs(reinterpret_cast<float4*>(P.out[0] + rowoff + go0 + 128 * r), o);
                 }
             } else {
 #pragma unroll 1
-                for (int r = 0; r < kTileVecs / kT; ++r) {
-                    const int v = tid + kT * r;
+                for (int r = 0; r < kVecsPerLane; ++r) {
+                    const int v = lane + 32 * r;
                     const long long q = tile_lo + 4 * v;
                     if (q + 3 < st_lo || q > st_hi) continue;
                     const int so = 4 * swz(v);
@@ -663,20 +652,19 @@ __global__ void __launch_bounds__(kT, Sweep2Cfg<M, NF, NIN, DIR, EPI, NAUX, ST>:
                 }
             }
         } else if (out_fast) {
-            // interior tile: every vector is complete; base + immediate addressing (swz(tid + kT r) = swz(tid) + kT r)
-            const int so0 = 4 * swz(tid);
-            const size_t go0 = rowoff + (size_t)tile_lo + 4 * tid;
+            // interior tile: every vector is complete
+            const size_t go0 = rowoff + (size_t)tile_lo + 4 * lane;
 #pragma unroll
-            for (int r = 0; r < kTileVecs / kT; ++r) {
+            for (int r = 0; r < kVecsPerLane; ++r) {
+                const int so = 4 * swz(lane + 32 * r);
 #pragma unroll
                 for (int f = 0; f < NOUT; ++f)
-                    __stcs(reinterpret_cast<float4*>(P.out[f] + go0 + 4 * kT * r),
-                           *reinterpret_cast<const float4*>(tout[f] + so0 + 4 * kT * r));
+                    __stcs(reinterpret_cast<float4*>(P.out[f] + go0 + 128 * r), *reinterpret_cast<const float4*>(tout[f] + so));
             }
         } else {
 #pragma unroll 1
-            for (int r = 0; r < kTileVecs / kT; ++r) {
-                const int v = tid + kT * r;
+            for (int r = 0; r < kVecsPerLane; ++r) {
+                const int v = lane + 32 * r;
                 const long long q = tile_lo + 4 * v;
                 if (q + 3 < st_lo || q > st_hi) continue;
                 const int so = 4 * swz(v);
@@ -690,27 +678,21 @@ __global__ void __launch_bounds__(kT, Sweep2Cfg<M, NF, NIN, DIR, EPI, NAUX, ST>:
                 }
             }
         }
-        if (EPI != EPI_STORE && P.peak != nullptr) {
+        if (EPI != EPI_STORE && pk_on) {
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) pk = fmaxf(pk, __shfl_xor_sync(0xffffffffu, pk, o));
             if (lane == 0 && pk > 0.f) atomicMax(reinterpret_cast<int*>(P.peak + row / P.channels), __float_as_int(pk));
         }
 
-        MM_TICK(7);
         if (ST > 1) slot ^= 1;
         else {
-            __syncthreads();                           // single stage: everyone done with the buffer
+            __syncwarp();                              // single stage: every lane is done with the buffer
             if (tile + 1 < t_end) issue_inputs(row, tile + 1, 0);
             cp_async_commit();
         }
     }   // tiles
     cp_async_wait<0>();
     }   // items
-    if (dbg_on) {
-        MM_TICK(7);
-        for (int k = 0; k < 8; ++k) PP.dbg[k] = t_ph[k];
-    }
-#undef MM_TICK
 }
 
 }  // namespace mm

@@ -105,3 +105,30 @@ def test_margin_is_what_decouples_the_ranks(gpu_lib):
     good, _, _ = _run_split(x, sr, "standard", "v2", 2)
     assert np.max(np.abs(bad - whole)) > 1e-3
     assert np.max(np.abs(good - whole)) <= 2e-6
+
+
+@pytest.mark.parametrize("world", [2, 8])
+def test_time_split_96k_against_oracle(gpu_lib, world):
+    """BASELINE configs[4] in miniature: a 64 s 96 kHz stereo file split over 2 and 8 virtual ranks with the library's own margin
+    (524288 frames per cut side at 96 kHz, W ~ 6-tile halos of the 30-40 Hz sections) against the CPU oracle and the whole-file
+    run: samples 1e-4 (measured ~5e-7), every rank ends up with the file's loudness / gain / peak."""
+    from mm_b200 import longform, pipeline as P, synth
+    from oracle import chain as oc
+    sr = 96000
+    x = synth.numpy_track(5, sr, 64.0)
+    n = x.shape[0]
+    assert longform.slice_margin(sr) == 524288
+    for chain, style in (("v2", "standard"),) + ((("v1", "edm"),) if world == 2 else ()):
+        target = P.STYLE_CONFIGS[style]["lufs"]
+        whole = P.master_batch([x], sr, [style], [target], chain=chain, measure=True)
+        audio, _, stats = _run_split(x, sr, style, chain, world)
+        assert audio.shape == (n, 2)
+        d = float(np.max(np.abs(audio.astype(np.float64) - whole["audio"][0].astype(np.float64))))
+        ref = (oc.run_v1 if chain == "v1" else oc.run_v2)(x.copy(), sr, target, style)
+        e = float(np.max(np.abs(audio.astype(np.float64) - ref.astype(np.float64))))
+        print(f"[parity] 96 kHz time split {chain}/{style} world {world}: max|split - whole| = {d:.3e}, max|split - oracle| = {e:.3e}")
+        assert d <= 2e-6 and e <= 1e-4
+        for s in stats:
+            for k in ("lufs_in", "lufs_out", "gain_db", "peak_in", "peak_out"):
+                assert abs(s[k] - whole["stats"][0][k]) <= 1e-6, (k, s[k], whole["stats"][0][k])
+        assert abs(stats[0]["lufs_out"] - oc.measure_lufs(ref, sr)) <= 0.01
