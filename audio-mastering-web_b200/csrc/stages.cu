@@ -5,6 +5,8 @@
 #include <cstdlib>
 #include <cstring>
 
+#include <cuda.h>
+
 #include "context.h"
 #include "sweep4.cuh"
 #include "lufs_kernel.cuh"
@@ -55,8 +57,41 @@ static void choose_segments(int rows, int ntiles, int whalo, int capacity, int* 
     *seglen_out = (ntiles + best - 1) / best;
 }
 
+// ---- TMA tensor maps ---------------------------------------------------------------------------------
+// cuTensorMapEncodeTiled is a driver entry point; it is fetched through the runtime (no link-time dependency on libcuda).
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) p = nullptr;
+        return (EncodeTiledFn)p;
+    }();
+    return fn;
+}
+static int tma_policy() {            // MM_TMA: 0 = per-lane cp.async loads and float4 stores, 1 = bulk tensor loads, 2 (default) = + bulk stores
+    static int pol = -1;
+    if (pol < 0) { const char* e = getenv("MM_TMA"); pol = e ? std::max(0, std::min(2, atoi(e))) : 2; }
+    return pol;
+}
+// A stream as a 2-D tensor of 128-byte lines: {32 floats, lines}; box = one warp-tile {32, 32}; SWIZZLE_128B.  `base` points at
+// float 0 of row 0 plus `shift` floats (backward sweeps: their tile origins are = qend mod 32), `lines` 128-byte lines follow.
+static bool make_stream_map(TmaDesc* out, const float* base, long long shift, long long lines) {
+    EncodeTiledFn enc = encode_tiled_fn();
+    if (!enc || lines < 32 || (((uintptr_t)(base + shift)) & 15)) return false;
+    static_assert(sizeof(CUtensorMap) == sizeof(TmaDesc), "CUtensorMap is 128 bytes");
+    const cuuint64_t dims[2] = {32, (cuuint64_t)lines};
+    const cuuint64_t strides[1] = {128};
+    const cuuint32_t box[2] = {32, 32};
+    const cuuint32_t estr[2] = {1, 1};
+    return enc(reinterpret_cast<CUtensorMap*>(out), CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)(base + shift), dims, strides, box, estr,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 template <int M, int NF, int NIN, int DIR, int EPI, int NAUX, int NF32>
-static int launch_sweep2(mm_ctx* c, SweepArgs<M, NF>* As, int whalo, const char* name) {
+static int launch_sweep2(mm_ctx* c, SweepArgs<M, NF>* As, int whalo, const char* name, int batch_rows) {
     constexpr int ST = SweepStages<NF, NIN>::value;
     typedef Sweep2Cfg<M, NF, NIN, DIR, EPI, NAUX, ST> Cfg;
     auto kern = sweep2_kernel<M, NF, NIN, DIR, EPI, NAUX, ST, NF32, 1>;
@@ -78,6 +113,28 @@ static int launch_sweep2(mm_ctx* c, SweepArgs<M, NF>* As, int whalo, const char*
     const long long items = (long long)A.rows * PP.nseg;
     const unsigned grid = (unsigned)std::min<long long>((items + kSW - 1) / kSW, capacity / kSW);
     PP.a[0] = A;
+    // interior input tiles by TMA: one tensor map per input stream over the whole batch buffer
+    PP.use_tma = 0;
+    PP.tma_shift = 0;
+    PP.tma_row_lines = A.stride / 32;
+    if (tma_policy() && (A.stride % 32) == 0 && batch_rows > 0) {
+        const long long q_last = kLead + A.n + A.pad - 1;
+        const long long qend = (q_last + 4) & ~3LL;
+        const long long shift = DIR > 0 ? 0 : (qend % 32);
+        const long long lines = ((long long)batch_rows * A.stride - shift) / 32;
+        bool ok = true;
+        for (int s = 0; s < NIN && ok; ++s) ok = make_stream_map(&PP.tmap[s], A.in[s], shift, lines);
+        if (ok) { PP.use_tma = 1; PP.tma_shift = (int)shift; }
+        // bulk stores pay for the four-output forward sweep (4.6 -> 3.9 ms per launch: 64 LDS + STG per lane and tile become four
+        // instructions of one lane); with one or two outputs the issuing lane's wait before the next tile costs more than the
+        // stores it saves (measured +2..3 %), so those keep their coalesced float4 stores
+        if (ok && EPI == EPI_STORE && NF >= 4 && tma_policy() >= 2) {
+            // (the halo start position is the same for loads and stores: both are tile origins)
+            bool oko = true;
+            for (int f = 0; f < NF && oko; ++f) oko = make_stream_map(&PP.tmap_out[f], A.out[f], shift, lines);
+            if (oko) PP.use_tma |= 2;
+        }
+    }
     {
         KernelScope ks(c, name);
         ks.samples = (double)A.rows * (double)A.n;
@@ -194,7 +251,7 @@ template <int M, int NF, int NIN, int DIR, int EPI, int NAUX, int NF32>
 static int run_sweep(mm_ctx* c, const mm_geom* g, const Arranged& R, int nout, const Pro& pro, int pad, const char* name) {
     SweepArgs<M, NF> A;
     fill_common<M, NF>(c, A, g, R.plans, R.in, NIN, R.out, nout, pro, R.epi, pad);
-    return launch_sweep2<M, NF, NIN, DIR, EPI, NAUX, NF32>(c, &A, halo_tiles(R.plans, NF), name);
+    return launch_sweep2<M, NF, NIN, DIR, EPI, NAUX, NF32>(c, &A, halo_tiles(R.plans, NF), name, g->tracks * g->channels);
 }
 
 int sweep_fwd(mm_ctx* c, const mm_geom* g, int nf, int nin, const FilterPlan* const* plans, const float* const* in,

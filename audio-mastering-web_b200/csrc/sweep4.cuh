@@ -39,9 +39,11 @@ namespace mm {
 constexpr int kWT = 1024;            // samples per warp-tile (32 lanes x kS)
 // Warps per sweep CTA.  The warps of a CTA share nothing but the read-only scan tables, so the CTA size only sets the granularity
 // at which an SM's 228 KB of shared memory is handed out: the count that fits the most warps on an SM wins (ties: the smaller
-// CTA).  `slice` = bytes of one warp's tiles, `tables` = bytes of the CTA's scan tables; 1.25 KB per CTA is reserved / static.
+// CTA).  `slice` = bytes of one warp's tiles, `tables` = bytes of the CTA's scan tables; see sweep_warps_on_sm for what else a CTA holds.
 constexpr int sweep_warps_on_sm(int k, size_t slice, size_t tables) {
-    const size_t cta = (size_t)k * slice + tables + 1280;
+    // per CTA besides the tiles and tables: 1 KB reserved by the driver, up to 1 KB of padding in front of the 1024-byte aligned
+    // dynamic part, and the static carries + mbarriers (<= 160 bytes per warp)
+    const size_t cta = (size_t)k * slice + tables + 2304 + 160 * (size_t)k;
     if (cta > 232448) return 0;
     const int ctas = (int)(232448 / cta) > 32 ? 32 : (int)(232448 / cta);
     return k * ctas > 16 ? 16 : k * ctas;      // beyond ~16 warps the register file (90 to 200 registers per thread) is the limit anyway
@@ -77,6 +79,43 @@ template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile(
 
 __device__ __forceinline__ int swz(int v) { return (v & ~7) | ((v ^ (v >> 3)) & 7); }   // v = chunk * 8 + u
 
+// ---- TMA (cp.async.bulk.tensor) + mbarrier: the input tiles of interior warp-tiles -----------------------------------------
+// A stream is viewed as a 2-D tensor [128-byte lines][32 floats]; one warp-tile is the box {32 floats, 32 lines} = 4 KB, and the
+// hardware's SWIZZLE_128B (16-byte chunk index XOR line index mod 8) is exactly swz() above, so a bulk tensor copy issued by ONE
+// lane lands the tile in the layout both the coalesced and the per-lane accesses want -- instead of 8 LDGSTS per lane and stream.
+struct alignas(64) TmaDesc { unsigned char bytes[128]; };     // CUtensorMap (opaque; filled by cuTensorMapEncodeTiled on the host)
+
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
+}
+// waits for the phase with the given parity; bounded: a tensor map / byte-count mistake traps instead of hanging the device
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+    const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+    unsigned done = 0;
+#pragma unroll 1
+    for (int spin = 0; spin < (1 << 22) && !done; ++spin)
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+                     : "=r"(done) : "r"(a), "r"(parity) : "memory");
+    if (!done) __trap();
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
+// smem -> global (bulk async-group completion): the finished float32 tiles of a storing sweep leave by one instruction per stream
+__device__ __forceinline__ void tma_store_2d(const TmaDesc* desc, const void* smem_src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];\n"
+                 ::"l"(desc), "r"((unsigned)__cvta_generic_to_shared(smem_src)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;\n" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory"); }
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const TmaDesc* desc, unsigned long long* bar, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];\n"
+                 ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(desc), "r"((unsigned)__cvta_generic_to_shared(bar)), "r"(c0), "r"(c1)
+                 : "memory");
+}
+
 template <int M> __device__ __forceinline__ void matvec_acc_s(const double* p, const double (&v)[M], double (&acc)[M]) {
 #pragma unroll
     for (int i = 0; i < M; ++i) {
@@ -88,10 +127,16 @@ template <int M> __device__ __forceinline__ void matvec_acc_s(const double* p, c
 }
 
 template <int M, int NF, int NSET = 1> struct Sweep2Args {
+    TmaDesc tmap[NF];           // tensor maps of the input streams (first NIN used); valid when use_tma != 0
+    TmaDesc tmap_out[NF];       // ... and of the output streams of a storing sweep (EPI_STORE); valid when use_tma & 2
     SweepArgs<M, NF> a[NSET];   // NSET is always 1 (the split-section experiment of round 1 is gone)
     int seglen;           // live warp-tiles per segment
     int nseg;             // segments per row
     int whalo;            // halo warp-tiles read before a segment (max over the sweep's sections)
+    int use_tma;          // bit 0: interior input tiles arrive by cp.async.bulk.tensor (else per-lane cp.async); bit 1: interior
+                          // output tiles of a storing sweep leave the same way
+    int tma_shift;        // floats the tensor maps' base is shifted by (backward sweeps: tile origins are = qend mod 32)
+    long long tma_row_lines;   // 128-byte lines per row (stride / 32)
 };
 
 template <int M, int NF, int NIN, int DIR, int EPI, int NAUX, int ST>
@@ -113,10 +158,12 @@ struct Sweep2Cfg {
     static constexpr int kCap = kCapW < 1 ? 1 : kCapW;
     static constexpr int kMinBlocks = kFit < 1 ? 1 : (kFit > kCap ? kCap : kFit);
 };
-// input ring depth per instantiation: double-buffered while a warp's slice stays within 20 KB (11+ warps per SM by shared memory)
+// input ring depth per instantiation: double-buffered while a warp's slice stays within 20 KB (10+ warps per SM by shared memory).
+// The four-input backward sweep would need 32 KB per warp (6 warps per SM: measured 8.7 ms against 6.5 ms single-stage with 10
+// warps); it stays single-stage and pulls the next tile's lines into L2 while the current one is scanned.
 template <int NF, int NIN> struct SweepStages {
     static constexpr int kExtra = NF > NIN ? NF - NIN : 0;
-    static constexpr int value = (2 * NIN + kExtra) * 4 <= 32 ? 2 : 1;
+    static constexpr int value = (2 * NIN + kExtra) * 4 <= 20 ? 2 : 1;
 };
 
 template <int M, int NF, int SW> struct Scratch2 {
@@ -137,8 +184,16 @@ __global__ void __launch_bounds__(Sweep2Cfg<M, NF, NIN, DIR, EPI, NAUX, ST>::kTh
     typedef Sweep2Cfg<M, NF, NIN, DIR, EPI, NAUX, ST> Cfg;
     constexpr int kSW = Cfg::kSW, kSweepThreads = Cfg::kThreads;
     const SweepArgs<M, NF>& P = PP.a[0];
-    extern __shared__ __align__(128) unsigned char smraw[];
+    extern __shared__ __align__(1024) unsigned char smraw[];       // SWIZZLE_128B destinations need 1024-byte alignment
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    __shared__ __align__(8) unsigned long long mbar[kSW][ST];
+    unsigned mphase = 0;                                           // bit s: parity the next wait on this warp's slot s expects
+    if ((PP.use_tma & 1) && lane == 0) {
+        if ((unsigned)__cvta_generic_to_shared(smraw) & 1023u) __trap();      // the swizzled boxes would land shifted: fail loudly
+#pragma unroll
+        for (int s = 0; s < ST; ++s) mbar_init(&mbar[warp][s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
     float* ring = reinterpret_cast<float*>(smraw + (size_t)warp * Cfg::kWarpBytes);            // this warp's input slots
     float* extra = reinterpret_cast<float*>(smraw + (size_t)warp * Cfg::kWarpBytes + Cfg::kExtraOff);
     SmemTab<M>* tab = reinterpret_cast<SmemTab<M>*>(smraw + Cfg::kTabOff);
@@ -175,7 +230,16 @@ __global__ void __launch_bounds__(Sweep2Cfg<M, NF, NIN, DIR, EPI, NAUX, ST>::kTh
     auto issue_inputs = [&](int row, int tile, int slot) {
         const long long lo = tile_origin(tile);
         const size_t rowoff = (size_t)row * (size_t)P.stride;
-        if (fast_in(lo)) {
+        if (fast_in(lo) && (PP.use_tma & 1)) {
+            // one lane arms the slot's mbarrier with the byte count and issues one bulk tensor copy per stream
+            if (lane == 0) {
+                fence_proxy_async();                       // earlier generic-proxy accesses of this slot (ordered by the caller's __syncwarp)
+                mbar_expect_tx(&mbar[warp][slot], NIN * (unsigned)Cfg::kTileBytes);
+                const int line = (int)((long long)row * PP.tma_row_lines + (lo - PP.tma_shift) / 32);
+#pragma unroll
+                for (int s = 0; s < NIN; ++s) tma_load_2d(ring + ((size_t)slot * NIN + s) * kWT, &PP.tmap[s], &mbar[warp][slot], 0, line);
+            }
+        } else if (fast_in(lo)) {
 #pragma unroll
             for (int s = 0; s < NIN; ++s) {
                 const float* src = P.in[s] + rowoff + lo + 4 * lane;
@@ -255,13 +319,29 @@ __global__ void __launch_bounds__(Sweep2Cfg<M, NF, NIN, DIR, EPI, NAUX, ST>::kTh
     for (int tile = t_first; tile < t_end; ++tile) {
         const bool live = tile >= t_live;
         const long long tile_lo = tile_origin(tile);
+        if (EPI == EPI_STORE && (PP.use_tma & 2) && lane == 0) tma_store_wait_read();   // last tile's bulk stores have read their tiles
         if (ST > 1) {
             __syncwarp();                              // every lane is done with the other slot (stored from it last tile)
             if (tile + 1 < t_end) issue_inputs(row, tile + 1, slot ^ 1);
             cp_async_commit();                         // group: inputs(tile + 1)
             cp_async_wait<1>();                        // inputs(tile) have landed (this lane's part)
+            if ((PP.use_tma & 1) && fast_in(tile_lo)) { mbar_wait(&mbar[warp][slot], (mphase >> slot) & 1u); mphase ^= 1u << slot; }
         } else {
             cp_async_wait<0>();
+            if ((PP.use_tma & 1) && fast_in(tile_lo)) { mbar_wait(&mbar[warp][0], mphase & 1u); mphase ^= 1u; }
+            if (tile + 1 < t_end && (lane & 7) == 0) {
+                // single-stage ring: the next tile's inputs can only be fetched once this tile has left the buffer; pull their
+                // lines into L2 now so that fetch is short (one request per 128 bytes)
+                const long long nlo = tile_origin(tile + 1);
+                if (fast_in(nlo)) {
+#pragma unroll
+                    for (int s = 0; s < NIN; ++s) {
+                        const float* np_ = P.in[s] + rowoff + nlo + 4 * lane;
+#pragma unroll
+                        for (int r = 0; r < kVecsPerLane; ++r) asm volatile("prefetch.global.L2 [%0];" ::"l"(np_ + 128 * r));
+                    }
+                }
+            }
         }
         __syncwarp();                                  // inputs(tile) and the carried state visible to all lanes
         if (EPI != EPI_STORE && live && (lane & 7) == 0) {
@@ -587,6 +667,8 @@ __global__ void __launch_bounds__(Sweep2Cfg<M, NF, NIN, DIR, EPI, NAUX, ST>::kTh
                 }
             }
         }
+        const bool bulk_out = EPI == EPI_STORE && (PP.use_tma & 2) && out_fast;
+        if (bulk_out) fence_proxy_async();             // this lane's staged results become visible to the async proxy
         __syncwarp();                                  // results visible to the whole warp
 
         // ---- store: coalesced.  EPI_STORE: NOUT finished float32 streams.  Recombining epilogues: finish here ------------
@@ -651,6 +733,14 @@ __global__ void __launch_bounds__(Sweep2Cfg<M, NF, NIN, DIR, EPI, NAUX, ST>::kTh
                     }
                 }
             }
+        } else if (bulk_out) {
+            // interior tile of a storing sweep: one bulk tensor store per stream, issued by one lane
+            if (lane == 0) {
+                const int line = (int)((long long)row * PP.tma_row_lines + (tile_lo - PP.tma_shift) / 32);
+#pragma unroll
+                for (int f = 0; f < NOUT; ++f) tma_store_2d(&PP.tmap_out[f], tout[f], 0, line);
+                tma_store_commit();
+            }
         } else if (out_fast) {
             // interior tile: every vector is complete
             const size_t go0 = rowoff + (size_t)tile_lo + 4 * lane;
@@ -686,12 +776,14 @@ __global__ void __launch_bounds__(Sweep2Cfg<M, NF, NIN, DIR, EPI, NAUX, ST>::kTh
 
         if (ST > 1) slot ^= 1;
         else {
+            if (bulk_out && lane == 0) tma_store_wait_read();
             __syncwarp();                              // single stage: every lane is done with the buffer
             if (tile + 1 < t_end) issue_inputs(row, tile + 1, 0);
             cp_async_commit();
         }
     }   // tiles
     cp_async_wait<0>();
+    if (EPI == EPI_STORE && (PP.use_tma & 2) && lane == 0) tma_store_wait_all();    // the segment's bulk stores are complete
     }   // items
 }
 
