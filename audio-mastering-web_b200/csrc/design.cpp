@@ -515,6 +515,13 @@ bool build_scan_tables_balanced(const Ba& f, int S, int T, ScanTables* out, int 
     if (f.m < 1 || f.m > kMaxOrder) return false;
     if (!balanced_realization(f, &ss, Tm)) return false;
     if (!build_scan_tables_ss(ss, S, T, out, max_window)) return false;
+    // the float32 pass 2 runs the realization with its states rescaled to B = (1, ..., 1) (common.cuh ss32_step): every state
+    // must be driven by the input
+    {
+        long double bmax = 0.0L;
+        for (int i = 0; i < ss.m; ++i) bmax = std::max(bmax, fabsl(ss.B[i]));
+        for (int i = 0; i < ss.m; ++i) if (!(fabsl(ss.B[i]) > 1e-9L * bmax)) return false;
+    }
     out->mode = kBalancedF32;
     out->norm2 = spectral_norm(ss.m, ss.A);
     // steady state of the unit-step response in these coordinates: (I - A) s = B

@@ -31,10 +31,13 @@ template <int M> static void fill_filter(FiltK<M>& fk, const FilterPlan* p) {
     for (int i = 0; i < M; ++i) fk.a[i] = p->ba.a[i + 1];
     for (int j = 0; j < kS; ++j)
         for (int i = 0; i < M; ++i) fk.g[j][i] = p->tabs.g[(size_t)j * M + i];
+    // float32 pass 2 in rescaled coordinates s' = d s, d_i = 1 / B_i (balanced plans guarantee B_i != 0; other plans never run it)
+    double d[M];
+    for (int i = 0; i < M; ++i) d[i] = (p->tabs.mode == kBalancedF32 && p->tabs.B[i] != 0.0) ? 1.0 / p->tabs.B[i] : 1.0;
     for (int i = 0; i < M; ++i) {
-        for (int k = 0; k < M; ++k) fk.A32[i][k] = (float)p->tabs.A[i * M + k];
-        fk.B32[i] = (float)p->tabs.B[i];
-        fk.C32[i] = (float)p->tabs.C[i];
+        for (int k = 0; k < M; ++k) fk.A32[i][k] = (float)(d[i] * p->tabs.A[i * M + k] / d[k]);
+        fk.dn32[i] = (float)d[i];
+        fk.C32[i] = (float)(p->tabs.C[i] / d[i]);
     }
     fk.D32 = (float)p->tabs.D;
 }

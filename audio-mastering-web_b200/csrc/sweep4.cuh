@@ -66,7 +66,9 @@ __device__ __forceinline__ double f2d_bits(float x) { return (double)x; }
 
 template <int M> struct SmemTab {
     double Pw[5][M * M];
-    double Plane[32][M * M];
+    double Plane[M * M][32];           // (A^32)^lane, TRANSPOSED: entry e of lane l at Plane[e][l] -- lane-contiguous, conflict free
+                                       // (lane-major rows of 32 bytes cost a 4-way bank conflict per read: the 70-100 M conflicts
+                                       // per launch ncu counted in both rounds)
     double Qpow[kNW + 1][M * M];       // Qpow[kNW] = A^kL carries a state across one tile
 };
 
@@ -205,7 +207,12 @@ __global__ void __launch_bounds__(Sweep2Cfg<M, NF, NIN, DIR, EPI, NAUX, ST>::kTh
     for (int f = 0; f < NF; ++f) {
         const double* g = P.tab[f];
         double* d = reinterpret_cast<double*>(&tab[f]);
-        for (int i = tid; i < (5 + 32 + kNW + 1) * MM; i += kSweepThreads) d[i] = __ldg(g + i);   // Pw, Plane, Qpow are contiguous
+        // device table: Pw [5][MM], Plane [32][MM], Qpow [kNW + 1][MM], contiguous; Plane is transposed on the way in
+        for (int i = tid; i < (5 + 32 + kNW + 1) * MM; i += kSweepThreads) {
+            const int j = i - 5 * MM;
+            const int dsti = (j >= 0 && j < 32 * MM) ? 5 * MM + (j % MM) * 32 + j / MM : i;
+            d[dsti] = __ldg(g + i);
+        }
     }
     __syncthreads();                                        // the only block barrier of the kernel
 
@@ -494,7 +501,13 @@ __global__ void __launch_bounds__(Sweep2Cfg<M, NF, NIN, DIR, EPI, NAUX, ST>::kTh
                 const double up = shfl_up_d(E[f][i], 1);
                 z[f][i] = (lane > 0) ? up : 0.0;
             }
-            matvec_acc_s<M>(tab[f].Plane[lane], C, z[f]);
+#pragma unroll
+            for (int i = 0; i < M; ++i) {
+                double acc = z[f][i];
+#pragma unroll
+                for (int k = 0; k < M; ++k) acc = fma(tab[f].Plane[i * M + k][lane], C[k], acc);
+                z[f][i] = acc;
+            }
         }
 
         // ---- pass 2 (+ the recombining epilogue, evaluated on the float64 section outputs) --------------------
@@ -578,18 +591,14 @@ __global__ void __launch_bounds__(Sweep2Cfg<M, NF, NIN, DIR, EPI, NAUX, ST>::kTh
                 return res;
             }
         };
-        // float32 sections start every chunk from the float64-resolved state
+        // float32 sections start every chunk from the float64-resolved state, mapped into the rescaled coordinates (B = 1) of
+        // ss32_step.  Scalar steps: packing the two sections of a pair into FFMA2 operands costs more register moves than the
+        // packed arithmetic saves (SASS of the loudness kernel: 26 instructions per sample packed, 15 scalar).
         float sf[NF32 > 0 ? NF32 : 1][M];
 #pragma unroll
         for (int f = 0; f < NF32; ++f)
 #pragma unroll
-            for (int i = 0; i < M; ++i) sf[f][i] = (float)z[f][i];
-        float2 S0[NP > 0 ? NP : 1], S1[NP > 0 ? NP : 1];
-#pragma unroll
-        for (int p = 0; p < NP; ++p) {
-            S0[p] = make_float2(sf[2 * p][0], sf[2 * p + 1][0]);
-            S1[p] = make_float2(sf[2 * p][M > 1 ? 1 : 0], sf[2 * p + 1][M > 1 ? 1 : 0]);
-        }
+            for (int i = 0; i < M; ++i) sf[f][i] = (float)(z[f][i] * (double)P.f[f].dn32[i]);
         if (!inj_thread) {
 #pragma unroll (EPI == EPI_STORE ? kS / 4 : 4)
             for (int u = 0; u < kS / 4; ++u) {
@@ -605,14 +614,7 @@ __global__ void __launch_bounds__(Sweep2Cfg<M, NF, NIN, DIR, EPI, NAUX, ST>::kTh
                     float yf[NF];
                     double yd[NF];
 #pragma unroll
-                    for (int p = 0; p < NP; ++p) {
-                        const float2 X = make_float2(comp4(xv[NIN == 1 ? 0 : 2 * p], cc), comp4(xv[NIN == 1 ? 0 : 2 * p + 1], cc));
-                        const float2 Y = pair_step(P.pr[p], X, S0[p], S1[p]);
-                        yf[2 * p] = Y.x; yf[2 * p + 1] = Y.y;
-                        yd[2 * p] = 0.0; yd[2 * p + 1] = 0.0;
-                    }
-#pragma unroll
-                    for (int f = 2 * NP; f < NF; ++f) {
+                    for (int f = 0; f < NF; ++f) {
                         const float xs = comp4(xv[NIN == 1 ? 0 : f], cc);
                         if (f < NF32) { yf[f] = ss32_step<M>(P.f[f], xs, sf[f < NF32 ? f : 0]); yd[f] = 0.0; }
                         else { yd[f] = df2t_step<M>(P.f[f], f2d_bits(xs), z[f]); yf[f] = 0.f; }
@@ -645,7 +647,7 @@ __global__ void __launch_bounds__(Sweep2Cfg<M, NF, NIN, DIR, EPI, NAUX, ST>::kTh
 #pragma unroll
                         for (int i = 0; i < M; ++i) {
                             z[f][i] = __ldg(P.tab[f] + Tab<M>::Zi + i) * (double)xs[NIN == 1 ? 0 : f];
-                            if (f < NF32) sf[f < NF32 ? f : 0][i] = (float)z[f][i];
+                            if (f < NF32) sf[f < NF32 ? f : 0][i] = (float)(z[f][i] * (double)P.f[f].dn32[i]);
                         }
                 }
                 float yf[NF];

@@ -301,4 +301,5 @@ class MasteringChain:
                 _mt.trace_stage(trace_ctx, "chain_finalize_clip", out, sr)
         if progress_callback:
             progress_callback(98, "Готово")
+        P._trim_engine()          # a worker thread does not keep more than MM_WORKSPACE_KEEP_MB of scratch between jobs
         return out

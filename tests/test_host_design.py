@@ -205,29 +205,33 @@ def _tables2(lib, b, a, mode):
 
 def _chunked_f32_pass2(tb, x, zi_scale):
     """Chunk-start states exactly as the float64 scan resolves them (here: a float64 run of the realization),
-    then the float32 recurrence of ss32_step inside every 32-sample chunk."""
+    then the float32 recurrence of ss32_step inside every 32-sample chunk: the balanced realization with its states
+    rescaled by d_i = 1 / B_i (B = 1: 7 operations per biquad sample), as csrc/stages.cu fill_filter prepares it."""
     A, B, Cv, D = tb["A"], tb["B"], tb["C"], tb["D"]
     n = len(x)
+    m = tb["m"]
     s = tb["zi"] * zi_scale
-    starts = np.zeros((n // 32 + 1, tb["m"]))
+    starts = np.zeros((n // 32 + 1, m))
     for i in range(n):
         if i % 32 == 0:
             starts[i // 32] = s
         s = A @ s + B * x[i]
-    A32, B32, C32, D32 = A.astype(np.float32), B.astype(np.float32), Cv.astype(np.float32), np.float32(D)
+    d = 1.0 / B
+    A32 = (d[:, None] * A / d[None, :]).astype(np.float32)
+    C32, D32, d32 = (Cv / d).astype(np.float32), np.float32(D), d.astype(np.float32)
     y = np.zeros(n, np.float32)
     x32 = x.astype(np.float32)
     for c0 in range(0, n, 32):
-        sf = starts[c0 // 32].astype(np.float32)
+        sf = (starts[c0 // 32] * d32.astype(np.float64)).astype(np.float32)
         for i in range(c0, min(c0 + 32, n)):
             acc = np.float32(D32 * x32[i])
-            for k in range(tb["m"] - 1, -1, -1):
+            for k in range(m - 1, -1, -1):
                 acc = np.float32(np.float64(C32[k]) * np.float64(sf[k]) + np.float64(acc))      # fmaf
             y[i] = acc
             sn = np.zeros_like(sf)
-            for r in range(tb["m"]):
-                t = np.float32(B32[r] * x32[i])
-                for k in range(tb["m"]):
+            for r in range(m):
+                t = x32[i]
+                for k in range(m - 1, -1, -1):
                     t = np.float32(np.float64(A32[r, k]) * np.float64(sf[k]) + np.float64(t))   # fmaf
                 sn[r] = t
             sf = sn
