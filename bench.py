@@ -352,6 +352,11 @@ def bench_batch(rt, args, *, chain, mixed, steps, warmup, main, envelope=False):
     # synthetic batch, generated on the device (SURVEY 8d generator), resident in HBM before timing
     src = eng.empty(tracks, 2, n, sr)
     ids = shard.shard_tracks(world * tracks, world, rank)      # track t -> rank t % world
+    if mixed and world > 1:
+        # presets cycle with period 8: plain t % world would hand a whole rank one preset at world = 8 (rank 1 all "edm", 676 B per
+        # frame; rank 0 all "standard", 436) and the step would wait for the heaviest rank.  Rotated round-robin (SURVEY 8e:
+        # "round-robin or size-balanced by track") gives every rank every preset.
+        ids = [t for t in range(world * tracks) if (t + t // world) % world == rank]
     with torch.cuda.stream(eng.stream):
         src.t.zero_()
         synth.torch_batch(ids, sr, dur, eng.tdev, out=src.t, row_stride=src.stride, lead=_lib.MM_LEAD)
@@ -514,6 +519,10 @@ def bench_batch(rt, args, *, chain, mixed, steps, warmup, main, envelope=False):
     peak, peak_src = measured_peak_gbs()
     rows_n = tracks * 2 * n
     roofline = dominant_roofline(tm["ktimes"], steps, rows_n, peak, peak_src)
+    if world > 1:      # bytes of ALL ranks over the slowest rank's time (ranks may hold different presets)
+        tt = torch.tensor([alg_per_frame], dtype=torch.float64, device=eng.tdev)
+        rt.dist.all_reduce(tt)
+        alg_per_frame = float(tt.item()) / world
     chain_gbs = alg_per_frame * tracks * n * world * steps / (ms * 1e-3) / 1e9
     roofline["chain"] = {"algorithmic_bytes_per_stereo_frame": alg_per_frame, "achieved": chain_gbs / world, "frac": chain_gbs / world / peak}
     cfg = {"workload": (f"configs[2]: {tracks} synthetic {dur:.0f} s {sr} Hz stereo tracks per GPU, genre presets cycling over the "
