@@ -137,8 +137,9 @@ static int master_impl(mm_ctx* c, const mm_geom* g, int chain, const mm_style* s
     if (c->track_ids_host) {
         int* d_ids;
         MM_TRY(arena(c, SL_TRACKIDS, (size_t)T, &d_ids));
+        // pageable source: staged before the call returns, so no host synchronisation is needed (one would put a bubble between
+        // the chunks of the host pipeline)
         MM_CUDA(cudaMemcpyAsync(d_ids, c->track_ids_host + g->track_base, (size_t)T * sizeof(int), cudaMemcpyHostToDevice, c->stream));
-        MM_CUDA(cudaStreamSynchronize(c->stream));
         c->track_ids_dev = d_ids;
     }
 
@@ -383,6 +384,7 @@ void mm_ctx_destroy(mm_ctx* c) {
         cudaFree(kv.second.bnd); cudaFree(kv.second.tile_seg); cudaFree(kv.second.blk_lo); cudaFree(kv.second.blk_hi);
     }
     for (auto& k : c->ktimes) { cudaEventDestroy(k.a); cudaEventDestroy(k.b); }
+    for (Slot& hp : c->host_pin) if (hp.p) cudaFreeHost(hp.p);
     if (c->h2d_stream) cudaStreamDestroy(c->h2d_stream);
     if (c->d2h_stream) cudaStreamDestroy(c->d2h_stream);
     if (c->own_stream) cudaStreamDestroy(c->stream);
@@ -396,6 +398,7 @@ int mm_ctx_release_workspace(mm_ctx* c) {
     for (int i = 0; i < SL_COUNT; ++i)
         if (c->slots[i].p) { cudaFree(c->slots[i].p); c->slots[i].p = nullptr; c->slots[i].cap = 0; }
     c->workspace_bytes = 0;
+    for (Slot& hp : c->host_pin) { if (hp.p) cudaFreeHost(hp.p); hp.p = nullptr; hp.cap = 0; }
     for (auto& kv : c->lufs_plans) { cudaFree(kv.second.bnd); cudaFree(kv.second.tile_seg); cudaFree(kv.second.blk_lo); cudaFree(kv.second.blk_hi); }
     c->lufs_plans.clear();
     return 0;
@@ -1014,58 +1017,67 @@ int mm_dev_master_slice(mm_ctx* c, const mm_geom* g, int chain, const mm_style* 
     return rc;
 }
 
-// Host-buffer entry point.  The batch is cut into chunks of tracks that flow through a three-stage pipeline --
+// Host-buffer entry points.  The call is cut into CHUNKS of equally-shaped tracks that flow through a three-stage pipeline --
 // host->device copy (copy stream), mastering chain (context stream), device->host copy (second copy stream) -- so
 // that on a PCIe-attached GPU the call costs about max(copy in, compute, copy out) instead of their sum.  Staging
-// buffers are double-buffered per direction; the chain's own workspace is sized for one chunk.  Results do not
-// depend on the chunking: the dither counter is keyed by the track's index in the whole call.
-static int master_host_impl(mm_ctx* c, int chain, int32_t tracks, int64_t n, int32_t channels, int32_t sr, const mm_style* styles,
-                            const float* audio_in, const int16_t* pcm16_in, float* audio_out, int16_t* pcm16_out,
-                            const float* noise_host, uint64_t seed, mm_track_stats* stats_host, uint32_t flags) {
-    mm_geom g;
-    g.n = n; g.stride = mm_row_stride(n); g.tracks = tracks; g.channels = channels; g.sr = sr; g.track_base = 0;
-    MM_TRY(check_geom(&g));
-    if (!audio_in && !pcm16_in) { set_error("mm_master_host: the input buffer is null"); return 1; }
-    const size_t in_elem = pcm16_in ? sizeof(int16_t) : sizeof(float);
+// buffers are double-buffered per direction; the chain's own workspace is sized for the largest chunk.  Results do not
+// depend on the chunking: the dither counter is keyed by the track's index in the whole call (or its explicit id).
+// A chunk carries its own geometry, and every track its own host pointers: the equal-shape entry points hand in one contiguous
+// buffer (consecutive tracks merge into one cudaMemcpyAsync), mm_master_host_jobs a list of uploads of different shapes.
+struct HostTrack {
+    const void* in;           // float32 or int16 interleaved frames of this track
+    float* out_f32;           // may be null
+    int16_t* out_pcm;         // may be null
+    const float* noise;       // may be null
+};
+struct HostChunk { int t0, tn; int64_t n; int32_t channels, sr; };      // tracks [t0, t0 + tn) of the plan
+
+static int master_host_plan(mm_ctx* c, int chain, const std::vector<HostChunk>& chunks, const std::vector<HostTrack>& trk, bool pcm_in,
+                            const mm_style* styles, uint64_t seed, mm_track_stats* stats_host, uint32_t flags, bool stage_in = false) {
+    const int nchunks = (int)chunks.size(), tracks = (int)trk.size();
+    if (nchunks == 0) return 0;
+    const size_t in_elem = pcm_in ? sizeof(int16_t) : sizeof(float);
     if (!c->h2d_stream) MM_CUDA(cudaStreamCreateWithFlags(&c->h2d_stream, cudaStreamNonBlocking));
     if (!c->d2h_stream) MM_CUDA(cudaStreamCreateWithFlags(&c->d2h_stream, cudaStreamNonBlocking));
-    const size_t per_track = (size_t)n * channels;                  // interleaved samples of one track
-    int tc = 0;                                                     // tracks per chunk: ~256 MB of float32 input.  Measured (64 x 180 s,
-                                                                    // float32 / PCM_16 in): 2 tracks 140 / 173 k audio-s/s, 4: 138 / 189 k,
-                                                                    // 8: 131 / 188 k, 16: 118 / 168 k -- short pipeline fill against small grids
-    if (const char* e = getenv("MM_HOST_CHUNK")) tc = atoi(e);
-    if (tc <= 0) tc = (int)std::max<size_t>(1, ((size_t)256 << 20) / std::max<size_t>(per_track * sizeof(float), 1));
-    tc = std::min(tc, (int)tracks);
-    // chunk plan: full chunks of tc tracks, with short chunks at both ends (1, 2, ... tracks) so that the pipeline's fill (the
-    // first copy-in before any compute) and drain (the last chunk's chain + copy-out after the last copy-in) cost one track
-    // instead of one full chunk.  MM_HOST_RAMP=0 switches the ramps off.
-    std::vector<int> c0, cn;
-    {
-        std::vector<int> head, tail;
-        int rem = tracks;
-        const char* er = getenv("MM_HOST_RAMP");
-        const bool ramp = !(er && atoi(er) == 0);
-        for (int s = 1; ramp && s < tc && rem >= 2 * s + tc; s *= 2) { head.push_back(s); tail.push_back(s); rem -= 2 * s; }
-        std::vector<int> sizes(head);
-        while (rem > 0) { const int s = std::min(tc, rem); sizes.push_back(s); rem -= s; }
-        for (size_t i = tail.size(); i-- > 0;) sizes.push_back(tail[i]);
-        int t0 = 0;
-        for (int s : sizes) { c0.push_back(t0); cn.push_back(s); t0 += s; }
+    bool any_noise = false, any_f32 = false, any_pcm = false;
+    for (const HostTrack& t : trk) { any_noise |= t.noise != nullptr; any_f32 |= t.out_f32 != nullptr; any_pcm |= t.out_pcm != nullptr; }
+    size_t cframes = 0, pfloats = 0;                               // staging sizes: the largest chunk
+    for (const HostChunk& ch : chunks) {
+        mm_geom gc;
+        gc.n = ch.n; gc.stride = mm_row_stride(ch.n); gc.tracks = ch.tn; gc.channels = ch.channels; gc.sr = ch.sr; gc.track_base = 0;
+        MM_TRY(check_geom(&gc));
+        cframes = std::max(cframes, (size_t)ch.tn * (size_t)ch.n * ch.channels);
+        pfloats = std::max(pfloats, batch_floats(&gc));
     }
-    const int nchunks = (int)c0.size();
-    const size_t cframes = (size_t)tc * per_track;
     float *il[2] = {nullptr, nullptr}, *ol[2] = {nullptr, nullptr}, *nz[2] = {nullptr, nullptr}, *pl = nullptr;
     int16_t* pcm[2] = {nullptr, nullptr};
     mm_track_stats* st = nullptr;
-    mm_geom gc = g;
-    gc.tracks = tc;
     MM_TRY(arena(c, SL_STAGE_IL, cframes, &il[0]));
     if (nchunks > 1) MM_TRY(arena(c, SL_STAGE_IL1, cframes, &il[1]));
-    MM_TRY(arena(c, SL_STAGE_PL, batch_floats(&gc), &pl));
-    if (pcm16_out) { MM_TRY(arena(c, SL_STAGE_PCM, cframes, &pcm[0])); if (nchunks > 1) MM_TRY(arena(c, SL_STAGE_PCM1, cframes, &pcm[1])); }
-    if (noise_host) { MM_TRY(arena(c, SL_STAGE_NOISE, cframes, &nz[0])); if (nchunks > 1) MM_TRY(arena(c, SL_STAGE_NOISE1, cframes, &nz[1])); }
-    if (audio_out) { MM_TRY(arena(c, SL_STAGE_OL, cframes, &ol[0])); if (nchunks > 1) MM_TRY(arena(c, SL_STAGE_OL1, cframes, &ol[1])); }
+    MM_TRY(arena(c, SL_STAGE_PL, pfloats, &pl));
+    if (any_pcm) { MM_TRY(arena(c, SL_STAGE_PCM, cframes, &pcm[0])); if (nchunks > 1) MM_TRY(arena(c, SL_STAGE_PCM1, cframes, &pcm[1])); }
+    if (any_noise) { MM_TRY(arena(c, SL_STAGE_NOISE, cframes, &nz[0])); if (nchunks > 1) MM_TRY(arena(c, SL_STAGE_NOISE1, cframes, &nz[1])); }
+    if (any_f32) { MM_TRY(arena(c, SL_STAGE_OL, cframes, &ol[0])); if (nchunks > 1) MM_TRY(arena(c, SL_STAGE_OL1, cframes, &ol[1])); }
     if (stats_host) MM_TRY(arena(c, SL_STATS, (size_t)tracks, &st));
+    // pageable inputs: a cudaMemcpyAsync from pageable memory runs at a few GB/s and holds the calling thread; instead the thread
+    // copies chunk k + 1 into a pinned ring slot (while the device works on chunk k) and the slot crosses PCIe at link speed
+    char *hpin[2] = {nullptr, nullptr}, *hpout[2] = {nullptr, nullptr};       // host_pin 0, 1: inputs; 2, 3: outputs
+    const size_t out_f32_off = any_pcm ? cframes * sizeof(int16_t) : 0;         // an output slot holds the chunk's PCM_16, then its float32
+    const size_t out_bytes = out_f32_off + (any_f32 ? cframes * sizeof(float) : 0);
+    if (stage_in) {
+        for (int i = 0; i < 4; ++i) {
+            if (nchunks == 1 && (i & 1)) continue;
+            Slot& hp = c->host_pin[i];
+            const size_t need = i < 2 ? cframes * in_elem : out_bytes;
+            if (hp.cap < need) {
+                if (hp.p) cudaFreeHost(hp.p);
+                hp.p = nullptr; hp.cap = 0;
+                MM_CUDA(cudaHostAlloc(&hp.p, need, cudaHostAllocDefault));
+                hp.cap = need;
+            }
+            (i < 2 ? hpin[i] : hpout[i - 2]) = reinterpret_cast<char*>(hp.p);
+        }
+    }
 
     std::vector<cudaEvent_t> ev_in(nchunks), ev_deint(nchunks), ev_done(nchunks), ev_out(nchunks);
     for (int k = 0; k < nchunks; ++k) {
@@ -1081,41 +1093,95 @@ static int master_host_impl(mm_ctx* c, int chain, int32_t tracks, int64_t n, int
     MM_CUDA(cudaEventRecord(ev_start, c->stream));
     MM_CUDA(cudaStreamWaitEvent(c->h2d_stream, ev_start, 0));
     MM_CUDA(cudaStreamWaitEvent(c->d2h_stream, ev_start, 0));
+    // one cudaMemcpyAsync per run of tracks whose host buffers lie back to back (the whole chunk, for the equal-shape entry points)
+    auto copy_runs = [&](const HostChunk& ch, size_t elem, auto host_of, auto issue) -> int {
+        const size_t per_track = (size_t)ch.n * ch.channels;
+        for (int a = 0; a < ch.tn;) {
+            const char* h0 = reinterpret_cast<const char*>(host_of(trk[ch.t0 + a]));
+            if (!h0) { ++a; continue; }
+            int b = a + 1;
+            while (b < ch.tn && reinterpret_cast<const char*>(host_of(trk[ch.t0 + b])) == h0 + (size_t)(b - a) * per_track * elem) ++b;
+            if (issue((size_t)a * per_track, h0, (size_t)(b - a) * per_track * elem) != cudaSuccess) { set_error("mm_master_host: copy failed"); return 1; }
+            a = b;
+        }
+        return 0;
+    };
     auto copy_in = [&](int k) -> int {
-        const int t0 = c0[k], tn = cn[k];
-        const size_t off = (size_t)t0 * per_track, cnt = (size_t)tn * per_track;
+        const HostChunk& ch = chunks[k];
         if (k >= 2) MM_CUDA(cudaStreamWaitEvent(c->h2d_stream, ev_deint[k - 2], 0));    // staging buffer k & 1 is free again
-        const void* hsrc = pcm16_in ? (const void*)(pcm16_in + off) : (const void*)(audio_in + off);
-        MM_CUDA(cudaMemcpyAsync(il[k & 1], hsrc, cnt * in_elem, cudaMemcpyHostToDevice, c->h2d_stream));
-        if (noise_host) {
+        char* dst = reinterpret_cast<char*>(il[k & 1]);
+        if (stage_in) {
+            if (k >= 2) MM_CUDA(cudaEventSynchronize(ev_in[k - 2]));                    // the ring slot has crossed the link
+            const size_t per_track = (size_t)ch.n * ch.channels * in_elem;
+            for (int t = 0; t < ch.tn; ++t) memcpy(hpin[k & 1] + (size_t)t * per_track, trk[ch.t0 + t].in, per_track);
+            MM_CUDA(cudaMemcpyAsync(dst, hpin[k & 1], (size_t)ch.tn * per_track, cudaMemcpyHostToDevice, c->h2d_stream));
+        } else
+        MM_TRY(copy_runs(ch, in_elem, [](const HostTrack& t) { return t.in; }, [&](size_t off, const char* h, size_t bytes) {
+            return cudaMemcpyAsync(dst + off * in_elem, h, bytes, cudaMemcpyHostToDevice, c->h2d_stream); }));
+        if (any_noise) {
             if (k >= 2) MM_CUDA(cudaStreamWaitEvent(c->h2d_stream, ev_done[k - 2], 0));
-            MM_CUDA(cudaMemcpyAsync(nz[k & 1], noise_host + off, cnt * sizeof(float), cudaMemcpyHostToDevice, c->h2d_stream));
+            float* nd = nz[k & 1];
+            MM_TRY(copy_runs(ch, sizeof(float), [](const HostTrack& t) { return (const void*)t.noise; }, [&](size_t off, const char* h, size_t bytes) {
+                return cudaMemcpyAsync(nd + off, h, bytes, cudaMemcpyHostToDevice, c->h2d_stream); }));
         }
         MM_CUDA(cudaEventRecord(ev_in[k], c->h2d_stream));
         return 0;
     };
+    auto drain_out = [&](int k) -> int {                                        // pinned ring slot of chunk k -> the caller's buffers
+        const HostChunk& ch = chunks[k];
+        if (cudaEventSynchronize(ev_out[k]) != cudaSuccess) { set_error("mm_master_host: copy-out failed"); return 1; }
+        const size_t per_track = (size_t)ch.n * ch.channels;
+        for (int t = 0; t < ch.tn; ++t) {
+            const HostTrack& h = trk[ch.t0 + t];
+            if (h.out_pcm) memcpy(h.out_pcm, hpout[k & 1] + (size_t)t * per_track * sizeof(int16_t), per_track * sizeof(int16_t));
+            if (h.out_f32) memcpy(h.out_f32, hpout[k & 1] + out_f32_off + (size_t)t * per_track * sizeof(float), per_track * sizeof(float));
+        }
+        return 0;
+    };
     rc = copy_in(0);
     for (int k = 0; k < nchunks && rc == 0; ++k) {
-        const int t0 = c0[k], tn = cn[k];
-        const size_t off = (size_t)t0 * per_track, cnt = (size_t)tn * per_track;
+        const HostChunk& ch = chunks[k];
         if (k + 1 < nchunks && (rc = copy_in(k + 1)) != 0) break;
-        mm_geom gk = g;
-        gk.tracks = tn;
-        gk.track_base = t0;                                  // index of the chunk's first track in the call (dither counter)
+        mm_geom gk;
+        gk.n = ch.n; gk.stride = mm_row_stride(ch.n); gk.channels = ch.channels; gk.sr = ch.sr;
+        gk.tracks = ch.tn;
+        gk.track_base = ch.t0;                               // index of the chunk's first track in the call (dither counter)
+        bool c_noise = false, c_f32 = false, c_pcm = false;
+        for (int t = 0; t < ch.tn; ++t) { const HostTrack& h = trk[ch.t0 + t]; c_noise |= h.noise != nullptr; c_f32 |= h.out_f32 != nullptr; c_pcm |= h.out_pcm != nullptr; }
         if ((rc = cudaStreamWaitEvent(c->stream, ev_in[k], 0) != cudaSuccess)) { set_error("cudaStreamWaitEvent failed"); break; }
-        if (pcm16_in) { if ((rc = run_layout_pcm16(c, &gk, reinterpret_cast<const int16_t*>(il[k & 1]), pl)) != 0) break; }
+        if (pcm_in) { if ((rc = run_layout_pcm16(c, &gk, reinterpret_cast<const int16_t*>(il[k & 1]), pl)) != 0) break; }
         else if ((rc = mm_dev_deinterleave(c, &gk, il[k & 1], pl)) != 0) break;
         cudaEventRecord(ev_deint[k], c->stream);
         if (k >= 2) cudaStreamWaitEvent(c->stream, ev_out[k - 2], 0);     // pcm / ol staging k & 1 has left the device
-        if ((rc = master_impl(c, &gk, chain, styles + t0, pl, pl, pcm16_out ? pcm[k & 1] : nullptr, noise_host ? nz[k & 1] : nullptr, seed,
-                              st ? st + t0 : nullptr, flags)) != 0) break;
-        if (audio_out && (rc = mm_dev_interleave(c, &gk, pl, ol[k & 1])) != 0) break;
+        if ((rc = master_impl(c, &gk, chain, styles + ch.t0, pl, pl, c_pcm ? pcm[k & 1] : nullptr, c_noise ? nz[k & 1] : nullptr, seed,
+                              st ? st + ch.t0 : nullptr, flags)) != 0) break;
+        if (c_f32 && (rc = mm_dev_interleave(c, &gk, pl, ol[k & 1])) != 0) break;
         cudaEventRecord(ev_done[k], c->stream);
         cudaStreamWaitEvent(c->d2h_stream, ev_done[k], 0);
-        if (audio_out) cudaMemcpyAsync(audio_out + off, ol[k & 1], cnt * sizeof(float), cudaMemcpyDeviceToHost, c->d2h_stream);
-        if (pcm16_out) cudaMemcpyAsync(pcm16_out + off, pcm[k & 1], cnt * sizeof(int16_t), cudaMemcpyDeviceToHost, c->d2h_stream);
+        if (stage_in) {
+            // pageable outputs: the chunk lands in a pinned ring slot; the thread hands it to the caller's buffers one chunk later
+            // (a device->pageable cudaMemcpyAsync would hold the thread until chunk k is done, with chunk k + 1's chain not yet queued)
+            if (k >= 2 && (rc = drain_out(k - 2)) != 0) break;
+            const size_t cnt = (size_t)ch.tn * ch.n * ch.channels;
+            if (c_pcm && cudaMemcpyAsync(hpout[k & 1], pcm[k & 1], cnt * sizeof(int16_t), cudaMemcpyDeviceToHost, c->d2h_stream) != cudaSuccess) rc = 1;
+            if (c_f32 && cudaMemcpyAsync(hpout[k & 1] + out_f32_off, ol[k & 1], cnt * sizeof(float), cudaMemcpyDeviceToHost, c->d2h_stream) != cudaSuccess) rc = 1;
+            if (rc) { set_error("mm_master_host: copy failed"); break; }
+        } else {
+        if (c_f32) {
+            const float* src = ol[k & 1];
+            rc = copy_runs(ch, sizeof(float), [](const HostTrack& t) { return (const void*)t.out_f32; }, [&](size_t off, const char* h, size_t bytes) {
+                return cudaMemcpyAsync(const_cast<char*>(h), src + off, bytes, cudaMemcpyDeviceToHost, c->d2h_stream); });
+        }
+        if (rc == 0 && c_pcm) {
+            const int16_t* src = pcm[k & 1];
+            rc = copy_runs(ch, sizeof(int16_t), [](const HostTrack& t) { return (const void*)t.out_pcm; }, [&](size_t off, const char* h, size_t bytes) {
+                return cudaMemcpyAsync(const_cast<char*>(h), src + off, bytes, cudaMemcpyDeviceToHost, c->d2h_stream); });
+        }
+        }
         cudaEventRecord(ev_out[k], c->d2h_stream);
     }
+    if (stage_in)
+        for (int k = std::max(0, nchunks - 2); k < nchunks && rc == 0; ++k) rc = drain_out(k);
     if (rc == 0 && stats_host) {
         if (cudaMemcpyAsync(stats_host, st, (size_t)tracks * sizeof(mm_track_stats), cudaMemcpyDeviceToHost, c->stream) != cudaSuccess) {
             set_error("copy of the track stats failed");
@@ -1130,6 +1196,51 @@ static int master_host_impl(mm_ctx* c, int chain, int32_t tracks, int64_t n, int
         rc = 1;
     }
     return rc;
+}
+
+// tracks per chunk: ~256 MB of float32 input.  Measured (64 x 180 s, float32 / PCM_16 in): 2 tracks 140 / 173 k audio-s/s,
+// 4: 138 / 189 k, 8: 131 / 188 k, 16: 118 / 168 k -- short pipeline fill against small grids
+static int host_chunk_tracks(size_t per_track) {
+    int tc = 0;
+    if (const char* e = getenv("MM_HOST_CHUNK")) tc = atoi(e);
+    if (tc <= 0) tc = (int)std::max<size_t>(1, ((size_t)256 << 20) / std::max<size_t>(per_track * sizeof(float), 1));
+    return tc;
+}
+
+static int master_host_impl(mm_ctx* c, int chain, int32_t tracks, int64_t n, int32_t channels, int32_t sr, const mm_style* styles,
+                            const float* audio_in, const int16_t* pcm16_in, float* audio_out, int16_t* pcm16_out,
+                            const float* noise_host, uint64_t seed, mm_track_stats* stats_host, uint32_t flags) {
+    mm_geom g;
+    g.n = n; g.stride = mm_row_stride(n); g.tracks = tracks; g.channels = channels; g.sr = sr; g.track_base = 0;
+    MM_TRY(check_geom(&g));
+    if (!audio_in && !pcm16_in) { set_error("mm_master_host: the input buffer is null"); return 1; }
+    const size_t per_track = (size_t)n * channels;                  // interleaved samples of one track
+    const int tc = std::min(host_chunk_tracks(per_track), (int)tracks);
+    // chunk plan: full chunks of tc tracks, with short chunks at both ends (1, 2, ... tracks) so that the pipeline's fill (the
+    // first copy-in before any compute) and drain (the last chunk's chain + copy-out after the last copy-in) cost one track
+    // instead of one full chunk.  MM_HOST_RAMP=0 switches the ramps off.
+    std::vector<HostChunk> chunks;
+    {
+        std::vector<int> head, tail;
+        int rem = tracks;
+        const char* er = getenv("MM_HOST_RAMP");
+        const bool ramp = !(er && atoi(er) == 0);
+        for (int s = 1; ramp && s < tc && rem >= 2 * s + tc; s *= 2) { head.push_back(s); tail.push_back(s); rem -= 2 * s; }
+        std::vector<int> sizes(head);
+        while (rem > 0) { const int s = std::min(tc, rem); sizes.push_back(s); rem -= s; }
+        for (size_t i = tail.size(); i-- > 0;) sizes.push_back(tail[i]);
+        int t0 = 0;
+        for (int s : sizes) { chunks.push_back(HostChunk{t0, s, n, channels, sr}); t0 += s; }
+    }
+    std::vector<HostTrack> trk((size_t)tracks);
+    for (int t = 0; t < tracks; ++t) {
+        const size_t off = (size_t)t * per_track;
+        trk[t].in = pcm16_in ? (const void*)(pcm16_in + off) : (const void*)(audio_in + off);
+        trk[t].out_f32 = audio_out ? audio_out + off : nullptr;
+        trk[t].out_pcm = pcm16_out ? pcm16_out + off : nullptr;
+        trk[t].noise = noise_host ? noise_host + off : nullptr;
+    }
+    return master_host_plan(c, chain, chunks, trk, pcm16_in != nullptr, styles, seed, stats_host, flags);
 }
 
 int mm_master_host(mm_ctx* c, int chain, int32_t tracks, int64_t n, int32_t channels, int32_t sr, const mm_style* styles,
@@ -1164,6 +1275,61 @@ int mm_master_host_pcm16(mm_ctx* c, int chain, int32_t tracks, int64_t n, int32_
 }
 
 // ---- filter design ----------------------------------------------------------------------------
+// A list of uploads of DIFFERENT shapes in one call (what /api/v2/batch receives, routers/mastering.py:855-1037): the jobs are
+// ordered by (rate, channels, frames), runs of equal shape become chunks of up to ~256 MB, and the chunks of all shapes flow through
+// ONE copy-in / chain / copy-out pipeline -- an upload's copy-in overlaps the previous upload's chain even when every upload has its
+// own length (round 1: one blocking call per shape).  Host buffers are the caller's (pinned or pageable), one per job.
+int mm_master_host_jobs(mm_ctx* c, int chain, int32_t njobs, mm_host_job* jobs, uint64_t seed, uint32_t flags) {
+    MM_API_BEGIN(c);
+    if (njobs < 0 || (njobs > 0 && !jobs)) { set_error("mm_master_host_jobs: bad job list"); return 1; }
+    if (njobs == 0) return 0;
+    bool pcm_in = jobs[0].pcm16_in != nullptr;
+    for (int j = 0; j < njobs; ++j) {
+        const mm_host_job& b = jobs[j];
+        if ((b.audio_in != nullptr) == (b.pcm16_in != nullptr)) { set_error("mm_master_host_jobs: job %d needs exactly one of audio_in / pcm16_in", j); return 1; }
+        if ((b.pcm16_in != nullptr) != pcm_in) { set_error("mm_master_host_jobs: float32 and PCM_16 inputs cannot be mixed in one call"); return 1; }
+        if (b.n <= 0 || (b.channels != 1 && b.channels != 2) || b.sr <= 0) { set_error("mm_master_host_jobs: job %d has a bad shape", j); return 1; }
+    }
+    std::vector<int> order((size_t)njobs);
+    for (int j = 0; j < njobs; ++j) order[j] = j;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
+        const mm_host_job &x = jobs[a], &y = jobs[b];
+        if (x.sr != y.sr) return x.sr < y.sr;
+        if (x.channels != y.channels) return x.channels < y.channels;
+        return x.n < y.n;
+    });
+    std::vector<HostChunk> chunks;
+    std::vector<HostTrack> trk((size_t)njobs);
+    std::vector<mm_style> styles((size_t)njobs);
+    std::vector<int32_t> ids((size_t)njobs);
+    std::vector<mm_track_stats> stats((size_t)njobs);
+    for (int p = 0; p < njobs; ++p) {
+        const mm_host_job& b = jobs[order[p]];
+        trk[p].in = pcm_in ? (const void*)b.pcm16_in : (const void*)b.audio_in;
+        trk[p].out_f32 = b.audio_out; trk[p].out_pcm = b.pcm16_out; trk[p].noise = nullptr;
+        styles[p] = b.style;
+        ids[p] = b.dither_id;
+        const int tc = host_chunk_tracks((size_t)b.n * b.channels);
+        if (!chunks.empty() && chunks.back().n == b.n && chunks.back().channels == b.channels && chunks.back().sr == b.sr && chunks.back().tn < tc)
+            chunks.back().tn += 1;
+        else
+            chunks.push_back(HostChunk{p, 1, b.n, b.channels, b.sr});
+    }
+    bool pageable = false;
+    for (int p = 0; p < njobs && !pageable; ++p) {
+        cudaPointerAttributes at;
+        if (cudaPointerGetAttributes(&at, trk[p].in) != cudaSuccess) { cudaGetLastError(); pageable = true; }
+        else pageable = at.type == cudaMemoryTypeUnregistered;
+    }
+    c->track_ids_host = ids.data();
+    const int rc = master_host_plan(c, chain, chunks, trk, pcm_in, styles.data(), seed, stats.data(), flags, pageable);
+    c->track_ids_host = nullptr;
+    c->track_ids_dev = nullptr;
+    if (rc == 0)
+        for (int p = 0; p < njobs; ++p) jobs[order[p]].stats = stats[p];
+    return rc;
+}
+
 int mm_design_butter(int order, int btype, const double* wn, double* b, double* a) {
     Ba f;
     memset(&f, 0, sizeof(f));

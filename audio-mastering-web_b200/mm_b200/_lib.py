@@ -31,6 +31,13 @@ class TrackStats(C.Structure):
                 ("peak_in", C.c_double), ("peak_out", C.c_double), ("mean", C.c_double * 2), ("nonfinite", C.c_double)]
 
 
+class HostJob(C.Structure):
+    """mm_host_job: one upload of mm_master_host_jobs (its own shape, host buffers, style and dither stream)."""
+    _fields_ = [("n", C.c_int64), ("channels", C.c_int32), ("sr", C.c_int32), ("audio_in", C.c_void_p), ("pcm16_in", C.c_void_p),
+                ("audio_out", C.c_void_p), ("pcm16_out", C.c_void_p), ("style", Style), ("dither_id", C.c_int32),
+                ("reserved", C.c_int32), ("stats", TrackStats)]
+
+
 class KTime(C.Structure):
     _fields_ = [("name", C.c_char * 48), ("ms", C.c_double), ("launches", C.c_int64), ("samples", C.c_double)]
 
@@ -117,6 +124,7 @@ SIGNATURES = {
                                   C.POINTER(TrackStats), _u32]),
     "mm_master_host_ids": (_i, [_vp, _i, C.c_int32, _i64, C.c_int32, C.c_int32, C.POINTER(Style), _vp, _vp, _vp, _vp, _u64,
                                 C.POINTER(TrackStats), _u32, C.POINTER(C.c_int32)]),
+    "mm_master_host_jobs": (_i, [_vp, _i, C.c_int32, C.POINTER(HostJob), _u64, _u32]),
     "mm_host_alloc": (_i, [C.POINTER(_vp), _i64]),
     "mm_host_free": (_i, [_vp]),
     "mm_ctx_workspace_bytes": (_i64, [_vp]),

@@ -751,22 +751,15 @@ def master_batch(tracks, sr, styles, targets=None, chain="v2", want_int16=False,
     return res
 
 
-def _shape_groups(shapes):
-    """Indices of equally-shaped items, groups in order of first appearance."""
-    groups = {}
-    for i, sh in enumerate(shapes):
-        groups.setdefault(sh, []).append(i)
-    return list(groups.items())
-
-
 def master_wav_jobs(wavs, styles, targets=None, chain="v2", seed=0, eng: Optional[Engine] = None) -> list:
     """Additive, job level: what ``_run_mastering_job(_v2)`` does per upload (routers/mastering.py:350-637) -- and what
     ``/api/v2/batch`` (routers/mastering.py:855-1037) does for up to ten uploads one after the other -- for a whole list of PCM_16
-    WAV uploads: decode, master, dither, encode, with the PCM frames crossing PCIe as int16 in both directions
-    (``mm_master_host_ids``).  Uploads may differ in length, channel count and sample rate: they are mastered group by group of
-    equal shape (one pipelined device batch per group), and every track's result -- dither stream included, keyed by the track's
-    index in ``wavs`` -- equals what the same upload gives alone at that index.  Returns a list of dicts ``wav`` (bytes), ``stats``."""
-    import ctypes as C_
+    WAV uploads: decode, master, dither, encode, with the PCM frames crossing PCIe as int16 in both directions.  Uploads may differ
+    in length, channel count and sample rate: ``mm_master_host_jobs`` takes the list as it is (one ``mm_host_job`` per upload, its
+    frames read in place from the WAV bytes), merges runs of equal shape into chunks and sends every chunk through ONE copy-in /
+    chain / copy-out pipeline, so an upload's transfer overlaps its neighbour's chain.  Every track's result -- dither stream
+    included, keyed by the track's index in ``wavs`` -- equals what the same upload gives alone at that index.  Returns a list of
+    dicts ``wav`` (bytes), ``stats``."""
     eng = eng or get_engine()
     metas = [wavio.pcm16_view(w) for w in wavs]
     names = [s if s in STYLE_CONFIGS else "standard" for s in styles]
@@ -774,20 +767,24 @@ def master_wav_jobs(wavs, styles, targets=None, chain="v2", seed=0, eng: Optiona
         targets = [STYLE_CONFIGS[s]["lufs"] for s in names]
     flags = (_lib.FLAG_MEASURE_IN | _lib.FLAG_MEASURE_OUT |
              (_lib.FLAG_ENVELOPE_COMPRESSOR if _compressor_id() == _lib.COMPRESSOR_ENVELOPE else 0))
-    out = [None] * len(wavs)
-    for (n, ch, sr), idx in _shape_groups([m[1:] for m in metas]):
+    jobs = (_lib.HostJob * len(wavs))()
+    keep = []                                                            # the views / result arrays the job list points into
+    for i, (frames, n, ch, sr) in enumerate(metas):
         if n == 0:
             raise ValueError("master_wav_jobs: an upload holds no frames")
-        pcm_in = np.ascontiguousarray(np.stack([metas[i][0] for i in idx]))                # (T, n, ch) int16
-        pcm_out = np.empty_like(pcm_in)
-        arr = (_lib.Style * len(idx))(*[style_struct(STYLE_CONFIGS[names[i]], targets[i]) for i in idx])
-        st = (_lib.TrackStats * len(idx))()
-        ids = (C_.c_int32 * len(idx))(*idx)
-        _lib.check(eng.lib.mm_master_host_ids(eng.ctx, _lib.CHAIN_V1 if chain == "v1" else _lib.CHAIN_V2, len(idx), n, ch, sr, arr, None,
-                                              pcm_in.ctypes.data_as(C_.c_void_p), None, pcm_out.ctypes.data_as(C_.c_void_p), int(seed), st,
-                                              flags, ids))
-        for k, i in enumerate(idx):
-            rec = {f: (list(getattr(st[k], f)) if f == "mean" else getattr(st[k], f)) for f, _ in st[k]._fields_}
-            out[i] = {"wav": wavio.pack_wav_pcm16(pcm_out[k], sr), "stats": rec}
+        src = np.ascontiguousarray(frames)                               # a view of the upload's bytes (no copy) unless it was strided
+        dst = np.empty((n, ch), np.int16)
+        keep.append((src, dst))
+        j = jobs[i]
+        j.n, j.channels, j.sr = n, ch, sr
+        j.pcm16_in, j.pcm16_out = src.ctypes.data, dst.ctypes.data
+        j.style = style_struct(STYLE_CONFIGS[names[i]], targets[i])
+        j.dither_id = i
+    _lib.check(eng.lib.mm_master_host_jobs(eng.ctx, _lib.CHAIN_V1 if chain == "v1" else _lib.CHAIN_V2, len(wavs), jobs, int(seed), flags))
+    out = []
+    for i, (_, dst) in enumerate(keep):
+        st = jobs[i].stats
+        rec = {f: (list(getattr(st, f)) if f == "mean" else getattr(st, f)) for f, _ in st._fields_}
+        out.append({"wav": wavio.pack_wav_pcm16(dst, metas[i][3]), "stats": rec})
     _trim_engine()
     return out

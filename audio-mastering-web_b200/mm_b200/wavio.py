@@ -42,7 +42,7 @@ def unpack_wav(data: bytes):
                 (tag,) = struct.unpack("<H", data[start + 24:start + 26])
             fmt = (tag, ch, sr, bits)
         elif cid == b"data":
-            body = data[start:start + size]
+            body = memoryview(data)[start:start + size]      # no copy: the frames are read in place
         pos = start + size + (size & 1)
     if fmt is None or body is None:
         raise ValueError("WAV stream lacks fmt or data chunk")
@@ -85,7 +85,7 @@ def pcm16_view(data: bytes):
             tag, ch, sr, _, _, bits = _st.unpack("<HHIIHH", data[start:start + 16])
             fmt = (tag, ch, sr, bits)
         elif cid == b"data":
-            body = data[start:start + size]
+            body = memoryview(data)[start:start + size]      # no copy: the frames are read in place
         pos = start + size + (size & 1)
     if fmt is None or body is None or fmt[0] != 1 or fmt[3] != 16:
         raise ValueError("pcm16_view: a PCM_16 WAV is required")

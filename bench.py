@@ -501,7 +501,23 @@ def bench_batch(rt, args, *, chain, mixed, steps, warmup, main, envelope=False):
                            "api": "mm_master_host_pcm16 (PCM_16 frames in and out, widened on the device: the job path of a WAV upload)",
                            "copy_ceiling": world * e_tracks * dur * reps / wall_c16,
                            "frac_of_copy_ceiling": (world * e_tracks * dur * reps / wall16) / (world * e_tracks * dur * reps / wall_c16)}
-        del hin16, hpcm, dpcm
+        # ragged variant (/api/v2/batch, routers/mastering.py:855-1037): the same uploads, no two of the same length, as ONE call
+        rjobs = (_lib.HostJob * e_tracks)()
+        r_audio_s = 0.0
+        for t in range(e_tracks):
+            nt = n - 4410 * t                                    # 180 s, 179.9 s, ... : every upload is a chunk of its own
+            rjobs[t].n, rjobs[t].channels, rjobs[t].sr = nt, 2, sr
+            rjobs[t].pcm16_in, rjobs[t].pcm16_out = hin16[t].data_ptr(), hpcm[t].data_ptr()
+            rjobs[t].style, rjobs[t].dither_id = earr[t], t
+            r_audio_s += nt / sr
+
+        def ragged_step(i):
+            _lib.check(eng.lib.mm_master_host_jobs(eng.ctx, chain_id, e_tracks, rjobs, 299 + i, flags))
+        wall_r = wall_of(ragged_step)
+        e2e["ragged_jobs"] = {"value": world * r_audio_s * reps / wall_r, "unit": UNIT, "uploads_per_step": e_tracks,
+                              "frames": f"{n - 4410 * (e_tracks - 1)} .. {n} (all different)",
+                              "api": "mm_master_host_jobs (one mm_host_job per upload: own length, own pinned PCM_16 buffers)"}
+        del hin16, hpcm, dpcm, rjobs
         # single-job latency through the Python drop-in (pageable numpy in / out, one 180 s track), rank 0
         if rank == 0 and not args.no_cpu:
             x1 = synth.numpy_track(1000, sr, dur)

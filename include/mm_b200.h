@@ -308,6 +308,27 @@ int mm_master_host_ids(mm_ctx*, int chain, int32_t tracks, int64_t n, int32_t ch
                        const float* audio_in, const int16_t* pcm16_in, float* audio_out, int16_t* pcm16_out, uint64_t dither_seed,
                        mm_track_stats* stats_host, uint32_t flags, const int32_t* track_ids);
 
+/* A list of uploads of DIFFERENT shapes in one call (backend/app/routers/mastering.py:855-1037, /api/v2/batch: up to ten arbitrary
+ * uploads, mastered one after the other by the reference).  Every job names its own frames / channels / rate, its own host buffers
+ * (exactly one of audio_in / pcm16_in; all jobs of a call the same kind; any subset of the outputs), its style and the index of
+ * its dither stream.  The library orders the jobs by shape, merges runs of equal shape into chunks and sends all chunks through ONE
+ * copy-in / chain / copy-out pipeline, so that an upload's transfer overlaps its neighbour's chain even when no two uploads are
+ * alike.  A job's result equals what the same upload gives alone with the same dither_id.  stats is written per job. */
+typedef struct mm_host_job {
+    int64_t n;
+    int32_t channels;
+    int32_t sr;
+    const float* audio_in;      /* (n, channels) interleaved float32, or NULL */
+    const int16_t* pcm16_in;    /* (n, channels) interleaved PCM_16 (widened on the device: x / 32768), or NULL */
+    float* audio_out;           /* may be NULL */
+    int16_t* pcm16_out;         /* may be NULL */
+    mm_style style;
+    int32_t dither_id;
+    int32_t reserved;
+    mm_track_stats stats;       /* out */
+} mm_host_job;
+int mm_master_host_jobs(mm_ctx*, int chain, int32_t njobs, mm_host_job* jobs, uint64_t dither_seed, uint32_t flags);
+
 /* Pinned host memory for the host-buffer entry point (cudaMallocHost / cudaFreeHost). */
 int mm_host_alloc(void** out, int64_t bytes);
 int mm_host_free(void* p);
