@@ -1366,6 +1366,24 @@ int mm_design_k_weighting(int stage, double rate, double* b, double* a) {
     return 0;
 }
 
+// The K-weighting high-pass as the state-variable filter the loudness kernel runs (host-side verification, tests/):
+// fqg = (f, q, g); abcd = A (2x2, row-major), B (2), C (2), D of  s[n] = A s[n-1] + B x[n],  y[n] = C s[n-1] + D x[n],  s = (lp, bp).
+int mm_design_svf_highpass(const double* b, const double* a, double* fqg, double* abcd) {
+    if (!b || !a || !fqg || !abcd || a[0] == 0.0) { set_error("mm_design_svf_highpass: bad arguments"); return 1; }
+    Ba f;
+    f.m = 2;
+    for (int i = 0; i < 3; ++i) { f.b[i] = b[i] / a[0]; f.a[i] = a[i] / a[0]; }
+    StateSpace ss;
+    if (!svf_highpass_realization(f, &ss, &fqg[0], &fqg[1], &fqg[2])) {
+        set_error("mm_design_svf_highpass: not a high-pass with a double zero at z = 1 (b = g [1, -2, 1], 1 + a1 + a2 > 0)");
+        return 1;
+    }
+    for (int i = 0; i < 4; ++i) abcd[i] = (double)ss.A[i];
+    for (int i = 0; i < 2; ++i) { abcd[4 + i] = (double)ss.B[i]; abcd[6 + i] = (double)ss.C[i]; }
+    abcd[8] = (double)ss.D;
+    return 0;
+}
+
 // Scan tables of a section, for host-side verification of the tile decomposition (tests/):
 // returns the look-back window W; g[kS*m], Pw[5*m*m], Plane[32*m*m], Qpow[(kNW+1)*m*m],
 // Mpow[cap_w*m*m] (first min(W, cap_w) powers), Apow[(kS+1)*m*m], zi[m].

@@ -135,8 +135,8 @@ const KwPlan* get_kw_plan(mm_ctx* c, int sr) {
     KwPlan p;
     StateSpace s0, s1, cas;
     const Ba f0 = k_weighting_stage(0, (double)sr), f1 = k_weighting_stage(1, (double)sr);
-    if (!balanced_realization(f0, &s0, nullptr) || !balanced_realization(f1, &s1, nullptr)) {
-        set_error("K-weighting at %d Hz: balanced realization failed", sr);
+    if (!balanced_realization(f0, &s0, nullptr) || !svf_highpass_realization(f1, &s1, &p.hp_f, &p.hp_q, &p.hp_g)) {
+        set_error("K-weighting at %d Hz: realization of the sections failed", sr);
         return nullptr;
     }
     cascade_realization(s0, s1, &cas);

@@ -48,9 +48,10 @@ struct FilterPlan {
 };
 
 struct KwPlan {                 // K-weighting cascade (shelf -> high-pass) of one sample rate as a 4-state system
-    ScanTables tabs;            // tables of the cascade in [balanced shelf; balanced high-pass] coordinates, 32-sample chunks
+    ScanTables tabs;            // tables of the cascade in [balanced shelf; state-variable high-pass (lp, bp)] coordinates, 32-sample chunks
     ScanTables tabs64;          // the same for 64-sample chunks (the loudness kernel's default)
-    ScanTables sec[2];          // the two sections' balanced realizations (A, B, C, D used)
+    ScanTables sec[2];          // the two sections' realizations (A, B, C, D used): balanced shelf, state-variable high-pass
+    double hp_f = 0, hp_q = 0, hp_g = 0;   // the high-pass as a Chamberlin state-variable filter (design.h)
     double* dev = nullptr;      // Tab<4> of `tabs`
     double* plane64 = nullptr;  // tabs64.Plane ([32][16]) on the device
 };

@@ -266,6 +266,30 @@ void df2t_realization(const Ba& f, StateSpace* out) {
     out->D = (long double)f.b[0];
 }
 
+bool svf_highpass_realization(const Ba& ba, StateSpace* out, double* f_out, double* q_out, double* g_out) {
+    if (ba.m != 2) return false;
+    const long double g = ba.b[0];
+    if (g == 0.0L || std::fabs((double)(ba.b[1] + 2.0L * g)) > 1e-12 * std::fabs((double)g) ||
+        std::fabs((double)(ba.b[2] - g)) > 1e-12 * std::fabs((double)g))
+        return false;
+    const long double f2 = 1.0L + (long double)ba.a[1] + (long double)ba.a[2];
+    if (!(f2 > 0.0L)) return false;
+    const long double f = std::sqrt(f2), q = (1.0L - (long double)ba.a[2]) / f;
+    StateSpace r;
+    r.m = 2;
+    // s[n] = A s[n-1] + B x[n], y[n] = C s[n-1] + D x[n] with s = (lp, bp)
+    r.A[0] = 1.0L;  r.A[1] = f;
+    r.A[2] = -f;    r.A[3] = 1.0L - f * (f + q);
+    r.B[0] = 0.0L;  r.B[1] = f;
+    r.C[0] = -g;    r.C[1] = -g * (f + q);
+    r.D = g;
+    *out = r;
+    if (f_out) *f_out = (double)f;
+    if (q_out) *q_out = (double)q;
+    if (g_out) *g_out = (double)g;
+    return true;
+}
+
 void cascade_realization(const StateSpace& s1, const StateSpace& s2, StateSpace* out) {
     const int m1 = s1.m, m2 = s2.m, m = m1 + m2;
     StateSpace r;
@@ -486,6 +510,22 @@ bool build_scan_tables_ss(const StateSpace& ss, int S, int T, ScanTables* out, i
     }
     if (W >= max_window) return false;   // pole too close to the unit circle for this tile size
     out->W = W;
+    // the same criterion at warp-tile granularity: first j with every entry of (A^(32 S))^j AND of the next power below 1e-18
+    // (an entry of a rotating state-transfer matrix may pass through zero; two consecutive powers cannot both by accident)
+    {
+        long double Y[kMaxOrder * kMaxOrder];
+        mat_eye(m, Y);
+        int wq = 0, below = 0;
+        for (int j = 0; j <= W * NW + 1; ++j) {
+            long double mx = 0.0L;
+            for (int i = 0; i < mm2; ++i) mx = fmaxl(mx, fabsl(Y[i]));
+            below = (j > 0 && mx < 1e-18L) ? below + 1 : 0;
+            if (below == 2) { wq = j - 1; break; }
+            wq = j;
+            mat_mul(m, Y, Q, Y);
+        }
+        out->Wq = std::max(1, std::min(wq, W * NW));
+    }
     if (out->Wh == 0) out->Wh = W;
     for (int i = 0; i < m; ++i) out->zi[i] = 0.0;
     // spectral radius estimate from M's decay: r ~ (max|M|)^(1/L)

@@ -51,6 +51,12 @@ void df2t_realization(const Ba& f, StateSpace* out);
 // the round-off noise gain of a float32 state update is O(1) instead of O(1/(1-r)^2) for DF2T.  T (m x m,
 // row-major) maps DF2T states into the balanced coordinates, s_bal = T z.  False if the section is not minimal.
 bool balanced_realization(const Ba& f, StateSpace* out, long double* T);
+// A high-pass biquad b = g [1, -2, 1] as a Chamberlin state-variable filter, state (lp, bp):
+//   lp' = lp + f bp;   hp = x - lp' - q bp;   bp' = bp + f hp;   y = g hp        (f^2 = 1 + a1 + a2,  f q = 1 - a2)
+// -- four float32 operations per sample where the balanced realization needs seven, with states of the signal's own magnitude
+// (the low-passed input and a band-pass of gain ~1/q), so a float32 update loses ~1e-7 of the SIGNAL per step instead of ~1e-7 of
+// a state that is 1/(1-r) times larger as in DF2T.  False if the numerator is not a double zero at z = 1 or f^2 <= 0.
+bool svf_highpass_realization(const Ba& f, StateSpace* out, double* f_out, double* q_out, double* g_out);
 // y2(y1(x)): state [s1; s2]
 void cascade_realization(const StateSpace& s1, const StateSpace& s2, StateSpace* out);
 
@@ -64,6 +70,8 @@ struct ScanTables {
     int S = 0, T = 0;                   // samples per thread, threads per tile
     int W = 0;                          // look-back window (tiles) after which A^(L*W) < 1e-18
     int Wh = 0;                         // halo length (tiles): every entry of A^(L*Wh) below 1e-13
+    int Wq = 0;                         // the 1e-18 look-back window counted in WARP-tiles of 32 S samples (<= W * T / 32): what a
+                                        // warp-autonomous kernel re-reads before a segment
     std::vector<double> g;              // [S][m]      g[j] = A^(S-1-j) B
     std::vector<double> Pw;             // [5][m*m]    (A^S)^(2^d)
     std::vector<double> Plane;          // [32][m*m]   (A^S)^l

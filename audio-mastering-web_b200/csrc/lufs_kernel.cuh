@@ -14,6 +14,7 @@
 // accumulators (integer atomics are associative, so the loudness -- and the gain derived from it -- is
 // bit-reproducible).
 #pragma once
+#include <cooperative_groups.h>
 #include "sweep4.cuh"
 
 namespace mm {
@@ -30,10 +31,12 @@ struct LufsArgs {
     float2 Pw2[5][4][2];     // (A^S)^(2^d)
     float2 Q1[4][2];         // A^(32 S): carries a state across one warp-tile
     // pass 2.  The shelf as a float32 DF2T section: b, negated a1 / a2, and the map from the balanced state to the DF2T state.
-    // The high-pass in its balanced realization with the states rescaled so that B = (1, 1) (floating-point round-off is scale
-    // invariant): y = C s + D u, s' = A s + (u, u) -- 7 operations; hp_d maps the balanced state into the rescaled one.
+    // The high-pass (b = g [1, -2, 1]) as a Chamberlin state-variable filter on the scan's states (lp, bp):
+    //   lp += f bp;  hp = (u - lp) - q bp;  bp += f hp  -- 4 operations (the balanced realization needed 7); its gain g is applied
+    // to the hop sums (g^2, in float64) instead of to every sample.
     float sh_b[3], sh_na[2], shT[2][2];
-    float hpA[2][2], hpC[2], hpD, hp_d[2];
+    float hp_f, hp_nq;
+    double hp_g2;
     const float* in;
     long long n, stride;
     int rows, ntiles, channels;   // ntiles, seglen, whalo: in WARP-tiles of 1024 samples
@@ -207,16 +210,15 @@ __global__ void __launch_bounds__(kT, LufsCfg<S>::kMinBlocks) lufs_kernel(const 
             // operations -- from the scan's state mapped into DF2T coordinates; the 38 Hz high-pass (poles at 0.995) keeps its
             // balanced realization (9 operations).  Every chunk restarts from the scan-resolved state, so round-off lives 32 samples.
             float zs0 = fmaf(P.shT[0][0], z[0], P.shT[0][1] * z[1]), zs1 = fmaf(P.shT[1][0], z[0], P.shT[1][1] * z[1]);
-            float sb0 = P.hp_d[0] * z[2], sb1 = P.hp_d[1] * z[3];
+            float lp = z[2], bp = z[3];
             auto kweight = [&](float x) -> float {
                 const float u = fmaf(P.sh_b[0], x, zs0);                                   // shelf, DF2T
                 zs0 = fmaf(P.sh_b[1], x, fmaf(P.sh_na[0], u, zs1));
                 zs1 = fmaf(P.sh_b[2], x, P.sh_na[1] * u);
-                const float y = fmaf(P.hpC[0], sb0, fmaf(P.hpC[1], sb1, P.hpD * u));       // high-pass, balanced states rescaled to B = (1, 1)
-                const float m0 = fmaf(P.hpA[0][0], sb0, fmaf(P.hpA[0][1], sb1, u));
-                const float m1 = fmaf(P.hpA[1][0], sb0, fmaf(P.hpA[1][1], sb1, u));
-                sb0 = m0; sb1 = m1;
-                return y;
+                lp = fmaf(P.hp_f, bp, lp);                                                 // high-pass, state-variable form (y / g)
+                const float hp = fmaf(P.hp_nq, bp, u - lp);
+                bp = fmaf(P.hp_f, hp, bp);
+                return hp;
             };
             float a0 = 0.f, a1 = 0.f, a2 = 0.f;                // sums of this lane's squares in hops hs, hs + 1, hs + 2
             if (fast) {
@@ -277,10 +279,11 @@ __global__ void __launch_bounds__(kT, LufsCfg<S>::kMinBlocks) lufs_kernel(const 
                 for (int o = 16; o > 0; o >>= 1) { a1 += __shfl_xor_sync(0xffffffffu, a1, o); a2 += __shfl_xor_sync(0xffffffffu, a2, o); }
             }
             if (lane == 0) {
-                if (hs < P.nhop && a0 != 0.f) atomicAdd(dst + hs, (unsigned long long)__double2ll_rn((double)a0 * kSqScale));
+                const double sc = P.hp_g2 * kSqScale;                  // the high-pass gain squared and the fixed-point scale
+                if (hs < P.nhop && a0 != 0.f) atomicAdd(dst + hs, (unsigned long long)__double2ll_rn((double)a0 * sc));
                 if (!fast) {
-                    if (hs + 1 < P.nhop && a1 != 0.f) atomicAdd(dst + hs + 1, (unsigned long long)__double2ll_rn((double)a1 * kSqScale));
-                    if (hs + 2 < P.nhop && a2 != 0.f) atomicAdd(dst + hs + 2, (unsigned long long)__double2ll_rn((double)a2 * kSqScale));
+                    if (hs + 1 < P.nhop && a1 != 0.f) atomicAdd(dst + hs + 1, (unsigned long long)__double2ll_rn((double)a1 * sc));
+                    if (hs + 2 < P.nhop && a2 != 0.f) atomicAdd(dst + hs + 2, (unsigned long long)__double2ll_rn((double)a2 * sc));
                 }
             }
         }
@@ -356,6 +359,78 @@ __global__ void __launch_bounds__(256) gate_kernel(const GateArgs P) {
             if (P.valid) {
                 gdb = P.target[track] - lufs;
                 gdb = fmin(fmax(gdb, -20.0), 20.0);      // np.clip; +inf (silence) -> +20
+                g = pow(10.0, gdb / 20.0);
+            }
+            if (P.gain_row) for (int c = 0; c < C; ++c) P.gain_row[track * C + c] = g;
+            if (P.gain_db) P.gain_db[track] = gdb;
+        }
+    }
+}
+
+// The same gating for LONG signals (a two-hour file has 72 000 blocks: one 256-thread CTA walks them in 2 x 281 dependent rounds
+// of L2 loads and float64 logarithms -- 0.53 ms, 11 % of a time slice's step on 8 GPUs).  A thread-block CLUSTER of kGateCluster
+// CTAs x 1024 threads shares the blocks; the per-CTA partial sums meet through distributed shared memory in rank order (fixed
+// order: bit-reproducible), every CTA ends with the same totals, rank 0 writes.  Chosen by the block count alone, so a signal's
+// loudness never depends on what it is batched with.
+constexpr int kGateCluster = 8;
+constexpr int kGateLongThreads = 1024;
+constexpr int kGateLongMinBlocks = 8192;
+
+__global__ void __cluster_dims__(kGateCluster, 1, 1) __launch_bounds__(kGateLongThreads) gate_long_kernel(const GateArgs P) {
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    __shared__ double red[kGateLongThreads / 32];
+    __shared__ double part[2][3];                                 // this CTA's (a0, a1, cnt) of pass 0 / pass 1
+    const int track = blockIdx.x / kGateCluster;
+    const int crank = (int)cluster.block_rank();
+    const int C = P.channels;
+    double lufs;
+    if (!P.valid) {                                               // uniform over the grid: nobody waits at a cluster barrier
+        lufs = __longlong_as_double(0x7ff8000000000000LL);
+    } else {
+        const unsigned long long* s0 = P.segsum + (size_t)(track * C) * P.nseg;
+        const unsigned long long* s1 = s0 + (C > 1 ? P.nseg : 0);
+        const double inv = 1.0 / kSqScale;
+        double gamma_r = 0.0, result = 0.0;
+        for (int pass = 0; pass < 2; ++pass) {
+            double a0 = 0.0, a1 = 0.0, cnt = 0.0;
+#pragma unroll 3
+            for (int j = crank * kGateLongThreads + threadIdx.x; j < P.nblocks; j += kGateCluster * kGateLongThreads) {
+                unsigned long long u0 = 0, u1 = 0;
+                const int lo = __ldg(P.blk_lo + j), hi = __ldg(P.blk_hi + j);
+                for (int s = lo; s < hi; ++s) { u0 += s0[s]; if (C > 1) u1 += s1[s]; }
+                const double z0 = (double)u0 * inv * P.scale, z1 = (double)u1 * inv * P.scale;
+                const double l = -0.691 + 10.0 * log10(z0 + (C > 1 ? z1 : 0.0));
+                const bool keep = pass == 0 ? (l >= -70.0) : (l > gamma_r && l > -70.0);
+                if (keep) { a0 += z0; a1 += z1; cnt += 1.0; }
+            }
+            a0 = block_reduce_sum(a0, red);
+            a1 = block_reduce_sum(a1, red);
+            cnt = block_reduce_sum(cnt, red);
+            if (threadIdx.x == 0) { part[pass][0] = a0; part[pass][1] = a1; part[pass][2] = cnt; }
+            cluster.sync();
+            a0 = a1 = cnt = 0.0;
+            for (int r = 0; r < kGateCluster; ++r) {
+                const double* q = cluster.map_shared_rank(&part[pass][0], r);
+                a0 += q[0]; a1 += q[1]; cnt += q[2];
+            }
+            double m0, m1;
+            if (cnt > 0.0) { m0 = a0 / cnt; m1 = a1 / cnt; }
+            else if (pass == 0) { m0 = m1 = __longlong_as_double(0x7ff8000000000000LL); }
+            else { m0 = m1 = 0.0; }
+            const double v = -0.691 + 10.0 * log10(m0 + (C > 1 ? m1 : 0.0));
+            if (pass == 0) gamma_r = v - 10.0; else result = v;
+        }
+        lufs = result;
+        cluster.sync();                                           // no CTA leaves while its shared memory may still be read
+    }
+    if (crank == 0 && threadIdx.x == 0) {
+        P.lufs[track] = lufs;
+        if (P.target != nullptr) {
+            double g = 1.0, gdb = 0.0;
+            if (P.valid) {
+                gdb = P.target[track] - lufs;
+                gdb = fmin(fmax(gdb, -20.0), 20.0);
                 g = pow(10.0, gdb / 20.0);
             }
             if (P.gain_row) for (int c = 0; c < C; ++c) P.gain_row[track * C + c] = g;

@@ -111,7 +111,7 @@ static int launch_sweep2(mm_ctx* c, SweepArgs<M, NF>* As, int whalo, const char*
     constexpr int kSW = Cfg::kSW, kSweepThreads = Cfg::kThreads;
     const int capacity = std::max(1, c->num_sms * blocks_per_sm * kSW);      // warps in flight = independent workers
     Sweep2Args<M, NF, 1> PP;
-    PP.whalo = whalo * (kL / kWT);                   // the tables count look-back windows in 4096-sample tiles
+    PP.whalo = whalo;                                // warp-tiles (ScanTables::Wq)
     choose_segments(A.rows, A.ntiles, PP.whalo, capacity, &PP.nseg, &PP.seglen);
     const long long items = (long long)A.rows * PP.nseg;
     const unsigned grid = (unsigned)std::min<long long>((items + kSW - 1) / kSW, capacity / kSW);
@@ -149,7 +149,9 @@ static int launch_sweep2(mm_ctx* c, SweepArgs<M, NF>* As, int whalo, const char*
 
 static int halo_tiles(const FilterPlan* const* plans, int nf) {
     int w = 1;
-    for (int f = 0; f < nf; ++f) w = std::max(w, plans[f]->tabs.W);   // 1e-18: results do not depend on the segmentation
+    // 1e-18: results do not depend on the segmentation.  Counted in warp-tiles (round 1 and early round 2: in 4096-sample tiles,
+    // i.e. rounded up to a multiple of four warp-tiles -- most sections forget within one or two)
+    for (int f = 0; f < nf; ++f) w = std::max(w, plans[f]->tabs.Wq);
     return w;
 }
 
@@ -367,7 +369,7 @@ int run_row_stats(mm_ctx* c, const mm_geom* g, const float* in, RowStats** st_ou
     }
     // a time slice contributes its own frames only (own_lo is a multiple of 4: the float4 loads stay aligned)
     const long long lo = c->slice ? c->slice->own_lo : 0, cnt = c->slice ? c->slice->own_hi - c->slice->own_lo : g->n;
-    dim3 grid((unsigned)((cnt + kPwFramesPerBlock - 1) / kPwFramesPerBlock), (unsigned)rows);
+    dim3 grid((unsigned)((cnt + kRsFramesPerBlock - 1) / kRsFramesPerBlock), (unsigned)rows);
     {
         KernelScope ks(c, "row_stats");
         row_stats_kernel<<<grid, kPwThreads, 0, c->stream>>>(in + lo, cnt, g->stride, st);
@@ -764,18 +766,10 @@ int st_lufs(mm_ctx* c, const mm_geom* g, const float* in, const Pro& pro, double
             for (int i = 0; i < 3; ++i) A.sh_b[i] = (float)sh.b[i];
             A.sh_na[0] = (float)-a1;
             A.sh_na[1] = (float)-a2;
-            // high-pass: balanced states rescaled by d_i = 1 / B_i, so that B' = (1, 1): A'_ij = d_i A_ij / d_j, C'_j = C_j / d_j
-            const double* Ah = kw->sec[1].A;
-            const double* Bh = kw->sec[1].B;
-            const double* Ch = kw->sec[1].C;
-            if (std::fabs(Bh[0]) < 1e-12 || std::fabs(Bh[1]) < 1e-12) { set_error("K-weighting at %d Hz: degenerate high-pass realization", g->sr); return 1; }
-            const double d[2] = {1.0 / Bh[0], 1.0 / Bh[1]};
-            for (int i = 0; i < 2; ++i) {
-                for (int j = 0; j < 2; ++j) A.hpA[i][j] = (float)(d[i] * Ah[i * 2 + j] / d[j]);
-                A.hpC[i] = (float)(Ch[i] / d[i]);
-                A.hp_d[i] = (float)d[i];
-            }
-            A.hpD = (float)kw->sec[1].D;
+            // high-pass: Chamberlin state-variable form in its own coordinates (lp, bp) -- the scan's states 2, 3 are used as they are
+            A.hp_f = (float)kw->hp_f;
+            A.hp_nq = (float)-kw->hp_q;
+            A.hp_g2 = kw->hp_g * kw->hp_g;
         }
         A.plane = S == 64 ? kw->plane64 : kw->dev + Tab<4>::Plane;
         A.in = in; A.n = g->n; A.stride = g->stride; A.rows = rows; A.channels = g->channels;
@@ -785,7 +779,7 @@ int st_lufs(mm_ctx* c, const mm_geom* g, const float* in, const Pro& pro, double
         A.goff = sl ? sl->global_off : 0;
         A.own_lo = sl ? sl->own_lo : 0;
         A.own_hi = sl ? sl->own_hi : g->n;
-        A.whalo = tb.W * (S * kT / wt);                            // the tables count tiles of S * kT samples
+        A.whalo = tb.Wq;                                           // warp-tiles of 32 S samples
         // every warp is an independent worker: capacity and segments are counted in warps / warp-tiles
         choose_segments(rows, A.ntiles, A.whalo, capacity * kNW, &A.nseg, &A.seglen);
         const long long items = (long long)rows * A.nseg;
@@ -806,7 +800,8 @@ int st_lufs(mm_ctx* c, const mm_geom* g, const float* in, const Pro& pro, double
     G.lufs = lufs_dev; G.target = target_dev; G.gain_row = gain_row; G.gain_db = gain_db;
     {
         KernelScope ks(c, "lufs_gate");
-        gate_kernel<<<g->tracks, 256, 0, c->stream>>>(G);
+        if (lp->nblocks >= kGateLongMinBlocks) gate_long_kernel<<<g->tracks * kGateCluster, kGateLongThreads, 0, c->stream>>>(G);
+        else gate_kernel<<<g->tracks, 256, 0, c->stream>>>(G);
     }
     MM_CUDA(cudaGetLastError());
     return 0;

@@ -133,6 +133,7 @@ SIGNATURES = {
     "mm_design_iirpeak": (_i, [_d, _d, _dp, _dp, C.POINTER(_i), _dp]),
     "mm_design_lfilter_zi": (_i, [_dp, _dp, _i, _dp]),
     "mm_design_k_weighting": (_i, [_i, _d, _dp, _dp]),
+    "mm_design_svf_highpass": (_i, [_dp, _dp, _dp, _dp]),
     "mm_design_scan_tables": (_i, [_dp, _dp, _i, _dp, _dp, _dp, _dp, _dp, _i, _dp, _dp, C.POINTER(_i), C.POINTER(_i)]),
     "mm_design_scan_tables2": (_i, [_dp, _dp, _i, _i, _dp, _dp, _dp, _dp, _dp, _i, _dp, _dp, _dp]),
 }

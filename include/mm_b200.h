@@ -356,6 +356,11 @@ int mm_design_lfilter_zi(const double* b, const double* a, int ncoef, double* zi
 /* pyloudnorm K-weighting stage (0 = high shelf, 1 = high pass) for a sample rate; b[3], a[3]
  * (call sites backend/app/pipeline.py:646-648). */
 int mm_design_k_weighting(int stage, double rate, double* b, double* a);
+/* The K-weighting high-pass (b = g [1, -2, 1]) as the Chamberlin state-variable filter the loudness kernel runs in float32:
+ * lp += f bp; hp = x - lp - q bp; bp += f hp; y = g hp.  fqg[3] = (f, q, g); abcd[9] = A (2x2 row-major), B[2], C[2], D of
+ * s[n] = A s[n-1] + B x[n], y[n] = C s[n-1] + D x[n] with s = (lp, bp).  Host-side verification (tests/); no reference
+ * counterpart: pyloudnorm runs scipy.signal.lfilter on (b, a) (call sites backend/app/pipeline.py:646-648). */
+int mm_design_svf_highpass(const double* b, const double* a, double* fqg, double* abcd);
 /* Tables of the chunked linear-recurrence scan for one section (host-side verification of the
  * tile decomposition in tests/): returns the look-back window W (tiles), <0 on error.
  * g[S*m], Pw[5*m*m], Plane[32*m*m], Qpow[(T/32+1)*m*m], Mpow[cap_w*m*m], Apow[(S+1)*m*m], zi[m];

@@ -63,6 +63,23 @@ def test_lufs_many_blocks_vs_oracle(P):
         assert abs(P.measure_lufs(x, sr) - oc.measure_lufs(x, sr)) <= 1e-3, sr
 
 
+def test_lufs_long_signal_cluster_gate_vs_oracle(P):
+    """A signal with more than 8192 gating blocks takes the thread-block-cluster gate (gate_long_kernel: 8 CTAs, partial sums
+    met through distributed shared memory); 15 minutes with loud, quiet (relatively gated) and silent (absolutely gated) parts."""
+    from oracle import chain as oc
+    sr, sec = 22050, 900
+    rng = np.random.default_rng(7)
+    t = np.arange(sr * sec) / sr
+    env = np.where((t % 60) < 35, 0.25, np.where((t % 60) < 50, 0.004, 0.0))
+    x = (env[:, None] * rng.standard_normal((sr * sec, 2))).astype(np.float32)
+    x[:, 1] *= 0.5
+    a, b = P.measure_lufs(x, sr), oc.measure_lufs(x, sr)
+    assert abs(a - b) <= 1e-4, (a, b)
+    m = P.measure_lufs(np.ascontiguousarray(x[:, 0]), sr)
+    assert abs(m - oc.measure_lufs(np.ascontiguousarray(x[:, 0]), sr)) <= 1e-4
+    assert P.measure_lufs(x, sr) == a                                  # bit-reproducible
+
+
 def test_true_peak_edges_and_intersample(P):
     from oracle import chain as oc
     sr = 44100

@@ -89,6 +89,58 @@ def test_k_weighting_matches_oracle(lib):
             assert np.allclose(np.array(a[:]), ref[stage][1], rtol=1e-13)
 
 
+def test_k_weighting_highpass_as_state_variable_filter(lib):
+    """The loudness kernel runs the K-weighting high-pass as a Chamberlin state-variable filter (4 float32 operations per sample,
+    csrc/lufs_kernel.cuh): the realization has the biquad's transfer function, and its float32 recurrence restarted from the exact
+    state every 64 samples (what the kernel's scan provides) stays within 1e-6 of scipy's float64 lfilter."""
+    import scipy.signal as sg
+    from mm_b200 import _lib
+    rng = np.random.default_rng(3)
+    for sr in (8000, 22050, 44100, 48000, 96000, 192000):
+        b = (C.c_double * 3)()
+        a = (C.c_double * 3)()
+        assert lib.mm_design_k_weighting(1, float(sr), b, a) == 0
+        fqg = (C.c_double * 3)()
+        abcd = (C.c_double * 9)()
+        assert lib.mm_design_svf_highpass(b, a, fqg, abcd) == 0
+        f, q, g = fqg[:]
+        A = np.array(abcd[:4]).reshape(2, 2)
+        B, Cm, D = np.array(abcd[4:6]), np.array(abcd[6:8]), abcd[8]
+        assert np.allclose(A, [[1.0, f], [-f, 1.0 - f * (f + q)]]) and np.allclose(B, [0.0, f])
+        assert np.allclose(Cm, [-g, -g * (f + q)]) and D == g
+        n = 1 << 15
+        x = (0.3 * rng.standard_normal(n) + 0.2 + 0.5 * np.sin(2 * np.pi * 30.0 * np.arange(n) / sr)).astype(np.float32)
+        ref = sg.lfilter(np.array(b[:]), np.array(a[:]), x.astype(np.float64))
+        # float64 state-space replay: same transfer function
+        s = np.zeros(2)
+        y = np.empty(n)
+        S = np.empty((n + 1, 2))
+        S[0] = s
+        xd = x.astype(np.float64)
+        for i in range(n):
+            y[i] = Cm @ s + D * xd[i]
+            s = A @ s + B * xd[i]
+            S[i + 1] = s
+        assert np.max(np.abs(y - ref)) <= 1e-11
+        # the kernel's float32 recurrence, restarted from the exact state every 64 samples
+        f32 = np.float32
+        ff, nq = f32(f), f32(-q)
+        got = np.empty(n)
+        for c0 in range(0, n, 64):
+            lp, bp = f32(S[c0, 0]), f32(S[c0, 1])
+            for i in range(c0, min(n, c0 + 64)):
+                lp = f32(np.float64(ff) * np.float64(bp) + np.float64(lp))           # fmaf: one rounding
+                hp = f32(np.float64(nq) * np.float64(bp) + np.float64(f32(x[i] - lp)))
+                bp = f32(np.float64(ff) * np.float64(hp) + np.float64(bp))
+                got[i] = g * float(hp)
+        assert np.max(np.abs(got - ref)) <= 1e-6, sr
+        assert abs(np.sum(got ** 2) / np.sum(ref ** 2) - 1.0) <= 1e-7
+    # a biquad that is not a double-zero high-pass is refused by name
+    bl, al = sg.butter(2, 0.1)
+    assert lib.mm_design_svf_highpass(_lib.darr(bl), _lib.darr(al), fqg, abcd) != 0
+    assert "double zero" in _lib.last_error()
+
+
 def _tables(lib, b, a):
     from mm_b200 import _lib
     m = len(b) - 1
