@@ -152,6 +152,15 @@ __device__ __forceinline__ int16_t quantize16(float x, double noise) {
     return (int16_t)min(max(q, -32768), 32767);
 }
 
+// The same quantiser for a sample the caller has already cleaned (finite, clipped to +-1): x * 32767 is exact in float64 (24 + 15
+// bits), so ONE fused multiply-add rounds exactly where the product followed by the add does; with |noise| < 1 (TPDF) the sum
+// cannot round below -32768 and only the upper clamp is needed.
+template <bool TPDF> __device__ __forceinline__ int16_t quantize16_clean(float x, double noise) {
+    const double d = fma((double)x, 32767.0, noise);
+    const int q = __double2loint(__dadd_rn(d, 6755399441055744.0));
+    return (int16_t)(TPDF ? min(q, 32767) : min(max(q, -32768), 32767));
+}
+
 // TPDF dither noise (rand + rand - 1.0, pipeline.py:830-832) from counter-based random bits.
 // One Philox4x32-10 call serves TWO frames: each 32-bit word gives one TPDF sample from its two 16-bit halves,
 //   n = (hi16 + lo16) / 65536 - 1  in (-1, 1)   (triangular on a 2^-16 LSB lattice).
@@ -357,12 +366,13 @@ __global__ void __launch_bounds__(kFinThreads, 3) finalize_kernel(const FinalArg
                 if (i + c < P.n) { setcomp4(a[r], c, P.in[r0 + i + c]); if (C > 1) setcomp4(b[r], c, P.in[r1 + i + c]); }
         }
     }
-    double bad = 0.0;
+    int bad = 0;                                             // non-finite samples seen by this thread (at most 32)
 #pragma unroll
     for (int r = 0; r < kFinVec; ++r) {
         const long long i = base + 4LL * (threadIdx.x + kFinThreads * r);
         if (i >= P.n) continue;
         const bool full = i + 3 < P.n;
+        const bool fading = i < P.n_fade;                    // uniform per vector: the 6 ms ramp touches the first CTA of a track only
         int16_t q[8];
         unsigned rnd[4] = {0u, 0u, 0u, 0u};
         float4 nz0 = make_float4(0.f, 0.f, 0.f, 0.f), nz1 = nz0;
@@ -386,13 +396,13 @@ __global__ void __launch_bounds__(kFinThreads, 3) finalize_kernel(const FinalArg
                 rr = fminf(fmaxf(__fsub_rn(mid, side), -1.f), 1.f);
             }
             if (P.nonfinite && i + c < P.n) {
-                if (!(fabsf(l) <= 3.4e38f)) bad += 1.0;
-                if (C > 1 && !(fabsf(rr) <= 3.4e38f)) bad += 1.0;
+                if (!(fabsf(l) <= 3.4e38f)) ++bad;
+                if (C > 1 && !(fabsf(rr) <= 3.4e38f)) ++bad;
             }
             l = __fmul_rn(l, mul0); rr = __fmul_rn(rr, mul1);
             l = (l != l) ? 0.f : fminf(fmaxf(l, -1.f), 1.f);
             rr = (rr != rr) ? 0.f : fminf(fmaxf(rr, -1.f), 1.f);
-            if (i + c < P.n_fade) {
+            if (fading && i + c < P.n_fade) {
                 const float ramp = (i + c == P.n_fade - 1) ? 1.f : (float)((double)(i + c) * P.fade_step);
                 l = __fmul_rn(l, ramp); rr = __fmul_rn(rr, ramp);
             }
@@ -412,8 +422,8 @@ __global__ void __launch_bounds__(kFinThreads, 3) finalize_kernel(const FinalArg
                     n0 = tpdf16(rnd[(c & 1) * 2]);
                     n1 = tpdf16(rnd[(c & 1) * 2 + 1]);
                 }
-                q[c * C] = quantize16(l, n0);
-                if (C > 1) q[c * C + 1] = quantize16(rr, n1);
+                q[c * C] = quantize16_clean<!NOISE>(l, n0);           // l, rr are finite and within +-1 here
+                if (C > 1) q[c * C + 1] = quantize16_clean<!NOISE>(rr, n1);
             }
         }
         if (full) {
@@ -440,8 +450,8 @@ __global__ void __launch_bounds__(kFinThreads, 3) finalize_kernel(const FinalArg
     }
     if (P.nonfinite) {
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) bad += shfl_xor_d(bad, o);
-        if ((threadIdx.x & 31) == 0 && bad > 0.0) atomicAdd(P.nonfinite + track, bad);
+        for (int o = 16; o > 0; o >>= 1) bad += __shfl_xor_sync(0xffffffffu, bad, o);
+        if ((threadIdx.x & 31) == 0 && bad > 0) atomicAdd(P.nonfinite + track, (double)bad);
     }
 }
 

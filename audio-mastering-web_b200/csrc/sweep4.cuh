@@ -594,13 +594,18 @@ __global__ void __launch_bounds__(Sweep2Cfg<M, NF, NIN, DIR, EPI, NAUX, ST>::kTh
         // float32 sections start every chunk from the float64-resolved state, mapped into the rescaled coordinates (B = 1) of
         // ss32_step.  Scalar steps: packing the two sections of a pair into FFMA2 operands costs more register moves than the
         // packed arithmetic saves (SASS of the loudness kernel: 26 instructions per sample packed, 15 scalar).
+        // Groups of four samples unrolled in pass 2.  The recombining kernels are 4000 instructions long and their warps drift apart
+        // through it: ncu showed `no_instruction` (instruction-cache misses) at 0.9 cycles per issued instruction in the dynamics
+        // sweep.  Measured per launch (64 x 180 s): dynamics 4.41 / 4.04 / 3.96 ms at 4 / 2 / 1 groups, four-section combine
+        // 4.77 / 4.64 / 4.75, two-section combine 2.88 / 2.91 / 2.96.
+        constexpr int kP2Unroll = (EPI == EPI_DYNAMICS || EPI == EPI_DYNAMICS_GEN) ? 1 : (NF >= 4 ? 2 : 4);
         float sf[NF32 > 0 ? NF32 : 1][M];
 #pragma unroll
         for (int f = 0; f < NF32; ++f)
 #pragma unroll
             for (int i = 0; i < M; ++i) sf[f][i] = (float)(z[f][i] * (double)P.f[f].dn32[i]);
         if (!inj_thread) {
-#pragma unroll (EPI == EPI_STORE ? kS / 4 : 4)
+#pragma unroll (EPI == EPI_STORE ? kS / 4 : kP2Unroll)     // storing sweeps: full unroll measured best (4-section forward: 7.51 / 7.59 / 7.76 ms at 8 / 4 / 2)
             for (int u = 0; u < kS / 4; ++u) {
                 const int uu = (DIR > 0) ? u : (kS / 4 - 1 - u);
                 const int off = cbase + ((4 * uu) ^ cx);
@@ -679,15 +684,23 @@ __global__ void __launch_bounds__(Sweep2Cfg<M, NF, NIN, DIR, EPI, NAUX, ST>::kTh
             const float* ax1 = (NAUX > 1) ? (P.aux[1] + rowoff) : ax0;
             if (out_fast) {
                 const size_t go0 = (size_t)tile_lo + 4 * lane;
-                float4 xa[kVecsPerLane], xb[kVecsPerLane];
+                // the dynamics epilogue finishes four band chains and the maximizer per sample: its store phase runs as two rolled
+                // halves (half the code; 4.17 -> 4.04 ms per launch), the lighter epilogues stay unrolled (rolling cost them 4 %)
+                constexpr int kStoreSplit = (EPI == EPI_DYNAMICS || EPI == EPI_DYNAMICS_GEN) ? 2 : 1;
+                constexpr int kPart = kVecsPerLane / kStoreSplit;
+#pragma unroll 1
+                for (int part = 0; part < kStoreSplit; ++part) {
+                float4 xa[kPart], xb[kPart];
 #pragma unroll
-                for (int r = 0; r < kVecsPerLane; ++r) {       // all aux loads first: 8 (16) independent requests in flight
-                    xa[r] = __ldcs(reinterpret_cast<const float4*>(ax0 + go0 + 128 * r));
-                    if (NAUX > 1) xb[r] = __ldcs(reinterpret_cast<const float4*>(ax1 + go0 + 128 * r));
+                for (int rr = 0; rr < kPart; ++rr) {           // all aux loads of the part first: independent requests in flight
+                    const int r = part * kPart + rr;
+                    xa[rr] = __ldcs(reinterpret_cast<const float4*>(ax0 + go0 + 128 * r));
+                    if (NAUX > 1) xb[rr] = __ldcs(reinterpret_cast<const float4*>(ax1 + go0 + 128 * r));
                 }
 #pragma unroll
-                for (int r = 0; r < kVecsPerLane; ++r) {
-                    float4 a0 = xa[r];
+                for (int rr = 0; rr < kPart; ++rr) {
+                    const int r = part * kPart + rr;
+                    float4 a0 = xa[rr];
                     if (aux_pmode == PRO_SUBMUL_F32) {
                         a0.x = __fmul_rn(__fsub_rn(a0.x, aux_subf), aux_mulf); a0.y = __fmul_rn(__fsub_rn(a0.y, aux_subf), aux_mulf);
                         a0.z = __fmul_rn(__fsub_rn(a0.z, aux_subf), aux_mulf); a0.w = __fmul_rn(__fsub_rn(a0.w, aux_subf), aux_mulf);
@@ -699,7 +712,7 @@ __global__ void __launch_bounds__(Sweep2Cfg<M, NF, NIN, DIR, EPI, NAUX, ST>::kTh
                     const float4 s0 = *reinterpret_cast<const float4*>(tout[0] + so);
                     float4 s1 = s0;
                     if (NSTAGE > 1) s1 = *reinterpret_cast<const float4*>(tout[NWR > 1 ? 1 : 0] + so);
-                    const float4 a1 = (NAUX > 1) ? xb[r] : a0;
+                    const float4 a1 = (NAUX > 1) ? xb[rr] : a0;
                     float4 o;
                     o.x = final_value(s0.x, s1.x, a0.x, a1.x); o.y = final_value(s0.y, s1.y, a0.y, a1.y);
                     o.z = final_value(s0.z, s1.z, a0.z, a1.z); o.w = final_value(s0.w, s1.w, a0.w, a1.w);
@@ -712,6 +725,7 @@ __global__ void __launch_bounds__(Sweep2Cfg<M, NF, NIN, DIR, EPI, NAUX, ST>::kTh
                             if (q + c >= P.pk_lo && q + c <= P.pk_hi) pk = fmaxf(pk, fabsf(comp4(o, c)));
                     }
                     __stcs(reinterpret_cast<float4*>(P.out[0] + rowoff + go0 + 128 * r), o);
+                }
                 }
             } else {
 #pragma unroll 1

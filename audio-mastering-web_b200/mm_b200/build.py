@@ -42,7 +42,20 @@ def _digest(paths) -> str:
     return h.hexdigest()
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
+def build(force: bool = False, verbose: bool = False, defs=(), tag: str = "") -> str:
+    """defs / tag: an experiment build (extra -D flags) into libmm_b200_<tag>.so with its own object directory; the loader picks
+    it up through MM_B200_LIB (A/B timing of kernel variants in one GPU call).  The product build has neither."""
+    global BUILD, LIB
+    if tag:
+        BUILD_, LIB_ = os.path.join(CSRC, "build_" + tag), os.path.join(HERE, f"libmm_b200_{tag}.so")
+        saved = (BUILD, LIB, list(NVCC_FLAGS))
+        BUILD, LIB = BUILD_, LIB_
+        NVCC_FLAGS.extend(defs)
+        try:
+            return build(force, verbose)
+        finally:
+            BUILD, LIB = saved[0], saved[1]
+            NVCC_FLAGS[:] = saved[2]
     os.makedirs(BUILD, exist_ok=True)
     headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".h", ".cuh"))]
     headers.append(os.path.join(INCLUDE, "mm_b200.h"))
@@ -81,4 +94,5 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    tag = next((a.split("=", 1)[1] for a in sys.argv if a.startswith("--tag=")), "")
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, defs=[a for a in sys.argv if a.startswith("-D")], tag=tag))

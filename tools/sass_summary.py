@@ -23,7 +23,7 @@ def main():
             continue
         if fn is None:
             continue
-        mm = re.match(r"\s*/\*[0-9a-f]{4}\*/\s+(?:@!?U?P\d+\s+)?([A-Z0-9_.]+)", line)
+        mm = re.match(r"\s*/\*[0-9a-f]{4,}\*/\s+(?:@!?U?P\d+\s+)?([A-Z0-9_.]+)", line)
         if mm:
             op = mm.group(1)
             counts[fn]["_n"] += 1
