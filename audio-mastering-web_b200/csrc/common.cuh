@@ -106,7 +106,7 @@ template <int M, int NF> struct SweepArgs {
     int epi;
     int epi_clip;            // EPI_COMBINE: clip the result to +-1
     double w[NF], wc, trim;
-    float w32[NF];
+    float w32[NF], wc32, trim32;
     PairK pr[(NF + 1) / 2];  // packed float32 sections (pairs 2p, 2p+1 with 2p+1 < NF32)
     DynParams dyn;
     double exc_gain, exc_k;

@@ -199,6 +199,8 @@ static void fill_common(const mm_ctx* c, SweepArgs<M, NF>& A, const mm_geom* g, 
     A.epi_clip = epi.clip;
     A.wc = epi.wc;
     A.trim = epi.trim;
+    A.wc32 = (float)epi.wc;
+    A.trim32 = (float)epi.trim;
     if (epi.dyn) A.dyn = *epi.dyn;
     A.exc_gain = epi.exc_gain;
     A.exc_k = epi.exc_k;

@@ -36,6 +36,9 @@
 
 namespace mm {
 
+#ifndef MM_COMBINE_F32
+#define MM_COMBINE_F32 1
+#endif
 constexpr int kWT = 1024;            // samples per warp-tile (32 lanes x kS)
 // Warps per sweep CTA.  The warps of a CTA share nothing but the read-only scan tables, so the CTA size only sets the granularity
 // at which an SM's 228 KB of shared memory is handed out: the count that fits the most warps on an SM wins (ties: the smaller
@@ -571,7 +574,15 @@ __global__ void __launch_bounds__(Sweep2Cfg<M, NF, NIN, DIR, EPI, NAUX, ST>::kTh
         // xa = aux0 (prologue applied), a1c = aux1
         auto final_value = [&](float s0, float s1, float xa, float a1c) -> float {
             if (EPI == EPI_COMBINE) {
-                const float res = (float)(fma(P.wc, (double)xa, (double)s0) * P.trim);      // float64 recombination, one cast
+                float res;
+                if (MM_COMBINE_F32 && NF32 == NF) {
+                    // every section ran in float32 (the staged sum is a float32 value already): recombine in float32 as well --
+                    // one fused multiply-add and one multiply, within two float32 ulps of the float64 expression below, without
+                    // its three float<->double conversions per sample (the conversion unit runs at 16 lanes per clock and SM)
+                    res = __fmul_rn(fmaf(P.wc32, xa, s0), P.trim32);
+                } else {
+                    res = (float)(fma(P.wc, (double)xa, (double)s0) * P.trim);              // float64 recombination, one cast
+                }
                 return P.epi_clip ? fminf(fmaxf(res, -1.f), 1.f) : res;
             } else if (EPI == EPI_EXCITER) {
                 return (float)((double)s0 + (double)xa);
