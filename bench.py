@@ -330,6 +330,8 @@ def dominant_roofline(ktimes, steps, default_samples, peak, peak_src):
     ksum = sum(v[0] for v in ktimes.values())
     return {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
             "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
+            "peak_note": "peak is the measured COPY bandwidth (one read + one write stream); a read-only kernel (row_stats) can "
+                         "exceed it -- HBM3e reads alone run at up to ~7.7 TB/s nominal",
             "kernel_share_of_step": kms / ksum, "kernels": kernel_table(ktimes, steps, default_samples)}
 
 

@@ -23,6 +23,7 @@ def main():
     ap.add_argument("--chain", default="v2")
     ap.add_argument("--style", default="standard")
     ap.add_argument("--reps", type=int, default=3)
+    ap.add_argument("--compressor", default="soft_knee", help="soft_knee | envelope")
     a = ap.parse_args()
     eng = get_engine()
     n = int(a.sec * a.sr)
@@ -36,7 +37,8 @@ def main():
     for rep in range(a.reps):
         eng.timing(True)
         t0 = time.time()
-        eng.master(b, chain, sts, out=out, want_int16=True, seed=1)
+        eng.master(b, chain, sts, out=out, want_int16=True, seed=1,
+                   flags=_lib.FLAG_ENVELOPE_COMPRESSOR if a.compressor == "envelope" else 0)
         eng.sync()
         wall = time.time() - t0
         kt = eng.kernel_times()
