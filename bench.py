@@ -14,12 +14,14 @@ The default line also carries, under "extra", bounded runs of the other BASELINE
 process (same command the driver runs): the v1 chain and the envelope-compressor mode on configs[1], configs[2] (mixed presets at 48 kHz),
 configs[3] (analyzer-only path) and configs[4] (one 2-hour 96 kHz file split in time over the N ranks).
 
-Accuracy gate ("check"): track 0 of the timed batch is the synthetic track the CPU oracle masters in the
-cpu_baseline leg; the timed run's own output for it is compared with the oracle's (samples, LUFS, true peak,
-int16 under a shared dither buffer) and the run FAILS (non-zero exit) beyond the north-star tolerances.
+Accuracy gate ("check"): track 0 of the timed batch is the synthetic track the CPU leg masters (cpu_baseline);
+the timed run's own output for it is compared with the CPU leg's (samples, LUFS, true peak, int16 under a shared
+dither buffer) and the run FAILS (non-zero exit) beyond the north-star tolerances.
 
---impl reference times the reference chain's CPU restatement (oracle/, numpy/scipy -- the reference
-itself is not on the GPU box) on the host cores, one track per process, on a bounded sample.
+CPU legs (cpu_baseline, --impl reference) run the UNMODIFIED reference when it is importable -- in the build container
+from /root/reference, on the GPU box from oracle/_ref (the byte-compiled modules oracle/make_ref.py built from that tree;
+kind "reference") -- and fall back to the oracle port (oracle/chain.py, kind "port") otherwise.  --impl reference uses all
+host cores, one track per process, on a bounded sample.
 """
 from __future__ import annotations
 
@@ -130,7 +132,23 @@ class ClockSampler:
 # -------------------------------------------------------------------------------------------------------
 # reference arm / CPU baseline: the oracle (test infrastructure) timed as the reference's CPU path
 # -------------------------------------------------------------------------------------------------------
+def _ref_kind(compressor="soft_knee"):
+    """"reference" when the unmodified reference is importable (the source tree in the build container, else oracle/_ref: the
+    byte-compiled copy oracle/make_ref.py built from it, which travels to the GPU box), "port" (oracle/chain.py) otherwise and for
+    the envelope-compressor mode, which exists only as a restatement (pedalboard is absent)."""
+    if compressor != "soft_knee" or os.environ.get("MM_BENCH_CPU", "") == "port":
+        return "port"
+    try:
+        from oracle import ref_harness
+        return "reference" if ref_harness.available() else "port"
+    except Exception:
+        return "port"
+
+
 def _cpu_one(args, keep=False):
+    """One track through the reference's CPU path: chain + 16-bit TPDF export, timed (synthesis excluded).  kind "reference": the
+    reference's own run_mastering_pipeline / MasteringChain.default_chain + apply_output_edge_fade_in (routers/mastering.py:583)
+    + export_audio(..., "wav", dither_type="tpdf"); kind "port": oracle/chain.py."""
     t, dur, chain = args[:3]
     sr = args[3] if len(args) > 3 else SR
     style = args[4] if len(args) > 4 else "standard"
@@ -139,20 +157,47 @@ def _cpu_one(args, keep=False):
     from mm_b200 import synth
     x = synth.numpy_track(t, sr, dur)
     target = oc.STYLE_CONFIGS[style]["lufs"]
+    rng = np.random.default_rng(t)
+    if _ref_kind(compressor) == "reference":
+        from oracle import ref_harness
+        ref = ref_harness.load()
+        RP = ref.pipeline
+        noise = None
+        if keep:        # the gate quantises the GPU's samples under the SAME dither values: hand the reference a known buffer
+            noise = (rng.random(x.shape) + rng.random(x.shape) - 1.0).astype(np.float32)
+            orig = RP._dither_noise_tpdf
+            RP._dither_noise_tpdf = lambda shape: noise
+        try:
+            t0 = time.time()
+            if chain == "v1":
+                out = RP.run_mastering_pipeline(x.copy(), sr, target_lufs=target, style=style)
+            else:
+                ch = ref.chain.MasteringChain.default_chain(target_lufs=target, style=style)
+                out = RP.apply_output_edge_fade_in(ch.process(x.copy(), sr, target_lufs=target, style=style), sr, fade_ms=6.0)
+            wav = RP.export_audio(out, sr, 2, "wav", dither_type="tpdf")
+            dt = time.time() - t0
+        finally:
+            if keep:
+                RP._dither_noise_tpdf = orig
+        if keep:
+            pcm = np.frombuffer(wav[44:], dtype="<i2").reshape(-1, out.shape[1] if out.ndim == 2 else 1)
+            return dt, {"x": x, "out": out, "noise": noise, "pcm": pcm, "lufs": RP.measure_lufs(out, sr), "tp": ref.true_peak_dbfs(out, sr),
+                        "kind": "reference"}
+        return dt
     t0 = time.time()
     out = (oc.run_v1 if chain == "v1" else oc.run_v2)(x, sr, target, style, compressor=compressor)
-    rng = np.random.default_rng(t)
     noise = (rng.random(out.shape) + rng.random(out.shape) - 1.0).astype(np.float32)
     pcm = oc.quantize_int16(out, noise)
     dt = time.time() - t0
     if keep:
-        return dt, {"x": x, "out": out, "noise": noise, "pcm": pcm, "lufs": oc.measure_lufs(out, sr), "tp": oc.true_peak_dbfs(out, sr)}
+        return dt, {"x": x, "out": out, "noise": noise, "pcm": pcm, "lufs": oc.measure_lufs(out, sr), "tp": oc.true_peak_dbfs(out, sr),
+                    "kind": "port"}
     return dt
 
 
 def cpu_baseline(chain, dur=60.0, procs=1, tracks=None, keep=False):
-    """oracle port on `procs` host processes, one track each; returns audio-s/s, a description and (keep, procs == 1) the
-    oracle's input / outputs for the accuracy gate."""
+    """the reference's CPU path (_ref_kind: the unmodified reference when importable, else the oracle port) on `procs` host
+    processes, one track each; returns audio-s/s, a description and (keep, procs == 1) its input / outputs for the accuracy gate."""
     import multiprocessing as mp
     tracks = tracks or procs
     work = [(1000 + i, dur, chain) for i in range(tracks)]
@@ -171,7 +216,10 @@ def cpu_baseline(chain, dur=60.0, procs=1, tracks=None, keep=False):
             per = pool.map(_cpu_one, work)
         waves = (tracks + procs - 1) // procs
         wall = max(per) * waves          # chain + export time of the slowest worker (synthesis excluded)
-    desc = f"{tracks} synthetic tracks x {dur:.0f} s, 44.1 kHz stereo, {chain} chain 'standard' + TPDF int16, oracle (numpy/scipy)"
+    kind = _ref_kind()
+    how = ("the unmodified reference (byte-compiled copy under oracle/_ref; pyloudnorm / soundfile stand-ins of oracle/ref_harness.py)"
+           if kind == "reference" else "oracle port (numpy/scipy)")
+    desc = f"{tracks} synthetic tracks x {dur:.0f} s, 44.1 kHz stereo, {chain} chain 'standard' + TPDF int16 WAV export, {how}"
     return tracks * dur / wall, desc, kept
 
 
@@ -182,6 +230,10 @@ def run_reference(args):
     cores = os.cpu_count() or 1
     procs = max(1, min(cores, 32))
     dur = 30.0
+    kind = _ref_kind()
+    if kind == "reference":
+        from oracle import ref_harness
+        ref_harness.load()          # imported (and its numba kernels compiled on first use) before the pool forks
     for _ in range(args.warmup):
         cpu_baseline(args.chain, dur=5.0, procs=procs)
     vals = []
@@ -196,10 +248,13 @@ def run_reference(args):
         "warmup": args.warmup, "ms_per_step": wall / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": f"bounded sample of configs[1]: per step {procs} tracks x {dur:.0f} s 44.1 kHz stereo, "
-                               f"{args.chain} chain + TPDF int16, one track per host process (the CPU restatement of the reference "
-                               f"chain, oracle/chain.py: the reference itself is pure Python and does not travel to this box)",
+                               f"{args.chain} chain + TPDF int16, one track per host process ("
+                               + ("the UNMODIFIED reference: run_mastering_pipeline / MasteringChain + export_audio imported from its "
+                                  "byte-compiled modules under oracle/_ref, built by oracle/make_ref.py from /root/reference"
+                                  if kind == "reference" else
+                                  "the CPU restatement of the reference chain, oracle/chain.py: no built reference under oracle/_ref") + ")",
                    "chain": args.chain},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": procs, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": procs, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -357,7 +412,7 @@ def side_gate(rt, chain, style, sr, dur=10.0, track=1001, compressor="soft_knee"
     return gate_record(max_abs, abs(res["stats"][0]["lufs_out"] - kept["lufs"]), abs(P.true_peak_dbfs(out, sr) - kept["tp"]),
                        int(np.count_nonzero(q != kept["pcm"])), int(np.max(np.abs(res["int16"][0].astype(np.int32) - kept["pcm"].astype(np.int32)))),
                        f"{dur:.0f} s synthetic track {track}, {sr} Hz, {chain}/{style}" + (" (envelope compressor)" if compressor != "soft_knee" else "") +
-                       " through master_batch vs the oracle")
+                       f" through master_batch vs the {kept['kind']}")
 
 
 # -------------------------------------------------------------------------------------------------------
@@ -391,7 +446,7 @@ def bench_batch(rt, args, *, chain, mixed, steps, warmup, main, envelope=False):
     do_gate = main and world == 1 and not args.no_cpu
     if do_gate:
         v, sample, kept = cpu_baseline(chain, dur=dur, procs=1, tracks=1, keep=True)
-        cb = {"value": v, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample}
+        cb = {"value": v, "unit": UNIT, "cores": 1, "kind": kept["kind"], "sample": sample}
         with torch.cuda.stream(eng.stream):
             xt = torch.from_numpy(np.ascontiguousarray(kept["x"].T)).to(eng.tdev)
             src.live()[0:2].copy_(xt)
@@ -444,7 +499,7 @@ def bench_batch(rt, args, *, chain, mixed, steps, warmup, main, envelope=False):
         own = eng.quantize_int16(eng.upload([got], sr), noise=kept["noise"][None])[0]            # chain output, shared dither buffer
         check["gate"] = gate_record(max_abs, abs(recs[0]["lufs_out"] - kept["lufs"]), abs(tp - kept["tp"]),
                                     int(np.count_nonzero(q != kept["pcm"])), int(np.max(np.abs(own.astype(np.int32) - kept["pcm"].astype(np.int32)))),
-                                    f"track 0 of the timed batch ({dur:.0f} s, synthetic track 1000) vs the oracle's output for the same samples")
+                                    f"track 0 of the timed batch ({dur:.0f} s, synthetic track 1000) vs the {kept['kind']}'s output for the same samples")
         check["gate"]["philox_int16_vs_oracle_float_lsb"] = float(np.max(np.abs(got_pcm.astype(np.float64) - kept["out"].astype(np.float64) * 32767.0)))
         del kept
     elif not args.no_cpu and rank == 0:

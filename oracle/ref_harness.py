@@ -4,10 +4,11 @@
 in this image (``pyloudnorm``, ``soundfile``, ``pydub``; ``backend/app/pipeline.py:13-15``).
 This module injects small stand-ins for exactly those three names into ``sys.modules`` and then
 imports ``app.pipeline`` / ``app.chain`` / ``app.routers.tools`` helpers from the read-only
-reference tree.  Nothing from the reference is copied; nothing here runs on the GPU box
-(``/root/reference`` does not exist there) -- it is used only by ``tests/golden/make_golden.py``
-and by ``tests/test_oracle_vs_reference.py`` (skipped when the tree is absent) to pin
-``oracle/chain.py`` against the reference's own arithmetic.
+reference tree.  No reference source is copied into the repository.  Where ``/root/reference`` does not exist
+(the GPU box) the same modules are imported from ``oracle/_ref/backend``: sourceless ``.pyc`` files that
+``oracle/make_ref.py`` byte-compiled from the tree (the "built reference" of this pure-Python path).  Used by
+``tests/golden/make_golden*.py``, by ``tests/test_oracle_vs_reference.py`` (pins ``oracle/chain.py`` against the
+reference's own arithmetic) and by ``bench.py``'s CPU legs (``--impl reference``, ``cpu_baseline``).
 
 Stand-ins:
 * ``pyloudnorm.Meter``  -> ``oracle.bs1770.Meter`` (restated BS.1770-4 / pyloudnorm algorithm)
@@ -23,12 +24,23 @@ import os
 import sys
 import types
 
-REFERENCE_BACKEND = os.environ.get("MM_REFERENCE_BACKEND", "/root/reference/backend")
-
 _REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+# The source tree where it exists (the build container); else the byte-compiled copy oracle/make_ref.py built from it
+# (oracle/_ref/backend: sourceless .pyc files, git-ignored, shipped to the GPU box like a built .so).
+PREBUILT_BACKEND = os.path.join(_REPO, "oracle", "_ref", "backend")
+REFERENCE_BACKEND = os.environ.get("MM_REFERENCE_BACKEND") or (
+    "/root/reference/backend" if os.path.isfile("/root/reference/backend/app/pipeline.py") else PREBUILT_BACKEND)
+
+
+def _has(backend: str) -> bool:
+    return any(os.path.isfile(os.path.join(backend, "app", "pipeline" + ext)) for ext in (".py", ".pyc"))
 
 
 def available() -> bool:
+    return _has(REFERENCE_BACKEND)
+
+
+def is_source_tree() -> bool:
     return os.path.isfile(os.path.join(REFERENCE_BACKEND, "app", "pipeline.py"))
 
 
@@ -79,6 +91,29 @@ def _install_standins():
 _cache = {}
 
 
+def _numba_cache_guard():
+    """Prebuilt copy only.  The reference decorates its two sample loops with numba.njit(cache=True) (pipeline.py:25-26); numba
+    stats the file named in the function's code object for its cache index and raises at decoration time when it is missing.
+    oracle/make_ref.py records the .pyc's own path under /root/repo there; if the copy was moved somewhere else, JIT-compile
+    without the on-disk cache instead of failing (same machine code, compiled once per process)."""
+    import marshal
+    with open(os.path.join(REFERENCE_BACKEND, "app", "pipeline.pyc"), "rb") as f:
+        recorded = marshal.loads(f.read()[16:]).co_filename
+    if os.path.exists(recorded):
+        return
+    try:
+        import numba
+    except ImportError:
+        return
+    orig = numba.njit
+
+    def njit_nocache(*a, **k):
+        k.pop("cache", None)
+        return orig(*a, **k)
+
+    numba.njit = njit_nocache
+
+
 def load():
     """Return a namespace with ``pipeline``, ``chain`` (modules) and ``true_peak_dbfs``."""
     if "ns" in _cache:
@@ -90,6 +125,8 @@ def load():
     os.environ.setdefault("NUMBA_CACHE_DIR", "/tmp/mm_numba_cache")
     if REFERENCE_BACKEND not in sys.path:
         sys.path.insert(0, REFERENCE_BACKEND)
+    if not is_source_tree():
+        _numba_cache_guard()
     pipeline = importlib.import_module("app.pipeline")
     chain = importlib.import_module("app.chain")
     ns = types.SimpleNamespace(pipeline=pipeline, chain=chain)
@@ -101,11 +138,16 @@ def load():
     from scipy.signal import resample_poly
 
     src_path = os.path.join(REFERENCE_BACKEND, "app", "routers", "tools.py")
-    tree = ast.parse(open(src_path, encoding="utf-8").read())
-    keep = [n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name in ("_true_peak_dbfs", "_loudness_range_lu")]
-    mod = ast.Module(body=keep, type_ignores=[])
+    if os.path.isfile(src_path):
+        tree = ast.parse(open(src_path, encoding="utf-8").read())
+        keep = [n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name in ("_true_peak_dbfs", "_loudness_range_lu")]
+        code = compile(ast.Module(body=keep, type_ignores=[]), src_path, "exec")
+    else:                                           # prebuilt copy: the same two definitions, compiled by oracle/make_ref.py
+        import marshal
+        with open(os.path.join(REFERENCE_BACKEND, "app", "_tools_numeric.pyc"), "rb") as f:
+            code = marshal.loads(f.read()[16:])
     g = {"np": np, "resample_poly": resample_poly, "compute_lufs_timeline": pipeline.compute_lufs_timeline}
-    exec(compile(mod, src_path, "exec"), g)  # noqa: S102 - reference code, run as the oracle's oracle
+    exec(code, g)  # noqa: S102 - reference code, run as the oracle's oracle
     ns.true_peak_dbfs = g["_true_peak_dbfs"]
     ns.loudness_range_lu = g["_loudness_range_lu"]
     _cache["ns"] = ns

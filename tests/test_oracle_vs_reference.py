@@ -85,3 +85,37 @@ def test_int16_export_equal_reference(ref):
         P._dither_noise_tpdf = orig
     pcm = np.frombuffer(wav[44:], dtype="<i2").reshape(-1, 2)
     assert np.array_equal(pcm, oc.quantize_int16(x, noise))
+
+
+def test_prebuilt_reference_copy_runs_sourceless_and_equals_the_oracle(tmp_path):
+    """oracle/make_ref.py byte-compiles the reference's mastering path into oracle/_ref (what bench.py's CPU legs import on the
+    GPU box, where /root/reference does not exist).  Imported SOURCELESS in a fresh process it must return the oracle's samples
+    bit for bit, like the tree itself does above."""
+    import os
+    import subprocess
+    import sys
+    from oracle import make_ref
+    if not os.path.isfile(os.path.join(make_ref.SRC, "app", "pipeline.py")):
+        pytest.skip("reference tree not present: nothing to build from")
+    out_dir = make_ref.build(verbose=False)
+    assert not [f for _, _, fs in os.walk(out_dir) for f in fs if f.endswith(".py")], "no reference source may be copied"
+    code = (
+        "import sys, numpy as np\n"
+        "from oracle import ref_harness, chain as oc\n"
+        "from mm_b200 import synth\n"
+        "assert ref_harness.available() and not ref_harness.is_source_tree()\n"
+        "ref = ref_harness.load()\n"
+        "assert ref.pipeline.__file__.endswith('.pyc')\n"
+        "x = synth.numpy_track(77, 48000, 3.0)\n"
+        "r1 = ref.pipeline.run_mastering_pipeline(x.copy(), 48000, target_lufs=-9.0, style='edm')\n"
+        "assert np.array_equal(r1, oc.run_v1(x.copy(), 48000, -9.0, 'edm'))\n"
+        "ch = ref.chain.MasteringChain.default_chain(target_lufs=-14.0, style='standard')\n"
+        "r2 = ref.pipeline.apply_output_edge_fade_in(ch.process(x.copy(), 48000, target_lufs=-14.0, style='standard'), 48000, fade_ms=6.0)\n"
+        "assert np.array_equal(r2, oc.run_v2(x.copy(), 48000, -14.0, 'standard'))\n"
+        "assert ref.true_peak_dbfs(r2, 48000) == oc.true_peak_dbfs(r2, 48000)\n"
+        "print('prebuilt ok')\n")
+    repo = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = {**os.environ, "MM_REFERENCE_BACKEND": out_dir, "PYTHONPATH": repo + os.pathsep + os.path.join(repo, "audio-mastering-web_b200"),
+           "NUMBA_CACHE_DIR": str(tmp_path)}
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "prebuilt ok" in r.stdout, r.stderr[-2000:]
