@@ -95,6 +95,7 @@ struct mm_ctx {
     const int* track_ids_dev = nullptr;        // ... and the current chunk's slice of it on the device
     const mm_slice* slice = nullptr;    // set for the duration of mm_dev_master_slice: the batch is a time slice of one file   // copy streams of the host-buffer entry point (lazy)
     mm::Slot slots[mm::SL_COUNT];
+    cudaEvent_t pin_in_done = nullptr;  // recorded after the last DMA out of host_pin[0] by mm_ctx_copy_in (the slot is rewritten only after it)
     mm::Slot host_pin[4];               // pinned staging ring of mm_master_host_jobs (pageable uploads and results pass through it): 0, 1 in; 2, 3 out
     std::map<std::string, mm::FilterPlan> plans;
     std::map<std::string, mm::LufsPlan> lufs_plans;

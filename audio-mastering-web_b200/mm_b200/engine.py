@@ -14,6 +14,12 @@ from . import _lib
 from ._lib import Geom, Style, TrackStats, MMError  # noqa: F401  (re-exported)
 
 
+def _torch_np_dtype(dt):
+    torch = _torch()
+    return {torch.float32: np.float32, torch.float64: np.float64, torch.int16: np.int16, torch.int32: np.int32,
+            torch.int64: np.int64, torch.uint8: np.uint8}[dt]
+
+
 def _torch():
     import torch
     return torch
@@ -87,41 +93,22 @@ class Engine:
         """list of (n,) / (n, ch) float32 arrays of identical shape (or one 3-D array) -> Batch."""
         torch = _torch()
         views = [np.asarray(a, dtype=np.float32).reshape(len(a), -1) for a in tracks_np]
-        # one track (the job path): no host-side copy, the caller's array goes to the device as it is
-        arr = views[0][None] if len(views) == 1 else np.stack(views, axis=0)
-        tracks, n, ch = arr.shape
+        if any(v.shape != views[0].shape for v in views):
+            raise ValueError("all input arrays must have the same shape")
+        # no host-side gathering: every caller's array goes to the device as it is
+        views = [np.ascontiguousarray(v) for v in views]
+        tracks, (n, ch) = len(views), views[0].shape
         b = self.empty(tracks, ch, n, sr)
         with torch.cuda.stream(self.stream):
-            pin = self._pinned("in", arr.nbytes)
-            if pin is not None:
-                # job path: one memcpy into a cached pinned buffer, then a DMA at link speed -- a pageable cudaMemcpy of a
-                # 3-minute track runs at ~3 GB/s (21 ms of the 49 ms a single job took), this at ~8 ms
-                host = pin[:arr.nbytes].view(torch.float32).view(tracks, n, ch)
-                np.copyto(host.numpy(), arr)
-                il = torch.empty((tracks, n, ch), dtype=torch.float32, device=self.tdev)
-                il.copy_(host, non_blocking=True)
-            else:
-                il = torch.from_numpy(np.ascontiguousarray(arr)).to(self.tdev, non_blocking=False)
+            il = torch.empty((tracks, n, ch), dtype=torch.float32, device=self.tdev)
+            # a caller's (pageable) array is staged into pinned memory by several threads inside the library while the DMA engine
+            # already moves the finished blocks (mm_ctx_copy_in): a 3-minute track took ~8 ms through one numpy copy + one DMA
+            for t, v in enumerate(views):
+                _lib.check(self.lib.mm_ctx_copy_in(self.ctx, C.c_void_p(il[t].data_ptr()), C.c_void_p(v.ctypes.data), v.nbytes))
             g = b.geom
             _lib.check(self.lib.mm_dev_deinterleave(self.ctx, C.byref(g), C.c_void_p(il.data_ptr()), b.ptr))
             self.sync()
         return b
-
-    _PIN_LIMIT = 512 << 20
-
-    def _pinned(self, which: str, nbytes: int):
-        """Cached pinned staging buffer (uint8 tensor) of at least ``nbytes``, or None above 512 MB (big batches go through
-        ``mm_master_host`` with the caller's own pinned buffers; allocating gigabytes of pinned memory here would cost seconds)."""
-        torch = _torch()
-        if nbytes <= 0 or nbytes > self._PIN_LIMIT:
-            return None
-        pins = self.__dict__.setdefault("_pins", {})
-        t = pins.get(which)
-        if t is None or t.numel() < nbytes:
-            cap = max(nbytes, 1 << 20)
-            cap = 1 << (cap - 1).bit_length() if cap < (64 << 20) else ((cap + (32 << 20) - 1) // (32 << 20)) * (32 << 20)
-            t = pins[which] = torch.empty(cap, dtype=torch.uint8, pin_memory=True)
-        return t
 
     def download(self, b: Batch) -> np.ndarray:
         """Batch -> float32 array (tracks, n, channels)."""
@@ -130,21 +117,24 @@ class Engine:
             il = torch.empty((b.tracks, b.n, b.channels), dtype=torch.float32, device=self.tdev)
             g = b.geom
             _lib.check(self.lib.mm_dev_interleave(self.ctx, C.byref(g), b.ptr, C.c_void_p(il.data_ptr())))
-            nbytes = il.numel() * 4
-            pin = self._pinned("out", nbytes)
-            if pin is None:
-                self.sync()
-                return il.cpu().numpy()
-            host = pin[:nbytes].view(torch.float32).view(b.tracks, b.n, b.channels)
-            host.copy_(il, non_blocking=True)
-            self.sync()
-            return host.numpy().copy()            # the caller owns its result; the staging buffer is reused
+            host = np.empty((b.tracks, b.n, b.channels), np.float32)       # the caller owns its result
+            _lib.check(self.lib.mm_ctx_copy_out(self.ctx, C.c_void_p(host.ctypes.data), C.c_void_p(il.data_ptr()), host.nbytes))
+        return host
+
+    def to_host(self, t) -> np.ndarray:
+        """A device tensor of this engine's stream -> a numpy array the caller owns (staged, see mm_ctx_copy_out)."""
+        if not t.is_contiguous():
+            with _torch().cuda.stream(self.stream):
+                t = t.contiguous()
+        host = np.empty(tuple(t.shape), dtype=_torch_np_dtype(t.dtype))
+        if host.nbytes:
+            _lib.check(self.lib.mm_ctx_copy_out(self.ctx, C.c_void_p(host.ctypes.data), C.c_void_p(t.data_ptr()), host.nbytes))
+        return host
 
     def release_workspace(self):
         """Give the device scratch and the pinned staging buffers back (they grow on demand and stay at their high-water mark
         otherwise)."""
         _lib.check(self.lib.mm_ctx_release_workspace(self.ctx))
-        self.__dict__.pop("_pins", None)
 
     def sync(self):
         _lib.check(self.lib.mm_ctx_sync(self.ctx))
@@ -235,8 +225,7 @@ class Engine:
             pcm = torch.empty((b.tracks, b.n, b.channels), dtype=torch.int32, device=self.tdev)
             g = b.geom
             _lib.check(self.lib.mm_dev_quantize_pcm24(self.ctx, C.byref(g), b.ptr, C.c_void_p(pcm.data_ptr())))
-            self.sync()
-            return pcm.cpu().numpy()
+            return self.to_host(pcm)
 
     def quantize_int16(self, b: Batch, noise: np.ndarray | None = None, seed: int = 0) -> np.ndarray:
         """-> int16 (tracks, n, channels); ``noise`` float32 of that shape selects the bit-exact mode."""
@@ -249,8 +238,7 @@ class Engine:
             g = b.geom
             _lib.check(self.lib.mm_dev_quantize_int16(self.ctx, C.byref(g), b.ptr, C.c_void_p(pcm.data_ptr()),
                                                       C.c_void_p(nz.data_ptr()) if nz is not None else None, int(seed)))
-            self.sync()
-            return pcm.cpu().numpy()
+            return self.to_host(pcm)
 
     def quantize_int16_shaped(self, b: Batch, shape: int, uniform: np.ndarray | None = None, seed: int = 0) -> np.ndarray:
         """Noise-shaped dither export (shape 1 = ns_e, 2 = ns_itu) -> int16 (tracks, n, channels); ``uniform`` =
@@ -264,8 +252,7 @@ class Engine:
             g = b.geom
             _lib.check(self.lib.mm_dev_quantize_int16_shaped(self.ctx, C.byref(g), b.ptr, C.c_void_p(pcm.data_ptr()),
                                                              C.c_void_p(un.data_ptr()) if un is not None else None, int(seed), int(shape)))
-            self.sync()
-            return pcm.cpu().numpy()
+            return self.to_host(pcm)
 
     # ---- whole chains -----------------------------------------------------------------------------
     def master(self, src: Batch, chain: int, styles, *, out: Batch | None = None, want_int16=False, noise=None,

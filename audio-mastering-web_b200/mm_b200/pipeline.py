@@ -744,8 +744,7 @@ def master_batch(tracks, sr, styles, targets=None, chain="v2", want_int16=False,
     audio = eng.download(out)
     res = {"audio": [a[:, 0] if mono else a for a in audio], "int16": None, "stats": []}
     if pcm is not None:
-        eng.sync()
-        res["int16"] = list(pcm.cpu().numpy())
+        res["int16"] = list(eng.to_host(pcm))
     for s in stats:
         res["stats"].append({k: (list(getattr(s, k)) if k == "mean" else getattr(s, k)) for k, _ in s._fields_})
     return res

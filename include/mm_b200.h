@@ -333,6 +333,15 @@ int mm_master_host_jobs(mm_ctx*, int chain, int32_t njobs, mm_host_job* jobs, ui
 int mm_host_alloc(void** out, int64_t bytes);
 int mm_host_free(void* p);
 
+/* Host <-> device transfers on the context stream for the Python mirror's numpy arguments and results (replaces: the implicit
+ * host arrays of backend/app/pipeline.py's function surface -- every stage takes and returns a numpy array, pipeline.py:134 ...).
+ * A pinned host buffer moves as one DMA; a pageable one is staged through the context's pinned slots by several host threads
+ * (MM_HOST_THREADS, default min(8, cores / 2)) with the DMA of finished blocks overlapping the staging of the next ones.
+ * mm_ctx_copy_in returns once the host buffer has been read (the DMA may be in flight: stream order protects the device side);
+ * mm_ctx_copy_out returns when the host buffer is complete. */
+int mm_ctx_copy_in(mm_ctx*, void* dev_dst, const void* host_src, int64_t bytes);
+int mm_ctx_copy_out(mm_ctx*, void* host_dst, const void* dev_src, int64_t bytes);
+
 /* Bytes of device workspace the context currently holds (for sizing sub-batches). */
 int64_t mm_ctx_workspace_bytes(mm_ctx*);
 /* Workspace the chain needs for a geometry (rows * stride * 4 * k + carries). */
