@@ -86,6 +86,86 @@ struct StyleSig {
     bool operator==(const StyleSig& o) const { return memcmp(this, &o, sizeof(StyleSig)) == 0; }
 };
 
+// ---- lanes --------------------------------------------------------------------------------------------------------------
+// One chain is ~21 dependent kernels; each has a prologue (scan tables into shared memory), a tail (the last warps of a persistent
+// grid) and a dependent successor, and a small batch cannot fill 148 SMs through all of them.  Measured on B200 (64 x 180 s tracks,
+// tools/lanes_probe.py): one-track launches 169 k audio-s/s on one stream, 228 k on two, 251 k on four; four-track launches 243 k on
+// one stream, 288 k on two -- ABOVE the 64-track batch on one stream (279 k).  So a call is spread over LANES: sub-batches (device
+// entry) or chunks (host entries) go round-robin to child contexts with their own streams and workspaces, all at full grid size.
+// Results do not depend on the split: every track's arithmetic is its own (batch == single-track bit equality), the dither stream is
+// keyed by the track's index in the call.
+static int lanes_wanted(const mm_ctx* c, int dflt) {
+    if (c->lanes_cfg > 0) return c->lanes_cfg;
+    if (const char* e = getenv("MM_LANES")) { const int v = atoi(e); if (v > 0) return std::min(v, 8); }
+    return dflt;
+}
+static int get_lane(mm_ctx* c, int i, mm_ctx** out) {
+    if (i == 0) { *out = c; return 0; }
+    while ((int)c->lanes.size() < i) {
+        mm_ctx* l = new mm_ctx();
+        l->device = c->device;
+        l->grid_div = c->grid_div;
+        if (cudaStreamCreateWithFlags(&l->stream, cudaStreamNonBlocking) != cudaSuccess) { delete l; set_error("lane: cudaStreamCreate failed"); return 1; }
+        l->own_stream = true;
+        if (cudaEventCreateWithFlags(&l->ev_join, cudaEventDisableTiming) != cudaSuccess) { cudaStreamDestroy(l->stream); delete l; set_error("lane: cudaEventCreate failed"); return 1; }
+        c->lanes.push_back(l);
+    }
+    *out = c->lanes[i - 1];
+    return 0;
+}
+// lane streams start after everything queued on the parent's stream so far
+static int lanes_fork(mm_ctx* c, int L) {
+    if (L <= 1) return 0;
+    if (!c->ev_fork) MM_CUDA(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+    MM_CUDA(cudaEventRecord(c->ev_fork, c->stream));
+    for (int l = 1; l < L; ++l) {
+        mm_ctx* cl;
+        MM_TRY(get_lane(c, l, &cl));
+        plan_gc(cl);
+        cl->track_ids_host = c->track_ids_host;
+        MM_CUDA(cudaStreamWaitEvent(cl->stream, c->ev_fork, 0));
+    }
+    return 0;
+}
+// ... and the parent's stream continues after everything the lanes have queued
+static int lanes_join(mm_ctx* c, int L) {
+    for (int l = 1; l < L && l <= (int)c->lanes.size(); ++l) {
+        mm_ctx* cl = c->lanes[l - 1];
+        cl->track_ids_host = nullptr;
+        cl->track_ids_dev = nullptr;
+        MM_CUDA(cudaEventRecord(cl->ev_join, cl->stream));
+        MM_CUDA(cudaStreamWaitEvent(c->stream, cl->ev_join, 0));
+    }
+    return 0;
+}
+
+static int master_impl(mm_ctx* c, const mm_geom* g, int chain, const mm_style* styles, const float* in, float* out,
+                       int16_t* pcm, const float* noise, uint64_t seed, mm_track_stats* stats_dev, uint32_t flags);
+
+// device-resident batch: contiguous runs of tracks go to the lanes (default 2: halves of the batch)
+static int master_lanes(mm_ctx* c, const mm_geom* g, int chain, const mm_style* styles, const float* in, float* out,
+                        int16_t* pcm, const float* noise, uint64_t seed, mm_track_stats* stats_dev, uint32_t flags) {
+    MM_TRY(check_geom(g));
+    int L = std::min(lanes_wanted(c, 2), (int)g->tracks);
+    if (c->timing || c->slice || !styles || !in || !out) L = 1;      // per-kernel events time kernels ALONE; a time slice is one track
+    if (L <= 1) return master_impl(c, g, chain, styles, in, out, pcm, noise, seed, stats_dev, flags);
+    MM_TRY(lanes_fork(c, L));
+    int rc = 0;
+    const size_t row_floats = (size_t)g->channels * (size_t)g->stride, frame_samples = (size_t)g->n * g->channels;
+    for (int l = 0; l < L && rc == 0; ++l) {
+        const int t0 = (int)((long long)g->tracks * l / L), t1 = (int)((long long)g->tracks * (l + 1) / L);
+        mm_ctx* cl;
+        if ((rc = get_lane(c, l, &cl)) != 0) break;
+        mm_geom gl = *g;
+        gl.tracks = t1 - t0;
+        gl.track_base = g->track_base + t0;
+        rc = master_impl(cl, &gl, chain, styles + t0, in + t0 * row_floats, out + t0 * row_floats, pcm ? pcm + t0 * frame_samples : nullptr,
+                         noise ? noise + t0 * frame_samples : nullptr, seed, stats_dev ? stats_dev + t0 : nullptr, flags);
+    }
+    const int rj = lanes_join(c, L);
+    return rc ? rc : rj;
+}
+
 static int master_impl(mm_ctx* c, const mm_geom* g, int chain, const mm_style* styles, const float* in, float* out,
                        int16_t* pcm, const float* noise, uint64_t seed, mm_track_stats* stats_dev, uint32_t flags) {
     MM_TRY(check_geom(g));
@@ -501,6 +581,7 @@ int mm_ctx_create(int device, void* stream, mm_ctx** out) {
     if (prop.major != 10) { set_error("device %d is sm_%d%d; this library holds sm_100a code only", device, prop.major, prop.minor); return 1; }
     mm_ctx* c = new mm_ctx();
     c->device = device;
+    if (const char* e = getenv("MM_GRID_DIV")) c->grid_div = std::max(1, atoi(e));      // experiments: several contexts sharing the device
     if (stream) {
         c->stream = (cudaStream_t)stream;
         c->own_stream = false;
@@ -516,6 +597,10 @@ void mm_ctx_destroy(mm_ctx* c) {
     if (!c) return;
     DeviceGuard guard(c->device);
     cudaStreamSynchronize(c->stream);
+    for (mm_ctx* l : c->lanes) mm_ctx_destroy(l);
+    c->lanes.clear();
+    if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+    if (c->ev_join) cudaEventDestroy(c->ev_join);
     bigfft_release(c);
     for (int i = 0; i < SL_COUNT; ++i) if (c->slots[i].p) cudaFree(c->slots[i].p);
     for (auto& kv : c->plans) if (kv.second.dev) cudaFree(kv.second.dev);
@@ -536,6 +621,7 @@ void mm_ctx_destroy(mm_ctx* c) {
 int mm_ctx_release_workspace(mm_ctx* c) {
     MM_API_BEGIN(c);
     MM_CUDA(cudaStreamSynchronize(c->stream));
+    for (mm_ctx* l : c->lanes) MM_TRY(mm_ctx_release_workspace(l));
     bigfft_release(c);
     for (int i = 0; i < SL_COUNT; ++i)
         if (c->slots[i].p) { cudaFree(c->slots[i].p); c->slots[i].p = nullptr; c->slots[i].cap = 0; }
@@ -552,7 +638,19 @@ int mm_ctx_sync(mm_ctx* c) {
     return 0;
 }
 
-int64_t mm_ctx_launch_count(mm_ctx* c) { return c ? c->launches : 0; }
+int64_t mm_ctx_launch_count(mm_ctx* c) {
+    if (!c) return 0;
+    int64_t n = c->launches;
+    for (const mm_ctx* l : c->lanes) n += l->launches;
+    return n;
+}
+
+int mm_ctx_set_lanes(mm_ctx* c, int lanes) {
+    MM_API_BEGIN(c);
+    if (lanes < 0 || lanes > 8) { set_error("mm_ctx_set_lanes: 0 (automatic) .. 8"); return 1; }
+    c->lanes_cfg = lanes;
+    return 0;
+}
 
 int mm_ctx_timing(mm_ctx* c, int enable) {
     MM_API_BEGIN(c);
@@ -561,6 +659,9 @@ int mm_ctx_timing(mm_ctx* c, int enable) {
     c->ktimes.clear();
     c->kacc.clear();
     c->timing = enable != 0;
+    // per-kernel events time kernels alone: calls stay on the context's own stream while timing is on, and the lanes' scratch is
+    // handed back so that lane 0 can grow to the whole batch
+    if (enable) for (mm_ctx* l : c->lanes) MM_TRY(mm_ctx_release_workspace(l));
     return 0;
 }
 
@@ -594,7 +695,12 @@ int mm_ctx_kernel_times(mm_ctx* c, mm_ktime* out, int cap, int* count) {
     return 0;
 }
 
-int64_t mm_ctx_workspace_bytes(mm_ctx* c) { return c ? c->workspace_bytes : 0; }
+int64_t mm_ctx_workspace_bytes(mm_ctx* c) {
+    if (!c) return 0;
+    int64_t n = c->workspace_bytes;
+    for (const mm_ctx* l : c->lanes) n += l->workspace_bytes;
+    return n;
+}
 
 int64_t mm_master_workspace_bytes(const mm_geom* g, int chain) {
     if (!g) return 0;
@@ -1151,7 +1257,7 @@ int mm_dev_signal_metrics(mm_ctx* c, const mm_geom* g, const float* in, double* 
 int mm_dev_master(mm_ctx* c, const mm_geom* g, int chain, const mm_style* styles, const float* in, float* out,
                   int16_t* pcm, const float* noise, uint64_t seed, mm_track_stats* stats_dev, uint32_t flags) {
     MM_API_BEGIN(c);
-    return master_impl(c, g, chain, styles, in, out, pcm, noise, seed, stats_dev, flags);
+    return master_lanes(c, g, chain, styles, in, out, pcm, noise, seed, stats_dev, flags);
 }
 
 int64_t mm_slice_margin(int32_t sr) {
@@ -1166,7 +1272,7 @@ int mm_dev_master_slice(mm_ctx* c, const mm_geom* g, int chain, const mm_style* 
                         int16_t* pcm, const float* noise, uint64_t seed, mm_track_stats* stats_dev, uint32_t flags,
                         const mm_slice* slice) {
     MM_API_BEGIN(c);
-    if (!slice) return master_impl(c, g, chain, style, in, out, pcm, noise, seed, stats_dev, flags);
+    if (!slice) return master_lanes(c, g, chain, style, in, out, pcm, noise, seed, stats_dev, flags);
     MM_TRY(check_geom(g));
     if (g->tracks != 1) { set_error("mm_dev_master_slice: one track (file) per call"); return 1; }
     if (slice->own_lo < 0 || slice->own_hi > g->n || slice->own_lo >= slice->own_hi || (slice->own_lo & 3) || slice->global_off < 0 || (slice->global_off & 1) ||
@@ -1212,16 +1318,26 @@ static int master_host_plan(mm_ctx* c, int chain, const std::vector<HostChunk>& 
         cframes = std::max(cframes, (size_t)ch.tn * (size_t)ch.n * ch.channels);
         pfloats = std::max(pfloats, batch_floats(&gc));
     }
-    float *il[2] = {nullptr, nullptr}, *ol[2] = {nullptr, nullptr}, *nz[2] = {nullptr, nullptr}, *pl = nullptr;
-    int16_t* pcm[2] = {nullptr, nullptr};
+    // lanes: chunk k's chain runs on lane k % L (own stream, own planar buffer and scratch), so that consecutive chunks' chains
+    // overlap; the device staging rings are 2 L deep so that a lane never waits for its previous chunk's copy-out
+    const int L = c->timing ? 1 : std::max(1, std::min(lanes_wanted(c, 4), nchunks));
+    const int R = std::min(2 * L, nchunks);
+    std::vector<mm_ctx*> lane((size_t)L);
+    std::vector<float*> pls((size_t)L, nullptr);
+    for (int l = 0; l < L; ++l) MM_TRY(get_lane(c, l, &lane[l]));
+    float *il_ring = nullptr, *ol_ring = nullptr, *nz_ring = nullptr;
+    int16_t* pcm_ring = nullptr;
     mm_track_stats* st = nullptr;
-    MM_TRY(arena(c, SL_STAGE_IL, cframes, &il[0]));
-    if (nchunks > 1) MM_TRY(arena(c, SL_STAGE_IL1, cframes, &il[1]));
-    MM_TRY(arena(c, SL_STAGE_PL, pfloats, &pl));
-    if (any_pcm) { MM_TRY(arena(c, SL_STAGE_PCM, cframes, &pcm[0])); if (nchunks > 1) MM_TRY(arena(c, SL_STAGE_PCM1, cframes, &pcm[1])); }
-    if (any_noise) { MM_TRY(arena(c, SL_STAGE_NOISE, cframes, &nz[0])); if (nchunks > 1) MM_TRY(arena(c, SL_STAGE_NOISE1, cframes, &nz[1])); }
-    if (any_f32) { MM_TRY(arena(c, SL_STAGE_OL, cframes, &ol[0])); if (nchunks > 1) MM_TRY(arena(c, SL_STAGE_OL1, cframes, &ol[1])); }
+    MM_TRY(arena(c, SL_STAGE_IL, cframes * R, &il_ring));
+    for (int l = 0; l < L; ++l) MM_TRY(arena(lane[l], SL_STAGE_PL, pfloats, &pls[l]));
+    if (any_pcm) MM_TRY(arena(c, SL_STAGE_PCM, cframes * R, &pcm_ring));
+    if (any_noise) MM_TRY(arena(c, SL_STAGE_NOISE, cframes * R, &nz_ring));
+    if (any_f32) MM_TRY(arena(c, SL_STAGE_OL, cframes * R, &ol_ring));
     if (stats_host) MM_TRY(arena(c, SL_STATS, (size_t)tracks, &st));
+    auto il_of = [&](int k) { return il_ring + (size_t)(k % R) * cframes; };
+    auto ol_of = [&](int k) { return ol_ring ? ol_ring + (size_t)(k % R) * cframes : nullptr; };
+    auto nz_of = [&](int k) { return nz_ring ? nz_ring + (size_t)(k % R) * cframes : nullptr; };
+    auto pcm_of = [&](int k) { return pcm_ring ? pcm_ring + (size_t)(k % R) * cframes : nullptr; };
     // pageable inputs: a cudaMemcpyAsync from pageable memory runs at a few GB/s and holds the calling thread; instead the thread
     // copies chunk k + 1 into a pinned ring slot (while the device works on chunk k) and the slot crosses PCIe at link speed
     char *hpin[2] = {nullptr, nullptr}, *hpout[2] = {nullptr, nullptr};       // host_pin 0, 1: inputs; 2, 3: outputs
@@ -1257,6 +1373,7 @@ static int master_host_plan(mm_ctx* c, int chain, const std::vector<HostChunk>& 
     MM_CUDA(cudaEventRecord(ev_start, c->stream));
     MM_CUDA(cudaStreamWaitEvent(c->h2d_stream, ev_start, 0));
     MM_CUDA(cudaStreamWaitEvent(c->d2h_stream, ev_start, 0));
+    MM_TRY(lanes_fork(c, L));
     // one cudaMemcpyAsync per run of tracks whose host buffers lie back to back (the whole chunk, for the equal-shape entry points)
     auto copy_runs = [&](const HostChunk& ch, size_t elem, auto host_of, auto issue) -> int {
         const size_t per_track = (size_t)ch.n * ch.channels;
@@ -1272,8 +1389,8 @@ static int master_host_plan(mm_ctx* c, int chain, const std::vector<HostChunk>& 
     };
     auto copy_in = [&](int k) -> int {
         const HostChunk& ch = chunks[k];
-        if (k >= 2) MM_CUDA(cudaStreamWaitEvent(c->h2d_stream, ev_deint[k - 2], 0));    // staging buffer k & 1 is free again
-        char* dst = reinterpret_cast<char*>(il[k & 1]);
+        if (k >= R) MM_CUDA(cudaStreamWaitEvent(c->h2d_stream, ev_deint[k - R], 0));    // staging slot k % R is free again
+        char* dst = reinterpret_cast<char*>(il_of(k));
         if (stage_in) {
             if (k >= 2) MM_CUDA(cudaEventSynchronize(ev_in[k - 2]));                    // the ring slot has crossed the link
             const size_t per_track = (size_t)ch.n * ch.channels * in_elem;
@@ -1283,8 +1400,8 @@ static int master_host_plan(mm_ctx* c, int chain, const std::vector<HostChunk>& 
         MM_TRY(copy_runs(ch, in_elem, [](const HostTrack& t) { return t.in; }, [&](size_t off, const char* h, size_t bytes) {
             return cudaMemcpyAsync(dst + off * in_elem, h, bytes, cudaMemcpyHostToDevice, c->h2d_stream); }));
         if (any_noise) {
-            if (k >= 2) MM_CUDA(cudaStreamWaitEvent(c->h2d_stream, ev_done[k - 2], 0));
-            float* nd = nz[k & 1];
+            if (k >= R) MM_CUDA(cudaStreamWaitEvent(c->h2d_stream, ev_done[k - R], 0));
+            float* nd = nz_of(k);
             MM_TRY(copy_runs(ch, sizeof(float), [](const HostTrack& t) { return (const void*)t.noise; }, [&](size_t off, const char* h, size_t bytes) {
                 return cudaMemcpyAsync(nd + off, h, bytes, cudaMemcpyHostToDevice, c->h2d_stream); }));
         }
@@ -1312,32 +1429,34 @@ static int master_host_plan(mm_ctx* c, int chain, const std::vector<HostChunk>& 
         gk.track_base = ch.t0;                               // index of the chunk's first track in the call (dither counter)
         bool c_noise = false, c_f32 = false, c_pcm = false;
         for (int t = 0; t < ch.tn; ++t) { const HostTrack& h = trk[ch.t0 + t]; c_noise |= h.noise != nullptr; c_f32 |= h.out_f32 != nullptr; c_pcm |= h.out_pcm != nullptr; }
-        if ((rc = cudaStreamWaitEvent(c->stream, ev_in[k], 0) != cudaSuccess)) { set_error("cudaStreamWaitEvent failed"); break; }
-        if (pcm_in) { if ((rc = run_layout_pcm16(c, &gk, reinterpret_cast<const int16_t*>(il[k & 1]), pl)) != 0) break; }
-        else if ((rc = mm_dev_deinterleave(c, &gk, il[k & 1], pl)) != 0) break;
-        cudaEventRecord(ev_deint[k], c->stream);
-        if (k >= 2) cudaStreamWaitEvent(c->stream, ev_out[k - 2], 0);     // pcm / ol staging k & 1 has left the device
-        if ((rc = master_impl(c, &gk, chain, styles + ch.t0, pl, pl, c_pcm ? pcm[k & 1] : nullptr, c_noise ? nz[k & 1] : nullptr, seed,
+        mm_ctx* cl = lane[k % L];
+        float* pl = pls[k % L];
+        if ((rc = cudaStreamWaitEvent(cl->stream, ev_in[k], 0) != cudaSuccess)) { set_error("cudaStreamWaitEvent failed"); break; }
+        if (pcm_in) { if ((rc = run_layout_pcm16(cl, &gk, reinterpret_cast<const int16_t*>(il_of(k)), pl)) != 0) break; }
+        else if ((rc = mm_dev_deinterleave(cl, &gk, il_of(k), pl)) != 0) break;
+        cudaEventRecord(ev_deint[k], cl->stream);
+        if (k >= R) cudaStreamWaitEvent(cl->stream, ev_out[k - R], 0);     // pcm / ol staging slot k % R has left the device
+        if ((rc = master_impl(cl, &gk, chain, styles + ch.t0, pl, pl, c_pcm ? pcm_of(k) : nullptr, c_noise ? nz_of(k) : nullptr, seed,
                               st ? st + ch.t0 : nullptr, flags)) != 0) break;
-        if (c_f32 && (rc = mm_dev_interleave(c, &gk, pl, ol[k & 1])) != 0) break;
-        cudaEventRecord(ev_done[k], c->stream);
+        if (c_f32 && (rc = mm_dev_interleave(cl, &gk, pl, ol_of(k))) != 0) break;
+        cudaEventRecord(ev_done[k], cl->stream);
         cudaStreamWaitEvent(c->d2h_stream, ev_done[k], 0);
         if (stage_in) {
             // pageable outputs: the chunk lands in a pinned ring slot; the thread hands it to the caller's buffers one chunk later
             // (a device->pageable cudaMemcpyAsync would hold the thread until chunk k is done, with chunk k + 1's chain not yet queued)
             if (k >= 2 && (rc = drain_out(k - 2)) != 0) break;
             const size_t cnt = (size_t)ch.tn * ch.n * ch.channels;
-            if (c_pcm && cudaMemcpyAsync(hpout[k & 1], pcm[k & 1], cnt * sizeof(int16_t), cudaMemcpyDeviceToHost, c->d2h_stream) != cudaSuccess) rc = 1;
-            if (c_f32 && cudaMemcpyAsync(hpout[k & 1] + out_f32_off, ol[k & 1], cnt * sizeof(float), cudaMemcpyDeviceToHost, c->d2h_stream) != cudaSuccess) rc = 1;
+            if (c_pcm && cudaMemcpyAsync(hpout[k & 1], pcm_of(k), cnt * sizeof(int16_t), cudaMemcpyDeviceToHost, c->d2h_stream) != cudaSuccess) rc = 1;
+            if (c_f32 && cudaMemcpyAsync(hpout[k & 1] + out_f32_off, ol_of(k), cnt * sizeof(float), cudaMemcpyDeviceToHost, c->d2h_stream) != cudaSuccess) rc = 1;
             if (rc) { set_error("mm_master_host: copy failed"); break; }
         } else {
         if (c_f32) {
-            const float* src = ol[k & 1];
+            const float* src = ol_of(k);
             rc = copy_runs(ch, sizeof(float), [](const HostTrack& t) { return (const void*)t.out_f32; }, [&](size_t off, const char* h, size_t bytes) {
                 return cudaMemcpyAsync(const_cast<char*>(h), src + off, bytes, cudaMemcpyDeviceToHost, c->d2h_stream); });
         }
         if (rc == 0 && c_pcm) {
-            const int16_t* src = pcm[k & 1];
+            const int16_t* src = pcm_of(k);
             rc = copy_runs(ch, sizeof(int16_t), [](const HostTrack& t) { return (const void*)t.out_pcm; }, [&](size_t off, const char* h, size_t bytes) {
                 return cudaMemcpyAsync(const_cast<char*>(h), src + off, bytes, cudaMemcpyDeviceToHost, c->d2h_stream); });
         }
@@ -1346,6 +1465,10 @@ static int master_host_plan(mm_ctx* c, int chain, const std::vector<HostChunk>& 
     }
     if (stage_in)
         for (int k = std::max(0, nchunks - 2); k < nchunks && rc == 0; ++k) rc = drain_out(k);
+    {
+        const int rj = lanes_join(c, L);           // the parent's stream (the stats copy, the caller's next call) follows every lane
+        if (rc == 0) rc = rj;
+    }
     if (rc == 0 && stats_host) {
         if (cudaMemcpyAsync(stats_host, st, (size_t)tracks * sizeof(mm_track_stats), cudaMemcpyDeviceToHost, c->stream) != cudaSuccess) {
             set_error("copy of the track stats failed");

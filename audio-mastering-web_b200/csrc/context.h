@@ -107,6 +107,13 @@ struct mm_ctx {
     int64_t workspace_bytes = 0;
     std::map<const void*, int> occupancy;   // kernel -> resident CTAs per SM on THIS device (attributes set when the entry is made)
     int num_sms = 0;
+    // LANES: child contexts (own stream, own workspace and plan caches) a call may spread its sub-batches / chunks over so that
+    // the tails, launch gaps and dependent-kernel bubbles of one chain are filled by another's kernels.  lanes[i] is lane i + 1;
+    // lane 0 is this context.  Owned by the parent, created lazily, never shared between threads (contexts are per thread).
+    std::vector<mm_ctx*> lanes;
+    int lanes_cfg = 0;                      // 0: automatic (MM_LANES or the entry point's default); >= 1: fixed (mm_ctx_set_lanes)
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;   // parent: "everything queued so far"; lane: "this lane's part of the call is queued"
+    int grid_div = 1;                       // persistent grids are sized for 1 / grid_div of the device (lanes of mm_master_host_jobs share it)
     std::map<int, float*> lp_taps;          // linear-phase target-curve IR per sample rate (device)
     uint64_t tick = 0;                      // use counter of the plan caches (least-recently-used eviction at API entry)
     void* bigfft = nullptr;             // bigfft.cu's plan cache (FFT tables, chirp-filter spectra); owned by the context: contexts are per thread

@@ -109,7 +109,8 @@ static int launch_sweep2(mm_ctx* c, SweepArgs<M, NF>* As, int whalo, const char*
     A.ntiles = DIR > 0 ? tiles_fwd(A.n, A.pad) : tiles_bwd(A.n, A.pad);
     if ((size_t)A.rows * (size_t)A.ntiles == 0) return 0;
     constexpr int kSW = Cfg::kSW, kSweepThreads = Cfg::kThreads;
-    const int capacity = std::max(1, c->num_sms * blocks_per_sm * kSW);      // warps in flight = independent workers
+    // warps in flight = independent workers (a lane context sizes its grid for its share of the device)
+    const int capacity = std::max(kSW, c->num_sms * blocks_per_sm / std::max(1, c->grid_div) * kSW);
     Sweep2Args<M, NF, 1> PP;
     PP.whalo = whalo;                                // warp-tiles (ScanTables::Wq)
     choose_segments(A.rows, A.ntiles, PP.whalo, capacity, &PP.nseg, &PP.seglen);
@@ -741,7 +742,7 @@ int st_lufs(mm_ctx* c, const mm_geom* g, const float* in, const Pro& pro, double
         const int smem = S == 64 ? LufsCfg<64>::kSmem : LufsCfg<32>::kSmem;
         int bps = 0;
         MM_TRY(kernel_setup(c, (const void*)kern, kT, smem, true, &bps));
-        const int capacity = std::max(1, bps) * c->num_sms;
+        const int capacity = std::max(1, std::max(1, bps) * c->num_sms / std::max(1, c->grid_div));
         LufsArgs A;
         memset(&A, 0, sizeof(A));
         for (int j = 0; j < S; ++j) {

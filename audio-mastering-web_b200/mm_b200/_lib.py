@@ -127,6 +127,7 @@ SIGNATURES = {
     "mm_master_host_jobs": (_i, [_vp, _i, C.c_int32, C.POINTER(HostJob), _u64, _u32]),
     "mm_host_alloc": (_i, [C.POINTER(_vp), _i64]),
     "mm_host_free": (_i, [_vp]),
+    "mm_ctx_set_lanes": (_i, [_vp, _i]),
     "mm_ctx_copy_in": (_i, [_vp, _vp, _vp, _i64]),
     "mm_ctx_copy_out": (_i, [_vp, _vp, _vp, _i64]),
     "mm_ctx_workspace_bytes": (_i64, [_vp]),

@@ -136,6 +136,10 @@ class Engine:
         otherwise)."""
         _lib.check(self.lib.mm_ctx_release_workspace(self.ctx))
 
+    def set_lanes(self, lanes: int):
+        """0 = automatic, 1 = one stream, up to 8 (mm_ctx_set_lanes): concurrent sub-batches / chunks of one call."""
+        _lib.check(self.lib.mm_ctx_set_lanes(self.ctx, int(lanes)))
+
     def sync(self):
         _lib.check(self.lib.mm_ctx_sync(self.ctx))
 

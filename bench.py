@@ -478,7 +478,9 @@ def bench_batch(rt, args, *, chain, mixed, steps, warmup, main, envelope=False):
             with torch.cuda.stream(eng.stream):
                 shard.gather_track_stats(stats, world * tracks, world, rank)
 
-    tm = timed_steps(rt, step, steps, warmup, clocks=main)
+    # the K timed steps run without per-kernel events and with the library's lanes (the batch split over concurrent streams); the
+    # per-kernel table comes from K further steps with events on, which the library runs on ONE stream so a kernel is timed alone
+    tm = timed_steps(rt, step, steps, warmup, clocks=main, separate_kernel_pass=True)
     ms = tm["ms"]
     value = world * tracks * dur * steps / (ms * 1e-3)
 
@@ -621,6 +623,10 @@ def bench_batch(rt, args, *, chain, mixed, steps, warmup, main, envelope=False):
         alg_per_frame = float(tt.item()) / world
     chain_gbs = alg_per_frame * tracks * n * world * steps / (ms * 1e-3) / 1e9
     roofline["chain"] = {"algorithmic_bytes_per_stereo_frame": alg_per_frame, "achieved": chain_gbs / world, "frac": chain_gbs / world / peak}
+    roofline["note"] = ("per-kernel times: a separate pass of K steps with CUDA events around every launch, run by the library on ONE stream "
+                        "(a kernel timed alone, over the whole batch); the K timed steps of `value` run without those events and with the "
+                        "batch split over the lanes, whose kernels overlap -- so the step is shorter than the sum of the per-kernel times "
+                        f"({sum(v[0] for v in tm['ktimes'].values()) / steps:.2f} ms)")
     cfg = {"workload": (f"configs[2]: {tracks} synthetic {dur:.0f} s {sr} Hz stereo tracks per GPU, genre presets cycling over the "
                         f"global track index (STYLE_CONFIGS order) at their own LUFS targets, {chain} chain + TPDF int16 + after-LUFS"
                         if mixed else
@@ -628,6 +634,8 @@ def bench_batch(rt, args, *, chain, mixed, steps, warmup, main, envelope=False):
                         f"(style standard, -14 LUFS) + TPDF dither to int16 + after-LUFS"),
            "chain": chain, "compressor": "envelope (pedalboard-style, parity unpinned)" if envelope else "soft_knee (pinned)",
            "tracks_per_gpu": tracks, "frames_per_track": n,
+           "lanes": "MM_LANES=" + os.environ.get("MM_LANES", "auto") + ": mm_dev_master spreads the batch over concurrent streams (auto: two "
+                    "halves); every timed step covers the whole batch",
            "cache": f"inputs ({tracks * n * 8 / 1e9:.2f} GB per GPU) exceed L2; no flush needed",
            "precision_policy": "MM_PASS2=" + os.environ.get("MM_PASS2", "auto") + ": float32 streams; float64 chunk scan everywhere; in-chunk "
                                "recurrences float64 (full-path low cut-offs) or float32 FFMA2 on balanced realizations (DESIGN.md)"}

@@ -342,6 +342,13 @@ int mm_host_free(void* p);
 int mm_ctx_copy_in(mm_ctx*, void* dev_dst, const void* host_src, int64_t bytes);
 int mm_ctx_copy_out(mm_ctx*, void* host_dst, const void* dev_src, int64_t bytes);
 
+/* Lanes: how many child contexts (own stream and workspace, created on demand, owned by this context) a call may spread its
+ * work over -- mm_dev_master splits a batch into that many runs of tracks (automatic: 2), the host entries send consecutive chunks
+ * to consecutive lanes (automatic: 4).  One chain is ~21 dependent kernels and a second stream's kernels fill the tails and launch
+ * gaps of the first: 64 one-track chains 169 -> 251 k audio-s/s, the 64-track batch 279 -> ~290 k.  Results do not depend on it.
+ * 0 = automatic (or MM_LANES), 1 = everything on the context's own stream.  No reference counterpart (an execution policy). */
+int mm_ctx_set_lanes(mm_ctx*, int lanes);
+
 /* Bytes of device workspace the context currently holds (for sizing sub-batches). */
 int64_t mm_ctx_workspace_bytes(mm_ctx*);
 /* Workspace the chain needs for a geometry (rows * stride * 4 * k + carries). */

@@ -393,3 +393,35 @@ def test_64_uploads_of_64_different_lengths_in_one_call(P):
     bad[0].n, bad[0].channels, bad[0].sr = 0, 2, sr
     assert eng.lib.mm_master_host_jobs(eng.ctx, _lib.CHAIN_V2, 1, bad, 0, 0) != 0
     assert "job 0" in _lib.last_error()
+
+
+def test_results_do_not_depend_on_the_lanes(P):
+    """mm_ctx_set_lanes: a call may spread its sub-batches (mm_dev_master) or chunks (host entries) over child contexts with their
+    own streams and workspaces.  An execution policy only: samples, int16 (Philox stream keyed by the track's index in the call) and
+    stats are bit-identical for 1, 2, 3 and 5 lanes, for a mixed-preset batch and for a list of uploads of different shapes."""
+    from mm_b200 import synth, wavio
+    from mm_b200.engine import get_engine
+    eng = get_engine()
+    sr = 48000
+    styles = ["standard", "edm", "lofi", "podcast", "hiphop", "classical", "house_basic"]
+    xs = [synth.numpy_track(500 + i, sr, 2.5) for i in range(len(styles))]
+    specs = [(44100, 1.3, 2), (48000, 0.9, 2), (44100, 2.1, 1), (44100, 1.3, 2), (44100, 0.8, 2), (96000, 0.6, 2), (44100, 1.7, 2)]
+    wavs = [wavio.pack_wav_pcm16(np.round(synth.numpy_track(520 + i, s, d, channels=c) * 32767.0).astype(np.int16), s)
+            for i, (s, d, c) in enumerate(specs)]
+    ref = {}
+    try:
+        for lanes in (1, 2, 3, 5):
+            eng.set_lanes(lanes)
+            for chain in ("v2", "v1"):
+                r = P.master_batch(xs, sr, styles, chain=chain, want_int16=True, measure=True, seed=11)
+                jobs = P.master_wav_jobs(wavs, styles, chain=chain, seed=5)
+                got = ([a.tobytes() for a in r["audio"]], [q.tobytes() for q in r["int16"]],
+                       [(s["lufs_in"], s["lufs_out"], s["gain_db"], s["peak_out"]) for s in r["stats"]],
+                       [j["wav"] for j in jobs], [j["stats"]["lufs_out"] for j in jobs])
+                if lanes == 1:
+                    ref[chain] = got
+                else:
+                    for part, (a, b) in enumerate(zip(ref[chain], got)):
+                        assert a == b, (lanes, chain, part)
+    finally:
+        eng.set_lanes(0)
