@@ -2,12 +2,14 @@
 
 The reference's hot path is pure Python (``backend/app/pipeline.py``, ``chain.py``, ``modules/*``): there is nothing to link, so
 "building" it means byte-compiling the modules the path imports, from the sources WHERE THEY LIE under ``/root/reference``, into
-sourceless ``.pyc`` files under ``oracle/_ref/backend/`` (git-ignored, NOT gpurun-ignored: like our own ``.so`` it travels to the
-GPU box, where ``/root/reference`` does not exist).  No reference source text is copied into the repository.
+compiled-code files under ``oracle/_ref/backend/`` (``<module>.bin``: the ``.pyc`` layout -- 16-byte header + marshalled code object --
+under another extension, because the GPU-box snapshot drops ``*.pyc``; ``oracle/ref_harness.py`` imports them through a small
+finder).  Git-ignored, NOT gpurun-ignored: like our own ``.so`` the directory travels to the GPU box, where ``/root/reference`` does
+not exist.  No reference source text is copied into the repository.
 
 What gets compiled is decided by importing the path through ``oracle/ref_harness.py`` and listing the modules that came from
 the reference tree, plus the two numeric helpers of ``app/routers/tools.py`` (``_true_peak_dbfs``, ``_loudness_range_lu``), whose
-function definitions alone are compiled into ``app/_tools_numeric.pyc`` (the router module itself drags FastAPI in).
+function definitions alone are compiled into ``app/_tools_numeric.bin`` (the router module itself drags FastAPI in).
 
 Users: ``bench.py --impl reference`` and the ``cpu_baseline`` leg (``kind: "reference"``), ``tests/test_oracle_vs_reference.py``
 (which prefers the source tree when it exists).  ``__graft_entry__.build()`` runs this where ``/root/reference`` is present.
@@ -23,6 +25,7 @@ import sys
 _HERE = os.path.dirname(os.path.abspath(__file__))
 OUT = os.path.join(_HERE, "_ref", "backend")
 SRC = "/root/reference/backend"
+EXT = ".bin"
 
 
 def _write_pyc(code, dst: str, mtime: int = 0, size: int = 0) -> None:
@@ -54,17 +57,17 @@ def build(verbose: bool = True) -> str | None:
         rel = os.path.relpath(path, SRC)
         with open(path, "rb") as f:
             data = f.read()
-        # The code objects name the .pyc itself as their file: numba's `cache=True` (pipeline.py:25-26) stats the function's
+        # The code objects name the compiled file itself as their file: numba's `cache=True` (pipeline.py:25-26) stats the function's
         # file for its cache index and refuses to decorate when it does not exist -- /root/reference does not on the GPU box,
         # /root/repo/oracle/_ref/... does (there /root/repo is a link to the snapshot).
-        dst = os.path.join(OUT, rel + "c")
+        dst = os.path.join(OUT, rel[:-3] + EXT)
         code = compile(data, dst, "exec", dont_inherit=True, optimize=0)
         _write_pyc(code, dst, int(os.stat(path).st_mtime), len(data))
     # the two numeric helpers of routers/tools.py, as oracle/ref_harness.py extracts them from the source tree
     tools = os.path.join(SRC, "app", "routers", "tools.py")
     tree = ast.parse(open(tools, encoding="utf-8").read())
     keep = [n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name in ("_true_peak_dbfs", "_loudness_range_lu")]
-    _write_pyc(compile(ast.Module(body=keep, type_ignores=[]), tools, "exec"), os.path.join(OUT, "app", "_tools_numeric.pyc"))
+    _write_pyc(compile(ast.Module(body=keep, type_ignores=[]), tools, "exec"), os.path.join(OUT, "app", "_tools_numeric" + EXT))
     if verbose:
         print(f"oracle/_ref: {len(mods)} reference modules byte-compiled into {OUT}")
     return OUT

@@ -5,7 +5,7 @@ in this image (``pyloudnorm``, ``soundfile``, ``pydub``; ``backend/app/pipeline.
 This module injects small stand-ins for exactly those three names into ``sys.modules`` and then
 imports ``app.pipeline`` / ``app.chain`` / ``app.routers.tools`` helpers from the read-only
 reference tree.  No reference source is copied into the repository.  Where ``/root/reference`` does not exist
-(the GPU box) the same modules are imported from ``oracle/_ref/backend``: sourceless ``.pyc`` files that
+(the GPU box) the same modules are imported from ``oracle/_ref/backend``: compiled-code files (``*.bin``) that
 ``oracle/make_ref.py`` byte-compiled from the tree (the "built reference" of this pure-Python path).  Used by
 ``tests/golden/make_golden*.py``, by ``tests/test_oracle_vs_reference.py`` (pins ``oracle/chain.py`` against the
 reference's own arithmetic) and by ``bench.py``'s CPU legs (``--impl reference``, ``cpu_baseline``).
@@ -26,14 +26,51 @@ import types
 
 _REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 # The source tree where it exists (the build container); else the byte-compiled copy oracle/make_ref.py built from it
-# (oracle/_ref/backend: sourceless .pyc files, git-ignored, shipped to the GPU box like a built .so).
+# (oracle/_ref/backend: compiled-code files, git-ignored, shipped to the GPU box like a built .so).
 PREBUILT_BACKEND = os.path.join(_REPO, "oracle", "_ref", "backend")
 REFERENCE_BACKEND = os.environ.get("MM_REFERENCE_BACKEND") or (
     "/root/reference/backend" if os.path.isfile("/root/reference/backend/app/pipeline.py") else PREBUILT_BACKEND)
 
 
+PREBUILT_EXT = ".bin"      # oracle/make_ref.py: .pyc layout under another name (the GPU-box snapshot drops *.pyc)
+
+
 def _has(backend: str) -> bool:
-    return any(os.path.isfile(os.path.join(backend, "app", "pipeline" + ext)) for ext in (".py", ".pyc"))
+    return any(os.path.isfile(os.path.join(backend, "app", "pipeline" + ext)) for ext in (".py", PREBUILT_EXT))
+
+
+def _load_code(path: str):
+    import marshal
+    with open(path, "rb") as f:
+        return marshal.loads(f.read()[16:])
+
+
+class _PrebuiltFinder:
+    """Imports ``app`` / ``app.*`` from the compiled-code files of oracle/_ref/backend (``<module>.bin``, ``<package>/__init__.bin``)."""
+
+    def __init__(self, root: str):
+        self.root = root
+
+    def find_spec(self, fullname, path=None, target=None):
+        if fullname != "app" and not fullname.startswith("app."):
+            return None
+        from importlib.util import spec_from_loader
+        rel = os.path.join(self.root, *fullname.split("."))
+        if os.path.isfile(os.path.join(rel, "__init__" + PREBUILT_EXT)):
+            spec = spec_from_loader(fullname, self, origin=os.path.join(rel, "__init__" + PREBUILT_EXT), is_package=True)
+            spec.submodule_search_locations = [rel]
+            return spec
+        if os.path.isfile(rel + PREBUILT_EXT):
+            return spec_from_loader(fullname, self, origin=rel + PREBUILT_EXT)
+        return None
+
+    def create_module(self, spec):
+        return None
+
+    def exec_module(self, module):
+        origin = module.__spec__.origin
+        module.__file__ = origin
+        exec(_load_code(origin), module.__dict__)  # noqa: S102 - the reference's own byte-compiled module
 
 
 def available() -> bool:
@@ -96,9 +133,7 @@ def _numba_cache_guard():
     stats the file named in the function's code object for its cache index and raises at decoration time when it is missing.
     oracle/make_ref.py records the .pyc's own path under /root/repo there; if the copy was moved somewhere else, JIT-compile
     without the on-disk cache instead of failing (same machine code, compiled once per process)."""
-    import marshal
-    with open(os.path.join(REFERENCE_BACKEND, "app", "pipeline.pyc"), "rb") as f:
-        recorded = marshal.loads(f.read()[16:]).co_filename
+    recorded = _load_code(os.path.join(REFERENCE_BACKEND, "app", "pipeline" + PREBUILT_EXT)).co_filename
     if os.path.exists(recorded):
         return
     try:
@@ -123,9 +158,11 @@ def load():
     _install_standins()
     # numba's on-disk cache would try to write next to the read-only reference file
     os.environ.setdefault("NUMBA_CACHE_DIR", "/tmp/mm_numba_cache")
-    if REFERENCE_BACKEND not in sys.path:
-        sys.path.insert(0, REFERENCE_BACKEND)
-    if not is_source_tree():
+    if is_source_tree():
+        if REFERENCE_BACKEND not in sys.path:
+            sys.path.insert(0, REFERENCE_BACKEND)
+    else:
+        sys.meta_path.insert(0, _PrebuiltFinder(REFERENCE_BACKEND))
         _numba_cache_guard()
     pipeline = importlib.import_module("app.pipeline")
     chain = importlib.import_module("app.chain")
@@ -143,9 +180,7 @@ def load():
         keep = [n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name in ("_true_peak_dbfs", "_loudness_range_lu")]
         code = compile(ast.Module(body=keep, type_ignores=[]), src_path, "exec")
     else:                                           # prebuilt copy: the same two definitions, compiled by oracle/make_ref.py
-        import marshal
-        with open(os.path.join(REFERENCE_BACKEND, "app", "_tools_numeric.pyc"), "rb") as f:
-            code = marshal.loads(f.read()[16:])
+        code = _load_code(os.path.join(REFERENCE_BACKEND, "app", "_tools_numeric" + PREBUILT_EXT))
     g = {"np": np, "resample_poly": resample_poly, "compute_lufs_timeline": pipeline.compute_lufs_timeline}
     exec(code, g)  # noqa: S102 - reference code, run as the oracle's oracle
     ns.true_peak_dbfs = g["_true_peak_dbfs"]

@@ -105,7 +105,7 @@ def test_prebuilt_reference_copy_runs_sourceless_and_equals_the_oracle(tmp_path)
         "from mm_b200 import synth\n"
         "assert ref_harness.available() and not ref_harness.is_source_tree()\n"
         "ref = ref_harness.load()\n"
-        "assert ref.pipeline.__file__.endswith('.pyc')\n"
+        "assert ref.pipeline.__file__.endswith('.bin')\n"
         "x = synth.numpy_track(77, 48000, 3.0)\n"
         "r1 = ref.pipeline.run_mastering_pipeline(x.copy(), 48000, target_lufs=-9.0, style='edm')\n"
         "assert np.array_equal(r1, oc.run_v1(x.copy(), 48000, -9.0, 'edm'))\n"
