@@ -30,8 +30,16 @@
 namespace mm {
 
 constexpr int kBcThreads = 32;
-constexpr int kBcDepth = 4;                 // lines in flight per thread and stream
-constexpr int kBcLine = 16;                 // samples per line (64 bytes)
+// ring geometry, measured with the cooperative fetch (64 x 180 s, ms per launch; MM_BC_DEPTH x MM_BC_LINE samples): 2 x 16: 7.2,
+// 3 x 16: 7.4, 4 x 16: 8.1, 2 x 32: 8.0, 3 x 32: 10.3, 2..4 x 8: 8.8 -- 16 KB per one-warp CTA (13 warps per SM) wins
+#ifndef MM_BC_DEPTH
+#define MM_BC_DEPTH 2
+#endif
+#ifndef MM_BC_LINE
+#define MM_BC_LINE 16
+#endif
+constexpr int kBcDepth = MM_BC_DEPTH;       // lines in flight per thread and stream
+constexpr int kBcLine = MM_BC_LINE;         // samples per line (64 bytes)
 
 struct BandCompArgs {
     const float* band[4];
@@ -68,33 +76,63 @@ __device__ __forceinline__ float bc_gain(float e, float thr, float thr_inv, floa
 }
 
 // ENV: bit k set = band k runs the envelope compressor (compile-time for the default configuration 0b1110: band 0 has ratio 1)
+//
+// Fetch pattern.  Lane l walks chunk l of the warp, so the 32 lanes read 32 different places of a row; the first version let
+// every lane copy its OWN line (cp.async, 16 bytes at a time): each warp-level copy instruction touched 32 different 128-byte
+// lines = 32 trips through the L1 / LSU pipeline, one instruction per band and four samples -- about one LSU wavefront per
+// sample and SM cycle, which is what bounded the kernel (9.5 ms per 64-track batch whatever the occupancy: 6 or 13 warps per SM,
+// 32- or 64-byte lines all measured the same).  Now the lanes fetch COOPERATIVELY: kUnits consecutive lanes copy the kUnits
+// 16-byte units of ONE chunk's line, so an instruction touches 32 / kUnits lines, each completely (8x fewer wavefronts with
+// 128-byte lines); a __syncwarp() hands the landed lines to their owners.  Trip counts are uniform across the warp (a chunk
+// without a left neighbourhood or with a short tail just skips the lines outside [0, n)).
 template <int ENV>
 __global__ void __launch_bounds__(kBcThreads) band_compress_kernel(const __grid_constant__ BandCompArgs P) {
     __shared__ __align__(128) float ring[kBcDepth][4][kBcThreads][kBcLine];
+    constexpr int kUnits = kBcLine / 4;                          // 16-byte units per line = lanes that fetch one line together
+    constexpr int kLPI = 32 / kUnits;                            // lines one warp-level copy instruction covers
+    constexpr int kSxShift = kUnits >= 8 ? 0 : (kUnits == 4 ? 1 : 2);
     const int lane = threadIdx.x;
     const long long gid = (long long)blockIdx.x * kBcThreads + lane;
     const long long total = (long long)P.rows * P.nchunks;
     const bool active = gid < total;
     const int row = active ? (int)(gid / P.nchunks) : 0;
     const int chunk = active ? (int)(gid % P.nchunks) : 0;
-    const size_t ro = (size_t)row * (size_t)P.stride + kLead;
+    const long long ro = (long long)row * P.stride + kLead;
     const long long live0 = (long long)chunk * P.chunk;
-    const long long live1 = active ? min(live0 + P.chunk, P.n) : live0;
-    const long long start = max(live0 - P.halo, 0LL);
-    const int nlines = active ? (int)((live1 - start + kBcLine - 1) / kBcLine) : 0;
-    const int halo_lines = active ? (int)((live0 - start) / kBcLine) : 0;
-    const int sx = (lane >> 1) & 3;                              // 16-byte unit swizzle: a quarter-warp's float4 reads hit 8 bank groups
+    const long long pos0 = live0 - P.halo;                       // position of line 0 (negative: no left neighbourhood, lines skipped)
+    const long long hi = active ? min(live0 + P.chunk, P.n) : pos0;
+    const int halo_lines = (int)(P.halo / kBcLine);
+    const int nlines = halo_lines + (int)(P.chunk / kBcLine);    // uniform; P.halo and P.chunk are multiples of kBcLine
+    // lines of this lane's chunk that hold samples of [0, n): [my_lo, my_hi)
+    const int my_lo = pos0 < 0 ? (int)((-pos0) / kBcLine) : 0;
+    const int my_hi = hi > pos0 ? (int)((hi - pos0 + kBcLine - 1) / kBcLine) : 0;
+    // 16-byte unit swizzle: a quarter-warp's float4 reads of its own rows hit 8 different bank groups
+    auto sx_of = [&](int l) -> int { return (l >> kSxShift) & (kUnits - 1); };
+    const int sx = sx_of(lane);
     auto env_on = [&](int k) -> bool { return ENV >= 0 ? ((ENV >> k) & 1) != 0 : P.env[k] != 0; };
+    // the chunks this lane helps to fetch: in copy instruction q, chunk-lane q * kLPI + lane / kUnits, unit lane % kUnits
+    const int fu = lane % kUnits;
+    long long p_off[kUnits];
+    int p_lo[kUnits], p_hi[kUnits], p_dst[kUnits];
+#pragma unroll
+    for (int q = 0; q < kUnits; ++q) {
+        const int cl = q * kLPI + lane / kUnits;
+        p_off[q] = __shfl_sync(0xffffffffu, ro + pos0, cl) + 4 * fu;
+        p_lo[q] = __shfl_sync(0xffffffffu, my_lo, cl);
+        p_hi[q] = __shfl_sync(0xffffffffu, my_hi, cl);
+        p_dst[q] = cl * kBcLine + 4 * (fu ^ sx_of(cl));
+    }
     auto fetch = [&](int line) {
         if (line < nlines) {
             const bool live = line >= halo_lines;
+            float* slot = &ring[line % kBcDepth][0][0][0];
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 if (!live && !env_on(k)) continue;              // a halo only feeds the followers
-                const float* g = P.band[k] + ro + start + (long long)kBcLine * line;
-                float* s = &ring[line % kBcDepth][k][lane][0];
+                const float* g = P.band[k] + (long long)kBcLine * line;
 #pragma unroll
-                for (int u = 0; u < 4; ++u) bc_cp16(s + 4 * (u ^ sx), g + 4 * u);
+                for (int q = 0; q < kUnits; ++q)
+                    if (line >= p_lo[q] && line < p_hi[q]) bc_cp16(slot + k * (kBcThreads * kBcLine) + p_dst[q], g + p_off[q]);
             }
         }
         asm volatile("cp.async.commit_group;\n" ::: "memory");
@@ -105,10 +143,13 @@ __global__ void __launch_bounds__(kBcThreads) band_compress_kernel(const __grid_
     // halo: only the states matter.  Loops over the units of a line are rolled: the body has to stay inside the instruction cache
 #pragma unroll 1
     for (int line = 0; line < halo_lines; ++line) {
+        __syncwarp();                                            // every lane is done with the slot the next fetch refills
         fetch(line + kBcDepth - 1);
         asm volatile("cp.async.wait_group %0;\n" ::"n"(kBcDepth - 1) : "memory");
+        __syncwarp();                                            // the partners' copies of this lane's line have landed
+        if (line < my_lo || line >= my_hi) continue;
 #pragma unroll 1
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < kUnits; ++u) {
             float4 v[4];
 #pragma unroll
             for (int k = 0; k < 4; ++k)
@@ -129,11 +170,14 @@ __global__ void __launch_bounds__(kBcThreads) band_compress_kernel(const __grid_
     float* dst = P.out + ro;
 #pragma unroll 1
     for (int line = halo_lines; line < nlines; ++line) {
+        __syncwarp();
         fetch(line + kBcDepth - 1);
         asm volatile("cp.async.wait_group %0;\n" ::"n"(kBcDepth - 1) : "memory");
-        const long long i0 = start + (long long)kBcLine * line;
+        __syncwarp();
+        if (line >= my_hi) continue;
+        const long long i0 = pos0 + (long long)kBcLine * line;
 #pragma unroll 1
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < kUnits; ++u) {
             float4 v[4];
 #pragma unroll
             for (int k = 0; k < 4; ++k) v[k] = *reinterpret_cast<const float4*>(&ring[line % kBcDepth][k][lane][4 * (u ^ sx)]);
