@@ -82,9 +82,16 @@ template <int MODE> __device__ __forceinline__ float env_step(float e, float ep,
 // One thread = one chunk (+ its halo) of one row: a strictly sequential recurrence, so the kernel is
 // latency bound by design; each thread streams its samples through a private ring of 128-byte lines in
 // shared memory (cp.async, kEnvDepth lines in flight) so that HBM latency never sits on the chain.
-constexpr int kEnvDepth = 4;
+#ifndef MM_ENV_DEPTH
+#define MM_ENV_DEPTH 4
+#endif
+constexpr int kEnvDepth = MM_ENV_DEPTH;
 constexpr int kEnvThreads = 32;
 
+// Lines are fetched COOPERATIVELY (as in bandcomp.cu): lane l walks chunk l, but eight consecutive lanes copy the eight 16-byte
+// units of ONE chunk's line, so a warp-level cp.async touches 4 lines completely instead of 32 lines partially (one trip through
+// the L1 / LSU pipeline per touched line: the per-lane pattern spent 32 trips per instruction).  Trip counts are uniform across
+// the warp; a chunk with a truncated left neighbourhood or a short tail skips the lines outside its range.
 template <int MODE> __global__ void __launch_bounds__(kEnvThreads) envelope_gain_kernel(const EnvArgs P) {
     __shared__ __align__(128) float ring[kEnvDepth][kEnvThreads][32];
     const int lane = threadIdx.x;
@@ -93,19 +100,36 @@ template <int MODE> __global__ void __launch_bounds__(kEnvThreads) envelope_gain
     const bool active = gid < total;
     const int row = active ? (int)(gid / P.nchunks) : 0;
     const int chunk = active ? (int)(gid % P.nchunks) : 0;
-    const float* src = P.sc + (size_t)row * (size_t)P.stride + kLead;
-    float* dst = P.gain + (size_t)row * (size_t)P.stride + kLead;
+    const long long ro = (long long)row * P.stride + kLead;
+    const float* src = P.sc + ro;
+    float* dst = P.gain + ro;
     const long long live0 = (long long)chunk * P.chunk;
     const long long live1 = active ? min(live0 + P.chunk, P.n) : live0;
-    const long long start = max(live0 - P.halo, 0LL);
-    const int nlines = active ? (int)((live1 - start + 31) / 32) : 0;
+    const long long pos0 = live0 - P.halo;                     // position of line 0; negative: the chunk starts at sample 0
+    const long long start = max(pos0, 0LL);
+    const int halo_lines = (int)(P.halo / 32);
+    const int nlines = halo_lines + (int)(P.chunk / 32);       // uniform (P.halo, P.chunk: multiples of 32)
+    const int my_lo = pos0 < 0 ? (int)((-pos0) / 32) : 0;      // this chunk's lines with samples of [0, n): [my_lo, my_hi)
+    const int my_hi = (active && live1 > pos0) ? (int)((live1 - pos0 + 31) / 32) : 0;
     const int sx = lane & 7;                                   // 16-byte unit swizzle of this thread's lines
+    const int fu = lane & 7;                                   // the unit this lane copies, of chunk-lane 4 q + lane / 8 in instruction q
+    long long p_off[8];
+    int p_lo[8], p_hi[8], p_dst[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        const int cl = 4 * q + (lane >> 3);
+        p_off[q] = __shfl_sync(0xffffffffu, ro + pos0, cl) + 4 * fu;
+        p_lo[q] = __shfl_sync(0xffffffffu, my_lo, cl);
+        p_hi[q] = __shfl_sync(0xffffffffu, my_hi, cl);
+        p_dst[q] = cl * 32 + 4 * (fu ^ (cl & 7));
+    }
     auto fetch = [&](int line) {
         if (line < nlines) {
-            const float* g = src + start + 32LL * line;
-            float* s = &ring[line % kEnvDepth][lane][0];
+            const float* g = P.sc + 32LL * line;
+            float* s = &ring[line % kEnvDepth][0][0];
 #pragma unroll
-            for (int u = 0; u < 8; ++u) cp_async16_env(s + 4 * (u ^ sx), g + 4 * u);
+            for (int q = 0; q < 8; ++q)
+                if (line >= p_lo[q] && line < p_hi[q]) cp_async16_env(s + p_dst[q], g + p_off[q]);
         }
         asm volatile("cp.async.commit_group;\n" ::: "memory");
     };
@@ -115,12 +139,14 @@ template <int MODE> __global__ void __launch_bounds__(kEnvThreads) envelope_gain
     // recurrence below needs no special case for the chunk's first sample
     float e = active ? fabsf(__ldg(src + start)) : 0.f;
     float ep = e;
-    const int halo_lines = active ? (int)((live0 - start) / 32) : 0;
     // halo: only the state matters -- 5 instructions per sample, all but two of them off the dependency chain
 #pragma unroll 1
     for (int line = 0; line < halo_lines; ++line) {
+        __syncwarp();                                          // every lane is done with the slot the next fetch refills
         fetch(line + kEnvDepth - 1);
         asm volatile("cp.async.wait_group %0;\n" ::"n"(kEnvDepth - 1) : "memory");
+        __syncwarp();                                          // the partners' copies of this lane's line have landed
+        if (line < my_lo || line >= my_hi) continue;
         const float* s = &ring[line % kEnvDepth][lane][0];
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
@@ -133,10 +159,13 @@ template <int MODE> __global__ void __launch_bounds__(kEnvThreads) envelope_gain
     }
 #pragma unroll 1
     for (int line = halo_lines; line < nlines; ++line) {
+        __syncwarp();
         fetch(line + kEnvDepth - 1);
         asm volatile("cp.async.wait_group %0;\n" ::"n"(kEnvDepth - 1) : "memory");
+        __syncwarp();
+        if (line >= my_hi) continue;
         const float* s = &ring[line % kEnvDepth][lane][0];
-        const long long i0 = start + 32LL * line;
+        const long long i0 = pos0 + 32LL * line;
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
             const float4 v = *reinterpret_cast<const float4*>(s + 4 * (u ^ sx));
@@ -251,7 +280,8 @@ static int launch_envelope(mm_ctx* c, const mm_geom* g, EnvArgs& A, double attac
     // chunk = halo / 2 (three times the work, short critical path) until the grid exceeds ~14 warps per SM.  Measured at the
     // bench size (972 one-warp CTAs): ring depth 8 (32 KB per CTA, 6 CTAs/SM = 888 slots) left a tail wave, 6.5 ms; depth 4
     // (12 CTAs/SM, one wave) 4.85 ms; chunk = halo / 4 (five times the work, twice the warps) 7.9 ms
-    long long chunk = std::max<long long>(((halo / 2 + 31) / 32) * 32, 4096);
+    static const int chunk_q = [] { const char* e = getenv("MM_ENV_CHUNK_Q"); const int v = e ? atoi(e) : 0; return v > 0 ? v : 2; }();   // chunk = halo * chunk_q / 4
+    long long chunk = std::max<long long>(((halo * chunk_q / 4 + 31) / 32) * 32, 4096);
     while ((long long)rows * ((g->n + chunk - 1) / chunk) > 148LL * 14 * 32 && chunk < nceil) chunk *= 2;
     A.chunk = chunk;
     A.nchunks = (int)((g->n + A.chunk - 1) / A.chunk);

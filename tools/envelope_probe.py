@@ -25,10 +25,11 @@ def main():
     out = eng.like(src)
     arr = (_lib.Style * tracks)(*[style_struct(P.STYLE_CONFIGS["standard"], -14.0)] * tracks)
     g = src.geom
-    flags = _lib.FLAG_MEASURE_OUT | _lib.FLAG_ENVELOPE_COMPRESSOR
+    flags = _lib.FLAG_MEASURE_OUT | (_lib.FLAG_ENVELOPE_COMPRESSOR if os.environ.get("ENVELOPE", "1") == "1" else 0)
+    chain_id = _lib.CHAIN_V1 if os.environ.get("CHAIN", "v2") == "v1" else _lib.CHAIN_V2
 
     def step(i):
-        _lib.check(eng.lib.mm_dev_master(eng.ctx, C.byref(g), _lib.CHAIN_V2, arr, src.ptr, out.ptr, C.c_void_p(pcm.data_ptr()), None,
+        _lib.check(eng.lib.mm_dev_master(eng.ctx, C.byref(g), chain_id, arr, src.ptr, out.ptr, C.c_void_p(pcm.data_ptr()), None,
                                          1234 + i, C.c_void_p(stats.data_ptr()), flags))
     for i in range(3):
         step(i)
@@ -48,7 +49,8 @@ def main():
     k = kt.get("band_envelope_compress")
     chk = float(out.live()[0:2, 1000:200000].double().abs().sum().item())
     print(json.dumps({"lib": os.path.basename(os.environ.get("MM_B200_LIB", "libmm_b200.so")), "ms_per_step": ms,
-                      "audio_s_per_s": tracks * dur / ms * 1e3, "band_envelope_compress_ms": k[0] / k[1] if k else None, "checksum": chk}))
+                      "audio_s_per_s": tracks * dur / ms * 1e3, "band_envelope_compress_ms": k[0] / k[1] if k else None, "checksum": chk,
+                      "followers_ms": {nm: v[0] / v[1] for nm, v in kt.items() if any(t in nm for t in ("env", "deess", "follow"))}}))
 
 
 if __name__ == "__main__":
