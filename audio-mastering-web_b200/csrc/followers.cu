@@ -58,19 +58,38 @@ __global__ void __launch_bounds__(kFolThreads) dual_follower_kernel(const FolArg
     const size_t r0 = (size_t)(unit * C) * (size_t)P.stride + kLead;
     const long long live0 = (long long)chunk * P.chunk;
     const long long live1 = active ? min(live0 + P.chunk, P.n) : live0;
-    const long long start = max(live0 - P.halo, 0LL);
-    const int nlines = active ? (int)((live1 - start + 31) / 32) : 0;
+    const long long pos0 = live0 - P.halo;                     // position of line 0; negative: the chunk starts at sample 0
+    const long long start = max(pos0, 0LL);
+    const int halo_lines = (int)(P.halo / 32);
+    const int nlines = halo_lines + (int)(P.chunk / 32);       // uniform across the warp (P.halo, P.chunk: multiples of 32)
+    const int my_lo = pos0 < 0 ? (int)((-pos0) / 32) : 0;      // this chunk's lines with samples of [0, n): [my_lo, my_hi)
+    const int my_hi = (active && live1 > pos0) ? (int)((live1 - pos0 + 31) / 32) : 0;
     const int sx = lane & 7;
+    // cooperative fetch (see deesser.cu): eight lanes copy the eight 16-byte units of one chunk's line -- a warp-level cp.async
+    // touches 4 lines completely instead of 32 partially
+    const int fu = lane & 7;
+    long long p_off[8];
+    int p_lo[8], p_hi[8], p_dst[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        const int cl = 4 * q + (lane >> 3);
+        p_off[q] = __shfl_sync(0xffffffffu, (long long)r0 + pos0, cl) + 4 * fu;
+        p_lo[q] = __shfl_sync(0xffffffffu, my_lo, cl);
+        p_hi[q] = __shfl_sync(0xffffffffu, my_hi, cl);
+        p_dst[q] = cl * 32 + 4 * (fu ^ (cl & 7));
+    }
     auto fetch = [&](int line) {
         if (line < nlines) {
 #pragma unroll
             for (int c = 0; c < C; ++c) {
-                const float* g = P.x + r0 + (size_t)c * (size_t)P.stride + start + 32LL * line;
-                float* s = &ring[c][line % kFolDepth][lane][0];
+                const float* g = P.x + (long long)c * P.stride + 32LL * line;
+                float* s = &ring[c][line % kFolDepth][0][0];
 #pragma unroll
-                for (int u = 0; u < 8; ++u) {
-                    const unsigned d = (unsigned)__cvta_generic_to_shared(s + 4 * (u ^ sx));
-                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(g + 4 * u) : "memory");
+                for (int q = 0; q < 8; ++q) {
+                    if (line >= p_lo[q] && line < p_hi[q]) {
+                        const unsigned d = (unsigned)__cvta_generic_to_shared(s + p_dst[q]);
+                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(g + p_off[q]) : "memory");
+                    }
                 }
             }
         }
@@ -87,15 +106,17 @@ __global__ void __launch_bounds__(kFolThreads) dual_follower_kernel(const FolArg
         const float a = __ldg(P.x + r0 + start), b = C > 1 ? __ldg(P.x + r0 + (size_t)P.stride + start) : 0.f;
         ef = es = detector(a, b);                                  // env[0] = |v0| (pipeline.py:499)
     }
-    const int halo_lines = active ? (int)((live0 - start) / 32) : 0;
     // the very first sample of the unit keeps env[0] = |v0| exactly: the recurrence starts at sample 1 there
     const bool first_exact = active && start == 0;
 #pragma unroll 1
     for (int line = 0; line < nlines; ++line) {
+        __syncwarp();                                          // every lane is done with the slot the next fetch refills
         fetch(line + kFolDepth - 1);
         asm volatile("cp.async.wait_group %0;\n" ::"n"(kFolDepth - 1) : "memory");
+        __syncwarp();                                          // the partners' copies of this lane's line have landed
+        if (line < my_lo || line >= my_hi) continue;
         const bool livel = line >= halo_lines;
-        const long long i0 = start + 32LL * line;
+        const long long i0 = pos0 + 32LL * line;
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
             const float4 va = *reinterpret_cast<const float4*>(&ring[0][line % kFolDepth][lane][4 * (u ^ sx)]);
@@ -106,7 +127,7 @@ __global__ void __launch_bounds__(kFolThreads) dual_follower_kernel(const FolArg
             for (int c = 0; c < 4; ++c) {
                 const float xa = comp4(va, c), xb = comp4(vb, c);
                 const float v = detector(xa, xb);
-                if (!(first_exact && line == 0 && u == 0 && c == 0)) {
+                if (!(first_exact && line == my_lo && u == 0 && c == 0)) {
                     ef = fol_step_branch(ef, v, P.f_atk, P.f_1matk, P.f_rel, P.f_1mrel);
                     es = fol_step_branch(es, v, P.s_atk, P.s_1matk, P.s_rel, P.s_1mrel);
                 }
