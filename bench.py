@@ -435,8 +435,11 @@ def bench_batch(rt, args, *, chain, mixed, steps, warmup, main, envelope=False):
     if mixed and world > 1:
         # presets cycle with period 8: plain t % world would hand a whole rank one preset at world = 8 (rank 1 all "edm", 676 B per
         # frame; rank 0 all "standard", 436) and the step would wait for the heaviest rank.  Rotated round-robin (SURVEY 8e:
-        # "round-robin or size-balanced by track") gives every rank every preset.
-        ids = [t for t in range(world * tracks) if (t + t // world) % world == rank]
+        # "round-robin or size-balanced by track"): the assignment shifts by one rank per period of the preset cycle, so every rank
+        # holds every preset in equal numbers whenever the world size divides the period (2, 4, 8 GPUs)
+        period = len(P.STYLE_CONFIGS)
+        rot = period if period % world == 0 else world
+        ids = [t for t in range(world * tracks) if (t + t // rot) % world == rank]
     with torch.cuda.stream(eng.stream):
         src.t.zero_()
         synth.torch_batch(ids, sr, dur, eng.tdev, out=src.t, row_stride=src.stride, lead=_lib.MM_LEAD)
