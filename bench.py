@@ -512,7 +512,7 @@ def bench_batch(rt, args, *, chain, mixed, steps, warmup, main, envelope=False):
 
     # ---- end-to-end through the host-buffer C-ABI call (pinned host memory, copies inside the timing) ----
     e2e = None
-    if main:
+    if main and args.e2e_tracks > 0:      # --e2e-tracks 0: device-resident numbers only (kernel experiments)
         e_tracks = min(tracks, args.e2e_tracks)
         frames = e_tracks * n * 2
         # pinned host buffers in the reference's own layout: float32 (n, 2) interleaved per track

@@ -293,3 +293,26 @@ def test_deesser_long_release_tails_against_oracle(P):
     e = _err(out, ref)
     print(f"[parity] deesser bursts + tails: {e:.3e}")
     assert e <= TIGHT and _err(ref, x) > 1e-2
+
+
+def test_host_copies_of_every_size_round_trip(P):
+    """mm_ctx_copy_in / mm_ctx_copy_out (Engine.upload / download / to_host): pageable numpy buffers are staged through pinned
+    memory in 4 MB blocks by several threads -- sizes below one block, at block edges, odd, mono / stereo, and several tracks must
+    come back bit for bit; a stage result on such buffers equals the same stage on a contiguous copy."""
+    from mm_b200.engine import get_engine
+    eng = get_engine()
+    rng = np.random.default_rng(7)
+    for n, ch in ((1, 1), (17, 2), (1000, 1), ((1 << 20) - 1, 2), ((1 << 20) + 3, 1), (3 * (1 << 20) + 5, 2), (2_500_001, 2)):
+        xs = [rng.standard_normal((n, ch)).astype(np.float32) for _ in range(3 if n < 2_000_000 else 1)]
+        b = eng.upload(xs if ch == 2 else [x[:, 0] for x in xs], 44100)
+        back = eng.download(b)
+        assert back.shape == (len(xs), n, ch)
+        for t, x in enumerate(xs):
+            assert np.array_equal(back[t], x), (n, ch, t)
+    # a strided (non-contiguous) input takes the same route after one host-side gather
+    big = rng.standard_normal((300_000, 4)).astype(np.float32)
+    view = big[:, 1:3]
+    assert not view.flags["C_CONTIGUOUS"]
+    assert np.array_equal(eng.download(eng.upload([view], 48000))[0], view)
+    a = P.remove_dc_offset(view)
+    assert np.array_equal(a, P.remove_dc_offset(np.ascontiguousarray(view)))
