@@ -262,8 +262,23 @@ static int run_sweep(mm_ctx* c, const mm_geom* g, const Arranged& R, int nout, c
     return launch_sweep2<M, NF, NIN, DIR, EPI, NAUX, NF32>(c, &A, halo_tiles(R.plans, NF), name, g->tracks * g->channels);
 }
 
+// `_safe_filtfilt` (pipeline.py:36-52): scipy's filtfilt refuses an input of <= padlen samples (ValueError) and the reference then
+// returns the CAUSAL lfilter(b, a, x) from a zero state.  Here a zero-phase pair is a forward sweep followed by a backward sweep
+// with the same pad; for such an input the forward sweep runs without extension and start state (pad 0: plain lfilter) and the
+// backward sweep runs IDENTITY sections (y = x) under the same epilogue -- no extra kernels.
+static bool degrades_to_lfilter(const mm_geom* g, int pad) { return pad > 0 && g->n <= pad; }
+static const FilterPlan* identity_plan(mm_ctx* c, int m) {
+    Ba ba;
+    memset(&ba, 0, sizeof(ba));
+    ba.m = m;
+    ba.b[0] = 1.0;
+    ba.a[0] = 1.0;
+    return get_plan_mode(c, ba, kDf2tF64);
+}
+
 int sweep_fwd(mm_ctx* c, const mm_geom* g, int nf, int nin, const FilterPlan* const* plans, const float* const* in,
               float* const* out, const Pro& pro, int pad) {
+    if (degrades_to_lfilter(g, pad)) pad = 0;
     Epi epi;
     const int m = plans[0]->ba.m;
     for (int f = 0; f < nf; ++f)
@@ -290,6 +305,14 @@ int sweep_fwd(mm_ctx* c, const mm_geom* g, int nf, int nin, const FilterPlan* co
 
 int sweep_bwd(mm_ctx* c, const mm_geom* g, int nf, const FilterPlan* const* plans, const float* const* in,
               float* const* out, int nout, const Epi& epi, int pad) {
+    const FilterPlan* ident[4];
+    if (degrades_to_lfilter(g, pad) && nf <= 4) {
+        const FilterPlan* id = identity_plan(c, plans[0]->ba.m);
+        if (!id) return 1;
+        for (int f = 0; f < nf; ++f) ident[f] = id;
+        plans = ident;
+        pad = 0;
+    }
     const int m = plans[0]->ba.m;
     const int naux = (epi.mode == EPI_STORE) ? 0 : ((epi.aux1 != nullptr) ? 2 : 1);
     if (epi.mode != EPI_STORE && epi.aux0 == nullptr) { set_error("backward sweep epilogue needs its x-domain stream"); return 1; }
@@ -347,15 +370,6 @@ int check_geom(const mm_geom* g) {
         return 1;
     }
     if (g->stride < mm_row_stride(g->n) || (g->stride & 3)) { set_error("stride must be >= mm_row_stride(n) and a multiple of 4"); return 1; }
-    return 0;
-}
-
-static int need_len(const mm_geom* g, int pad, const char* what) {
-    if (g->n <= pad) {
-        set_error("%s: %lld frames is not longer than scipy filtfilt's padlen %d (the reference would degrade to lfilter; use mm_dev_iir)",
-                  what, (long long)g->n, pad);
-        return 1;
-    }
     return 0;
 }
 
@@ -569,7 +583,6 @@ int st_target_curve(mm_ctx* c, const mm_geom* g, const float* in, float* out, co
     const FilterPlan* pres = plan_butter(c, 1, kBand, fp * 0.7, fp * 1.3, PREC_F32);   // enter through weights of 0.04 / 0.03
     const FilterPlan* mud = plan_butter(c, 1, kBand, fm * 0.7, fm * 1.3, PREC_F32);
     if (!hp || !lp || !pres || !mud) return 1;
-    MM_TRY(need_len(g, 9, "apply_target_curve"));
     Bufs B;
     MM_TRY(get_bufs(c, g, &B));
     const double gp = std::pow(10.0, 0.35 / 20.0), gm = std::pow(10.0, -0.25 / 20.0);
@@ -631,7 +644,6 @@ int st_dynamics(mm_ctx* c, const mm_geom* g, const float* in, float* out, double
     const FilterPlan* lp3 = plan_butter(c, 2, kLow, f[2], 0);
     const FilterPlan* hp3 = plan_butter(c, 2, kHigh, f[2], 0);
     if (!lp1 || !hp1 || !lp2 || !hp2 || !lp3 || !hp3) return 1;
-    MM_TRY(need_len(g, 9, "apply_dynamics"));
     Bufs B;
     MM_TRY(get_bufs(c, g, &B));
     Pro none;
@@ -692,7 +704,6 @@ int st_split_bands(mm_ctx* c, const mm_geom* g, const float* in, const double* c
     const FilterPlan* lp3 = plan_butter(c, 2, kLow, f[2], 0);
     const FilterPlan* hp3 = plan_butter(c, 2, kHigh, f[2], 0);
     if (!lp1 || !hp1 || !lp2 || !hp2 || !lp3 || !hp3) return 1;
-    MM_TRY(need_len(g, 9, "_split_bands"));
     Bufs B;
     MM_TRY(get_bufs(c, g, &B));
     Pro none;
@@ -820,7 +831,6 @@ int st_final_balance(mm_ctx* c, const mm_geom* g, const float* in, float* out, c
     const FilterPlan* plo = plan_butter(c, 2, kLow, std::min(180.0 / nyq, 0.99), 0, PREC_F32);
     const FilterPlan* p8 = plan_butter(c, 1, kBand, f8 * 0.8, f8 * 1.2, PREC_F32);
     if (!p3 || !p16 || !plo || !p8) return 1;
-    MM_TRY(need_len(g, 9, "apply_final_spectral_balance"));
     Bufs B;
     MM_TRY(get_bufs(c, g, &B));
     const FilterPlan* p[4] = {p3, p16, plo, p8};
@@ -848,7 +858,6 @@ int st_final_balance(mm_ctx* c, const mm_geom* g, const float* in, float* out, c
 // (pipeline.py:1427-1431), the exciter's high-pass (:1303-1315), or plain filtfilt (w_x = 0, w = 1)
 int st_filtfilt_combine(mm_ctx* c, const mm_geom* g, const FilterPlan* plan, const float* in, float* out, const Epi& epi_in,
                         const Pro& pro) {
-    MM_TRY(need_len(g, plan->pad, "zero-phase section"));
     Bufs B;
     MM_TRY(get_bufs(c, g, &B));
     const FilterPlan* p[1] = {plan};

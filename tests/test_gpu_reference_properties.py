@@ -224,7 +224,11 @@ def test_error_conventions_at_the_boundary(P, stereo):
                 _lib.Geom(b.n, b.stride, 0, 2, SR, 0)):
         rc = eng.lib.mm_dev_remove_dc_offset(eng.ctx, C.byref(bad), b.ptr, b.ptr)
         assert rc != 0 and _lib.last_error()
-    tiny = eng.upload([stereo[:8]], SR)                  # shorter than filtfilt's padlen: the reference would degrade to lfilter
-    g = tiny.geom
-    assert eng.lib.mm_dev_apply_target_curve(eng.ctx, C.byref(g), tiny.ptr, tiny.ptr, 0) != 0 and "padlen" in _lib.last_error()
+    tiny = eng.upload([stereo[:8]], SR)                  # shorter than filtfilt's padlen: degrades to lfilter like the reference
+    g = tiny.geom                                        # (values: test_inputs_not_longer_than_padlen_degrade_to_lfilter)
+    tout = eng.like(tiny)
+    assert eng.lib.mm_dev_apply_target_curve(eng.ctx, C.byref(g), tiny.ptr, tout.ptr, 0) == 0
+    # the de-esser on such an input: the reference's own np.convolve smoothing raises (67-tap box against 8 samples); refused by name
+    assert eng.lib.mm_dev_apply_deesser(eng.ctx, C.byref(g), tiny.ptr, tout.ptr, -6.0, 3.0, 5000.0, 9000.0, 4.0, 85.0) != 0
+    assert "padlen" in _lib.last_error()
     assert eng.lib.mm_dev_master(eng.ctx, C.byref(g), 7, None, tiny.ptr, tiny.ptr, None, None, 0, None, 0) != 0

@@ -316,3 +316,29 @@ def test_host_copies_of_every_size_round_trip(P):
     assert np.array_equal(eng.download(eng.upload([view], 48000))[0], view)
     a = P.remove_dc_offset(view)
     assert np.array_equal(a, P.remove_dc_offset(np.ascontiguousarray(view)))
+
+
+@pytest.mark.parametrize("n", [3, 9, 10, 15, 16])
+def test_inputs_not_longer_than_padlen_degrade_to_lfilter(P, n):
+    """`_safe_filtfilt` (pipeline.py:36-52): scipy's filtfilt raises for an input of <= padlen (9 / 15) samples and the reference
+    returns the causal lfilter instead.  The sweeps do the same (forward sweep without extension and start state, identity
+    backward sweep under the same epilogue) -- every stage the reference itself completes on such an input must match the
+    oracle (which equals the reference bit for bit here), for mono and stereo."""
+    from oracle import chain as oc
+    rng = np.random.default_rng(100 + n)
+    sr = 44100
+    for ch in (2, 1):
+        x = (0.3 * rng.standard_normal((n, ch))).astype(np.float32)
+        x = x if ch == 2 else x[:, 0]
+        cases = [
+            ("target_curve", P.apply_target_curve(x, sr), oc.apply_target_curve(x, sr)),
+            ("dynamics", P.apply_dynamics(x, sr), oc.apply_dynamics(x, sr)),
+            ("final_balance", P.apply_final_spectral_balance(x, sr), oc.apply_final_spectral_balance(x, sr)),
+            ("style_eq", P.apply_style_eq(x, sr, "edm"), oc.apply_style_eq(x, sr, "edm")),
+            ("exciter", P.apply_harmonic_exciter(x, sr, 1.2), oc.apply_harmonic_exciter(x, sr, 1.2)),
+            ("rumble", P.apply_rumble_filter(x, sr, 80.0), oc.zero_phase(*oc.sg.butter(2, 80.0 / (sr / 2), btype="high"),
+                                                                          x.astype(np.float64).T).T.astype(np.float32)),
+        ]
+        for name, got, want in cases:
+            assert got.shape == want.shape and got.dtype == np.float32, (name, n, ch, got.shape, want.shape)
+            assert float(np.max(np.abs(got.astype(np.float64) - want.astype(np.float64)))) <= 2e-6, (name, n, ch)
