@@ -12,6 +12,14 @@ constexpr int kT = 128;                  // threads per tile
 constexpr int kNW = kT / 32;             // warps per tile
 constexpr int kL = kS * kT;              // samples per tile (4096)
 constexpr int kLead = 32;                // == MM_LEAD: float offset of sample 0 inside a row
+// Backward sweeps count their tiles down from `qend`, one past the last position of tile 0.  Rounding qend up to a whole 128-byte
+// line (32 floats) makes every backward tile origin line aligned -- bulk tensor loads and the coalesced stores then move whole
+// lines (with the minimal rounding, to 4 floats, a tile's 128-byte rows each straddled two lines); tile 0 just starts with up to
+// 31 dead samples instead of up to 3 (dead < kS either way).
+#ifndef MM_BWD_ALIGN
+#define MM_BWD_ALIGN 32
+#endif
+__host__ __device__ inline long long bwd_qend(long long q_last) { return (q_last + MM_BWD_ALIGN) & ~(long long)(MM_BWD_ALIGN - 1); }
 
 // Offsets (in doubles) inside a per-filter device table, see design.h ScanTables.
 template <int M> struct Tab {

@@ -22,7 +22,7 @@ namespace mm {
 static inline int tiles_fwd(long long n, int pad) { return (int)((kLead + n + pad - 1 + kWT) / kWT); }
 static inline int tiles_bwd(long long n, int pad) {
     const long long q_last = kLead + n + pad - 1, q_first = kLead - pad;
-    const long long qend = (q_last + 4) & ~3LL;
+    const long long qend = bwd_qend(q_last);
     return (int)((qend - q_first + kWT - 1) / kWT);
 }
 
@@ -123,7 +123,7 @@ static int launch_sweep2(mm_ctx* c, SweepArgs<M, NF>* As, int whalo, const char*
     PP.tma_row_lines = A.stride / 32;
     if (tma_policy() && (A.stride % 32) == 0 && batch_rows > 0) {
         const long long q_last = kLead + A.n + A.pad - 1;
-        const long long qend = (q_last + 4) & ~3LL;
+        const long long qend = bwd_qend(q_last);
         const long long shift = DIR > 0 ? 0 : (qend % 32);
         const long long lines = ((long long)batch_rows * A.stride - shift) / 32;
         bool ok = true;

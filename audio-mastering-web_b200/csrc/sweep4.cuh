@@ -221,7 +221,7 @@ __global__ void __launch_bounds__(Sweep2Cfg<M, NF, NIN, DIR, EPI, NAUX, ST>::kTh
 
     const long long q_first = kLead - P.pad;
     const long long q_last = kLead + P.n + P.pad - 1;
-    const long long qend = (q_last + 4) & ~3LL;             // BWD: one past the last tile-0 position
+    const long long qend = bwd_qend(q_last);                // BWD: one past the last tile-0 position (line aligned)
     const int dead0 = (DIR > 0) ? (int)q_first : (int)(qend - 1 - q_last);
     // store range of this sweep (inclusive)
     const long long st_lo = (DIR > 0) ? q_first : (long long)kLead;
