@@ -425,3 +425,28 @@ def test_results_do_not_depend_on_the_lanes(P):
                         assert a == b, (lanes, chain, part)
     finally:
         eng.set_lanes(0)
+
+
+def test_stagewise_v1_path_is_device_resident_and_equal_to_per_stage_copies(P, monkeypatch):
+    """run_mastering_pipeline's stage-by-stage path (transient designer, denoise, reference match, tracing) runs the public stage
+    functions inside a resident scope: `_down` hands out placeholders registered against the device batch and `_up` resolves them
+    without a copy.  The result must equal the same stages with an upload and a download each (MM_RESIDENT=0) bit for bit --
+    stereo, mono and (n, 1) inputs, with a reference track at another rate -- and placeholders must not leak out of the scope."""
+    from mm_b200 import synth
+    sr = 44100
+    x = synth.numpy_track(700, sr, 3.0)
+    ref = synth.numpy_track(701, 48000, 2.5)
+    cases = [dict(transient_attack=1.3, transient_sustain=0.9), dict(denoise_strength=0.4),
+             dict(reference_audio=ref, reference_sr=48000, reference_strength=0.7, transient_attack=1.2)]
+    for inp in (x, np.ascontiguousarray(x[:, 0]), np.ascontiguousarray(x[:, :1])):
+        for kw in cases:
+            monkeypatch.setenv("MM_RESIDENT", "1")
+            a = P.run_mastering_pipeline(inp, sr, style="edm", target_lufs=-9.0, **kw)
+            monkeypatch.setenv("MM_RESIDENT", "0")
+            b = P.run_mastering_pipeline(inp, sr, style="edm", target_lufs=-9.0, **kw)
+            assert a.shape == b.shape and a.dtype == np.float32 and np.array_equal(a, b), (inp.shape, sorted(kw))
+            assert np.isfinite(a).all() and float(np.max(np.abs(a))) > 1e-3
+    monkeypatch.setenv("MM_RESIDENT", "1")
+    assert getattr(P._resident, "reg", None) is None            # no scope left open
+    y = P.apply_target_curve(x, sr)                                # outside a scope a stage returns real samples
+    assert float(np.max(np.abs(y))) > 1e-3 and P._resident_hit(y) is None

@@ -39,6 +39,7 @@ def main():
     res["master_batch_v2_ms"] = med(lambda: P.master_batch([x], sr, ["standard"], chain="v2", eng=eng))
     res["master_batch_v2_int16_ms"] = med(lambda: P.master_batch([x], sr, ["standard"], chain="v2", eng=eng, want_int16=True))
     res["run_mastering_pipeline_v1_ms"] = med(lambda: P.run_mastering_pipeline(x, sr))
+    res["run_mastering_pipeline_v1_stagewise_ms"] = med(lambda: P.run_mastering_pipeline(x, sr, transient_attack=1.3), reps=3)
     res["apply_target_curve_ms"] = med(lambda: P.apply_target_curve(x, sr))
     res["measure_lufs_ms"] = med(lambda: P.measure_lufs(x, sr))
     print(json.dumps(res))
