@@ -122,6 +122,14 @@ def _materialize(a):
     return out[:, 0] if arr.ndim == 1 else out
 
 
+# additive, opt-in for an integrator who strings stage functions together on one track (the v2 job function calls up to ten PRO
+# stages between the chain and the export, routers/mastering.py:443-609): `with resident_scope(): ...; out = materialize(out)`.
+# Inside the scope every array a stage returns is a placeholder -- it must only be passed to other functions of this module (or
+# to `materialize`), never read on the host.
+resident_scope = _ResidentScope
+materialize = _materialize
+
+
 def _up(audio, sr, eng: Optional[Engine] = None, squeeze: bool = True):
     eng = eng or get_engine()
     a = np.asarray(audio)
