@@ -70,8 +70,17 @@ __device__ __forceinline__ float bc_step(float e, float a, float cat, float crl)
 // juce::dsp::Compressor::processSample: the VCA gain of one envelope value, (e / thr)^(1/ratio - 1) above the threshold.
 // MUFU.LG2 / MUFU.EX2 (2^-22 absolute on the logarithm, 2 ulp on the power): the gain is good to ~3e-7 relative, far inside
 // what an unpinned restatement of std::pow can claim, and an order of magnitude cheaper than powf; branch free.
+// The .ftz forms are single MUFU instructions; without them the compiler wraps each in denormal-range scaling (several FSETP /
+// FMUL / FSEL per call).  The arguments never come near that range here: max(e, thr) / thr is in [1, ~1e3], the exponent in
+// [-10, 0] -- so the values are bit for bit those of __log2f / exp2f.
+__device__ __forceinline__ float bc_lg2(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float bc_ex2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float bc_gain(float e, float thr, float thr_inv, float pw) {
+#ifdef MM_BC_LIBM_POW
     const float g = exp2f(__fmul_rn(pw, __log2f(__fmul_rn(fmaxf(e, thr), thr_inv))));
+#else
+    const float g = bc_ex2(__fmul_rn(pw, bc_lg2(__fmul_rn(fmaxf(e, thr), thr_inv))));
+#endif
     return e < thr ? 1.f : g;
 }
 
