@@ -550,6 +550,9 @@ static int staged_copy_out(mm_ctx* c, char* dst, const char* dev, size_t bytes) 
 }
 }  // namespace mm
 
+#ifndef MM_D2H_STREAMS_DEFAULT
+#define MM_D2H_STREAMS_DEFAULT 1
+#endif
 #define MM_API_BEGIN(ctx)                                   \
     if (!(ctx)) { mm::set_error("null context"); return 1; } \
     mm::DeviceGuard _guard((ctx)->device);                   \
@@ -614,6 +617,7 @@ void mm_ctx_destroy(mm_ctx* c) {
     if (c->pin_in_done) cudaEventDestroy(c->pin_in_done);
     if (c->h2d_stream) cudaStreamDestroy(c->h2d_stream);
     if (c->d2h_stream) cudaStreamDestroy(c->d2h_stream);
+    if (c->d2h_stream2) cudaStreamDestroy(c->d2h_stream2);
     if (c->own_stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -1308,6 +1312,10 @@ static int master_host_plan(mm_ctx* c, int chain, const std::vector<HostChunk>& 
     const size_t in_elem = pcm_in ? sizeof(int16_t) : sizeof(float);
     if (!c->h2d_stream) MM_CUDA(cudaStreamCreateWithFlags(&c->h2d_stream, cudaStreamNonBlocking));
     if (!c->d2h_stream) MM_CUDA(cudaStreamCreateWithFlags(&c->d2h_stream, cudaStreamNonBlocking));
+    // copy-out on one or two streams (two copies in flight keep the link's read side busier while the chain loads HBM)
+    static const int n_d2h = [] { const char* e = getenv("MM_D2H_STREAMS"); const int v = e ? atoi(e) : 0; return v == 2 ? 2 : (v == 1 ? 1 : MM_D2H_STREAMS_DEFAULT); }();
+    if (n_d2h > 1 && !c->d2h_stream2) MM_CUDA(cudaStreamCreateWithFlags(&c->d2h_stream2, cudaStreamNonBlocking));
+    auto d2h_of = [&](int k) { return (n_d2h > 1 && (k & 1)) ? c->d2h_stream2 : c->d2h_stream; };
     bool any_noise = false, any_f32 = false, any_pcm = false;
     for (const HostTrack& t : trk) { any_noise |= t.noise != nullptr; any_f32 |= t.out_f32 != nullptr; any_pcm |= t.out_pcm != nullptr; }
     size_t cframes = 0, pfloats = 0;                               // staging sizes: the largest chunk
@@ -1359,20 +1367,25 @@ static int master_host_plan(mm_ctx* c, int chain, const std::vector<HostChunk>& 
         }
     }
 
+    // MM_HOST_TIMELINE=1: the pipeline's events carry timestamps and the call prints when each chunk's copy-in, layout, chain and
+    // copy-out ended (ms after the call's start) -- the tool that shows which stage a chunk waited for
+    static const bool timeline = [] { const char* e = getenv("MM_HOST_TIMELINE"); return e && atoi(e) != 0; }();
+    const unsigned ev_flags = timeline ? cudaEventDefault : cudaEventDisableTiming;
     std::vector<cudaEvent_t> ev_in(nchunks), ev_deint(nchunks), ev_done(nchunks), ev_out(nchunks);
     for (int k = 0; k < nchunks; ++k) {
-        MM_CUDA(cudaEventCreateWithFlags(&ev_in[k], cudaEventDisableTiming));
-        MM_CUDA(cudaEventCreateWithFlags(&ev_deint[k], cudaEventDisableTiming));
-        MM_CUDA(cudaEventCreateWithFlags(&ev_done[k], cudaEventDisableTiming));
-        MM_CUDA(cudaEventCreateWithFlags(&ev_out[k], cudaEventDisableTiming));
+        MM_CUDA(cudaEventCreateWithFlags(&ev_in[k], ev_flags));
+        MM_CUDA(cudaEventCreateWithFlags(&ev_deint[k], ev_flags));
+        MM_CUDA(cudaEventCreateWithFlags(&ev_done[k], ev_flags));
+        MM_CUDA(cudaEventCreateWithFlags(&ev_out[k], ev_flags));
     }
     int rc = 0;
     // everything queued earlier on the context stream (the caller's own work, buffer growth) precedes the copies
     cudaEvent_t ev_start;
-    MM_CUDA(cudaEventCreateWithFlags(&ev_start, cudaEventDisableTiming));
+    MM_CUDA(cudaEventCreateWithFlags(&ev_start, ev_flags));
     MM_CUDA(cudaEventRecord(ev_start, c->stream));
     MM_CUDA(cudaStreamWaitEvent(c->h2d_stream, ev_start, 0));
     MM_CUDA(cudaStreamWaitEvent(c->d2h_stream, ev_start, 0));
+    if (n_d2h > 1) MM_CUDA(cudaStreamWaitEvent(c->d2h_stream2, ev_start, 0));
     MM_TRY(lanes_fork(c, L));
     // one cudaMemcpyAsync per run of tracks whose host buffers lie back to back (the whole chunk, for the equal-shape entry points)
     auto copy_runs = [&](const HostChunk& ch, size_t elem, auto host_of, auto issue) -> int {
@@ -1440,28 +1453,29 @@ static int master_host_plan(mm_ctx* c, int chain, const std::vector<HostChunk>& 
                               st ? st + ch.t0 : nullptr, flags)) != 0) break;
         if (c_f32 && (rc = mm_dev_interleave(cl, &gk, pl, ol_of(k))) != 0) break;
         cudaEventRecord(ev_done[k], cl->stream);
-        cudaStreamWaitEvent(c->d2h_stream, ev_done[k], 0);
+        cudaStream_t d2h = d2h_of(k);
+        cudaStreamWaitEvent(d2h, ev_done[k], 0);
         if (stage_in) {
             // pageable outputs: the chunk lands in a pinned ring slot; the thread hands it to the caller's buffers one chunk later
             // (a device->pageable cudaMemcpyAsync would hold the thread until chunk k is done, with chunk k + 1's chain not yet queued)
             if (k >= 2 && (rc = drain_out(k - 2)) != 0) break;
             const size_t cnt = (size_t)ch.tn * ch.n * ch.channels;
-            if (c_pcm && cudaMemcpyAsync(hpout[k & 1], pcm_of(k), cnt * sizeof(int16_t), cudaMemcpyDeviceToHost, c->d2h_stream) != cudaSuccess) rc = 1;
-            if (c_f32 && cudaMemcpyAsync(hpout[k & 1] + out_f32_off, ol_of(k), cnt * sizeof(float), cudaMemcpyDeviceToHost, c->d2h_stream) != cudaSuccess) rc = 1;
+            if (c_pcm && cudaMemcpyAsync(hpout[k & 1], pcm_of(k), cnt * sizeof(int16_t), cudaMemcpyDeviceToHost, d2h) != cudaSuccess) rc = 1;
+            if (c_f32 && cudaMemcpyAsync(hpout[k & 1] + out_f32_off, ol_of(k), cnt * sizeof(float), cudaMemcpyDeviceToHost, d2h) != cudaSuccess) rc = 1;
             if (rc) { set_error("mm_master_host: copy failed"); break; }
         } else {
         if (c_f32) {
             const float* src = ol_of(k);
             rc = copy_runs(ch, sizeof(float), [](const HostTrack& t) { return (const void*)t.out_f32; }, [&](size_t off, const char* h, size_t bytes) {
-                return cudaMemcpyAsync(const_cast<char*>(h), src + off, bytes, cudaMemcpyDeviceToHost, c->d2h_stream); });
+                return cudaMemcpyAsync(const_cast<char*>(h), src + off, bytes, cudaMemcpyDeviceToHost, d2h); });
         }
         if (rc == 0 && c_pcm) {
             const int16_t* src = pcm_of(k);
             rc = copy_runs(ch, sizeof(int16_t), [](const HostTrack& t) { return (const void*)t.out_pcm; }, [&](size_t off, const char* h, size_t bytes) {
-                return cudaMemcpyAsync(const_cast<char*>(h), src + off, bytes, cudaMemcpyDeviceToHost, c->d2h_stream); });
+                return cudaMemcpyAsync(const_cast<char*>(h), src + off, bytes, cudaMemcpyDeviceToHost, d2h); });
         }
         }
-        cudaEventRecord(ev_out[k], c->d2h_stream);
+        cudaEventRecord(ev_out[k], d2h);
     }
     if (stage_in)
         for (int k = std::max(0, nchunks - 2); k < nchunks && rc == 0; ++k) rc = drain_out(k);
@@ -1476,6 +1490,16 @@ static int master_host_plan(mm_ctx* c, int chain, const std::vector<HostChunk>& 
         }
     }
     cudaError_t e1 = cudaStreamSynchronize(c->h2d_stream), e2 = cudaStreamSynchronize(c->stream), e3 = cudaStreamSynchronize(c->d2h_stream);
+    if (c->d2h_stream2 && e3 == cudaSuccess) e3 = cudaStreamSynchronize(c->d2h_stream2);
+    if (timeline && rc == 0 && e1 == cudaSuccess && e2 == cudaSuccess && e3 == cudaSuccess) {
+        fprintf(stderr, "[mm timeline] %d chunks on %d lanes (ms after the start: copy-in end | layout end | chain end | copy-out end)\n", nchunks, L);
+        for (int k = 0; k < nchunks; ++k) {
+            float a = 0, b = 0, d = 0, o = 0;
+            cudaEventElapsedTime(&a, ev_start, ev_in[k]); cudaEventElapsedTime(&b, ev_start, ev_deint[k]);
+            cudaEventElapsedTime(&d, ev_start, ev_done[k]); cudaEventElapsedTime(&o, ev_start, ev_out[k]);
+            fprintf(stderr, "[mm timeline] chunk %3d lane %d tracks %2d: %8.3f | %8.3f | %8.3f | %8.3f\n", k, k % L, chunks[k].tn, a, b, d, o);
+        }
+    }
     for (int k = 0; k < nchunks; ++k) { cudaEventDestroy(ev_in[k]); cudaEventDestroy(ev_deint[k]); cudaEventDestroy(ev_done[k]); cudaEventDestroy(ev_out[k]); }
     cudaEventDestroy(ev_start);
     if (rc == 0 && (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess)) {

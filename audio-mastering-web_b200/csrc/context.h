@@ -88,7 +88,7 @@ struct mm_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
-    cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
+    cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr, d2h_stream2 = nullptr;   // d2h_stream2: odd chunks' copy-out (MM_D2H_STREAMS=2)
     const int* row_map = nullptr;       // set around the per-style stages of a mixed batch: device list of the rows to visit
     int row_map_rows = 0;
     const int32_t* track_ids_host = nullptr;   // set for the duration of mm_master_host_ids: dither-stream index of every track of the call
