@@ -92,8 +92,9 @@ struct StyleSig {
 // tools/lanes_probe.py): one-track launches 169 k audio-s/s on one stream, 228 k on two, 251 k on four; four-track launches 243 k on
 // one stream, 288 k on two -- ABOVE the 64-track batch on one stream (279 k).  So a call is spread over LANES: sub-batches (device
 // entry) or chunks (host entries) go round-robin to child contexts with their own streams and workspaces, all at full grid size.
-// Results do not depend on the split: every track's arithmetic is its own (batch == single-track bit equality), the dither stream is
-// keyed by the track's index in the call.
+// Every track's arithmetic is its own and its dither stream is keyed by its index in the call; what a split can change is only where
+// a launch cuts its rows into segments (halo-rebuilt start states: 1e-18), i.e. the last float32 bits of a few samples of a
+// full-length track, exactly as between batches of different sizes (tools/lanes_soak.py; short tracks: bit for bit).
 static int lanes_wanted(const mm_ctx* c, int dflt) {
     if (c->lanes_cfg > 0) return c->lanes_cfg;
     if (const char* e = getenv("MM_LANES")) { const int v = atoi(e); if (v > 0) return std::min(v, 8); }

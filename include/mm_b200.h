@@ -345,7 +345,8 @@ int mm_ctx_copy_out(mm_ctx*, void* host_dst, const void* dev_src, int64_t bytes)
 /* Lanes: how many child contexts (own stream and workspace, created on demand, owned by this context) a call may spread its
  * work over -- mm_dev_master splits a batch into that many runs of tracks (automatic: 2), the host entries send consecutive chunks
  * to consecutive lanes (automatic: 4).  One chain is ~21 dependent kernels and a second stream's kernels fill the tails and launch
- * gaps of the first: 64 one-track chains 169 -> 251 k audio-s/s, the 64-track batch 279 -> ~290 k.  Results do not depend on it.
+ * gaps of the first: 64 one-track chains 169 -> 251 k audio-s/s, the 64-track batch 279 -> ~290 k.  Every lane count is bit-reproducible; between lane counts full-length tracks can
+ * differ in the last float32 bits (a launch's size decides where its rows are cut into segments), as between batches of different sizes.
  * 0 = automatic (or MM_LANES), 1 = everything on the context's own stream.  No reference counterpart (an execution policy). */
 int mm_ctx_set_lanes(mm_ctx*, int lanes);
 

@@ -398,7 +398,9 @@ def test_64_uploads_of_64_different_lengths_in_one_call(P):
 def test_results_do_not_depend_on_the_lanes(P):
     """mm_ctx_set_lanes: a call may spread its sub-batches (mm_dev_master) or chunks (host entries) over child contexts with their
     own streams and workspaces.  An execution policy only: samples, int16 (Philox stream keyed by the track's index in the call) and
-    stats are bit-identical for 1, 2, 3 and 5 lanes, for a mixed-preset batch and for a list of uploads of different shapes."""
+    stats are bit-identical for 1, 2, 3 and 5 lanes, for a mixed-preset batch and for a list of uploads of different shapes.
+    (Tracks this short segment alike whatever the launch size; at full length a launch's size decides where rows are cut into
+    segments and a few samples move in their last bits, as between batches of different sizes -- tools/lanes_soak.py.)"""
     from mm_b200 import synth, wavio
     from mm_b200.engine import get_engine
     eng = get_engine()
