@@ -132,7 +132,8 @@ static int launch_sweep2(mm_ctx* c, SweepArgs<M, NF>* As, int whalo, const char*
         // bulk stores pay for the four-output forward sweep (4.6 -> 3.9 ms per launch: 64 LDS + STG per lane and tile become four
         // instructions of one lane); with one or two outputs the issuing lane's wait before the next tile costs more than the
         // stores it saves (measured +2..3 %), so those keep their coalesced float4 stores
-        if (ok && EPI == EPI_STORE && NF >= 4 && tma_policy() >= 2) {
+        static const int store_min_nf = [] { const char* e = getenv("MM_TMA_STORE_MIN_NF"); const int v = e ? atoi(e) : 0; return v > 0 ? v : 4; }();
+        if (ok && EPI == EPI_STORE && NF >= store_min_nf && tma_policy() >= 2) {
             // (the halo start position is the same for loads and stores: both are tile origins)
             bool oko = true;
             for (int f = 0; f < NF && oko; ++f) oko = make_stream_map(&PP.tmap_out[f], A.out[f], shift, lines);
