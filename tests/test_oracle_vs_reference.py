@@ -119,3 +119,25 @@ def test_prebuilt_reference_copy_runs_sourceless_and_equals_the_oracle(tmp_path)
            "NUMBA_CACHE_DIR": str(tmp_path)}
     r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "prebuilt ok" in r.stdout, r.stderr[-2000:]
+
+
+@pytest.mark.parametrize("n", [3, 9, 10, 15, 16])
+def test_tiny_inputs_equal_reference(ref, n):
+    """Inputs of <= padlen samples: scipy's filtfilt raises and the reference's _safe_filtfilt returns lfilter (pipeline.py:36-52).
+    The oracle must follow the reference there bit for bit -- it is what the GPU's degrade path is tested against
+    (tests/test_gpu_stages.py::test_inputs_not_longer_than_padlen_degrade_to_lfilter)."""
+    rng = np.random.default_rng(100 + n)
+    sr = 44100
+    P = ref.pipeline
+    for ch in (2, 1):
+        x = (0.3 * rng.standard_normal((n, ch))).astype(np.float32)
+        x = x if ch == 2 else x[:, 0]
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            pairs = [(P.apply_target_curve(x.copy(), sr), oc.apply_target_curve(x.copy(), sr)),
+                     (P.apply_dynamics(x.copy(), sr), oc.apply_dynamics(x.copy(), sr)),
+                     (P.apply_final_spectral_balance(x.copy(), sr), oc.apply_final_spectral_balance(x.copy(), sr)),
+                     (P.apply_style_eq(x.copy(), sr, "edm"), oc.apply_style_eq(x.copy(), sr, "edm")),
+                     (P.apply_harmonic_exciter(x.copy(), sr, 1.2), oc.apply_harmonic_exciter(x.copy(), sr, 1.2))]
+        for i, (a, b) in enumerate(pairs):
+            assert a.shape == b.shape and np.array_equal(a, b), (n, ch, i)
